@@ -1,0 +1,95 @@
+"""
+oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.json by running the UNMODIFIED reference (compiled by
+oracle/Makefile into oracle/_ref/ref_driver) on the small variants of the named
+workloads.  Run in the development container (needs /root/reference to build
+oracle/_ref); the fixtures are committed so the GPU box never needs the
+reference sources.
+
+    python -m oracle.make_golden
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from paropt_b200 import configs  # noqa: E402
+
+DRIVER = os.path.join(HERE, "_ref", "ref_driver")
+
+
+def driver_args(cfg):
+    args = []
+    if cfg["kind"] == "rosenbrock":
+        args += ["problem=rosenbrock", "n=%d" % cfg["problem"]["n"]]
+    else:
+        args += ["problem=sepquad"]
+        for k, v in cfg["problem"].items():
+            key = "n" if k == "ntotal" else k
+            args.append("%s=%r" % (key, v))
+    for k, v in cfg["options"].items():
+        if isinstance(v, bool):
+            v = int(v)
+        args.append("opt:%s=%s" % (k, v))
+    return args
+
+
+def parse_log(path):
+    """Iteration rows of the reference's text log (IP.cpp:4777-4801)."""
+    rows = []
+    status = None
+    for line in open(path):
+        parts = line.split()
+        if line.startswith("ParOpt: Successfully converged to requested"):
+            status = "tolerance"
+        elif line.startswith("ParOpt: Successfully converged on relative"):
+            status = "rel_function"
+        elif line.startswith("ParOpt Warning: Current design point could not"):
+            status = "no_improvement"
+        if len(parts) >= 15 and parts[0].isdigit() and parts[1].isdigit():
+            rows.append({"iter": int(parts[0]), "alpha": parts[4], "alpha_x": parts[5],
+                         "alpha_z": parts[6], "info": " ".join(parts[15:])})
+    return rows, status
+
+
+def run_reference(cfg, nranks=1, extra_env=None):
+    env = dict(os.environ)
+    env["OPENBLAS_NUM_THREADS"] = "1"
+    env["PCU_SHIM_NP"] = str(nranks)
+    if extra_env:
+        env.update(extra_env)
+    with tempfile.TemporaryDirectory() as tmp:
+        hist = os.path.join(tmp, "hist.jsonl")
+        log = os.path.join(tmp, "paropt.out")
+        cmd = [DRIVER] + driver_args(cfg) + ["hist=" + hist, "log=" + log]
+        subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
+        recs = [json.loads(line) for line in open(hist)]
+        rows, status = parse_log(log)
+    its = [r for r in recs if "iter" in r]
+    final = [r for r in recs if "final" in r][0]
+    return {"config": cfg, "nranks": nranks, "history": its, "final": final,
+            "log": rows, "status": status}
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    jobs = [("C1", 1), ("C2", 1), ("C3", 1), ("C4", 1), ("C2", 2), ("C3", 2)]
+    for name, nranks in jobs:
+        cfg = configs.small(name)
+        data = run_reference(cfg, nranks)
+        data["generator"] = "oracle/make_golden.py (oracle/_ref/ref_driver, unmodified reference)"
+        fname = "%s_small%s.json" % (name, "" if nranks == 1 else "_np%d" % nranks)
+        with open(os.path.join(out_dir, fname), "w") as fp:
+            json.dump(data, fp, indent=0)
+        print(fname, "niter", data["final"]["niter"], data["status"])
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,7 @@ void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
   double xnorm = v.x->norm();
   double zlnorm = v.zl->norm(), zunorm = v.zu->norm();
   double zwnorm = v.zw->norm();
+  double gmax = ip->g->maxabs();
 
   if (rank == 0 && hist) {
     int ncon = ip->ncon;
@@ -162,11 +163,11 @@ void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
             "\"xnorm\": %.17g, \"zlsum\": %.17g, \"zusum\": %.17g, "
             "\"zlnorm\": %.17g, \"zunorm\": %.17g, \"zwsum\": %.17g, "
             "\"zwnorm\": %.17g, \"swsum\": %.17g, \"twsum\": %.17g, "
-            "\"zswsum\": %.17g, \"ztwsum\": %.17g, ",
+            "\"zswsum\": %.17g, \"ztwsum\": %.17g, \"gmax\": %.17g, ",
             iter, ip->fobj, ip->barrier_param, ip->rho_penalty_search, comp,
             max_prime, max_dual, max_infeas, res_norm, ip->neval, ip->ngeval,
             alpha, pnorm2, b0, qsize, sums[0], xnorm, sums[1], sums[2], zlnorm,
-            zunorm, sums[3], zwnorm, sums[4], sums[5], sums[6], sums[7]);
+            zunorm, sums[3], zwnorm, sums[4], sums[5], sums[6], sums[7], gmax);
     print_arr(hist, "c", ip->c, ncon);
     fprintf(hist, ", ");
     print_arr(hist, "z", v.z, ncon);
