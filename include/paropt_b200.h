@@ -1,0 +1,238 @@
+/*
+  paropt_b200.h -- C ABI of the B200-native interior-point hot path.
+
+  This is the drop-in boundary a ParOpt maintainer binds (INTEGRATION.md shows
+  the C++ adapter classes).  Every entry point cites the reference interface it
+  replaces; paths are relative to the reference's src/ directory and
+  IP.cpp = ParOptInteriorPoint.cpp, QN.cpp = ParOptQuasiNewton.cpp,
+  SM.cpp = ParOptSparseMat.cpp.
+
+  Conventions (kept from the reference):
+    * plain C types only; sizes are int (local sizes, as in ParOptVec.h:96);
+    * functions returning int return 0 on success; on failure a message is also
+      printed to stderr (reference style, IP.cpp:4534-4537);
+    * all calls are collective over the ranks of the context and must be made in
+      the same order on every rank (one host thread per rank / GPU);
+    * reductions return the GLOBAL value on every rank (ParOptVec.cpp:63-170);
+    * there is no CPU fallback: every call needs a CUDA device.
+*/
+#ifndef PAROPT_B200_H
+#define PAROPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcu_ctx pcu_ctx;
+typedef struct pcu_vec pcu_vec;
+typedef struct pcu_problem pcu_problem;
+typedef struct pcu_ip pcu_ip;
+
+/* ------------------------------------------------------------------ context
+   Replaces the MPI communicator every reference object carries
+   (ParOptProblem.h:48 MPI_Comm; IP.cpp:198-229 rank/size/ranges).           */
+
+/* Library version string. */
+const char *pcu_version(void);
+
+/* One context per process / GPU.  `device` is the CUDA ordinal. */
+pcu_ctx *pcu_ctx_create(int device);
+void pcu_ctx_destroy(pcu_ctx *ctx);
+
+/* Multi-GPU: rank 0 obtains a 128-byte NCCL unique id, the host side ships it
+   to the other ranks (torch.distributed broadcast), then every rank calls
+   pcu_ctx_init_comm.  Replaces MPI_Init / MPI_Comm_rank / MPI_Comm_size.      */
+int pcu_nccl_unique_id(unsigned char id128[128]);
+int pcu_ctx_init_comm(pcu_ctx *ctx, const unsigned char id128[128], int rank,
+                      int world_size);
+int pcu_ctx_rank(pcu_ctx *ctx);
+int pcu_ctx_size(pcu_ctx *ctx);
+int pcu_ctx_sync(pcu_ctx *ctx); /* cudaStreamSynchronize on the ctx stream */
+void *pcu_ctx_stream(pcu_ctx *ctx); /* cudaStream_t, for callers that enqueue */
+/* Number of kernels of THIS library launched on the context since creation.  */
+int64_t pcu_ctx_kernel_launches(pcu_ctx *ctx);
+/* Device-side timing helpers (cudaEvent on the ctx stream), milliseconds.     */
+int pcu_ctx_timer_start(pcu_ctx *ctx);
+int pcu_ctx_timer_stop(pcu_ctx *ctx, double *ms);
+
+/* ------------------------------------------------------------------ vectors
+   ParOptVec / ParOptBasicVec (ParOptVec.h:53-98, ParOptVec.cpp:15-217).      */
+pcu_vec *pcu_vec_create(pcu_ctx *ctx, int n);               /* ParOptVec.cpp:15 */
+void pcu_vec_destroy(pcu_vec *v);                           /* ParOptVec.cpp:25 */
+int pcu_vec_size(pcu_vec *v);                               /* getArray return  */
+int pcu_vec_set(pcu_vec *v, double alpha);                  /* :32  set         */
+int pcu_vec_zero(pcu_vec *v);                               /* :41  zeroEntries */
+int pcu_vec_copy(pcu_vec *dst, pcu_vec *src);               /* :50  copyValues  */
+int pcu_vec_norm(pcu_vec *v, double *out);                  /* :63  norm        */
+int pcu_vec_maxabs(pcu_vec *v, double *out);                /* :87  maxabs      */
+int pcu_vec_l1norm(pcu_vec *v, double *out);                /* :106 l1norm      */
+int pcu_vec_dot(pcu_vec *x, pcu_vec *y, double *out);       /* :124 dot         */
+int pcu_vec_mdot(pcu_vec *x, pcu_vec **vecs, int nvecs,
+                 double *out);                              /* :152 mdot        */
+int pcu_vec_scale(pcu_vec *v, double alpha);                /* :177 scale       */
+int pcu_vec_axpy(pcu_vec *y, double alpha, pcu_vec *x);     /* :194 axpy        */
+/* getArray (ParOptVec.cpp:211) is a host-pointer contract in the reference.
+   Here the storage is device memory: device_ptr gives the raw pointer for
+   GPU-resident callers, the two copies serve host callbacks.                  */
+double *pcu_vec_device_ptr(pcu_vec *v);
+int pcu_vec_to_host(pcu_vec *v, double *host, int n);   /* D2H, synchronous */
+int pcu_vec_from_host(pcu_vec *v, const double *host, int n); /* H2D, sync  */
+
+/* ------------------------------------------------------------------ problem
+   ParOptProblem (ParOptProblem.h:42-299).  The sparse "weighting" constraints
+   are declared as data so that Aw, Aw^T and Aw D^-1 Aw^T fuse into the kernels
+   (they replace the callbacks evalSparseCon / addSparseJacobian /
+   addSparseJacobianTranspose / addSparseInnerProduct, ParOptProblem.h:225-272,
+   and ParOptQuasiDefBlockMat, SM.cpp:11-229, with nwblock = 1):
+       cw_i(x) = wconst + coef0 * x[j0] + coef_rest * sum_{k=1}^{nw-1} x[j0+k],
+       j0 = wstart + i * wstride,  i < nwcon,  wstride >= nw.                  */
+typedef struct pcu_weighting {
+  int nwcon;      /* local number of weighting constraints (0 = none)          */
+  int wstart;     /* first variable of constraint 0                            */
+  int nw;         /* variables per constraint                                  */
+  int wstride;    /* distance between first variables of consecutive rows      */
+  double coef0;   /* coefficient of the first variable of a row                */
+  double coef_rest; /* coefficient of the other nw-1 variables                 */
+  double wconst;  /* constant term                                             */
+} pcu_weighting;
+
+/* Host/device callbacks: the exact callback set of ParOptProblem
+   (getVarsAndBounds :143, evalObjCon :157, evalObjConGradient :172).  Vectors
+   are pcu_vec handles; a host callback uses pcu_vec_to_host / _from_host, a
+   GPU-resident one uses pcu_vec_device_ptr and enqueues on pcu_ctx_stream.    */
+typedef struct pcu_problem_callbacks {
+  void *user;
+  int (*get_vars_and_bounds)(void *user, pcu_vec *x, pcu_vec *lb, pcu_vec *ub);
+  int (*eval_obj_con)(void *user, pcu_vec *x, double *fobj, double *cons);
+  int (*eval_obj_con_gradient)(void *user, pcu_vec *x, pcu_vec *g, pcu_vec **Ac);
+} pcu_problem_callbacks;
+
+/* ParOptProblem::setProblemSizes / setNumInequalities (ParOptProblem.cpp:47-76)
+   nvars, nwcon are LOCAL sizes; ncon is global.                               */
+pcu_problem *pcu_problem_create(pcu_ctx *ctx, int nvars, int ncon,
+                                int ninequality, int nwinequality,
+                                int use_lower, int use_upper,
+                                const pcu_weighting *weighting,
+                                const pcu_problem_callbacks *callbacks);
+void pcu_problem_destroy(pcu_problem *prob);
+
+/* Built-in GPU-resident synthetic problems (DESIGN.md "Synthetic problems");
+   they implement the same three callbacks with CUDA kernels.
+   Parameters of the separable / Householder convex QP family:                 */
+typedef struct pcu_sepquad_params {
+  int64_t ntotal;   /* GLOBAL number of design variables                       */
+  int ncon;         /* dense constraints                                       */
+  int nw;           /* variables per weighting block (0: none)                 */
+  uint64_t seed;
+  double lam_min, lam_max;
+  double b_lo, b_w;
+  double a_lo, a_w;
+  double beta_c, beta_n, beta_u;
+  double x0_lo[2], x0_w[2];
+  double lb[2], ub[2];
+  int householder;
+} pcu_sepquad_params;
+pcu_problem *pcu_problem_create_sepquad(pcu_ctx *ctx,
+                                        const pcu_sepquad_params *params);
+/* examples/rosenbrock/rosenbrock.cpp:9-199 (single rank). */
+pcu_problem *pcu_problem_create_rosenbrock(pcu_ctx *ctx, int nvars, int nwcon,
+                                           int nwstart, int nw, int nwskip);
+int pcu_problem_sizes(pcu_problem *prob, int *nvars, int *ncon, int *nwcon);
+/* Seconds spent inside the problem callbacks (device time, user code). */
+double pcu_problem_callback_ms(pcu_problem *prob);
+
+/* --------------------------------------------------- interior-point optimizer
+   ParOptInteriorPoint public API (ParOptInteriorPoint.h:128-217).             */
+pcu_ip *pcu_ip_create(pcu_problem *prob);                  /* IP.cpp:182       */
+void pcu_ip_destroy(pcu_ip *ip);
+/* ParOptOptions::setOption (ParOptOptions.h:35-37); names, defaults and ranges
+   as registered by addDefaultOptions (IP.cpp:536-727).  Unknown name -> 1.     */
+int pcu_ip_set_option_float(pcu_ip *ip, const char *name, double value);
+int pcu_ip_set_option_int(pcu_ip *ip, const char *name, int value);
+int pcu_ip_set_option_str(pcu_ip *ip, const char *name, const char *value);
+/* optimize (IP.cpp:4399).  Returns 0 on completion. */
+int pcu_ip_optimize(pcu_ip *ip);
+/* The same major loop, resumable: begin = everything before the loop
+   (IP.cpp:4399-4606), iterate = up to `max_iters` passes of the loop body
+   (IP.cpp:4607-5329); *converged is set when the convergence test fires.       */
+int pcu_ip_begin(pcu_ip *ip);
+int pcu_ip_iterate(pcu_ip *ip, int max_iters, int *converged);
+/* getOptimizedPoint / getOptimizedSlacks (IP.h:156-163): device vectors owned
+   by the optimizer plus host copies of the dense parts.                       */
+int pcu_ip_get_point(pcu_ip *ip, pcu_vec **x, pcu_vec **zw, pcu_vec **zl,
+                     pcu_vec **zu, pcu_vec **sw, pcu_vec **tw);
+int pcu_ip_get_dense(pcu_ip *ip, double *z, double *s, double *t, double *zs,
+                     double *zt, double *c);
+double pcu_ip_barrier_param(pcu_ip *ip);       /* getBarrierParameter IP.h:177 */
+int pcu_ip_complementarity(pcu_ip *ip, double *comp); /* getComplementarity    */
+int pcu_ip_counters(pcu_ip *ip, int *niter, int *neval, int *ngeval);
+/* 0 none, 1 "converged to requested tolerance", 2 relative function test,
+   3 "could not be improved" (the three messages at IP.cpp:4815-4830).         */
+int pcu_ip_status(pcu_ip *ip);
+
+/* Per-iteration history at the point of the reference's writeOutput hook
+   (IP.cpp:4620-4631): one record per major iteration, PCU_HIST_FIELDS doubles
+   followed by 6*ncon doubles (c, z, s, t, zs, zt).  Field order:
+   iter fobj mu rho comp max_prime max_dual max_infeas res_norm neval ngeval
+   alpha pnorm2 qn_b0 qn_size xsum xnorm zlsum zusum zwsum swsum twsum gmax
+   alpha_x alpha_z                                                            */
+#define PCU_HIST_FIELDS 25
+int pcu_ip_history_len(pcu_ip *ip);
+int pcu_ip_history_get(pcu_ip *ip, int k, double *out, int out_len);
+/* The `info` tag string of the log row printed at iteration k (IP.cpp:5272).  */
+const char *pcu_ip_history_info(pcu_ip *ip, int k);
+/* Device milliseconds of each completed major iteration and the share spent in
+   problem callbacks and in the KKT solve (setUpKKTDiagSystem + setUpKKTSystem
+   + first computeKKTStep).                                                    */
+int pcu_ip_iter_times(pcu_ip *ip, int k, double *total_ms, double *callback_ms,
+                      double *kkt_ms);
+
+/* ---------------------------------------------- hot-path functions, one by one
+   (kernel-level parity tests drive these; each acts on the optimizer's own
+   state exactly as the private method of the same name does).  `which` selects
+   a ParOptVars bundle: 0 variables, 1 residual, 2 update, 3 refine
+   (ParOptInteriorPoint.h:413-416).                                            */
+enum { PCU_VARS = 0, PCU_RESIDUAL = 1, PCU_UPDATE = 2, PCU_REFINE = 3 };
+/* component ids for pcu_ip_vars_vec */
+enum { PCU_X = 0, PCU_ZL, PCU_ZU, PCU_ZW, PCU_SW, PCU_TW, PCU_ZSW, PCU_ZTW };
+pcu_vec *pcu_ip_vars_vec(pcu_ip *ip, int which, int component);
+/* dense parts: 5*ncon doubles in the order z, s, t, zs, zt */
+int pcu_ip_vars_dense_get(pcu_ip *ip, int which, double *out5c);
+int pcu_ip_vars_dense_set(pcu_ip *ip, int which, const double *in5c);
+/* other state vectors: 0 lb, 1 ub, 2 g, 3 Dinv, 4 Cw(factor), 100+j Ac[j]      */
+pcu_vec *pcu_ip_state_vec(pcu_ip *ip, int id);
+int pcu_ip_set_obj_con(pcu_ip *ip, double fobj, const double *c);
+int pcu_ip_set_barrier(pcu_ip *ip, double mu, double rho);
+/* Loads the quasi-Newton memory from host arrays (S, Y: msub vectors of n) by
+   replaying ParOptLBFGS/LSR1::update (QN.cpp:162 / :636) on the device.       */
+int pcu_ip_qn_update(pcu_ip *ip, pcu_vec *s, pcu_vec *y, int *update_type);
+int pcu_ip_qn_reset(pcu_ip *ip);                                /* QN.cpp:132  */
+int pcu_ip_qn_mult(pcu_ip *ip, pcu_vec *x, pcu_vec *y);         /* QN.cpp:390  */
+int pcu_ip_qn_compact(pcu_ip *ip, double *b0, int *size, double *d0,
+                      double *M);                               /* QN.cpp:471  */
+
+int pcu_ip_kkt_res(pcu_ip *ip, int vars, double mu, int res);   /* IP.cpp:1337 */
+int pcu_ip_res_norm(pcu_ip *ip, double *max_prime, double *max_dual,
+                    double *max_infeas, double *res_norm);       /* IP.cpp:1588 */
+int pcu_ip_comp(pcu_ip *ip, double *comp);                       /* IP.cpp:2742 */
+int pcu_ip_setup_kkt_diag(pcu_ip *ip, int use_qn);               /* IP.cpp:1832 */
+int pcu_ip_setup_kkt(pcu_ip *ip, int use_qn);                    /* IP.cpp:2634 */
+int pcu_ip_kkt_step(pcu_ip *ip, int res, int step, int use_qn);  /* IP.cpp:2700 */
+int pcu_ip_add_kkt_res_step(pcu_ip *ip, int step, int res);      /* IP.cpp:1451 */
+int pcu_ip_max_step(pcu_ip *ip, double tau, int step, double *max_x,
+                    double *max_z);                              /* IP.cpp:2942 */
+int pcu_ip_comp_step(pcu_ip *ip, double alpha_x, double alpha_z, int step,
+                     double *comp);                              /* IP.cpp:2825 */
+int pcu_ip_merit_init_deriv(pcu_ip *ip, double max_x, double *merit,
+                            double *pmerit);                     /* IP.cpp:3652 */
+/* Gram blocks of the last setup: G (ncon x ncon, col-major, before LU) and
+   Ce (q x q, col-major, before LU) -- IP.cpp:1932-1961 and 2646-2661.         */
+int pcu_ip_get_gram(pcu_ip *ip, double *G, double *Ce, int *q);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PAROPT_B200_H */

@@ -1,0 +1,420 @@
+"""Host-side mirror of the reference's Python surface for the interior-point path
+(paropt/ParOpt.pyx: PVec :914, Problem :787, InteriorPoint :1189), bound to the
+C ABI in include/paropt_b200.h through ctypes.
+
+Everything numerical runs in libparopt_b200.so on the GPU; this module only
+marshals arguments.  There is no CPU fallback: constructing a Context without a
+CUDA device raises RuntimeError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+HIST_FIELDS = ("iter", "fobj", "mu", "rho", "comp", "max_prime", "max_dual",
+               "max_infeas", "res_norm", "neval", "ngeval", "alpha", "pnorm2",
+               "qn_b0", "qn_size", "xsum", "xnorm", "zlsum", "zusum", "zwsum",
+               "swsum", "twsum", "gmax", "alpha_x", "alpha_z")
+STATUS = {0: None, 1: "tolerance", 2: "rel_function", 3: "no_improvement"}
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("paropt_b200: %s failed (code %d)" % (what, rc))
+
+
+class Context:
+    """One per process / GPU (replaces the MPI communicator)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.h = self.lib.pcu_ctx_create(int(device))
+        if not self.h:
+            raise RuntimeError(
+                "paropt_b200: could not create a CUDA context on device %d; the "
+                "interior-point core has no CPU fallback" % device)
+        self.rank, self.size = 0, 1
+
+    def init_distributed(self):
+        """Bootstraps the NCCL communicator of this context from an initialised
+        torch.distributed process group (one process per GPU)."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            _check(self.lib.pcu_nccl_unique_id(raw), "ncclGetUniqueId")
+            buf = torch.tensor(list(raw.raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            tmp = buf.to(dev)
+            dist.broadcast(tmp, 0)
+            buf = tmp.cpu()
+        else:
+            dist.broadcast(buf, 0)
+        raw = bytes(buf.tolist())
+        _check(self.lib.pcu_ctx_init_comm(self.h, raw, rank, world), "ncclCommInitRank")
+        self.rank, self.size = rank, world
+
+    def sync(self):
+        _check(self.lib.pcu_ctx_sync(self.h), "sync")
+
+    def kernel_launches(self):
+        return int(self.lib.pcu_ctx_kernel_launches(self.h))
+
+    def timer_start(self):
+        _check(self.lib.pcu_ctx_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _check(self.lib.pcu_ctx_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def close(self):
+        if self.h:
+            self.lib.pcu_ctx_destroy(self.h)
+            self.h = None
+
+
+class PVec:
+    """ParOptVec / PVec (ParOptVec.h:53-70, ParOpt.pyx:914) in device memory."""
+
+    def __init__(self, ctx, n=None, handle=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.owns = handle is None
+        self.h = handle if handle is not None else self.lib.pcu_vec_create(ctx.h, int(n))
+        if not self.h:
+            raise RuntimeError("paropt_b200: vector allocation failed")
+
+    def __len__(self):
+        return int(self.lib.pcu_vec_size(self.h))
+
+    def set(self, alpha):
+        _check(self.lib.pcu_vec_set(self.h, float(alpha)), "set")
+
+    def zeroEntries(self):
+        _check(self.lib.pcu_vec_zero(self.h), "zeroEntries")
+
+    def copyValues(self, other):
+        _check(self.lib.pcu_vec_copy(self.h, other.h), "copyValues")
+
+    def norm(self):
+        out = C.c_double()
+        _check(self.lib.pcu_vec_norm(self.h, C.byref(out)), "norm")
+        return out.value
+
+    def maxabs(self):
+        out = C.c_double()
+        _check(self.lib.pcu_vec_maxabs(self.h, C.byref(out)), "maxabs")
+        return out.value
+
+    def l1norm(self):
+        out = C.c_double()
+        _check(self.lib.pcu_vec_l1norm(self.h, C.byref(out)), "l1norm")
+        return out.value
+
+    def dot(self, other):
+        out = C.c_double()
+        _check(self.lib.pcu_vec_dot(self.h, other.h, C.byref(out)), "dot")
+        return out.value
+
+    def mdot(self, vecs):
+        k = len(vecs)
+        arr = (C.c_void_p * k)(*[v.h for v in vecs])
+        out = np.zeros(k)
+        _check(self.lib.pcu_vec_mdot(self.h, arr, k, out.ctypes.data_as(_lib.c_double_p)), "mdot")
+        return out
+
+    def scale(self, alpha):
+        _check(self.lib.pcu_vec_scale(self.h, float(alpha)), "scale")
+
+    def axpy(self, alpha, x):
+        _check(self.lib.pcu_vec_axpy(self.h, float(alpha), x.h), "axpy")
+
+    def device_ptr(self):
+        return int(self.lib.pcu_vec_device_ptr(self.h) or 0)
+
+    def to_numpy(self):
+        out = np.empty(len(self))
+        if len(self):
+            _check(self.lib.pcu_vec_to_host(self.h, out.ctypes.data, len(self)), "to_host")
+        return out
+
+    def from_numpy(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        if arr.size != len(self):
+            raise ValueError("size mismatch")
+        if arr.size:
+            _check(self.lib.pcu_vec_from_host(self.h, arr.ctypes.data, arr.size), "from_host")
+
+    def free(self):
+        if self.owns and self.h:
+            self.lib.pcu_vec_destroy(self.h)
+            self.h = None
+
+
+def sepquad_params(**kw):
+    p = _lib.SepQuadParams()
+    defaults = dict(ntotal=1000, ncon=1, nw=0, seed=0, lam_min=1.0, lam_max=1e3,
+                    b_lo=0.0, b_w=1.0, a_lo=0.0, a_w=1.0, beta_c=0.0, beta_n=0.0,
+                    beta_u=1.0, x0_lo0=-2.0, x0_lo1=-2.0, x0_w0=1.0, x0_w1=1.0,
+                    lb0=-5.0, lb1=-5.0, ub0=5.0, ub1=5.0, householder=0)
+    for k in kw:
+        if k not in defaults:
+            raise ValueError("unknown sepquad parameter %s" % k)
+    defaults.update(kw)
+    d = defaults
+    for name in ("ntotal", "ncon", "nw", "seed", "lam_min", "lam_max", "b_lo", "b_w",
+                 "a_lo", "a_w", "beta_c", "beta_n", "beta_u", "householder"):
+        setattr(p, name, d[name])
+    p.x0_lo[0], p.x0_lo[1] = d["x0_lo0"], d["x0_lo1"]
+    p.x0_w[0], p.x0_w[1] = d["x0_w0"], d["x0_w1"]
+    p.lb[0], p.lb[1] = d["lb0"], d["lb1"]
+    p.ub[0], p.ub[1] = d["ub0"], d["ub1"]
+    return p
+
+
+class Problem:
+    """ParOpt.Problem (ParOpt.pyx:787-907): subclass and implement
+    getVarsAndBounds(x, lb, ub), evalObjCon(x) -> (fail, fobj, con) and
+    evalObjConGradient(x, g, A) -> fail on numpy arrays.  The arrays are host
+    mirrors of device vectors (the reference's getArray contract); each callback
+    costs one device->host and one host->device copy of its vectors."""
+
+    def __init__(self, ctx, nvars, ncon, ninequality=-1, nwinequality=-1,
+                 use_lower=True, use_upper=True, weighting=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.nvars, self.ncon = int(nvars), int(ncon)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        w = _lib.Weighting()
+        if weighting:
+            for k, v in weighting.items():
+                setattr(w, k, v)
+        self._w = w
+        self._cb = _lib.Callbacks()
+        self._cb.user = None
+        self._cb.get_vars_and_bounds = _lib.GET_VARS_CB(self._get_vars)
+        self._cb.eval_obj_con = _lib.EVAL_OBJ_CB(self._eval_obj)
+        self._cb.eval_obj_con_gradient = _lib.EVAL_GRAD_CB(self._eval_grad)
+        self.h = self.lib.pcu_problem_create(
+            ctx.h, self.nvars, self.ncon, int(ninequality), int(nwinequality),
+            int(use_lower), int(use_upper), C.byref(self._w), C.byref(self._cb))
+        if not self.h:
+            raise RuntimeError("paropt_b200: problem creation failed")
+
+    def _vec(self, handle):
+        return PVec(self.ctx, handle=handle)
+
+    def _get_vars(self, user, x, lb, ub):
+        try:
+            n = self.nvars
+            xa, la, ua = np.zeros(n), np.zeros(n), np.zeros(n)
+            self.getVarsAndBounds(xa, la, ua)
+            for h, a in ((x, xa), (lb, la), (ub, ua)):
+                self._vec(h).from_numpy(a)
+                self.h2d_bytes += a.nbytes
+            return 0
+        except Exception:  # mirrors ParOpt.pyx:528-531 (report, do not unwind C)
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _eval_obj(self, user, x, fobj, cons):
+        try:
+            xa = self._vec(x).to_numpy()
+            self.d2h_bytes += xa.nbytes
+            fail, f, con = self.evalObjCon(xa)
+            fobj[0] = float(f)
+            for i in range(self.ncon):
+                cons[i] = float(con[i])
+            return int(fail)
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _eval_grad(self, user, x, g, Ac):
+        try:
+            xa = self._vec(x).to_numpy()
+            self.d2h_bytes += xa.nbytes
+            ga = np.zeros(self.nvars)
+            A = [np.zeros(self.nvars) for _ in range(self.ncon)]
+            fail = self.evalObjConGradient(xa, ga, A)
+            self._vec(g).from_numpy(ga)
+            self.h2d_bytes += ga.nbytes
+            for i in range(self.ncon):
+                self._vec(Ac[i]).from_numpy(A[i])
+                self.h2d_bytes += A[i].nbytes
+            return int(fail or 0)
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_problem_destroy(self.h)
+            self.h = None
+
+
+class BuiltinProblem:
+    """GPU-resident synthetic problems (pcu_problem_create_sepquad / _rosenbrock)."""
+
+    def __init__(self, ctx, kind, **params):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        if kind == "sepquad":
+            self._p = sepquad_params(**params)
+            self.h = self.lib.pcu_problem_create_sepquad(ctx.h, C.byref(self._p))
+        elif kind == "rosenbrock":
+            n = int(params.get("n", 1000))
+            self.h = self.lib.pcu_problem_create_rosenbrock(ctx.h, n - 1, 5, 1, 5, 1)
+        else:
+            raise ValueError(kind)
+        if not self.h:
+            raise RuntimeError("paropt_b200: problem creation failed")
+        nv, nc, nw = C.c_int(), C.c_int(), C.c_int()
+        self.lib.pcu_problem_sizes(self.h, C.byref(nv), C.byref(nc), C.byref(nw))
+        self.nvars, self.ncon, self.nwcon = nv.value, nc.value, nw.value
+
+    def callback_ms(self):
+        return float(self.lib.pcu_problem_callback_ms(self.h))
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_problem_destroy(self.h)
+            self.h = None
+
+
+def problem_from_config(ctx, cfg):
+    if cfg["kind"] == "rosenbrock":
+        return BuiltinProblem(ctx, "rosenbrock", **cfg["problem"])
+    return BuiltinProblem(ctx, "sepquad", **cfg["problem"])
+
+
+class InteriorPoint:
+    """ParOpt.InteriorPoint (ParOpt.pyx:1189-1365 / ParOptInteriorPoint.h:128)."""
+
+    def __init__(self, problem, options=None):
+        self.prob = problem
+        self.ctx = problem.ctx
+        self.lib = self.ctx.lib
+        self.h = self.lib.pcu_ip_create(problem.h)
+        if not self.h:
+            raise RuntimeError("paropt_b200: interior-point creation failed")
+        self.ncon = problem.ncon
+        for k, v in (options or {}).items():
+            self.setOption(k, v)
+
+    def setOption(self, name, value):
+        key = name.encode()
+        if isinstance(value, bool):
+            rc = self.lib.pcu_ip_set_option_int(self.h, key, int(value))
+        elif isinstance(value, int):
+            rc = self.lib.pcu_ip_set_option_int(self.h, key, value)
+        elif isinstance(value, float):
+            rc = self.lib.pcu_ip_set_option_float(self.h, key, value)
+        else:
+            rc = self.lib.pcu_ip_set_option_str(self.h, key, str(value).encode())
+        if rc != 0:  # ParOpt.pyx:411-413 raises ValueError for unknown options
+            raise ValueError("unknown or out-of-range option %s=%r" % (name, value))
+
+    def optimize(self):
+        _check(self.lib.pcu_ip_optimize(self.h), "optimize")
+
+    def begin(self):
+        _check(self.lib.pcu_ip_begin(self.h), "begin")
+
+    def iterate(self, n=1):
+        conv = C.c_int()
+        _check(self.lib.pcu_ip_iterate(self.h, int(n), C.byref(conv)), "iterate")
+        return bool(conv.value)
+
+    def status(self):
+        return STATUS[int(self.lib.pcu_ip_status(self.h))]
+
+    def counters(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.lib.pcu_ip_counters(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def getBarrierParameter(self):
+        return float(self.lib.pcu_ip_barrier_param(self.h))
+
+    def getComplementarity(self):
+        out = C.c_double()
+        _check(self.lib.pcu_ip_complementarity(self.h, C.byref(out)), "comp")
+        return out.value
+
+    def getOptimizedPoint(self):
+        hs = [C.c_void_p() for _ in range(6)]
+        self.lib.pcu_ip_get_point(self.h, *[C.byref(h) for h in hs])
+        vecs = [PVec(self.ctx, handle=h.value) for h in hs]
+        dense = self.get_dense()
+        # reference order: x, z, zw, zl, zu
+        return vecs[0], dense["z"], vecs[1], vecs[2], vecs[3]
+
+    def get_dense(self):
+        c = self.ncon
+        arrs = {k: np.zeros(c) for k in ("z", "s", "t", "zs", "zt", "c")}
+        self.lib.pcu_ip_get_dense(self.h, *[arrs[k].ctypes.data_as(_lib.c_double_p)
+                                           for k in ("z", "s", "t", "zs", "zt", "c")])
+        return arrs
+
+    def history(self):
+        n = int(self.lib.pcu_ip_history_len(self.h))
+        c = self.ncon
+        buf = np.zeros(len(HIST_FIELDS) + 6 * c)
+        out = []
+        for k in range(n):
+            _check(self.lib.pcu_ip_history_get(self.h, k, buf.ctypes.data_as(_lib.c_double_p),
+                                               buf.size), "history")
+            rec = {name: float(buf[i]) for i, name in enumerate(HIST_FIELDS)}
+            for name in ("iter", "neval", "ngeval", "qn_size"):
+                rec[name] = int(rec[name])
+            off = len(HIST_FIELDS)
+            for j, name in enumerate(("c", "z", "s", "t", "zs", "zt")):
+                rec[name] = buf[off + j * c: off + (j + 1) * c].tolist()
+            rec["info"] = self.lib.pcu_ip_history_info(self.h, k).decode()
+            out.append(rec)
+        return out
+
+    def iter_times(self):
+        out = []
+        k = 0
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        while self.lib.pcu_ip_iter_times(self.h, k, C.byref(a), C.byref(b), C.byref(c)) == 0:
+            out.append((a.value, b.value, c.value))
+            k += 1
+        return out
+
+    # ---- function-level access (kernel parity tests) -------------------
+    def vars_vec(self, which, comp):
+        h = self.lib.pcu_ip_vars_vec(self.h, which, comp)
+        return PVec(self.ctx, handle=h)
+
+    def state_vec(self, ident):
+        return PVec(self.ctx, handle=self.lib.pcu_ip_state_vec(self.h, ident))
+
+    def dense_get(self, which):
+        buf = np.zeros(5 * self.ncon)
+        self.lib.pcu_ip_vars_dense_get(self.h, which, buf.ctypes.data_as(_lib.c_double_p))
+        c = self.ncon
+        return {k: buf[i * c:(i + 1) * c].copy() for i, k in enumerate(("z", "s", "t", "zs", "zt"))}
+
+    def dense_set(self, which, d):
+        buf = np.concatenate([np.asarray(d[k], dtype=np.float64) for k in ("z", "s", "t", "zs", "zt")]) \
+            if self.ncon else np.zeros(0)
+        buf = np.ascontiguousarray(buf)
+        self.lib.pcu_ip_vars_dense_set(self.h, which, buf.ctypes.data_as(_lib.c_double_p))
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_ip_destroy(self.h)
+            self.h = None

@@ -1,0 +1,320 @@
+// pcu_gram.cu -- weighted tall-skinny Gram  S = V^T P V  on the FP64 tensor cores.
+//
+// V = [A | Z] are the (c + q) column vectors (dense constraint gradients and the
+// compact quasi-Newton vectors), P = D0^-1 restricted to the design variables:
+//     P = Dinv - Dinv Aw^T Ew^-1 Aw Dinv          (SM.cpp:122-190, nwblock = 1)
+// One pass over the columns replaces the reference's c + q sequential
+// mat->apply / solveKKTDiagSystem calls and their c(c+1)/2 + q^2 separately
+// reduced dot products (IP.cpp:1932-1961 and 2646-2661).
+//
+// Tensor-core mapping: mma.sync.aligned.m8n8k4 .f64 (DMMA; tcgen05 has no fp64
+// kind).  A lane (gi = lane/4, kk = lane%4) loads, for every 8-column tile T, the
+// two rows r0 + 2kk, r0 + 2kk + 1 of column 8T + gi with one 128-bit access.
+// That register pair is simultaneously the B fragment (k = kk, n = gi) of tile
+// T and, multiplied by the row weight, the A fragment (m = gi, k = kk): the
+// reduction index may be permuted freely as long as A and B use the same
+// permutation, so two DMMAs (.x rows, .y rows) consume 8 rows.
+// The weighting-constraint correction  - sum_i Cw_i u_i u_i^T,
+// u_i = sum_{r in block i} coef_r Dinv_r V[r,:], is formed in registers with
+// two shuffles and issued as one more DMMA with a single non-zero k slot.
+#include <string.h>
+
+#include "pcu_ctx.cuh"
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, "
+      "{%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
+}
+
+template <int NTA, int NTB, bool DIAG>
+struct GramPairs {
+  static constexpr int N = DIAG ? (NTA * (NTA + 1)) / 2 : NTA * NTB;
+};
+
+// result layout: col-major mpad x mpad, tile (Ti, Tj) written at rows 8Ti..,
+// cols 8Tj.. ; DIAG computes tiles with Ti >= Tj of block A.
+template <int NTA, int NTB, bool DIAG>
+__global__ void __launch_bounds__(PCU_THREADS)
+    gram_kernel(const ColTable cols, const int colA0, const int colB0,
+                const int m, const double *__restrict__ Dinv,
+                const double *__restrict__ Cw, const WDesc w, const long long n,
+                double *__restrict__ partials, unsigned int *counter,
+                double *__restrict__ result, const int ld) {
+  constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gi = lane >> 2, kk = lane & 3;
+  const int nwarps_cta = blockDim.x >> 5;
+  const long long gwarp = (long long)blockIdx.x * nwarps_cta + warp;
+  const long long nwarps = (long long)gridDim.x * nwarps_cta;
+
+  double acc[NP][2];
+#pragma unroll
+  for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
+  double uA[NTA], uB[NTB];
+#pragma unroll
+  for (int t = 0; t < NTA; t++) uA[t] = 0.0;
+#pragma unroll
+  for (int t = 0; t < NTB; t++) uB[t] = 0.0;
+
+  const bool wmode = (w.mode == 1);
+  const long long ncon_elems = wmode ? (long long)w.nwcon * w.nw : 0;
+  const int L = wmode ? ((w.nw < 8 ? w.nw : 8) >> 1) : 1;  // lanes per block
+
+  const double *colA[NTA];
+  const double *colB[NTB];
+#pragma unroll
+  for (int t = 0; t < NTA; t++) {
+    const int c = colA0 + 8 * t + gi;
+    colA[t] = (c < m) ? cols.p[c] : nullptr;
+  }
+#pragma unroll
+  for (int t = 0; t < NTB; t++) {
+    const int c = colB0 + 8 * t + gi;
+    colB[t] = (c < m) ? cols.p[c] : nullptr;
+  }
+
+  const long long nchunks = (n + 63) / 64;
+  for (long long chunk = gwarp; chunk < nchunks; chunk += nwarps) {
+#pragma unroll 1
+    for (int step = 0; step < 8; step++) {
+      const long long r0 = chunk * 64 + step * 8;
+      if (r0 >= n) break;
+      const long long r = r0 + 2 * kk;
+      const bool ok0 = r < n, ok1 = (r + 1) < n;
+      double2 wv = make_double2(0.0, 0.0);
+      if (ok1) {
+        wv = Dinv ? *reinterpret_cast<const double2 *>(Dinv + r)
+                  : make_double2(1.0, 1.0);
+      } else if (ok0) {
+        wv.x = Dinv ? Dinv[r] : 1.0;
+      }
+      double2 fa[NTA], fb[NTB];
+#pragma unroll
+      for (int t = 0; t < NTB; t++) {
+        double2 f = make_double2(0.0, 0.0);
+        if (colB[t]) {
+          if (ok1) f = *reinterpret_cast<const double2 *>(colB[t] + r);
+          else if (ok0) f.x = colB[t][r];
+        }
+        fb[t] = f;
+      }
+#pragma unroll
+      for (int t = 0; t < NTA; t++) {
+        double2 f = make_double2(0.0, 0.0);
+        if (DIAG) {
+          f = fb[t < NTB ? t : 0];
+        } else if (colA[t]) {
+          if (ok1) f = *reinterpret_cast<const double2 *>(colA[t] + r);
+          else if (ok0) f.x = colA[t][r];
+        }
+        fa[t] = make_double2(f.x * wv.x, f.y * wv.y);
+      }
+      {
+        int p = 0;
+#pragma unroll
+        for (int ti = 0; ti < NTA; ti++) {
+#pragma unroll
+          for (int tj = 0; tj < NTB; tj++) {
+            if (!DIAG || tj <= ti) {
+              dmma884(acc[p], fa[ti].x, fb[tj].x);
+              dmma884(acc[p], fa[ti].y, fb[tj].y);
+              p++;
+            }
+          }
+        }
+      }
+      if (wmode) {
+        const bool in_con = r < ncon_elems;
+        const double c0 = ((r & (long long)(w.nw - 1)) == 0) ? w.coef0 : w.coef_rest;
+        const double c1 = w.coef_rest;
+#pragma unroll
+        for (int t = 0; t < NTA; t++)
+          uA[t] += in_con ? fma(fa[t].x, c0, fa[t].y * c1) : 0.0;
+        if (!DIAG) {
+#pragma unroll
+          for (int t = 0; t < NTB; t++)
+            uB[t] += in_con ? fma(fb[t].x * wv.x, c0, fb[t].y * wv.y * c1) : 0.0;
+        }
+        const bool block_end = (w.nw <= 8) || (((r0 + 8) & (long long)(w.nw - 1)) == 0);
+        if (block_end) {
+          for (int o = 1; o < L; o <<= 1) {
+#pragma unroll
+            for (int t = 0; t < NTA; t++) uA[t] += shfl_xor_d(uA[t], o);
+            if (!DIAG) {
+#pragma unroll
+              for (int t = 0; t < NTB; t++) uB[t] += shfl_xor_d(uB[t], o);
+            }
+          }
+          const bool lead = in_con && ((kk & (L - 1)) == 0);
+          const double cw = lead ? Cw[r / w.nw] : 0.0;
+          double ua[NTA], ub[NTB];
+#pragma unroll
+          for (int t = 0; t < NTA; t++) ua[t] = lead ? -cw * uA[t] : 0.0;
+#pragma unroll
+          for (int t = 0; t < NTB; t++)
+            ub[t] = lead ? (DIAG ? uA[t < NTA ? t : 0] : uB[t]) : 0.0;
+          int p = 0;
+#pragma unroll
+          for (int ti = 0; ti < NTA; ti++) {
+#pragma unroll
+            for (int tj = 0; tj < NTB; tj++) {
+              if (!DIAG || tj <= ti) {
+                dmma884(acc[p], ua[ti], ub[tj]);
+                p++;
+              }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < NTA; t++) uA[t] = 0.0;
+#pragma unroll
+          for (int t = 0; t < NTB; t++) uB[t] = 0.0;
+        }
+      }
+    }
+  }
+
+  // ---- CTA combine (pair by pair), then grid combine by the last block ----
+  __shared__ double sm[PCU_THREADS / 32][64];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    // element (row gi, col 2kk+e) of the 8x8 tile, stored col-major in sm
+    sm[warp][gi + 8 * (2 * kk)] = acc[p][0];
+    sm[warp][gi + 8 * (2 * kk + 1)] = acc[p][1];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      double v = 0.0;
+      for (int ww = 0; ww < nwarps_cta; ww++) v += sm[ww][threadIdx.x];
+      partials[((size_t)blockIdx.x * NP + p) * 64 + threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int idx = threadIdx.x; idx < NP * 64; idx += blockDim.x) {
+      double v = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; b++)
+        v += partials[(size_t)b * NP * 64 + idx];
+      // decode pair -> (ti, tj)
+      const int p = idx >> 6, e = idx & 63;
+      int ti = 0, tj = 0;
+      if (DIAG) {
+        int q = p;
+        while (q > ti) {
+          q -= ti + 1;
+          ti++;
+        }
+        tj = q;
+      } else {
+        ti = p / NTB;
+        tj = p % NTB;
+      }
+      const int row = colA0 + 8 * ti + (e & 7);
+      const int col = colB0 + 8 * tj + (e >> 3);
+      if (row < ld && col < ld) result[(size_t)row + (size_t)ld * col] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// Compatibility path for weighting patterns the shuffle layout cannot express
+// (WDesc.mode == 2, e.g. the 5-of-6 pattern of examples/rosenbrock): subtracts
+// sum_i Cw_i u_i u_i^T from the lower triangle.  One thread per (row, col) entry;
+// meant for small W.
+__global__ void gram_generic_correction(const ColTable cols, int m,
+                                        const double *__restrict__ Dinv,
+                                        const double *__restrict__ Cw,
+                                        const WDesc w, double *result, int ld) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * m) return;
+  const int i = idx % m, j = idx / m;
+  if (j > i) return;
+  double s = 0.0;
+  for (int ci = 0; ci < w.nwcon; ci++) {
+    const long long j0 = w.wstart + (long long)ci * w.wstride;
+    double ui = 0.0, uj = 0.0;
+    for (int k = 0; k < w.nw; k++) {
+      const double cf = (k == 0 ? w.coef0 : w.coef_rest);
+      const double d = Dinv ? Dinv[j0 + k] : 1.0;
+      ui = fma(cf * d, cols.p[i][j0 + k], ui);
+      uj = fma(cf * d, cols.p[j][j0 + k], uj);
+    }
+    s = fma(Cw[ci] * ui, uj, s);
+  }
+  result[(size_t)i + (size_t)ld * j] -= s;
+}
+
+template <int NTA, int NTB, bool DIAG>
+static int launch_gram(pcu_ctx *ctx, const ColTable &cols, int colA0, int colB0,
+                       int m, const double *Dinv, const double *Cw,
+                       const WDesc &w, long long n, double *result, int ld) {
+  constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
+  long long nchunks = (n + 63) / 64;
+  long long need = (nchunks + (PCU_THREADS / 32) - 1) / (PCU_THREADS / 32);
+  int grid = ctx->grid / 2;
+  if (need < grid) grid = (int)(need < 1 ? 1 : need);
+  if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
+  gram_kernel<NTA, NTB, DIAG><<<grid, PCU_THREADS, 0, ctx->stream>>>(
+      cols, colA0, colB0, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter,
+      result, ld);
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Enqueue S = V^T P V into ctx->d_big (col-major, leading dimension *ld_out =
+// 8*ceil(m/8); only entries with row >= col are meaningful).
+int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
+                     const double *Dinv, const double *Cw, const WDesc &wd,
+                     long long n, int *ld_out) {
+  const int nt = (m + 7) / 8;
+  const int ld = 8 * nt;
+  *ld_out = ld;
+  if (m == 0) return 0;
+  if (ctx->big_reserve((size_t)ld * ld + 64, 1)) return 1;
+  WDesc w = wd;
+  if (w.mode == 2 || w.nwcon == 0) {
+    w.mode = 0;  // the tensor-core pass computes V^T Dinv V only
+  }
+  double *R = ctx->d_big;
+  int rc = 0;
+  if (nt <= 5) {
+    switch (nt) {
+      case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
+      case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
+      case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
+      case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
+      default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
+    }
+  } else {
+    // column blocks of 40; block pairs (bi >= bj); ragged last block is masked
+    const int nb = (nt + 4) / 5;
+    for (int bi = 0; bi < nb && !rc; bi++) {
+      for (int bj = 0; bj <= bi && !rc; bj++) {
+        if (bi == bj)
+          rc = launch_gram<5, 5, true>(ctx, cols, 40 * bi, 40 * bi, m, Dinv, Cw, w, n, R, ld);
+        else
+          rc = launch_gram<5, 5, false>(ctx, cols, 40 * bi, 40 * bj, m, Dinv, Cw, w, n, R, ld);
+      }
+    }
+  }
+  if (rc) return rc;
+  if (wd.mode == 2 && wd.nwcon > 0) {
+    const int total = m * m;
+    gram_generic_correction<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
+        cols, m, Dinv, Cw, wd, R, ld);
+    ctx->launches++;
+    PCU_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}

@@ -1,0 +1,1326 @@
+// pcu_ip_solve.cu -- KKT set-up / solve, step statistics, starting point and the
+// major loop of the CUDA-resident interior-point core (second half of pcu_ip).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "pcu_ip.cuh"
+
+int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
+                     int ncols, long long n, int dst_off);
+int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
+                     const double *Dinv, const double *Cw, const WDesc &wd,
+                     long long n, int *ld_out);
+int pcu_lu_factor(int n, double *A, int *piv);
+void pcu_lu_solve(int n, const double *LU, const int *piv, double *b);
+
+template <class F>
+static int launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
+                       RedBuf rb) {
+  const int grid = pcu_grid_for(ctx, n);
+  tile_kernel<F><<<grid, PCU_THREADS, 0, ctx->stream>>>(f, n, w, rb);
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static const RedBuf NO_RED = {nullptr, nullptr, nullptr};
+
+// LS flags (IP.h:220-225)
+enum {
+  LS_SUCCESS = 1,
+  LS_FAILURE = 2,
+  LS_MIN_STEP = 4,
+  LS_MAX_ITERS = 8,
+  LS_NO_IMPROVEMENT = 16,
+  LS_SHORT_STEP = 32
+};
+enum { BS_MONOTONE = 0, BS_MEHROTRA = 1, BS_MPC = 2, BS_COMP_FRACTION = 3 };
+
+// ------------------------------------------------------- setUpKKTDiagSystem
+// IP.cpp:1832-1930 (diagonal + Ew factor; G follows in setUpKKTSystem)
+int pcu_ip::setUpKKTDiagSystem(Vars &vars, int use_qn, int identity) {
+  DiagF f;
+  f.v = vars.dv();
+  f.lb = lb->d;
+  f.ub = ub->d;
+  f.Dinv = Dinv->d;
+  f.Cw = Cw->d;
+  double b0 = 0.0;
+  if (qn && use_qn) b0 = qn->b0;
+  b0_used = b0;
+  f.b0sig = b0 + opt.qn_sigma;
+  f.identity = identity;
+  f.small_ = 1e-4;
+  f.k = kconst();
+  return launch_tile(ctx, f, nvars, wd, NO_RED);
+}
+
+// ----------------------------------------------------------- setUpKKTSystem
+// One weighted Gram pass S = [A|Z]^T D0^-1 [A|Z] gives
+//   G  = C0 + S_AA                                  (IP.cpp:1932-1969)
+//   Ce = S_ZZ - S_ZA G^-1 S_AZ - M / (d d^T)        (IP.cpp:2646-2664)
+// gdiag: diagonal added to G (s/zs + t/zt, or `small` for the least-squares
+// start); NULL means s/zs + t/zt of `vars`.
+int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag) {
+  const int q = (qn && use_qn) ? qn->size() : 0;
+  sq = q;
+  const int m = ncon + q;
+  ColTable V;
+  for (int j = 0; j < ncon; j++) V.p[j] = Ac[j]->d;
+  if (q > 0) qn->z_table(V, ncon);
+  int ld = 0;
+  if (m > 0) {
+    if (pcu_gram_enqueue(ctx, V, m, Dinv->d, Cw->d, wd, nvars, &ld)) return 1;
+    Sgram.assign((size_t)ld * ld, 0.0);
+    if (ctx->big_fetch((size_t)ld * ld, Sgram.data())) return 1;
+    for (int j = 0; j < m; j++)  // symmetrise from the lower triangle
+      for (int i = j + 1; i < m; i++)
+        Sgram[j + (size_t)ld * i] = Sgram[i + (size_t)ld * j];
+  }
+  sld = ld;
+  Graw.assign((size_t)ncon * ncon, 0.0);
+  for (int j = 0; j < ncon; j++)
+    for (int i = 0; i < ncon; i++) Graw[i + (size_t)ncon * j] = Sgram[i + (size_t)ld * j];
+  for (int i = 0; i < ncon; i++) {
+    Graw[i * (size_t)(ncon + 1)] +=
+        gdiag ? gdiag[i] : vars.s[i] / vars.zs[i] + vars.t[i] / vars.zt[i];
+  }
+  Gfac = Graw;
+  gpiv.assign(ncon > 0 ? ncon : 1, 0);
+  if (ncon > 0) pcu_lu_factor(ncon, Gfac.data(), gpiv.data());
+  Ceraw.clear();
+  Cefac.clear();
+  if (q > 0) {
+    Ceraw.assign((size_t)q * q, 0.0);
+    std::vector<double> col(ncon);
+    for (int i = 0; i < q; i++) {
+      // column i: Z^T P Z_i - S_ZA G^-1 (A^T P Z_i)
+      for (int j = 0; j < ncon; j++) col[j] = Sgram[j + (size_t)ld * (ncon + i)];
+      if (ncon > 0) pcu_lu_solve(ncon, Gfac.data(), gpiv.data(), col.data());
+      for (int k = 0; k < q; k++) {
+        double v = Sgram[(ncon + k) + (size_t)ld * (ncon + i)];
+        for (int j = 0; j < ncon; j++) v -= Sgram[(ncon + k) + (size_t)ld * j] * col[j];
+        Ceraw[k + (size_t)q * i] = v;
+      }
+    }
+    const std::vector<double> &M = qn->M, &d0 = qn->d0;
+    for (int j = 0; j < q; j++)
+      for (int i = 0; i < q; i++)
+        Ceraw[i + (size_t)q * j] -= M[i + (size_t)q * j] / (d0[i] * d0[j]);
+    Cefac = Ceraw;
+    cpiv.assign(q, 0);
+    pcu_lu_factor(q, Cefac.data(), cpiv.data());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------ computeKKTStep
+// IP.cpp:2700-2737 with both inner diagonal solves (IP.cpp:2074-2243 and
+// 2257-2369) merged: pass 1 -> reductions -> dense solves -> pass 2.
+// VTp (optional, ncon + qn->size() values): [A | Z]^T of the (accumulated) step.
+int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
+                           int accumulate, double *VTp) {
+  const int q = (qn && use_qn && !Cefac.empty()) ? std::min(sq, qn->size()) : 0;
+  const int m = ncon + q;
+  const IPConst k = kconst();
+  Pass1F f1;
+  f1.v = vars.dv();
+  f1.b = b.dv();
+  f1.lb = lb->d;
+  f1.ub = ub->d;
+  f1.Dinv = Dinv->d;
+  f1.Cw = Cw->d;
+  f1.d1 = d1->d;
+  f1.d2 = d2->d;
+  f1.t1 = t1->d;
+  f1.k = k;
+  if (launch_tile(ctx, f1, nvars, wd, NO_RED)) return 1;
+  ColTable V;
+  for (int j = 0; j < ncon; j++) V.p[j] = Ac[j]->d;
+  if (q > 0) qn->z_table(V, ncon);
+  std::vector<double> r(m > 0 ? m : 1, 0.0);
+  if (m > 0) {
+    if (pcu_mdot_enqueue(ctx, t1->d, V, m, nvars, 0)) return 1;
+    if (ctx->big_fetch(m, r.data())) return 1;
+  }
+  // dense solves (IP.cpp:2150-2170, 2716-2722, 2288-2306)
+  std::vector<double> yz1(ncon), pz(ncon), ps(ncon), pt(ncon), pzs(ncon), pzt(ncon);
+  for (int i = 0; i < ncon; i++) {
+    yz1[i] = (b.z[i] + (b.zs[i] + vars.s[i] * b.s[i]) / vars.zs[i] -
+              (b.zt[i] + vars.t[i] * b.t[i]) / vars.zt[i] - r[i]);
+  }
+  if (ncon > 0) pcu_lu_solve(ncon, Gfac.data(), gpiv.data(), yz1.data());
+  for (int i = 0; i < ncon; i++) {
+    pz[i] = yz1[i];
+    pzs[i] = yz1[i] - b.s[i];
+    pzt[i] = -b.t[i] - yz1[i];
+    ps[i] = (b.zs[i] - vars.s[i] * pzs[i]) / vars.zs[i];
+    pt[i] = (b.zt[i] - vars.t[i] * pzt[i]) / vars.zt[i];
+  }
+  Pass2F f2;
+  for (int i = 0; i < ncon; i++) f2.alpha.v[i] = yz1[i];
+  if (q > 0) {
+    const int ld = sld;
+    std::vector<double> w(q), yz2(ncon);
+    for (int kq = 0; kq < q; kq++) {  // Z^T yx = r_Z + S_ZA yz1
+      double v = r[ncon + kq];
+      for (int j = 0; j < ncon; j++) v += Sgram[(ncon + kq) + (size_t)ld * j] * yz1[j];
+      w[kq] = v;
+    }
+    pcu_lu_solve(q, Cefac.data(), cpiv.data(), w.data());
+    for (int j = 0; j < ncon; j++) {  // second solve: A^T P Z w = S_AZ w
+      double v = 0.0;
+      for (int kq = 0; kq < q; kq++) v += Sgram[j + (size_t)ld * (ncon + kq)] * w[kq];
+      yz2[j] = -v;
+    }
+    if (ncon > 0) pcu_lu_solve(ncon, Gfac.data(), gpiv.data(), yz2.data());
+    for (int i = 0; i < ncon; i++) {
+      const double yzs2 = yz2[i], yzt2 = -yz2[i];
+      const double ys2 = -(vars.s[i] * yzs2) / vars.zs[i];
+      const double yt2 = -(vars.t[i] * yzt2) / vars.zt[i];
+      pz[i] -= yz2[i];
+      pzs[i] -= yzs2;
+      pzt[i] -= yzt2;
+      ps[i] -= ys2;
+      pt[i] -= yt2;
+      f2.alpha.v[i] = pz[i];
+    }
+    for (int kq = 0; kq < q; kq++) f2.alpha.v[ncon + kq] = -w[kq];
+  }
+  for (int i = 0; i < ncon; i++) {
+    if (accumulate) {
+      y.z[i] += pz[i];
+      y.s[i] += ps[i];
+      y.t[i] += pt[i];
+      y.zs[i] += pzs[i];
+      y.zt[i] += pzt[i];
+    } else {
+      y.z[i] = pz[i];
+      y.s[i] = ps[i];
+      y.t[i] = pt[i];
+      y.zs[i] = pzs[i];
+      y.zt[i] = pzt[i];
+    }
+  }
+  f2.v = vars.dv();
+  f2.b = b.dv();
+  f2.y = y.dv();
+  f2.lb = lb->d;
+  f2.ub = ub->d;
+  f2.Dinv = Dinv->d;
+  f2.Cw = Cw->d;
+  f2.d1 = d1->d;
+  f2.d2 = d2->d;
+  f2.V = V;
+  f2.ncols = m;
+  f2.accumulate = accumulate;
+  f2.k = k;
+  if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
+  if (VTp) {
+    const int qa = qn ? qn->size() : 0;
+    ColTable Vall;
+    for (int j = 0; j < ncon; j++) Vall.p[j] = Ac[j]->d;
+    if (qa > 0) qn->z_table(Vall, ncon);
+    if (ncon + qa > 0) {
+      if (pcu_mdot_enqueue(ctx, y.v[PCU_X]->d, Vall, ncon + qa, nvars, 0)) return 1;
+      if (ctx->big_fetch(ncon + qa, VTp)) return 1;
+    }
+  }
+  return 0;
+}
+
+int pcu_ip::stepStats(Vars &vars, Vars &step, double tau, double *sums,
+                      double *mins) {
+  StatsF f;
+  f.v = vars.dv();
+  f.p = step.dv();
+  f.lb = lb->d;
+  f.ub = ub->d;
+  f.g = g->d;
+  f.tau = tau;
+  f.k = kconst();
+  RedBuf rb = ctx->redbuf(StatsF::NS, StatsF::NX, StatsF::NM);
+  if (launch_tile(ctx, f, nvars, wd, rb)) return 1;
+  double out[StatsF::NS + StatsF::NX + StatsF::NM];
+  if (ctx->fetch(out)) return 1;
+  memcpy(sums, out, sizeof(double) * StatsF::NS);
+  stats_pmax = out[StatsF::NS];
+  mins[0] = std::min(1.0, out[StatsF::NS + 1]);
+  mins[1] = std::min(1.0, out[StatsF::NS + 2]);
+  // dense slack / multiplier steps (IP.cpp:2986-3017)
+  for (int i = 0; i < ncon; i++) {
+    if (step.s[i] < 0.0) mins[0] = std::min(mins[0], -tau * vars.s[i] / step.s[i]);
+    if (step.t[i] < 0.0) mins[0] = std::min(mins[0], -tau * vars.t[i] / step.t[i]);
+    if (step.zs[i] < 0.0) mins[1] = std::min(mins[1], -tau * vars.zs[i] / step.zs[i]);
+    if (step.zt[i] < 0.0) mins[1] = std::min(mins[1], -tau * vars.zt[i] / step.zt[i]);
+  }
+  return 0;
+}
+
+// ---------------------------------------------- initLeastSquaresMultipliers
+// IP.cpp:5366-5534
+struct MaskBoundMultF {  // zl = 0 where lb <= -mbv, zu = 0 where ub >= mbv
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  const double *lb, *ub;
+  double *zl, *zu;
+  double mbv;
+  // affine start (IP.cpp:5629-5651): z = max(mn, |z + pz|) where the bound exists
+  const double *pzl, *pzu;
+  double mn;
+  int affine;
+  // least-squares right-hand side rx = -(g - zl + zu) (IP.cpp:5472-5475)
+  const double *g;
+  double *rx;
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
+                                    AccT &) const {}
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {
+    double l[W], u[W], a[W], b[W];
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(zl, i, a);
+    ldv<W>(zu, i, b);
+    if (affine) {
+      double pa[W], pb[W];
+      ldv<W>(pzl, i, pa);
+      ldv<W>(pzu, i, pb);
+#pragma unroll
+      for (int e = 0; e < W; e++) {
+        if (l[e] > -mbv) a[e] = fmax(mn, fabs(a[e] + pa[e]));
+        if (u[e] < mbv) b[e] = fmax(mn, fabs(b[e] + pb[e]));
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < W; e++) {
+      if (l[e] <= -mbv) a[e] = 0.0;
+      if (u[e] >= mbv) b[e] = 0.0;
+    }
+    stv<W>(zl, i, a);
+    stv<W>(zu, i, b);
+    if (rx) {
+      double gv[W], r[W];
+      ldv<W>(g, i, gv);
+#pragma unroll
+      for (int e = 0; e < W; e++) r[e] = -((gv[e] - a[e]) + b[e]);
+      stv<W>(rx, i, r);
+    }
+  }
+};
+
+struct SparseStartF {  // W-sized pieces of the starting-point strategies
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  DVars v, p;
+  double mn, gamma;
+  int nwineq;
+  int mode;  // 0: clip zw to +-10 gamma (IP.cpp:5520-5533); 1: affine (IP.cpp:5605-5627)
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
+                                    AccT &) const {}
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {
+#pragma unroll
+    for (int e = 0; e < W; e++) {
+      const long long ci = i + e;
+      if (mode == 0) {
+        const double gam = 10.0 * gamma;  // max(gamma_sw, gamma_tw) = gamma
+        const double zw = v.zw[ci];
+        if (zw < -gam || zw > gam) v.zw[ci] = 0.0;
+      } else {
+        v.zw[ci] = v.zw[ci] + p.zw[ci];
+        v.sw[ci] = fmax(mn, fabs(v.sw[ci] + p.sw[ci]));
+        v.tw[ci] = fmax(mn, fabs(v.tw[ci] + p.tw[ci]));
+        v.zsw[ci] = fmax(mn, fabs(v.zsw[ci] + p.zsw[ci]));
+        v.ztw[ci] = fmax(mn, fabs(v.ztw[ci] + p.ztw[ci]));
+      }
+    }
+  }
+};
+
+int pcu_ip::initLeastSquaresMultipliers() {
+  Vars &vars = variables, &res = residual;
+  const double mu0 = opt.init_barrier_param;
+  for (int i = 1; i < 8; i++)
+    if (pcu_vec_set(vars.v[i], mu0)) return 1;
+  for (int i = 0; i < ncon; i++)
+    vars.z[i] = vars.s[i] = vars.t[i] = vars.zs[i] = vars.zt[i] = mu0;
+  WDesc w0;
+  memset(&w0, 0, sizeof(w0));
+  // zero out-of-range bound multipliers and form rx = -(g - zl + zu)
+  MaskBoundMultF fm;
+  fm.lb = lb->d;
+  fm.ub = ub->d;
+  fm.zl = vars.v[PCU_ZL]->d;
+  fm.zu = vars.v[PCU_ZU]->d;
+  fm.mbv = opt.max_bound_value;
+  fm.affine = 0;
+  fm.pzl = fm.pzu = nullptr;
+  fm.mn = 0.0;
+  fm.g = g->d;
+  fm.rx = res.v[PCU_X]->d;
+  if (launch_tile(ctx, fm, nvars, w0, NO_RED)) return 1;
+  // D = I, C = small (IP.cpp:5418-5431), G = small*I + A^T D0^-1 A
+  if (setUpKKTDiagSystem(vars, 0, 1)) return 1;
+  std::vector<double> small(ncon, 1e-4);
+  if (setUpKKTSystem(vars, 0, small.data())) return 1;
+  // Right-hand side: only bx is non-zero.  With b.zl = b.zu = 0 and zero
+  // sparse/dense parts the full solve reduces to IP.cpp:5478-5508.
+  for (int i = 1; i < 8; i++)
+    if (pcu_vec_zero(res.v[i])) return 1;
+  for (int i = 0; i < ncon; i++) res.z[i] = res.s[i] = res.t[i] = res.zs[i] = res.zt[i] = 0.0;
+  // The dense solve of the reference here is z = -G^-1 A^T yx with no slack
+  // terms: emulate with s = t = 0 contributions by calling the generic step with
+  // temporary unit slacks (b dense parts are zero so only G matters).
+  Vars &step = update;
+  // Use the low-level pieces directly: pass 1, mdot, solve, pass 2.
+  {
+    Pass1F f1;
+    f1.v = vars.dv();
+    f1.b = res.dv();
+    f1.lb = lb->d;
+    f1.ub = ub->d;
+    f1.Dinv = Dinv->d;
+    f1.Cw = Cw->d;
+    f1.d1 = d1->d;
+    f1.d2 = d2->d;
+    f1.t1 = t1->d;
+    f1.k = kconst();
+    if (launch_tile(ctx, f1, nvars, wd, NO_RED)) return 1;
+    ColTable V;
+    for (int j = 0; j < ncon; j++) V.p[j] = Ac[j]->d;
+    std::vector<double> z(ncon);
+    if (ncon > 0) {
+      if (pcu_mdot_enqueue(ctx, t1->d, V, ncon, nvars, 0)) return 1;
+      if (ctx->big_fetch(ncon, z.data())) return 1;
+      for (int i = 0; i < ncon; i++) z[i] = -z[i];
+      pcu_lu_solve(ncon, Gfac.data(), gpiv.data(), z.data());
+    }
+    Pass2F f2;
+    for (int i = 0; i < ncon; i++) f2.alpha.v[i] = z[i];
+    f2.v = vars.dv();
+    f2.b = res.dv();
+    f2.y = step.dv();
+    f2.lb = lb->d;
+    f2.ub = ub->d;
+    f2.Dinv = Dinv->d;
+    f2.Cw = Cw->d;
+    f2.d1 = d1->d;
+    f2.d2 = d2->d;
+    f2.V = V;
+    f2.ncols = ncon;
+    f2.accumulate = 0;
+    f2.k = kconst();
+    if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
+    // vars.z = z, vars.zw = yw (IP.cpp:5483-5508)
+    for (int i = 0; i < ncon; i++) {
+      const double gam = 10.0 * std::max(gamma_s[i], gamma_t[i]);
+      vars.z[i] = (z[i] < -gam || z[i] > gam) ? 0.0 : z[i];
+    }
+    if (pcu_vec_copy(vars.v[PCU_ZW], step.v[PCU_ZW])) return 1;
+  }
+  if (nwcon > 0) {
+    SparseStartF fs;
+    fs.v = vars.dv();
+    fs.p = step.dv();
+    fs.mn = 0.0;
+    fs.gamma = opt.penalty_gamma;
+    fs.nwineq = prob->nwinequality;
+    fs.mode = 0;
+    if (launch_tile(ctx, fs, nwcon, w0, NO_RED)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------ initAffineStepMultipliers
+// IP.cpp:5536-5656
+int pcu_ip::initAffineStepMultipliers() {
+  Vars &vars = variables, &res = residual, &step = update;
+  if (initLeastSquaresMultipliers()) return 1;
+  // (out-of-range multipliers are already zero)
+  if (computeKKTRes(vars, 0.0, res, nullptr, nullptr, nullptr)) return 1;
+  int use_qn = opt.sequential_linear_method ? 0 : 1;
+  if (setUpKKTDiagSystem(vars, use_qn, 0)) return 1;
+  if (setUpKKTSystem(vars, use_qn, nullptr)) return 1;
+  if (computeKKTStep(vars, res, step, use_qn, 0, nullptr)) return 1;
+  const double mn = opt.start_affine_multiplier_min;
+  for (int i = 0; i < ncon; i++) {
+    vars.z[i] = vars.z[i] + step.z[i];
+    vars.s[i] = std::max(mn, fabs(vars.s[i] + step.s[i]));
+    vars.t[i] = std::max(mn, fabs(vars.t[i] + step.t[i]));
+    vars.zs[i] = std::max(mn, fabs(vars.zs[i] + step.zs[i]));
+    vars.zt[i] = std::max(mn, fabs(vars.zt[i] + step.zt[i]));
+  }
+  WDesc w0;
+  memset(&w0, 0, sizeof(w0));
+  if (nwcon > 0) {
+    SparseStartF fs;
+    fs.v = vars.dv();
+    fs.p = step.dv();
+    fs.mn = mn;
+    fs.gamma = opt.penalty_gamma;
+    fs.nwineq = prob->nwinequality;
+    fs.mode = 1;
+    if (launch_tile(ctx, fs, nwcon, w0, NO_RED)) return 1;
+  }
+  MaskBoundMultF fm;
+  fm.lb = lb->d;
+  fm.ub = ub->d;
+  fm.zl = vars.v[PCU_ZL]->d;
+  fm.zu = vars.v[PCU_ZU]->d;
+  fm.mbv = opt.max_bound_value;
+  fm.affine = 1;
+  fm.pzl = step.v[PCU_ZL]->d;
+  fm.pzu = step.v[PCU_ZU]->d;
+  fm.mn = mn;
+  fm.g = nullptr;
+  fm.rx = nullptr;
+  if (launch_tile(ctx, fm, nvars, w0, NO_RED)) return 1;
+  // barrier_param = computeComp(vars) (IP.cpp:5655): statistics of a residual pass
+  if (computeKKTRes(vars, 0.0, res, nullptr, nullptr, nullptr)) return 1;
+  barrier_param = compFromStats(vars);
+  return 0;
+}
+
+// ------------------------------------------------------------------ history
+struct StateSumF {  // checksums of the iterate for the parity history
+  static constexpr int NS = 7, NX = 1, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  DVars v;
+  const double *g;
+  int sparse;  // 0: N-sized pass, 1: W-sized pass
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
+                                    AccT &) const {}
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &acc) const {
+    if (!sparse) {
+      double x[W], a[W], b[W], gv[W];
+      ldv<W>(v.x, i, x);
+      ldv<W>(v.zl, i, a);
+      ldv<W>(v.zu, i, b);
+      ldv<W>(g, i, gv);
+#pragma unroll
+      for (int e = 0; e < W; e++) {
+        acc.s[0] += x[e];
+        acc.s[1] = fma(x[e], x[e], acc.s[1]);
+        acc.s[2] += a[e];
+        acc.s[3] += b[e];
+        acc.x[0] = fmax(acc.x[0], fabs(gv[e]));
+      }
+    } else {
+      double a[W], b[W], c[W];
+      ldv<W>(v.zw, i, a);
+      ldv<W>(v.sw, i, b);
+      ldv<W>(v.tw, i, c);
+#pragma unroll
+      for (int e = 0; e < W; e++) {
+        acc.s[4] += a[e];
+        acc.s[5] += b[e];
+        acc.s[6] += c[e];
+      }
+    }
+  }
+};
+
+int pcu_ip::snapshot(int k, double comp, double max_prime, double max_dual,
+                     double max_infeas, double res_norm) {
+  if (opt.history_level <= 0) return 0;
+  HistRec rec;
+  memset(rec.f, 0, sizeof(rec.f));
+  double sums[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (opt.history_level >= 2) {
+    WDesc w0;
+    memset(&w0, 0, sizeof(w0));
+    StateSumF f;
+    f.v = variables.dv();
+    f.g = g->d;
+    f.sparse = 0;
+    RedBuf rb = ctx->redbuf(7, 1, 0);
+    if (launch_tile(ctx, f, nvars, w0, rb)) return 1;
+    double o1[8], o2[8];
+    if (ctx->fetch(o1)) return 1;
+    memcpy(sums, o1, sizeof(o1));
+    if (nwcon > 0 || ctx->world > 1) {
+      f.sparse = 1;
+      RedBuf rb2 = ctx->redbuf(7, 1, 0);
+      if (launch_tile(ctx, f, nwcon, w0, rb2)) return 1;
+      if (ctx->fetch(o2)) return 1;
+      sums[4] = o2[4];
+      sums[5] = o2[5];
+      sums[6] = o2[6];
+    }
+  }
+  double *f = rec.f;
+  f[0] = k;
+  f[1] = fobj;
+  f[2] = barrier_param;
+  f[3] = rho_penalty_search;
+  f[4] = comp;
+  f[5] = max_prime;
+  f[6] = max_dual;
+  f[7] = max_infeas;
+  f[8] = res_norm;
+  f[9] = neval;
+  f[10] = ngeval;
+  f[11] = ls.alpha_prev;
+  f[12] = ls.last_pnorm2;
+  f[13] = qn ? qn->b0 : 0.0;
+  f[14] = qn ? qn->size() : 0;
+  f[15] = sums[0];
+  f[16] = sqrt(sums[1]);
+  f[17] = sums[2];
+  f[18] = sums[3];
+  f[19] = sums[4];
+  f[20] = sums[5];
+  f[21] = sums[6];
+  f[22] = sums[7];
+  f[23] = ls.alpha_xprev;
+  f[24] = ls.alpha_zprev;
+  rec.dense.reserve(6 * ncon);
+  const std::vector<double> *parts[6] = {&c, &variables.z, &variables.s,
+                                         &variables.t, &variables.zs,
+                                         &variables.zt};
+  for (auto p : parts) rec.dense.insert(rec.dense.end(), p->begin(), p->end());
+  rec.info = ls.info;
+  history.push_back(rec);
+  return 0;
+}
+
+// Text log row, same format as the reference (IP.cpp:4777-4801)
+void pcu_ip::log_line(int k, double comp, double max_prime, double max_infeas,
+                      double max_dual) {
+  if (!outfp || ctx->rank != 0) return;
+  if (k % 10 == 0 || opt.output_level > 0) {
+    fprintf(outfp,
+            "\n%4s %4s %4s %4s %7s %7s %7s %12s %7s %7s %7s %7s %7s %8s %7s info\n",
+            "iter", "nobj", "ngrd", "nhvc", "alpha", "alphx", "alphz", "fobj",
+            "|opt|", "|infes|", "|dual|", "mu", "comp", "dmerit", "rho");
+  }
+  if (k == 0) {
+    fprintf(outfp,
+            "%4d %4d %4d %4d %7s %7s %7s %12.5e %7.1e %7.1e %7.1e %7.1e %7.1e %8s %7s %s\n",
+            k, neval, ngeval, 0, "--", "--", "--", fobj, max_prime, max_infeas,
+            max_dual, barrier_param, comp, "--", "--", ls.info.c_str());
+  } else {
+    fprintf(outfp,
+            "%4d %4d %4d %4d %7.1e %7.1e %7.1e %12.5e %7.1e %7.1e %7.1e %7.1e %7.1e %8.1e %7.1e %s\n",
+            k, neval, ngeval, 0, ls.alpha_prev, ls.alpha_xprev, ls.alpha_zprev,
+            fobj, max_prime, max_infeas, max_dual, barrier_param, comp,
+            ls.dm0_prev, rho_penalty_search, ls.info.c_str());
+  }
+  fflush(outfp);
+}
+
+// scaleKKTStep (IP.cpp:3196-3274) + evalMeritInitDeriv (IP.cpp:3652-3924) from
+// ONE statistics pass; the step itself stays unscaled on the device.
+// fixed_scale < 0: the step lengths come from the fraction-to-boundary rule and
+// the step is treated as scaled by alpha_x (the optimizer's path).
+// fixed_scale >= 0: the step is taken as already scaled (factor 1) and
+// fixed_scale is the max_x argument of the reference's evalMeritInitDeriv.
+int pcu_ip::scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
+                          const double *VTp, double fixed_scale,
+                          StepScale *out) {
+  const double abs_res_tol = opt.abs_res_tol;
+  const int slm = opt.sequential_linear_method;
+  const int nA = ncon;
+  double sums[StatsF::NS], mins[2];
+  double alpha_x = 1.0, alpha_z = 1.0, m0 = 0.0, dm0 = 0.0, pnorm2 = 0.0;
+  int ceq_step = 0;
+    if (stepStats(v, upd, tau, sums, mins)) return 1;
+    alpha_x = mins[0];
+    alpha_z = mins[1];
+    ceq_step = 0;
+    const double max_bnd = 100.0;
+    if (alpha_x > alpha_z) {
+      if (alpha_x > max_bnd * alpha_z) alpha_x = max_bnd * alpha_z;
+      else if (alpha_x < alpha_z / max_bnd) alpha_x = alpha_z / max_bnd;
+    } else {
+      if (alpha_z > max_bnd * alpha_x) alpha_z = max_bnd * alpha_x;
+      else if (alpha_z < alpha_x / max_bnd) alpha_z = alpha_x / max_bnd;
+    }
+    double product = (sums[0] + alpha_x * sums[1] + alpha_z * sums[2] +
+                      alpha_x * alpha_z * sums[3]) / opt.rel_bound_barrier +
+                     (sums[4] + alpha_x * sums[5] + alpha_z * sums[6] +
+                      alpha_x * alpha_z * sums[7]);
+    double count = res_sums[1];
+    for (int i = 0; i < ncon; i++) {
+      product += (v.s[i] + alpha_x * upd.s[i]) * (v.zs[i] + alpha_z * upd.zs[i]) +
+                 (v.t[i] + alpha_x * upd.t[i]) * (v.zt[i] + alpha_z * upd.zt[i]);
+      count += 2.0;
+    }
+    const double comp_new = count != 0.0 ? product / count : 0.0;
+    if (comp_new > 10.0 * comp) {
+      ceq_step = 1;
+      if (alpha_x > alpha_z) alpha_x = alpha_z;
+      else alpha_z = alpha_x;
+    }
+    if (fixed_scale >= 0.0) {
+      alpha_x = 1.0;
+      alpha_z = 1.0;
+      ceq_step = 0;
+    }
+    pnorm2 = alpha_x * alpha_x * sums[17];
+    // ---- merit function and derivative with the step scaled by alpha_x ----
+    const double kap = opt.rel_bound_barrier;
+    double pos = sums[8] * kap + sums[12], neg = sums[9] * kap + sums[13];
+    double ppos = alpha_x * (sums[10] * kap + sums[14]);
+    double pneg = alpha_x * (sums[11] * kap + sums[15]);
+    for (int i = 0; i < ncon; i++) {
+      const double lsv = log(v.s[i]), ltv = log(v.t[i]);
+      if (v.s[i] > 1.0) pos += lsv; else neg += lsv;
+      if (v.t[i] > 1.0) pos += ltv; else neg += ltv;
+      const double ps = alpha_x * upd.s[i], pt = alpha_x * upd.t[i];
+      if (ps > 0.0) ppos += ps / v.s[i]; else pneg += ps / v.s[i];
+      if (pt > 0.0) ppos += pt / v.t[i]; else pneg += pt / v.t[i];
+    }
+    // evalInfeasDeriv (IP.cpp:3465-3509)
+    double dense_infeas = 0.0, pdense_infeas = 0.0;
+    for (int i = 0; i < ncon; i++) {
+      const double cval = c[i] - v.s[i] + v.t[i];
+      const double pcval = alpha_x * (VTp[i] - upd.s[i] + upd.t[i]);
+      dense_infeas += cval * cval;
+      pdense_infeas += cval * pcval;
+    }
+    const double infeas = sqrt(dense_infeas + sums[20]);
+    const double psparse = alpha_x * sums[21];
+    const double infeas_proj = infeas > 0.0 ? (pdense_infeas + psparse) / infeas : 0.0;
+    // p^T B p through the compact form (IP.cpp:3820-3821)
+    double pTBp = 0.0;
+    if (qn && !slm) {
+      double v2 = qn->b0 * sums[17];
+      const int q = qn->size();
+      if (q > 0) {
+        std::vector<double> kapq(q);
+        qn->solve_compact(VTp + nA, kapq.data());
+        for (int i = 0; i < q; i++) v2 -= kapq[i] * VTp[nA + i];
+      }
+      pTBp = 0.5 * alpha_x * alpha_x * v2;
+    }
+    double merit = fobj + sums[18] - barrier_param * (pos + neg);
+    double pmerit = alpha_x * sums[16] + alpha_x * sums[19] -
+                    barrier_param * (ppos + pneg);
+    for (int i = 0; i < ncon; i++) {
+      merit += gamma_s[i] * v.s[i] + gamma_t[i] * v.t[i];
+      pmerit += alpha_x * (gamma_s[i] * upd.s[i] + gamma_t[i] * upd.t[i]);
+    }
+    double numer = pmerit;
+    if (pTBp > 0.0) numer += 0.5 * pTBp;
+    const double pdf = opt.penalty_descent_fraction;
+    const double max_x = fixed_scale >= 0.0 ? fixed_scale : alpha_x;
+    double rho_hat = 0.0;
+    if (infeas < 0.1 * abs_res_tol) {
+      const double denom = -(1.0 - pdf) * max_x * infeas;
+      if (numer >= 0.0 && denom < 0.0) rho_hat = -numer / denom;
+    } else {
+      double denom = infeas_proj + pdf * max_x * infeas;
+      if (numer >= 0.0) {
+        if (denom < 0.0) {
+          rho_hat = -numer / denom;
+        } else {
+          denom = -(1.0 - pdf) * max_x * infeas;
+          rho_hat = -numer / denom;
+        }
+      }
+    }
+    if (rho_hat > rho_penalty_search) {
+      rho_penalty_search = rho_hat;
+    } else {
+      rho_penalty_search *= 0.5;
+      if (rho_penalty_search < rho_hat) rho_penalty_search = rho_hat;
+    }
+    if (rho_penalty_search < opt.min_rho_penalty_search)
+      rho_penalty_search = opt.min_rho_penalty_search;
+    merit += rho_penalty_search * infeas;
+    if (infeas < 0.1 * abs_res_tol) pmerit -= rho_penalty_search * max_x * infeas;
+    else pmerit += rho_penalty_search * infeas_proj;
+    m0 = merit;
+    dm0 = pmerit;
+    out->alpha_x = alpha_x;
+    out->alpha_z = alpha_z;
+    out->ceq = ceq_step;
+    out->m0 = m0;
+    out->dm0 = dm0;
+    out->pnorm2 = pnorm2;
+    return 0;
+}
+
+// -------------------------------------------------------------------- begin
+// Everything ParOptInteriorPoint::optimize does before its major loop
+// (IP.cpp:4399-4606).
+int pcu_ip::begin() {
+  if (ensure_qn()) return 1;
+  refresh_penalties();
+  if (!opt.output_file.empty() && !outfp && ctx->rank == 0) {
+    outfp = fopen(opt.output_file.c_str(), "w");
+  }
+  ls = LoopState();
+  auto strat = [](const std::string &s) {
+    if (s == "monotone") return (int)BS_MONOTONE;
+    if (s == "mehrotra") return (int)BS_MEHROTRA;
+    if (s == "mehrotra_predictor_corrector") return (int)BS_MPC;
+    return (int)BS_COMP_FRACTION;
+  };
+  ls.barrier_strategy = BS_MONOTONE;
+  ls.input_barrier_strategy = strat(opt.barrier_strategy);
+  barrier_param = opt.init_barrier_param;
+  rho_penalty_search = opt.init_rho_penalty_search;
+  niter = neval = ngeval = 0;
+  status = 0;
+  history.clear();
+  times.clear();
+  if (!opt.sequential_linear_method && !qn) {
+    if (ctx->rank == 0)
+      fprintf(stderr,
+              "ParOpt Error: Must use a sequential linear method if no "
+              "quasi-Newton approximation is defined\n");
+    return 1;
+  }
+  if (initAndCheckDesignAndBounds()) return 1;
+  if (evalObjCon(variables.v[PCU_X])) {
+    fprintf(stderr, "ParOpt: Initial function and constraint evaluation failed\n");
+    return 1;
+  }
+  if (evalObjConGradient(variables.v[PCU_X])) {
+    fprintf(stderr, "ParOpt: Initial gradient evaluation failed\n");
+    return 1;
+  }
+  if (opt.starting_point_strategy == "affine_step") {
+    if (initAffineStepMultipliers()) return 1;
+  } else if (opt.starting_point_strategy == "least_squares_multipliers") {
+    if (initLeastSquaresMultipliers()) return 1;
+  }
+  if (pcu_ctx_sync(ctx)) return 1;
+  cb_collect();
+  ls.started = 1;
+  return 0;
+}
+
+// ------------------------------------------------------------- iterate_once
+// One pass of the major loop body (IP.cpp:4607-5329).
+int pcu_ip::iterate_once(int *converged) {
+  *converged = 0;
+  if (!ls.started || ls.finished) return ls.finished ? 0 : 1;
+  Vars &v = variables, &res = residual, &upd = update, &ref = refine;
+  const int k = ls.k;
+  const double abs_res_tol = opt.abs_res_tol;
+  const double fp = opt.function_precision;
+  const int uq = opt.use_quasi_newton_update;
+  const int slm = opt.sequential_linear_method;
+  PCU_CUDA_OK(cudaEventRecord(ev_it0, ctx->stream));
+  const double cb_before = prob->callback_ms;
+
+  int qn_hessian_reset = 0;
+  if (qn && !slm) {
+    if (k > 0 && k % opt.hessian_reset_freq == 0 && uq) {
+      qn->reset();
+      qn_hessian_reset = 1;
+    }
+  }
+  const int rel_function_test =
+      (ls.alpha_xprev == 1.0 && ls.alpha_zprev == 1.0 &&
+       fabs(fobj - ls.fobj_prev) < opt.rel_func_tol * fabs(ls.fobj_prev));
+  if (ls.no_merit_function_improvement) ls.line_search_test += 1;
+  else ls.line_search_test = 0;
+
+  double max_prime = 0.0, max_dual = 0.0, max_infeas = 0.0, res_norm = 0.0;
+  int monotone_barrier_converged = 0;
+  // residual + norms + complementarity in one pass (IP.cpp:4656-4671)
+  if (ls.barrier_strategy == BS_COMP_FRACTION) {
+    // mu depends on comp: a first pass for comp, then the residual
+    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+  }
+  double comp;
+  if (ls.barrier_strategy == BS_COMP_FRACTION) {
+    comp = compFromStats(v);
+    if (snapshot(k, comp, 0, 0, 0, 0)) return 1;
+    barrier_param = opt.monotone_barrier_fraction * comp;
+    if (barrier_param < 0.1 * abs_res_tol) barrier_param = 0.1 * abs_res_tol;
+    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+    computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+    if (k == 0) ls.res_norm_prev = res_norm;
+  } else {
+    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+    comp = compFromStats(v);
+    computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+    if (snapshot(k, comp, max_prime, max_dual, max_infeas, res_norm)) return 1;
+    if (k == 0) ls.res_norm_prev = res_norm;
+    if (ls.barrier_strategy == BS_MONOTONE) {
+      if (k > 0 && ((res_norm < 10.0 * barrier_param) || rel_function_test ||
+                    (ls.line_search_test >= 2))) {
+        monotone_barrier_converged = 1;
+      }
+      if (monotone_barrier_converged) {  // IP.cpp:4695-4735
+        if (barrier_param > 0.1 * abs_res_tol) ls.line_search_test = 0;
+        const double mu_frac = opt.monotone_barrier_fraction * barrier_param;
+        const double mu_pow = pow(barrier_param, opt.monotone_barrier_power);
+        double new_mu = mu_frac;
+        if (mu_pow < mu_frac) new_mu = mu_pow;
+        if (new_mu < 0.1 * abs_res_tol) new_mu = 0.09999 * abs_res_tol;
+        if (computeKKTRes(v, new_mu, res, nullptr, nullptr, nullptr)) return 1;
+        computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+        rho_penalty_search = opt.min_rho_penalty_search;
+        barrier_param = new_mu;
+      }
+    }
+  }
+  last_comp = comp;
+  log_line(k, comp, max_prime, max_infeas, max_dual);
+
+  // convergence test (IP.cpp:4811-4840)
+  if (k > 0 && (barrier_param <= 0.1 * abs_res_tol) &&
+      (res_norm < abs_res_tol || rel_function_test || (ls.line_search_test >= 2))) {
+    if (rel_function_test) status = 2;
+    else if (ls.line_search_test >= 2) status = 3;
+    else status = 1;
+    if (outfp && ctx->rank == 0) {
+      if (status == 2)
+        fprintf(outfp, "\nParOpt: Successfully converged on relative function test\n");
+      else if (status == 3)
+        fprintf(outfp,
+                "\nParOpt Warning: Current design point could not be improved. "
+                "No barrier function decrease in previous two iterations\n");
+      else
+        fprintf(outfp, "\nParOpt: Successfully converged to requested tolerance\n");
+      fflush(outfp);
+    }
+    ls.finished = 1;
+    *converged = 1;
+    return 0;
+  }
+
+  ls.fobj_prev = fobj;
+  ls.res_norm_prev = res_norm;
+  int seq_linear_step = 0, diagonal_qn_step = 0;
+  int use_qn = 1;
+  if (slm) {
+    use_qn = 0;
+  } else if (ls.line_search_failed && !uq) {
+    use_qn = 0;
+    seq_linear_step = 1;
+    if (qn && qn->b0 > 0.0) {
+      seq_linear_step = 0;
+      diagonal_qn_step = 1;
+    }
+  }
+  double mu_for_res = barrier_param;
+  const bool mehrotra =
+      ls.barrier_strategy == BS_MEHROTRA || ls.barrier_strategy == BS_MPC;
+  if (mehrotra) {
+    mu_for_res = 0.0;
+    if (computeKKTRes(v, mu_for_res, res, nullptr, nullptr, nullptr)) return 1;
+    computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+  }
+  if (diagonal_qn_step) use_qn = 1;
+  const int nA = ncon, nZ = qn ? qn->max_size() : 0;
+  std::vector<double> VTp(nA + nZ + 1, 0.0), VTr(nA + nZ + 1, 0.0);
+
+  PCU_CUDA_OK(cudaEventRecord(ev_k0, ctx->stream));
+  if (setUpKKTDiagSystem(v, use_qn, 0)) return 1;
+  if (setUpKKTSystem(v, use_qn, nullptr)) return 1;
+  if (diagonal_qn_step) use_qn = 0;
+  const int nref = opt.iterative_refinement_steps;
+  auto kkt_with_refinement = [&](double mu_res, bool allow_refine) -> int {
+    const bool need_dots = true;
+    if (computeKKTStep(v, res, upd, use_qn, 0, need_dots ? VTp.data() : nullptr))
+      return 1;
+    if (!allow_refine) return 0;
+    for (int it = 0; it < nref; it++) {  // IP.cpp:4985-4991
+      if (computeKKTRes(v, mu_res, res, &upd, VTp.data(), VTp.data() + nA)) return 1;
+      if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data())) return 1;
+    }
+    return 0;
+  };
+  {
+    // first step without refinement timing split: KKT solve = setup + first step
+    if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data())) return 1;
+    PCU_CUDA_OK(cudaEventRecord(ev_k1, ctx->stream));
+    for (int it = 0; it < nref; it++) {
+      if (computeKKTRes(v, mu_for_res, res, &upd, VTp.data(), VTp.data() + nA)) return 1;
+      if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data())) return 1;
+    }
+  }
+  (void)ref;
+  double sums[StatsF::NS], mins[2];
+  if (mehrotra) {  // IP.cpp:4999-5051
+    if (stepStats(v, upd, 1.0, sums, mins)) return 1;
+    const double max_x = mins[0], max_z = mins[1];
+    double product = (sums[0] + max_x * sums[1] + max_z * sums[2] +
+                      max_x * max_z * sums[3]) / opt.rel_bound_barrier +
+                     (sums[4] + max_x * sums[5] + max_z * sums[6] +
+                      max_x * max_z * sums[7]);
+    double count = res_sums[1];
+    for (int i = 0; i < ncon; i++) {
+      product += (v.s[i] + max_x * upd.s[i]) * (v.zs[i] + max_z * upd.zs[i]) +
+                 (v.t[i] + max_x * upd.t[i]) * (v.zt[i] + max_z * upd.zt[i]);
+      count += 2.0;
+    }
+    const double comp_affine = count != 0.0 ? product / count : 0.0;
+    const double s1 = comp_affine / comp;
+    double sigma = s1 * s1 * s1;
+    if (sigma < 0.01) sigma = 0.01;
+    barrier_param = sigma * comp;
+    if (barrier_param < 0.09999 * abs_res_tol) barrier_param = 0.09999 * abs_res_tol;
+    if (ls.barrier_strategy == BS_MPC) {
+      fprintf(stderr,
+              "paropt_b200: mehrotra_predictor_corrector is not built yet; "
+              "using mehrotra\n");
+    }
+    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+    computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+    if (kkt_with_refinement(barrier_param, true)) return 1;
+  }
+
+  // fraction to the boundary (IP.cpp:5069-5077)
+  double tau = opt.min_fraction_to_boundary;
+  if (1.0 - barrier_param >= tau) tau = 1.0 - barrier_param;
+
+  double alpha_x = 1.0, alpha_z = 1.0;
+  int ceq_step = 0;
+  double m0 = 0.0, dm0 = 0.0;
+  double pnorm2 = 0.0, px_maxabs_scaled = 0.0;
+
+  // scaleKKTStep (IP.cpp:3196-3274) + evalMeritInitDeriv (IP.cpp:3652-3924) from
+  // ONE statistics pass; the step itself stays unscaled on the device.
+  auto scale_and_merit = [&]() -> int {
+    StepScale sc;
+    if (scaleAndMerit(v, upd, tau, comp, VTp.data(), -1.0, &sc)) return 1;
+    alpha_x = sc.alpha_x;
+    alpha_z = sc.alpha_z;
+    ceq_step = sc.ceq;
+    m0 = sc.m0;
+    dm0 = sc.dm0;
+    pnorm2 = sc.pnorm2;
+    return 0;
+  };
+  if (scale_and_merit()) return 1;
+
+  double alpha = 1.0;
+  int line_fail = LS_FAILURE;
+  int update_type = 0;
+  int line_search_skipped = 0;
+  ls.no_merit_function_improvement = 0;
+
+  // computeStepAndUpdate (IP.cpp:4169-4267)
+  auto step_and_update = [&](double a, int eval_obj_con) -> int {
+    const double ax = a * alpha_x, az = a * alpha_z;
+    const bool form_pair = qn && uq;
+    const IPConst kc = kconst();
+    for (int i = 0; i < ncon; i++) {  // dense parts (IP.cpp:4190-4194)
+      const double dp = opt.design_precision;
+      auto clip0 = [&](double x0, double st, double p) {
+        double r = x0 + st * p;
+        if (r <= dp) r = dp;
+        return r;
+      };
+      v.s[i] = clip0(v.s[i], ax, upd.s[i]);
+      v.t[i] = clip0(v.t[i], ax, upd.t[i]);
+      v.z[i] = v.z[i] + az * upd.z[i];
+      v.zs[i] = clip0(v.zs[i], az, upd.zs[i]);
+      v.zt[i] = clip0(v.zt[i], az, upd.zt[i]);
+    }
+    Update1F f1;
+    f1.v = v.dv();
+    f1.p = upd.dv();
+    f1.lb = lb->d;
+    f1.ub = ub->d;
+    f1.g = g->d;
+    f1.ncon = ncon;
+    for (int j = 0; j < ncon; j++) {
+      f1.Acol.p[j] = Ac[j]->d;
+      f1.z.v[j] = v.z[j];
+    }
+    f1.yqn = form_pair ? y_qn->d : nullptr;
+    f1.ax = ax;
+    f1.az = az;
+    f1.k = kc;
+    if (launch_tile(ctx, f1, nvars, wd, NO_RED)) return 1;
+    if (eval_obj_con) {
+      if (evalObjCon(v.v[PCU_X])) {
+        fprintf(stderr, "ParOpt: Function and constraint evaluation failed\n");
+        return 1;
+      }
+    }
+    if (evalObjConGradient(v.v[PCU_X])) {
+      fprintf(stderr, "ParOpt: Gradient evaluation failed at final line search\n");
+    }
+    update_type = 0;
+    if (qn) {
+      if (uq) {
+        Update2F f2;
+        f2.zw = v.v[PCU_ZW]->d;
+        f2.px = upd.v[PCU_X]->d;
+        f2.g = g->d;
+        f2.ncon = ncon;
+        for (int j = 0; j < ncon; j++) {
+          f2.Acol.p[j] = Ac[j]->d;
+          f2.z.v[j] = v.z[j];
+        }
+        f2.yqn = y_qn->d;
+        f2.sqn = s_qn->d;
+        f2.ax = ax;
+        RedBuf rb = ctx->redbuf(3, 0, 0);
+        if (launch_tile(ctx, f2, nvars, wd, rb)) return 1;
+        double dots[3];
+        if (ctx->fetch(dots)) return 1;
+        if (qn->update(s_qn, y_qn, dots[0], dots[1], dots[2], &update_type)) return 1;
+      }
+    }
+    return 0;
+  };
+
+  // lineSearch (IP.cpp:3939-4156)
+  auto line_search = [&](double alpha_min) -> int {
+    int fail = LS_FAILURE;
+    double merit = 0.0, best_merit = 0.0, best_alpha = -1.0;
+    const int max_iters = opt.max_line_iters;
+    std::vector<double> rs(ncon), rt(ncon);
+    const double dp = opt.design_precision;
+    auto eval_trial = [&](double a, bool merit_too, double *merit_out) -> int {
+      TrialF ft;
+      ft.v = v.dv();
+      ft.p = upd.dv();
+      ft.lb = lb->d;
+      ft.ub = ub->d;
+      ft.rx = rx->d;
+      ft.rsw = rsw->d;
+      ft.rtw = rtw->d;
+      ft.ax = a * alpha_x;
+      ft.k = kconst();
+      RedBuf rb = ctx->redbuf(TrialF::NS, 0, 0);
+      if (launch_tile(ctx, ft, nvars, wd, rb)) return -1;
+      double ts[TrialF::NS];
+      // the objective callback fetches its own reductions; keep ours first
+      if (ctx->fetch(ts)) return -1;
+      int fail_obj = evalObjCon(rx);
+      if (fail_obj) return 1;
+      if (!merit_too) return 0;
+      for (int i = 0; i < ncon; i++) {
+        double r = v.s[i] + a * alpha_x * upd.s[i];
+        if (r <= dp) r = dp;
+        rs[i] = r;
+        r = v.t[i] + a * alpha_x * upd.t[i];
+        if (r <= dp) r = dp;
+        rt[i] = r;
+      }
+      // evalMeritFunc (IP.cpp:3524-3637)
+      const double kap = opt.rel_bound_barrier;
+      double pos = ts[0] * kap + ts[2], neg = ts[1] * kap + ts[3];
+      double dense_infeas = 0.0;
+      double m = fobj + ts[4];
+      for (int i = 0; i < ncon; i++) {
+        const double l1 = log(rs[i]), l2 = log(rt[i]);
+        if (rs[i] > 1.0) pos += l1; else neg += l1;
+        if (rt[i] > 1.0) pos += l2; else neg += l2;
+        const double cval = c[i] - rs[i] + rt[i];
+        dense_infeas += cval * cval;
+      }
+      const double infeas = sqrt(dense_infeas + ts[5]);
+      m += -barrier_param * (pos + neg) + rho_penalty_search * infeas;
+      for (int i = 0; i < ncon; i++) m += gamma_s[i] * rs[i] + gamma_t[i] * rt[i];
+      *merit_out = m;
+      return 0;
+    };
+    int j = 0;
+    for (; j < max_iters; j++) {
+      int rc = eval_trial(alpha, true, &merit);
+      if (rc < 0) return -1;
+      if (rc > 0) {
+        fprintf(stderr,
+                "ParOpt: Evaluation failed during line search, trying new point\n");
+        alpha *= 0.1;
+        continue;
+      }
+      if (best_alpha < 0.0 || merit < best_merit) {
+        best_alpha = alpha;
+        best_merit = merit;
+      }
+      if (merit - opt.armijo_constant * alpha * dm0 < m0 + fp) {
+        if (fail & LS_MIN_STEP) fail = LS_SUCCESS | LS_MIN_STEP;
+        else fail = LS_SUCCESS;
+        if (merit <= m0 + fp && merit + fp >= m0) fail |= LS_NO_IMPROVEMENT;
+        break;
+      } else if (fail & LS_MIN_STEP) {
+        break;
+      }
+      if (j < max_iters - 1) {
+        if (opt.use_backtracking_alpha) {
+          alpha = 0.5 * alpha;
+          if (alpha <= alpha_min) {
+            alpha = alpha_min;
+            fail |= LS_MIN_STEP;
+          }
+        } else {
+          const double alpha_new =
+              -0.5 * dm0 * (alpha * alpha) / (merit - m0 - dm0 * alpha);
+          if (alpha_new <= alpha_min) {
+            alpha = alpha_min;
+            fail |= LS_MIN_STEP;
+          } else if (alpha_new < 0.01 * alpha) {
+            alpha = 0.01 * alpha;
+          } else {
+            alpha = alpha_new;
+          }
+        }
+      }
+    }
+    if (j == max_iters) fail |= LS_MAX_ITERS;
+    if (!(fail & LS_SUCCESS)) {
+      if (best_merit <= m0 + fp) {
+        fail |= LS_SUCCESS;
+        fail &= ~LS_FAILURE;
+      } else if (merit <= m0 + fp && merit + fp >= m0) {
+        fail |= LS_NO_IMPROVEMENT;
+      }
+      if (alpha != best_alpha) {
+        alpha = best_alpha;
+        double dummy;
+        int rc = eval_trial(alpha, false, &dummy);
+        if (rc != 0) {
+          fprintf(stderr, "ParOpt: Evaluation failed during line search\n");
+          fail = LS_FAILURE;
+        }
+      }
+    }
+    return fail;
+  };
+
+  if (opt.use_line_search) {
+    ls.dm0_prev = dm0;
+    if (dm0 >= 0.0 && dm0 <= fp) {
+      line_search_skipped = 1;
+      if (step_and_update(alpha, 1)) return 1;
+      if ((ls.fobj_prev + fp <= fobj) && (fobj + fp <= ls.fobj_prev))
+        line_fail = LS_NO_IMPROVEMENT;
+    } else {
+      if (dm0 >= 0.0) {  // IP.cpp:5130-5173
+        if (qn) {
+          qn_hessian_reset = 1;
+          qn->reset();
+        }
+        if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+        computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+        diagonal_qn_step = 1;
+        use_qn = 1;
+        if (setUpKKTDiagSystem(v, use_qn, 0)) return 1;
+        if (setUpKKTSystem(v, use_qn, nullptr)) return 1;
+        if (kkt_with_refinement(barrier_param, true)) return 1;
+        if (scale_and_merit()) return 1;
+        ls.dm0_prev = dm0;
+      }
+      if (dm0 >= 0.0) {
+        line_fail = LS_FAILURE;
+      } else {
+        // px_norm is the max-abs of the alpha_x-scaled step (IP.cpp:5183)
+        px_maxabs_scaled = alpha_x * stats_pmax;
+        double alpha_min = 1.0;
+        if (px_maxabs_scaled != 0.0) alpha_min = fp / px_maxabs_scaled;
+        if (alpha_min > 0.5) alpha_min = 0.5;
+        line_fail = line_search(alpha_min);
+        if (line_fail < 0) return 1;
+        if (px_maxabs_scaled < opt.design_precision) line_fail |= LS_SHORT_STEP;
+        if (!(line_fail & LS_FAILURE)) {
+          if (step_and_update(alpha, 0)) return 1;
+        }
+      }
+    }
+  } else {
+    ls.dm0_prev = dm0;
+    line_fail = LS_SUCCESS;
+    if (step_and_update(alpha, 1)) return 1;
+    // merit at the new point (IP.cpp:5236-5243): trial kernel with zero step
+    TrialF ft;
+    ft.v = v.dv();
+    ft.p = upd.dv();
+    ft.lb = lb->d;
+    ft.ub = ub->d;
+    ft.rx = rx->d;
+    ft.rsw = rsw->d;
+    ft.rtw = rtw->d;
+    ft.ax = 0.0;
+    ft.k = kconst();
+    RedBuf rb = ctx->redbuf(TrialF::NS, 0, 0);
+    if (launch_tile(ctx, ft, nvars, wd, rb)) return 1;
+    double ts[TrialF::NS];
+    if (ctx->fetch(ts)) return 1;
+    const double kap = opt.rel_bound_barrier;
+    double pos = ts[0] * kap + ts[2], neg = ts[1] * kap + ts[3];
+    double dense_infeas = 0.0;
+    double m1 = fobj + ts[4];
+    for (int i = 0; i < ncon; i++) {
+      const double l1 = log(v.s[i]), l2 = log(v.t[i]);
+      if (v.s[i] > 1.0) pos += l1; else neg += l1;
+      if (v.t[i] > 1.0) pos += l2; else neg += l2;
+      const double cval = c[i] - v.s[i] + v.t[i];
+      dense_infeas += cval * cval;
+      m1 += gamma_s[i] * v.s[i] + gamma_t[i] * v.t[i];
+    }
+    m1 += -barrier_param * (pos + neg) +
+          rho_penalty_search * sqrt(dense_infeas + ts[5]);
+    if (m1 <= m0 + fp && m1 + fp >= m0) line_fail |= LS_NO_IMPROVEMENT;
+    else if (fabs(dm0) <= fp) line_fail = LS_NO_IMPROVEMENT;
+  }
+
+  ls.no_merit_function_improvement =
+      ((line_fail & LS_NO_IMPROVEMENT) || (line_fail & LS_MIN_STEP) ||
+       (line_fail & LS_SHORT_STEP) || (line_fail & LS_FAILURE)) ? 1 : 0;
+  ls.line_search_failed = (line_fail & LS_FAILURE);
+  ls.alpha_prev = alpha;
+  ls.alpha_xprev = alpha_x;
+  ls.alpha_zprev = alpha_z;
+  ls.last_pnorm2 = pnorm2;
+  if (qn && uq && (line_fail & LS_FAILURE)) {
+    qn_hessian_reset = 1;
+    qn->reset();
+  }
+  std::string info;
+  if (update_type == 1) info += "dampH ";
+  else if (update_type == 2) info += "skipH ";
+  if (qn_hessian_reset) info += "resetH ";
+  if (line_fail & LS_FAILURE) info += "LFail ";
+  if (line_fail & LS_MIN_STEP) info += "LMnStp ";
+  if (line_fail & LS_MAX_ITERS) info += "LMxItr ";
+  if (line_fail & LS_NO_IMPROVEMENT) info += "LNoImprv ";
+  if (seq_linear_step) info += "SLP ";
+  if (diagonal_qn_step) info += "DQN ";
+  if (line_search_skipped) info += "LSkip ";
+  if (ceq_step) info += "cmpEq ";
+  while (!info.empty() && info.back() == ' ') info.pop_back();
+  ls.info = info;
+  if (monotone_barrier_converged) ls.barrier_strategy = ls.input_barrier_strategy;
+
+  PCU_CUDA_OK(cudaEventRecord(ev_it1, ctx->stream));
+  PCU_CUDA_OK(cudaEventSynchronize(ev_it1));
+  cb_collect();
+  IterTime tm;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev_it0, ev_it1);
+  tm.total_ms = ms;
+  cudaEventElapsedTime(&ms, ev_k0, ev_k1);
+  tm.kkt_ms = ms;
+  tm.callback_ms = prob->callback_ms - cb_before;
+  times.push_back(tm);
+  ls.k++;
+  niter++;
+  return 0;
+}

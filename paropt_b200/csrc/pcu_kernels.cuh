@@ -1,0 +1,839 @@
+// pcu_kernels.cuh -- the fused interior-point kernels (functors for tile_kernel).
+//
+// Each functor restates one or more private methods of the reference's
+// ParOptInteriorPoint (IP.cpp = /root/reference/src/ParOptInteriorPoint.cpp) as a
+// single pass over the local design variables (N) and weighting constraints
+// (W).  Algorithmic traffic per launch is stated with every functor
+// ("words" = fp64 words; c = dense constraints, q = quasi-Newton width).
+//
+// Functor protocol (see tile_kernel in pcu_common.cuh):
+//   A<W>(i, coef, elem, part)   loads W consecutive elements, returns the terms
+//                               of the per-constraint block sums; idempotent
+//   B(ci, sum, con, acc)        run by ONE thread per weighting constraint; the
+//                               harness broadcasts con.d[] to the constraint's
+//                               elements
+//   C<W>(i, coef, elem, con, acc)  finishes the elements and stores
+#pragma once
+
+#include "pcu_common.cuh"
+
+struct DVars {  // device view of ParOptVars (IP.h:373-389)
+  double *x, *zl, *zu;               // N
+  double *zw, *sw, *tw, *zsw, *ztw;  // W
+};
+
+struct IPConst {
+  double mbv;     // max_bound_value
+  double kappa;   // rel_bound_barrier
+  double gamma;   // penalty_gamma: gamma_tw = gamma, gamma_sw = gamma for sparse
+                  // equalities and 0 for sparse inequalities (IP.cpp:357-374)
+  double dp;      // design_precision
+  double wconst;  // constant term of cw(x)
+  int use_lower, use_upper;
+  int nwineq;     // local number of sparse inequalities
+};
+
+__device__ __forceinline__ double gamma_sw(const IPConst &k, long long ci) {
+  return ci < k.nwineq ? 0.0 : k.gamma;
+}
+
+struct Con0 {  // no per-constraint data
+  static constexpr int ND = 0;
+  double d[1];
+  __device__ __forceinline__ void zero() {}
+};
+struct Con1 {  // one broadcast value
+  static constexpr int ND = 1;
+  double d[1];
+  __device__ __forceinline__ void zero() { d[0] = 0.0; }
+};
+
+// ============================================================== ResF
+// computeKKTRes (IP.cpp:1337-1446) + computeResNorm (IP.cpp:1588-1723) +
+// computeComp (IP.cpp:2742-2820) and, when has_step, addKKTResStep
+// (IP.cpp:1451-1583) with the quasi-Newton product expanded through the compact
+// form  B p = (b0 + sigma) p - sum_k kap_k Z_k.
+// Traffic: reads (6 + c)N [+ (3 + q)N with step], writes 3N; W: 5r [+5r] + 5w.
+// sums: 0 bound comp product, 1 comp count (bounds present + 2 per sparse
+//       constraint), 2 sparse comp product,
+//       3 norm-sum rx, 4 norm-sum rzw, 5..8 l1 of rsw,rtw,rzsw,rztw,
+//       9,10 norm-sum rzl, rzu;   maxima: 0 |rx|, 1 |rzw|, 2 dual parts
+struct ResF {
+  static constexpr int NS = 11, NX = 3, NM = 0, NB = 2;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // zw (+ pzw)
+  struct Elem {
+    double rx, rzl, rzu, cprod, ccount;
+  };
+  DVars v, r, p;
+  const double *lb, *ub, *g;
+  ColTable Acol;
+  CoefTable z;  // dense multipliers z_j (+ pz_j when has_step, added on host)
+  int ncon;
+  ColTable Z;
+  CoefTable kap;
+  int nq;
+  double b0sig;
+  double mu;
+  int has_step;
+  int norm_type;  // 0 infinity, 1 l1, 2 l2
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][2]) const {
+    double x[W], l[W], u[W], zl[W], zu[W], gv[W], rx[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = 0.0;
+    if (k.use_lower) ldv<W>(v.zl, i, zl);
+    if (k.use_upper) ldv<W>(v.zu, i, zu);
+#pragma unroll
+    for (int q = 0; q < W; q++) rx[q] = (zl[q] - zu[q]) - gv[q];
+    for (int j = 0; j < ncon; j++) {
+      double a[W];
+      ldv<W>(Acol.p[j], i, a);
+#pragma unroll
+      for (int q = 0; q < W; q++) rx[q] = fma(z.v[j], a[q], rx[q]);
+    }
+    double px[W], pzl[W], pzu[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) px[q] = pzl[q] = pzu[q] = 0.0;
+    if (has_step) {
+      ldv<W>(p.x, i, px);
+      if (k.use_lower) ldv<W>(p.zl, i, pzl);
+      if (k.use_upper) ldv<W>(p.zu, i, pzu);
+#pragma unroll
+      for (int q = 0; q < W; q++)
+        rx[q] = fma(-b0sig, px[q], rx[q]) + (pzl[q] - pzu[q]);
+      for (int j = 0; j < nq; j++) {
+        double zc[W];
+        ldv<W>(Z.p[j], i, zc);
+#pragma unroll
+        for (int q = 0; q < W; q++) rx[q] = fma(kap.v[j], zc[q], rx[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      const bool ml = k.use_lower && (l[q] > -k.mbv);
+      const bool mu_ = k.use_upper && (u[q] < k.mbv);
+      const double dl = x[q] - l[q], du = u[q] - x[q];
+      double rzl = 0.0, rzu = 0.0, cp = 0.0, cc = 0.0;
+      if (ml) {
+        rzl = -(dl * zl[q] - k.kappa * mu);
+        if (has_step) rzl -= (dl * pzl[q] + px[q] * zl[q]);
+        cp += zl[q] * dl;
+        cc += 1.0;
+      }
+      if (mu_) {
+        rzu = -(du * zu[q] - k.kappa * mu);
+        if (has_step) rzu -= (du * pzu[q] - px[q] * zu[q]);
+        cp += zu[q] * du;
+        cc += 1.0;
+      }
+      e[q].rx = rx[q];
+      e[q].rzl = rzl;
+      e[q].rzu = rzu;
+      e[q].cprod = cp;
+      e[q].ccount = cc;
+      part[q][0] = coef[q] * x[q];
+      part[q][1] = coef[q] * px[q];
+    }
+  }
+
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[2],
+                                    Con &con, AccT &acc) const {
+    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
+    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double gsw = gamma_sw(k, ci), gtw = k.gamma;
+    double rzw = -(((k.wconst + sum[0]) - sw) + tw);
+    double rsw = (zsw - gsw) - zw;
+    double rtw = (ztw - gtw) + zw;
+    double rzsw = mu - sw * zsw;
+    double rztw = mu - tw * ztw;
+    con.d[0] = zw;
+    if (has_step) {
+      const double pzw = p.zw[ci], psw = p.sw[ci], ptw = p.tw[ci];
+      const double pzsw = p.zsw[ci], pztw = p.ztw[ci];
+      rzw += (psw - sum[1]) - ptw;
+      rsw += pzsw - pzw;
+      rtw += pztw + pzw;
+      rzsw -= (psw * zsw + sw * pzsw);
+      rztw -= (ptw * ztw + tw * pztw);
+      con.d[0] += pzw;
+    }
+    r.zw[ci] = rzw;
+    r.sw[ci] = rsw;
+    r.tw[ci] = rtw;
+    r.zsw[ci] = rzsw;
+    r.ztw[ci] = rztw;
+    acc.s[2] += sw * zsw + tw * ztw;
+    acc.s[1] += 2.0;
+    acc.x[1] = fmax(acc.x[1], fabs(rzw));
+    acc.x[2] = fmax(acc.x[2], fmax(fmax(fabs(rsw), fabs(rtw)),
+                                   fmax(fabs(rzsw), fabs(rztw))));
+    if (norm_type == 1) {
+      acc.s[4] += fabs(rzw);
+    } else if (norm_type == 2) {
+      acc.s[4] = fma(rzw, rzw, acc.s[4]);
+    }
+    if (norm_type != 0) {
+      acc.s[5] += fabs(rsw);
+      acc.s[6] += fabs(rtw);
+      acc.s[7] += fabs(rzsw);
+      acc.s[8] += fabs(rztw);
+    }
+  }
+
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AccT &acc) const {
+    double rx[W], rzl[W], rzu[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      rx[q] = fma(coef[q], con.d[0], e[q].rx);  // + Aw^T (zw [+ pzw])
+      rzl[q] = e[q].rzl;
+      rzu[q] = e[q].rzu;
+      acc.s[0] += e[q].cprod;
+      acc.s[1] += e[q].ccount;
+      acc.x[0] = fmax(acc.x[0], fabs(rx[q]));
+      acc.x[2] = fmax(acc.x[2], fmax(fabs(rzl[q]), fabs(rzu[q])));
+      if (norm_type == 1) {
+        acc.s[3] += fabs(rx[q]);
+        acc.s[9] += fabs(rzl[q]);
+        acc.s[10] += fabs(rzu[q]);
+      } else if (norm_type == 2) {
+        acc.s[3] = fma(rx[q], rx[q], acc.s[3]);
+        acc.s[9] = fma(rzl[q], rzl[q], acc.s[9]);
+        acc.s[10] = fma(rzu[q], rzu[q], acc.s[10]);
+      }
+    }
+    stv<W>(r.x, i, rx);
+    if (k.use_lower) stv<W>(r.zl, i, rzl);
+    if (k.use_upper) stv<W>(r.zu, i, rzu);
+  }
+};
+
+// ============================================================== DiagF
+// setUpKKTDiagSystem, diagonal part (IP.cpp:1864-1927) + ParOptQuasiDefBlockMat
+// ::factor with nwblock = 1 (SM.cpp:41-115): Dinv and Cw = 1/(Cdiag + Aw Dinv
+// Aw^T).  identity != 0 gives the matrices of initLeastSquaresMultipliers
+// (IP.cpp:5418-5431): Dinv = 1, Cdiag = small.
+// Traffic: reads 5N + 4W, writes N + W.
+struct DiagF {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  DVars v;
+  const double *lb, *ub;
+  double *Dinv, *Cw;
+  double b0sig;
+  int identity;
+  double small_;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&)[W], double (&part)[W][1]) const {
+    double d[W];
+    if (identity) {
+#pragma unroll
+      for (int q = 0; q < W; q++) d[q] = 1.0;
+    } else {
+      double x[W], l[W], u[W], zl[W], zu[W];
+      ldv<W>(v.x, i, x);
+      ldv<W>(lb, i, l);
+      ldv<W>(ub, i, u);
+#pragma unroll
+      for (int q = 0; q < W; q++) zl[q] = zu[q] = 0.0;
+      if (k.use_lower) ldv<W>(v.zl, i, zl);
+      if (k.use_upper) ldv<W>(v.zu, i, zu);
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        double t = b0sig;
+        if (k.use_lower && l[q] > -k.mbv) t += zl[q] / (x[q] - l[q]);
+        if (k.use_upper && u[q] < k.mbv) t += zu[q] / (u[q] - x[q]);
+        d[q] = 1.0 / t;
+      }
+    }
+    stv<W>(Dinv, i, d);
+#pragma unroll
+    for (int q = 0; q < W; q++) part[q][0] = coef[q] * coef[q] * d[q];
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1], Con &,
+                                    AccT &) const {
+    double cdiag = small_;
+    if (!identity) cdiag = v.sw[ci] / v.zsw[ci] + v.tw[ci] / v.ztw[ci];
+    Cw[ci] = 1.0 / (cdiag + sum[0]);
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {}
+};
+
+// ============================================================== Pass1F
+// First half of solveKKTDiagSystem (IP.cpp:2091-2139): d1, d2 and the first
+// ParOptQuasiDefBlockMat::apply (SM.cpp:160-190), t1 = D0^-1 (d1, d2)|x.
+// Traffic: reads 7N + 10W, writes 2N + W.
+struct Pass1F {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // yw
+  struct Elem {
+    double d1, dinv;
+  };
+  DVars v, b;
+  const double *lb, *ub, *Dinv, *Cw;
+  double *d1, *d2, *t1;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1]) const {
+    double x[W], l[W], u[W], bx[W], bzl[W], bzu[W], di[W], d[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(b.x, i, bx);
+    ldv<W>(Dinv, i, di);
+#pragma unroll
+    for (int q = 0; q < W; q++) bzl[q] = bzu[q] = 0.0;
+    if (k.use_lower) ldv<W>(b.zl, i, bzl);
+    if (k.use_upper) ldv<W>(b.zu, i, bzu);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      double t = bx[q];
+      if (k.use_lower && l[q] > -k.mbv) t += bzl[q] / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv) t -= bzu[q] / (u[q] - x[q]);
+      d[q] = t;
+      e[q].d1 = t;
+      e[q].dinv = di[q];
+      part[q][0] = coef[q] * di[q] * t;
+    }
+    stv<W>(d1, i, d);
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
+                                    Con &con, AccT &) const {
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double dd = b.zw[ci] + (b.zsw[ci] + sw * b.sw[ci]) / zsw -
+                      (b.ztw[ci] + tw * b.tw[ci]) / ztw;
+    con.d[0] = Cw[ci] * (dd - sum[0]);
+    d2[ci] = dd;
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AccT &) const {
+    double t[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+    stv<W>(t1, i, t);
+  }
+};
+
+// ============================================================== Pass2F
+// Second half of solveKKTDiagSystem (IP.cpp:2165-2242) merged with the
+// Sherman-Morrison-Woodbury correction of computeKKTStep (IP.cpp:2716-2735):
+//   d1' = d1 + sum_j alpha_j V_j,  V = [A | Z]   (alpha from the small dense
+//   solves), (px, pzw) = D0^-1 (d1', d2), then the bound / slack multipliers.
+// accumulate != 0 adds the result to the step (update.add(refine), IP.cpp:4990).
+// Traffic: reads (9 + c + q)N + 10W, writes 3N + 5W (+3N + 5W reads when
+// accumulating).
+struct Pass2F {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // yw
+  struct Elem {
+    double d1, dinv;
+  };
+  DVars v, b, y;
+  const double *lb, *ub, *Dinv, *Cw, *d1, *d2;
+  ColTable V;
+  CoefTable alpha;
+  int ncols;
+  int accumulate;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1]) const {
+    double d[W], di[W];
+    ldv<W>(d1, i, d);
+    ldv<W>(Dinv, i, di);
+    for (int j = 0; j < ncols; j++) {
+      double c[W];
+      ldv<W>(V.p[j], i, c);
+#pragma unroll
+      for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j], c[q], d[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      e[q].d1 = d[q];
+      e[q].dinv = di[q];
+      part[q][0] = coef[q] * di[q] * d[q];
+    }
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
+                                    Con &con, AccT &) const {
+    const double yw = Cw[ci] * (d2[ci] - sum[0]);
+    con.d[0] = yw;
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double pzsw = yw - b.sw[ci];
+    const double pztw = -b.tw[ci] - yw;
+    const double psw = (b.zsw[ci] - sw * pzsw) / zsw;
+    const double ptw = (b.ztw[ci] - tw * pztw) / ztw;
+    if (accumulate) {
+      y.zw[ci] += yw;
+      y.zsw[ci] += pzsw;
+      y.ztw[ci] += pztw;
+      y.sw[ci] += psw;
+      y.tw[ci] += ptw;
+    } else {
+      y.zw[ci] = yw;
+      y.zsw[ci] = pzsw;
+      y.ztw[ci] = pztw;
+      y.sw[ci] = psw;
+      y.tw[ci] = ptw;
+    }
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AccT &) const {
+    double x[W], l[W], u[W], zl[W], zu[W], bzl[W], bzu[W];
+    double px[W], pzl[W], pzu[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
+    if (k.use_lower) {
+      ldv<W>(v.zl, i, zl);
+      ldv<W>(b.zl, i, bzl);
+    }
+    if (k.use_upper) {
+      ldv<W>(v.zu, i, zu);
+      ldv<W>(b.zu, i, bzu);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      px[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+      pzl[q] = 0.0;
+      pzu[q] = 0.0;
+      if (k.use_lower && l[q] > -k.mbv)
+        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv)
+        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+    }
+    if (accumulate) {
+      double o[W];
+      ldv<W>(y.x, i, o);
+#pragma unroll
+      for (int q = 0; q < W; q++) px[q] += o[q];
+      if (k.use_lower) {
+        ldv<W>(y.zl, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzl[q] += o[q];
+      }
+      if (k.use_upper) {
+        ldv<W>(y.zu, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzu[q] += o[q];
+      }
+    }
+    stv<W>(y.x, i, px);
+    if (k.use_lower) stv<W>(y.zl, i, pzl);
+    if (k.use_upper) stv<W>(y.zu, i, pzu);
+  }
+};
+
+// ============================================================== StatsF
+// One pass giving every reduction needed between the KKT step and the line
+// search: computeMaxStep (IP.cpp:2942-3103), computeCompStep (IP.cpp:2825-2923,
+// as the 4 coefficients of its bilinear form in (alpha_x, alpha_z)), and the
+// sums of evalMeritInitDeriv / evalInfeasDeriv (IP.cpp:3652-3790, 3465-3509).
+// Traffic: reads 9N + 8W.
+//   sums: 0-3 bound comp poly [1, ax, az, ax*az]; 4-7 sparse comp poly;
+//         8,9 pos/neg log (bounds); 10,11 pos/neg p/(.) (bounds);
+//         12,13 pos/neg log (sw,tw); 14,15 pos/neg p/(.) (sw,tw);
+//         16 g.p; 17 p.p; 18 gam.(sw,tw); 19 gam.(psw,ptw);
+//         20 |cw - sw + tw|^2; 21 (cw - sw + tw).(Aw p - psw + ptw)
+//   maxima: 0 |px|_inf;  mins: 0 max_x, 1 max_z
+struct StatsF {
+  static constexpr int NS = 22, NX = 1, NM = 2, NB = 2;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {
+    double c0, c1, c2, c3, lpos, lneg, ppos, pneg, gp, pp, mx, mz;
+  };
+  DVars v, p;
+  const double *lb, *ub, *g;
+  double tau;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][2]) const {
+    double x[W], l[W], u[W], zl[W], zu[W], px[W], pzl[W], pzu[W], gv[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(p.x, i, px);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = pzl[q] = pzu[q] = 0.0;
+    if (k.use_lower) {
+      ldv<W>(v.zl, i, zl);
+      ldv<W>(p.zl, i, pzl);
+    }
+    if (k.use_upper) {
+      ldv<W>(v.zu, i, zu);
+      ldv<W>(p.zu, i, pzu);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      Elem t;
+      t.c0 = t.c1 = t.c2 = t.c3 = 0.0;
+      t.lpos = t.lneg = t.ppos = t.pneg = 0.0;
+      t.mx = 1.0e300;
+      t.mz = 1.0e300;
+      const double dl = x[q] - l[q], du = u[q] - x[q];
+      if (k.use_lower) {
+        if (px[q] < 0.0) t.mx = fmin(t.mx, -tau * dl / px[q]);
+        if (pzl[q] < 0.0) t.mz = fmin(t.mz, -tau * zl[q] / pzl[q]);
+        if (l[q] > -k.mbv) {
+          t.c0 += zl[q] * dl;
+          t.c1 += zl[q] * px[q];
+          t.c2 += pzl[q] * dl;
+          t.c3 += pzl[q] * px[q];
+          const double lg = log(dl);
+          if (dl > 1.0) t.lpos += lg; else t.lneg += lg;
+          const double r = px[q] / dl;
+          if (px[q] > 0.0) t.ppos += r; else t.pneg += r;
+        }
+      }
+      if (k.use_upper) {
+        if (px[q] > 0.0) t.mx = fmin(t.mx, tau * du / px[q]);
+        if (pzu[q] < 0.0) t.mz = fmin(t.mz, -tau * zu[q] / pzu[q]);
+        if (u[q] < k.mbv) {
+          t.c0 += zu[q] * du;
+          t.c1 -= zu[q] * px[q];
+          t.c2 += pzu[q] * du;
+          t.c3 -= pzu[q] * px[q];
+          const double lg = log(du);
+          if (du > 1.0) t.lpos += lg; else t.lneg += lg;
+          const double r = px[q] / du;
+          if (px[q] > 0.0) t.pneg -= r; else t.ppos -= r;
+        }
+      }
+      t.gp = gv[q] * px[q];
+      t.pp = px[q] * px[q];
+      e[q] = t;
+      part[q][0] = coef[q] * x[q];
+      part[q][1] = coef[q] * px[q];
+    }
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
+                                    AccT &acc) const {
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double psw = p.sw[ci], ptw = p.tw[ci], pzsw = p.zsw[ci],
+                 pztw = p.ztw[ci];
+    if (psw < 0.0) acc.m[0] = fmin(acc.m[0], -tau * sw / psw);
+    if (ptw < 0.0) acc.m[0] = fmin(acc.m[0], -tau * tw / ptw);
+    if (pzsw < 0.0) acc.m[1] = fmin(acc.m[1], -tau * zsw / pzsw);
+    if (pztw < 0.0) acc.m[1] = fmin(acc.m[1], -tau * ztw / pztw);
+    acc.s[4] += sw * zsw + tw * ztw;
+    acc.s[5] += psw * zsw + ptw * ztw;
+    acc.s[6] += sw * pzsw + tw * pztw;
+    acc.s[7] += psw * pzsw + ptw * pztw;
+    const double ls = log(sw), lt = log(tw);
+    if (sw > 1.0) acc.s[12] += ls; else acc.s[13] += ls;
+    if (tw > 1.0) acc.s[12] += lt; else acc.s[13] += lt;
+    const double rs = psw / sw, rt = ptw / tw;
+    if (psw > 0.0) acc.s[14] += rs; else acc.s[15] += rs;
+    if (ptw > 0.0) acc.s[14] += rt; else acc.s[15] += rt;
+    const double gsw = gamma_sw(k, ci), gtw = k.gamma;
+    acc.s[18] += gsw * sw + gtw * tw;
+    acc.s[19] += gsw * psw + gtw * ptw;
+    const double rw1 = ((k.wconst + sum[0]) - sw) + tw;
+    const double rw2 = (sum[1] - psw) + ptw;
+    acc.s[20] = fma(rw1, rw1, acc.s[20]);
+    acc.s[21] = fma(rw1, rw2, acc.s[21]);
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long, const double (&)[W],
+                                    const Elem (&e)[W], const Con &,
+                                    AccT &acc) const {
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      acc.s[0] += e[q].c0;
+      acc.s[1] += e[q].c1;
+      acc.s[2] += e[q].c2;
+      acc.s[3] += e[q].c3;
+      acc.s[8] += e[q].lpos;
+      acc.s[9] += e[q].lneg;
+      acc.s[10] += e[q].ppos;
+      acc.s[11] += e[q].pneg;
+      acc.s[16] += e[q].gp;
+      acc.s[17] += e[q].pp;
+      acc.x[0] = fmax(acc.x[0], sqrt(e[q].pp));
+      acc.m[0] = fmin(acc.m[0], e[q].mx);
+      acc.m[1] = fmin(acc.m[1], e[q].mz);
+    }
+  }
+};
+
+// ============================================================== TrialF
+// Line-search trial point (IP.cpp:3997-4013: rx, rsw, rtw via computeStepVec)
+// fused with the reductions of evalMeritFunc / evalInfeas (IP.cpp:3524-3601,
+// 3438-3460) at that point.  ax = alpha * alpha_x (the step is kept unscaled).
+// Traffic: reads 4N + 4W, writes N + 2W.
+//   sums: 0,1 pos/neg log (bounds); 2,3 pos/neg log (sw,tw); 4 gam.(rsw,rtw);
+//         5 |cw(rx) - rsw + rtw|^2
+struct TrialF {
+  static constexpr int NS = 6, NX = 0, NM = 0, NB = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {
+    double lpos, lneg;
+  };
+  DVars v, p;
+  const double *lb, *ub;
+  double *rx, *rsw, *rtw;
+  double ax;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1]) const {
+    double x[W], l[W], u[W], px[W], r[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(p.x, i, px);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      r[q] = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
+      double lp = 0.0, ln = 0.0;
+      if (k.use_lower && l[q] > -k.mbv) {
+        const double d = r[q] - l[q], lg = log(d);
+        if (d > 1.0) lp += lg; else ln += lg;
+      }
+      if (k.use_upper && u[q] < k.mbv) {
+        const double d = u[q] - r[q], lg = log(d);
+        if (d > 1.0) lp += lg; else ln += lg;
+      }
+      e[q].lpos = lp;
+      e[q].lneg = ln;
+      part[q][0] = coef[q] * r[q];
+    }
+    stv<W>(rx, i, r);
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1], Con &,
+                                    AccT &acc) const {
+    const double s = step_clip0(v.sw[ci], ax, p.sw[ci], k.dp);
+    const double t = step_clip0(v.tw[ci], ax, p.tw[ci], k.dp);
+    rsw[ci] = s;
+    rtw[ci] = t;
+    const double ls = log(s), lt = log(t);
+    if (s > 1.0) acc.s[2] += ls; else acc.s[3] += ls;
+    if (t > 1.0) acc.s[2] += lt; else acc.s[3] += lt;
+    acc.s[4] += gamma_sw(k, ci) * s + k.gamma * t;
+    const double rw = ((k.wconst + sum[0]) - s) + t;
+    acc.s[5] = fma(rw, rw, acc.s[5]);
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long, const double (&)[W],
+                                    const Elem (&e)[W], const Con &,
+                                    AccT &acc) const {
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      acc.s[0] += e[q].lpos;
+      acc.s[1] += e[q].lneg;
+    }
+  }
+};
+
+// ============================================================== Update1F
+// computeStepAndUpdate, first half (IP.cpp:4178-4216): every variable takes its
+// step (ax = alpha*alpha_x for primal, az = alpha*alpha_z for dual parts) and
+// y_qn = -g + sum_j z_j A_j + Aw^T zw with the NEW multipliers and the OLD
+// gradients.  Traffic: reads (6 + c)N + 10W, writes 4N + 5W.
+struct Update1F {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // new zw
+  struct Elem {};
+  DVars v, p;
+  const double *lb, *ub, *g;
+  ColTable Acol;
+  CoefTable z;  // NEW dense multipliers
+  int ncon;
+  double *yqn;  // null when no quasi-Newton pair is formed
+  double ax, az;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &con,
+                                    AccT &) const {
+    const double zwn = fma(az, p.zw[ci], v.zw[ci]);  // no clipping (IP.cpp:4181)
+    con.d[0] = zwn;
+    v.zw[ci] = zwn;
+    v.sw[ci] = step_clip0(v.sw[ci], ax, p.sw[ci], k.dp);
+    v.tw[ci] = step_clip0(v.tw[ci], ax, p.tw[ci], k.dp);
+    v.zsw[ci] = step_clip0(v.zsw[ci], az, p.zsw[ci], k.dp);
+    v.ztw[ci] = step_clip0(v.ztw[ci], az, p.ztw[ci], k.dp);
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&)[W], const Con &con,
+                                    AccT &) const {
+    double x[W], l[W], u[W], px[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(p.x, i, px);
+    if (k.use_lower) {
+      double zl[W], pzl[W];
+      ldv<W>(v.zl, i, zl);
+      ldv<W>(p.zl, i, pzl);
+#pragma unroll
+      for (int q = 0; q < W; q++) zl[q] = step_clip0(zl[q], az, pzl[q], k.dp);
+      stv<W>(v.zl, i, zl);
+    }
+    if (k.use_upper) {
+      double zu[W], pzu[W];
+      ldv<W>(v.zu, i, zu);
+      ldv<W>(p.zu, i, pzu);
+#pragma unroll
+      for (int q = 0; q < W; q++) zu[q] = step_clip0(zu[q], az, pzu[q], k.dp);
+      stv<W>(v.zu, i, zu);
+    }
+    if (yqn) {
+      double gv[W], yv[W];
+      ldv<W>(g, i, gv);
+#pragma unroll
+      for (int q = 0; q < W; q++) yv[q] = -gv[q];
+      for (int j = 0; j < ncon; j++) {
+        double a[W];
+        ldv<W>(Acol.p[j], i, a);
+#pragma unroll
+        for (int q = 0; q < W; q++) yv[q] = fma(z.v[j], a[q], yv[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < W; q++) yv[q] = fma(coef[q], con.d[0], yv[q]);
+      stv<W>(yqn, i, yv);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++)
+      x[q] = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
+    stv<W>(v.x, i, x);
+  }
+};
+
+// ============================================================== Update2F
+// computeStepAndUpdate, second half (IP.cpp:4244-4256) after the new gradients:
+//   s_qn = ax * px,  y_qn += g - sum_j z_j A_j - Aw^T zw
+// fused with the three dot products that open ParOptLBFGS::update /
+// ParOptLSR1::update (QN.cpp:168-170, 641-642).
+// Traffic: reads (3 + c)N + W, writes 2N.   sums: 0 y.y, 1 y.s, 2 s.s
+struct Update2F {
+  static constexpr int NS = 3, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // zw
+  struct Elem {};
+  const double *zw, *px, *g;
+  ColTable Acol;
+  CoefTable z;
+  int ncon;
+  double *yqn, *sqn;
+  double ax;
+
+  template <int W>
+  __device__ __forceinline__ void A_unused() const {}
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &con,
+                                    AccT &) const {
+    con.d[0] = zw[ci];
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&)[W], const Con &con,
+                                    AccT &acc) const {
+    double yv[W], gv[W], pv[W], sv[W];
+    ldv<W>(yqn, i, yv);
+    ldv<W>(g, i, gv);
+    ldv<W>(px, i, pv);
+#pragma unroll
+    for (int q = 0; q < W; q++) yv[q] += gv[q];
+    for (int j = 0; j < ncon; j++) {
+      double a[W];
+      ldv<W>(Acol.p[j], i, a);
+#pragma unroll
+      for (int q = 0; q < W; q++) yv[q] = fma(-z.v[j], a[q], yv[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      yv[q] = fma(-coef[q], con.d[0], yv[q]);
+      sv[q] = ax * pv[q];
+      acc.s[0] = fma(yv[q], yv[q], acc.s[0]);
+      acc.s[1] = fma(yv[q], sv[q], acc.s[1]);
+      acc.s[2] = fma(sv[q], sv[q], acc.s[2]);
+    }
+    stv<W>(yqn, i, yv);
+    stv<W>(sqn, i, sv);
+  }
+};
+
+// ============================================================== LinCombF
+// out = beta * x + sum_j alpha_j V_j   (ParOptLBFGS::mult, QN.cpp:390-418, second
+// pass; ParOptLSR1's Z_i = Y_i - b0 S_i, QN.cpp:730-735; damped-update vector).
+// Traffic: reads (1 + ncols)N, writes N.
+struct LinCombF {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  const double *x;
+  double beta;
+  ColTable V;
+  CoefTable alpha;
+  int ncols;
+  double *out;
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
+                                    AccT &) const {}
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {
+    double o[W];
+    if (x) {
+      ldv<W>(x, i, o);
+#pragma unroll
+      for (int q = 0; q < W; q++) o[q] *= beta;
+    } else {
+#pragma unroll
+      for (int q = 0; q < W; q++) o[q] = 0.0;
+    }
+    for (int j = 0; j < ncols; j++) {
+      double c[W];
+      ldv<W>(V.p[j], i, c);
+#pragma unroll
+      for (int q = 0; q < W; q++) o[q] = fma(alpha.v[j], c[q], o[q]);
+    }
+    stv<W>(out, i, o);
+  }
+};

@@ -1,0 +1,25 @@
+// pcu_problem.cuh -- the problem object behind pcu_problem (ParOptProblem).
+#pragma once
+
+#include <vector>
+
+#include "pcu_ctx.cuh"
+
+struct pcu_problem {
+  pcu_ctx *ctx = nullptr;
+  int nvars = 0, ncon = 0, nwcon = 0;
+  int ninequality = 0, nwinequality = 0;
+  int use_lower = 1, use_upper = 1;
+  pcu_weighting weighting;
+  double callback_ms = 0.0;  // device time inside the callbacks
+  cudaEvent_t cb0 = nullptr, cb1 = nullptr;
+  bool time_callbacks = true;
+
+  virtual ~pcu_problem() {}
+  virtual int getVarsAndBounds(pcu_vec *x, pcu_vec *lb, pcu_vec *ub) = 0;
+  // fobj / cons are host outputs (the reference's signature, ParOptProblem.h:157)
+  virtual int evalObjCon(pcu_vec *x, double *fobj, double *cons) = 0;
+  virtual int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) = 0;
+};
+
+WDesc pcu_make_wdesc(const pcu_weighting &w, int nvars);

@@ -1,0 +1,578 @@
+// pcu_vec.cu -- context implementation and the ParOptVec kernels
+// (reference: src/ParOptVec.cpp:15-217; one fused, deterministic kernel per
+// BLAS-1 call + MPI_Allreduce pair of the reference).
+#include <dlfcn.h>
+#include <string.h>
+
+#include "pcu_ctx.cuh"
+
+// ------------------------------------------------------------------ NCCL api
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+      api.GetErrorString =
+          (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce &&
+               api.AllGather;
+    }
+  }
+  return api;
+}
+
+#define PCU_NCCL_OK(call)                                                     \
+  do {                                                                        \
+    ncclResult_t r__ = (call);                                                \
+    if (r__ != ncclSuccess) {                                                 \
+      fprintf(stderr, "paropt_b200: NCCL error %d at %s:%d\n", (int)r__,      \
+              __FILE__, __LINE__);                                            \
+      return 1;                                                               \
+    }                                                                         \
+  } while (0)
+
+// Combine the per-rank copies of the small reduction buffer: slot i of rank r
+// sits at gather[r * stride + i]; ops by range [0,ns) sum, [ns,ns+nx) max, rest
+// min, for each pending descriptor.  Fixed rank order -> identical on all ranks.
+struct CombineDesc {
+  int n;
+  int off[32], ns[32], nx[32], nm[32];
+};
+__global__ void combine_ranks_kernel(const double *gather, double *result,
+                                     int world, int stride, CombineDesc d) {
+  for (int k = 0; k < d.n; k++) {
+    const int nr = d.ns[k] + d.nx[k] + d.nm[k];
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+      const int idx = d.off[k] + i;
+      double v = gather[idx];
+      for (int r = 1; r < world; r++) {
+        const double p = gather[(size_t)r * stride + idx];
+        if (i < d.ns[k]) v += p;
+        else if (i < d.ns[k] + d.nx[k]) v = fmax(v, p);
+        else v = fmin(v, p);
+      }
+      result[idx] = v;
+    }
+  }
+}
+
+RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
+  RedBuf rb;
+  rb.partials = d_partials;
+  rb.counter = d_counter;
+  const int nr = ns + nx + nm;
+  if (result_used + nr > PCU_RESULT_CAP || pending.size() >= 32) {
+    fprintf(stderr, "paropt_b200: reduction slots exhausted\n");
+    result_used = 0;
+    pending.clear();
+  }
+  rb.result = d_result + result_used;
+  pending.push_back({result_used, ns, nx, nm});
+  result_used += nr;
+  return rb;
+}
+
+int pcu_ctx::fetch(double *out) {
+  const int total = result_used;
+  if (total > 0) {
+    if (world > 1) {
+      NcclApi &api = nccl_api();
+      PCU_NCCL_OK(api.AllGather(d_result, d_gather, PCU_RESULT_CAP, ncclFloat64,
+                                comm, stream));
+      CombineDesc d;
+      d.n = (int)pending.size();
+      for (int k = 0; k < d.n; k++) {
+        d.off[k] = pending[k].offset;
+        d.ns[k] = pending[k].ns;
+        d.nx[k] = pending[k].nx;
+        d.nm[k] = pending[k].nm;
+      }
+      combine_ranks_kernel<<<1, 128, 0, stream>>>(d_gather, d_result, world,
+                                                  PCU_RESULT_CAP, d);
+      launches++;
+    }
+    PCU_CUDA_OK(cudaMemcpyAsync(h_result, d_result, total * sizeof(double),
+                                cudaMemcpyDeviceToHost, stream));
+  }
+  PCU_CUDA_OK(cudaStreamSynchronize(stream));
+  if (out && total > 0) memcpy(out, h_result, total * sizeof(double));
+  result_used = 0;
+  pending.clear();
+  return 0;
+}
+
+int pcu_ctx::big_reserve(size_t nresult, size_t npartials) {
+  if (nresult > big_cap) {
+    if (d_big) cudaFree(d_big);
+    if (h_big) cudaFreeHost(h_big);
+    big_cap = nresult * 2;
+    PCU_CUDA_OK(cudaMalloc(&d_big, big_cap * sizeof(double)));
+    PCU_CUDA_OK(cudaMallocHost(&h_big, big_cap * sizeof(double)));
+  }
+  if (npartials > big_partials_cap) {
+    if (d_big_partials) cudaFree(d_big_partials);
+    big_partials_cap = npartials * 2;
+    PCU_CUDA_OK(cudaMalloc(&d_big_partials, big_partials_cap * sizeof(double)));
+  }
+  return 0;
+}
+
+int pcu_ctx::big_fetch(size_t n, double *out) {
+  if (world > 1 && n > 0) {
+    PCU_NCCL_OK(nccl_api().AllReduce(d_big, d_big, n, ncclFloat64, ncclSum, comm,
+                                     stream));
+  }
+  if (n > 0) {
+    PCU_CUDA_OK(cudaMemcpyAsync(h_big, d_big, n * sizeof(double),
+                                cudaMemcpyDeviceToHost, stream));
+  }
+  PCU_CUDA_OK(cudaStreamSynchronize(stream));
+  if (out && n > 0) memcpy(out, h_big, n * sizeof(double));
+  return 0;
+}
+
+// ------------------------------------------------------------- C ABI: context
+extern "C" {
+
+const char *pcu_version(void) { return "paropt_b200 0.1 (sm_100a)"; }
+
+pcu_ctx *pcu_ctx_create(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr,
+            "paropt_b200: no CUDA device available (there is no CPU path)\n");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fprintf(stderr, "paropt_b200: cannot select CUDA device %d\n", device);
+    return nullptr;
+  }
+  pcu_ctx *ctx = new pcu_ctx;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  ctx->grid = prop.multiProcessorCount * 4;
+  if (ctx->grid > PCU_MAX_BLOCKS) ctx->grid = PCU_MAX_BLOCKS;
+  bool ok = true;
+  ok &= cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok &= cudaMalloc(&ctx->d_partials, sizeof(double) * PCU_MAX_BLOCKS * PCU_MAX_RED) == cudaSuccess;
+  ok &= cudaMalloc(&ctx->d_counter, 64) == cudaSuccess;
+  ok &= cudaMalloc(&ctx->d_result, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
+  ok &= cudaMallocHost(&ctx->h_result, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
+  ok &= cudaMemset(ctx->d_counter, 0, 64) == cudaSuccess;
+  ok &= cudaMemset(ctx->d_result, 0, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
+  ok &= cudaEventCreate(&ctx->ev0) == cudaSuccess;
+  ok &= cudaEventCreate(&ctx->ev1) == cudaSuccess;
+  ok &= cudaDeviceSynchronize() == cudaSuccess;
+  if (!ok) {
+    fprintf(stderr, "paropt_b200: context allocation failed: %s\n",
+            cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return nullptr;
+  }
+  return ctx;
+}
+
+void pcu_ctx_destroy(pcu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
+  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_counter);
+  cudaFree(ctx->d_result);
+  cudaFreeHost(ctx->h_result);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->d_big) cudaFree(ctx->d_big);
+  if (ctx->h_big) cudaFreeHost(ctx->h_big);
+  if (ctx->d_big_partials) cudaFree(ctx->d_big_partials);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int pcu_nccl_unique_id(unsigned char id128[128]) {
+  NcclApi &api = nccl_api();
+  if (!api.ok) {
+    fprintf(stderr, "paropt_b200: libnccl.so.2 not found\n");
+    return 1;
+  }
+  ncclUniqueId id;
+  PCU_NCCL_OK(api.GetUniqueId(&id));
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+int pcu_ctx_init_comm(pcu_ctx *ctx, const unsigned char id128[128], int rank,
+                      int world_size) {
+  if (world_size <= 1) {
+    ctx->rank = 0;
+    ctx->world = 1;
+    return 0;
+  }
+  NcclApi &api = nccl_api();
+  if (!api.ok) {
+    fprintf(stderr, "paropt_b200: libnccl.so.2 not found\n");
+    return 1;
+  }
+  PCU_CUDA_OK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(id.internal, id128, 128);
+  PCU_NCCL_OK(api.CommInitRank(&ctx->comm, world_size, id, rank));
+  ctx->rank = rank;
+  ctx->world = world_size;
+  PCU_CUDA_OK(cudaMalloc(&ctx->d_gather,
+                         sizeof(double) * PCU_RESULT_CAP * world_size));
+  return 0;
+}
+
+int pcu_ctx_rank(pcu_ctx *ctx) { return ctx->rank; }
+int pcu_ctx_size(pcu_ctx *ctx) { return ctx->world; }
+int pcu_ctx_sync(pcu_ctx *ctx) {
+  PCU_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+void *pcu_ctx_stream(pcu_ctx *ctx) { return (void *)ctx->stream; }
+int64_t pcu_ctx_kernel_launches(pcu_ctx *ctx) { return ctx->launches; }
+int pcu_ctx_timer_start(pcu_ctx *ctx) {
+  PCU_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+int pcu_ctx_timer_stop(pcu_ctx *ctx, double *ms) {
+  PCU_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+  PCU_CUDA_OK(cudaEventSynchronize(ctx->ev1));
+  float f = 0.f;
+  PCU_CUDA_OK(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = (double)f;
+  return 0;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------- vec kernels
+struct NoElem {};
+struct NoCon {
+  static constexpr int ND = 0;
+  double d[1];
+  __device__ __forceinline__ void zero() {}
+};
+
+// y = alpha  |  y *= alpha  |  y += alpha * x      (ParOptVec.cpp:32,177,194)
+struct VecOpF {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef NoElem Elem;
+  typedef NoCon Con;
+  int op;  // 0 set, 1 scale, 2 axpy
+  double alpha;
+  double *y;
+  const double *x;
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
+                                    AccT &) const {}
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {
+    double out[W];
+    if (op == 0) {
+#pragma unroll
+      for (int e = 0; e < W; e++) out[e] = alpha;
+    } else if (op == 1) {
+      ldv<W>(y, i, out);
+#pragma unroll
+      for (int e = 0; e < W; e++) out[e] *= alpha;
+    } else {
+      double xv[W];
+      ldv<W>(y, i, out);
+      ldv<W>(x, i, xv);
+#pragma unroll
+      for (int e = 0; e < W; e++) out[e] = fma(alpha, xv[e], out[e]);
+    }
+    stv<W>(y, i, out);
+  }
+};
+
+// sum x*y, sum x^2, sum |x|, max |x| in one pass (ParOptVec.cpp:63-143)
+struct VecRedF {
+  static constexpr int NS = 3, NX = 1, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef NoElem Elem;
+  typedef NoCon Con;
+  const double *x, *y;
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1]) const {}
+  __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
+                                    AccT &) const {}
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &acc) const {
+    double xv[W], yv[W];
+    ldv<W>(x, i, xv);
+    if (y) {
+      ldv<W>(y, i, yv);
+    } else {
+#pragma unroll
+      for (int e = 0; e < W; e++) yv[e] = 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < W; e++) {
+      acc.s[0] = fma(xv[e], yv[e], acc.s[0]);
+      acc.s[1] = fma(xv[e], xv[e], acc.s[1]);
+      acc.s[2] += fabs(xv[e]);
+      acc.x[0] = fmax(acc.x[0], fabs(xv[e]));
+    }
+  }
+};
+
+// Multi-vector dot: out[k] = sum_i x[i] * V_k[i] for up to KC vectors per pass
+// over x (the reference re-reads x once per vector, ParOptVec.cpp:152-167).
+template <int KC>
+__global__ void __launch_bounds__(PCU_THREADS)
+    mdot_kernel(const double *__restrict__ x, ColTable cols, int col0, int ncols,
+                long long n, double *partials, unsigned int *counter,
+                double *result) {
+  double acc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; k++) acc[k] = 0.0;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long nvec = n / 2;
+  for (long long v = tid; v < nvec; v += nthreads) {
+    const double2 xv = *reinterpret_cast<const double2 *>(x + 2 * v);
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+      if (k < ncols) {
+        const double2 c =
+            *reinterpret_cast<const double2 *>(cols.p[col0 + k] + 2 * v);
+        acc[k] = fma(xv.x, c.x, acc[k]);
+        acc[k] = fma(xv.y, c.y, acc[k]);
+      }
+    }
+  }
+  if ((n & 1) && tid == 0) {
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+      if (k < ncols) acc[k] = fma(x[n - 1], cols.p[col0 + k][n - 1], acc[k]);
+    }
+  }
+  // block reduce
+  __shared__ double sm[PCU_THREADS / 32][KC];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KC; k++) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
+    if (lane == 0) sm[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < KC) {
+    double v = 0.0;
+    for (int w = 0; w < PCU_THREADS / 32; w++) v += sm[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * KC + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int k = warp; k < ncols; k += PCU_THREADS / 32) {
+      double v = 0.0;
+      for (unsigned int b = lane; b < gridDim.x; b += 32)
+        v += partials[(size_t)b * KC + k];
+      for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
+      if (lane == 0) result[col0 + k] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// Enqueue out[k] = x . cols[k], k < ncols, into ctx->d_big[dst_off + k].
+int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
+                     int ncols, long long n, int dst_off) {
+  constexpr int KC = 8;
+  if (ctx->big_reserve(dst_off + ncols + 8, (size_t)PCU_MAX_BLOCKS * KC)) return 1;
+  const int grid = pcu_grid_for(ctx, n);
+  for (int c0 = 0; c0 < ncols; c0 += KC) {
+    const int nc = (ncols - c0 < KC) ? ncols - c0 : KC;
+    mdot_kernel<KC><<<grid, PCU_THREADS, 0, ctx->stream>>>(
+        x, cols, c0, nc, n, ctx->d_big_partials, ctx->d_counter,
+        ctx->d_big + dst_off);
+    ctx->launches++;
+  }
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <class F>
+static int launch_plain(pcu_ctx *ctx, const F &f, long long n, RedBuf rb) {
+  WDesc w;
+  memset(&w, 0, sizeof(w));
+  const int grid = pcu_grid_for(ctx, n);
+  tile_kernel<F><<<grid, PCU_THREADS, 0, ctx->stream>>>(f, n, w, rb);
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int vec_reduce(pcu_vec *x, pcu_vec *y, double out[4]) {
+  pcu_ctx *ctx = x->ctx;
+  VecRedF f;
+  f.x = x->d;
+  f.y = y ? y->d : nullptr;
+  RedBuf rb = ctx->redbuf(3, 1, 0);
+  if (launch_plain(ctx, f, x->n, rb)) return 1;
+  return ctx->fetch(out);
+}
+
+extern "C" {
+
+pcu_vec *pcu_vec_create(pcu_ctx *ctx, int n) {
+  if (!ctx || n < 0) return nullptr;
+  pcu_vec *v = new pcu_vec;
+  v->ctx = ctx;
+  v->n = n;
+  size_t bytes = ((size_t)n + 2) * sizeof(double);
+  if (cudaMalloc(&v->d, bytes) != cudaSuccess) {
+    fprintf(stderr, "paropt_b200: cudaMalloc of %zu bytes failed\n", bytes);
+    delete v;
+    return nullptr;
+  }
+  cudaMemsetAsync(v->d, 0, bytes, ctx->stream);
+  return v;
+}
+
+void pcu_vec_destroy(pcu_vec *v) {
+  if (!v) return;
+  if (v->owns && v->d) {
+    cudaStreamSynchronize(v->ctx->stream);
+    cudaFree(v->d);
+  }
+  delete v;
+}
+
+int pcu_vec_size(pcu_vec *v) { return v->n; }
+
+int pcu_vec_set(pcu_vec *v, double alpha) {
+  VecOpF f;
+  f.op = 0;
+  f.alpha = alpha;
+  f.y = v->d;
+  f.x = nullptr;
+  RedBuf rb = {nullptr, nullptr, nullptr};
+  return launch_plain(v->ctx, f, v->n, rb);
+}
+
+int pcu_vec_zero(pcu_vec *v) {
+  PCU_CUDA_OK(cudaMemsetAsync(v->d, 0, (size_t)v->n * sizeof(double),
+                              v->ctx->stream));
+  return 0;
+}
+
+int pcu_vec_copy(pcu_vec *dst, pcu_vec *src) {
+  // a mismatched vector is silently ignored in the reference
+  // (ParOptVec.cpp:51-55); here a size mismatch is an error
+  if (!src || src->n != dst->n) return 1;
+  PCU_CUDA_OK(cudaMemcpyAsync(dst->d, src->d, (size_t)dst->n * sizeof(double),
+                              cudaMemcpyDeviceToDevice, dst->ctx->stream));
+  return 0;
+}
+
+int pcu_vec_norm(pcu_vec *v, double *out) {
+  double r[4];
+  if (vec_reduce(v, nullptr, r)) return 1;
+  *out = sqrt(r[1]);
+  return 0;
+}
+
+int pcu_vec_maxabs(pcu_vec *v, double *out) {
+  double r[4];
+  if (vec_reduce(v, nullptr, r)) return 1;
+  *out = r[3];
+  return 0;
+}
+
+int pcu_vec_l1norm(pcu_vec *v, double *out) {
+  double r[4];
+  if (vec_reduce(v, nullptr, r)) return 1;
+  *out = r[2];
+  return 0;
+}
+
+int pcu_vec_dot(pcu_vec *x, pcu_vec *y, double *out) {
+  if (!y || y->n != x->n) return 1;
+  double r[4];
+  if (vec_reduce(x, y, r)) return 1;
+  *out = r[0];
+  return 0;
+}
+
+int pcu_vec_mdot(pcu_vec *x, pcu_vec **vecs, int nvecs, double *out) {
+  if (nvecs > PCU_MAX_COLS) return 1;
+  ColTable cols;
+  for (int k = 0; k < nvecs; k++) {
+    if (!vecs[k] || vecs[k]->n != x->n) return 1;
+    cols.p[k] = vecs[k]->d;
+  }
+  if (pcu_mdot_enqueue(x->ctx, x->d, cols, nvecs, x->n, 0)) return 1;
+  return x->ctx->big_fetch(nvecs, out);
+}
+
+int pcu_vec_scale(pcu_vec *v, double alpha) {
+  VecOpF f;
+  f.op = 1;
+  f.alpha = alpha;
+  f.y = v->d;
+  f.x = nullptr;
+  RedBuf rb = {nullptr, nullptr, nullptr};
+  return launch_plain(v->ctx, f, v->n, rb);
+}
+
+int pcu_vec_axpy(pcu_vec *y, double alpha, pcu_vec *x) {
+  if (!x || x->n != y->n) return 1;
+  VecOpF f;
+  f.op = 2;
+  f.alpha = alpha;
+  f.y = y->d;
+  f.x = x->d;
+  RedBuf rb = {nullptr, nullptr, nullptr};
+  return launch_plain(y->ctx, f, y->n, rb);
+}
+
+double *pcu_vec_device_ptr(pcu_vec *v) { return v->d; }
+
+int pcu_vec_to_host(pcu_vec *v, double *host, int n) {
+  if (n > v->n) return 1;
+  PCU_CUDA_OK(cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double),
+                              cudaMemcpyDeviceToHost, v->ctx->stream));
+  PCU_CUDA_OK(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+int pcu_vec_from_host(pcu_vec *v, const double *host, int n) {
+  if (n > v->n) return 1;
+  PCU_CUDA_OK(cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double),
+                              cudaMemcpyHostToDevice, v->ctx->stream));
+  PCU_CUDA_OK(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+}  // extern "C"

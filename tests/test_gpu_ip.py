@@ -1,0 +1,60 @@
+"""GPU parity: the CUDA interior-point core (through the C ABI) against
+ (a) histories of the unmodified reference (tests/golden, oracle/_ref), and
+ (b) the numpy oracle run here on the same seeded inputs.
+Tolerances: tests/parity.py (RTOL = 1e-10)."""
+import numpy as np
+import pytest
+
+from tests.parity import compare_histories, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from paropt_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def run_gpu(ctx, cfg, max_iters=None, history_level=2):
+    from paropt_b200.api import InteriorPoint, problem_from_config
+    prob = problem_from_config(ctx, cfg)
+    opts = dict(cfg["options"])
+    opts["history_level"] = history_level
+    if max_iters is not None:
+        opts["max_major_iters"] = max_iters
+    ip = InteriorPoint(prob, opts)
+    ip.optimize()
+    out = dict(history=ip.history(), status=ip.status(), counters=ip.counters(),
+               launches=ctx.kernel_launches())
+    ip.free()
+    prob.free()
+    return out
+
+
+@pytest.mark.parametrize("name", ["C1_small", "C2_small"])
+def test_full_history_matches_reference(ctx, name):
+    gold = load_golden(name)
+    out = run_gpu(ctx, gold["config"])
+    n, worst, first = compare_histories(gold["history"], out["history"])
+    assert first is None, (first, worst)
+    assert n == len(gold["history"])
+    niter, neval, ngeval = out["counters"]
+    assert niter == gold["final"]["niter"]
+    assert neval == gold["final"]["neval"]
+    assert ngeval == gold["final"]["ngeval"]
+    assert out["status"] == gold["status"]
+    for row, rec in zip(gold["log"], out["history"]):
+        assert row["info"] == rec["info"], (row, rec["iter"])
+    assert out["launches"] > 0
+
+
+@pytest.mark.parametrize("name,iters", [("C3_small", 50), ("C4_small", 9)])
+def test_prefix_history_matches_reference(ctx, name, iters):
+    gold = load_golden(name)
+    out = run_gpu(ctx, gold["config"], max_iters=iters + 1)
+    n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters)
+    assert n == iters
+    assert first is None, (first, worst)
