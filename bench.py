@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- interior-point iterations/s and KKT-solve ms at n = 64M (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config C3] [--n NTOTAL]
+
+A "step" is one pass of the interior-point major loop (IP.cpp:4607-5329) on the
+named synthetic workload (default: configs[2] of BASELINE.json -- multi-material
+topology-style problem, n = 64M, nwcon = 8M, 1 dense constraint, L-BFGS m = 10).
+Multi-GPU runs shard the design vector exactly as the reference shards it over
+MPI ranks (strong scaling: the global n stays 64M).
+
+Prints ONE JSON line (rank 0).  Extra keys: `roofline` (dominant kernel, measured
+live with CUDA events on the launching stream), `cpu_baseline` (the unmodified
+reference compiled in oracle/_ref, timed on a bounded sample on the host cores),
+`e2e` (same metric through the host-callback API: the iterate goes device->host
+and the gradients host->device through pinned buffers on every callback),
+`kkt_solve_ms`, `iter_roofline_frac`, `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from paropt_b200 import configs  # noqa: E402
+
+METRIC = "interior_point_iterations_per_sec"
+UNIT = "iterations/s"
+QN_WARMUP = 12  # iterations until the L-BFGS memory (m = 10) is full
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------ algorithmic traffic
+def kernel_words(name, N, W, c, q):
+    """Algorithmic fp64 words per launch of each kernel."""
+    m = c + q
+    table = {
+        "ResF": (9 + c) * N + 10 * W + 0.5 * ((3 + q) * N + 5 * W),  # 1 plain + 1 with step
+        "DiagF": 6 * N + 5 * W,
+        "Pass1F": 9 * N + 11 * W,
+        "Pass2F": (12 + m) * N + 15 * W + 0.5 * (3 * N + 5 * W),  # every 2nd accumulates
+        "StatsF": 9 * N + 8 * W,
+        "TrialF": 5 * N + 6 * W,
+        "Update1F": (10 + c) * N + 15 * W,
+        "Update2F": (5 + c) * N + W,
+        "gram_kernel": (m + 1) * N + W,
+        "mdot_kernel": None,  # (1 + columns of the chunk) N, see below
+    }
+    return table.get(name)
+
+
+def iteration_words(N, W, c, q):
+    """algorithmic words per interior-point iteration."""
+    return (200 + 16 * c + 9 * q) * N + 238 * W
+
+
+def kkt_words(N, W, c, q):
+    return (51 + 5 * c + 3 * q) * N + 62 * W
+
+
+# ---------------------------------------------------------------- reference
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_ref_driver(cfg, nranks, timeout=1200):
+    """Runs the unmodified reference (oracle/_ref/ref_driver) and returns the
+    per-iteration records (with wall-clock stamps) and the final record."""
+    sys.path.insert(0, ROOT)
+    from oracle.make_golden import DRIVER, driver_args  # checker side (cpu baseline leg)
+
+    if not os.path.exists(DRIVER):
+        return None, None
+    env = dict(os.environ)
+    env["OPENBLAS_NUM_THREADS"] = "1"
+    env["PCU_SHIM_NP"] = str(nranks)
+    with tempfile.TemporaryDirectory() as tmp:
+        hist = os.path.join(tmp, "hist.jsonl")
+        cmd = [DRIVER] + driver_args(cfg) + ["hist=" + hist, "log=/dev/null"]
+        subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL, timeout=timeout)
+        recs = [json.loads(line) for line in open(hist)]
+    return [r for r in recs if "iter" in r], [r for r in recs if "final" in r][0]
+
+
+def reference_rate(cfg_name, ntotal, warmup, steps, budget_s=25.0):
+    """Iterations/s of the reference's CPU implementation at `ntotal` variables,
+    measured on a bounded sample (smaller n, linear scaling in n) with one shim
+    rank per host core."""
+    cores = host_cores()
+    nranks = max(1, min(cores, 64))
+    iters = warmup + steps
+
+    def cfg_for(n):
+        cfg = configs.get(cfg_name, n)
+        cfg["options"] = dict(cfg["options"], max_major_iters=iters + 1)
+        return cfg
+
+    unit = 8 * nranks
+    n_probe = max(unit * 64, (1 << 18) // unit * unit)
+    t0 = time.time()
+    hist, fin = run_ref_driver(cfg_for(n_probe), nranks)
+    if hist is None:
+        return None
+    probe_s = time.time() - t0
+    n_s = int(n_probe * min(64.0, max(1.0, budget_s / max(probe_s, 1e-3))))
+    n_s = max(unit, n_s // unit * unit)
+    n_s = min(n_s, ntotal)
+    if n_s > n_probe:
+        hist, fin = run_ref_driver(cfg_for(n_s), nranks)
+    else:
+        n_s = n_probe
+    k0 = min(warmup, len(hist) - 2)
+    k1 = len(hist) - 1
+    dt = hist[k1]["wall"] - hist[k0]["wall"]
+    rate_sample = (k1 - k0) / dt
+    return {
+        "value": rate_sample * (float(n_s) / float(ntotal)),
+        "unit": UNIT,
+        "cores": nranks,
+        "kind": "reference",
+        "sample": ("unmodified reference ParOptInteriorPoint (oracle/_ref), %d shim "
+                   "ranks, n=%d, iterations %d..%d timed (%.2f s); scaled by n/%d "
+                   "(O(n) work per iteration)" % (nranks, n_s, k0, k1, dt, ntotal)),
+        "sample_iterations_per_sec": rate_sample,
+        "sample_n": n_s,
+    }
+
+
+# --------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from paropt_b200.api import Context, InteriorPoint, problem_from_config
+    from paropt_b200.host_problems import HostSepQuad
+
+    ctx = Context(local_rank)
+    if world > 1:
+        ctx.init_distributed()
+
+    cfg = configs.get(args.config, args.n)
+    ntotal = cfg["problem"]["ntotal"]
+    c = cfg["problem"]["ncon"]
+    msub = cfg["options"].get("qn_subspace_size", 10)
+    q = 2 * msub if cfg["options"].get("qn_type", "bfgs") == "bfgs" else msub
+    warmup = max(args.warmup, QN_WARMUP)
+    steps = args.steps
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident run: `value` --------------------------------------
+    prob = problem_from_config(ctx, cfg)
+    N, W = prob.nvars, prob.nwcon
+    opts = dict(cfg["options"], max_major_iters=1000000, history_level=1)
+    ip = InteriorPoint(prob, opts)
+    ip.begin()
+    ip.iterate(warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(2)
+    launches0 = ctx.kernel_launches()
+    it0 = ip.counters()[0]
+    ctx.timer_start()
+    ip.iterate(steps)
+    ms = ctx.timer_stop()
+    barrier()
+    ctx.profile(0)
+    clocks = sampler.stop() if rank == 0 else None
+    done = ip.counters()[0] - it0
+    launches = ctx.kernel_launches() - launches0
+    ms = max_over_ranks(ms)
+    times = ip.iter_times()[-done:] if done else []
+    kkt_ms = max_over_ranks(sum(t[2] for t in times) / max(len(times), 1))
+    cb_ms = max_over_ranks(sum(t[1] for t in times) / max(len(times), 1))
+    prof = ctx.profile_totals()
+    hist = ip.history()
+    qn_size = hist[-1]["qn_size"] if hist else q
+    ip.free()
+    prob.free()
+    value = done / (ms / 1e3) if ms > 0 else 0.0
+    ms_per_step = ms / max(done, 1)
+
+    # dominant kernel of the timed region and its roofline
+    peak, peak_src = measured_peak_gbs()
+    roof = None
+    if prof:
+        name = max(prof, key=lambda k: prof[k][0])
+        tot_ms, cnt = prof[name]
+        words = kernel_words(name, N, W, c, qn_size)
+        if name == "mdot_kernel":
+            # launches of 8-column chunks: average columns per launch from totals
+            m = c + qn_size
+            chunks = -(-m // 8)
+            words = (m / chunks + 1) * N
+        avg_ms = tot_ms / cnt
+        achieved = words * 8 / (avg_ms * 1e-3) / 1e9 if words else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(name)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "launches": cnt,
+                "share_of_step": tot_ms / ms if ms else None,
+                "algorithmic_bytes_per_launch": words * 8 if words else None,
+                "kernels": {k: {"ms": round(v[0], 3), "launches": v[1]}
+                            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    iter_bytes = 8.0 * iteration_words(N, W, c, qn_size)
+    user_ms = cb_ms
+    solver_ms = max(ms_per_step - user_ms, 1e-9)
+    iter_frac = iter_bytes / (solver_ms * 1e-3) / 1e9 / peak
+    kkt_frac = 8.0 * kkt_words(N, W, c, qn_size) / (max(kkt_ms, 1e-9) * 1e-3) / 1e9 / peak
+
+    # ---- end to end through the host-callback API: `e2e` --------------------
+    e2e = None
+    if not args.no_e2e:
+        def allreduce(a):
+            if world == 1:
+                return a
+            t = torch.tensor(a, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+
+        hp = HostSepQuad(ctx, allreduce=allreduce, **cfg["problem"])
+        hip = InteriorPoint(hp, dict(cfg["options"], max_major_iters=1000000,
+                                     history_level=1))
+        e_warm, e_steps = args.e2e_warmup, args.e2e_steps
+        hip.begin()
+        hip.iterate(e_warm)
+        barrier()
+        h2d0, d2h0 = hp.h2d_bytes, hp.d2h_bytes
+        i0 = hip.counters()[0]
+        ctx.timer_start()
+        hip.iterate(e_steps)
+        e_ms = max_over_ranks(ctx.timer_stop())
+        barrier()
+        e_done = hip.counters()[0] - i0
+        e2e = {"value": e_done / (e_ms / 1e3) if e_ms > 0 else 0.0, "unit": UNIT,
+               "h2d_bytes_per_step": (hp.h2d_bytes - h2d0) // max(e_done, 1),
+               "d2h_bytes_per_step": (hp.d2h_bytes - d2h0) // max(e_done, 1),
+               "steps": e_done, "warmup": e_warm,
+               "note": "host numpy callbacks (user code) + pinned-buffer copies inside "
+                       "the timed region; quasi-Newton memory still filling"}
+        hip.free()
+        hp.free()
+
+    # ---- CPU baseline (rank 0, single-GPU runs only) -------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = reference_rate(args.config, ntotal, QN_WARMUP, 6)
+        except Exception as exc:  # the checker must never sink the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference",
+                   "sample": "failed: %r" % (exc,)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": done, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s n=%d ncon=%d nwcon=%d qn=%s m=%d" % (
+                args.config, cfg["kind"], ntotal, c, ntotal // 8 if cfg["problem"].get("nw") else 0,
+                cfg["options"].get("qn_type", "bfgs"), msub),
+                "n_per_gpu": N, "partition": "block-row over %d GPU(s)" % world,
+                "l2_note": "every pass streams >= 0.5 GB per vector (>> 126 MB L2)",
+                "warmup_note": "warm-up raised to %d so the L-BFGS memory is full" % QN_WARMUP},
+            "kkt_solve_ms": kkt_ms, "kkt_roofline_frac": kkt_frac,
+            "callback_ms_per_step": cb_ms, "iter_roofline_frac": iter_frac,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = configs.get(args.config, args.n)
+    ntotal = cfg["problem"]["ntotal"]
+    warmup = max(args.warmup, QN_WARMUP)
+    t0 = time.time()
+    res = reference_rate(args.config, ntotal, warmup, args.steps)
+    if res is None:
+        print(json.dumps({"impl": "reference",
+                          "unavailable": "oracle/_ref/ref_driver has not been built"}))
+        return
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s n=%d (CPU sample n=%d, linear in n)" % (
+            args.config, ntotal, res["sample_n"])},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=QN_WARMUP)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--n", type=int, default=None, help="global number of design variables")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-warmup", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

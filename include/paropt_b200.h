@@ -53,6 +53,13 @@ int pcu_ctx_sync(pcu_ctx *ctx); /* cudaStreamSynchronize on the ctx stream */
 void *pcu_ctx_stream(pcu_ctx *ctx); /* cudaStream_t, for callers that enqueue */
 /* Number of kernels of THIS library launched on the context since creation.  */
 int64_t pcu_ctx_kernel_launches(pcu_ctx *ctx);
+/* Per-kernel device timing: enable = 1 starts bracketing every launch of this
+   library with CUDA events on the launching stream, 2 also clears the totals,
+   0 stops.  profile_get returns kernel name, accumulated ms and launch count. */
+int pcu_ctx_profile(pcu_ctx *ctx, int enable);
+int pcu_ctx_profile_count(pcu_ctx *ctx);
+int pcu_ctx_profile_get(pcu_ctx *ctx, int index, char *name, int name_len,
+                        double *ms, int64_t *count);
 /* Device-side timing helpers (cudaEvent on the ctx stream), milliseconds.     */
 int pcu_ctx_timer_start(pcu_ctx *ctx);
 int pcu_ctx_timer_stop(pcu_ctx *ctx, double *ms);

@@ -155,7 +155,7 @@ void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
   if (rank == 0 && hist) {
     int ncon = ip->ncon;
     fprintf(hist,
-            "{\"iter\": %d, \"fobj\": %.17g, \"mu\": %.17g, \"rho\": %.17g, "
+            "{\"iter\": %d, \"wall\": %.6f, \"fobj\": %.17g, \"mu\": %.17g, \"rho\": %.17g, "
             "\"comp\": %.17g, \"max_prime\": %.17g, \"max_dual\": %.17g, "
             "\"max_infeas\": %.17g, \"res_norm\": %.17g, \"neval\": %d, "
             "\"ngeval\": %d, \"alpha\": %.17g, \"pnorm2\": %.17g, "
@@ -164,7 +164,7 @@ void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
             "\"zlnorm\": %.17g, \"zunorm\": %.17g, \"zwsum\": %.17g, "
             "\"zwnorm\": %.17g, \"swsum\": %.17g, \"twsum\": %.17g, "
             "\"zswsum\": %.17g, \"ztwsum\": %.17g, \"gmax\": %.17g, ",
-            iter, ip->fobj, ip->barrier_param, ip->rho_penalty_search, comp,
+            iter, MPI_Wtime(), ip->fobj, ip->barrier_param, ip->rho_penalty_search, comp,
             max_prime, max_dual, max_infeas, res_norm, ip->neval, ip->ngeval,
             alpha, pnorm2, b0, qsize, sums[0], xnorm, sums[1], sums[2], zlnorm,
             zunorm, sums[3], zwnorm, sums[4], sums[5], sums[6], sums[7], gmax);

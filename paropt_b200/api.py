@@ -65,6 +65,21 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.pcu_ctx_kernel_launches(self.h))
 
+    def profile(self, enable):
+        _check(self.lib.pcu_ctx_profile(self.h, int(enable)), "profile")
+
+    def profile_totals(self):
+        """{kernel name: (total ms, launches)} accumulated while profiling."""
+        out = {}
+        n = int(self.lib.pcu_ctx_profile_count(self.h))
+        name = C.create_string_buffer(256)
+        ms, cnt = C.c_double(), C.c_int64()
+        for i in range(n):
+            if self.lib.pcu_ctx_profile_get(self.h, i, name, 256, C.byref(ms),
+                                            C.byref(cnt)) == 0:
+                out[name.value.decode()] = (ms.value, int(cnt.value))
+        return out
+
     def timer_start(self):
         _check(self.lib.pcu_ctx_timer_start(self.h), "timer_start")
 
@@ -192,6 +207,8 @@ class Problem:
         self.nvars, self.ncon = int(nvars), int(ncon)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._bufs = {}
+        self._pinned = []
         w = _lib.Weighting()
         if weighting:
             for k, v in weighting.items():
@@ -211,14 +228,38 @@ class Problem:
     def _vec(self, handle):
         return PVec(self.ctx, handle=handle)
 
+    def _host(self, key):
+        """Persistent pinned host mirror (the reference's getArray buffer)."""
+        buf = self._bufs.get(key)
+        if buf is None:
+            try:
+                import torch
+                t = torch.empty(self.nvars, dtype=torch.float64, pin_memory=True)
+                self._pinned.append(t)
+                buf = t.numpy()
+            except Exception:
+                buf = np.empty(self.nvars)
+            self._bufs[key] = buf
+        return buf
+
+    def _d2h(self, handle, key):
+        buf = self._host(key)
+        if self.nvars:
+            _check(self.lib.pcu_vec_to_host(handle, buf.ctypes.data, self.nvars), "to_host")
+        self.d2h_bytes += buf.nbytes
+        return buf
+
+    def _h2d(self, handle, buf):
+        if self.nvars:
+            _check(self.lib.pcu_vec_from_host(handle, buf.ctypes.data, self.nvars), "from_host")
+        self.h2d_bytes += buf.nbytes
+
     def _get_vars(self, user, x, lb, ub):
         try:
-            n = self.nvars
-            xa, la, ua = np.zeros(n), np.zeros(n), np.zeros(n)
+            xa, la, ua = self._host("x"), self._host("g"), self._host("a0")
             self.getVarsAndBounds(xa, la, ua)
             for h, a in ((x, xa), (lb, la), (ub, ua)):
-                self._vec(h).from_numpy(a)
-                self.h2d_bytes += a.nbytes
+                self._h2d(h, a)
             return 0
         except Exception:  # mirrors ParOpt.pyx:528-531 (report, do not unwind C)
             import traceback
@@ -227,8 +268,7 @@ class Problem:
 
     def _eval_obj(self, user, x, fobj, cons):
         try:
-            xa = self._vec(x).to_numpy()
-            self.d2h_bytes += xa.nbytes
+            xa = self._d2h(x, "x")
             fail, f, con = self.evalObjCon(xa)
             fobj[0] = float(f)
             for i in range(self.ncon):
@@ -241,16 +281,13 @@ class Problem:
 
     def _eval_grad(self, user, x, g, Ac):
         try:
-            xa = self._vec(x).to_numpy()
-            self.d2h_bytes += xa.nbytes
-            ga = np.zeros(self.nvars)
-            A = [np.zeros(self.nvars) for _ in range(self.ncon)]
+            xa = self._d2h(x, "x")
+            ga = self._host("g")
+            A = [self._host("a%d" % i) for i in range(self.ncon)]
             fail = self.evalObjConGradient(xa, ga, A)
-            self._vec(g).from_numpy(ga)
-            self.h2d_bytes += ga.nbytes
+            self._h2d(g, ga)
             for i in range(self.ncon):
-                self._vec(Ac[i]).from_numpy(A[i])
-                self.h2d_bytes += A[i].nbytes
+                self._h2d(Ac[i], A[i])
             return int(fail or 0)
         except Exception:
             import traceback

@@ -297,7 +297,7 @@ int pcu_ip_qn_update(pcu_ip *ip, pcu_vec *s, pcu_vec *y, int *update_type) {
   if (pcu_vec_dot(y, y, &yy) || pcu_vec_dot(y, s, &ys) || pcu_vec_dot(s, s, &ss))
     return 1;
   int ut = 0;
-  if (ip->qn->update(s, y, yy, ys, ss, &ut)) return 1;
+  if (ip->qn->update(s, y, yy, ys, ss, nullptr, &ut)) return 1;
   if (update_type) *update_type = ut;
   return 0;
 }

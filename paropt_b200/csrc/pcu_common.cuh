@@ -18,8 +18,9 @@
 
 #define PCU_MAX_COLS 160   // max ncon + quasi-Newton width handled by kernels
 #define PCU_THREADS 256
+#define PCU_TILE_THREADS 128  // block size of the fused streaming kernels
 #define PCU_MAX_RED 64     // max scalars reduced by one fused kernel
-#define PCU_MAX_BLOCKS 2048
+#define PCU_MAX_BLOCKS 4096
 
 #define PCU_CUDA_OK(call)                                                      \
   do {                                                                         \
@@ -204,7 +205,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       typename F::Elem e[1];
       double coef[1] = {0.0};
       double part[1][NB];
-      f.template A<1>(i, coef, e, part);
+      f.template A<1>(i, coef, e, part, &acc);
       typename F::Con con;
       con.zero();
       f.template C<1>(i, coef, e, con, acc);
@@ -224,7 +225,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
-        f.template A<1>(j0 + k, coef, e, part);
+        f.template A<1>(j0 + k, coef, e, part, (typename F::AccT *)nullptr);
 #pragma unroll
         for (int b = 0; b < NB; b++) sum[b] += part[0][b];
       }
@@ -235,7 +236,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
-        f.template A<1>(j0 + k, coef, e, part);
+        f.template A<1>(j0 + k, coef, e, part, &acc);
         f.template C<1>(j0 + k, coef, e, con, acc);
       }
     }
@@ -243,7 +244,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
 }
 
 template <class F>
-__global__ void __launch_bounds__(PCU_THREADS)
+__global__ void __launch_bounds__(PCU_TILE_THREADS)
     tile_kernel(const F f, const long long n, const WDesc w, const RedBuf rb) {
   constexpr int NB = F::NB > 0 ? F::NB : 1;
   typename F::AccT acc;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(PCU_THREADS)
         coef[0] = (k == 0) ? w.coef0 : w.coef_rest;
         coef[1] = w.coef_rest;
       }
-      f.template A<2>(i, coef, e, part);
+      f.template A<2>(i, coef, e, part, &acc);
       typename F::Con con;
       con.zero();
       if (w.mode == 1) {

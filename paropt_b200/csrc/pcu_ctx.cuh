@@ -3,6 +3,8 @@
 
 #include <nccl.h>  // types only; the library is resolved with dlopen at run time
 
+#include <map>
+#include <string>
 #include <vector>
 
 #include "pcu_common.cuh"
@@ -35,8 +37,26 @@ struct pcu_ctx {
   size_t big_partials_cap = 0;
 
   int grid = 148 * 4;
+  int num_sms = 148;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // optional per-kernel device timing (CUDA events on the launching stream)
+  struct ProfPending {
+    const char *name;
+    cudaEvent_t e0, e1;
+  };
+  struct ProfTotal {
+    double ms = 0.0;
+    long count = 0;
+  };
+  bool profiling = false;
+  std::vector<ProfPending> prof_pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t> > prof_pool;
+  std::map<std::string, ProfTotal> prof_totals;
+  void prof_begin(const char *name);
+  void prof_end();
+  void prof_collect();  // call after a stream synchronisation
 
   RedBuf redbuf(int ns, int nx, int nm);       // reserves a result slot
   int fetch(double *out);                      // all pending slots -> host, sync
@@ -68,10 +88,41 @@ struct pcu_vec {
   bool owns = true;
 };
 
+template <class F>
+const char *pcu_kernel_name() {
+  return __PRETTY_FUNCTION__;  // "... [with F = ResF]"; trimmed when reported
+}
+
 // launch helper: grid sized to the work, capped at the persistent grid
 static inline int pcu_grid_for(const pcu_ctx *ctx, long long n) {
   long long need = (n / 2 + PCU_THREADS - 1) / PCU_THREADS;
   if (need < 1) need = 1;
   if (need > ctx->grid) need = ctx->grid;
   return (int)need;
+}
+
+template <class F>
+int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
+                    RedBuf rb) {
+  // persistent grid: exactly as many blocks as can be co-resident
+  static int blocks_per_sm = -1;
+  if (blocks_per_sm < 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, tile_kernel<F>,
+                                                      PCU_TILE_THREADS, 0) != cudaSuccess ||
+        v < 1)
+      v = 1;
+    blocks_per_sm = v > 16 ? 16 : v;
+  }
+  long long need = (n / 2 + PCU_TILE_THREADS - 1) / PCU_TILE_THREADS;
+  if (need < 1) need = 1;
+  long long cap = (long long)ctx->num_sms * blocks_per_sm;
+  if (cap > PCU_MAX_BLOCKS) cap = PCU_MAX_BLOCKS;
+  const int grid = (int)(need < cap ? need : cap);
+  ctx->prof_begin(pcu_kernel_name<F>());
+  tile_kernel<F><<<grid, PCU_TILE_THREADS, 0, ctx->stream>>>(f, n, w, rb);
+  ctx->prof_end();
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
 }

@@ -53,11 +53,11 @@ __global__ void __launch_bounds__(PCU_THREADS)
   double acc[NP][2];
 #pragma unroll
   for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
-  double uA[NTA], uB[NTB];
+  double uA[NTA], uB[NTB], hA[NTA], hB[NTB], hcw = 0.0;
 #pragma unroll
-  for (int t = 0; t < NTA; t++) uA[t] = 0.0;
+  for (int t = 0; t < NTA; t++) uA[t] = hA[t] = 0.0;
 #pragma unroll
-  for (int t = 0; t < NTB; t++) uB[t] = 0.0;
+  for (int t = 0; t < NTB; t++) uB[t] = hB[t] = 0.0;
 
   const bool wmode = (w.mode == 1);
   const long long ncon_elems = wmode ? (long long)w.nwcon * w.nw : 0;
@@ -148,22 +148,55 @@ __global__ void __launch_bounds__(PCU_THREADS)
               for (int t = 0; t < NTB; t++) uB[t] += shfl_xor_d(uB[t], o);
             }
           }
-          const bool lead = in_con && ((kk & (L - 1)) == 0);
-          const double cw = lead ? Cw[r / w.nw] : 0.0;
-          double ua[NTA], ub[NTB];
+          if (w.nw >= 8) {
+            // one block per >= 1 steps: park its u in k-slot (block & 3) and issue
+            // ONE correction DMMA per four blocks (all four k slots in use)
+            const int blk = (int)((r0 / w.nw) & 3);
+            if (kk == blk) {
+              hcw = in_con ? Cw[r0 / w.nw] : 0.0;
 #pragma unroll
-          for (int t = 0; t < NTA; t++) ua[t] = lead ? -cw * uA[t] : 0.0;
+              for (int t = 0; t < NTA; t++) hA[t] = in_con ? uA[t] : 0.0;
 #pragma unroll
-          for (int t = 0; t < NTB; t++)
-            ub[t] = lead ? (DIAG ? uA[t < NTA ? t : 0] : uB[t]) : 0.0;
-          int p = 0;
+              for (int t = 0; t < NTB; t++)
+                hB[t] = in_con ? (DIAG ? uA[t < NTA ? t : 0] : uB[t]) : 0.0;
+            }
+            const bool flush = (blk == 3) || (step == 7) || (r0 + 8 >= n);
+            if (flush) {
+              int p = 0;
 #pragma unroll
-          for (int ti = 0; ti < NTA; ti++) {
+              for (int ti = 0; ti < NTA; ti++) {
 #pragma unroll
-            for (int tj = 0; tj < NTB; tj++) {
-              if (!DIAG || tj <= ti) {
-                dmma884(acc[p], ua[ti], ub[tj]);
-                p++;
+                for (int tj = 0; tj < NTB; tj++) {
+                  if (!DIAG || tj <= ti) {
+                    dmma884(acc[p], -hcw * hA[ti], hB[tj]);
+                    p++;
+                  }
+                }
+              }
+              hcw = 0.0;
+#pragma unroll
+              for (int t = 0; t < NTA; t++) hA[t] = 0.0;
+#pragma unroll
+              for (int t = 0; t < NTB; t++) hB[t] = 0.0;
+            }
+          } else {
+            const bool lead = in_con && ((kk & (L - 1)) == 0);
+            const double cw = lead ? Cw[r / w.nw] : 0.0;
+            double ua[NTA], ub[NTB];
+#pragma unroll
+            for (int t = 0; t < NTA; t++) ua[t] = lead ? -cw * uA[t] : 0.0;
+#pragma unroll
+            for (int t = 0; t < NTB; t++)
+              ub[t] = lead ? (DIAG ? uA[t < NTA ? t : 0] : uB[t]) : 0.0;
+            int p = 0;
+#pragma unroll
+            for (int ti = 0; ti < NTA; ti++) {
+#pragma unroll
+              for (int tj = 0; tj < NTB; tj++) {
+                if (!DIAG || tj <= ti) {
+                  dmma884(acc[p], ua[ti], ub[tj]);
+                  p++;
+                }
               }
             }
           }
@@ -261,12 +294,22 @@ static int launch_gram(pcu_ctx *ctx, const ColTable &cols, int colA0, int colB0,
   constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
   long long nchunks = (n + 63) / 64;
   long long need = (nchunks + (PCU_THREADS / 32) - 1) / (PCU_THREADS / 32);
-  int grid = ctx->grid / 2;
+  static int blocks_per_sm = -1;
+  if (blocks_per_sm < 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, gram_kernel<NTA, NTB, DIAG>, PCU_THREADS, 0) != cudaSuccess || v < 1)
+      v = 1;
+    blocks_per_sm = v > 4 ? 4 : v;
+  }
+  int grid = ctx->num_sms * blocks_per_sm;
   if (need < grid) grid = (int)(need < 1 ? 1 : need);
   if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
+  ctx->prof_begin("gram_kernel");
   gram_kernel<NTA, NTB, DIAG><<<grid, PCU_THREADS, 0, ctx->stream>>>(
       cols, colA0, colB0, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter,
       result, ld);
+  ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
   return 0;

@@ -17,15 +17,7 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
                      const double *Dinv, const double *Cw, const WDesc &wd,
                      long long n, int *ld_out);
 
-template <class F>
-static int launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
-                       RedBuf rb) {
-  const int grid = pcu_grid_for(ctx, n);
-  tile_kernel<F><<<grid, PCU_THREADS, 0, ctx->stream>>>(f, n, w, rb);
-  ctx->launches++;
-  PCU_CUDA_OK(cudaGetLastError());
-  return 0;
-}
+#define launch_tile pcu_launch_tile
 
 static const RedBuf NO_RED = {nullptr, nullptr, nullptr};
 
@@ -204,12 +196,19 @@ void QuasiNewton::mat_update() {
 // One multi-dot pass gives s.S_i and s.Y_i for every stored pair: it provides
 // both Z^T s (for s^T B s) and the new rows of S^T S and L.
 int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
-                        double sTs, int *update_type) {
+                        double sTs, const double *sZ, int *update_type) {
   *update_type = 0;
   const int m = msub_max;
   std::vector<double> sS(msub), sY(msub);
   auto stored_dots = [&]() -> int {
     if (msub == 0) return 0;
+    if (sZ && type == 0) {  // supplied by the caller (Z = [S | Y])
+      for (int i = 0; i < msub; i++) {
+        sS[i] = sZ[i];
+        sY[i] = sZ[msub + i];
+      }
+      return 0;
+    }
     ColTable t;
     for (int i = 0; i < msub; i++) {
       t.p[i] = S[i]->d;
@@ -512,7 +511,7 @@ struct BoundsF {
   int both;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>

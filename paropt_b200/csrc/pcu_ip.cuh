@@ -94,7 +94,7 @@ struct QuasiNewton {
   void solve_compact(const double *rz, double *kap) const;
   int mult(pcu_vec *x, pcu_vec *y);
   int update(pcu_vec *s, pcu_vec *y, double yTy, double yTs, double sTs,
-             int *update_type);
+             const double *sZ, int *update_type);
   void mat_update();
 };
 
@@ -148,6 +148,7 @@ struct pcu_ip {
   // statistics of the last ResF launch
   double res_sums[11], res_max[3];
   double last_comp = 0.0;
+  int force_direct_dots = 0;  // debugging: recompute [A|Z]^T p with multi-dots
   double stats_pmax = 0.0;  // |px|_inf of the last StatsF launch
 
   // resumable major loop state (locals of optimize(), IP.cpp:4570-4606)

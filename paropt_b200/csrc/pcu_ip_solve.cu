@@ -15,15 +15,7 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
 int pcu_lu_factor(int n, double *A, int *piv);
 void pcu_lu_solve(int n, const double *LU, const int *piv, double *b);
 
-template <class F>
-static int launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
-                       RedBuf rb) {
-  const int grid = pcu_grid_for(ctx, n);
-  tile_kernel<F><<<grid, PCU_THREADS, 0, ctx->stream>>>(f, n, w, rb);
-  ctx->launches++;
-  PCU_CUDA_OK(cudaGetLastError());
-  return 0;
-}
+#define launch_tile pcu_launch_tile
 static const RedBuf NO_RED = {nullptr, nullptr, nullptr};
 
 // LS flags (IP.h:220-225)
@@ -124,25 +116,54 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
   const int q = (qn && use_qn && !Cefac.empty()) ? std::min(sq, qn->size()) : 0;
   const int m = ncon + q;
   const IPConst k = kconst();
-  Pass1F f1;
-  f1.v = vars.dv();
-  f1.b = b.dv();
-  f1.lb = lb->d;
-  f1.ub = ub->d;
-  f1.Dinv = Dinv->d;
-  f1.Cw = Cw->d;
-  f1.d1 = d1->d;
-  f1.d2 = d2->d;
-  f1.t1 = t1->d;
-  f1.k = k;
-  if (launch_tile(ctx, f1, nvars, wd, NO_RED)) return 1;
   ColTable V;
   for (int j = 0; j < ncon; j++) V.p[j] = Ac[j]->d;
   if (q > 0) qn->z_table(V, ncon);
   std::vector<double> r(m > 0 ? m : 1, 0.0);
-  if (m > 0) {
-    if (pcu_mdot_enqueue(ctx, t1->d, V, m, nvars, 0)) return 1;
-    if (ctx->big_fetch(m, r.data())) return 1;
+  auto fused_pass1 = [&](auto f1) -> int {
+    f1.v = vars.dv();
+    f1.b = b.dv();
+    f1.lb = lb->d;
+    f1.ub = ub->d;
+    f1.Dinv = Dinv->d;
+    f1.Cw = Cw->d;
+    f1.d1 = d1->d;
+    f1.d2 = d2->d;
+    f1.V = V;
+    f1.m = m;
+    f1.k = k;
+    RedBuf rb = ctx->redbuf(decltype(f1)::NS, 0, 0);
+    if (launch_tile(ctx, f1, nvars, wd, rb)) return 1;
+    double out[decltype(f1)::NS];
+    if (ctx->fetch(out)) return 1;
+    for (int i = 0; i < m; i++) r[i] = out[i];
+    return 0;
+  };
+  if (m > 0 && m <= 8) {
+    if (fused_pass1(Pass1RF<8>())) return 1;
+  } else if (m <= 16 && m > 0) {
+    if (fused_pass1(Pass1RF<16>())) return 1;
+  } else if (m <= 24 && m > 0) {
+    if (fused_pass1(Pass1RF<24>())) return 1;
+  } else if (m <= 32 && m > 0) {
+    if (fused_pass1(Pass1RF<32>())) return 1;
+  } else {
+    Pass1F f1;
+    f1.v = vars.dv();
+    f1.b = b.dv();
+    f1.lb = lb->d;
+    f1.ub = ub->d;
+    f1.Dinv = Dinv->d;
+    f1.Cw = Cw->d;
+    f1.d1 = d1->d;
+    f1.d2 = d2->d;
+    f1.t1 = t1->d;
+    f1.k = k;
+    if (launch_tile(ctx, f1, nvars, wd, NO_RED)) return 1;
+    if (m > 0) {
+      if (pcu_mdot_enqueue(ctx, t1->d, V, m, nvars, 0)) return 1;
+      if (ctx->big_fetch(m, r.data())) return 1;
+    }
   }
   // dense solves (IP.cpp:2150-2170, 2716-2722, 2288-2306)
   std::vector<double> yz1(ncon), pz(ncon), ps(ncon), pt(ncon), pzs(ncon), pzt(ncon);
@@ -218,13 +239,24 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
   f2.k = k;
   if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
   if (VTp) {
+    // [A | Z]^T p.  When the Gram pass covered every quasi-Newton vector the
+    // products follow from linearity, [A|Z]^T D0^-1 (d1 + V alpha) = r + S alpha,
+    // without touching the N-vectors again.
     const int qa = qn ? qn->size() : 0;
-    ColTable Vall;
-    for (int j = 0; j < ncon; j++) Vall.p[j] = Ac[j]->d;
-    if (qa > 0) qn->z_table(Vall, ncon);
-    if (ncon + qa > 0) {
-      if (pcu_mdot_enqueue(ctx, y.v[PCU_X]->d, Vall, ncon + qa, nvars, 0)) return 1;
-      if (ctx->big_fetch(ncon + qa, VTp)) return 1;
+    if (q == qa && !force_direct_dots) {
+      for (int i = 0; i < m; i++) {
+        double v = r[i];
+        for (int j = 0; j < m; j++) v += Sgram[i + (size_t)sld * j] * f2.alpha.v[j];
+        VTp[i] = accumulate ? VTp[i] + v : v;
+      }
+    } else {
+      ColTable Vall;
+      for (int j = 0; j < ncon; j++) Vall.p[j] = Ac[j]->d;
+      if (qa > 0) qn->z_table(Vall, ncon);
+      if (ncon + qa > 0) {
+        if (pcu_mdot_enqueue(ctx, y.v[PCU_X]->d, Vall, ncon + qa, nvars, 0)) return 1;
+        if (ctx->big_fetch(ncon + qa, VTp)) return 1;
+      }
     }
   }
   return 0;
@@ -277,7 +309,7 @@ struct MaskBoundMultF {  // zl = 0 where lb <= -mbv, zu = 0 where ub >= mbv
   double *rx;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -327,7 +359,7 @@ struct SparseStartF {  // W-sized pieces of the starting-point strategies
   int mode;  // 0: clip zw to +-10 gamma (IP.cpp:5520-5533); 1: affine (IP.cpp:5605-5627)
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -507,7 +539,7 @@ struct StateSumF {  // checksums of the iterate for the parity history
   int sparse;  // 0: N-sized pass, 1: W-sized pass
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -933,7 +965,8 @@ int pcu_ip::iterate_once(int *converged) {
   }
   if (diagonal_qn_step) use_qn = 1;
   const int nA = ncon, nZ = qn ? qn->max_size() : 0;
-  std::vector<double> VTp(nA + nZ + 1, 0.0), VTr(nA + nZ + 1, 0.0);
+  std::vector<double> VTp(nA + nZ + 1, 0.0);
+  bool vtp_valid = true;
 
   PCU_CUDA_OK(cudaEventRecord(ev_k0, ctx->stream));
   if (setUpKKTDiagSystem(v, use_qn, 0)) return 1;
@@ -1083,7 +1116,15 @@ int pcu_ip::iterate_once(int *converged) {
         if (launch_tile(ctx, f2, nvars, wd, rb)) return 1;
         double dots[3];
         if (ctx->fetch(dots)) return 1;
-        if (qn->update(s_qn, y_qn, dots[0], dots[1], dots[2], &update_type)) return 1;
+        // s.S_i and s.Y_i: s = ax * p, so they are ax * (Z^T p) for L-BFGS
+        std::vector<double> sZ;
+        if (qn->type == 0 && !force_direct_dots && vtp_valid) {
+          sZ.resize(qn->size());
+          for (int i = 0; i < qn->size(); i++) sZ[i] = ax * VTp[nA + i];
+        }
+        if (qn->update(s_qn, y_qn, dots[0], dots[1], dots[2],
+                       sZ.empty() ? nullptr : sZ.data(), &update_type))
+          return 1;
       }
     }
     return 0;

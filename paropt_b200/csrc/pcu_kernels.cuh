@@ -81,7 +81,7 @@ struct ResF {
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][2]) const {
+                                    Elem (&e)[W], double (&part)[W][2], AccT *acc) const {
     double x[W], l[W], u[W], zl[W], zu[W], gv[W], rx[W];
     ldv<W>(v.x, i, x);
     ldv<W>(lb, i, l);
@@ -239,7 +239,7 @@ struct DiagF {
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&)[W], double (&part)[W][1]) const {
+                                    Elem (&)[W], double (&part)[W][1], AccT *acc) const {
     double d[W];
     if (identity) {
 #pragma unroll
@@ -295,7 +295,7 @@ struct Pass1F {
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][1]) const {
+                                    Elem (&e)[W], double (&part)[W][1], AccT *acc) const {
     double x[W], l[W], u[W], bx[W], bzl[W], bzu[W], di[W], d[W];
     ldv<W>(v.x, i, x);
     ldv<W>(lb, i, l);
@@ -362,7 +362,7 @@ struct Pass2F {
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][1]) const {
+                                    Elem (&e)[W], double (&part)[W][1], AccT *acc) const {
     double d[W], di[W];
     ldv<W>(d1, i, d);
     ldv<W>(Dinv, i, di);
@@ -469,22 +469,30 @@ struct StatsF {
   static constexpr int NS = 22, NX = 1, NM = 2, NB = 2;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
-  struct Elem {
-    double c0, c1, c2, c3, lpos, lneg, ppos, pneg, gp, pp, mx, mz;
-  };
+  struct Elem {};
   DVars v, p;
   const double *lb, *ub, *g;
   double tau;
   IPConst k;
 
+  // All element reductions happen here (acc is null on the generic path's
+  // first, sum-only visit of an element).
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][2]) const {
-    double x[W], l[W], u[W], zl[W], zu[W], px[W], pzl[W], pzu[W], gv[W];
+                                    Elem (&)[W], double (&part)[W][2],
+                                    AccT *acc) const {
+    double x[W], l[W], u[W], px[W];
     ldv<W>(v.x, i, x);
+    ldv<W>(p.x, i, px);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      part[q][0] = coef[q] * x[q];
+      part[q][1] = coef[q] * px[q];
+    }
+    if (!acc) return;
+    double zl[W], zu[W], pzl[W], pzu[W], gv[W];
     ldv<W>(lb, i, l);
     ldv<W>(ub, i, u);
-    ldv<W>(p.x, i, px);
     ldv<W>(g, i, gv);
 #pragma unroll
     for (int q = 0; q < W; q++) zl[q] = zu[q] = pzl[q] = pzu[q] = 0.0;
@@ -496,47 +504,42 @@ struct StatsF {
       ldv<W>(v.zu, i, zu);
       ldv<W>(p.zu, i, pzu);
     }
+    AccT &a = *acc;
 #pragma unroll
     for (int q = 0; q < W; q++) {
-      Elem t;
-      t.c0 = t.c1 = t.c2 = t.c3 = 0.0;
-      t.lpos = t.lneg = t.ppos = t.pneg = 0.0;
-      t.mx = 1.0e300;
-      t.mz = 1.0e300;
       const double dl = x[q] - l[q], du = u[q] - x[q];
+      const double pxq = px[q];
       if (k.use_lower) {
-        if (px[q] < 0.0) t.mx = fmin(t.mx, -tau * dl / px[q]);
-        if (pzl[q] < 0.0) t.mz = fmin(t.mz, -tau * zl[q] / pzl[q]);
+        if (pxq < 0.0) a.m[0] = fmin(a.m[0], -tau * dl / pxq);
+        if (pzl[q] < 0.0) a.m[1] = fmin(a.m[1], -tau * zl[q] / pzl[q]);
         if (l[q] > -k.mbv) {
-          t.c0 += zl[q] * dl;
-          t.c1 += zl[q] * px[q];
-          t.c2 += pzl[q] * dl;
-          t.c3 += pzl[q] * px[q];
+          a.s[0] = fma(zl[q], dl, a.s[0]);
+          a.s[1] = fma(zl[q], pxq, a.s[1]);
+          a.s[2] = fma(pzl[q], dl, a.s[2]);
+          a.s[3] = fma(pzl[q], pxq, a.s[3]);
           const double lg = log(dl);
-          if (dl > 1.0) t.lpos += lg; else t.lneg += lg;
-          const double r = px[q] / dl;
-          if (px[q] > 0.0) t.ppos += r; else t.pneg += r;
+          if (dl > 1.0) a.s[8] += lg; else a.s[9] += lg;
+          const double r = pxq / dl;
+          if (pxq > 0.0) a.s[10] += r; else a.s[11] += r;
         }
       }
       if (k.use_upper) {
-        if (px[q] > 0.0) t.mx = fmin(t.mx, tau * du / px[q]);
-        if (pzu[q] < 0.0) t.mz = fmin(t.mz, -tau * zu[q] / pzu[q]);
+        if (pxq > 0.0) a.m[0] = fmin(a.m[0], tau * du / pxq);
+        if (pzu[q] < 0.0) a.m[1] = fmin(a.m[1], -tau * zu[q] / pzu[q]);
         if (u[q] < k.mbv) {
-          t.c0 += zu[q] * du;
-          t.c1 -= zu[q] * px[q];
-          t.c2 += pzu[q] * du;
-          t.c3 -= pzu[q] * px[q];
+          a.s[0] = fma(zu[q], du, a.s[0]);
+          a.s[1] = fma(-zu[q], pxq, a.s[1]);
+          a.s[2] = fma(pzu[q], du, a.s[2]);
+          a.s[3] = fma(-pzu[q], pxq, a.s[3]);
           const double lg = log(du);
-          if (du > 1.0) t.lpos += lg; else t.lneg += lg;
-          const double r = px[q] / du;
-          if (px[q] > 0.0) t.pneg -= r; else t.ppos -= r;
+          if (du > 1.0) a.s[8] += lg; else a.s[9] += lg;
+          const double r = pxq / du;
+          if (pxq > 0.0) a.s[11] -= r; else a.s[10] -= r;
         }
       }
-      t.gp = gv[q] * px[q];
-      t.pp = px[q] * px[q];
-      e[q] = t;
-      part[q][0] = coef[q] * x[q];
-      part[q][1] = coef[q] * px[q];
+      a.s[16] = fma(gv[q], pxq, a.s[16]);
+      a.s[17] = fma(pxq, pxq, a.s[17]);
+      a.x[0] = fmax(a.x[0], fabs(pxq));
     }
   }
   __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
@@ -568,25 +571,8 @@ struct StatsF {
   }
   template <int W>
   __device__ __forceinline__ void C(long long, const double (&)[W],
-                                    const Elem (&e)[W], const Con &,
-                                    AccT &acc) const {
-#pragma unroll
-    for (int q = 0; q < W; q++) {
-      acc.s[0] += e[q].c0;
-      acc.s[1] += e[q].c1;
-      acc.s[2] += e[q].c2;
-      acc.s[3] += e[q].c3;
-      acc.s[8] += e[q].lpos;
-      acc.s[9] += e[q].lneg;
-      acc.s[10] += e[q].ppos;
-      acc.s[11] += e[q].pneg;
-      acc.s[16] += e[q].gp;
-      acc.s[17] += e[q].pp;
-      acc.x[0] = fmax(acc.x[0], sqrt(e[q].pp));
-      acc.m[0] = fmin(acc.m[0], e[q].mx);
-      acc.m[1] = fmin(acc.m[1], e[q].mz);
-    }
-  }
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {}
 };
 
 // ============================================================== TrialF
@@ -611,7 +597,7 @@ struct TrialF {
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][1]) const {
+                                    Elem (&e)[W], double (&part)[W][1], AccT *acc) const {
     double x[W], l[W], u[W], px[W], r[W];
     ldv<W>(v.x, i, x);
     ldv<W>(lb, i, l);
@@ -681,7 +667,7 @@ struct Update1F {
 
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &con,
                                     AccT &) const {
     const double zwn = fma(az, p.zw[ci], v.zw[ci]);  // no clipping (IP.cpp:4181)
@@ -761,7 +747,7 @@ struct Update2F {
   __device__ __forceinline__ void A_unused() const {}
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &con,
                                     AccT &) const {
     con.d[0] = zw[ci];
@@ -812,7 +798,7 @@ struct LinCombF {
   double *out;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -835,5 +821,78 @@ struct LinCombF {
       for (int q = 0; q < W; q++) o[q] = fma(alpha.v[j], c[q], o[q]);
     }
     stv<W>(out, i, o);
+  }
+};
+
+// ============================================================== Pass1RF<MR>
+// Pass1F fused with the reductions r_j = V_j . t1 (j < m <= MR) that the
+// reference obtains with y.x->mdot(Ac) and step.x->mdot(Z) (IP.cpp:2142-2143,
+// 2718): t1 never goes to memory.
+// Traffic: reads (7 + m)N + 10W, writes N + W.   sums: 0..m-1 = [A|Z]^T t1
+template <int MR>
+struct Pass1RF {
+  static constexpr int NS = MR, NX = 0, NM = 0, NB = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // yw
+  struct Elem {
+    double d1, dinv;
+  };
+  DVars v, b;
+  const double *lb, *ub, *Dinv, *Cw;
+  double *d1, *d2;
+  ColTable V;
+  int m;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1],
+                                    AccT *) const {
+    double x[W], l[W], u[W], bx[W], bzl[W], bzu[W], di[W], d[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(b.x, i, bx);
+    ldv<W>(Dinv, i, di);
+#pragma unroll
+    for (int q = 0; q < W; q++) bzl[q] = bzu[q] = 0.0;
+    if (k.use_lower) ldv<W>(b.zl, i, bzl);
+    if (k.use_upper) ldv<W>(b.zu, i, bzu);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      double t = bx[q];
+      if (k.use_lower && l[q] > -k.mbv) t += bzl[q] / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv) t -= bzu[q] / (u[q] - x[q]);
+      d[q] = t;
+      e[q].d1 = t;
+      e[q].dinv = di[q];
+      part[q][0] = coef[q] * di[q] * t;
+    }
+    stv<W>(d1, i, d);
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
+                                    Con &con, AccT &) const {
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double dd = b.zw[ci] + (b.zsw[ci] + sw * b.sw[ci]) / zsw -
+                      (b.ztw[ci] + tw * b.tw[ci]) / ztw;
+    con.d[0] = Cw[ci] * (dd - sum[0]);
+    d2[ci] = dd;
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AccT &acc) const {
+    double t[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+#pragma unroll
+    for (int j = 0; j < MR; j++) {
+      if (j < m) {
+        double c[W];
+        ldv<W>(V.p[j], i, c);
+#pragma unroll
+        for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
+      }
+    }
   }
 };

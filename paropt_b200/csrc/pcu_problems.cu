@@ -8,15 +8,6 @@
 #include "pcu_kernels.cuh"
 #include "pcu_problem.cuh"
 
-template <class F>
-int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
-                    RedBuf rb) {
-  const int grid = pcu_grid_for(ctx, n);
-  tile_kernel<F><<<grid, PCU_THREADS, 0, ctx->stream>>>(f, n, w, rb);
-  ctx->launches++;
-  PCU_CUDA_OK(cudaGetLastError());
-  return 0;
-}
 
 WDesc pcu_make_wdesc(const pcu_weighting &w, int nvars) {
   WDesc d;
@@ -84,7 +75,7 @@ struct SQInitF {  // lam, b, vh fill + sum vh^2
   double *lam, *b, *vh;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -116,7 +107,7 @@ struct SQBoundsF {  // getVarsAndBounds
   double *x, *lb, *ub;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -153,7 +144,7 @@ struct SQObjF {
   uint64_t keys[8];
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -201,7 +192,7 @@ struct SQGrad1F {
   double *g;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -237,7 +228,7 @@ struct SQGrad2F {  // g = (w - hf2 * vh) + b
   double *g;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -265,7 +256,7 @@ struct SQConGradF {  // A_j[i] = a_lo + a_w u(100 + j, gi), up to 8 columns
   int nj;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -428,7 +419,7 @@ struct RosenObjF {  // examples/rosenbrock/rosenbrock.cpp:49-79
   long long n;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -459,7 +450,7 @@ struct RosenGradF {  // rosenbrock.cpp:82-107
   long long n;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>

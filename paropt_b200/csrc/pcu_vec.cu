@@ -109,6 +109,49 @@ int pcu_ctx::fetch(double *out) {
   return 0;
 }
 
+void pcu_ctx::prof_begin(const char *name) {
+  if (!profiling) return;
+  if (prof_pool.empty()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    prof_pool.push_back({a, b});
+  }
+  ProfPending p;
+  p.name = name;
+  p.e0 = prof_pool.back().first;
+  p.e1 = prof_pool.back().second;
+  prof_pool.pop_back();
+  cudaEventRecord(p.e0, stream);
+  prof_pending.push_back(p);
+}
+
+void pcu_ctx::prof_end() {
+  if (!profiling || prof_pending.empty()) return;
+  cudaEventRecord(prof_pending.back().e1, stream);
+}
+
+void pcu_ctx::prof_collect() {
+  for (auto &p : prof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.e1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      std::string name(p.name);
+      size_t pos = name.find("F = ");
+      if (pos != std::string::npos) {
+        name = name.substr(pos + 4);
+        size_t end = name.find_first_of("];");
+        if (end != std::string::npos) name = name.substr(0, end);
+      }
+      ProfTotal &t = prof_totals[name];
+      t.ms += ms;
+      t.count += 1;
+    }
+    prof_pool.push_back({p.e0, p.e1});
+  }
+  prof_pending.clear();
+}
+
 int pcu_ctx::big_reserve(size_t nresult, size_t npartials) {
   if (nresult > big_cap) {
     if (d_big) cudaFree(d_big);
@@ -159,6 +202,7 @@ pcu_ctx *pcu_ctx_create(int device) {
   ctx->device = device;
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
+  ctx->num_sms = prop.multiProcessorCount;
   ctx->grid = prop.multiProcessorCount * 4;
   if (ctx->grid > PCU_MAX_BLOCKS) ctx->grid = PCU_MAX_BLOCKS;
   bool ok = true;
@@ -243,6 +287,31 @@ int pcu_ctx_sync(pcu_ctx *ctx) {
 }
 void *pcu_ctx_stream(pcu_ctx *ctx) { return (void *)ctx->stream; }
 int64_t pcu_ctx_kernel_launches(pcu_ctx *ctx) { return ctx->launches; }
+int pcu_ctx_profile(pcu_ctx *ctx, int enable) {
+  cudaStreamSynchronize(ctx->stream);
+  ctx->prof_collect();
+  if (enable == 2) ctx->prof_totals.clear();
+  ctx->profiling = enable != 0;
+  return 0;
+}
+int pcu_ctx_profile_count(pcu_ctx *ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  ctx->prof_collect();
+  return (int)ctx->prof_totals.size();
+}
+int pcu_ctx_profile_get(pcu_ctx *ctx, int index, char *name, int name_len,
+                        double *ms, int64_t *count) {
+  int i = 0;
+  for (auto &kv : ctx->prof_totals) {
+    if (i++ == index) {
+      snprintf(name, name_len, "%s", kv.first.c_str());
+      *ms = kv.second.ms;
+      *count = kv.second.count;
+      return 0;
+    }
+  }
+  return 1;
+}
 int pcu_ctx_timer_start(pcu_ctx *ctx) {
   PCU_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
   return 0;
@@ -278,7 +347,7 @@ struct VecOpF {
   const double *x;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -313,7 +382,7 @@ struct VecRedF {
   const double *x, *y;
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1]) const {}
+                                    double (&)[W][1], AccT *acc) const {}
   __device__ __forceinline__ void B(long long, const double (&)[1], Con &,
                                     AccT &) const {}
   template <int W>
@@ -413,9 +482,11 @@ int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
   const int grid = pcu_grid_for(ctx, n);
   for (int c0 = 0; c0 < ncols; c0 += KC) {
     const int nc = (ncols - c0 < KC) ? ncols - c0 : KC;
+    ctx->prof_begin("mdot_kernel");
     mdot_kernel<KC><<<grid, PCU_THREADS, 0, ctx->stream>>>(
         x, cols, c0, nc, n, ctx->d_big_partials, ctx->d_counter,
         ctx->d_big + dst_off);
+    ctx->prof_end();
     ctx->launches++;
   }
   PCU_CUDA_OK(cudaGetLastError());
@@ -426,11 +497,7 @@ template <class F>
 static int launch_plain(pcu_ctx *ctx, const F &f, long long n, RedBuf rb) {
   WDesc w;
   memset(&w, 0, sizeof(w));
-  const int grid = pcu_grid_for(ctx, n);
-  tile_kernel<F><<<grid, PCU_THREADS, 0, ctx->stream>>>(f, n, w, rb);
-  ctx->launches++;
-  PCU_CUDA_OK(cudaGetLastError());
-  return 0;
+  return pcu_launch_tile(ctx, f, n, w, rb);
 }
 
 static int vec_reduce(pcu_vec *x, pcu_vec *y, double out[4]) {
