@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ldl"]
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-ldl"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -22,7 +22,7 @@
 #include "pcu_ctx.cuh"
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, "
       "{%0,%1};"
       : "+d"(c[0]), "+d"(c[1])
@@ -76,42 +76,74 @@ __global__ void __launch_bounds__(PCU_THREADS)
     colB[t] = (c < m) ? cols.p[c] : nullptr;
   }
 
+  // Software-pipelined walk over this warp's 64-row chunks, 8 rows per step:
+  // the loads of step s+1 are issued before the DMMAs of step s.
   const long long nchunks = (n + 63) / 64;
-  for (long long chunk = gwarp; chunk < nchunks; chunk += nwarps) {
-#pragma unroll 1
-    for (int step = 0; step < 8; step++) {
-      const long long r0 = chunk * 64 + step * 8;
-      if (r0 >= n) break;
-      const long long r = r0 + 2 * kk;
-      const bool ok0 = r < n, ok1 = (r + 1) < n;
-      double2 wv = make_double2(0.0, 0.0);
-      if (ok1) {
-        wv = Dinv ? *reinterpret_cast<const double2 *>(Dinv + r)
+  struct Frag {
+    double2 wv;
+    double2 fb[NTB];
+    double2 fa[DIAG ? 1 : NTA];
+  };
+  auto load_step = [&](long long r0, Frag &f) {
+    const long long r = r0 + 2 * kk;
+    const bool ok0 = r < n, ok1 = (r + 1) < n;
+    f.wv = make_double2(0.0, 0.0);
+    if (ok1) {
+      f.wv = Dinv ? *reinterpret_cast<const double2 *>(Dinv + r)
                   : make_double2(1.0, 1.0);
-      } else if (ok0) {
-        wv.x = Dinv ? Dinv[r] : 1.0;
-      }
-      double2 fa[NTA], fb[NTB];
+    } else if (ok0) {
+      f.wv.x = Dinv ? Dinv[r] : 1.0;
+    }
 #pragma unroll
-      for (int t = 0; t < NTB; t++) {
-        double2 f = make_double2(0.0, 0.0);
-        if (colB[t]) {
-          if (ok1) f = *reinterpret_cast<const double2 *>(colB[t] + r);
-          else if (ok0) f.x = colB[t][r];
-        }
-        fb[t] = f;
+    for (int t = 0; t < NTB; t++) {
+      double2 v = make_double2(0.0, 0.0);
+      if (colB[t]) {
+        if (ok1) v = *reinterpret_cast<const double2 *>(colB[t] + r);
+        else if (ok0) v.x = colB[t][r];
       }
+      f.fb[t] = v;
+    }
+    if (!DIAG) {
 #pragma unroll
       for (int t = 0; t < NTA; t++) {
-        double2 f = make_double2(0.0, 0.0);
-        if (DIAG) {
-          f = fb[t < NTB ? t : 0];
-        } else if (colA[t]) {
-          if (ok1) f = *reinterpret_cast<const double2 *>(colA[t] + r);
-          else if (ok0) f.x = colA[t][r];
+        double2 v = make_double2(0.0, 0.0);
+        if (colA[t]) {
+          if (ok1) v = *reinterpret_cast<const double2 *>(colA[t] + r);
+          else if (ok0) v.x = colA[t][r];
         }
+        f.fa[t] = v;
+      }
+    }
+  };
+
+  long long chunk = gwarp;
+  int step = 0;
+  bool have = chunk < nchunks;
+  Frag cur, nxt;
+  if (have) load_step(chunk * 64, cur);
+  while (have) {
+    long long nchunk = chunk;
+    int nstep = step + 1;
+    if (nstep == 8) {
+      nstep = 0;
+      nchunk += nwarps;
+    }
+    const long long r0 = chunk * 64 + step * 8;
+    bool nhave = nchunk < nchunks;
+    if (nhave && nchunk * 64 + nstep * 8 >= n) {  // ragged last chunk
+      nhave = false;
+    }
+    if (nhave) load_step(nchunk * 64 + nstep * 8, nxt);
+    {
+      const long long r = r0 + 2 * kk;
+      const double2 wv = cur.wv;
+      double2 fa[NTA];
+#pragma unroll
+      for (int t = 0; t < NTA; t++) {
+        const double2 f = DIAG ? cur.fb[t < NTB ? t : 0] : cur.fa[DIAG ? 0 : t];
         fa[t] = make_double2(f.x * wv.x, f.y * wv.y);
       }
+      const double2 *fb = cur.fb;
       {
         int p = 0;
 #pragma unroll
@@ -207,6 +239,10 @@ __global__ void __launch_bounds__(PCU_THREADS)
         }
       }
     }
+    cur = nxt;
+    chunk = nchunk;
+    step = nstep;
+    have = nhave;
   }
 
   // ---- CTA combine (pair by pair), then grid combine by the last block ----
