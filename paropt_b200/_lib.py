@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libparopt_b200.so")
+LIB_PATH = os.environ.get("PCU_LIB", os.path.join(HERE, "libparopt_b200.so"))
 
 _lib = None
 

@@ -6,14 +6,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libparopt_b200.so")
+LIB = os.path.join(HERE, os.environ.get("PCU_LIB_NAME", "libparopt_b200.so"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
     "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-Xptxas", "-v" if os.environ.get("PCU_PTXAS_V") else "-O3",
-]
+] + os.environ.get("PCU_EXTRA_FLAGS", "").split()
 
 
 def needs_build():
@@ -30,9 +30,10 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build", os.path.basename(LIB))
+    os.makedirs(bdir, exist_ok=True)
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE,
                                             stderr=subprocess.STDOUT, text=True)))

@@ -108,6 +108,7 @@ struct RedBuf {
   double *partials;        // [gridDim.x][NR]
   unsigned int *counter;   // zero before launch, reset by the last block
   double *result;          // [NR] device
+  int prefetch;            // grid-stride iterations to prefetch ahead into L2 (0: off)
 };
 
 // Block-level + grid-level deterministic combine.  Every thread of the block
@@ -178,6 +179,39 @@ __device__ void finish_reduction(Acc<NS, NX, NM> &acc, const RedBuf &rb) {
   }
 }
 
+// ------------------------------------------------------------ L2 prefetch
+// The fused kernels read 10-35 independent streams with 50-130 registers per
+// thread, i.e. at 20-50 % occupancy: not enough loads in flight to cover DRAM
+// latency.  Instead of buying occupancy, each warp asks the L2 for the 512-byte
+// slice of every stream that it will touch in its NEXT grid-stride iteration
+// (cp.async.bulk.prefetch.L2, one instruction per stream, spread over the
+// lanes): the demand loads then hit in L2 and DRAM runs one iteration ahead.
+struct NoStreams {
+  static constexpr int MINB = 7;  // __launch_bounds__ minimum blocks per SM (<= 73 regs)
+  template <class P>
+  __device__ __forceinline__ void streams(P &) const {}
+};
+struct Prefetcher {
+  long long off;  // element offset of the warp's next 64-element slice
+  int lane;
+  int idx;
+  __device__ __forceinline__ void operator()(const double *ptr) {
+    if (ptr != nullptr && ((idx++) & 31) == lane) {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + off),
+                   "r"(512)
+                   : "memory");
+    }
+  }
+};
+
+struct PrefetcherNow {  // same-iteration prefetch of the thread's own 16 bytes
+  long long i;
+  __device__ __forceinline__ void operator()(const double *ptr) {
+    if (ptr != nullptr)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + i) : "memory");
+  }
+};
+
 // ------------------------------------------------------------ tile harness
 // A fused kernel is a functor F with
 //   static constexpr int NS, NX, NM   number of sum / max / min accumulators
@@ -244,7 +278,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
 }
 
 template <class F>
-__global__ void __launch_bounds__(PCU_TILE_THREADS)
+__global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
     tile_kernel(const F f, const long long n, const WDesc w, const RedBuf rb) {
   constexpr int NB = F::NB > 0 ? F::NB : 1;
   typename F::AccT acc;
@@ -262,6 +296,18 @@ __global__ void __launch_bounds__(PCU_TILE_THREADS)
     const int half = (w.mode == 1) ? (w.nw >> 1) : 1;  // lanes per constraint
     for (long long v = tid; v < nvec_main; v += nthreads) {
       const long long i = 2 * v;
+      if (rb.prefetch < 0) {
+        PrefetcherNow pn;
+        pn.i = i;
+        f.streams(pn);
+      }
+      if (rb.prefetch > 0 && v + rb.prefetch * nthreads < nvec_main) {
+        Prefetcher pf;
+        pf.lane = threadIdx.x & 31;
+        pf.off = 2 * (v + rb.prefetch * nthreads - pf.lane);
+        pf.idx = 0;
+        f.streams(pf);
+      }
       typename F::Elem e[2];
       double coef[2] = {0.0, 0.0};
       double part[2][NB];

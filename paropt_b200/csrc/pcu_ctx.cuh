@@ -38,6 +38,8 @@ struct pcu_ctx {
 
   int grid = 148 * 4;
   int num_sms = 148;
+  int max_blocks_per_sm = 16;  // occupancy cap of the streaming kernels
+  int prefetch = -1;           // -1: same-iteration L2 prefetch; k > 0: k iterations ahead; 0 off
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -116,10 +118,12 @@ int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
   }
   long long need = (n / 2 + PCU_TILE_THREADS - 1) / PCU_TILE_THREADS;
   if (need < 1) need = 1;
-  long long cap = (long long)ctx->num_sms * blocks_per_sm;
+  int bps = blocks_per_sm < ctx->max_blocks_per_sm ? blocks_per_sm : ctx->max_blocks_per_sm;
+  long long cap = (long long)ctx->num_sms * bps;
   if (cap > PCU_MAX_BLOCKS) cap = PCU_MAX_BLOCKS;
   const int grid = (int)(need < cap ? need : cap);
   ctx->prof_begin(pcu_kernel_name<F>());
+  rb.prefetch = ctx->prefetch;
   tile_kernel<F><<<grid, PCU_TILE_THREADS, 0, ctx->stream>>>(f, n, w, rb);
   ctx->prof_end();
   ctx->launches++;

@@ -152,6 +152,18 @@ __global__ void __launch_bounds__(PCU_THREADS)
           for (int tj = 0; tj < NTB; tj++) {
             if (!DIAG || tj <= ti) {
               dmma884(acc[p], fa[ti].x, fb[tj].x);
+              p++;
+            }
+          }
+        }
+        // second half of the 8 rows: the two DMMAs on one accumulator are kept
+        // NP instructions apart so they never issue back to back
+        p = 0;
+#pragma unroll
+        for (int ti = 0; ti < NTA; ti++) {
+#pragma unroll
+          for (int tj = 0; tj < NTB; tj++) {
+            if (!DIAG || tj <= ti) {
               dmma884(acc[p], fa[ti].y, fb[tj].y);
               p++;
             }

@@ -19,7 +19,7 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
 
 #define launch_tile pcu_launch_tile
 
-static const RedBuf NO_RED = {nullptr, nullptr, nullptr};
+static const RedBuf NO_RED = {nullptr, nullptr, nullptr, 0};
 
 // ------------------------------------------------------------ small dense LU
 // Same algorithm as LAPACK dgetrf/dgetrs (partial pivoting, column-major), used
@@ -501,7 +501,7 @@ int pcu_ip::evalObjConGradient(pcu_vec *x) {
 
 // ---------------------------------------------- initAndCheckDesignAndBounds
 // IP.cpp:4277-4361
-struct BoundsF {
+struct BoundsF : NoStreams {
   static constexpr int NS = 0, NX = 3, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;

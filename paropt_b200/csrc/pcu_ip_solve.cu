@@ -16,7 +16,7 @@ int pcu_lu_factor(int n, double *A, int *piv);
 void pcu_lu_solve(int n, const double *LU, const int *piv, double *b);
 
 #define launch_tile pcu_launch_tile
-static const RedBuf NO_RED = {nullptr, nullptr, nullptr};
+static const RedBuf NO_RED = {nullptr, nullptr, nullptr, 0};
 
 // LS flags (IP.h:220-225)
 enum {
@@ -292,7 +292,7 @@ int pcu_ip::stepStats(Vars &vars, Vars &step, double tau, double *sums,
 
 // ---------------------------------------------- initLeastSquaresMultipliers
 // IP.cpp:5366-5534
-struct MaskBoundMultF {  // zl = 0 where lb <= -mbv, zu = 0 where ub >= mbv
+struct MaskBoundMultF : NoStreams {  // zl = 0 where lb <= -mbv, zu = 0 where ub >= mbv
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -348,7 +348,7 @@ struct MaskBoundMultF {  // zl = 0 where lb <= -mbv, zu = 0 where ub >= mbv
   }
 };
 
-struct SparseStartF {  // W-sized pieces of the starting-point strategies
+struct SparseStartF : NoStreams {  // W-sized pieces of the starting-point strategies
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -529,7 +529,7 @@ int pcu_ip::initAffineStepMultipliers() {
 }
 
 // ------------------------------------------------------------------ history
-struct StateSumF {  // checksums of the iterate for the parity history
+struct StateSumF : NoStreams {  // checksums of the iterate for the parity history
   static constexpr int NS = 7, NX = 1, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;

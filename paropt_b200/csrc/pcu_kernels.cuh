@@ -17,6 +17,17 @@
 
 #include "pcu_common.cuh"
 
+// occupancy hints (blocks of 128 threads per SM) of the register-heavy kernels
+#ifndef PCU_MINB_RES
+#define PCU_MINB_RES 6
+#endif
+#ifndef PCU_MINB_STATS
+#define PCU_MINB_STATS 5
+#endif
+#ifndef PCU_MINB_PASS1
+#define PCU_MINB_PASS1 5
+#endif
+
 struct DVars {  // device view of ParOptVars (IP.h:373-389)
   double *x, *zl, *zu;               // N
   double *zw, *sw, *tw, *zsw, *ztw;  // W
@@ -58,7 +69,8 @@ struct Con1 {  // one broadcast value
 //       constraint), 2 sparse comp product,
 //       3 norm-sum rx, 4 norm-sum rzw, 5..8 l1 of rsw,rtw,rzsw,rztw,
 //       9,10 norm-sum rzl, rzu;   maxima: 0 |rx|, 1 |rzw|, 2 dual parts
-struct ResF {
+struct ResF : NoStreams {
+  static constexpr int MINB = PCU_MINB_RES;
   static constexpr int NS = 11, NX = 3, NM = 0, NB = 2;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // zw (+ pzw)
@@ -78,6 +90,20 @@ struct ResF {
   int has_step;
   int norm_type;  // 0 infinity, 1 l1, 2 l2
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) p_(v.zl);
+    if (k.use_upper) p_(v.zu);
+    for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
+    if (has_step) {
+      p_(p.x);
+      if (k.use_lower) p_(p.zl);
+      if (k.use_upper) p_(p.zu);
+      for (int j = 0; j < nq; j++) p_(Z.p[j]);
+    }
+  }
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
@@ -224,7 +250,7 @@ struct ResF {
 // Aw^T).  identity != 0 gives the matrices of initLeastSquaresMultipliers
 // (IP.cpp:5418-5431): Dinv = 1, Cdiag = small.
 // Traffic: reads 5N + 4W, writes N + W.
-struct DiagF {
+struct DiagF : NoStreams {
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -236,6 +262,15 @@ struct DiagF {
   int identity;
   double small_;
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    if (!identity) {
+      p_(v.x); p_(lb); p_(ub);
+      if (k.use_lower) p_(v.zl);
+      if (k.use_upper) p_(v.zu);
+    }
+  }
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
@@ -281,7 +316,7 @@ struct DiagF {
 // First half of solveKKTDiagSystem (IP.cpp:2091-2139): d1, d2 and the first
 // ParOptQuasiDefBlockMat::apply (SM.cpp:160-190), t1 = D0^-1 (d1, d2)|x.
 // Traffic: reads 7N + 10W, writes 2N + W.
-struct Pass1F {
+struct Pass1F : NoStreams {
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // yw
@@ -345,7 +380,7 @@ struct Pass1F {
 // accumulate != 0 adds the result to the step (update.add(refine), IP.cpp:4990).
 // Traffic: reads (9 + c + q)N + 10W, writes 3N + 5W (+3N + 5W reads when
 // accumulating).
-struct Pass2F {
+struct Pass2F : NoStreams {
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // yw
@@ -359,6 +394,19 @@ struct Pass2F {
   int ncols;
   int accumulate;
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(d1); p_(Dinv); p_(v.x); p_(lb); p_(ub);
+    if (k.use_lower) { p_(v.zl); p_(b.zl); }
+    if (k.use_upper) { p_(v.zu); p_(b.zu); }
+    for (int j = 0; j < ncols; j++) p_(V.p[j]);
+    if (accumulate) {
+      p_(y.x);
+      if (k.use_lower) p_(y.zl);
+      if (k.use_upper) p_(y.zu);
+    }
+  }
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
@@ -465,7 +513,8 @@ struct Pass2F {
 //         16 g.p; 17 p.p; 18 gam.(sw,tw); 19 gam.(psw,ptw);
 //         20 |cw - sw + tw|^2; 21 (cw - sw + tw).(Aw p - psw + ptw)
 //   maxima: 0 |px|_inf;  mins: 0 max_x, 1 max_z
-struct StatsF {
+struct StatsF : NoStreams {
+  static constexpr int MINB = PCU_MINB_STATS;
   static constexpr int NS = 22, NX = 1, NM = 2, NB = 2;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -474,6 +523,13 @@ struct StatsF {
   const double *lb, *ub, *g;
   double tau;
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(p.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) { p_(v.zl); p_(p.zl); }
+    if (k.use_upper) { p_(v.zu); p_(p.zu); }
+  }
 
   // All element reductions happen here (acc is null on the generic path's
   // first, sum-only visit of an element).
@@ -509,28 +565,59 @@ struct StatsF {
     for (int q = 0; q < W; q++) {
       const double dl = x[q] - l[q], du = u[q] - x[q];
       const double pxq = px[q];
+      const bool ml = k.use_lower && l[q] > -k.mbv;
+      const bool mu_ = k.use_upper && u[q] < k.mbv;
+      // Fraction to the boundary (IP.cpp:2959-2982, 3064-3091): the quotient is
+      // only formed for elements that can lower the running minimum (the
+      // product test keeps a 1e-12 slack so no candidate is lost).
       if (k.use_lower) {
-        if (pxq < 0.0) a.m[0] = fmin(a.m[0], -tau * dl / pxq);
-        if (pzl[q] < 0.0) a.m[1] = fmin(a.m[1], -tau * zl[q] / pzl[q]);
-        if (l[q] > -k.mbv) {
-          a.s[0] = fma(zl[q], dl, a.s[0]);
-          a.s[1] = fma(zl[q], pxq, a.s[1]);
-          a.s[2] = fma(pzl[q], dl, a.s[2]);
-          a.s[3] = fma(pzl[q], pxq, a.s[3]);
+        if (pxq < 0.0 && tau * dl <= -a.m[0] * pxq * (1.0 + 1e-12))
+          a.m[0] = fmin(a.m[0], -tau * dl / pxq);
+        if (pzl[q] < 0.0 && tau * zl[q] <= -a.m[1] * pzl[q] * (1.0 + 1e-12))
+          a.m[1] = fmin(a.m[1], -tau * zl[q] / pzl[q]);
+      }
+      if (k.use_upper) {
+        if (pxq > 0.0 && tau * du <= a.m[0] * pxq * (1.0 + 1e-12))
+          a.m[0] = fmin(a.m[0], tau * du / pxq);
+        if (pzu[q] < 0.0 && tau * zu[q] <= -a.m[1] * pzu[q] * (1.0 + 1e-12))
+          a.m[1] = fmin(a.m[1], -tau * zu[q] / pzu[q]);
+      }
+      if (ml) {
+        a.s[0] = fma(zl[q], dl, a.s[0]);
+        a.s[1] = fma(zl[q], pxq, a.s[1]);
+        a.s[2] = fma(pzl[q], dl, a.s[2]);
+        a.s[3] = fma(pzl[q], pxq, a.s[3]);
+      }
+      if (mu_) {
+        a.s[0] = fma(zu[q], du, a.s[0]);
+        a.s[1] = fma(-zu[q], pxq, a.s[1]);
+        a.s[2] = fma(pzu[q], du, a.s[2]);
+        a.s[3] = fma(-pzu[q], pxq, a.s[3]);
+      }
+      // Barrier terms (IP.cpp:3684-3722).  When both bounds exist and fall in
+      // the same (>1 / <=1) bucket, log(dl) + log(du) = log(dl * du) and the two
+      // quotients share one reciprocal: one log and one division per element.
+      if (ml && mu_ && ((dl > 1.0) == (du > 1.0))) {
+        const double prod = dl * du;
+        const double lg = log(prod);
+        if (dl > 1.0) a.s[8] += lg; else a.s[9] += lg;
+        const double rinv = 1.0 / prod;
+        const double rl = pxq * du * rinv, ru = pxq * dl * rinv;
+        if (pxq > 0.0) {
+          a.s[10] += rl;
+          a.s[11] -= ru;
+        } else {
+          a.s[11] += rl;
+          a.s[10] -= ru;
+        }
+      } else {
+        if (ml) {
           const double lg = log(dl);
           if (dl > 1.0) a.s[8] += lg; else a.s[9] += lg;
           const double r = pxq / dl;
           if (pxq > 0.0) a.s[10] += r; else a.s[11] += r;
         }
-      }
-      if (k.use_upper) {
-        if (pxq > 0.0) a.m[0] = fmin(a.m[0], tau * du / pxq);
-        if (pzu[q] < 0.0) a.m[1] = fmin(a.m[1], -tau * zu[q] / pzu[q]);
-        if (u[q] < k.mbv) {
-          a.s[0] = fma(zu[q], du, a.s[0]);
-          a.s[1] = fma(-zu[q], pxq, a.s[1]);
-          a.s[2] = fma(pzu[q], du, a.s[2]);
-          a.s[3] = fma(-pzu[q], pxq, a.s[3]);
+        if (mu_) {
           const double lg = log(du);
           if (du > 1.0) a.s[8] += lg; else a.s[9] += lg;
           const double r = pxq / du;
@@ -582,7 +669,7 @@ struct StatsF {
 // Traffic: reads 4N + 4W, writes N + 2W.
 //   sums: 0,1 pos/neg log (bounds); 2,3 pos/neg log (sw,tw); 4 gam.(rsw,rtw);
 //         5 |cw(rx) - rsw + rtw|^2
-struct TrialF {
+struct TrialF : NoStreams {
   static constexpr int NS = 6, NX = 0, NM = 0, NB = 1;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -594,6 +681,11 @@ struct TrialF {
   double *rx, *rsw, *rtw;
   double ax;
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(p.x); p_(lb); p_(ub);
+  }
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
@@ -607,13 +699,21 @@ struct TrialF {
     for (int q = 0; q < W; q++) {
       r[q] = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
       double lp = 0.0, ln = 0.0;
-      if (k.use_lower && l[q] > -k.mbv) {
-        const double d = r[q] - l[q], lg = log(d);
-        if (d > 1.0) lp += lg; else ln += lg;
-      }
-      if (k.use_upper && u[q] < k.mbv) {
-        const double d = u[q] - r[q], lg = log(d);
-        if (d > 1.0) lp += lg; else ln += lg;
+      const bool ml = k.use_lower && l[q] > -k.mbv;
+      const bool mu_ = k.use_upper && u[q] < k.mbv;
+      const double dl = r[q] - l[q], du = u[q] - r[q];
+      if (ml && mu_ && ((dl > 1.0) == (du > 1.0))) {
+        const double lg = log(dl * du);  // log(dl) + log(du), same bucket
+        if (dl > 1.0) lp += lg; else ln += lg;
+      } else {
+        if (ml) {
+          const double lg = log(dl);
+          if (dl > 1.0) lp += lg; else ln += lg;
+        }
+        if (mu_) {
+          const double lg = log(du);
+          if (du > 1.0) lp += lg; else ln += lg;
+        }
       }
       e[q].lpos = lp;
       e[q].lneg = ln;
@@ -651,7 +751,7 @@ struct TrialF {
 // step (ax = alpha*alpha_x for primal, az = alpha*alpha_z for dual parts) and
 // y_qn = -g + sum_j z_j A_j + Aw^T zw with the NEW multipliers and the OLD
 // gradients.  Traffic: reads (6 + c)N + 10W, writes 4N + 5W.
-struct Update1F {
+struct Update1F : NoStreams {
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // new zw
@@ -664,6 +764,17 @@ struct Update1F {
   double *yqn;  // null when no quasi-Newton pair is formed
   double ax, az;
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(p.x); p_(lb); p_(ub);
+    if (k.use_lower) { p_(v.zl); p_(p.zl); }
+    if (k.use_upper) { p_(v.zu); p_(p.zu); }
+    if (yqn) {
+      p_(g);
+      for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
+    }
+  }
 
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
@@ -731,7 +842,7 @@ struct Update1F {
 // fused with the three dot products that open ParOptLBFGS::update /
 // ParOptLSR1::update (QN.cpp:168-170, 641-642).
 // Traffic: reads (3 + c)N + W, writes 2N.   sums: 0 y.y, 1 y.s, 2 s.s
-struct Update2F {
+struct Update2F : NoStreams {
   static constexpr int NS = 3, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // zw
@@ -742,6 +853,12 @@ struct Update2F {
   int ncon;
   double *yqn, *sqn;
   double ax;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(yqn); p_(g); p_(px);
+    for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
+  }
 
   template <int W>
   __device__ __forceinline__ void A_unused() const {}
@@ -785,7 +902,7 @@ struct Update2F {
 // out = beta * x + sum_j alpha_j V_j   (ParOptLBFGS::mult, QN.cpp:390-418, second
 // pass; ParOptLSR1's Z_i = Y_i - b0 S_i, QN.cpp:730-735; damped-update vector).
 // Traffic: reads (1 + ncols)N, writes N.
-struct LinCombF {
+struct LinCombF : NoStreams {
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -796,6 +913,12 @@ struct LinCombF {
   CoefTable alpha;
   int ncols;
   double *out;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(x);
+    for (int j = 0; j < ncols; j++) p_(V.p[j]);
+  }
   template <int W>
   __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
                                     double (&)[W][1], AccT *acc) const {}
@@ -830,7 +953,8 @@ struct LinCombF {
 // 2718): t1 never goes to memory.
 // Traffic: reads (7 + m)N + 10W, writes N + W.   sums: 0..m-1 = [A|Z]^T t1
 template <int MR>
-struct Pass1RF {
+struct Pass1RF : NoStreams {
+  static constexpr int MINB = PCU_MINB_PASS1;
   static constexpr int NS = MR, NX = 0, NM = 0, NB = 1;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // yw
@@ -843,6 +967,14 @@ struct Pass1RF {
   ColTable V;
   int m;
   IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(lb); p_(ub); p_(b.x); p_(Dinv);
+    if (k.use_lower) p_(b.zl);
+    if (k.use_upper) p_(b.zu);
+    for (int j = 0; j < m; j++) p_(V.p[j]);
+  }
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],

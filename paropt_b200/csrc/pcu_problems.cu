@@ -66,7 +66,7 @@ struct SepQuadDev {
   uint64_t klam, kb, kv, kx;
 };
 
-struct SQInitF {  // lam, b, vh fill + sum vh^2
+struct SQInitF : NoStreams {  // lam, b, vh fill + sum vh^2
   static constexpr int NS = 1, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -98,7 +98,7 @@ struct SQInitF {  // lam, b, vh fill + sum vh^2
   }
 };
 
-struct SQBoundsF {  // getVarsAndBounds
+struct SQBoundsF : NoStreams {  // getVarsAndBounds
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -131,7 +131,7 @@ struct SQBoundsF {  // getVarsAndBounds
 };
 
 // objective + up to 8 constraint sums per pass
-struct SQObjF {
+struct SQObjF : NoStreams {
   static constexpr int NS = 9, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -182,7 +182,7 @@ struct SQObjF {
 
 // gradient stage 1: w = lam * (x - hf * vh) (+ b when not householder);
 // reduces v.w
-struct SQGrad1F {
+struct SQGrad1F : NoStreams {
   static constexpr int NS = 1, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -218,7 +218,7 @@ struct SQGrad1F {
   }
 };
 
-struct SQGrad2F {  // g = (w - hf2 * vh) + b
+struct SQGrad2F : NoStreams {  // g = (w - hf2 * vh) + b
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -245,7 +245,7 @@ struct SQGrad2F {  // g = (w - hf2 * vh) + b
   }
 };
 
-struct SQConGradF {  // A_j[i] = a_lo + a_w u(100 + j, gi), up to 8 columns
+struct SQConGradF : NoStreams {  // A_j[i] = a_lo + a_w u(100 + j, gi), up to 8 columns
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -319,7 +319,7 @@ struct SepQuadProblem : pcu_problem {
     f.x = x->d;
     f.lb = lb->d;
     f.ub = ub->d;
-    RedBuf rb = {nullptr, nullptr, nullptr};
+    RedBuf rb = {nullptr, nullptr, nullptr, 0};
     return pcu_launch_tile(ctx, f, nvars, no_weighting(), rb);
   }
 
@@ -385,7 +385,7 @@ struct SepQuadProblem : pcu_problem {
       f2.vh = vh->d;
       f2.hf2 = 2.0 * vw / vtv;
       f2.g = g->d;
-      RedBuf rb2 = {nullptr, nullptr, nullptr};
+      RedBuf rb2 = {nullptr, nullptr, nullptr, 0};
       if (pcu_launch_tile(ctx, f2, nvars, no_weighting(), rb2)) return 1;
     } else {
       // NS = 1 but unused: still needs a reduction slot for the harness
@@ -402,7 +402,7 @@ struct SepQuadProblem : pcu_problem {
         f.cols[j] = Ac[j0 + j]->d;
         f.keys[j] = stream_key(q.p.seed, 100 + (uint64_t)(j0 + j));
       }
-      RedBuf rb = {nullptr, nullptr, nullptr};
+      RedBuf rb = {nullptr, nullptr, nullptr, 0};
       if (pcu_launch_tile(ctx, f, nvars, no_weighting(), rb)) return 1;
     }
     return 0;
@@ -410,7 +410,7 @@ struct SepQuadProblem : pcu_problem {
 };
 
 // ================================================================ rosenbrock
-struct RosenObjF {  // examples/rosenbrock/rosenbrock.cpp:49-79
+struct RosenObjF : NoStreams {  // examples/rosenbrock/rosenbrock.cpp:49-79
   static constexpr int NS = 3, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -440,7 +440,7 @@ struct RosenObjF {  // examples/rosenbrock/rosenbrock.cpp:49-79
   }
 };
 
-struct RosenGradF {  // rosenbrock.cpp:82-107
+struct RosenGradF : NoStreams {  // rosenbrock.cpp:82-107
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
@@ -505,7 +505,7 @@ struct RosenProblem : pcu_problem {
     f.a0 = Ac[0]->d;
     f.a1 = Ac[1]->d;
     f.n = nvars;
-    RedBuf rb = {nullptr, nullptr, nullptr};
+    RedBuf rb = {nullptr, nullptr, nullptr, 0};
     return pcu_launch_tile(ctx, f, nvars, no_weighting(), rb);
   }
 };

@@ -2,6 +2,7 @@
 // (reference: src/ParOptVec.cpp:15-217; one fused, deterministic kernel per
 // BLAS-1 call + MPI_Allreduce pair of the reference).
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pcu_ctx.cuh"
@@ -66,6 +67,7 @@ __global__ void combine_ranks_kernel(const double *gather, double *result,
 
 RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
   RedBuf rb;
+  rb.prefetch = 0;
   rb.partials = d_partials;
   rb.counter = d_counter;
   const int nr = ns + nx + nm;
@@ -203,6 +205,8 @@ pcu_ctx *pcu_ctx_create(int device) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("PCU_MAX_BLOCKS_PER_SM")) ctx->max_blocks_per_sm = atoi(e);
+  if (const char *e = getenv("PCU_PREFETCH")) ctx->prefetch = atoi(e);
   ctx->grid = prop.multiProcessorCount * 4;
   if (ctx->grid > PCU_MAX_BLOCKS) ctx->grid = PCU_MAX_BLOCKS;
   bool ok = true;
@@ -336,7 +340,7 @@ struct NoCon {
 };
 
 // y = alpha  |  y *= alpha  |  y += alpha * x      (ParOptVec.cpp:32,177,194)
-struct VecOpF {
+struct VecOpF : NoStreams {
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef NoElem Elem;
@@ -374,7 +378,7 @@ struct VecOpF {
 };
 
 // sum x*y, sum x^2, sum |x|, max |x| in one pass (ParOptVec.cpp:63-143)
-struct VecRedF {
+struct VecRedF : NoStreams {
   static constexpr int NS = 3, NX = 1, NM = 0, NB = 0;
   typedef Acc<NS, NX, NM> AccT;
   typedef NoElem Elem;
@@ -544,7 +548,7 @@ int pcu_vec_set(pcu_vec *v, double alpha) {
   f.alpha = alpha;
   f.y = v->d;
   f.x = nullptr;
-  RedBuf rb = {nullptr, nullptr, nullptr};
+  RedBuf rb = {nullptr, nullptr, nullptr, 0};
   return launch_plain(v->ctx, f, v->n, rb);
 }
 
@@ -609,7 +613,7 @@ int pcu_vec_scale(pcu_vec *v, double alpha) {
   f.alpha = alpha;
   f.y = v->d;
   f.x = nullptr;
-  RedBuf rb = {nullptr, nullptr, nullptr};
+  RedBuf rb = {nullptr, nullptr, nullptr, 0};
   return launch_plain(v->ctx, f, v->n, rb);
 }
 
@@ -620,7 +624,7 @@ int pcu_vec_axpy(pcu_vec *y, double alpha, pcu_vec *x) {
   f.alpha = alpha;
   f.y = y->d;
   f.x = x->d;
-  RedBuf rb = {nullptr, nullptr, nullptr};
+  RedBuf rb = {nullptr, nullptr, nullptr, 0};
   return launch_plain(y->ctx, f, y->n, rb);
 }
 
