@@ -367,7 +367,7 @@ int pcu_ip_setup_kkt(pcu_ip *ip, int use_qn) {
 int pcu_ip_kkt_step(pcu_ip *ip, int res, int step, int use_qn) {
   Vars *r = bundle(ip, res), *s = bundle(ip, step);
   if (!r || !s) return 1;
-  return ip->computeKKTStep(ip->variables, *r, *s, use_qn, 0, nullptr);
+  return ip->computeKKTStep(ip->variables, *r, *s, use_qn, 0, nullptr, 0, 0.0, nullptr);
 }
 
 int pcu_ip_add_kkt_res_step(pcu_ip *ip, int step, int res) {

@@ -187,6 +187,7 @@ __device__ void finish_reduction(Acc<NS, NX, NM> &acc, const RedBuf &rb) {
 // (cp.async.bulk.prefetch.L2, one instruction per stream, spread over the
 // lanes): the demand loads then hit in L2 and DRAM runs one iteration ahead.
 struct NoStreams {
+  static constexpr int NB2 = 0;   // second-round per-constraint block sums (C2 / E phases)
   static constexpr int MINB = 7;  // __launch_bounds__ minimum blocks per SM (<= 73 regs)
   template <class P>
   __device__ __forceinline__ void streams(P &) const {}
@@ -242,7 +243,12 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       f.template A<1>(i, coef, e, part, &acc);
       typename F::Con con;
       con.zero();
-      f.template C<1>(i, coef, e, con, acc);
+      if constexpr (F::NB2 > 0) {
+        double part2[1][F::NB2];
+        f.template C2<1>(i, coef, e, con, acc, part2);
+      } else {
+        f.template C<1>(i, coef, e, con, acc);
+      }
     }
   }
   // (2) whole constraints, one thread per constraint
@@ -266,13 +272,24 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       typename F::Con con;
       con.zero();
       f.B(ci, sum, con, acc);
+      double sum2[F::NB2 > 0 ? F::NB2 : 1];
+#pragma unroll
+      for (int b = 0; b < (F::NB2 > 0 ? F::NB2 : 1); b++) sum2[b] = 0.0;
       for (int k = 0; k < w.nw; k++) {
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
         f.template A<1>(j0 + k, coef, e, part, &acc);
-        f.template C<1>(j0 + k, coef, e, con, acc);
+        if constexpr (F::NB2 > 0) {
+          double part2[1][F::NB2];
+          f.template C2<1>(j0 + k, coef, e, con, acc, part2);
+#pragma unroll
+          for (int b = 0; b < F::NB2; b++) sum2[b] += part2[0][b];
+        } else {
+          f.template C<1>(j0 + k, coef, e, con, acc);
+        }
       }
+      if constexpr (F::NB2 > 0) f.E(ci, sum2, con, acc);
     }
   }
 }
@@ -339,7 +356,24 @@ __global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
             con.d[b] = __shfl_sync(0xffffffffu, con.d[b], lead);
         }
       }
-      f.template C<2>(i, coef, e, con, acc);
+      if constexpr (F::NB2 > 0) {
+        double part2[2][F::NB2];
+        f.template C2<2>(i, coef, e, con, acc, part2);
+        if (w.mode == 1) {
+          double sum2[F::NB2];
+#pragma unroll
+          for (int b = 0; b < F::NB2; b++)
+            sum2[b] = in_con ? part2[0][b] + part2[1][b] : 0.0;
+          for (int o = 1; o < half; o <<= 1) {
+#pragma unroll
+            for (int b = 0; b < F::NB2; b++) sum2[b] += shfl_xor_d(sum2[b], o);
+          }
+          const int lane = threadIdx.x & 31;
+          if (in_con && lane == (lane & ~(half - 1))) f.E(i / w.nw, sum2, con, acc);
+        }
+      } else {
+        f.template C<2>(i, coef, e, con, acc);
+      }
     }
     const long long tail_lo = 2 * nvec_main;
     if (tail_lo < n && blockIdx.x == 0) {

@@ -42,7 +42,10 @@ __global__ void __launch_bounds__(PCU_THREADS)
                 const int m, const double *__restrict__ Dinv,
                 const double *__restrict__ Cw, const WDesc w, const long long n,
                 double *__restrict__ partials, unsigned int *counter,
-                double *__restrict__ result, const int ld) {
+                double *__restrict__ result, const int ld,
+                const long long list0, const long long list1, const int nlist,
+                const int accumulate) {
+  // nlist > 0: process only the chunks list0 [, list1] and add to `result`
   constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = lane >> 2, kk = lane & 3;
@@ -78,7 +81,10 @@ __global__ void __launch_bounds__(PCU_THREADS)
 
   // Software-pipelined walk over this warp's 64-row chunks, 8 rows per step:
   // the loads of step s+1 are issued before the DMMAs of step s.
-  const long long nchunks = (n + 63) / 64;
+  const long long nchunks = nlist > 0 ? nlist : (n + 63) / 64;
+  auto chunk_row = [&](long long c) -> long long {
+    return 64 * (nlist > 0 ? (c == 0 ? list0 : list1) : c);
+  };
   struct Frag {
     double2 wv;
     double2 fb[NTB];
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(PCU_THREADS)
   int step = 0;
   bool have = chunk < nchunks;
   Frag cur, nxt;
-  if (have) load_step(chunk * 64, cur);
+  if (have) load_step(chunk_row(chunk), cur);
   while (have) {
     long long nchunk = chunk;
     int nstep = step + 1;
@@ -128,12 +134,18 @@ __global__ void __launch_bounds__(PCU_THREADS)
       nstep = 0;
       nchunk += nwarps;
     }
-    const long long r0 = chunk * 64 + step * 8;
+    const long long r0 = chunk_row(chunk) + step * 8;
     bool nhave = nchunk < nchunks;
-    if (nhave && nchunk * 64 + nstep * 8 >= n) {  // ragged last chunk
-      nhave = false;
+    if (nhave && chunk_row(nchunk) + nstep * 8 >= n) {  // ragged last chunk
+      if (nlist > 0 && nstep != 0) {
+        nstep = 0;  // rest of this listed chunk is past the end: go to the next one
+        nchunk += nwarps;
+        nhave = nchunk < nchunks && chunk_row(nchunk) < n;
+      } else {
+        nhave = false;
+      }
     }
-    if (nhave) load_step(nchunk * 64 + nstep * 8, nxt);
+    if (nhave) load_step(chunk_row(nchunk) + nstep * 8, nxt);
     {
       const long long r = r0 + 2 * kk;
       const double2 wv = cur.wv;
@@ -302,11 +314,16 @@ __global__ void __launch_bounds__(PCU_THREADS)
       }
       const int row = colA0 + 8 * ti + (e & 7);
       const int col = colB0 + 8 * tj + (e >> 3);
-      if (row < ld && col < ld) result[(size_t)row + (size_t)ld * col] = v;
+      if (row < ld && col < ld) {
+        if (accumulate) result[(size_t)row + (size_t)ld * col] += v;
+        else result[(size_t)row + (size_t)ld * col] = v;
+      }
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
 }
+
+#include "pcu_gram_fast.cuh"
 
 // Compatibility path for weighting patterns the shuffle layout cannot express
 // (WDesc.mode == 2, e.g. the 5-of-6 pattern of examples/rosenbrock): subtracts
@@ -338,7 +355,9 @@ __global__ void gram_generic_correction(const ColTable cols, int m,
 template <int NTA, int NTB, bool DIAG>
 static int launch_gram(pcu_ctx *ctx, const ColTable &cols, int colA0, int colB0,
                        int m, const double *Dinv, const double *Cw,
-                       const WDesc &w, long long n, double *result, int ld) {
+                       const WDesc &w, long long n, double *result, int ld,
+                       long long list0 = 0, long long list1 = 0, int nlist = 0,
+                       int accumulate = 0) {
   constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
   long long nchunks = (n + 63) / 64;
   long long need = (nchunks + (PCU_THREADS / 32) - 1) / (PCU_THREADS / 32);
@@ -352,15 +371,66 @@ static int launch_gram(pcu_ctx *ctx, const ColTable &cols, int colA0, int colB0,
   }
   int grid = ctx->num_sms * blocks_per_sm;
   if (need < grid) grid = (int)(need < 1 ? 1 : need);
+  if (nlist > 0) grid = 1;
   if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
   ctx->prof_begin("gram_kernel");
   gram_kernel<NTA, NTB, DIAG><<<grid, PCU_THREADS, 0, ctx->stream>>>(
       cols, colA0, colB0, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter,
-      result, ld);
+      result, ld, list0, list1, nlist, accumulate);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int NT, int NWC>
+static int launch_gram_fast_t(pcu_ctx *ctx, const ColTable &cols, int m,
+                              const double *Dinv, const double *Cw,
+                              const WDesc &w, long long n, double *result,
+                              int ld) {
+  constexpr int NP = (NT * (NT + 1)) / 2;
+  static int blocks_per_sm = -1;
+  if (blocks_per_sm < 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, gram_fast_kernel<NT, NWC>, PCU_THREADS, 0) != cudaSuccess || v < 1)
+      v = 1;
+    blocks_per_sm = v > 4 ? 4 : v;
+  }
+  const long long nchunks = n / 64;
+  long long need = (nchunks + (PCU_THREADS / 32) - 1) / (PCU_THREADS / 32);
+  int grid = ctx->num_sms * blocks_per_sm;
+  if (need < grid) grid = (int)(need < 1 ? 1 : need);
+  if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
+  ctx->prof_begin("gram_kernel");
+  gram_fast_kernel<NT, NWC><<<grid, PCU_THREADS, 0, ctx->stream>>>(
+      cols, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter, result, ld);
+  ctx->prof_end();
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int NT>
+static int launch_gram_fast_n(pcu_ctx *ctx, const ColTable &cols, int m,
+                              const double *Dinv, const double *Cw,
+                              const WDesc &w, long long n, double *result,
+                              int ld, int nwc) {
+  if (nwc == 0) return launch_gram_fast_t<NT, 0>(ctx, cols, m, Dinv, Cw, w, n, result, ld);
+  if (nwc == 8) return launch_gram_fast_t<NT, 8>(ctx, cols, m, Dinv, Cw, w, n, result, ld);
+  return launch_gram_fast_t<NT, -1>(ctx, cols, m, Dinv, Cw, w, n, result, ld);
+}
+
+static int launch_gram_fast(pcu_ctx *ctx, const ColTable &cols, int m,
+                            const double *Dinv, const double *Cw, const WDesc &w,
+                            long long n, double *result, int ld, int nt, int nwc) {
+  switch (nt) {
+    case 1: return launch_gram_fast_n<1>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
+    case 2: return launch_gram_fast_n<2>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
+    case 3: return launch_gram_fast_n<3>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
+    case 4: return launch_gram_fast_n<4>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
+    default: return launch_gram_fast_n<5>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
+  }
 }
 
 // Enqueue S = V^T P V into ctx->d_big (col-major, leading dimension *ld_out =
@@ -379,7 +449,34 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
   }
   double *R = ctx->d_big;
   int rc = 0;
-  if (nt <= 5) {
+  const bool fast_ok = nt <= 5 && Dinv != nullptr && n >= 64 &&
+                       (w.mode == 0 || (w.mode == 1 && w.nw >= 8));
+  if (fast_ok) {
+    // straight-line kernel on the clean 64-row chunks, general kernel on the
+    // (at most two) ragged ones
+    const int nwc = (w.mode == 0) ? 0 : (w.nw == 8 ? 8 : -1);
+    rc = launch_gram_fast(ctx, cols, m, Dinv, Cw, w, n, R, ld, nt, nwc);
+    if (rc) return rc;
+    long long lst[2];
+    int nl = 0;
+    const long long nfull = n / 64;
+    if (w.mode == 1) {
+      const long long ncon_elems = (long long)w.nwcon * w.nw;
+      const long long cb = ncon_elems / 64;
+      if (ncon_elems % 64 != 0 && cb < nfull) lst[nl++] = cb;
+    }
+    if (n % 64 != 0) lst[nl++] = nfull;
+    if (nl > 0) {
+      const long long l0 = lst[0], l1 = nl > 1 ? lst[1] : 0;
+      switch (nt) {
+        case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
+        case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
+        case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
+        case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
+        default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
+      }
+    }
+  } else if (nt <= 5) {
     switch (nt) {
       case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
       case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;

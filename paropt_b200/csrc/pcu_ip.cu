@@ -624,7 +624,13 @@ int pcu_ip::computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
   if (ctx->fetch(out)) return 1;
   memcpy(res_sums, out, sizeof(res_sums));
   memcpy(res_max, out + ResF::NS, sizeof(res_max));
-  // dense parts (IP.cpp:1401-1407, 1535-1541)
+  denseResidual(vars, mu, res, step, ATp);
+  return 0;
+}
+
+// dense parts of computeKKTRes / addKKTResStep (IP.cpp:1401-1407, 1535-1541)
+void pcu_ip::denseResidual(Vars &vars, double mu, Vars &res, Vars *step,
+                           const double *ATp) {
   for (int i = 0; i < ncon; i++) {
     res.z[i] = -(c[i] - vars.s[i] + vars.t[i]);
     res.s[i] = -(gamma_s[i] - vars.zs[i] + vars.z[i]);
@@ -639,7 +645,6 @@ int pcu_ip::computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
       res.zt[i] -= (step->t[i] * vars.zt[i] + vars.t[i] * step->zt[i]);
     }
   }
-  return 0;
 }
 
 // computeResNorm (IP.cpp:1588-1723) from the statistics of the last ResF launch

@@ -195,7 +195,10 @@ struct pcu_ip {
   int setUpKKTDiagSystem(Vars &vars, int use_qn, int identity);
   int setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag);
   int computeKKTStep(Vars &vars, Vars &res, Vars &step, int use_qn,
-                     int accumulate, double *VTp);
+                     int accumulate, double *VTp, int emit_res, double mu_res,
+                     int *emitted);
+  void denseResidual(Vars &vars, double mu, Vars &res, Vars *step,
+                     const double *ATp);
   int stepStats(Vars &vars, Vars &step, double tau, double *sums, double *mins);
   int scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
                     const double *VTp, double fixed_scale, StepScale *out);

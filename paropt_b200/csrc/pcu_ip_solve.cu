@@ -112,7 +112,9 @@ int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag) {
 // 2257-2369) merged: pass 1 -> reductions -> dense solves -> pass 2.
 // VTp (optional, ncon + qn->size() values): [A | Z]^T of the (accumulated) step.
 int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
-                           int accumulate, double *VTp) {
+                           int accumulate, double *VTp, int emit_res,
+                           double mu_res, int *emitted) {
+  if (emitted) *emitted = 0;
   const int q = (qn && use_qn && !Cefac.empty()) ? std::min(sq, qn->size()) : 0;
   const int m = ncon + q;
   const IPConst k = kconst();
@@ -237,26 +239,62 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
   f2.ncols = m;
   f2.accumulate = accumulate;
   f2.k = k;
+  // [A | Z]^T p.  When the Gram pass covered every quasi-Newton vector the
+  // products follow from linearity, [A|Z]^T D0^-1 (d1 + V alpha) = r + S alpha,
+  // without touching the N-vectors again.
+  const int qa = qn ? qn->size() : 0;
+  const bool derived = (q == qa) && !force_direct_dots;
+  if (VTp && derived) {
+    for (int i = 0; i < m; i++) {
+      double vv = r[i];
+      for (int j = 0; j < m; j++) vv += Sgram[i + (size_t)sld * j] * f2.alpha.v[j];
+      VTp[i] = accumulate ? VTp[i] + vv : vv;
+    }
+  }
+  if (emit_res && VTp && derived) {
+    // pass 2 also writes the refinement residual (computeKKTRes +
+    // addKKTResStep at the accumulated step) into `b`
+    Pass2RF fr;
+    fr.v = f2.v;
+    fr.b = f2.b;
+    fr.y = f2.y;
+    fr.lb = f2.lb;
+    fr.ub = f2.ub;
+    fr.Dinv = f2.Dinv;
+    fr.Cw = f2.Cw;
+    fr.d1 = f2.d1;
+    fr.d2 = f2.d2;
+    fr.g = g->d;
+    fr.V = V;
+    fr.alpha = f2.alpha;
+    fr.ncols = m;
+    fr.accumulate = accumulate;
+    fr.k = k;
+    fr.mu = mu_res;
+    fr.b0sig = opt.qn_sigma;
+    for (int j = 0; j < ncon; j++) fr.beta.v[j] = vars.z[j] + y.z[j];
+    for (int j = 0; j < q; j++) fr.beta.v[ncon + j] = 0.0;
+    if (qn && !opt.sequential_linear_method) {  // IP.cpp:1474-1476
+      fr.b0sig += qn->b0;
+      if (q > 0) {
+        std::vector<double> kap(q);
+        qn->solve_compact(VTp + ncon, kap.data());
+        for (int j = 0; j < q; j++) fr.beta.v[ncon + j] = kap[j];
+      }
+    }
+    if (launch_tile(ctx, fr, nvars, wd, NO_RED)) return 1;
+    denseResidual(vars, mu_res, b, &y, VTp);
+    if (emitted) *emitted = 1;
+    return 0;
+  }
   if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
-  if (VTp) {
-    // [A | Z]^T p.  When the Gram pass covered every quasi-Newton vector the
-    // products follow from linearity, [A|Z]^T D0^-1 (d1 + V alpha) = r + S alpha,
-    // without touching the N-vectors again.
-    const int qa = qn ? qn->size() : 0;
-    if (q == qa && !force_direct_dots) {
-      for (int i = 0; i < m; i++) {
-        double v = r[i];
-        for (int j = 0; j < m; j++) v += Sgram[i + (size_t)sld * j] * f2.alpha.v[j];
-        VTp[i] = accumulate ? VTp[i] + v : v;
-      }
-    } else {
-      ColTable Vall;
-      for (int j = 0; j < ncon; j++) Vall.p[j] = Ac[j]->d;
-      if (qa > 0) qn->z_table(Vall, ncon);
-      if (ncon + qa > 0) {
-        if (pcu_mdot_enqueue(ctx, y.v[PCU_X]->d, Vall, ncon + qa, nvars, 0)) return 1;
-        if (ctx->big_fetch(ncon + qa, VTp)) return 1;
-      }
+  if (VTp && !derived) {
+    ColTable Vall;
+    for (int j = 0; j < ncon; j++) Vall.p[j] = Ac[j]->d;
+    if (qa > 0) qn->z_table(Vall, ncon);
+    if (ncon + qa > 0) {
+      if (pcu_mdot_enqueue(ctx, y.v[PCU_X]->d, Vall, ncon + qa, nvars, 0)) return 1;
+      if (ctx->big_fetch(ncon + qa, VTp)) return 1;
     }
   }
   return 0;
@@ -488,7 +526,7 @@ int pcu_ip::initAffineStepMultipliers() {
   int use_qn = opt.sequential_linear_method ? 0 : 1;
   if (setUpKKTDiagSystem(vars, use_qn, 0)) return 1;
   if (setUpKKTSystem(vars, use_qn, nullptr)) return 1;
-  if (computeKKTStep(vars, res, step, use_qn, 0, nullptr)) return 1;
+  if (computeKKTStep(vars, res, step, use_qn, 0, nullptr, 0, 0.0, nullptr)) return 1;
   const double mn = opt.start_affine_multiplier_min;
   for (int i = 0; i < ncon; i++) {
     vars.z[i] = vars.z[i] + step.z[i];
@@ -975,22 +1013,35 @@ int pcu_ip::iterate_once(int *converged) {
   const int nref = opt.iterative_refinement_steps;
   auto kkt_with_refinement = [&](double mu_res, bool allow_refine) -> int {
     const bool need_dots = true;
-    if (computeKKTStep(v, res, upd, use_qn, 0, need_dots ? VTp.data() : nullptr))
+    (void)need_dots;
+    const int nr = allow_refine ? nref : 0;
+    int emitted = 0;
+    if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nr > 0, mu_res, &emitted))
       return 1;
-    if (!allow_refine) return 0;
-    for (int it = 0; it < nref; it++) {  // IP.cpp:4985-4991
-      if (computeKKTRes(v, mu_res, res, &upd, VTp.data(), VTp.data() + nA)) return 1;
-      if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data())) return 1;
+    for (int it = 0; it < nr; it++) {  // IP.cpp:4985-4991
+      if (!emitted &&
+          computeKKTRes(v, mu_res, res, &upd, VTp.data(), VTp.data() + nA))
+        return 1;
+      if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data(), it + 1 < nr, mu_res,
+                         &emitted))
+        return 1;
     }
     return 0;
   };
   {
     // first step without refinement timing split: KKT solve = setup + first step
-    if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data())) return 1;
+    int emitted = 0;
+    if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nref > 0, mu_for_res,
+                       &emitted))
+      return 1;
     PCU_CUDA_OK(cudaEventRecord(ev_k1, ctx->stream));
     for (int it = 0; it < nref; it++) {
-      if (computeKKTRes(v, mu_for_res, res, &upd, VTp.data(), VTp.data() + nA)) return 1;
-      if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data())) return 1;
+      if (!emitted &&
+          computeKKTRes(v, mu_for_res, res, &upd, VTp.data(), VTp.data() + nA))
+        return 1;
+      if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data(), it + 1 < nref,
+                         mu_for_res, &emitted))
+        return 1;
     }
   }
   (void)ref;

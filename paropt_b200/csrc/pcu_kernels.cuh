@@ -53,6 +53,11 @@ struct Con0 {  // no per-constraint data
   double d[1];
   __device__ __forceinline__ void zero() {}
 };
+struct Con2 {  // two broadcast values
+  static constexpr int ND = 2;
+  double d[2];
+  __device__ __forceinline__ void zero() { d[0] = d[1] = 0.0; }
+};
 struct Con1 {  // one broadcast value
   static constexpr int ND = 1;
   double d[1];
@@ -1026,5 +1031,181 @@ struct Pass1RF : NoStreams {
         for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
       }
     }
+  }
+};
+
+// ============================================================== Pass2RF
+// Pass2F that also emits the residual of the linearised KKT system at the step
+// it has just produced (computeKKTRes + addKKTResStep, IP.cpp:1337-1583): the
+// right-hand side of the next iterative-refinement solve (IP.cpp:4985-4991)
+// costs one extra read (g) and three extra writes instead of a separate pass
+// over (9 + c + q)N words.  The residual is written into the bundle `b` the
+// right-hand side was read from (each entry is read before it is overwritten by
+// the same thread).  beta_j = z_j + pz_j for the A columns and kap_k for the Z
+// columns (B p = (b0 + sigma) p - Z kap), all for the accumulated step.
+// Traffic: reads (10 + c + q)N + 20W, writes 6N + 10W (+3N + 5W reads when
+// accumulating).
+struct Pass2RF : NoStreams {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 1, NB2 = 2;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con2 Con;  // yw (this solve), zw + total pzw
+  struct Elem {
+    double d1, dinv, lin;
+  };
+  DVars v, b, y;
+  const double *lb, *ub, *Dinv, *Cw, *d1, *d2, *g;
+  ColTable V;
+  CoefTable alpha, beta;
+  int ncols;
+  int accumulate;
+  double b0sig, mu;
+  IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(d1); p_(Dinv); p_(v.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) { p_(v.zl); p_(b.zl); }
+    if (k.use_upper) { p_(v.zu); p_(b.zu); }
+    for (int j = 0; j < ncols; j++) p_(V.p[j]);
+    if (accumulate) {
+      p_(y.x);
+      if (k.use_lower) p_(y.zl);
+      if (k.use_upper) p_(y.zu);
+    }
+  }
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1],
+                                    AccT *) const {
+    double d[W], di[W], lin[W];
+    ldv<W>(d1, i, d);
+    ldv<W>(Dinv, i, di);
+#pragma unroll
+    for (int q = 0; q < W; q++) lin[q] = 0.0;
+    for (int j = 0; j < ncols; j++) {
+      double c[W];
+      ldv<W>(V.p[j], i, c);
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        d[q] = fma(alpha.v[j], c[q], d[q]);
+        lin[q] = fma(beta.v[j], c[q], lin[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      e[q].d1 = d[q];
+      e[q].dinv = di[q];
+      e[q].lin = lin[q];
+      part[q][0] = coef[q] * di[q] * d[q];
+    }
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
+                                    Con &con, AccT &) const {
+    const double yw = Cw[ci] * (d2[ci] - sum[0]);
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double pzsw = yw - b.sw[ci];
+    const double pztw = -b.tw[ci] - yw;
+    const double psw = (b.zsw[ci] - sw * pzsw) / zsw;
+    const double ptw = (b.ztw[ci] - tw * pztw) / ztw;
+    double tzw = yw;
+    if (accumulate) {
+      tzw += y.zw[ci];
+      y.zw[ci] = tzw;
+      y.zsw[ci] += pzsw;
+      y.ztw[ci] += pztw;
+      y.sw[ci] += psw;
+      y.tw[ci] += ptw;
+    } else {
+      y.zw[ci] = yw;
+      y.zsw[ci] = pzsw;
+      y.ztw[ci] = pztw;
+      y.sw[ci] = psw;
+      y.tw[ci] = ptw;
+    }
+    con.d[0] = yw;
+    con.d[1] = v.zw[ci] + tzw;
+  }
+  template <int W>
+  __device__ __forceinline__ void C2(long long i, const double (&coef)[W],
+                                     const Elem (&e)[W], const Con &con, AccT &,
+                                     double (&part2)[W][2]) const {
+    double x[W], l[W], u[W], zl[W], zu[W], bzl[W], bzu[W], gv[W];
+    double px[W], pzl[W], pzu[W], rx[W], rzl[W], rzu[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
+    if (k.use_lower) {
+      ldv<W>(v.zl, i, zl);
+      ldv<W>(b.zl, i, bzl);
+    }
+    if (k.use_upper) {
+      ldv<W>(v.zu, i, zu);
+      ldv<W>(b.zu, i, bzu);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      px[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+      pzl[q] = 0.0;
+      pzu[q] = 0.0;
+      if (k.use_lower && l[q] > -k.mbv)
+        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv)
+        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+    }
+    if (accumulate) {
+      double o[W];
+      ldv<W>(y.x, i, o);
+#pragma unroll
+      for (int q = 0; q < W; q++) px[q] += o[q];
+      if (k.use_lower) {
+        ldv<W>(y.zl, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzl[q] += o[q];
+      }
+      if (k.use_upper) {
+        ldv<W>(y.zu, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzu[q] += o[q];
+      }
+    }
+    stv<W>(y.x, i, px);
+    if (k.use_lower) stv<W>(y.zl, i, pzl);
+    if (k.use_upper) stv<W>(y.zu, i, pzu);
+    // residual of the linearised system at the (accumulated) step
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      const double dl = x[q] - l[q], du = u[q] - x[q];
+      double r = ((zl[q] - zu[q]) - gv[q]) + e[q].lin;
+      r = fma(-b0sig, px[q], r) + (pzl[q] - pzu[q]);
+      rx[q] = fma(coef[q], con.d[1], r);
+      rzl[q] = 0.0;
+      rzu[q] = 0.0;
+      if (k.use_lower && l[q] > -k.mbv)
+        rzl[q] = -(dl * zl[q] - k.kappa * mu) - (dl * pzl[q] + px[q] * zl[q]);
+      if (k.use_upper && u[q] < k.mbv)
+        rzu[q] = -(du * zu[q] - k.kappa * mu) - (du * pzu[q] - px[q] * zu[q]);
+      part2[q][0] = coef[q] * x[q];
+      part2[q][1] = coef[q] * px[q];
+    }
+    stv<W>(b.x, i, rx);
+    if (k.use_lower) stv<W>(b.zl, i, rzl);
+    if (k.use_upper) stv<W>(b.zu, i, rzu);
+  }
+  __device__ __forceinline__ void E(long long ci, const double (&sum2)[2],
+                                    const Con &, AccT &) const {
+    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
+    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double pzw = y.zw[ci], psw = y.sw[ci], ptw = y.tw[ci];
+    const double pzsw = y.zsw[ci], pztw = y.ztw[ci];
+    const double gsw = gamma_sw(k, ci), gtw = k.gamma;
+    b.zw[ci] = -(((k.wconst + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
+    b.sw[ci] = ((zsw - gsw) - zw) + (pzsw - pzw);
+    b.tw[ci] = ((ztw - gtw) + zw) + (pztw + pzw);
+    b.zsw[ci] = (mu - sw * zsw) - (psw * zsw + sw * pzsw);
+    b.ztw[ci] = (mu - tw * ztw) - (ptw * ztw + tw * pztw);
   }
 };
