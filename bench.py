@@ -108,10 +108,12 @@ def kernel_words(name, N, W, c, q):
     """Algorithmic fp64 words per launch of each kernel."""
     m = c + q
     table = {
-        "ResF": (9 + c) * N + 10 * W + 0.5 * ((3 + q) * N + 5 * W),  # 1 plain + 1 with step
+        "ResF": (9 + c) * N + 10 * W,
         "DiagF": 6 * N + 5 * W,
         "Pass1F": 9 * N + 11 * W,
-        "Pass2F": (12 + m) * N + 15 * W + 0.5 * (3 * N + 5 * W),  # every 2nd accumulates
+        "Pass1RF": (8 + m) * N + 11 * W,
+        "Pass2F": (12 + m) * N + 15 * W + 3 * N + 5 * W,   # the accumulating refinement solve
+        "Pass2RF": (16 + m) * N + 30 * W,                   # pass 2 + refinement residual
         "StatsF": 9 * N + 8 * W,
         "TrialF": 5 * N + 6 * W,
         "Update1F": (10 + c) * N + 15 * W,
@@ -119,6 +121,7 @@ def kernel_words(name, N, W, c, q):
         "gram_kernel": (m + 1) * N + W,
         "mdot_kernel": None,  # (1 + columns of the chunk) N, see below
     }
+    name = name.split("<")[0]
     return table.get(name)
 
 

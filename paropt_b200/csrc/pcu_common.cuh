@@ -188,6 +188,7 @@ __device__ void finish_reduction(Acc<NS, NX, NM> &acc, const RedBuf &rb) {
 // lanes): the demand loads then hit in L2 and DRAM runs one iteration ahead.
 struct NoStreams {
   static constexpr int NB2 = 0;   // second-round per-constraint block sums (C2 / E phases)
+  static constexpr int HASP = 0;  // P(ci, con): per-constraint prologue seen by A (AP form)
   static constexpr int MINB = 7;  // __launch_bounds__ minimum blocks per SM (<= 73 regs)
   template <class P>
   __device__ __forceinline__ void streams(P &) const {}
@@ -240,7 +241,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       typename F::Elem e[1];
       double coef[1] = {0.0};
       double part[1][NB];
-      f.template A<1>(i, coef, e, part, &acc);
+      if constexpr (F::HASP) { typename F::Con c0; c0.zero(); f.template AP<1>(i, coef, e, part, &acc, c0); } else { f.template A<1>(i, coef, e, part, &acc); }
       typename F::Con con;
       con.zero();
       if constexpr (F::NB2 > 0) {
@@ -261,16 +262,17 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       double sum[NB];
 #pragma unroll
       for (int b = 0; b < NB; b++) sum[b] = 0.0;
+      typename F::Con con;
+      con.zero();
+      if constexpr (F::HASP) f.P(ci, con);
       for (int k = 0; k < w.nw; k++) {
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
-        f.template A<1>(j0 + k, coef, e, part, (typename F::AccT *)nullptr);
+        if constexpr (F::HASP) { f.template AP<1>(j0 + k, coef, e, part, (typename F::AccT *)nullptr, con); } else { f.template A<1>(j0 + k, coef, e, part, (typename F::AccT *)nullptr); }
 #pragma unroll
         for (int b = 0; b < NB; b++) sum[b] += part[0][b];
       }
-      typename F::Con con;
-      con.zero();
       f.B(ci, sum, con, acc);
       double sum2[F::NB2 > 0 ? F::NB2 : 1];
 #pragma unroll
@@ -279,7 +281,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
-        f.template A<1>(j0 + k, coef, e, part, &acc);
+        if constexpr (F::HASP) { f.template AP<1>(j0 + k, coef, e, part, &acc, con); } else { f.template A<1>(j0 + k, coef, e, part, &acc); }
         if constexpr (F::NB2 > 0) {
           double part2[1][F::NB2];
           f.template C2<1>(j0 + k, coef, e, con, acc, part2);
@@ -334,9 +336,14 @@ __global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
         coef[0] = (k == 0) ? w.coef0 : w.coef_rest;
         coef[1] = w.coef_rest;
       }
-      f.template A<2>(i, coef, e, part, &acc);
       typename F::Con con;
       con.zero();
+      if constexpr (F::HASP) {
+        if (in_con) f.P(i / w.nw, con);
+        f.template AP<2>(i, coef, e, part, &acc, con);
+      } else {
+        f.template A<2>(i, coef, e, part, &acc);
+      }
       if (w.mode == 1) {
         double sum[NB];
 #pragma unroll

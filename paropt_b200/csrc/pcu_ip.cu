@@ -586,8 +586,9 @@ int pcu_ip::initAndCheckDesignAndBounds() {
 
 // --------------------------------------------------------------- residuals
 int pcu_ip::computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
-                          const double *ATp, const double *ZTp) {
+                          const double *ATp, const double *ZTp, int store) {
   ResF f;
+  f.store = store;
   f.v = vars.dv();
   f.r = res.dv();
   f.p = step ? step->dv() : vars.dv();
@@ -618,12 +619,15 @@ int pcu_ip::computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
   f.mu = mu;
   f.norm_type = norm_type_id();
   f.k = kconst();
-  RedBuf rb = ctx->redbuf(ResF::NS, ResF::NX, 0);
+  RedBuf rb = ctx->redbuf(ResF::NS, ResF::NX, ResF::NM);
   if (launch_tile(ctx, f, nvars, wd, rb)) return 1;
-  double out[ResF::NS + ResF::NX];
+  double out[ResF::NS + ResF::NX + ResF::NM];
   if (ctx->fetch(out)) return 1;
   memcpy(res_sums, out, sizeof(res_sums));
   memcpy(res_max, out + ResF::NS, sizeof(res_max));
+  memcpy(res_min, out + ResF::NS + ResF::NX, sizeof(res_min));
+  res_mu = mu;
+  res_has_step = step ? 1 : 0;
   denseResidual(vars, mu, res, step, ATp);
   return 0;
 }
@@ -656,6 +660,14 @@ void pcu_ip::computeResNorm(Vars &res, double *max_prime, double *max_dual,
     mp = res_max[0];
     mi = res_max[1];
     md = res_max[2];
+    if (!res_has_step) {
+      // |kappa mu - a_i| over the bound products, |mu - a_i| over the sparse ones
+      const double km = opt.rel_bound_barrier * res_mu;
+      if (res_min[0] < 1e299)
+        md = std::max(md, std::max(fabs(km - res_max[3]), fabs(km - res_min[0])));
+      if (res_min[1] < 1e299)
+        md = std::max(md, std::max(fabs(res_mu - res_max[4]), fabs(res_mu - res_min[1])));
+    }
     for (int i = 0; i < ncon; i++) {
       mp = std::max(mp, std::max(fabs(res.s[i]), fabs(res.t[i])));
       mi = std::max(mi, fabs(res.z[i]));
@@ -691,6 +703,16 @@ void pcu_ip::computeResNorm(Vars &res, double *max_prime, double *max_dual,
   *max_dual = md;
   *max_infeas = mi;
   if (res_norm) *res_norm = std::max(mp, std::max(md, mi));
+}
+
+int pcu_ip::resNormAtBarrier(Vars &vars, double mu, Vars &res, double *max_prime,
+                             double *max_dual, double *max_infeas,
+                             double *res_norm) {
+  if (norm_type_id() != 0 || res_has_step) return 0;
+  res_mu = mu;
+  denseResidual(vars, mu, res, nullptr, nullptr);
+  computeResNorm(res, max_prime, max_dual, max_infeas, res_norm);
+  return 1;
 }
 
 // computeComp (IP.cpp:2742-2820) from the statistics of the last ResF launch

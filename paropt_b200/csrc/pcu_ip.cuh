@@ -146,7 +146,9 @@ struct pcu_ip {
   int status = 0;
 
   // statistics of the last ResF launch
-  double res_sums[11], res_max[3];
+  double res_sums[11], res_max[5], res_min[2];
+  double res_mu = 0.0;   // barrier of the last ResF launch
+  int res_has_step = 0;  // the last ResF launch included the step terms
   double last_comp = 0.0;
   int force_direct_dots = 0;  // debugging: recompute [A|Z]^T p with multi-dots
   double stats_pmax = 0.0;  // |px|_inf of the last StatsF launch
@@ -188,15 +190,19 @@ struct pcu_ip {
   // hot-path functions (same names as the reference's private methods)
   int initAndCheckDesignAndBounds();
   int computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
-                    const double *ATp, const double *ZTp);
+                    const double *ATp, const double *ZTp, int store = 1);
   void computeResNorm(Vars &res, double *max_prime, double *max_dual,
                       double *max_infeas, double *res_norm);
+  // infinity-norm residual norms at another barrier value from the statistics
+  // of the last (step-free) ResF launch; returns 0 when not available
+  int resNormAtBarrier(Vars &vars, double mu, Vars &res, double *max_prime,
+                       double *max_dual, double *max_infeas, double *res_norm);
   double compFromStats(Vars &vars);
   int setUpKKTDiagSystem(Vars &vars, int use_qn, int identity);
   int setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag);
   int computeKKTStep(Vars &vars, Vars &res, Vars &step, int use_qn,
                      int accumulate, double *VTp, int emit_res, double mu_res,
-                     int *emitted);
+                     int *emitted, int rhs_from_vars = 0);
   void denseResidual(Vars &vars, double mu, Vars &res, Vars *step,
                      const double *ATp);
   int stepStats(Vars &vars, Vars &step, double tau, double *sums, double *mins);

@@ -113,8 +113,21 @@ int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag) {
 // VTp (optional, ncon + qn->size() values): [A | Z]^T of the (accumulated) step.
 int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
                            int accumulate, double *VTp, int emit_res,
-                           double mu_res, int *emitted) {
+                           double mu_res, int *emitted, int rhs_from_vars) {
   if (emitted) *emitted = 0;
+  {
+    // The residual-free first solve needs the fused pass-1 / pass-2 kernels;
+    // otherwise materialise the right-hand side first.
+    const int q0 = (qn && use_qn && !Cefac.empty()) ? std::min(sq, qn->size()) : 0;
+    const bool fused_ok = emit_res && VTp && !force_direct_dots &&
+                          q0 == (qn ? qn->size() : 0) && ncon + q0 > 0 &&
+                          ncon + q0 <= 32;
+    if (rhs_from_vars && !fused_ok) {
+      if (computeKKTRes(vars, mu_res, b, nullptr, nullptr, nullptr, 1)) return 1;
+      rhs_from_vars = 0;
+    }
+    if (rhs_from_vars) denseResidual(vars, mu_res, b, nullptr, nullptr);
+  }
   const int q = (qn && use_qn && !Cefac.empty()) ? std::min(sq, qn->size()) : 0;
   const int m = ncon + q;
   const IPConst k = kconst();
@@ -141,7 +154,39 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     for (int i = 0; i < m; i++) r[i] = out[i];
     return 0;
   };
-  if (m > 0 && m <= 8) {
+  auto vars_pass1 = [&](auto f1) -> int {
+    f1.v = vars.dv();
+    f1.lb = lb->d;
+    f1.ub = ub->d;
+    f1.g = g->d;
+    f1.Dinv = Dinv->d;
+    f1.Cw = Cw->d;
+    f1.d1 = d1->d;
+    f1.d2 = d2->d;
+    f1.V = V;
+    f1.m = m;
+    f1.ncon = ncon;
+    for (int j = 0; j < ncon; j++) f1.z.v[j] = vars.z[j];
+    f1.mu = mu_res;
+    f1.k = k;
+    RedBuf rb = ctx->redbuf(decltype(f1)::NS, 0, 0);
+    if (launch_tile(ctx, f1, nvars, wd, rb)) return 1;
+    double out[decltype(f1)::NS];
+    if (ctx->fetch(out)) return 1;
+    for (int i = 0; i < m; i++) r[i] = out[i];
+    return 0;
+  };
+  if (rhs_from_vars) {
+    if (m <= 8) {
+      if (vars_pass1(Pass1VF<8>())) return 1;
+    } else if (m <= 16) {
+      if (vars_pass1(Pass1VF<16>())) return 1;
+    } else if (m <= 24) {
+      if (vars_pass1(Pass1VF<24>())) return 1;
+    } else {
+      if (vars_pass1(Pass1VF<32>())) return 1;
+    }
+  } else if (m > 0 && m <= 8) {
     if (fused_pass1(Pass1RF<8>())) return 1;
   } else if (m <= 16 && m > 0) {
     if (fused_pass1(Pass1RF<16>())) return 1;
@@ -269,6 +314,8 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     fr.alpha = f2.alpha;
     fr.ncols = m;
     fr.accumulate = accumulate;
+    fr.from_vars = rhs_from_vars;
+    fr.mu_rhs = mu_res;
     fr.k = k;
     fr.mu = mu_res;
     fr.b0sig = opt.qn_sigma;
@@ -915,6 +962,9 @@ int pcu_ip::iterate_once(int *converged) {
 
   double max_prime = 0.0, max_dual = 0.0, max_infeas = 0.0, res_norm = 0.0;
   int monotone_barrier_converged = 0;
+  // monotone strategy with refinement: the residual vectors are never stored
+  const bool lazy_res = (ls.barrier_strategy == BS_MONOTONE) &&
+                        opt.iterative_refinement_steps > 0;
   // residual + norms + complementarity in one pass (IP.cpp:4656-4671)
   if (ls.barrier_strategy == BS_COMP_FRACTION) {
     // mu depends on comp: a first pass for comp, then the residual
@@ -930,7 +980,9 @@ int pcu_ip::iterate_once(int *converged) {
     computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
     if (k == 0) ls.res_norm_prev = res_norm;
   } else {
-    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+    // statistics only: the first solve recomputes the residual on the fly
+    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr, lazy_res ? 0 : 1))
+      return 1;
     comp = compFromStats(v);
     computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
     if (snapshot(k, comp, max_prime, max_dual, max_infeas, res_norm)) return 1;
@@ -947,8 +999,12 @@ int pcu_ip::iterate_once(int *converged) {
         double new_mu = mu_frac;
         if (mu_pow < mu_frac) new_mu = mu_pow;
         if (new_mu < 0.1 * abs_res_tol) new_mu = 0.09999 * abs_res_tol;
-        if (computeKKTRes(v, new_mu, res, nullptr, nullptr, nullptr)) return 1;
-        computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+        if (!(lazy_res && resNormAtBarrier(v, new_mu, res, &max_prime, &max_dual,
+                                           &max_infeas, &res_norm))) {
+          if (computeKKTRes(v, new_mu, res, nullptr, nullptr, nullptr, lazy_res ? 0 : 1))
+            return 1;
+          computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+        }
         rho_penalty_search = opt.min_rho_penalty_search;
         barrier_param = new_mu;
       }
@@ -1032,7 +1088,7 @@ int pcu_ip::iterate_once(int *converged) {
     // first step without refinement timing split: KKT solve = setup + first step
     int emitted = 0;
     if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nref > 0, mu_for_res,
-                       &emitted))
+                       &emitted, lazy_res ? 1 : 0))
       return 1;
     PCU_CUDA_OK(cudaEventRecord(ev_k1, ctx->stream));
     for (int it = 0; it < nref; it++) {

@@ -19,7 +19,7 @@
 
 // occupancy hints (blocks of 128 threads per SM) of the register-heavy kernels
 #ifndef PCU_MINB_RES
-#define PCU_MINB_RES 6
+#define PCU_MINB_RES 5
 #endif
 #ifndef PCU_MINB_STATS
 #define PCU_MINB_STATS 5
@@ -76,11 +76,16 @@ struct Con1 {  // one broadcast value
 //       9,10 norm-sum rzl, rzu;   maxima: 0 |rx|, 1 |rzw|, 2 dual parts
 struct ResF : NoStreams {
   static constexpr int MINB = PCU_MINB_RES;
-  static constexpr int NS = 11, NX = 3, NM = 0, NB = 2;
+  // maxima: 0 |rx|, 1 |rzw|, 2 mu-independent dual parts (|rsw|, |rtw|) and, for
+  // l1/l2 bookkeeping, every dual part; 3 max zl(x-lb) | zu(ub-x); 4 max sw zsw |
+  // tw ztw.  minima: 0 / 1 the same two products.  With them the infinity-norm
+  // of the mu-dependent parts |kappa mu - a_i| is exact for ANY mu, so a barrier
+  // update needs no second pass (IP.cpp:4726-4729).
+  static constexpr int NS = 11, NX = 5, NM = 2, NB = 2;
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // zw (+ pzw)
   struct Elem {
-    double rx, rzl, rzu, cprod, ccount;
+    double rx, rzl, rzu, cprod, ccount, amax, amin;
   };
   DVars v, r, p;
   const double *lb, *ub, *g;
@@ -94,6 +99,7 @@ struct ResF : NoStreams {
   double mu;
   int has_step;
   int norm_type;  // 0 infinity, 1 l1, 2 l2
+  int store;      // write the residual vectors (0: statistics only)
   IPConst k;
 
   template <class P>
@@ -153,18 +159,27 @@ struct ResF : NoStreams {
       const bool mu_ = k.use_upper && (u[q] < k.mbv);
       const double dl = x[q] - l[q], du = u[q] - x[q];
       double rzl = 0.0, rzu = 0.0, cp = 0.0, cc = 0.0;
+      double amax = 0.0, amin = 1.0e300;
       if (ml) {
-        rzl = -(dl * zl[q] - k.kappa * mu);
+        const double a = dl * zl[q];
+        rzl = -(a - k.kappa * mu);
         if (has_step) rzl -= (dl * pzl[q] + px[q] * zl[q]);
-        cp += zl[q] * dl;
+        cp += a;
         cc += 1.0;
+        amax = fmax(amax, a);
+        amin = fmin(amin, a);
       }
       if (mu_) {
-        rzu = -(du * zu[q] - k.kappa * mu);
+        const double a = du * zu[q];
+        rzu = -(a - k.kappa * mu);
         if (has_step) rzu -= (du * pzu[q] - px[q] * zu[q]);
-        cp += zu[q] * du;
+        cp += a;
         cc += 1.0;
+        amax = fmax(amax, a);
+        amin = fmin(amin, a);
       }
+      e[q].amax = amax;
+      e[q].amin = amin;
       e[q].rx = rx[q];
       e[q].rzl = rzl;
       e[q].rzu = rzu;
@@ -183,8 +198,11 @@ struct ResF : NoStreams {
     double rzw = -(((k.wconst + sum[0]) - sw) + tw);
     double rsw = (zsw - gsw) - zw;
     double rtw = (ztw - gtw) + zw;
-    double rzsw = mu - sw * zsw;
-    double rztw = mu - tw * ztw;
+    const double asw = sw * zsw, atw = tw * ztw;
+    double rzsw = mu - asw;
+    double rztw = mu - atw;
+    acc.x[4] = fmax(acc.x[4], fmax(asw, atw));
+    acc.m[1] = fmin(acc.m[1], fmin(asw, atw));
     con.d[0] = zw;
     if (has_step) {
       const double pzw = p.zw[ci], psw = p.sw[ci], ptw = p.tw[ci];
@@ -196,16 +214,19 @@ struct ResF : NoStreams {
       rztw -= (ptw * ztw + tw * pztw);
       con.d[0] += pzw;
     }
-    r.zw[ci] = rzw;
-    r.sw[ci] = rsw;
-    r.tw[ci] = rtw;
-    r.zsw[ci] = rzsw;
-    r.ztw[ci] = rztw;
-    acc.s[2] += sw * zsw + tw * ztw;
+    if (store) {
+      r.zw[ci] = rzw;
+      r.sw[ci] = rsw;
+      r.tw[ci] = rtw;
+      r.zsw[ci] = rzsw;
+      r.ztw[ci] = rztw;
+    }
+    acc.s[2] += asw + atw;
     acc.s[1] += 2.0;
     acc.x[1] = fmax(acc.x[1], fabs(rzw));
-    acc.x[2] = fmax(acc.x[2], fmax(fmax(fabs(rsw), fabs(rtw)),
-                                   fmax(fabs(rzsw), fabs(rztw))));
+    acc.x[2] = fmax(acc.x[2], fmax(fabs(rsw), fabs(rtw)));
+    if (has_step)  // no closed form in mu once the step terms are in
+      acc.x[2] = fmax(acc.x[2], fmax(fabs(rzsw), fabs(rztw)));
     if (norm_type == 1) {
       acc.s[4] += fabs(rzw);
     } else if (norm_type == 2) {
@@ -232,7 +253,9 @@ struct ResF : NoStreams {
       acc.s[0] += e[q].cprod;
       acc.s[1] += e[q].ccount;
       acc.x[0] = fmax(acc.x[0], fabs(rx[q]));
-      acc.x[2] = fmax(acc.x[2], fmax(fabs(rzl[q]), fabs(rzu[q])));
+      acc.x[3] = fmax(acc.x[3], e[q].amax);
+      acc.m[0] = fmin(acc.m[0], e[q].amin);
+      if (has_step) acc.x[2] = fmax(acc.x[2], fmax(fabs(rzl[q]), fabs(rzu[q])));
       if (norm_type == 1) {
         acc.s[3] += fabs(rx[q]);
         acc.s[9] += fabs(rzl[q]);
@@ -243,9 +266,11 @@ struct ResF : NoStreams {
         acc.s[10] = fma(rzu[q], rzu[q], acc.s[10]);
       }
     }
-    stv<W>(r.x, i, rx);
-    if (k.use_lower) stv<W>(r.zl, i, rzl);
-    if (k.use_upper) stv<W>(r.zu, i, rzu);
+    if (store) {
+      stv<W>(r.x, i, rx);
+      if (k.use_lower) stv<W>(r.zl, i, rzl);
+      if (k.use_upper) stv<W>(r.zu, i, rzu);
+    }
   }
 };
 
@@ -1058,14 +1083,16 @@ struct Pass2RF : NoStreams {
   CoefTable alpha, beta;
   int ncols;
   int accumulate;
-  double b0sig, mu;
+  int from_vars;  // the right-hand side is computeKKTRes(vars, mu_rhs), recomputed
+                  // here instead of being read from `b`
+  double b0sig, mu, mu_rhs;
   IPConst k;
 
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
     p_(d1); p_(Dinv); p_(v.x); p_(lb); p_(ub); p_(g);
-    if (k.use_lower) { p_(v.zl); p_(b.zl); }
-    if (k.use_upper) { p_(v.zu); p_(b.zu); }
+    if (k.use_lower) { p_(v.zl); if (!from_vars) p_(b.zl); }
+    if (k.use_upper) { p_(v.zu); if (!from_vars) p_(b.zu); }
     for (int j = 0; j < ncols; j++) p_(V.p[j]);
     if (accumulate) {
       p_(y.x);
@@ -1104,10 +1131,23 @@ struct Pass2RF : NoStreams {
                                     Con &con, AccT &) const {
     const double yw = Cw[ci] * (d2[ci] - sum[0]);
     const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double pzsw = yw - b.sw[ci];
-    const double pztw = -b.tw[ci] - yw;
-    const double psw = (b.zsw[ci] - sw * pzsw) / zsw;
-    const double ptw = (b.ztw[ci] - tw * pztw) / ztw;
+    double bsw, btw, bzsw, bztw;
+    if (from_vars) {  // IP.cpp:1361-1389
+      const double zw = v.zw[ci];
+      bsw = (zsw - gamma_sw(k, ci)) - zw;
+      btw = (ztw - k.gamma) + zw;
+      bzsw = mu_rhs - sw * zsw;
+      bztw = mu_rhs - tw * ztw;
+    } else {
+      bsw = b.sw[ci];
+      btw = b.tw[ci];
+      bzsw = b.zsw[ci];
+      bztw = b.ztw[ci];
+    }
+    const double pzsw = yw - bsw;
+    const double pztw = -btw - yw;
+    const double psw = (bzsw - sw * pzsw) / zsw;
+    const double ptw = (bztw - tw * pztw) / ztw;
     double tzw = yw;
     if (accumulate) {
       tzw += y.zw[ci];
@@ -1140,11 +1180,18 @@ struct Pass2RF : NoStreams {
     for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
     if (k.use_lower) {
       ldv<W>(v.zl, i, zl);
-      ldv<W>(b.zl, i, bzl);
+      if (!from_vars) ldv<W>(b.zl, i, bzl);
     }
     if (k.use_upper) {
       ldv<W>(v.zu, i, zu);
-      ldv<W>(b.zu, i, bzu);
+      if (!from_vars) ldv<W>(b.zu, i, bzu);
+    }
+    if (from_vars) {  // rzl, rzu of computeKKTRes (IP.cpp:1417-1444)
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        bzl[q] = -((x[q] - l[q]) * zl[q] - k.kappa * mu_rhs);
+        bzu[q] = -((u[q] - x[q]) * zu[q] - k.kappa * mu_rhs);
+      }
     }
 #pragma unroll
     for (int q = 0; q < W; q++) {
@@ -1207,5 +1254,107 @@ struct Pass2RF : NoStreams {
     b.tw[ci] = ((ztw - gtw) + zw) + (pztw + pzw);
     b.zsw[ci] = (mu - sw * zsw) - (psw * zsw + sw * pzsw);
     b.ztw[ci] = (mu - tw * ztw) - (ptw * ztw + tw * pztw);
+  }
+};
+
+// ============================================================== Pass1VF<MR>
+// Pass1RF whose right-hand side is the KKT residual itself (computeKKTRes,
+// IP.cpp:1337-1446, at barrier mu), recomputed from the variables: the first
+// solve of an iteration never reads (and ResF never writes) the residual
+// vectors.  Traffic: reads (8 + c + m)N + 6W, writes N + W.
+template <int MR>
+struct Pass1VF : NoStreams {
+  static constexpr int MINB = PCU_MINB_PASS1;
+  static constexpr int NS = MR, NX = 0, NM = 0, NB = 2, HASP = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con2 Con;  // yw, zw
+  struct Elem {
+    double d1, dinv;
+  };
+  DVars v;
+  const double *lb, *ub, *g, *Dinv, *Cw;
+  double *d1, *d2;
+  ColTable V;   // [A | Z]; the first ncon columns are the constraint gradients
+  CoefTable z;  // dense multipliers
+  int m, ncon;
+  double mu;
+  IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(lb); p_(ub); p_(g); p_(Dinv);
+    if (k.use_lower) p_(v.zl);
+    if (k.use_upper) p_(v.zu);
+    for (int j = 0; j < m; j++) p_(V.p[j]);
+  }
+  __device__ __forceinline__ void P(long long ci, Con &con) const {
+    con.d[1] = v.zw[ci];
+  }
+  template <int W>
+  __device__ __forceinline__ void AP(long long i, const double (&coef)[W],
+                                     Elem (&e)[W], double (&part)[W][2], AccT *,
+                                     const Con &con) const {
+    double x[W], l[W], u[W], gv[W], zl[W], zu[W], di[W], d[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+    ldv<W>(Dinv, i, di);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = 0.0;
+    if (k.use_lower) ldv<W>(v.zl, i, zl);
+    if (k.use_upper) ldv<W>(v.zu, i, zu);
+#pragma unroll
+    for (int q = 0; q < W; q++) d[q] = (zl[q] - zu[q]) - gv[q];
+    for (int j = 0; j < ncon; j++) {
+      double a[W];
+      ldv<W>(V.p[j], i, a);
+#pragma unroll
+      for (int q = 0; q < W; q++) d[q] = fma(z.v[j], a[q], d[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      const double dl = x[q] - l[q], du = u[q] - x[q];
+      double t = fma(coef[q], con.d[1], d[q]);  // rx
+      if (k.use_lower && l[q] > -k.mbv) t += -(dl * zl[q] - k.kappa * mu) / dl;
+      if (k.use_upper && u[q] < k.mbv) t -= -(du * zu[q] - k.kappa * mu) / du;
+      d[q] = t;
+      e[q].d1 = t;
+      e[q].dinv = di[q];
+      part[q][0] = coef[q] * di[q] * t;
+      part[q][1] = coef[q] * x[q];
+    }
+    stv<W>(d1, i, d);
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[2],
+                                    Con &con, AccT &) const {
+    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
+    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double bzw = -(((k.wconst + sum[1]) - sw) + tw);
+    const double bsw = (zsw - gamma_sw(k, ci)) - zw;
+    const double btw = (ztw - k.gamma) + zw;
+    const double bzsw = mu - sw * zsw;
+    const double bztw = mu - tw * ztw;
+    const double dd = bzw + (bzsw + sw * bsw) / zsw - (bztw + tw * btw) / ztw;
+    con.d[0] = Cw[ci] * (dd - sum[0]);
+    con.d[1] = zw;
+    d2[ci] = dd;
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AccT &acc) const {
+    double t[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+#pragma unroll
+    for (int j = 0; j < MR; j++) {
+      if (j < m) {
+        double c[W];
+        ldv<W>(V.p[j], i, c);
+#pragma unroll
+        for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
+      }
+    }
   }
 };
