@@ -217,7 +217,7 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from paropt_b200.api import Context, InteriorPoint, problem_from_config
+    from paropt_b200.api import BuiltinProblem, Context, InteriorPoint, problem_from_config
     from paropt_b200.host_problems import HostSepQuad
 
     ctx = Context(local_rank)
@@ -297,7 +297,7 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(name)
+                traffic = json.load(open(tpath)).get(name.split("<")[0])
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak,
@@ -324,26 +324,39 @@ def run_ours(args):
             dist.all_reduce(t)
             return t.cpu().numpy()
 
-        hp = HostSepQuad(ctx, allreduce=allreduce, **cfg["problem"])
+        if args.e2e_python:
+            hp = HostSepQuad(ctx, allreduce=allreduce, **cfg["problem"])
+            e_kind = ("python callbacks (torch-CPU threaded numpy views) on the library's "
+                      "pinned host arrays")
+        else:
+            hp = BuiltinProblem(ctx, "sepquad", host=True, nthreads=host_cores() // world,
+                                **cfg["problem"])
+            e_kind = ("C++ host callbacks over host arrays (pcu_problem_create_host), "
+                      "%d host threads" % max(1, host_cores() // world))
         hip = InteriorPoint(hp, dict(cfg["options"], max_major_iters=1000000,
                                      history_level=1))
-        e_warm, e_steps = args.e2e_warmup, args.e2e_steps
+        e_warm, e_steps = max(args.e2e_warmup, QN_WARMUP), args.e2e_steps
         hip.begin()
         hip.iterate(e_warm)
         barrier()
-        h2d0, d2h0 = hp.h2d_bytes, hp.d2h_bytes
+        h2d0, d2h0 = hp.transfer_bytes()
         i0 = hip.counters()[0]
         ctx.timer_start()
         hip.iterate(e_steps)
         e_ms = max_over_ranks(ctx.timer_stop())
         barrier()
+        h2d1, d2h1 = hp.transfer_bytes()
         e_done = hip.counters()[0] - i0
+        e_times = hip.iter_times()[-e_done:] if e_done else []
         e2e = {"value": e_done / (e_ms / 1e3) if e_ms > 0 else 0.0, "unit": UNIT,
-               "h2d_bytes_per_step": (hp.h2d_bytes - h2d0) // max(e_done, 1),
-               "d2h_bytes_per_step": (hp.d2h_bytes - d2h0) // max(e_done, 1),
-               "steps": e_done, "warmup": e_warm,
-               "note": "host numpy callbacks (user code) + pinned-buffer copies inside "
-                       "the timed region; quasi-Newton memory still filling"}
+               "h2d_bytes_per_step": (h2d1 - h2d0) // max(e_done, 1),
+               "d2h_bytes_per_step": (d2h1 - d2h0) // max(e_done, 1),
+               "steps": e_done, "warmup": e_warm, "ms_per_step": e_ms / max(e_done, 1),
+               "callback_ms_per_step": sum(t[1] for t in e_times) / max(len(e_times), 1),
+               "note": "same loop through the host-array problem API: " + e_kind +
+                       "; per callback the iterate is copied device->host and the "
+                       "gradients host->device (pinned buffers) inside the timed region; "
+                       "callback_ms = user code + copies"}
         hip.free()
         hp.free()
 
@@ -415,8 +428,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3")
     ap.add_argument("--n", type=int, default=None, help="global number of design variables")
-    ap.add_argument("--e2e-steps", type=int, default=4)
-    ap.add_argument("--e2e-warmup", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-warmup", type=int, default=QN_WARMUP)
+    ap.add_argument("--e2e-python", action="store_true",
+                    help="drive the end-to-end leg through the Python Problem class")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

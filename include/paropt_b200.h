@@ -125,6 +125,34 @@ pcu_problem *pcu_problem_create(pcu_ctx *ctx, int nvars, int ncon,
                                 const pcu_problem_callbacks *callbacks);
 void pcu_problem_destroy(pcu_problem *prob);
 
+/* Host-array callbacks: the shape of a ParOptProblem whose callbacks work on
+   ParOptVec::getArray pointers (ParOptProblem.h:143-172, ParOpt.pyx:520-640).
+   The library owns page-locked host mirrors of x, g and the ncon constraint
+   gradients (the arrays the callbacks see), copies the iterate device->host
+   before a callback and the gradients host->device after it.  The copy of x is
+   skipped when the optimizer knows the point is bit-identical to the one of the
+   previous callback (accepted line-search trial, IP.cpp:4169-4215).            */
+typedef struct pcu_host_callbacks {
+  void *user;
+  int (*get_vars_and_bounds)(void *user, int n, double *x, double *lb, double *ub);
+  int (*eval_obj_con)(void *user, int n, const double *x, double *fobj,
+                      double *cons);
+  int (*eval_obj_con_gradient)(void *user, int n, const double *x, double *g,
+                               double **Ac);
+} pcu_host_callbacks;
+pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
+                                     int ninequality, int nwinequality,
+                                     int use_lower, int use_upper,
+                                     const pcu_weighting *weighting,
+                                     const pcu_host_callbacks *callbacks);
+/* Bytes moved over PCIe by a host-array problem since its creation. */
+int pcu_problem_transfer_bytes(pcu_problem *prob, int64_t *h2d, int64_t *d2h);
+
+/* MPI_Allreduce(MPI_SUM) stand-in for user callbacks that reduce their own
+   partial sums (e.g. examples/rosenbrock/rosenbrock.cpp:100-117): `vals` are
+   host doubles, summed over the ranks of the context in place.               */
+int pcu_ctx_allreduce_sum(pcu_ctx *ctx, double *vals, int n);
+
 /* Built-in GPU-resident synthetic problems (DESIGN.md "Synthetic problems");
    they implement the same three callbacks with CUDA kernels.
    Parameters of the separable / Householder convex QP family:                 */
@@ -143,6 +171,15 @@ typedef struct pcu_sepquad_params {
 } pcu_sepquad_params;
 pcu_problem *pcu_problem_create_sepquad(pcu_ctx *ctx,
                                         const pcu_sepquad_params *params);
+/* The same workload as a HOST problem: C++ callbacks over host arrays, threaded
+   over `nthreads` host cores (<= 0: all), registered through
+   pcu_problem_create_host -- what the end-to-end benchmark drives.  `user_out`
+   receives the callback state; free it with pcu_problem_sepquad_host_free after
+   pcu_problem_destroy.                                                        */
+pcu_problem *pcu_problem_create_sepquad_host(pcu_ctx *ctx,
+                                             const pcu_sepquad_params *params,
+                                             int nthreads, void **user_out);
+void pcu_problem_sepquad_host_free(void *user);
 /* examples/rosenbrock/rosenbrock.cpp:9-199 (single rank). */
 pcu_problem *pcu_problem_create_rosenbrock(pcu_ctx *ctx, int nvars, int nwcon,
                                            int nwstart, int nw, int nwskip);

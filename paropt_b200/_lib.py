@@ -45,6 +45,20 @@ class Callbacks(C.Structure):
                 ("eval_obj_con_gradient", EVAL_GRAD_CB)]
 
 
+HOST_GET_VARS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p,
+                               c_double_p)
+HOST_EVAL_OBJ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p,
+                               c_double_p)
+HOST_EVAL_GRAD_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p,
+                                C.POINTER(c_double_p))
+
+
+class HostCallbacks(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("get_vars_and_bounds", HOST_GET_VARS_CB),
+                ("eval_obj_con", HOST_EVAL_OBJ_CB),
+                ("eval_obj_con_gradient", HOST_EVAL_GRAD_CB)]
+
+
 VP = C.c_void_p
 
 # name -> (restype, argtypes); every symbol include/paropt_b200.h declares
@@ -83,7 +97,16 @@ SIGNATURES = {
     "pcu_vec_from_host": (C.c_int, [VP, VP, C.c_int]),
     "pcu_problem_create": (VP, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.POINTER(Weighting), C.POINTER(Callbacks)]),
+    "pcu_problem_create_host": (VP, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.POINTER(Weighting),
+                                     C.POINTER(HostCallbacks)]),
+    "pcu_problem_transfer_bytes": (C.c_int, [VP, C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_int64)]),
     "pcu_problem_destroy": (None, [VP]),
+    "pcu_ctx_allreduce_sum": (C.c_int, [VP, c_double_p, C.c_int]),
+    "pcu_problem_create_sepquad_host": (VP, [VP, C.POINTER(SepQuadParams), C.c_int,
+                                             C.POINTER(VP)]),
+    "pcu_problem_sepquad_host_free": (None, [VP]),
     "pcu_problem_create_sepquad": (VP, [VP, C.POINTER(SepQuadParams)]),
     "pcu_problem_create_rosenbrock": (VP, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pcu_problem_sizes": (C.c_int, [VP, c_int_p, c_int_p, c_int_p]),

@@ -196,80 +196,67 @@ def sepquad_params(**kw):
 class Problem:
     """ParOpt.Problem (ParOpt.pyx:787-907): subclass and implement
     getVarsAndBounds(x, lb, ub), evalObjCon(x) -> (fail, fobj, con) and
-    evalObjConGradient(x, g, A) -> fail on numpy arrays.  The arrays are host
-    mirrors of device vectors (the reference's getArray contract); each callback
-    costs one device->host and one host->device copy of its vectors."""
+    evalObjConGradient(x, g, A) -> fail on numpy arrays.  The arrays are views
+    of page-locked host mirrors owned by the library (the reference's getArray
+    contract, pcu_problem_create_host); each callback costs one device->host
+    copy of the iterate (skipped when the point is the one the previous callback
+    saw) and one host->device copy of the vectors it fills."""
 
     def __init__(self, ctx, nvars, ncon, ninequality=-1, nwinequality=-1,
                  use_lower=True, use_upper=True, weighting=None):
         self.ctx = ctx
         self.lib = ctx.lib
         self.nvars, self.ncon = int(nvars), int(ncon)
-        self.h2d_bytes = 0
-        self.d2h_bytes = 0
-        self._bufs = {}
-        self._pinned = []
         w = _lib.Weighting()
         if weighting:
             for k, v in weighting.items():
                 setattr(w, k, v)
         self._w = w
-        self._cb = _lib.Callbacks()
+        self._cb = _lib.HostCallbacks()
         self._cb.user = None
-        self._cb.get_vars_and_bounds = _lib.GET_VARS_CB(self._get_vars)
-        self._cb.eval_obj_con = _lib.EVAL_OBJ_CB(self._eval_obj)
-        self._cb.eval_obj_con_gradient = _lib.EVAL_GRAD_CB(self._eval_grad)
-        self.h = self.lib.pcu_problem_create(
+        self._cb.get_vars_and_bounds = _lib.HOST_GET_VARS_CB(self._get_vars)
+        self._cb.eval_obj_con = _lib.HOST_EVAL_OBJ_CB(self._eval_obj)
+        self._cb.eval_obj_con_gradient = _lib.HOST_EVAL_GRAD_CB(self._eval_grad)
+        self._views = {}
+        self.h = self.lib.pcu_problem_create_host(
             ctx.h, self.nvars, self.ncon, int(ninequality), int(nwinequality),
             int(use_lower), int(use_upper), C.byref(self._w), C.byref(self._cb))
         if not self.h:
             raise RuntimeError("paropt_b200: problem creation failed")
 
-    def _vec(self, handle):
-        return PVec(self.ctx, handle=handle)
+    def _view(self, ptr, n):
+        """numpy view of a library-owned host array (cached per address)."""
+        addr = C.addressof(ptr.contents) if n > 0 else 0
+        v = self._views.get(addr)
+        if v is None or v.shape[0] != n:
+            v = np.ctypeslib.as_array(ptr, shape=(n,)) if n > 0 else np.empty(0)
+            self._views[addr] = v
+        return v
 
-    def _host(self, key):
-        """Persistent pinned host mirror (the reference's getArray buffer)."""
-        buf = self._bufs.get(key)
-        if buf is None:
-            try:
-                import torch
-                t = torch.empty(self.nvars, dtype=torch.float64, pin_memory=True)
-                self._pinned.append(t)
-                buf = t.numpy()
-            except Exception:
-                buf = np.empty(self.nvars)
-            self._bufs[key] = buf
-        return buf
+    @property
+    def h2d_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.pcu_problem_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value
 
-    def _d2h(self, handle, key):
-        buf = self._host(key)
-        if self.nvars:
-            _check(self.lib.pcu_vec_to_host(handle, buf.ctypes.data, self.nvars), "to_host")
-        self.d2h_bytes += buf.nbytes
-        return buf
+    @property
+    def d2h_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.pcu_problem_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return b.value
 
-    def _h2d(self, handle, buf):
-        if self.nvars:
-            _check(self.lib.pcu_vec_from_host(handle, buf.ctypes.data, self.nvars), "from_host")
-        self.h2d_bytes += buf.nbytes
-
-    def _get_vars(self, user, x, lb, ub):
+    def _get_vars(self, user, n, x, lb, ub):
         try:
-            xa, la, ua = self._host("x"), self._host("g"), self._host("a0")
-            self.getVarsAndBounds(xa, la, ua)
-            for h, a in ((x, xa), (lb, la), (ub, ua)):
-                self._h2d(h, a)
+            self.getVarsAndBounds(self._view(x, n), self._view(lb, n), self._view(ub, n))
             return 0
         except Exception:  # mirrors ParOpt.pyx:528-531 (report, do not unwind C)
             import traceback
             traceback.print_exc()
             return 1
 
-    def _eval_obj(self, user, x, fobj, cons):
+    def _eval_obj(self, user, n, x, fobj, cons):
         try:
-            xa = self._d2h(x, "x")
-            fail, f, con = self.evalObjCon(xa)
+            fail, f, con = self.evalObjCon(self._view(x, n))
             fobj[0] = float(f)
             for i in range(self.ncon):
                 cons[i] = float(con[i])
@@ -279,15 +266,10 @@ class Problem:
             traceback.print_exc()
             return 1
 
-    def _eval_grad(self, user, x, g, Ac):
+    def _eval_grad(self, user, n, x, g, Ac):
         try:
-            xa = self._d2h(x, "x")
-            ga = self._host("g")
-            A = [self._host("a%d" % i) for i in range(self.ncon)]
-            fail = self.evalObjConGradient(xa, ga, A)
-            self._h2d(g, ga)
-            for i in range(self.ncon):
-                self._h2d(Ac[i], A[i])
+            A = [self._view(Ac[i], n) for i in range(self.ncon)]
+            fail = self.evalObjConGradient(self._view(x, n), self._view(g, n), A)
             return int(fail or 0)
         except Exception:
             import traceback
@@ -296,19 +278,30 @@ class Problem:
 
     def free(self):
         if self.h:
+            self._views.clear()
             self.lib.pcu_problem_destroy(self.h)
             self.h = None
 
 
 class BuiltinProblem:
-    """GPU-resident synthetic problems (pcu_problem_create_sepquad / _rosenbrock)."""
+    """Synthetic problems shipped with the library: GPU-resident
+    (pcu_problem_create_sepquad / _rosenbrock) or, with host=True, the same
+    sepquad workload as threaded C++ host callbacks over host arrays
+    (pcu_problem_create_sepquad_host) -- the end-to-end path."""
 
-    def __init__(self, ctx, kind, **params):
+    def __init__(self, ctx, kind, host=False, nthreads=0, **params):
         self.ctx = ctx
         self.lib = ctx.lib
+        self._user = None
         if kind == "sepquad":
             self._p = sepquad_params(**params)
-            self.h = self.lib.pcu_problem_create_sepquad(ctx.h, C.byref(self._p))
+            if host:
+                user = C.c_void_p()
+                self.h = self.lib.pcu_problem_create_sepquad_host(
+                    ctx.h, C.byref(self._p), int(nthreads), C.byref(user))
+                self._user = user
+            else:
+                self.h = self.lib.pcu_problem_create_sepquad(ctx.h, C.byref(self._p))
         elif kind == "rosenbrock":
             n = int(params.get("n", 1000))
             self.h = self.lib.pcu_problem_create_rosenbrock(ctx.h, n - 1, 5, 1, 5, 1)
@@ -323,10 +316,18 @@ class BuiltinProblem:
     def callback_ms(self):
         return float(self.lib.pcu_problem_callback_ms(self.h))
 
+    def transfer_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        self.lib.pcu_problem_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def free(self):
         if self.h:
             self.lib.pcu_problem_destroy(self.h)
             self.h = None
+        if self._user is not None and self._user.value:
+            self.lib.pcu_problem_sepquad_host_free(self._user)
+            self._user = None
 
 
 def problem_from_config(ctx, cfg):

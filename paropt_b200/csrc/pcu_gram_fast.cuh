@@ -8,16 +8,23 @@
 // general kernel.  Included by pcu_gram.cu only.
 #pragma once
 
+#ifndef PCU_GRAM_G
+#define PCU_GRAM_G 2   // 8-row steps per load group (double-buffered)
+#endif
+#ifndef PCU_GRAM_MINB
+#define PCU_GRAM_MINB 2
+#endif
+
 template <int NT>
 struct GramBuf {
-  double2 wv[2];
-  double2 f[2][NT];
+  double2 wv[PCU_GRAM_G];
+  double2 f[PCU_GRAM_G][NT];
 };
 
 // NWC: 0 = no weighting correction, 8 = blocks of exactly 8 rows,
 //     -1 = runtime block size w.nw in {16, 32, 64}
 template <int NT, int NWC>
-__global__ void __launch_bounds__(PCU_THREADS, 2)
+__global__ void __launch_bounds__(PCU_THREADS, PCU_GRAM_MINB)
     gram_fast_kernel(const ColTable cols, const int m,
                      const double *__restrict__ Dinv,
                      const double *__restrict__ Cw, const WDesc w,
@@ -67,9 +74,9 @@ __global__ void __launch_bounds__(PCU_THREADS, 2)
   };
 
   auto load_group = [&](long long chunk, int g, GramBuf<NT> &b) {
-    const long long off = chunk * 64 + g * 16;
+    const long long off = chunk * 64 + g * (8 * PCU_GRAM_G);
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < PCU_GRAM_G; s++) {
       b.wv[s] = *reinterpret_cast<const double2 *>(dinv + off + 8 * s);
 #pragma unroll
       for (int t = 0; t < NT; t++)
@@ -80,8 +87,8 @@ __global__ void __launch_bounds__(PCU_THREADS, 2)
   auto compute_group = [&](long long chunk, int g, const GramBuf<NT> &b,
                            bool in_con) {
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const int step = 2 * g + s;
+    for (int s = 0; s < PCU_GRAM_G; s++) {
+      const int step = PCU_GRAM_G * g + s;
       double2 fb[NT], fa[NT];
 #pragma unroll
       for (int t = 0; t < NT; t++) {
@@ -164,14 +171,15 @@ __global__ void __launch_bounds__(PCU_THREADS, 2)
     const bool in_con = (NWC != 0) && (chunk * 64 < ncon_elems);
     long long next = chunk + nwarps;
     while (next < nfull && !clean(next)) next += nwarps;
-    load_group(chunk, 1, bb);
-    compute_group(chunk, 0, ba, in_con);
-    load_group(chunk, 2, ba);
-    compute_group(chunk, 1, bb, in_con);
-    load_group(chunk, 3, bb);
-    compute_group(chunk, 2, ba, in_con);
-    if (next < nfull) load_group(next, 0, ba);
-    compute_group(chunk, 3, bb, in_con);
+    constexpr int NG = 8 / PCU_GRAM_G;  // groups per chunk (even)
+#pragma unroll
+    for (int g = 0; g < NG; g += 2) {
+      load_group(chunk, g + 1, bb);
+      compute_group(chunk, g, ba, in_con);
+      if (g + 2 < NG) load_group(chunk, g + 2, ba);
+      else if (next < nfull) load_group(next, 0, ba);
+      compute_group(chunk, g + 1, bb, in_con);
+    }
     chunk = next;
   }
 

@@ -491,9 +491,11 @@ int pcu_ip::evalObjCon(pcu_vec *x) {
   if (cb_end()) return 1;
   return fail;
 }
-int pcu_ip::evalObjConGradient(pcu_vec *x) {
+int pcu_ip::evalObjConGradient(pcu_vec *x, int same_point) {
   if (cb_begin()) return 1;
+  prob->same_point_hint = same_point;
   int fail = prob->evalObjConGradient(x, g, Ac.data());
+  prob->same_point_hint = 0;
   ngeval++;
   if (cb_end()) return 1;
   return fail;

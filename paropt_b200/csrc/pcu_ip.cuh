@@ -185,7 +185,7 @@ struct pcu_ip {
   int cb_end();
   double cb_collect();
   int evalObjCon(pcu_vec *x);
-  int evalObjConGradient(pcu_vec *x);
+  int evalObjConGradient(pcu_vec *x, int same_point = 0);
 
   // hot-path functions (same names as the reference's private methods)
   int initAndCheckDesignAndBounds();

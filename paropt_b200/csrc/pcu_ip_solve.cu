@@ -918,7 +918,7 @@ int pcu_ip::begin() {
     fprintf(stderr, "ParOpt: Initial function and constraint evaluation failed\n");
     return 1;
   }
-  if (evalObjConGradient(variables.v[PCU_X])) {
+  if (evalObjConGradient(variables.v[PCU_X], 1)) {
     fprintf(stderr, "ParOpt: Initial gradient evaluation failed\n");
     return 1;
   }
@@ -1201,7 +1201,10 @@ int pcu_ip::iterate_once(int *converged) {
         return 1;
       }
     }
-    if (evalObjConGradient(v.v[PCU_X])) {
+    // the new point is bit-identical to the one the objective callback saw last:
+    // either x itself (eval_obj_con) or the accepted line-search trial point
+    // (step_clip is the one definition of both)
+    if (evalObjConGradient(v.v[PCU_X], 1)) {
       fprintf(stderr, "ParOpt: Gradient evaluation failed at final line search\n");
     }
     update_type = 0;

@@ -14,6 +14,11 @@ struct pcu_problem {
   double callback_ms = 0.0;  // device time inside the callbacks
   cudaEvent_t cb0 = nullptr, cb1 = nullptr;
   bool time_callbacks = true;
+  // Set by the optimizer right before a callback: the vector handed over holds
+  // bit-identical values to the one of the previous callback (the accepted
+  // line-search trial point).  Host-array problems skip the device->host copy.
+  int same_point_hint = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0;  // host-array problems only
 
   virtual ~pcu_problem() {}
   virtual int getVarsAndBounds(pcu_vec *x, pcu_vec *lb, pcu_vec *ub) = 0;

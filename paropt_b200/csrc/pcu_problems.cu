@@ -524,6 +524,82 @@ struct CallbackProblem : pcu_problem {
   }
 };
 
+// ======================================================= host-array callbacks
+// The reference's problem callbacks read and write ParOptVec::getArray host
+// pointers; here those arrays are page-locked mirrors owned by the problem.
+struct HostProblem : pcu_problem {
+  pcu_host_callbacks cb;
+  double *hx = nullptr, *hg = nullptr;
+  std::vector<double *> hA;
+  cudaEvent_t up_done = nullptr;  // last host->device copy of g / A
+  bool up_pending = false;
+
+  ~HostProblem() {
+    if (hx) cudaFreeHost(hx);
+    if (hg) cudaFreeHost(hg);
+    for (double *p : hA)
+      if (p) cudaFreeHost(p);
+    if (up_done) cudaEventDestroy(up_done);
+  }
+  int init() {
+    const size_t bytes = sizeof(double) * (size_t)(nvars > 0 ? nvars : 1);
+    PCU_CUDA_OK(cudaHostAlloc(&hx, bytes, cudaHostAllocDefault));
+    PCU_CUDA_OK(cudaHostAlloc(&hg, bytes, cudaHostAllocDefault));
+    // getVarsAndBounds needs three arrays: at least two gradient mirrors
+    hA.assign(ncon > 1 ? ncon : 1, nullptr);
+    for (size_t j = 0; j < hA.size(); j++)
+      PCU_CUDA_OK(cudaHostAlloc(&hA[j], bytes, cudaHostAllocDefault));
+    PCU_CUDA_OK(cudaEventCreateWithFlags(&up_done, cudaEventDisableTiming));
+    return 0;
+  }
+  int wait_uploads() {  // the callbacks may overwrite hg / hA only after this
+    if (up_pending) {
+      PCU_CUDA_OK(cudaEventSynchronize(up_done));
+      up_pending = false;
+    }
+    return 0;
+  }
+  int fetch_x(pcu_vec *x) {
+    if (same_point_hint) return 0;
+    const size_t bytes = sizeof(double) * (size_t)nvars;
+    if (nvars > 0) {
+      PCU_CUDA_OK(cudaMemcpyAsync(hx, x->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      PCU_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    d2h_bytes += (long long)bytes;
+    return 0;
+  }
+  int push(pcu_vec *v, const double *h) {
+    const size_t bytes = sizeof(double) * (size_t)nvars;
+    if (nvars > 0)
+      PCU_CUDA_OK(cudaMemcpyAsync(v->d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    h2d_bytes += (long long)bytes;
+    return 0;
+  }
+  int getVarsAndBounds(pcu_vec *x, pcu_vec *lb, pcu_vec *ub) override {
+    if (wait_uploads()) return 1;
+    int fail = cb.get_vars_and_bounds(cb.user, nvars, hx, hg, hA[0]);
+    if (push(x, hx) || push(lb, hg) || push(ub, hA[0])) return 1;
+    PCU_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return fail;
+  }
+  int evalObjCon(pcu_vec *x, double *fobj, double *cons) override {
+    if (fetch_x(x)) return 1;
+    return cb.eval_obj_con(cb.user, nvars, hx, fobj, cons);
+  }
+  int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) override {
+    if (fetch_x(x) || wait_uploads()) return 1;
+    int fail = cb.eval_obj_con_gradient(cb.user, nvars, hx, hg, hA.data());
+    if (push(g, hg)) return 1;
+    for (int j = 0; j < ncon; j++)
+      if (push(Ac[j], hA[j])) return 1;
+    // stream-ordered: the kernels that consume g / A are enqueued behind the copies
+    PCU_CUDA_OK(cudaEventRecord(up_done, ctx->stream));
+    up_pending = true;
+    return fail;
+  }
+};
+
 extern "C" {
 
 pcu_problem *pcu_problem_create(pcu_ctx *ctx, int nvars, int ncon,
@@ -549,6 +625,39 @@ pcu_problem *pcu_problem_create(pcu_ctx *ctx, int nvars, int ncon,
 }
 
 void pcu_problem_destroy(pcu_problem *prob) { delete prob; }
+
+pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
+                                     int ninequality, int nwinequality,
+                                     int use_lower, int use_upper,
+                                     const pcu_weighting *weighting,
+                                     const pcu_host_callbacks *callbacks) {
+  if (!ctx || !callbacks || ncon > PCU_MAX_COLS) return nullptr;
+  HostProblem *p = new HostProblem;
+  p->ctx = ctx;
+  p->nvars = nvars;
+  p->ncon = ncon;
+  memset(&p->weighting, 0, sizeof(p->weighting));
+  if (weighting) p->weighting = *weighting;
+  p->nwcon = p->weighting.nwcon;
+  p->ninequality = ninequality < 0 ? ncon : ninequality;
+  p->nwinequality = nwinequality < 0 ? p->nwcon : nwinequality;
+  p->use_lower = use_lower;
+  p->use_upper = use_upper;
+  p->cb = *callbacks;
+  if (p->init()) {
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+int pcu_problem_transfer_bytes(pcu_problem *prob, int64_t *h2d, int64_t *d2h) {
+  if (!prob) return 1;
+  if (h2d) *h2d = prob->h2d_bytes;
+  if (d2h) *d2h = prob->d2h_bytes;
+  return 0;
+}
+
 
 pcu_problem *pcu_problem_create_sepquad(pcu_ctx *ctx,
                                         const pcu_sepquad_params *params) {

@@ -187,6 +187,16 @@ int pcu_ctx::big_fetch(size_t n, double *out) {
 // ------------------------------------------------------------- C ABI: context
 extern "C" {
 
+int pcu_ctx_allreduce_sum(pcu_ctx *ctx, double *vals, int n) {
+  if (!ctx || n < 0) return 1;
+  if (ctx->world <= 1 || n == 0) return 0;
+  if (ctx->big_reserve((size_t)n, 0)) return 1;
+  memcpy(ctx->h_big, vals, sizeof(double) * (size_t)n);
+  PCU_CUDA_OK(cudaMemcpyAsync(ctx->d_big, ctx->h_big, sizeof(double) * (size_t)n,
+                              cudaMemcpyHostToDevice, ctx->stream));
+  return ctx->big_fetch((size_t)n, vals);
+}
+
 const char *pcu_version(void) { return "paropt_b200 0.1 (sm_100a)"; }
 
 pcu_ctx *pcu_ctx_create(int device) {

@@ -1,8 +1,11 @@
 """Runs a few interior-point iterations of a named workload (for ncu captures).
+The last `--capture` iterations run between cudaProfilerStart/Stop, so
+`ncu --profile-from-start off` sees exactly those.
 
-    python scripts/profile_run.py --config C3 --n 16777216 --iters 14
+    python scripts/profile_run.py --config C3 --n 67108864 --iters 13 --capture 1
 """
 import argparse
+import ctypes
 import os
 import sys
 
@@ -13,7 +16,8 @@ from paropt_b200.api import Context, InteriorPoint, problem_from_config  # noqa:
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C3")
 ap.add_argument("--n", type=int, default=1 << 24)
-ap.add_argument("--iters", type=int, default=14)
+ap.add_argument("--iters", type=int, default=13)
+ap.add_argument("--capture", type=int, default=1)
 args = ap.parse_args()
 ctx = Context(0)
 cfg = configs.get(args.config, args.n)
@@ -22,4 +26,17 @@ ip = InteriorPoint(prob, dict(cfg["options"], max_major_iters=1000000, history_l
 ip.begin()
 ip.iterate(args.iters)
 ctx.sync()
+rt = None
+for name in ("libcudart.so", "libcudart.so.12"):
+    try:
+        rt = ctypes.CDLL(name)
+        break
+    except OSError:
+        pass
+if rt is not None:
+    rt.cudaProfilerStart()
+ip.iterate(args.capture)
+ctx.sync()
+if rt is not None:
+    rt.cudaProfilerStop()
 print("iterations", ip.counters(), "launches", ctx.kernel_launches())

@@ -58,3 +58,35 @@ def test_prefix_history_matches_reference(ctx, name, iters):
     n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters)
     assert n == iters
     assert first is None, (first, worst)
+
+
+@pytest.mark.parametrize("name,iters,flavour", [
+    ("C3_small", 50, "cxx"), ("C2_small", 41, "cxx"), ("C3_small", 30, "python"),
+    ("C2_small", 30, "python")])
+def test_host_array_problem_matches_reference(ctx, name, iters, flavour):
+    """End-to-end boundary: the same workloads as HOST problems (callbacks over the
+    library's pinned host arrays, pcu_problem_create_host) -- threaded C++
+    callbacks and the Python Problem class -- reproduce the reference history, and
+    the iterate is copied device->host only when the point changed."""
+    from paropt_b200.api import BuiltinProblem, InteriorPoint
+    from paropt_b200.host_problems import HostSepQuad
+    gold = load_golden(name)
+    cfg = gold["config"]
+    if flavour == "cxx":
+        prob = BuiltinProblem(ctx, "sepquad", host=True, nthreads=3, **cfg["problem"])
+    else:
+        prob = HostSepQuad(ctx, **cfg["problem"])
+    ip = InteriorPoint(prob, dict(cfg["options"], history_level=2, max_major_iters=iters + 1))
+    ip.optimize()
+    hist = ip.history()
+    niter, neval, ngeval = ip.counters()
+    h2d, d2h = prob.transfer_bytes()
+    ip.free()
+    prob.free()
+    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
+    assert n == iters and first is None, (first, worst)
+    nbytes = 8 * prob.nvars
+    # gradients: g + ncon columns per gradient evaluation (+ 3 vectors at start-up)
+    assert h2d == nbytes * (ngeval * (1 + prob.ncon) + 3)
+    # the iterate: once per objective evaluation, never again for the gradient
+    assert d2h == nbytes * neval
