@@ -189,6 +189,8 @@ __device__ void finish_reduction(Acc<NS, NX, NM> &acc, const RedBuf &rb) {
 struct NoStreams {
   static constexpr int NB2 = 0;   // second-round per-constraint block sums (C2 / E phases)
   static constexpr int HASP = 0;  // P(ci, con): per-constraint prologue seen by A (AP form)
+  static constexpr int NF = 0;    // third round F / FG after E: E leaves con.d[FD] to broadcast
+  static constexpr int FD = 0;
   static constexpr int MINB = 7;  // __launch_bounds__ minimum blocks per SM (<= 73 regs)
   template <class P>
   __device__ __forceinline__ void streams(P &) const {}
@@ -250,6 +252,7 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       } else {
         f.template C<1>(i, coef, e, con, acc);
       }
+      if constexpr (F::NF > 0) f.FG(i, coef[0], con, acc);
     }
   }
   // (2) whole constraints, one thread per constraint
@@ -292,6 +295,10 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
         }
       }
       if constexpr (F::NB2 > 0) f.E(ci, sum2, con, acc);
+      if constexpr (F::NF > 0) {
+        for (int k = 0; k < w.nw; k++)
+          f.FG(j0 + k, k == 0 ? w.coef0 : w.coef_rest, con, acc);
+      }
     }
   }
 }
@@ -376,8 +383,12 @@ __global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
             for (int b = 0; b < F::NB2; b++) sum2[b] += shfl_xor_d(sum2[b], o);
           }
           const int lane = threadIdx.x & 31;
-          if (in_con && lane == (lane & ~(half - 1))) f.E(i / w.nw, sum2, con, acc);
+          const int lead = lane & ~(half - 1);
+          if (in_con && lane == lead) f.E(i / w.nw, sum2, con, acc);
+          if constexpr (F::NF > 0)
+            con.d[F::FD] = __shfl_sync(0xffffffffu, con.d[F::FD], lead);
         }
+        if constexpr (F::NF > 0) f.template F<2>(i, coef, e, con, acc);
       } else {
         f.template C<2>(i, coef, e, con, acc);
       }

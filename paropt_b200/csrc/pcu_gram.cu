@@ -44,8 +44,11 @@ __global__ void __launch_bounds__(PCU_THREADS)
                 double *__restrict__ partials, unsigned int *counter,
                 double *__restrict__ result, const int ld,
                 const long long list0, const long long list1, const int nlist,
-                const int accumulate) {
+                const int accumulate, const double *__restrict__ d2,
+                const int rhs_col) {
   // nlist > 0: process only the chunks list0 [, list1] and add to `result`
+  // rhs_col >= 0: see gram_fast_kernel (the A-side block sum of that column is
+  // shifted by -d2)
   constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = lane >> 2, kk = lane & 3;
@@ -57,6 +60,9 @@ __global__ void __launch_bounds__(PCU_THREADS)
 #pragma unroll
   for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
   double uA[NTA], uB[NTB], hA[NTA], hB[NTB], hcw = 0.0;
+  bool rhsA[NTA];
+#pragma unroll
+  for (int t = 0; t < NTA; t++) rhsA[t] = (rhs_col >= 0) && (colA0 + 8 * t + gi == rhs_col);
 #pragma unroll
   for (int t = 0; t < NTA; t++) uA[t] = hA[t] = 0.0;
 #pragma unroll
@@ -211,7 +217,8 @@ __global__ void __launch_bounds__(PCU_THREADS)
             if (kk == blk) {
               hcw = in_con ? Cw[r0 / w.nw] : 0.0;
 #pragma unroll
-              for (int t = 0; t < NTA; t++) hA[t] = in_con ? uA[t] : 0.0;
+              for (int t = 0; t < NTA; t++)
+                hA[t] = in_con ? (rhsA[t] ? uA[t] - d2[r0 / w.nw] : uA[t]) : 0.0;
 #pragma unroll
               for (int t = 0; t < NTB; t++)
                 hB[t] = in_con ? (DIAG ? uA[t < NTA ? t : 0] : uB[t]) : 0.0;
@@ -240,7 +247,8 @@ __global__ void __launch_bounds__(PCU_THREADS)
             const double cw = lead ? Cw[r / w.nw] : 0.0;
             double ua[NTA], ub[NTB];
 #pragma unroll
-            for (int t = 0; t < NTA; t++) ua[t] = lead ? -cw * uA[t] : 0.0;
+            for (int t = 0; t < NTA; t++)
+              ua[t] = lead ? -cw * (rhsA[t] ? uA[t] - d2[r / w.nw] : uA[t]) : 0.0;
 #pragma unroll
             for (int t = 0; t < NTB; t++)
               ub[t] = lead ? (DIAG ? uA[t < NTA ? t : 0] : uB[t]) : 0.0;
@@ -332,7 +340,9 @@ __global__ void __launch_bounds__(PCU_THREADS)
 __global__ void gram_generic_correction(const ColTable cols, int m,
                                         const double *__restrict__ Dinv,
                                         const double *__restrict__ Cw,
-                                        const WDesc w, double *result, int ld) {
+                                        const WDesc w, double *result, int ld,
+                                        const double *__restrict__ d2,
+                                        int rhs_col) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m * m) return;
   const int i = idx % m, j = idx / m;
@@ -347,6 +357,7 @@ __global__ void gram_generic_correction(const ColTable cols, int m,
       ui = fma(cf * d, cols.p[i][j0 + k], ui);
       uj = fma(cf * d, cols.p[j][j0 + k], uj);
     }
+    if (i == rhs_col) ui -= d2[ci];
     s = fma(Cw[ci] * ui, uj, s);
   }
   result[(size_t)i + (size_t)ld * j] -= s;
@@ -357,7 +368,8 @@ static int launch_gram(pcu_ctx *ctx, const ColTable &cols, int colA0, int colB0,
                        int m, const double *Dinv, const double *Cw,
                        const WDesc &w, long long n, double *result, int ld,
                        long long list0 = 0, long long list1 = 0, int nlist = 0,
-                       int accumulate = 0) {
+                       int accumulate = 0, const double *d2 = nullptr,
+                       int rhs_col = -1) {
   constexpr int NP = GramPairs<NTA, NTB, DIAG>::N;
   long long nchunks = (n + 63) / 64;
   long long need = (nchunks + (PCU_THREADS / 32) - 1) / (PCU_THREADS / 32);
@@ -376,7 +388,7 @@ static int launch_gram(pcu_ctx *ctx, const ColTable &cols, int colA0, int colB0,
   ctx->prof_begin("gram_kernel");
   gram_kernel<NTA, NTB, DIAG><<<grid, PCU_THREADS, 0, ctx->stream>>>(
       cols, colA0, colB0, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter,
-      result, ld, list0, list1, nlist, accumulate);
+      result, ld, list0, list1, nlist, accumulate, d2, rhs_col);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
@@ -387,7 +399,7 @@ template <int NT, int NWC>
 static int launch_gram_fast_t(pcu_ctx *ctx, const ColTable &cols, int m,
                               const double *Dinv, const double *Cw,
                               const WDesc &w, long long n, double *result,
-                              int ld) {
+                              int ld, const double *d2, int rhs_col) {
   constexpr int NP = (NT * (NT + 1)) / 2;
   static int blocks_per_sm = -1;
   if (blocks_per_sm < 0) {
@@ -404,7 +416,8 @@ static int launch_gram_fast_t(pcu_ctx *ctx, const ColTable &cols, int m,
   if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
   ctx->prof_begin("gram_kernel");
   gram_fast_kernel<NT, NWC><<<grid, PCU_THREADS, 0, ctx->stream>>>(
-      cols, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter, result, ld);
+      cols, m, Dinv, Cw, w, n, ctx->d_big_partials, ctx->d_counter, result, ld, d2,
+      rhs_col);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
@@ -415,33 +428,38 @@ template <int NT>
 static int launch_gram_fast_n(pcu_ctx *ctx, const ColTable &cols, int m,
                               const double *Dinv, const double *Cw,
                               const WDesc &w, long long n, double *result,
-                              int ld, int nwc) {
-  if (nwc == 0) return launch_gram_fast_t<NT, 0>(ctx, cols, m, Dinv, Cw, w, n, result, ld);
-  if (nwc == 8) return launch_gram_fast_t<NT, 8>(ctx, cols, m, Dinv, Cw, w, n, result, ld);
-  return launch_gram_fast_t<NT, -1>(ctx, cols, m, Dinv, Cw, w, n, result, ld);
+                              int ld, int nwc, const double *d2, int rhs_col) {
+  if (nwc == 0) return launch_gram_fast_t<NT, 0>(ctx, cols, m, Dinv, Cw, w, n, result, ld, d2, rhs_col);
+  if (nwc == 8) return launch_gram_fast_t<NT, 8>(ctx, cols, m, Dinv, Cw, w, n, result, ld, d2, rhs_col);
+  return launch_gram_fast_t<NT, -1>(ctx, cols, m, Dinv, Cw, w, n, result, ld, d2, rhs_col);
 }
 
 static int launch_gram_fast(pcu_ctx *ctx, const ColTable &cols, int m,
                             const double *Dinv, const double *Cw, const WDesc &w,
-                            long long n, double *result, int ld, int nt, int nwc) {
+                            long long n, double *result, int ld, int nt, int nwc,
+                            const double *d2, int rhs_col) {
   switch (nt) {
-    case 1: return launch_gram_fast_n<1>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
-    case 2: return launch_gram_fast_n<2>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
-    case 3: return launch_gram_fast_n<3>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
-    case 4: return launch_gram_fast_n<4>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
-    default: return launch_gram_fast_n<5>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc);
+    case 1: return launch_gram_fast_n<1>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc, d2, rhs_col);
+    case 2: return launch_gram_fast_n<2>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc, d2, rhs_col);
+    case 3: return launch_gram_fast_n<3>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc, d2, rhs_col);
+    case 4: return launch_gram_fast_n<4>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc, d2, rhs_col);
+    default: return launch_gram_fast_n<5>(ctx, cols, m, Dinv, Cw, w, n, result, ld, nwc, d2, rhs_col);
   }
 }
 
 // Enqueue S = V^T P V into ctx->d_big (col-major, leading dimension *ld_out =
 // 8*ceil(m/8); only entries with row >= col are meaningful).
+// rhs_col >= 0 (must be m - 1, and m <= 40): that column is the right-hand side
+// d1 of a diagonal solve and d2 its constraint part; row rhs_col of S then
+// holds V_j . t1 with t1 = D0^-1 (d1, d2)|x instead of V_j . P d1.
 int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
                      const double *Dinv, const double *Cw, const WDesc &wd,
-                     long long n, int *ld_out) {
+                     long long n, int *ld_out, const double *d2, int rhs_col) {
   const int nt = (m + 7) / 8;
   const int ld = 8 * nt;
   *ld_out = ld;
   if (m == 0) return 0;
+  if (rhs_col >= 0 && (rhs_col != m - 1 || nt > 5)) return 1;
   if (ctx->big_reserve((size_t)ld * ld + 64, 1)) return 1;
   WDesc w = wd;
   if (w.mode == 2 || w.nwcon == 0) {
@@ -455,7 +473,7 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
     // straight-line kernel on the clean 64-row chunks, general kernel on the
     // (at most two) ragged ones
     const int nwc = (w.mode == 0) ? 0 : (w.nw == 8 ? 8 : -1);
-    rc = launch_gram_fast(ctx, cols, m, Dinv, Cw, w, n, R, ld, nt, nwc);
+    rc = launch_gram_fast(ctx, cols, m, Dinv, Cw, w, n, R, ld, nt, nwc, d2, rhs_col);
     if (rc) return rc;
     long long lst[2];
     int nl = 0;
@@ -469,20 +487,20 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
     if (nl > 0) {
       const long long l0 = lst[0], l1 = nl > 1 ? lst[1] : 0;
       switch (nt) {
-        case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
-        case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
-        case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
-        case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
-        default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1); break;
+        case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1, d2, rhs_col); break;
+        case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1, d2, rhs_col); break;
+        case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1, d2, rhs_col); break;
+        case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1, d2, rhs_col); break;
+        default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, l0, l1, nl, 1, d2, rhs_col); break;
       }
     }
   } else if (nt <= 5) {
     switch (nt) {
-      case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
-      case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
-      case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
-      case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
-      default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld); break;
+      case 1: rc = launch_gram<1, 1, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
+      case 2: rc = launch_gram<2, 2, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
+      case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
+      case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
+      default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
     }
   } else {
     // column blocks of 40; block pairs (bi >= bj); ragged last block is masked
@@ -500,7 +518,7 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
   if (wd.mode == 2 && wd.nwcon > 0) {
     const int total = m * m;
     gram_generic_correction<<<(total + 127) / 128, 128, 0, ctx->stream>>>(
-        cols, m, Dinv, Cw, wd, R, ld);
+        cols, m, Dinv, Cw, wd, R, ld, d2, rhs_col);
     ctx->launches++;
     PCU_CUDA_OK(cudaGetLastError());
   }

@@ -30,7 +30,12 @@ __global__ void __launch_bounds__(PCU_THREADS, PCU_GRAM_MINB)
                      const double *__restrict__ Cw, const WDesc w,
                      const long long n, double *__restrict__ partials,
                      unsigned int *counter, double *__restrict__ result,
-                     const int ld) {
+                     const int ld, const double *__restrict__ d2,
+                     const int rhs_col) {
+  // rhs_col >= 0: column rhs_col (the last one) is the right-hand side d1 of a
+  // diagonal solve with constraint part d2; its ROW of the result then holds
+  // V_j . t1, t1 = D0^-1 (d1, d2)|x  (SM.cpp:160-190): the block sums u of that
+  // column are shifted by -d2 on the A side of the correction.
   constexpr int NP = (NT * (NT + 1)) / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = lane >> 2, kk = lane & 3;
@@ -41,9 +46,10 @@ __global__ void __launch_bounds__(PCU_THREADS, PCU_GRAM_MINB)
   double acc[NP][2];
 #pragma unroll
   for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
-  double u[NT], h[NT], hcw = 0.0;
+  double u[NT], h[NT], hcw = 0.0, hd = 0.0;
 #pragma unroll
   for (int t = 0; t < NT; t++) u[t] = h[t] = 0.0;
+  const bool rhs_lane = (rhs_col >= 0) && (8 * (NT - 1) + gi == rhs_col);
 
   const double *col[NT];
   double cmask = 1.0;
@@ -139,6 +145,7 @@ __global__ void __launch_bounds__(PCU_THREADS, PCU_GRAM_MINB)
               hcw = Cw[ci];
 #pragma unroll
               for (int t = 0; t < NT; t++) h[t] = u[t];
+              hd = rhs_lane ? d2[ci] : 0.0;
             }
 #pragma unroll
             for (int t = 0; t < NT; t++) u[t] = 0.0;
@@ -148,11 +155,12 @@ __global__ void __launch_bounds__(PCU_THREADS, PCU_GRAM_MINB)
               for (int ti = 0; ti < NT; ti++) {
 #pragma unroll
                 for (int tj = 0; tj <= ti; tj++) {
-                  dmma884(acc[pp], -hcw * h[ti], h[tj]);
+                  dmma884(acc[pp], -hcw * (ti == NT - 1 ? h[ti] - hd : h[ti]), h[tj]);
                   pp++;
                 }
               }
               hcw = 0.0;
+              hd = 0.0;
 #pragma unroll
               for (int t = 0; t < NT; t++) h[t] = 0.0;
             }

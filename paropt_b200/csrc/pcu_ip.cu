@@ -5,6 +5,7 @@
 // its root rank) and the scalar control flow.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -15,7 +16,8 @@ int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
                      int ncols, long long n, int dst_off);
 int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
                      const double *Dinv, const double *Cw, const WDesc &wd,
-                     long long n, int *ld_out);
+                     long long n, int *ld_out, const double *d2 = nullptr,
+                     int rhs_col = -1);
 
 #define launch_tile pcu_launch_tile
 
@@ -358,6 +360,8 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
     // checked again when the quasi-Newton size is known
   }
   wd = pcu_make_wdesc(p->weighting, nvars);
+  if (getenv("PCU_NO_FUSE21")) opt_no_fuse21 = 1;
+  if (getenv("PCU_NO_RHSGRAM")) opt_no_rhsgram = 1;
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all) {
     for (int i = 0; i < 8; i++) {

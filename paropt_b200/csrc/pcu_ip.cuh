@@ -151,6 +151,10 @@ struct pcu_ip {
   int res_has_step = 0;  // the last ResF launch included the step terms
   double last_comp = 0.0;
   int force_direct_dots = 0;  // debugging: recompute [A|Z]^T p with multi-dots
+  int opt_no_rhsgram = 0;     // debugging: keep the first solve's pass 1 out of the Gram pass
+  int opt_no_fuse21 = 0;      // debugging: keep pass 2 and the next pass 1 separate
+  int pass1_ready = 0;        // Pass2R1F left d1', d2' and [A|Z]^T t1' for the next solve
+  std::vector<double> pass1_r;
   double stats_pmax = 0.0;  // |px|_inf of the last StatsF launch
 
   // resumable major loop state (locals of optimize(), IP.cpp:4570-4606)
@@ -199,7 +203,8 @@ struct pcu_ip {
                        double *max_dual, double *max_infeas, double *res_norm);
   double compFromStats(Vars &vars);
   int setUpKKTDiagSystem(Vars &vars, int use_qn, int identity);
-  int setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag);
+  int setUpKKTDiagRhs(Vars &vars, int use_qn, double mu);
+  int setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag, int with_rhs = 0);
   int computeKKTStep(Vars &vars, Vars &res, Vars &step, int use_qn,
                      int accumulate, double *VTp, int emit_res, double mu_res,
                      int *emitted, int rhs_from_vars = 0);

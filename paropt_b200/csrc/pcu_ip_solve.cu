@@ -11,7 +11,8 @@ int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
                      int ncols, long long n, int dst_off);
 int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
                      const double *Dinv, const double *Cw, const WDesc &wd,
-                     long long n, int *ld_out);
+                     long long n, int *ld_out, const double *d2 = nullptr,
+                     int rhs_col = -1);
 int pcu_lu_factor(int n, double *A, int *piv);
 void pcu_lu_solve(int n, const double *LU, const int *piv, double *b);
 
@@ -32,6 +33,7 @@ enum { BS_MONOTONE = 0, BS_MEHROTRA = 1, BS_MPC = 2, BS_COMP_FRACTION = 3 };
 // ------------------------------------------------------- setUpKKTDiagSystem
 // IP.cpp:1832-1930 (diagonal + Ew factor; G follows in setUpKKTSystem)
 int pcu_ip::setUpKKTDiagSystem(Vars &vars, int use_qn, int identity) {
+  pass1_ready = 0;
   DiagF f;
   f.v = vars.dv();
   f.lb = lb->d;
@@ -48,13 +50,42 @@ int pcu_ip::setUpKKTDiagSystem(Vars &vars, int use_qn, int identity) {
   return launch_tile(ctx, f, nvars, wd, NO_RED);
 }
 
+// setUpKKTDiagSystem + the right-hand side (d1, d2) of the iteration's first
+// diagonal solve, whose block part and reductions then ride in the Gram pass
+// (setUpKKTSystem with_rhs).
+int pcu_ip::setUpKKTDiagRhs(Vars &vars, int use_qn, double mu) {
+  pass1_ready = 0;
+  DiagRhsF f;
+  f.v = vars.dv();
+  f.lb = lb->d;
+  f.ub = ub->d;
+  f.g = g->d;
+  f.Dinv = Dinv->d;
+  f.Cw = Cw->d;
+  f.d1 = d1->d;
+  f.d2 = d2->d;
+  f.ncon = ncon;
+  for (int j = 0; j < ncon; j++) {
+    f.Acol.p[j] = Ac[j]->d;
+    f.z.v[j] = vars.z[j];
+  }
+  double b0 = 0.0;
+  if (qn && use_qn) b0 = qn->b0;
+  b0_used = b0;
+  f.b0sig = b0 + opt.qn_sigma;
+  f.mu = mu;
+  f.k = kconst();
+  return launch_tile(ctx, f, nvars, wd, NO_RED);
+}
+
 // ----------------------------------------------------------- setUpKKTSystem
 // One weighted Gram pass S = [A|Z]^T D0^-1 [A|Z] gives
 //   G  = C0 + S_AA                                  (IP.cpp:1932-1969)
 //   Ce = S_ZZ - S_ZA G^-1 S_AZ - M / (d d^T)        (IP.cpp:2646-2664)
 // gdiag: diagonal added to G (s/zs + t/zt, or `small` for the least-squares
 // start); NULL means s/zs + t/zt of `vars`.
-int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag) {
+int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag,
+                           int with_rhs) {
   const int q = (qn && use_qn) ? qn->size() : 0;
   sq = q;
   const int m = ncon + q;
@@ -63,9 +94,21 @@ int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag) {
   if (q > 0) qn->z_table(V, ncon);
   int ld = 0;
   if (m > 0) {
-    if (pcu_gram_enqueue(ctx, V, m, Dinv->d, Cw->d, wd, nvars, &ld)) return 1;
+    if (with_rhs) {
+      // column m = d1 of the first solve: row m of S is [A|Z]^T t1
+      V.p[m] = d1->d;
+      if (pcu_gram_enqueue(ctx, V, m + 1, Dinv->d, Cw->d, wd, nvars, &ld, d2->d, m))
+        return 1;
+    } else {
+      if (pcu_gram_enqueue(ctx, V, m, Dinv->d, Cw->d, wd, nvars, &ld)) return 1;
+    }
     Sgram.assign((size_t)ld * ld, 0.0);
     if (ctx->big_fetch((size_t)ld * ld, Sgram.data())) return 1;
+    if (with_rhs) {
+      pass1_r.resize(m);
+      for (int j = 0; j < m; j++) pass1_r[j] = Sgram[m + (size_t)ld * j];
+      pass1_ready = 1;
+    }
     for (int j = 0; j < m; j++)  // symmetrise from the lower triangle
       for (int i = j + 1; i < m; i++)
         Sgram[j + (size_t)ld * i] = Sgram[i + (size_t)ld * j];
@@ -176,7 +219,13 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     for (int i = 0; i < m; i++) r[i] = out[i];
     return 0;
   };
-  if (rhs_from_vars) {
+  if (pass1_ready) {
+    // the previous (fused) pass 2 already did this solve's first half
+    pass1_ready = 0;
+    if ((int)pass1_r.size() != m) return 1;
+    r = pass1_r;
+    if (m == 0) r.assign(1, 0.0);
+  } else if (rhs_from_vars) {
     if (m <= 8) {
       if (vars_pass1(Pass1VF<8>())) return 1;
     } else if (m <= 16) {
@@ -329,7 +378,35 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
         for (int j = 0; j < q; j++) fr.beta.v[ncon + j] = kap[j];
       }
     }
-    if (launch_tile(ctx, fr, nvars, wd, NO_RED)) return 1;
+    if (m <= 32 && !opt_no_fuse21) {
+      // ... and the first half of the refinement solve on that residual
+      auto fused21 = [&](auto ff) -> int {
+        ff.v = fr.v; ff.b = fr.b; ff.y = fr.y;
+        ff.lb = fr.lb; ff.ub = fr.ub; ff.Dinv = fr.Dinv; ff.Cw = fr.Cw;
+        ff.d1 = fr.d1; ff.g = fr.g;
+        ff.d2 = d2->d;
+        ff.d1out = t1->d;
+        ff.V = fr.V; ff.alpha = fr.alpha; ff.beta = fr.beta;
+        ff.ncols = m; ff.accumulate = accumulate; ff.from_vars = fr.from_vars;
+        ff.b0sig = fr.b0sig; ff.mu = fr.mu; ff.mu_rhs = fr.mu_rhs; ff.k = k;
+        RedBuf rb = ctx->redbuf(decltype(ff)::NS, 0, 0);
+        if (launch_tile(ctx, ff, nvars, wd, rb)) return 1;
+        double out[decltype(ff)::NS];
+        if (ctx->fetch(out)) return 1;
+        pass1_r.assign(out, out + m);
+        return 0;
+      };
+      int rc;
+      if (m <= 8) rc = fused21(Pass2R1F<8>());
+      else if (m <= 16) rc = fused21(Pass2R1F<16>());
+      else if (m <= 24) rc = fused21(Pass2R1F<24>());
+      else rc = fused21(Pass2R1F<32>());
+      if (rc) return 1;
+      std::swap(d1, t1);  // the next pass 2 reads d1' where the fused pass wrote it
+      pass1_ready = 1;
+    } else {
+      if (launch_tile(ctx, fr, nvars, wd, NO_RED)) return 1;
+    }
     denseResidual(vars, mu_res, b, &y, VTp);
     if (emitted) *emitted = 1;
     return 0;
@@ -1063,8 +1140,23 @@ int pcu_ip::iterate_once(int *converged) {
   bool vtp_valid = true;
 
   PCU_CUDA_OK(cudaEventRecord(ev_k0, ctx->stream));
-  if (setUpKKTDiagSystem(v, use_qn, 0)) return 1;
-  if (setUpKKTSystem(v, use_qn, nullptr)) return 1;
+  // The first solve's right-hand side can ride in the Gram pass when that solve
+  // takes the fused residual-free route (see computeKKTStep).
+  bool rhs_in_gram = false;
+  {
+    const int qa = qn ? qn->size() : 0;
+    const int q0 = (qn && use_qn) ? qa : 0;
+    rhs_in_gram = lazy_res && !opt_no_rhsgram && !force_direct_dots &&
+                  !diagonal_qn_step && q0 == qa && ncon + q0 >= 1 &&
+                  ncon + q0 <= 32;
+  }
+  if (rhs_in_gram) {
+    if (setUpKKTDiagRhs(v, use_qn, mu_for_res)) return 1;
+    if (setUpKKTSystem(v, use_qn, nullptr, 1)) return 1;
+  } else {
+    if (setUpKKTDiagSystem(v, use_qn, 0)) return 1;
+    if (setUpKKTSystem(v, use_qn, nullptr)) return 1;
+  }
   if (diagonal_qn_step) use_qn = 0;
   const int nref = opt.iterative_refinement_steps;
   auto kkt_with_refinement = [&](double mu_res, bool allow_refine) -> int {

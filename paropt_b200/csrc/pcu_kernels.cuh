@@ -27,6 +27,9 @@
 #ifndef PCU_MINB_PASS1
 #define PCU_MINB_PASS1 5
 #endif
+#ifndef PCU_MINB_PASS21
+#define PCU_MINB_PASS21 4
+#endif
 
 struct DVars {  // device view of ParOptVars (IP.h:373-389)
   double *x, *zl, *zu;               // N
@@ -335,6 +338,98 @@ struct DiagF : NoStreams {
     double cdiag = small_;
     if (!identity) cdiag = v.sw[ci] / v.zsw[ci] + v.tw[ci] / v.ztw[ci];
     Cw[ci] = 1.0 / (cdiag + sum[0]);
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {}
+};
+
+// ============================================================== DiagRhsF
+// DiagF fused with the right-hand side of the iteration's first diagonal solve:
+// d1, d2 of solveKKTDiagSystem (IP.cpp:2091-2139) applied to the KKT residual
+// itself (computeKKTRes, IP.cpp:1337-1446, at barrier mu), recomputed from the
+// variables exactly as Pass1VF does.  The solve's block part and the products
+// [A|Z]^T t1 then ride along in the Gram pass as one more column (pcu_gram.cu),
+// so the first solve of an iteration has no pass 1 of its own.
+// Traffic: reads (6 + c)N + 5W, writes 2N + 2W.
+struct DiagRhsF : NoStreams {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 2, HASP = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // zw
+  struct Elem {};
+  DVars v;
+  const double *lb, *ub, *g;
+  double *Dinv, *Cw, *d1, *d2;
+  ColTable Acol;
+  CoefTable z;
+  int ncon;
+  double b0sig, mu;
+  IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) p_(v.zl);
+    if (k.use_upper) p_(v.zu);
+    for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
+  }
+  __device__ __forceinline__ void P(long long ci, Con &con) const {
+    con.d[0] = v.zw[ci];
+  }
+  template <int W>
+  __device__ __forceinline__ void AP(long long i, const double (&coef)[W],
+                                     Elem (&)[W], double (&part)[W][2], AccT *,
+                                     const Con &con) const {
+    double x[W], l[W], u[W], gv[W], zl[W], zu[W], di[W], d[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = 0.0;
+    if (k.use_lower) ldv<W>(v.zl, i, zl);
+    if (k.use_upper) ldv<W>(v.zu, i, zu);
+#pragma unroll
+    for (int q = 0; q < W; q++) d[q] = (zl[q] - zu[q]) - gv[q];
+    for (int j = 0; j < ncon; j++) {
+      double a[W];
+      ldv<W>(Acol.p[j], i, a);
+#pragma unroll
+      for (int q = 0; q < W; q++) d[q] = fma(z.v[j], a[q], d[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      const double dl = x[q] - l[q], du = u[q] - x[q];
+      double c = b0sig;                           // IP.cpp:1864-1910
+      double t = fma(coef[q], con.d[0], d[q]);    // rx
+      if (k.use_lower && l[q] > -k.mbv) {
+        c += zl[q] / dl;
+        t += -(dl * zl[q] - k.kappa * mu) / dl;
+      }
+      if (k.use_upper && u[q] < k.mbv) {
+        c += zu[q] / du;
+        t -= -(du * zu[q] - k.kappa * mu) / du;
+      }
+      di[q] = 1.0 / c;
+      d[q] = t;
+      part[q][0] = coef[q] * coef[q] * di[q];
+      part[q][1] = coef[q] * x[q];
+    }
+    stv<W>(Dinv, i, di);
+    stv<W>(d1, i, d);
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
+                                    AccT &) const {
+    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
+    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
+    Cw[ci] = 1.0 / ((sw / zsw + tw / ztw) + sum[0]);
+    const double bzw = -(((k.wconst + sum[1]) - sw) + tw);
+    const double bsw = (zsw - gamma_sw(k, ci)) - zw;
+    const double btw = (ztw - k.gamma) + zw;
+    const double bzsw = mu - sw * zsw;
+    const double bztw = mu - tw * ztw;
+    d2[ci] = bzw + (bzsw + sw * bsw) / zsw - (bztw + tw * btw) / ztw;
   }
   template <int W>
   __device__ __forceinline__ void C(long long, const double (&)[W],
@@ -1254,6 +1349,250 @@ struct Pass2RF : NoStreams {
     b.tw[ci] = ((ztw - gtw) + zw) + (pztw + pzw);
     b.zsw[ci] = (mu - sw * zsw) - (psw * zsw + sw * pzsw);
     b.ztw[ci] = (mu - tw * ztw) - (ptw * ztw + tw * pztw);
+  }
+};
+
+// ============================================================== Pass2R1F<MR>
+// Pass2RF fused with the first half of the NEXT (iterative-refinement) solve:
+// the residual this pass produces is immediately turned into that solve's
+// d1' / d2' (Pass1RF::A/B), its block solve t1' = D0^-1 (d1', d2')|x and the
+// reductions [A|Z]^T t1' -- the columns of V are read once from HBM (the third
+// round re-reads them through L1/L2 a few hundred cycles later).  Of the
+// residual only the parts pass 2 of the next solve reads are stored (b.zl,
+// b.zu, b.sw, b.tw, b.zsw, b.ztw); d1' goes to `d1out` (not in place: the
+// generic path re-runs A).
+// Traffic: reads (9 + c + q)N + 20W, writes 6N + 10W.   sums: [A|Z]^T t1'
+struct Con3 {
+  static constexpr int ND = 3;
+  double d[3];
+  __device__ __forceinline__ void zero() { d[0] = d[1] = d[2] = 0.0; }
+};
+template <int MR>
+struct Pass2R1F : NoStreams {
+  static constexpr int MINB = PCU_MINB_PASS21;
+  static constexpr int NS = MR, NX = 0, NM = 0, NB = 1, NB2 = 3, NF = 1, FD = 2;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con3 Con;  // yw (this solve), zw + total pzw, yw' (next solve, first half)
+  struct Elem {
+    double d1, dinv, lin;
+  };
+  DVars v, b, y;
+  const double *lb, *ub, *Dinv, *Cw, *d1, *g;
+  double *d2, *d1out;
+  ColTable V;
+  CoefTable alpha, beta;
+  int ncols;
+  int accumulate;
+  int from_vars;
+  double b0sig, mu, mu_rhs;
+  IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(d1); p_(Dinv); p_(v.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) { p_(v.zl); if (!from_vars) p_(b.zl); }
+    if (k.use_upper) { p_(v.zu); if (!from_vars) p_(b.zu); }
+    for (int j = 0; j < ncols; j++) p_(V.p[j]);
+    if (accumulate) {
+      p_(y.x);
+      if (k.use_lower) p_(y.zl);
+      if (k.use_upper) p_(y.zu);
+    }
+  }
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1],
+                                    AccT *) const {
+    double d[W], di[W], lin[W];
+    ldv<W>(d1, i, d);
+    ldv<W>(Dinv, i, di);
+#pragma unroll
+    for (int q = 0; q < W; q++) lin[q] = 0.0;
+    for (int j = 0; j < ncols; j++) {
+      double c[W];
+      ldv<W>(V.p[j], i, c);
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        d[q] = fma(alpha.v[j], c[q], d[q]);
+        lin[q] = fma(beta.v[j], c[q], lin[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      e[q].d1 = d[q];
+      e[q].dinv = di[q];
+      e[q].lin = lin[q];
+      part[q][0] = coef[q] * di[q] * d[q];
+    }
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
+                                    Con &con, AccT &) const {
+    const double yw = Cw[ci] * (d2[ci] - sum[0]);
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    double bsw, btw, bzsw, bztw;
+    if (from_vars) {  // IP.cpp:1361-1389
+      const double zw = v.zw[ci];
+      bsw = (zsw - gamma_sw(k, ci)) - zw;
+      btw = (ztw - k.gamma) + zw;
+      bzsw = mu_rhs - sw * zsw;
+      bztw = mu_rhs - tw * ztw;
+    } else {
+      bsw = b.sw[ci];
+      btw = b.tw[ci];
+      bzsw = b.zsw[ci];
+      bztw = b.ztw[ci];
+    }
+    const double pzsw = yw - bsw;
+    const double pztw = -btw - yw;
+    const double psw = (bzsw - sw * pzsw) / zsw;
+    const double ptw = (bztw - tw * pztw) / ztw;
+    double tzw = yw;
+    if (accumulate) {
+      tzw += y.zw[ci];
+      y.zw[ci] = tzw;
+      y.zsw[ci] += pzsw;
+      y.ztw[ci] += pztw;
+      y.sw[ci] += psw;
+      y.tw[ci] += ptw;
+    } else {
+      y.zw[ci] = yw;
+      y.zsw[ci] = pzsw;
+      y.ztw[ci] = pztw;
+      y.sw[ci] = psw;
+      y.tw[ci] = ptw;
+    }
+    con.d[0] = yw;
+    con.d[1] = v.zw[ci] + tzw;
+  }
+  template <int W>
+  __device__ __forceinline__ void C2(long long i, const double (&coef)[W],
+                                     Elem (&e)[W], const Con &con, AccT &,
+                                     double (&part2)[W][3]) const {
+    double x[W], l[W], u[W], zl[W], zu[W], bzl[W], bzu[W], gv[W];
+    double px[W], pzl[W], pzu[W], rzl[W], rzu[W], dn[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
+    if (k.use_lower) {
+      ldv<W>(v.zl, i, zl);
+      if (!from_vars) ldv<W>(b.zl, i, bzl);
+    }
+    if (k.use_upper) {
+      ldv<W>(v.zu, i, zu);
+      if (!from_vars) ldv<W>(b.zu, i, bzu);
+    }
+    if (from_vars) {  // rzl, rzu of computeKKTRes (IP.cpp:1417-1444)
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        bzl[q] = -((x[q] - l[q]) * zl[q] - k.kappa * mu_rhs);
+        bzu[q] = -((u[q] - x[q]) * zu[q] - k.kappa * mu_rhs);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      px[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+      pzl[q] = 0.0;
+      pzu[q] = 0.0;
+      if (k.use_lower && l[q] > -k.mbv)
+        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv)
+        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+    }
+    if (accumulate) {
+      double o[W];
+      ldv<W>(y.x, i, o);
+#pragma unroll
+      for (int q = 0; q < W; q++) px[q] += o[q];
+      if (k.use_lower) {
+        ldv<W>(y.zl, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzl[q] += o[q];
+      }
+      if (k.use_upper) {
+        ldv<W>(y.zu, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzu[q] += o[q];
+      }
+    }
+    stv<W>(y.x, i, px);
+    if (k.use_lower) stv<W>(y.zl, i, pzl);
+    if (k.use_upper) stv<W>(y.zu, i, pzu);
+    // residual of the linearised system at the (accumulated) step, and the
+    // first half of the diagonal solve on it (IP.cpp:2091-2107)
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      const double dl = x[q] - l[q], du = u[q] - x[q];
+      double r = ((zl[q] - zu[q]) - gv[q]) + e[q].lin;
+      r = fma(-b0sig, px[q], r) + (pzl[q] - pzu[q]);
+      double t = fma(coef[q], con.d[1], r);  // rx
+      rzl[q] = 0.0;
+      rzu[q] = 0.0;
+      if (k.use_lower && l[q] > -k.mbv) {
+        rzl[q] = -(dl * zl[q] - k.kappa * mu) - (dl * pzl[q] + px[q] * zl[q]);
+        t += rzl[q] / dl;
+      }
+      if (k.use_upper && u[q] < k.mbv) {
+        rzu[q] = -(du * zu[q] - k.kappa * mu) - (du * pzu[q] - px[q] * zu[q]);
+        t -= rzu[q] / du;
+      }
+      dn[q] = t;
+      e[q].d1 = t;
+      part2[q][0] = coef[q] * x[q];
+      part2[q][1] = coef[q] * px[q];
+      part2[q][2] = coef[q] * e[q].dinv * t;
+    }
+    stv<W>(d1out, i, dn);
+    if (k.use_lower) stv<W>(b.zl, i, rzl);
+    if (k.use_upper) stv<W>(b.zu, i, rzu);
+  }
+  __device__ __forceinline__ void E(long long ci, const double (&sum2)[3],
+                                    Con &con, AccT &) const {
+    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
+    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double pzw = y.zw[ci], psw = y.sw[ci], ptw = y.tw[ci];
+    const double pzsw = y.zsw[ci], pztw = y.ztw[ci];
+    const double gsw = gamma_sw(k, ci), gtw = k.gamma;
+    const double bzw = -(((k.wconst + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
+    const double bsw = ((zsw - gsw) - zw) + (pzsw - pzw);
+    const double btw = ((ztw - gtw) + zw) + (pztw + pzw);
+    const double bzsw = (mu - sw * zsw) - (psw * zsw + sw * pzsw);
+    const double bztw = (mu - tw * ztw) - (ptw * ztw + tw * pztw);
+    b.sw[ci] = bsw;
+    b.tw[ci] = btw;
+    b.zsw[ci] = bzsw;
+    b.ztw[ci] = bztw;
+    const double dd = bzw + (bzsw + sw * bsw) / zsw - (bztw + tw * btw) / ztw;
+    d2[ci] = dd;
+    con.d[2] = Cw[ci] * (dd - sum2[2]);
+  }
+  template <int W>
+  __device__ __forceinline__ void F(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AccT &acc) const {
+    double t[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[2], e[q].d1);
+#pragma unroll
+    for (int j = 0; j < MR; j++) {
+      if (j < ncols) {
+        double c[W];
+        ldv<W>(V.p[j], i, c);
+#pragma unroll
+        for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
+      }
+    }
+  }
+  __device__ __forceinline__ void FG(long long i, double coef, const Con &con,
+                                     AccT &acc) const {
+    const double t = Dinv[i] * fma(coef, con.d[2], d1out[i]);
+#pragma unroll
+    for (int j = 0; j < MR; j++) {
+      if (j < ncols) acc.s[j] = fma(t, V.p[j][i], acc.s[j]);
+    }
   }
 };
 
