@@ -97,6 +97,36 @@ struct Acc {
   }
 };
 
+// Variant whose sums live in dynamic shared memory ([slot][thread], conflict
+// free): for kernels that carry 16-32 running dot products next to 30+ live
+// values, registers are what limits the loads in flight.  The functor must
+// set SMEM >= NS * PCU_TILE_THREADS * 8.
+__device__ __forceinline__ double *pcu_dyn_smem_d() {
+  extern __shared__ double2 pcu_dyn_smem[];
+  return reinterpret_cast<double *>(pcu_dyn_smem);
+}
+struct SmemSums {
+  double *b;
+  __device__ __forceinline__ double &operator[](int j) const {
+    return b[j * PCU_TILE_THREADS];
+  }
+};
+template <int NS, int NX, int NM>
+struct AccS {
+  SmemSums s;
+  double x[NX > 0 ? NX : 1];
+  double m[NM > 0 ? NM : 1];
+  __device__ __forceinline__ void init() {
+    s.b = pcu_dyn_smem_d() + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < (NS > 0 ? NS : 1); i++) s[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < (NX > 0 ? NX : 1); i++) x[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < (NM > 0 ? NM : 1); i++) m[i] = 1.0e300;
+  }
+};
+
 __device__ __forceinline__ double shfl_xor_d(double v, int o) {
   return __shfl_xor_sync(0xffffffffu, v, o);
 }
@@ -113,8 +143,8 @@ struct RedBuf {
 
 // Block-level + grid-level deterministic combine.  Every thread of the block
 // must call this.  Result layout: sums, then maxima, then minima.
-template <int NS, int NX, int NM>
-__device__ void finish_reduction(Acc<NS, NX, NM> &acc, const RedBuf &rb) {
+template <int NS, int NX, int NM, class AccT_>
+__device__ void finish_reduction(AccT_ &acc, const RedBuf &rb) {
   constexpr int NR = NS + NX + NM;
   __shared__ double sm[PCU_THREADS / 32][NR > 0 ? NR : 1];
   __shared__ bool is_last;
@@ -179,6 +209,23 @@ __device__ void finish_reduction(Acc<NS, NX, NM> &acc, const RedBuf &rb) {
   }
 }
 
+// ------------------------------------------------------- sums of logarithms
+// sum_i log(f_i) is accumulated as the logarithm of a running product: the
+// mantissa product P in [1, 2) and the exponent sum E live in two accumulator
+// slots (P == 0 stands for "empty"), one multiplication and a few integer
+// operations per factor instead of one fp64 log.  Factors must be positive and
+// in [1e-150, 1e150].  lp_value turns the pair into E ln2 + log(P).
+__device__ __forceinline__ void lp_mul(double &P, double &E, double f) {
+  double p = (P == 0.0 ? 1.0 : P) * f;
+  const long long bits = __double_as_longlong(p);
+  const int e = (int)((bits >> 52) & 0x7ff) - 1023;
+  P = __longlong_as_double((bits & 0x800FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
+  E += (double)e;
+}
+__device__ __forceinline__ double lp_value(double P, double E) {
+  return fma(E, 0.693147180559945309417232121458, P == 0.0 ? 0.0 : log(P));
+}
+
 // ------------------------------------------------------------ L2 prefetch
 // The fused kernels read 10-35 independent streams with 50-130 registers per
 // thread, i.e. at 20-50 % occupancy: not enough loads in flight to cover DRAM
@@ -191,6 +238,9 @@ struct NoStreams {
   static constexpr int HASP = 0;  // P(ci, con): per-constraint prologue seen by A (AP form)
   static constexpr int NF = 0;    // third round F / FG after E: E leaves con.d[FD] to broadcast
   static constexpr int FD = 0;
+  static constexpr int SMEM = 0;  // dynamic shared memory per block (bytes)
+  template <class A_>
+  __device__ __forceinline__ void finalize(A_ &) const {}  // per-thread, before the combine
   static constexpr int MINB = 7;  // __launch_bounds__ minimum blocks per SM (<= 73 regs)
   template <class P>
   __device__ __forceinline__ void streams(P &) const {}
@@ -400,7 +450,10 @@ __global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
       generic_range(f, wt, tail_lo, n, threadIdx.x, blockDim.x, acc);
     }
   }
-  if (F::NS + F::NX + F::NM > 0) finish_reduction(acc, rb);
+  if (F::NS + F::NX + F::NM > 0) {
+    f.finalize(acc);
+    finish_reduction<F::NS, F::NX, F::NM>(acc, rb);
+  }
 }
 
 // x + a*p clipped into [lb + dp, ub - dp]  (computeStep, IP.cpp:3148-3191).

@@ -110,8 +110,11 @@ int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
   static int blocks_per_sm = -1;
   if (blocks_per_sm < 0) {
     int v = 0;
+    if (F::SMEM > 0)
+      cudaFuncSetAttribute(tile_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           F::SMEM);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, tile_kernel<F>,
-                                                      PCU_TILE_THREADS, 0) != cudaSuccess ||
+                                                      PCU_TILE_THREADS, F::SMEM) != cudaSuccess ||
         v < 1)
       v = 1;
     blocks_per_sm = v > 16 ? 16 : v;
@@ -124,7 +127,7 @@ int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
   const int grid = (int)(need < cap ? need : cap);
   ctx->prof_begin(pcu_kernel_name<F>());
   rb.prefetch = ctx->prefetch;
-  tile_kernel<F><<<grid, PCU_TILE_THREADS, 0, ctx->stream>>>(f, n, w, rb);
+  tile_kernel<F><<<grid, PCU_TILE_THREADS, F::SMEM, ctx->stream>>>(f, n, w, rb);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());

@@ -17,6 +17,7 @@
 // The weighting-constraint correction  - sum_i Cw_i u_i u_i^T,
 // u_i = sum_{r in block i} coef_r Dinv_r V[r,:], is formed in registers with
 // two shuffles and issued as one more DMMA with a single non-zero k slot.
+#include <stdlib.h>
 #include <string.h>
 
 #include "pcu_ctx.cuh"
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(PCU_THREADS)
 }
 
 #include "pcu_gram_fast.cuh"
+#include "pcu_gram_tma.cuh"
 
 // Compatibility path for weighting patterns the shuffle layout cannot express
 // (WDesc.mode == 2, e.g. the 5-of-6 pattern of examples/rosenbrock): subtracts
@@ -447,6 +449,103 @@ static int launch_gram_fast(pcu_ctx *ctx, const ColTable &cols, int m,
   }
 }
 
+template <int NT, int NWC>
+static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
+                             const double *Dinv, const double *Cw, const WDesc &w,
+                             long long nslabs, long long slab_con,
+                             long long slab_skip, double *result, int ld,
+                             const double *d2, int rhs_col) {
+  constexpr int NP = (NT * (NT + 1)) / 2;
+  int stage_bytes = (m + 1) * PCU_GT_COLB + 512;
+  stage_bytes = (stage_bytes + 127) / 128 * 128;
+  int nstages = (216 * 1024) / stage_bytes;
+  if (nstages > PCU_GT_MAXSTAGES) nstages = PCU_GT_MAXSTAGES;
+  if (nstages < 2) return -1;
+  if (const char *e = getenv("PCU_GT_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= nstages) nstages = v;
+  }
+  const int smem = nstages * stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCU_CUDA_OK(cudaFuncSetAttribute(gram_tma_kernel<NT, NWC>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     220 * 1024));
+    attr_set = true;
+  }
+  int grid = ctx->num_sms;
+  if (nslabs < grid) grid = (int)nslabs;
+  if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
+  ctx->prof_begin("gram_kernel");
+  gram_tma_kernel<NT, NWC><<<grid, PCU_GT_THREADS, smem, ctx->stream>>>(
+      cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, nstages, stage_bytes,
+      ctx->d_big_partials, ctx->d_counter, result, ld, d2, rhs_col);
+  ctx->prof_end();
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_gram_tma(pcu_ctx *ctx, const ColTable &cols, int m,
+                           const double *Dinv, const double *Cw, const WDesc &w,
+                           long long nslabs, long long slab_con, long long slab_skip,
+                           double *result, int ld, const double *d2, int rhs_col,
+                           int nt, int nwc) {
+#define PCU_GT_CASE(NT_)                                                              \
+  case NT_:                                                                           \
+    return nwc == 0 ? launch_gram_tma_t<NT_, 0>(ctx, cols, m, Dinv, Cw, w, nslabs,    \
+                                                slab_con, slab_skip, result, ld, d2,  \
+                                                rhs_col)                              \
+                    : launch_gram_tma_t<NT_, 8>(ctx, cols, m, Dinv, Cw, w, nslabs,    \
+                                                slab_con, slab_skip, result, ld, d2,  \
+                                                rhs_col);
+  switch (nt) {
+    PCU_GT_CASE(1)
+    PCU_GT_CASE(2)
+    PCU_GT_CASE(3)
+    PCU_GT_CASE(4)
+    default:
+      return nwc == 0 ? launch_gram_tma_t<5, 0>(ctx, cols, m, Dinv, Cw, w, nslabs, slab_con,
+                                                slab_skip, result, ld, d2, rhs_col)
+                      : launch_gram_tma_t<5, 8>(ctx, cols, m, Dinv, Cw, w, nslabs, slab_con,
+                                                slab_skip, result, ld, d2, rhs_col);
+  }
+#undef PCU_GT_CASE
+}
+
+// General kernel on the row range [lo, hi) (lo a multiple of 64 and of the block
+// size), added to `result`.
+static int gram_range_accumulate(pcu_ctx *ctx, const ColTable &cols, int m,
+                                 const double *Dinv, const double *Cw,
+                                 const WDesc &w, long long lo, long long hi,
+                                 double *R, int ld, int nt, const double *d2,
+                                 int rhs_col) {
+  ColTable c2;
+  for (int j = 0; j < m; j++) c2.p[j] = cols.p[j] + lo;
+  WDesc w2 = w;
+  const double *Cw2 = Cw, *d22 = d2;
+  if (w.mode == 1) {
+    const long long ncon_elems = (long long)w.nwcon * w.nw;
+    if (lo >= ncon_elems) {
+      w2.mode = 0;
+      w2.nwcon = 0;
+    } else {
+      w2.nwcon = (int)((ncon_elems - lo) / w.nw);
+      Cw2 = Cw + lo / w.nw;
+      if (d2) d22 = d2 + lo / w.nw;
+    }
+    w2.wend = (long long)w2.nwcon * w2.wstride;
+  }
+  const long long n2 = hi - lo;
+  switch (nt) {
+    case 1: return launch_gram<1, 1, true>(ctx, c2, 0, 0, m, Dinv + lo, Cw2, w2, n2, R, ld, 0, 0, 0, 1, d22, rhs_col);
+    case 2: return launch_gram<2, 2, true>(ctx, c2, 0, 0, m, Dinv + lo, Cw2, w2, n2, R, ld, 0, 0, 0, 1, d22, rhs_col);
+    case 3: return launch_gram<3, 3, true>(ctx, c2, 0, 0, m, Dinv + lo, Cw2, w2, n2, R, ld, 0, 0, 0, 1, d22, rhs_col);
+    case 4: return launch_gram<4, 4, true>(ctx, c2, 0, 0, m, Dinv + lo, Cw2, w2, n2, R, ld, 0, 0, 0, 1, d22, rhs_col);
+    default: return launch_gram<5, 5, true>(ctx, c2, 0, 0, m, Dinv + lo, Cw2, w2, n2, R, ld, 0, 0, 0, 1, d22, rhs_col);
+  }
+}
+
 // Enqueue S = V^T P V into ctx->d_big (col-major, leading dimension *ld_out =
 // 8*ceil(m/8); only entries with row >= col are meaningful).
 // rhs_col >= 0 (must be m - 1, and m <= 40): that column is the right-hand side
@@ -469,7 +568,34 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
   int rc = 0;
   const bool fast_ok = nt <= 5 && Dinv != nullptr && n >= 64 &&
                        (w.mode == 0 || (w.mode == 1 && w.nw >= 8));
-  if (fast_ok) {
+  const bool tma_ok = nt <= 5 && Dinv != nullptr && n >= 64 * PCU_GT_ROWS &&
+                      (w.mode == 0 || (w.mode == 1 && w.nw == 8)) &&
+                      !getenv("PCU_NO_GRAM_TMA");
+  if (tma_ok) {
+    // bulk-copy staged kernel on the whole 256-row slabs, general kernel on the
+    // slab that straddles the end of the weighting blocks and on the tail
+    const long long nslabs = n / PCU_GT_ROWS;
+    long long slab_con = 0, slab_skip = -1;
+    if (w.mode == 1) {
+      const long long ncon_elems = (long long)w.nwcon * w.nw;
+      slab_con = ncon_elems / PCU_GT_ROWS;
+      if (slab_con > nslabs) slab_con = nslabs;
+      if (ncon_elems % PCU_GT_ROWS != 0 && slab_con < nslabs) slab_skip = slab_con;
+    }
+    rc = launch_gram_tma(ctx, cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, R, ld,
+                         d2, rhs_col, nt, w.mode == 0 ? 0 : 8);
+    if (rc) return rc;
+    if (slab_skip >= 0) {
+      rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, slab_skip * PCU_GT_ROWS,
+                                 (slab_skip + 1) * PCU_GT_ROWS, R, ld, nt, d2, rhs_col);
+      if (rc) return rc;
+    }
+    if (n % PCU_GT_ROWS != 0) {
+      rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, nslabs * PCU_GT_ROWS, n, R,
+                                 ld, nt, d2, rhs_col);
+      if (rc) return rc;
+    }
+  } else if (fast_ok) {
     // straight-line kernel on the clean 64-row chunks, general kernel on the
     // (at most two) ragged ones
     const int nwc = (w.mode == 0) ? 0 : (w.nw == 8 ? 8 : -1);

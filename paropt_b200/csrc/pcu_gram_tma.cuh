@@ -1,0 +1,280 @@
+// pcu_gram_tma.cuh -- the weighted Gram pass with its operands staged through
+// shared memory by the bulk-copy engine (cp.async.bulk + mbarrier ring).
+//
+// The register-fed kernels (gram_kernel, gram_fast_kernel) can only keep as
+// many bytes in flight as their 128-register threads have outstanding loads,
+// and stop at ~50 % of HBM bandwidth.  Here one producer warp per CTA streams
+// 256-row slabs of every column ([A | Z | d1], Dinv, and the Cw / d2 entries of
+// the slab's weighting blocks) into a ring of shared-memory stages, one bulk
+// copy per column per slab, completion counted on the stage's "full" mbarrier;
+// eight consumer warps read their DMMA fragments from shared memory (each warp
+// owns 32 rows of the slab = four blocks of 8 rows) and release the stage
+// through its "empty" mbarrier.  One CTA per SM, persistent, slabs dealt round
+// robin; bytes in flight = (stages - 1) * stage size, independent of registers.
+//
+// Fragment mapping, block correction and right-hand-side row: exactly as in
+// gram_fast_kernel (pcu_gram_fast.cuh).  Only whole slabs that lie entirely
+// inside or entirely outside the weighting blocks are handled here; the (at
+// most two) remaining row ranges go to gram_kernel.  Included by pcu_gram.cu.
+#pragma once
+
+#define PCU_GT_ROWS 256                         // rows per slab
+#define PCU_GT_CONSUMERS 8                      // consumer warps (32 rows each)
+#define PCU_GT_THREADS (32 * (PCU_GT_CONSUMERS + 1))
+#define PCU_GT_COLB (PCU_GT_ROWS * 8 + 64)      // bytes per staged column (+64: bank shift)
+#define PCU_GT_MAXSTAGES 6
+
+__device__ __forceinline__ unsigned gt_smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void gt_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void gt_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void gt_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gt_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GT_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GT_DONE_%=;\n"
+      "bra GT_WAIT_%=;\n"
+      "GT_DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void *src,
+                                            unsigned bytes, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], "
+      "%2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// NWC: 0 = no weighting correction, 8 = blocks of exactly 8 rows.
+// Slabs [0, slab_con) lie inside the weighting blocks, slab `slab_skip` (if >= 0)
+// straddles their end and is skipped, slabs up to nslabs are plain.
+template <int NT, int NWC>
+__global__ void __launch_bounds__(PCU_GT_THREADS, 1)
+    gram_tma_kernel(const ColTable cols, const int m,
+                    const double *__restrict__ Dinv,
+                    const double *__restrict__ Cw, const WDesc w,
+                    const long long nslabs, const long long slab_con,
+                    const long long slab_skip, const int nstages,
+                    const int stage_bytes, double *__restrict__ partials,
+                    unsigned int *counter, double *__restrict__ result,
+                    const int ld, const double *__restrict__ d2,
+                    const int rhs_col) {
+  constexpr int NP = (NT * (NT + 1)) / 2;
+  extern __shared__ __align__(128) unsigned char gt_smem[];
+  __shared__ __align__(8) unsigned long long gt_full[PCU_GT_MAXSTAGES];
+  __shared__ __align__(8) unsigned long long gt_empty[PCU_GT_MAXSTAGES];
+  __shared__ double sm[PCU_GT_CONSUMERS][64];
+  __shared__ bool is_last;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gi = lane >> 2, kk = lane & 3;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) {
+      gt_mbar_init(gt_smem_u32(&gt_full[s]), 1);
+      gt_mbar_init(gt_smem_u32(&gt_empty[s]), PCU_GT_CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const bool with_d2 = (NWC != 0) && (rhs_col >= 0);
+  const unsigned col_bytes = PCU_GT_ROWS * 8;
+  const unsigned blk_bytes = (PCU_GT_ROWS / 8) * 8;
+  // staged "columns": m vectors, Dinv, then (NWC) Cw and d2 of the slab's blocks
+  const int off_dinv = m * PCU_GT_COLB;
+  const int off_cw = off_dinv + PCU_GT_COLB;
+  const int off_d2 = off_cw + 256;
+
+  double acc[NP][2];
+#pragma unroll
+  for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
+
+  if (warp == PCU_GT_CONSUMERS) {
+    // ------------------------------------------------------------ producer
+    long long it = 0;
+    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+      if (slab == slab_skip) continue;
+      const int s = (int)(it % nstages);
+      const unsigned round = (unsigned)(it / nstages);
+      if (round > 0) gt_mbar_wait(gt_smem_u32(&gt_empty[s]), (round - 1) & 1);
+      const bool in_con = (NWC != 0) && (slab < slab_con);
+      const unsigned full = gt_smem_u32(&gt_full[s]);
+      if (lane == 0) {
+        unsigned tx = (unsigned)(m + 1) * col_bytes;
+        if (in_con) tx += blk_bytes * (with_d2 ? 2u : 1u);
+        gt_mbar_expect_tx(full, tx);
+      }
+      __syncwarp();
+      const unsigned base = gt_smem_u32(gt_smem + (size_t)s * stage_bytes);
+      const long long row0 = slab * PCU_GT_ROWS;
+      for (int c = lane; c < m + 3; c += 32) {
+        if (c < m) {
+          gt_bulk_g2s(base + c * PCU_GT_COLB, cols.p[c] + row0, col_bytes, full);
+        } else if (c == m) {
+          gt_bulk_g2s(base + off_dinv, Dinv + row0, col_bytes, full);
+        } else if (in_con && c == m + 1) {
+          gt_bulk_g2s(base + off_cw, Cw + row0 / 8, blk_bytes, full);
+        } else if (in_con && with_d2 && c == m + 2) {
+          gt_bulk_g2s(base + off_d2, d2 + row0 / 8, blk_bytes, full);
+        }
+      }
+      it++;
+    }
+  } else {
+    // ----------------------------------------------------------- consumers
+    double cmask = 1.0;
+    int colo[NT];  // byte offset of this lane's column of tile t inside a stage
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      int c = 8 * t + gi;
+      if (c >= m) {  // padded column of the last tile: read a valid one, mask it
+        c = m - 1;
+        cmask = 0.0;
+      }
+      colo[t] = c * PCU_GT_COLB;
+    }
+    const bool rhs_lane = (rhs_col >= 0) && (8 * (NT - 1) + gi == rhs_col);
+    const double c1 = w.coef_rest;
+    const double dc = (kk == 0) ? (w.coef0 - w.coef_rest) : 0.0;
+    const int rowb = (warp * 32 + 2 * kk) * 8;  // byte offset of the lane's first row
+
+    long long it = 0;
+    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+      if (slab == slab_skip) continue;
+      const int s = (int)(it % nstages);
+      const unsigned round = (unsigned)(it / nstages);
+      gt_mbar_wait(gt_smem_u32(&gt_full[s]), round & 1);
+      const unsigned char *st = gt_smem + (size_t)s * stage_bytes;
+      const bool in_con = (NWC != 0) && (slab < slab_con);
+      double h[NT], hcw = 0.0, hd = 0.0;
+#pragma unroll
+      for (int t = 0; t < NT; t++) h[t] = 0.0;
+#pragma unroll
+      for (int step = 0; step < 4; step++) {
+        const int ro = rowb + step * 64;
+        const double2 wv = *reinterpret_cast<const double2 *>(st + off_dinv + ro);
+        double2 fb[NT], fa[NT];
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+          fb[t] = *reinterpret_cast<const double2 *>(st + colo[t] + ro);
+          if (t == NT - 1) {
+            fb[t].x *= cmask;
+            fb[t].y *= cmask;
+          }
+          fa[t] = make_double2(fb[t].x * wv.x, fb[t].y * wv.y);
+        }
+        int p = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++) {
+#pragma unroll
+          for (int tj = 0; tj <= ti; tj++) {
+            dmma884(acc[p], fa[ti].x, fb[tj].x);
+            p++;
+          }
+        }
+        p = 0;
+#pragma unroll
+        for (int ti = 0; ti < NT; ti++) {
+#pragma unroll
+          for (int tj = 0; tj <= ti; tj++) {
+            dmma884(acc[p], fa[ti].y, fb[tj].y);
+            p++;
+          }
+        }
+        if (NWC != 0) {
+          if (in_con) {
+            // this step is one block of 8 rows: u = sum coef Dinv V over the block
+            double u[NT];
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+              u[t] = fma(dc, fa[t].x, c1 * (fa[t].x + fa[t].y));
+              u[t] += shfl_xor_d(u[t], 1);
+              u[t] += shfl_xor_d(u[t], 2);
+            }
+            if (kk == step) {  // park it in k-slot `step`
+              const int bi = warp * 4 + step;
+              hcw = *reinterpret_cast<const double *>(st + off_cw + bi * 8);
+              if (rhs_lane) hd = *reinterpret_cast<const double *>(st + off_d2 + bi * 8);
+#pragma unroll
+              for (int t = 0; t < NT; t++) h[t] = u[t];
+            }
+          }
+        }
+      }
+      if (NWC != 0) {
+        if (in_con) {  // one correction DMMA set for the warp's four blocks
+          int pp = 0;
+#pragma unroll
+          for (int ti = 0; ti < NT; ti++) {
+#pragma unroll
+            for (int tj = 0; tj <= ti; tj++) {
+              dmma884(acc[pp], -hcw * (ti == NT - 1 ? h[ti] - hd : h[ti]), h[tj]);
+              pp++;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) gt_mbar_arrive(gt_smem_u32(&gt_empty[s]));
+      it++;
+    }
+  }
+
+  // ---- CTA combine (pair by pair), then grid combine by the last block ----
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    if (warp < PCU_GT_CONSUMERS) {
+      sm[warp][gi + 8 * (2 * kk)] = acc[p][0];
+      sm[warp][gi + 8 * (2 * kk + 1)] = acc[p][1];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      double v = 0.0;
+      for (int ww = 0; ww < PCU_GT_CONSUMERS; ww++) v += sm[ww][threadIdx.x];
+      partials[((size_t)blockIdx.x * NP + p) * 64 + threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int idx = threadIdx.x; idx < NP * 64; idx += blockDim.x) {
+      double v = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; b++)
+        v += partials[(size_t)b * NP * 64 + idx];
+      const int p = idx >> 6, e = idx & 63;
+      int ti = 0, q = p;
+      while (q > ti) {
+        q -= ti + 1;
+        ti++;
+      }
+      const int tj = q;
+      const int row = 8 * ti + (e & 7);
+      const int cc = 8 * tj + (e >> 3);
+      if (row < ld && cc < ld) result[(size_t)row + (size_t)ld * cc] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}

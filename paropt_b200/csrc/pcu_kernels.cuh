@@ -28,7 +28,10 @@
 #define PCU_MINB_PASS1 5
 #endif
 #ifndef PCU_MINB_PASS21
-#define PCU_MINB_PASS21 4
+#define PCU_MINB_PASS21 6
+#endif
+#ifndef PCU_SMEMACC21
+#define PCU_SMEMACC21 1
 #endif
 
 struct DVars {  // device view of ParOptVars (IP.h:373-389)
@@ -686,6 +689,7 @@ struct StatsF : NoStreams {
       ldv<W>(p.zu, i, pzu);
     }
     AccT &a = *acc;
+    double fac = 1.0;  // product of the barrier arguments of these W elements
 #pragma unroll
     for (int q = 0; q < W; q++) {
       const double dl = x[q] - l[q], du = u[q] - x[q];
@@ -719,13 +723,14 @@ struct StatsF : NoStreams {
         a.s[2] = fma(pzu[q], du, a.s[2]);
         a.s[3] = fma(-pzu[q], pxq, a.s[3]);
       }
-      // Barrier terms (IP.cpp:3684-3722).  When both bounds exist and fall in
-      // the same (>1 / <=1) bucket, log(dl) + log(du) = log(dl * du) and the two
-      // quotients share one reciprocal: one log and one division per element.
-      if (ml && mu_ && ((dl > 1.0) == (du > 1.0))) {
+      // Barrier terms (IP.cpp:3684-3722).  The logarithms are accumulated as a
+      // running product (lp_mul: slots 8, 9 hold mantissa product and exponent
+      // sum; finalize() turns them into the sum of logs, so the reference's
+      // > 1 / <= 1 buckets collapse into slot 8); with both bounds present the
+      // two quotients share one reciprocal.
+      if (ml && mu_) {
         const double prod = dl * du;
-        const double lg = log(prod);
-        if (dl > 1.0) a.s[8] += lg; else a.s[9] += lg;
+        fac *= prod;
         const double rinv = 1.0 / prod;
         const double rl = pxq * du * rinv, ru = pxq * dl * rinv;
         if (pxq > 0.0) {
@@ -737,14 +742,12 @@ struct StatsF : NoStreams {
         }
       } else {
         if (ml) {
-          const double lg = log(dl);
-          if (dl > 1.0) a.s[8] += lg; else a.s[9] += lg;
+          fac *= dl;
           const double r = pxq / dl;
           if (pxq > 0.0) a.s[10] += r; else a.s[11] += r;
         }
         if (mu_) {
-          const double lg = log(du);
-          if (du > 1.0) a.s[8] += lg; else a.s[9] += lg;
+          fac *= du;
           const double r = pxq / du;
           if (pxq > 0.0) a.s[11] -= r; else a.s[10] -= r;
         }
@@ -753,6 +756,7 @@ struct StatsF : NoStreams {
       a.s[17] = fma(pxq, pxq, a.s[17]);
       a.x[0] = fmax(a.x[0], fabs(pxq));
     }
+    lp_mul(a.s[8], a.s[9], fac);
   }
   __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
                                     AccT &acc) const {
@@ -767,10 +771,10 @@ struct StatsF : NoStreams {
     acc.s[5] += psw * zsw + ptw * ztw;
     acc.s[6] += sw * pzsw + tw * pztw;
     acc.s[7] += psw * pzsw + ptw * pztw;
-    const double ls = log(sw), lt = log(tw);
-    if (sw > 1.0) acc.s[12] += ls; else acc.s[13] += ls;
-    if (tw > 1.0) acc.s[12] += lt; else acc.s[13] += lt;
-    const double rs = psw / sw, rt = ptw / tw;
+    const double swtw = sw * tw;
+    lp_mul(acc.s[12], acc.s[13], swtw);
+    const double rinv = 1.0 / swtw;
+    const double rs = psw * tw * rinv, rt = ptw * sw * rinv;
     if (psw > 0.0) acc.s[14] += rs; else acc.s[15] += rs;
     if (ptw > 0.0) acc.s[14] += rt; else acc.s[15] += rt;
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
@@ -785,6 +789,12 @@ struct StatsF : NoStreams {
   __device__ __forceinline__ void C(long long, const double (&)[W],
                                     const Elem (&)[W], const Con &,
                                     AccT &) const {}
+  __device__ __forceinline__ void finalize(AccT &acc) const {
+    acc.s[8] = lp_value(acc.s[8], acc.s[9]);
+    acc.s[9] = 0.0;
+    acc.s[12] = lp_value(acc.s[12], acc.s[13]);
+    acc.s[13] = 0.0;
+  }
 };
 
 // ============================================================== TrialF
@@ -799,7 +809,7 @@ struct TrialF : NoStreams {
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
   struct Elem {
-    double lpos, lneg;
+    double f;
   };
   DVars v, p;
   const double *lb, *ub;
@@ -823,25 +833,11 @@ struct TrialF : NoStreams {
 #pragma unroll
     for (int q = 0; q < W; q++) {
       r[q] = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
-      double lp = 0.0, ln = 0.0;
       const bool ml = k.use_lower && l[q] > -k.mbv;
       const bool mu_ = k.use_upper && u[q] < k.mbv;
       const double dl = r[q] - l[q], du = u[q] - r[q];
-      if (ml && mu_ && ((dl > 1.0) == (du > 1.0))) {
-        const double lg = log(dl * du);  // log(dl) + log(du), same bucket
-        if (dl > 1.0) lp += lg; else ln += lg;
-      } else {
-        if (ml) {
-          const double lg = log(dl);
-          if (dl > 1.0) lp += lg; else ln += lg;
-        }
-        if (mu_) {
-          const double lg = log(du);
-          if (du > 1.0) lp += lg; else ln += lg;
-        }
-      }
-      e[q].lpos = lp;
-      e[q].lneg = ln;
+      // factor of the running product whose logarithm is the barrier sum
+      e[q].f = (ml ? dl : 1.0) * (mu_ ? du : 1.0);
       part[q][0] = coef[q] * r[q];
     }
     stv<W>(rx, i, r);
@@ -852,9 +848,7 @@ struct TrialF : NoStreams {
     const double t = step_clip0(v.tw[ci], ax, p.tw[ci], k.dp);
     rsw[ci] = s;
     rtw[ci] = t;
-    const double ls = log(s), lt = log(t);
-    if (s > 1.0) acc.s[2] += ls; else acc.s[3] += ls;
-    if (t > 1.0) acc.s[2] += lt; else acc.s[3] += lt;
+    lp_mul(acc.s[2], acc.s[3], s * t);
     acc.s[4] += gamma_sw(k, ci) * s + k.gamma * t;
     const double rw = ((k.wconst + sum[0]) - s) + t;
     acc.s[5] = fma(rw, rw, acc.s[5]);
@@ -863,11 +857,16 @@ struct TrialF : NoStreams {
   __device__ __forceinline__ void C(long long, const double (&)[W],
                                     const Elem (&e)[W], const Con &,
                                     AccT &acc) const {
+    double f = e[0].f;
 #pragma unroll
-    for (int q = 0; q < W; q++) {
-      acc.s[0] += e[q].lpos;
-      acc.s[1] += e[q].lneg;
-    }
+    for (int q = 1; q < W; q++) f *= e[q].f;
+    lp_mul(acc.s[0], acc.s[1], f);
+  }
+  __device__ __forceinline__ void finalize(AccT &acc) const {
+    acc.s[0] = lp_value(acc.s[0], acc.s[1]);
+    acc.s[1] = 0.0;
+    acc.s[2] = lp_value(acc.s[2], acc.s[3]);
+    acc.s[3] = 0.0;
   }
 };
 
@@ -1371,7 +1370,13 @@ template <int MR>
 struct Pass2R1F : NoStreams {
   static constexpr int MINB = PCU_MINB_PASS21;
   static constexpr int NS = MR, NX = 0, NM = 0, NB = 1, NB2 = 3, NF = 1, FD = 2;
+#if PCU_SMEMACC21
+  // the MR running dot products live in shared memory (AccS): ~48 registers less
+  static constexpr int SMEM = MR * PCU_TILE_THREADS * 8;
+  typedef AccS<NS, NX, NM> AccT;
+#else
   typedef Acc<NS, NX, NM> AccT;
+#endif
   typedef Con3 Con;  // yw (this solve), zw + total pzw, yw' (next solve, first half)
   struct Elem {
     double d1, dinv, lin;

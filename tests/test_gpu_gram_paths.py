@@ -1,0 +1,100 @@
+"""GPU parity of the fused / bulk-copy-staged KKT paths at sizes where they are
+active (n >= 16384 rows, ragged tails, a slab straddling the end of the
+weighting blocks): the optimizer history must match (a) the numpy oracle and
+(b) the plain path (separate pass 1 kernels, register-fed Gram) selected with the
+PCU_NO_* switches.  Tolerances: tests/parity.py (RTOL = 1e-10)."""
+import os
+
+import numpy as np
+import pytest
+
+from paropt_b200 import configs
+from tests.parity import compare_histories
+
+pytestmark = pytest.mark.gpu
+
+SWITCHES = ("PCU_NO_GRAM_TMA", "PCU_NO_RHSGRAM", "PCU_NO_FUSE21")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from paropt_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def run(ctx, make_problem, options, iters, plain):
+    from paropt_b200.api import InteriorPoint
+    for k in SWITCHES:
+        if plain:
+            os.environ[k] = "1"
+        else:
+            os.environ.pop(k, None)
+    try:
+        prob = make_problem()
+        ip = InteriorPoint(prob, dict(options, history_level=2, max_major_iters=iters))
+        ip.optimize()
+        hist = ip.history()
+        ip.free()
+        prob.free()
+    finally:
+        for k in SWITCHES:
+            os.environ.pop(k, None)
+    return hist
+
+
+@pytest.mark.parametrize("name,n", [("C3", 8 * 5003), ("C2", 50001), ("C3", 8 * 4096)])
+def test_fused_paths_match_oracle_and_plain_path(ctx, name, n):
+    from oracle.ip_oracle import InteriorPointOracle
+    from oracle.problems import SepQuad
+    from paropt_b200.api import problem_from_config
+    cfg = configs.get(name, n)
+    iters = 14
+    fused = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], iters, False)
+    plain = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], iters, True)
+    ref = InteriorPointOracle(SepQuad(**cfg["problem"]),
+                              dict(cfg["options"], max_major_iters=iters))
+    ref.optimize()
+    for other, label in ((ref.history, "oracle"), (plain, "plain path")):
+        cnt, worst, first = compare_histories(other, fused, max_iters=iters - 1)
+        assert cnt == iters - 1 and first is None, (label, first, worst)
+
+
+def test_weighting_blocks_ending_inside_a_slab(ctx):
+    """Blocks of 8 cover only the first 24008 of 40024 variables: the Gram slab
+    that straddles their end and the ragged tail go to the general kernel."""
+    from paropt_b200.api import Problem
+
+    n, nwcon = 40024, 3001
+    rng = np.random.default_rng(5)
+    lam = 1.0 + 9.0 * rng.random(n)
+    b = rng.random(n) - 0.3
+    a = 0.5 + rng.random(n)
+
+    class Partial(Problem):
+        def __init__(self):
+            super().__init__(ctx, n, 1, weighting=dict(nwcon=nwcon, wstart=0, nw=8, wstride=8,
+                                                      coef0=1.0, coef_rest=-1.0, wconst=0.0))
+
+        def getVarsAndBounds(self, x, lb, ub):
+            x[:] = 0.5
+            lb[:] = 0.0
+            ub[:] = 1.0
+            x[0:8 * nwcon:8] = 4.0
+            lb[0:8 * nwcon:8] = -1e30
+            ub[0:8 * nwcon:8] = 10.0
+
+        def evalObjCon(self, x):
+            return 0, float(0.5 * np.dot(lam * x, x) + np.dot(b, x)), [0.3 * n - float(np.dot(a, x))]
+
+        def evalObjConGradient(self, x, g, A):
+            g[:] = lam * x + b
+            A[0][:] = -a
+            return 0
+
+    opts = dict(configs.get("C3", 8192)["options"])
+    fused = run(ctx, Partial, opts, 14, False)
+    plain = run(ctx, Partial, opts, 14, True)
+    cnt, worst, first = compare_histories(plain, fused, max_iters=13)
+    assert cnt == 13 and first is None, (first, worst)
