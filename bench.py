@@ -110,15 +110,18 @@ def kernel_words(name, N, W, c, q):
     table = {
         "ResF": (9 + c) * N + 10 * W,
         "DiagF": 6 * N + 5 * W,
+        "DiagRhsF": (8 + c) * N + 7 * W,                    # DiagF + d1, d2 of the first solve
         "Pass1F": 9 * N + 11 * W,
         "Pass1RF": (8 + m) * N + 11 * W,
+        "Pass1VF": (9 + c + m) * N + 7 * W,
         "Pass2F": (12 + m) * N + 15 * W + 3 * N + 5 * W,   # the accumulating refinement solve
         "Pass2RF": (16 + m) * N + 30 * W,                   # pass 2 + refinement residual
+        "Pass2R1F": (14 + m) * N + 30 * W,                  # ... + first half of the next solve
         "StatsF": 9 * N + 8 * W,
         "TrialF": 5 * N + 6 * W,
         "Update1F": (10 + c) * N + 15 * W,
         "Update2F": (5 + c) * N + W,
-        "gram_kernel": (m + 1) * N + W,
+        "gram_kernel": (m + 2) * N + 2 * W,                 # [A|Z|d1] columns + Dinv; Cw, d2
         "mdot_kernel": None,  # (1 + columns of the chunk) N, see below
     }
     name = name.split("<")[0]

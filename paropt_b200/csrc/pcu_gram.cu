@@ -449,35 +449,45 @@ static int launch_gram_fast(pcu_ctx *ctx, const ColTable &cols, int m,
   }
 }
 
-template <int NT, int NWC>
+template <int NT, int NWC, int NCW>
 static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
                              const double *Dinv, const double *Cw, const WDesc &w,
-                             long long nslabs, long long slab_con,
-                             long long slab_skip, double *result, int ld,
-                             const double *d2, int rhs_col) {
+                             long long n, double *result, int ld, const double *d2,
+                             int rhs_col, long long *rows_done, long long *skip_lo) {
   constexpr int NP = (NT * (NT + 1)) / 2;
-  int stage_bytes = (m + 1) * PCU_GT_COLB + 512;
+  constexpr int ROWS = PCU_GT_ROWS(NCW);
+  int stage_bytes = (m + 1) * PCU_GT_COLB(NCW) + 2 * ROWS;
   stage_bytes = (stage_bytes + 127) / 128 * 128;
-  int nstages = (216 * 1024) / stage_bytes;
+  int nstages = (208 * 1024) / stage_bytes;
   if (nstages > PCU_GT_MAXSTAGES) nstages = PCU_GT_MAXSTAGES;
   if (nstages < 2) return -1;
   if (const char *e = getenv("PCU_GT_STAGES")) {
     const int v = atoi(e);
     if (v >= 2 && v <= nstages) nstages = v;
   }
+  // whole slabs; the one that straddles the end of the weighting blocks is skipped
+  const long long nslabs = n / ROWS;
+  long long slab_con = 0, slab_skip = -1;
+  if (w.mode == 1) {
+    const long long ncon_elems = (long long)w.nwcon * w.nw;
+    slab_con = ncon_elems / ROWS;
+    if (slab_con > nslabs) slab_con = nslabs;
+    if (ncon_elems % ROWS != 0 && slab_con < nslabs) slab_skip = slab_con;
+  }
+  *rows_done = nslabs * ROWS;
+  *skip_lo = slab_skip >= 0 ? slab_skip * ROWS : -1;
   const int smem = nstages * stage_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCU_CUDA_OK(cudaFuncSetAttribute(gram_tma_kernel<NT, NWC>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     220 * 1024));
-    attr_set = true;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    PCU_CUDA_OK(cudaFuncSetAttribute(gram_tma_kernel<NT, NWC, NCW>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
   }
   int grid = ctx->num_sms;
   if (nslabs < grid) grid = (int)nslabs;
   if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
   ctx->prof_begin("gram_kernel");
-  gram_tma_kernel<NT, NWC><<<grid, PCU_GT_THREADS, smem, ctx->stream>>>(
+  gram_tma_kernel<NT, NWC, NCW><<<grid, PCU_GT_THREADS(NCW), smem, ctx->stream>>>(
       cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, nstages, stage_bytes,
       ctx->d_big_partials, ctx->d_counter, result, ld, d2, rhs_col);
   ctx->prof_end();
@@ -488,29 +498,24 @@ static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
 
 static int launch_gram_tma(pcu_ctx *ctx, const ColTable &cols, int m,
                            const double *Dinv, const double *Cw, const WDesc &w,
-                           long long nslabs, long long slab_con, long long slab_skip,
-                           double *result, int ld, const double *d2, int rhs_col,
-                           int nt, int nwc) {
-#define PCU_GT_CASE(NT_)                                                              \
-  case NT_:                                                                           \
-    return nwc == 0 ? launch_gram_tma_t<NT_, 0>(ctx, cols, m, Dinv, Cw, w, nslabs,    \
-                                                slab_con, slab_skip, result, ld, d2,  \
-                                                rhs_col)                              \
-                    : launch_gram_tma_t<NT_, 8>(ctx, cols, m, Dinv, Cw, w, nslabs,    \
-                                                slab_con, slab_skip, result, ld, d2,  \
-                                                rhs_col);
+                           long long n, double *result, int ld, const double *d2,
+                           int rhs_col, int nt, int nwc, long long *rows_done,
+                           long long *skip_lo) {
+#define PCU_GT_ARGS ctx, cols, m, Dinv, Cw, w, n, result, ld, d2, rhs_col, rows_done, skip_lo
+#define PCU_GT_CASE(NT_, NCW_)                                          \
+  case NT_:                                                             \
+    return nwc == 0 ? launch_gram_tma_t<NT_, 0, NCW_>(PCU_GT_ARGS)      \
+                    : launch_gram_tma_t<NT_, 8, NCW_>(PCU_GT_ARGS);
   switch (nt) {
-    PCU_GT_CASE(1)
-    PCU_GT_CASE(2)
-    PCU_GT_CASE(3)
-    PCU_GT_CASE(4)
-    default:
-      return nwc == 0 ? launch_gram_tma_t<5, 0>(ctx, cols, m, Dinv, Cw, w, nslabs, slab_con,
-                                                slab_skip, result, ld, d2, rhs_col)
-                      : launch_gram_tma_t<5, 8>(ctx, cols, m, Dinv, Cw, w, nslabs, slab_con,
-                                                slab_skip, result, ld, d2, rhs_col);
+    PCU_GT_CASE(1, 16)
+    PCU_GT_CASE(2, 16)
+    PCU_GT_CASE(3, 16)
+    PCU_GT_CASE(4, 8)
+    PCU_GT_CASE(5, 8)
   }
+  return -1;
 #undef PCU_GT_CASE
+#undef PCU_GT_ARGS
 }
 
 // General kernel on the row range [lo, hi) (lo a multiple of 64 and of the block
@@ -568,31 +573,25 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
   int rc = 0;
   const bool fast_ok = nt <= 5 && Dinv != nullptr && n >= 64 &&
                        (w.mode == 0 || (w.mode == 1 && w.nw >= 8));
-  const bool tma_ok = nt <= 5 && Dinv != nullptr && n >= 64 * PCU_GT_ROWS &&
+  const bool tma_ok = nt <= 5 && Dinv != nullptr && n >= 32768 &&
                       (w.mode == 0 || (w.mode == 1 && w.nw == 8)) &&
                       !getenv("PCU_NO_GRAM_TMA");
   if (tma_ok) {
-    // bulk-copy staged kernel on the whole 256-row slabs, general kernel on the
-    // slab that straddles the end of the weighting blocks and on the tail
-    const long long nslabs = n / PCU_GT_ROWS;
-    long long slab_con = 0, slab_skip = -1;
-    if (w.mode == 1) {
-      const long long ncon_elems = (long long)w.nwcon * w.nw;
-      slab_con = ncon_elems / PCU_GT_ROWS;
-      if (slab_con > nslabs) slab_con = nslabs;
-      if (ncon_elems % PCU_GT_ROWS != 0 && slab_con < nslabs) slab_skip = slab_con;
-    }
-    rc = launch_gram_tma(ctx, cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, R, ld,
-                         d2, rhs_col, nt, w.mode == 0 ? 0 : 8);
-    if (rc) return rc;
-    if (slab_skip >= 0) {
-      rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, slab_skip * PCU_GT_ROWS,
-                                 (slab_skip + 1) * PCU_GT_ROWS, R, ld, nt, d2, rhs_col);
+    // bulk-copy staged kernel on the whole slabs, general kernel on the slab that
+    // straddles the end of the weighting blocks and on the tail
+    long long rows_done = 0, skip_lo = -1;
+    rc = launch_gram_tma(ctx, cols, m, Dinv, Cw, w, n, R, ld, d2, rhs_col, nt,
+                         w.mode == 0 ? 0 : 8, &rows_done, &skip_lo);
+    if (rc) return 1;
+    if (skip_lo >= 0) {
+      const long long hi = skip_lo + (nt <= 3 ? PCU_GT_ROWS(16) : PCU_GT_ROWS(8));
+      rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, skip_lo, hi, R, ld, nt, d2,
+                                 rhs_col);
       if (rc) return rc;
     }
-    if (n % PCU_GT_ROWS != 0) {
-      rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, nslabs * PCU_GT_ROWS, n, R,
-                                 ld, nt, d2, rhs_col);
+    if (rows_done < n) {
+      rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, rows_done, n, R, ld, nt, d2,
+                                 rhs_col);
       if (rc) return rc;
     }
   } else if (fast_ok) {

@@ -4,10 +4,10 @@
 // The register-fed kernels (gram_kernel, gram_fast_kernel) can only keep as
 // many bytes in flight as their 128-register threads have outstanding loads,
 // and stop at ~50 % of HBM bandwidth.  Here one producer warp per CTA streams
-// 256-row slabs of every column ([A | Z | d1], Dinv, and the Cw / d2 entries of
+// slabs (32 rows per consumer warp) of every column ([A | Z | d1], Dinv, and the Cw / d2 entries of
 // the slab's weighting blocks) into a ring of shared-memory stages, one bulk
 // copy per column per slab, completion counted on the stage's "full" mbarrier;
-// eight consumer warps read their DMMA fragments from shared memory (each warp
+// the consumer warps (16 for up to 24 columns, else 8) read their DMMA fragments from shared memory (each warp
 // owns 32 rows of the slab = four blocks of 8 rows) and release the stage
 // through its "empty" mbarrier.  One CTA per SM, persistent, slabs dealt round
 // robin; bytes in flight = (stages - 1) * stage size, independent of registers.
@@ -18,10 +18,10 @@
 // most two) remaining row ranges go to gram_kernel.  Included by pcu_gram.cu.
 #pragma once
 
-#define PCU_GT_ROWS 256                         // rows per slab
-#define PCU_GT_CONSUMERS 8                      // consumer warps (32 rows each)
-#define PCU_GT_THREADS (32 * (PCU_GT_CONSUMERS + 1))
-#define PCU_GT_COLB (PCU_GT_ROWS * 8 + 64)      // bytes per staged column (+64: bank shift)
+// NCW consumer warps of 32 rows each: a slab has 32 NCW rows
+#define PCU_GT_ROWS(NCW) (32 * (NCW))
+#define PCU_GT_THREADS(NCW) (32 * ((NCW) + 1))
+#define PCU_GT_COLB(NCW) (PCU_GT_ROWS(NCW) * 8 + 64)  // bytes per staged column (+64: bank shift)
 #define PCU_GT_MAXSTAGES 6
 
 __device__ __forceinline__ unsigned gt_smem_u32(const void *p) {
@@ -63,8 +63,8 @@ __device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void *src,
 // NWC: 0 = no weighting correction, 8 = blocks of exactly 8 rows.
 // Slabs [0, slab_con) lie inside the weighting blocks, slab `slab_skip` (if >= 0)
 // straddles their end and is skipped, slabs up to nslabs are plain.
-template <int NT, int NWC>
-__global__ void __launch_bounds__(PCU_GT_THREADS, 1)
+template <int NT, int NWC, int NCW>
+__global__ void __launch_bounds__(PCU_GT_THREADS(NCW), 1)
     gram_tma_kernel(const ColTable cols, const int m,
                     const double *__restrict__ Dinv,
                     const double *__restrict__ Cw, const WDesc w,
@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(PCU_GT_THREADS, 1)
                     const int ld, const double *__restrict__ d2,
                     const int rhs_col) {
   constexpr int NP = (NT * (NT + 1)) / 2;
+  constexpr int ROWS = PCU_GT_ROWS(NCW), COLB = PCU_GT_COLB(NCW);
   extern __shared__ __align__(128) unsigned char gt_smem[];
   __shared__ __align__(8) unsigned long long gt_full[PCU_GT_MAXSTAGES];
   __shared__ __align__(8) unsigned long long gt_empty[PCU_GT_MAXSTAGES];
-  __shared__ double sm[PCU_GT_CONSUMERS][64];
+  __shared__ double sm[NCW][64];
   __shared__ bool is_last;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,25 +88,25 @@ __global__ void __launch_bounds__(PCU_GT_THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; s++) {
       gt_mbar_init(gt_smem_u32(&gt_full[s]), 1);
-      gt_mbar_init(gt_smem_u32(&gt_empty[s]), PCU_GT_CONSUMERS);
+      gt_mbar_init(gt_smem_u32(&gt_empty[s]), NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const bool with_d2 = (NWC != 0) && (rhs_col >= 0);
-  const unsigned col_bytes = PCU_GT_ROWS * 8;
-  const unsigned blk_bytes = (PCU_GT_ROWS / 8) * 8;
+  const unsigned col_bytes = ROWS * 8;
+  const unsigned blk_bytes = (ROWS / 8) * 8;
   // staged "columns": m vectors, Dinv, then (NWC) Cw and d2 of the slab's blocks
-  const int off_dinv = m * PCU_GT_COLB;
-  const int off_cw = off_dinv + PCU_GT_COLB;
-  const int off_d2 = off_cw + 256;
+  const int off_dinv = m * COLB;
+  const int off_cw = off_dinv + COLB;
+  const int off_d2 = off_cw + ROWS;
 
   double acc[NP][2];
 #pragma unroll
   for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
 
-  if (warp == PCU_GT_CONSUMERS) {
+  if (warp == NCW) {
     // ------------------------------------------------------------ producer
     long long it = 0;
     for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
@@ -122,10 +123,10 @@ __global__ void __launch_bounds__(PCU_GT_THREADS, 1)
       }
       __syncwarp();
       const unsigned base = gt_smem_u32(gt_smem + (size_t)s * stage_bytes);
-      const long long row0 = slab * PCU_GT_ROWS;
+      const long long row0 = slab * ROWS;
       for (int c = lane; c < m + 3; c += 32) {
         if (c < m) {
-          gt_bulk_g2s(base + c * PCU_GT_COLB, cols.p[c] + row0, col_bytes, full);
+          gt_bulk_g2s(base + c * COLB, cols.p[c] + row0, col_bytes, full);
         } else if (c == m) {
           gt_bulk_g2s(base + off_dinv, Dinv + row0, col_bytes, full);
         } else if (in_con && c == m + 1) {
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS, 1)
         c = m - 1;
         cmask = 0.0;
       }
-      colo[t] = c * PCU_GT_COLB;
+      colo[t] = c * COLB;
     }
     const bool rhs_lane = (rhs_col >= 0) && (8 * (NT - 1) + gi == rhs_col);
     const double c1 = w.coef_rest;
@@ -239,14 +240,14 @@ __global__ void __launch_bounds__(PCU_GT_THREADS, 1)
   // ---- CTA combine (pair by pair), then grid combine by the last block ----
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    if (warp < PCU_GT_CONSUMERS) {
+    if (warp < NCW) {
       sm[warp][gi + 8 * (2 * kk)] = acc[p][0];
       sm[warp][gi + 8 * (2 * kk + 1)] = acc[p][1];
     }
     __syncthreads();
     if (threadIdx.x < 64) {
       double v = 0.0;
-      for (int ww = 0; ww < PCU_GT_CONSUMERS; ww++) v += sm[ww][threadIdx.x];
+      for (int ww = 0; ww < NCW; ww++) v += sm[ww][threadIdx.x];
       partials[((size_t)blockIdx.x * NP + p) * 64 + threadIdx.x] = v;
     }
     __syncthreads();
