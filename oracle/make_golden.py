@@ -77,9 +77,52 @@ def run_reference(cfg, nranks=1, extra_env=None):
             "log": rows, "status": status}
 
 
+# Option coverage (barrier strategies, starting-point
+# strategies, norms, line-search and quasi-Newton flavours): (label, base
+# workload, option overrides, problem-size override).  Histories are capped at
+# 30 iterations to keep the fixtures small.
+VARIANTS = [
+    ("mehrotra", "C1", dict(barrier_strategy="mehrotra"), None),
+    ("mpc", "C1", dict(barrier_strategy="mehrotra_predictor_corrector"), None),
+    ("compfrac", "C1", dict(barrier_strategy="complementarity_fraction"), None),
+    ("lsq_start", "C1", dict(starting_point_strategy="least_squares_multipliers"), None),
+    ("no_start", "C1", dict(starting_point_strategy="no_start_strategy"), None),
+    ("l1norm", "C1", dict(norm_type="l1"), None),
+    ("l2norm", "C1", dict(norm_type="l2"), None),
+    ("backtrack", "C1", dict(use_backtracking_alpha=True), None),
+    ("damped", "C1", dict(qn_update_type="damped_update"), None),
+    ("yts_sts", "C1", dict(qn_diag_type="yts_over_sts"), None),
+    ("mpc", "C3", dict(barrier_strategy="mehrotra_predictor_corrector"), 4000),
+    ("compfrac", "C3", dict(barrier_strategy="complementarity_fraction"), 4000),
+    ("lsq_start", "C3", dict(starting_point_strategy="least_squares_multipliers"), 4000),
+    ("slp", "C3", dict(sequential_linear_method=True), 4000),
+    ("mehrotra", "C2", dict(barrier_strategy="mehrotra"), 4000),
+    ("norefine", "C2", dict(iterative_refinement_steps=0), 4000),
+    ("refine2", "C3", dict(iterative_refinement_steps=2), 4000),
+]
+
+
+def variant_config(base, overrides, n):
+    cfg = configs.small(base)
+    if n is not None:
+        key = "n" if cfg["kind"] == "rosenbrock" else "ntotal"
+        cfg["problem"][key] = n
+    cfg["options"] = dict(cfg["options"], max_major_iters=30, **overrides)
+    return cfg
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--variants" in sys.argv:
+        for label, base, overrides, n in VARIANTS:
+            data = run_reference(variant_config(base, overrides, n))
+            data["generator"] = "oracle/make_golden.py --variants (oracle/_ref/ref_driver, unmodified reference)"
+            fname = "%s_var_%s.json" % (base, label)
+            with open(os.path.join(out_dir, fname), "w") as fp:
+                json.dump(data, fp, separators=(",", ":"))
+            print(fname, "niter", data["final"]["niter"], data["status"])
+        return
     jobs = [("C1", 1), ("C2", 1), ("C3", 1), ("C4", 1), ("C2", 2), ("C3", 2)]
     for name, nranks in jobs:
         cfg = configs.small(name)

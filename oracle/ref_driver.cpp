@@ -118,8 +118,13 @@ void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
   double comp = ip->computeComp(v);
   double max_prime, max_dual, max_infeas, res_norm;
   ip->computeKKTRes(v, ip->barrier_param, ip->residual);
-  ip->computeResNorm(PAROPT_INFTY_NORM, ip->residual, &max_prime, &max_dual,
-                     &max_infeas, &res_norm);
+  // in the norm the optimizer itself uses (option norm_type, IP.cpp:4462-4470)
+  ParOptNormType ntype = PAROPT_INFTY_NORM;
+  const char *nname = ip->options->getEnumOption("norm_type");
+  if (strcmp(nname, "l1") == 0) ntype = PAROPT_L1_NORM;
+  else if (strcmp(nname, "l2") == 0) ntype = PAROPT_L2_NORM;
+  ip->computeResNorm(ntype, ip->residual, &max_prime, &max_dual, &max_infeas,
+                     &res_norm);
 
   // Recover the accepted line-search step length from x_k - x_{k-1} and the
   // (already alpha_x-scaled) step still stored in ip->update.x

@@ -210,6 +210,7 @@ struct pcu_ip {
                      int *emitted, int rhs_from_vars = 0);
   void denseResidual(Vars &vars, double mu, Vars &res, Vars *step,
                      const double *ATp);
+  int addMehrotraCorrectorResidual(Vars &step, Vars &res);
   int stepStats(Vars &vars, Vars &step, double tau, double *sums, double *mins);
   int scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
                     const double *VTp, double fixed_scale, StepScale *out);

@@ -424,6 +424,21 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
   return 0;
 }
 
+// addMehrotraCorrectorResidual (IP.cpp:1729-1789)
+int pcu_ip::addMehrotraCorrectorResidual(Vars &step, Vars &res) {
+  for (int i = 0; i < ncon; i++) {
+    res.zs[i] -= step.s[i] * step.zs[i];
+    res.zt[i] -= step.t[i] * step.zt[i];
+  }
+  MehrotraCorrF f;
+  f.p = step.dv();
+  f.r = res.dv();
+  f.lb = lb->d;
+  f.ub = ub->d;
+  f.k = kconst();
+  return launch_tile(ctx, f, nvars, wd, NO_RED);
+}
+
 int pcu_ip::stepStats(Vars &vars, Vars &step, double tau, double *sums,
                       double *mins) {
   StatsF f;
@@ -1213,14 +1228,13 @@ int pcu_ip::iterate_once(int *converged) {
     if (sigma < 0.01) sigma = 0.01;
     barrier_param = sigma * comp;
     if (barrier_param < 0.09999 * abs_res_tol) barrier_param = 0.09999 * abs_res_tol;
-    if (ls.barrier_strategy == BS_MPC) {
-      fprintf(stderr,
-              "paropt_b200: mehrotra_predictor_corrector is not built yet; "
-              "using mehrotra\n");
-    }
     if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
     computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
-    if (kkt_with_refinement(barrier_param, true)) return 1;
+    // predictor-corrector: second-order terms of the affine step; the corrected
+    // residual cannot be refined (IP.cpp:5029-5051)
+    const bool mpc = ls.barrier_strategy == BS_MPC;
+    if (mpc && addMehrotraCorrectorResidual(upd, res)) return 1;
+    if (kkt_with_refinement(barrier_param, !mpc)) return 1;
   }
 
   // fraction to the boundary (IP.cpp:5069-5077)

@@ -440,6 +440,54 @@ struct DiagRhsF : NoStreams {
                                     AccT &) const {}
 };
 
+// ============================================================== MehrotraCorrF
+// addMehrotraCorrectorResidual (IP.cpp:1729-1789): second-order terms of the
+// affine predictor step added to the complementarity residuals.
+// Traffic: reads 7N + 6W, writes 2N + 2W.
+struct MehrotraCorrF : NoStreams {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  DVars p, r;  // step (read), residual (updated in place)
+  const double *lb, *ub;
+  IPConst k;
+
+  template <int W>
+  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1], AccT *) const {}
+  __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &,
+                                    AccT &) const {
+    r.zsw[ci] -= p.sw[ci] * p.zsw[ci];
+    r.ztw[ci] -= p.tw[ci] * p.ztw[ci];
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&)[W],
+                                    const Elem (&)[W], const Con &,
+                                    AccT &) const {
+    double px[W], l[W], u[W], pz[W], rz[W];
+    ldv<W>(p.x, i, px);
+    if (k.use_lower) {
+      ldv<W>(lb, i, l);
+      ldv<W>(p.zl, i, pz);
+      ldv<W>(r.zl, i, rz);
+#pragma unroll
+      for (int q = 0; q < W; q++)
+        if (l[q] > -k.mbv) rz[q] -= px[q] * pz[q];
+      stv<W>(r.zl, i, rz);
+    }
+    if (k.use_upper) {
+      ldv<W>(ub, i, u);
+      ldv<W>(p.zu, i, pz);
+      ldv<W>(r.zu, i, rz);
+#pragma unroll
+      for (int q = 0; q < W; q++)
+        if (u[q] < k.mbv) rz[q] += px[q] * pz[q];
+      stv<W>(r.zu, i, rz);
+    }
+  }
+};
+
 // ============================================================== Pass1F
 // First half of solveKKTDiagSystem (IP.cpp:2091-2139): d1, d2 and the first
 // ParOptQuasiDefBlockMat::apply (SM.cpp:160-190), t1 = D0^-1 (d1, d2)|x.

@@ -92,3 +92,22 @@ def test_host_array_problem_matches_reference(ctx, name, iters, flavour):
     assert extra > 0 and extra % (3 * nbytes) == 0, (h2d, nbytes, ngeval, prob.ncon)
     # the iterate: once per objective evaluation, never again for the gradient
     assert d2h == nbytes * neval
+
+
+from tests.test_oracle_golden import VARIANT_ITERS, VARIANT_NAMES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", VARIANT_NAMES)
+def test_option_variants_match_reference(ctx, name):
+    """Barrier strategies (Mehrotra, predictor-corrector, complementarity
+    fraction), starting-point strategies, l1 / l2 norms, back-tracking line search,
+    damped / yts-over-sts quasi-Newton updates, sequential linear method, 0 and 2
+    refinement steps: the first 30 iterations of the unmodified reference."""
+    gold = load_golden(name)
+    out = run_gpu(ctx, gold["config"])
+    iters = VARIANT_ITERS.get(name, len(gold["history"]))
+    n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters)
+    assert first is None, (first, worst)
+    assert n == iters
+    for row, rec in list(zip(gold["log"], out["history"]))[:iters]:
+        assert row["info"] == rec["info"], (row, rec["iter"])
