@@ -1065,7 +1065,9 @@ int pcu_ip::iterate_once(int *converged) {
   double comp;
   if (ls.barrier_strategy == BS_COMP_FRACTION) {
     comp = compFromStats(v);
-    if (snapshot(k, comp, 0, 0, 0, 0)) return 1;
+    // the history row shows the norms at the barrier the iteration starts with
+    computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+    if (snapshot(k, comp, max_prime, max_dual, max_infeas, res_norm)) return 1;
     barrier_param = opt.monotone_barrier_fraction * comp;
     if (barrier_param < 0.1 * abs_res_tol) barrier_param = 0.1 * abs_res_tol;
     if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
