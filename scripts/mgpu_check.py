@@ -32,6 +32,41 @@ for name, iters in (("C2_small", 41), ("C3_small", 50)):
                               "worst": max(worst.values()), "nvars_local": prob.nvars}
     ip.free()
     prob.free()
+# fused / bulk-copy-staged paths at a size where they are active on every rank,
+# against the plain path (PCU_NO_* switches) and against the host-array problem
+from paropt_b200 import configs  # noqa: E402
+from paropt_b200.api import BuiltinProblem  # noqa: E402
+
+SWITCHES = ("PCU_NO_GRAM_TMA", "PCU_NO_RHSGRAM", "PCU_NO_FUSE21")
+
+
+def run_big(make, plain):
+    for k in SWITCHES:
+        if plain:
+            os.environ[k] = "1"
+        else:
+            os.environ.pop(k, None)
+    prob = make()
+    ip = InteriorPoint(prob, dict(cfg_big["options"], history_level=2, max_major_iters=13))
+    ip.optimize()
+    hist = ip.history()
+    ip.free()
+    prob.free()
+    for k in SWITCHES:
+        os.environ.pop(k, None)
+    return hist
+
+
+for label, nbig in (("C3_big", 8 * 5003 * ctx.size), ("C2_big", 50001 * ctx.size)):
+    cfg_big = configs.get(label[:2], nbig)
+    fused = run_big(lambda: problem_from_config(ctx, cfg_big), False)
+    plain = run_big(lambda: problem_from_config(ctx, cfg_big), True)
+    host = run_big(lambda: BuiltinProblem(ctx, "sepquad", host=True, nthreads=2,
+                                          **cfg_big["problem"]), False)
+    n1, w1, f1 = compare_histories(plain, fused, max_iters=12)
+    n2, w2, f2 = compare_histories(fused, host, max_iters=12)
+    verdict["cases"][label] = {"compared": min(n1, n2), "first_violation": f1 or f2,
+                               "worst": max(max(w1.values()), max(w2.values()))}
 if ctx.rank == 0:
     print("MGPU_VERDICT " + json.dumps(verdict))
 ctx.close()
