@@ -347,6 +347,7 @@ def run_ours(args):
         hip.iterate(e_warm)
         barrier()
         h2d0, d2h0 = hp.transfer_bytes()
+        ht0 = hp.host_times() if hasattr(hp, "host_times") else None
         i0 = hip.counters()[0]
         ctx.timer_start()
         hip.iterate(e_steps)
@@ -354,12 +355,19 @@ def run_ours(args):
         barrier()
         h2d1, d2h1 = hp.transfer_bytes()
         e_done = hip.counters()[0] - i0
+        host_ms = None
+        if hasattr(hp, "host_times"):
+            ht1 = hp.host_times()
+            host_ms = {"d2h": (ht1[0] - ht0[0]) / max(e_done, 1),
+                       "user": (ht1[1] - ht0[1]) / max(e_done, 1),
+                       "h2d_if_PCU_HOST_TIMING": (ht1[2] - ht0[2]) / max(e_done, 1)}
         e_times = hip.iter_times()[-e_done:] if e_done else []
         e2e = {"value": e_done / (e_ms / 1e3) if e_ms > 0 else 0.0, "unit": UNIT,
                "h2d_bytes_per_step": (h2d1 - h2d0) // max(e_done, 1),
                "d2h_bytes_per_step": (d2h1 - d2h0) // max(e_done, 1),
                "steps": e_done, "warmup": e_warm, "ms_per_step": e_ms / max(e_done, 1),
                "callback_ms_per_step": sum(t[1] for t in e_times) / max(len(e_times), 1),
+               "host_ms_per_step": host_ms,
                "note": "same loop through the host-array problem API: " + e_kind +
                        "; per callback the iterate is copied device->host and the "
                        "gradients host->device (pinned buffers) inside the timed region; "

@@ -147,6 +147,11 @@ pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
                                      const pcu_host_callbacks *callbacks);
 /* Bytes moved over PCIe by a host-array problem since its creation. */
 int pcu_problem_transfer_bytes(pcu_problem *prob, int64_t *h2d, int64_t *d2h);
+/* Wall-clock milliseconds a host-array problem spent copying the iterate to the
+   host, inside the user callbacks, and (only with PCU_HOST_TIMING set, which
+   synchronises after the uploads) copying the gradients to the device.        */
+int pcu_problem_host_times(pcu_problem *prob, double *d2h_ms, double *user_ms,
+                           double *h2d_ms);
 
 /* MPI_Allreduce(MPI_SUM) stand-in for user callbacks that reduce their own
    partial sums (e.g. examples/rosenbrock/rosenbrock.cpp:100-117): `vals` are

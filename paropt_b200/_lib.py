@@ -102,6 +102,7 @@ SIGNATURES = {
                                      C.POINTER(HostCallbacks)]),
     "pcu_problem_transfer_bytes": (C.c_int, [VP, C.POINTER(C.c_int64),
                                              C.POINTER(C.c_int64)]),
+    "pcu_problem_host_times": (C.c_int, [VP, c_double_p, c_double_p, c_double_p]),
     "pcu_problem_destroy": (None, [VP]),
     "pcu_ctx_allreduce_sum": (C.c_int, [VP, c_double_p, C.c_int]),
     "pcu_problem_create_sepquad_host": (VP, [VP, C.POINTER(SepQuadParams), C.c_int,

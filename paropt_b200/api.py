@@ -321,6 +321,12 @@ class BuiltinProblem:
         self.lib.pcu_problem_transfer_bytes(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def host_times(self):
+        """(d2h_ms, user_ms, h2d_ms) of a host-array problem (see the header)."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.lib.pcu_problem_host_times(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
     def free(self):
         if self.h:
             self.lib.pcu_problem_destroy(self.h)

@@ -361,6 +361,7 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
   }
   wd = pcu_make_wdesc(p->weighting, nvars);
   if (getenv("PCU_NO_FUSE21")) opt_no_fuse21 = 1;
+  if (getenv("PCU_NO_FUSE2S")) opt_no_fuse2s = 1;
   if (getenv("PCU_NO_RHSGRAM")) opt_no_rhsgram = 1;
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all) {

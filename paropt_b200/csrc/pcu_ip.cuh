@@ -152,6 +152,10 @@ struct pcu_ip {
   double last_comp = 0.0;
   int force_direct_dots = 0;  // debugging: recompute [A|Z]^T p with multi-dots
   int opt_no_rhsgram = 0;     // debugging: keep the first solve's pass 1 out of the Gram pass
+  int opt_no_fuse2s = 0;      // debugging: keep the step statistics in their own pass
+  int stats_ready = 0;        // Pass2SF left the step statistics in stats_out
+  double stats_tau_used = 0.0;
+  double stats_out[32];
   int opt_no_fuse21 = 0;      // debugging: keep pass 2 and the next pass 1 separate
   int pass1_ready = 0;        // Pass2R1F left d1', d2' and [A|Z]^T t1' for the next solve
   std::vector<double> pass1_r;
@@ -207,7 +211,7 @@ struct pcu_ip {
   int setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag, int with_rhs = 0);
   int computeKKTStep(Vars &vars, Vars &res, Vars &step, int use_qn,
                      int accumulate, double *VTp, int emit_res, double mu_res,
-                     int *emitted, int rhs_from_vars = 0);
+                     int *emitted, int rhs_from_vars = 0, double stats_tau = -1.0);
   void denseResidual(Vars &vars, double mu, Vars &res, Vars *step,
                      const double *ATp);
   int addMehrotraCorrectorResidual(Vars &step, Vars &res);

@@ -156,8 +156,10 @@ int pcu_ip::setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag,
 // VTp (optional, ncon + qn->size() values): [A | Z]^T of the (accumulated) step.
 int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
                            int accumulate, double *VTp, int emit_res,
-                           double mu_res, int *emitted, int rhs_from_vars) {
+                           double mu_res, int *emitted, int rhs_from_vars,
+                           double stats_tau) {
   if (emitted) *emitted = 0;
+  stats_ready = 0;
   {
     // The residual-free first solve needs the fused pass-1 / pass-2 kernels;
     // otherwise materialise the right-hand side first.
@@ -411,7 +413,22 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     if (emitted) *emitted = 1;
     return 0;
   }
-  if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
+  if (stats_tau > 0.0 && !opt_no_fuse2s) {
+    // last pass of the iteration's solves: take the step statistics on the way
+    Pass2SF fs;
+    fs.v = f2.v; fs.b = f2.b; fs.y = f2.y;
+    fs.lb = f2.lb; fs.ub = f2.ub; fs.Dinv = f2.Dinv; fs.Cw = f2.Cw;
+    fs.d1 = f2.d1; fs.d2 = f2.d2; fs.g = g->d;
+    fs.V = f2.V; fs.alpha = f2.alpha; fs.ncols = f2.ncols;
+    fs.accumulate = f2.accumulate; fs.tau = stats_tau; fs.k = f2.k;
+    RedBuf rb = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
+    if (launch_tile(ctx, fs, nvars, wd, rb)) return 1;
+    if (ctx->fetch(stats_out)) return 1;
+    stats_ready = 1;
+    stats_tau_used = stats_tau;
+  } else {
+    if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
+  }
   if (VTp && !derived) {
     ColTable Vall;
     for (int j = 0; j < ncon; j++) Vall.p[j] = Ac[j]->d;
@@ -441,18 +458,24 @@ int pcu_ip::addMehrotraCorrectorResidual(Vars &step, Vars &res) {
 
 int pcu_ip::stepStats(Vars &vars, Vars &step, double tau, double *sums,
                       double *mins) {
-  StatsF f;
-  f.v = vars.dv();
-  f.p = step.dv();
-  f.lb = lb->d;
-  f.ub = ub->d;
-  f.g = g->d;
-  f.tau = tau;
-  f.k = kconst();
-  RedBuf rb = ctx->redbuf(StatsF::NS, StatsF::NX, StatsF::NM);
-  if (launch_tile(ctx, f, nvars, wd, rb)) return 1;
   double out[StatsF::NS + StatsF::NX + StatsF::NM];
-  if (ctx->fetch(out)) return 1;
+  if (stats_ready && stats_tau_used == tau) {
+    // taken by the last pass of the KKT solve (Pass2SF)
+    memcpy(out, stats_out, sizeof(out));
+    stats_ready = 0;
+  } else {
+    StatsF f;
+    f.v = vars.dv();
+    f.p = step.dv();
+    f.lb = lb->d;
+    f.ub = ub->d;
+    f.g = g->d;
+    f.tau = tau;
+    f.k = kconst();
+    RedBuf rb = ctx->redbuf(StatsF::NS, StatsF::NX, StatsF::NM);
+    if (launch_tile(ctx, f, nvars, wd, rb)) return 1;
+    if (ctx->fetch(out)) return 1;
+  }
   memcpy(sums, out, sizeof(double) * StatsF::NS);
   stats_pmax = out[StatsF::NS];
   mins[0] = std::min(1.0, out[StatsF::NS + 1]);
@@ -1194,10 +1217,19 @@ int pcu_ip::iterate_once(int *converged) {
     return 0;
   };
   {
+    // the fraction-to-boundary parameter is known before the solves (it depends on
+    // the barrier only, IP.cpp:5069-5077), so the last pass of the last solve can
+    // take the step statistics (not under the Mehrotra strategies, whose
+    // predictor step is only a probe)
+    double tau_s = -1.0;
+    if (!mehrotra) {
+      tau_s = opt.min_fraction_to_boundary;
+      if (1.0 - barrier_param >= tau_s) tau_s = 1.0 - barrier_param;
+    }
     // first step without refinement timing split: KKT solve = setup + first step
     int emitted = 0;
     if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nref > 0, mu_for_res,
-                       &emitted, lazy_res ? 1 : 0))
+                       &emitted, lazy_res ? 1 : 0, nref == 0 ? tau_s : -1.0))
       return 1;
     PCU_CUDA_OK(cudaEventRecord(ev_k1, ctx->stream));
     for (int it = 0; it < nref; it++) {
@@ -1205,7 +1237,7 @@ int pcu_ip::iterate_once(int *converged) {
           computeKKTRes(v, mu_for_res, res, &upd, VTp.data(), VTp.data() + nA))
         return 1;
       if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data(), it + 1 < nref,
-                         mu_for_res, &emitted))
+                         mu_for_res, &emitted, 0, it + 1 == nref ? tau_s : -1.0))
         return 1;
     }
   }

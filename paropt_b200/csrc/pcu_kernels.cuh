@@ -30,6 +30,9 @@
 #ifndef PCU_MINB_PASS21
 #define PCU_MINB_PASS21 6
 #endif
+#ifndef PCU_MINB_PASS2S
+#define PCU_MINB_PASS2S 7
+#endif
 #ifndef PCU_SMEMACC21
 #define PCU_SMEMACC21 1
 #endif
@@ -677,66 +680,14 @@ struct Pass2F : NoStreams {
   }
 };
 
-// ============================================================== StatsF
-// One pass giving every reduction needed between the KKT step and the line
-// search: computeMaxStep (IP.cpp:2942-3103), computeCompStep (IP.cpp:2825-2923,
-// as the 4 coefficients of its bilinear form in (alpha_x, alpha_z)), and the
-// sums of evalMeritInitDeriv / evalInfeasDeriv (IP.cpp:3652-3790, 3465-3509).
-// Traffic: reads 9N + 8W.
-//   sums: 0-3 bound comp poly [1, ax, az, ax*az]; 4-7 sparse comp poly;
-//         8,9 pos/neg log (bounds); 10,11 pos/neg p/(.) (bounds);
-//         12,13 pos/neg log (sw,tw); 14,15 pos/neg p/(.) (sw,tw);
-//         16 g.p; 17 p.p; 18 gam.(sw,tw); 19 gam.(psw,ptw);
-//         20 |cw - sw + tw|^2; 21 (cw - sw + tw).(Aw p - psw + ptw)
-//   maxima: 0 |px|_inf;  mins: 0 max_x, 1 max_z
-struct StatsF : NoStreams {
-  static constexpr int MINB = PCU_MINB_STATS;
-  static constexpr int NS = 22, NX = 1, NM = 2, NB = 2;
-  typedef Acc<NS, NX, NM> AccT;
-  typedef Con0 Con;
-  struct Elem {};
-  DVars v, p;
-  const double *lb, *ub, *g;
-  double tau;
-  IPConst k;
-
-  template <class P>
-  __device__ __forceinline__ void streams(P &p_) const {
-    p_(v.x); p_(p.x); p_(lb); p_(ub); p_(g);
-    if (k.use_lower) { p_(v.zl); p_(p.zl); }
-    if (k.use_upper) { p_(v.zu); p_(p.zu); }
-  }
-
-  // All element reductions happen here (acc is null on the generic path's
-  // first, sum-only visit of an element).
-  template <int W>
-  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&)[W], double (&part)[W][2],
-                                    AccT *acc) const {
-    double x[W], l[W], u[W], px[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(p.x, i, px);
-#pragma unroll
-    for (int q = 0; q < W; q++) {
-      part[q][0] = coef[q] * x[q];
-      part[q][1] = coef[q] * px[q];
-    }
-    if (!acc) return;
-    double zl[W], zu[W], pzl[W], pzu[W], gv[W];
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(g, i, gv);
-#pragma unroll
-    for (int q = 0; q < W; q++) zl[q] = zu[q] = pzl[q] = pzu[q] = 0.0;
-    if (k.use_lower) {
-      ldv<W>(v.zl, i, zl);
-      ldv<W>(p.zl, i, pzl);
-    }
-    if (k.use_upper) {
-      ldv<W>(v.zu, i, zu);
-      ldv<W>(p.zu, i, pzu);
-    }
-    AccT &a = *acc;
+// Element / constraint terms of the step statistics, shared by StatsF and by
+// Pass2SF (which produces the step in the same pass).
+template <int W, class AccT_>
+__device__ __forceinline__ void stats_elements(
+    const IPConst &k, double tau, const double (&x)[W], const double (&l)[W],
+    const double (&u)[W], const double (&zl)[W], const double (&zu)[W],
+    const double (&px)[W], const double (&pzl)[W], const double (&pzu)[W],
+    const double (&gv)[W], AccT_ &a) {
     double fac = 1.0;  // product of the barrier arguments of these W elements
 #pragma unroll
     for (int q = 0; q < W; q++) {
@@ -805,9 +756,13 @@ struct StatsF : NoStreams {
       a.x[0] = fmax(a.x[0], fabs(pxq));
     }
     lp_mul(a.s[8], a.s[9], fac);
-  }
-  __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
-                                    AccT &acc) const {
+}
+template <class AccT_>
+__device__ __forceinline__ void stats_constraint(const IPConst &k, double tau,
+                                                 long long ci, const DVars &v,
+                                                 const DVars &p,
+                                                 const double (&sum)[2],
+                                                 AccT_ &acc) {
     const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
     const double psw = p.sw[ci], ptw = p.tw[ci], pzsw = p.zsw[ci],
                  pztw = p.ztw[ci];
@@ -832,11 +787,223 @@ struct StatsF : NoStreams {
     const double rw2 = (sum[1] - psw) + ptw;
     acc.s[20] = fma(rw1, rw1, acc.s[20]);
     acc.s[21] = fma(rw1, rw2, acc.s[21]);
+}
+
+// ============================================================== StatsF
+// One pass giving every reduction needed between the KKT step and the line
+// search: computeMaxStep (IP.cpp:2942-3103), computeCompStep (IP.cpp:2825-2923,
+// as the 4 coefficients of its bilinear form in (alpha_x, alpha_z)), and the
+// sums of evalMeritInitDeriv / evalInfeasDeriv (IP.cpp:3652-3790, 3465-3509).
+// Traffic: reads 9N + 8W.
+//   sums: 0-3 bound comp poly [1, ax, az, ax*az]; 4-7 sparse comp poly;
+//         8,9 pos/neg log (bounds); 10,11 pos/neg p/(.) (bounds);
+//         12,13 pos/neg log (sw,tw); 14,15 pos/neg p/(.) (sw,tw);
+//         16 g.p; 17 p.p; 18 gam.(sw,tw); 19 gam.(psw,ptw);
+//         20 |cw - sw + tw|^2; 21 (cw - sw + tw).(Aw p - psw + ptw)
+//   maxima: 0 |px|_inf;  mins: 0 max_x, 1 max_z
+struct StatsF : NoStreams {
+  static constexpr int MINB = PCU_MINB_STATS;
+  static constexpr int NS = 22, NX = 1, NM = 2, NB = 2;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  DVars v, p;
+  const double *lb, *ub, *g;
+  double tau;
+  IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(v.x); p_(p.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) { p_(v.zl); p_(p.zl); }
+    if (k.use_upper) { p_(v.zu); p_(p.zu); }
+  }
+
+  // All element reductions happen here (acc is null on the generic path's
+  // first, sum-only visit of an element).
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&)[W], double (&part)[W][2],
+                                    AccT *acc) const {
+    double x[W], l[W], u[W], px[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(p.x, i, px);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      part[q][0] = coef[q] * x[q];
+      part[q][1] = coef[q] * px[q];
+    }
+    if (!acc) return;
+    double zl[W], zu[W], pzl[W], pzu[W], gv[W];
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = pzl[q] = pzu[q] = 0.0;
+    if (k.use_lower) {
+      ldv<W>(v.zl, i, zl);
+      ldv<W>(p.zl, i, pzl);
+    }
+    if (k.use_upper) {
+      ldv<W>(v.zu, i, zu);
+      ldv<W>(p.zu, i, pzu);
+    }
+    stats_elements<W>(k, tau, x, l, u, zl, zu, px, pzl, pzu, gv, *acc);
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
+                                    AccT &acc) const {
+    stats_constraint(k, tau, ci, v, p, sum, acc);
   }
   template <int W>
   __device__ __forceinline__ void C(long long, const double (&)[W],
                                     const Elem (&)[W], const Con &,
                                     AccT &) const {}
+  __device__ __forceinline__ void finalize(AccT &acc) const {
+    acc.s[8] = lp_value(acc.s[8], acc.s[9]);
+    acc.s[9] = 0.0;
+    acc.s[12] = lp_value(acc.s[12], acc.s[13]);
+    acc.s[13] = 0.0;
+  }
+};
+
+// ============================================================== Pass2SF
+// Pass2F (the last pass of the iteration's KKT solves) fused with StatsF: the
+// step statistics are taken from the step while it is still in registers, so
+// the separate 9N + 8W statistics pass disappears (one extra stream: g).
+// Traffic: Pass2F + N.   Reductions: as StatsF (sums in shared memory).
+struct Pass2SF : NoStreams {
+  static constexpr int MINB = PCU_MINB_PASS2S;
+  static constexpr int NS = 22, NX = 1, NM = 2, NB = 1, NB2 = 2;
+  static constexpr int SMEM = NS * PCU_TILE_THREADS * 8;
+  typedef AccS<NS, NX, NM> AccT;
+  typedef Con1 Con;  // yw
+  struct Elem {
+    double d1, dinv;
+  };
+  DVars v, b, y;
+  const double *lb, *ub, *Dinv, *Cw, *d1, *d2, *g;
+  ColTable V;
+  CoefTable alpha;
+  int ncols;
+  int accumulate;
+  double tau;
+  IPConst k;
+
+  template <class P>
+  __device__ __forceinline__ void streams(P &p_) const {
+    p_(d1); p_(Dinv); p_(v.x); p_(lb); p_(ub); p_(g);
+    if (k.use_lower) { p_(v.zl); p_(b.zl); }
+    if (k.use_upper) { p_(v.zu); p_(b.zu); }
+    for (int j = 0; j < ncols; j++) p_(V.p[j]);
+    if (accumulate) {
+      p_(y.x);
+      if (k.use_lower) p_(y.zl);
+      if (k.use_upper) p_(y.zu);
+    }
+  }
+
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1], AccT *) const {
+    double d[W], di[W];
+    ldv<W>(d1, i, d);
+    ldv<W>(Dinv, i, di);
+    for (int j = 0; j < ncols; j++) {
+      double c[W];
+      ldv<W>(V.p[j], i, c);
+#pragma unroll
+      for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j], c[q], d[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      e[q].d1 = d[q];
+      e[q].dinv = di[q];
+      part[q][0] = coef[q] * di[q] * d[q];
+    }
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
+                                    Con &con, AccT &) const {
+    const double yw = Cw[ci] * (d2[ci] - sum[0]);
+    con.d[0] = yw;
+    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+    const double pzsw = yw - b.sw[ci];
+    const double pztw = -b.tw[ci] - yw;
+    const double psw = (b.zsw[ci] - sw * pzsw) / zsw;
+    const double ptw = (b.ztw[ci] - tw * pztw) / ztw;
+    if (accumulate) {
+      y.zw[ci] += yw;
+      y.zsw[ci] += pzsw;
+      y.ztw[ci] += pztw;
+      y.sw[ci] += psw;
+      y.tw[ci] += ptw;
+    } else {
+      y.zw[ci] = yw;
+      y.zsw[ci] = pzsw;
+      y.ztw[ci] = pztw;
+      y.sw[ci] = psw;
+      y.tw[ci] = ptw;
+    }
+  }
+  template <int W>
+  __device__ __forceinline__ void C2(long long i, const double (&coef)[W],
+                                     const Elem (&e)[W], const Con &con, AccT &acc,
+                                     double (&part2)[W][2]) const {
+    double x[W], l[W], u[W], zl[W], zu[W], bzl[W], bzu[W], gv[W];
+    double px[W], pzl[W], pzu[W];
+    ldv<W>(v.x, i, x);
+    ldv<W>(lb, i, l);
+    ldv<W>(ub, i, u);
+    ldv<W>(g, i, gv);
+#pragma unroll
+    for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
+    if (k.use_lower) {
+      ldv<W>(v.zl, i, zl);
+      ldv<W>(b.zl, i, bzl);
+    }
+    if (k.use_upper) {
+      ldv<W>(v.zu, i, zu);
+      ldv<W>(b.zu, i, bzu);
+    }
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      px[q] = e[q].dinv * fma(coef[q], con.d[0], e[q].d1);
+      pzl[q] = 0.0;
+      pzu[q] = 0.0;
+      if (k.use_lower && l[q] > -k.mbv)
+        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv)
+        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+    }
+    if (accumulate) {
+      double o[W];
+      ldv<W>(y.x, i, o);
+#pragma unroll
+      for (int q = 0; q < W; q++) px[q] += o[q];
+      if (k.use_lower) {
+        ldv<W>(y.zl, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzl[q] += o[q];
+      }
+      if (k.use_upper) {
+        ldv<W>(y.zu, i, o);
+#pragma unroll
+        for (int q = 0; q < W; q++) pzu[q] += o[q];
+      }
+    }
+    stv<W>(y.x, i, px);
+    if (k.use_lower) stv<W>(y.zl, i, pzl);
+    if (k.use_upper) stv<W>(y.zu, i, pzu);
+    stats_elements<W>(k, tau, x, l, u, zl, zu, px, pzl, pzu, gv, acc);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      part2[q][0] = coef[q] * x[q];
+      part2[q][1] = coef[q] * px[q];
+    }
+  }
+  __device__ __forceinline__ void E(long long ci, const double (&sum2)[2],
+                                    const Con &, AccT &acc) const {
+    stats_constraint(k, tau, ci, v, y, sum2, acc);
+  }
   __device__ __forceinline__ void finalize(AccT &acc) const {
     acc.s[8] = lp_value(acc.s[8], acc.s[9]);
     acc.s[9] = 0.0;

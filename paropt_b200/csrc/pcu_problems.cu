@@ -3,7 +3,10 @@
 // problems of DESIGN.md ("Synthetic problems").  These are the "user code" side
 // of the boundary (ParOptProblem.h:143-282); their time is reported separately.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include "pcu_kernels.cuh"
 #include "pcu_problem.cuh"
@@ -527,8 +530,15 @@ struct CallbackProblem : pcu_problem {
 // ======================================================= host-array callbacks
 // The reference's problem callbacks read and write ParOptVec::getArray host
 // pointers; here those arrays are page-locked mirrors owned by the problem.
+static double host_now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
 struct HostProblem : pcu_problem {
   pcu_host_callbacks cb;
+  double t_d2h = 0.0, t_user = 0.0, t_h2d = 0.0;  // wall-clock ms per phase
+  bool timing = false;  // PCU_HOST_TIMING: synchronise after the uploads to time them
   double *hx = nullptr, *hg = nullptr;
   std::vector<double *> hA;
   cudaEvent_t up_done = nullptr;  // last host->device copy of g / A
@@ -562,10 +572,14 @@ struct HostProblem : pcu_problem {
   int fetch_x(pcu_vec *x) {
     if (same_point_hint) return 0;
     const size_t bytes = sizeof(double) * (size_t)nvars;
+    const double t0 = host_now_ms();
+    if (timing) cudaStreamSynchronize(ctx->stream);  // kernels that produce x
+    const double t1 = timing ? host_now_ms() : t0;
     if (nvars > 0) {
       PCU_CUDA_OK(cudaMemcpyAsync(hx, x->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
       PCU_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
+    t_d2h += host_now_ms() - t1;
     d2h_bytes += (long long)bytes;
     return 0;
   }
@@ -585,14 +599,24 @@ struct HostProblem : pcu_problem {
   }
   int evalObjCon(pcu_vec *x, double *fobj, double *cons) override {
     if (fetch_x(x)) return 1;
-    return cb.eval_obj_con(cb.user, nvars, hx, fobj, cons);
+    const double t0 = host_now_ms();
+    const int fail = cb.eval_obj_con(cb.user, nvars, hx, fobj, cons);
+    t_user += host_now_ms() - t0;
+    return fail;
   }
   int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) override {
     if (fetch_x(x) || wait_uploads()) return 1;
+    const double t0 = host_now_ms();
     int fail = cb.eval_obj_con_gradient(cb.user, nvars, hx, hg, hA.data());
+    const double t1 = host_now_ms();
+    t_user += t1 - t0;
     if (push(g, hg)) return 1;
     for (int j = 0; j < ncon; j++)
       if (push(Ac[j], hA[j])) return 1;
+    if (timing) {
+      cudaStreamSynchronize(ctx->stream);
+      t_h2d += host_now_ms() - t1;
+    }
     // stream-ordered: the kernels that consume g / A are enqueued behind the copies
     PCU_CUDA_OK(cudaEventRecord(up_done, ctx->stream));
     up_pending = true;
@@ -648,7 +672,18 @@ pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
     delete p;
     return nullptr;
   }
+  p->timing = getenv("PCU_HOST_TIMING") != nullptr;
   return p;
+}
+
+int pcu_problem_host_times(pcu_problem *prob, double *d2h_ms, double *user_ms,
+                           double *h2d_ms) {
+  HostProblem *p = dynamic_cast<HostProblem *>(prob);
+  if (!p) return 1;
+  if (d2h_ms) *d2h_ms = p->t_d2h;
+  if (user_ms) *user_ms = p->t_user;
+  if (h2d_ms) *h2d_ms = p->t_h2d;
+  return 0;
 }
 
 int pcu_problem_transfer_bytes(pcu_problem *prob, int64_t *h2d, int64_t *d2h) {

@@ -37,7 +37,7 @@ for name, iters in (("C2_small", 41), ("C3_small", 50)):
 from paropt_b200 import configs  # noqa: E402
 from paropt_b200.api import BuiltinProblem  # noqa: E402
 
-SWITCHES = ("PCU_NO_GRAM_TMA", "PCU_NO_RHSGRAM", "PCU_NO_FUSE21")
+SWITCHES = ("PCU_NO_GRAM_TMA", "PCU_NO_RHSGRAM", "PCU_NO_FUSE21", "PCU_NO_FUSE2S")
 
 
 def run_big(make, plain):

@@ -13,7 +13,7 @@ from tests.parity import compare_histories
 
 pytestmark = pytest.mark.gpu
 
-SWITCHES = ("PCU_NO_GRAM_TMA", "PCU_NO_RHSGRAM", "PCU_NO_FUSE21")
+SWITCHES = ("PCU_NO_GRAM_TMA", "PCU_NO_RHSGRAM", "PCU_NO_FUSE21", "PCU_NO_FUSE2S")
 
 
 @pytest.fixture(scope="module")
