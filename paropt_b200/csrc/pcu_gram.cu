@@ -518,6 +518,55 @@ static int launch_gram_tma(pcu_ctx *ctx, const ColTable &cols, int m,
 #undef PCU_GT_ARGS
 }
 
+// Wide path: one launch for up to 160 columns, no weighting correction.
+static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
+                            const double *Dinv, long long n, double *result, int ld,
+                            long long *rows_done) {
+  const int nt = (m + 7) / 8;
+  GramSegTable segs;
+  memset(&segs, 0, sizeof(segs));
+  int cnt[PCU_GW_NCW] = {0};
+  int next = 0;
+  // longest rows first so that the single-pair segments spread out
+  for (int ti = nt - 1; ti >= 0; ti--) {
+    for (int tj = 0; tj <= ti; tj += 2) {
+      const int w = next % PCU_GW_NCW;
+      next++;
+      if (cnt[w] >= PCU_GW_MAXSEG) return -1;
+      segs.ti[w][cnt[w]] = (unsigned char)ti;
+      segs.tj[w][cnt[w]] = (unsigned char)tj;
+      segs.np[w][cnt[w]] = (unsigned char)((tj + 1 <= ti) ? 2 : 1);
+      cnt[w]++;
+    }
+  }
+  int stage_bytes = (m + 2) * PCU_GW_COLB;
+  stage_bytes = (stage_bytes + 127) / 128 * 128;
+  int nstages = (208 * 1024) / stage_bytes;
+  if (nstages > PCU_GT_MAXSTAGES) nstages = PCU_GT_MAXSTAGES;
+  if (nstages < 2) return -1;
+  const long long nslabs = n / PCU_GW_ROWS;
+  *rows_done = nslabs * PCU_GW_ROWS;
+  const int smem = nstages * stage_bytes;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    PCU_CUDA_OK(cudaFuncSetAttribute(gram_wide_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  int grid = ctx->num_sms;
+  if (nslabs < grid) grid = (int)nslabs;
+  const int npairs = nt * (nt + 1) / 2;
+  if (ctx->big_reserve(0, (size_t)grid * npairs * 64)) return 1;
+  ctx->prof_begin("gram_kernel");
+  gram_wide_kernel<<<grid, 32 * (PCU_GW_NCW + 1), smem, ctx->stream>>>(
+      cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, ctx->d_big_partials,
+      ctx->d_counter, result, ld);
+  ctx->prof_end();
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // General kernel on the row range [lo, hi) (lo a multiple of 64 and of the block
 // size), added to `result`.
 static int gram_range_accumulate(pcu_ctx *ctx, const ColTable &cols, int m,
@@ -626,6 +675,27 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
       case 3: rc = launch_gram<3, 3, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
       case 4: rc = launch_gram<4, 4, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
       default: rc = launch_gram<5, 5, true>(ctx, cols, 0, 0, m, Dinv, Cw, w, n, R, ld, 0, 0, 0, 0, d2, rhs_col); break;
+    }
+  } else if (nt <= 20 && w.mode == 0 && Dinv != nullptr && n >= 32768 && rhs_col < 0 &&
+             !getenv("PCU_NO_GRAM_TMA")) {
+    // wide bulk-copy staged kernel (tile pairs dealt to the warps) on the whole
+    // 64-row slabs, 40-column block pairs of the general kernel on the tail
+    long long rows_done = 0;
+    rc = launch_gram_wide(ctx, cols, m, Dinv, n, R, ld, &rows_done);
+    if (rc) return 1;
+    if (rows_done < n) {
+      ColTable c2;
+      for (int j = 0; j < m; j++) c2.p[j] = cols.p[j] + rows_done;
+      const long long n2 = n - rows_done;
+      const int nb = (nt + 4) / 5;
+      for (int bi = 0; bi < nb && !rc; bi++) {
+        for (int bj = 0; bj <= bi && !rc; bj++) {
+          if (bi == bj)
+            rc = launch_gram<5, 5, true>(ctx, c2, 40 * bi, 40 * bi, m, Dinv + rows_done, Cw, w, n2, R, ld, 0, 0, 0, 1);
+          else
+            rc = launch_gram<5, 5, false>(ctx, c2, 40 * bi, 40 * bj, m, Dinv + rows_done, Cw, w, n2, R, ld, 0, 0, 0, 1);
+        }
+      }
     }
   } else {
     // column blocks of 40; block pairs (bi >= bj); ragged last block is masked

@@ -279,3 +279,165 @@ __global__ void __launch_bounds__(PCU_GT_THREADS(NCW), 1)
     if (threadIdx.x == 0) *counter = 0u;
   }
 }
+
+// ----------------------------------------------------------------------------
+// Wide variant (m up to 160 columns, no weighting correction): FP64-tensor-bound
+// (C4: 120 columns, 15 flop/B).  The slab is 64 rows and every consumer warp
+// reads ALL of it; the work is split over the lower-triangle TILE PAIRS instead
+// of over rows: row ti of the tile triangle is cut into segments of two pairs
+// (ti, tj0), (ti, tj0 + 1) that share the weighted A fragment, and the segments
+// are dealt round robin to the 16 consumer warps (nt = 15: 64 segments, four per
+// warp, 120 of 128 pair slots busy).  One pass over the columns replaces the
+// six 40-column block-pair launches of the register-fed path.
+#define PCU_GW_ROWS 64
+#define PCU_GW_NCW 16
+#define PCU_GW_COLB (PCU_GW_ROWS * 8 + 64)
+#define PCU_GW_MAXSEG 7   // segments per warp (nt <= 20: 110 segments)
+
+struct GramSegTable {
+  // segment s of warp w: tile row, first tile column, pairs (1 or 2; 0 = none)
+  unsigned char ti[PCU_GW_NCW][PCU_GW_MAXSEG];
+  unsigned char tj[PCU_GW_NCW][PCU_GW_MAXSEG];
+  unsigned char np[PCU_GW_NCW][PCU_GW_MAXSEG];
+};
+
+__global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
+    gram_wide_kernel(const ColTable cols, const int m, const int nt,
+                     const GramSegTable segs, const double *__restrict__ Dinv,
+                     const long long nslabs, const int nstages,
+                     const int stage_bytes, double *__restrict__ partials,
+                     unsigned int *counter, double *__restrict__ result,
+                     const int ld) {
+  extern __shared__ __align__(128) unsigned char gt_smem[];
+  __shared__ __align__(8) unsigned long long gt_full[PCU_GT_MAXSTAGES];
+  __shared__ __align__(8) unsigned long long gt_empty[PCU_GT_MAXSTAGES];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gi = lane >> 2, kk = lane & 3;
+  const int npairs_tot = nt * (nt + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; s++) {
+      gt_mbar_init(gt_smem_u32(&gt_full[s]), 1);
+      gt_mbar_init(gt_smem_u32(&gt_empty[s]), PCU_GW_NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned col_bytes = PCU_GW_ROWS * 8;
+  const int off_dinv = m * PCU_GW_COLB;
+  const int off_zero = off_dinv + PCU_GW_COLB;  // all-zero column: padding of the last tile
+  for (int i = threadIdx.x; i < nstages * (PCU_GW_ROWS * 8 / 16); i += blockDim.x) {
+    const int s = i / (PCU_GW_ROWS * 8 / 16), o = i % (PCU_GW_ROWS * 8 / 16);
+    *reinterpret_cast<double2 *>(gt_smem + (size_t)s * stage_bytes + off_zero + 16 * o) =
+        make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+
+  double acc[PCU_GW_MAXSEG][2][2];
+#pragma unroll
+  for (int s = 0; s < PCU_GW_MAXSEG; s++)
+    acc[s][0][0] = acc[s][0][1] = acc[s][1][0] = acc[s][1][1] = 0.0;
+
+  if (warp == PCU_GW_NCW) {
+    long long it = 0;
+    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
+      const int s = (int)(it % nstages);
+      const unsigned round = (unsigned)(it / nstages);
+      if (round > 0) gt_mbar_wait(gt_smem_u32(&gt_empty[s]), (round - 1) & 1);
+      const unsigned full = gt_smem_u32(&gt_full[s]);
+      if (lane == 0) gt_mbar_expect_tx(full, (unsigned)(m + 1) * col_bytes);
+      __syncwarp();
+      const unsigned base = gt_smem_u32(gt_smem + (size_t)s * stage_bytes);
+      const long long row0 = slab * PCU_GW_ROWS;
+      for (int c = lane; c <= m; c += 32) {
+        if (c < m) gt_bulk_g2s(base + c * PCU_GW_COLB, cols.p[c] + row0, col_bytes, full);
+        else gt_bulk_g2s(base + off_dinv, Dinv + row0, col_bytes, full);
+      }
+    }
+  } else {
+    // this lane's column offsets per segment (padded columns read the zero column)
+    int offA[PCU_GW_MAXSEG], offB0[PCU_GW_MAXSEG], offB1[PCU_GW_MAXSEG];
+    int npv[PCU_GW_MAXSEG];
+#pragma unroll
+    for (int s = 0; s < PCU_GW_MAXSEG; s++) {
+      npv[s] = segs.np[warp][s];
+      auto colof = [&](int t) -> int {
+        const int c = 8 * t + gi;
+        return c < m ? c * PCU_GW_COLB : off_zero;
+      };
+      offA[s] = colof(segs.ti[warp][s]);
+      offB0[s] = colof(segs.tj[warp][s]);
+      offB1[s] = colof(segs.tj[warp][s] + 1);
+    }
+    long long it = 0;
+    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
+      const int s = (int)(it % nstages);
+      const unsigned round = (unsigned)(it / nstages);
+      gt_mbar_wait(gt_smem_u32(&gt_full[s]), round & 1);
+      const unsigned char *st = gt_smem + (size_t)s * stage_bytes;
+#pragma unroll 2
+      for (int step = 0; step < PCU_GW_ROWS / 8; step++) {
+        const int ro = step * 64 + kk * 16;
+        double2 wv = *reinterpret_cast<const double2 *>(st + off_dinv + ro);
+#pragma unroll
+        for (int sg = 0; sg < PCU_GW_MAXSEG; sg++) {
+          if (npv[sg] > 0) {  // warp-uniform
+            const double2 a = *reinterpret_cast<const double2 *>(st + offA[sg] + ro);
+            const double2 b0 = *reinterpret_cast<const double2 *>(st + offB0[sg] + ro);
+            const double ax = a.x * wv.x, ay = a.y * wv.y;
+            dmma884(acc[sg][0], ax, b0.x);
+            dmma884(acc[sg][0], ay, b0.y);
+            if (npv[sg] > 1) {
+              const double2 b1 = *reinterpret_cast<const double2 *>(st + offB1[sg] + ro);
+              dmma884(acc[sg][1], ax, b1.x);
+              dmma884(acc[sg][1], ay, b1.y);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) gt_mbar_arrive(gt_smem_u32(&gt_empty[s]));
+    }
+    // every tile pair is owned by exactly one warp of the CTA
+#pragma unroll
+    for (int sg = 0; sg < PCU_GW_MAXSEG; sg++) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (q < npv[sg]) {
+          const int ti = segs.ti[warp][sg], tj = segs.tj[warp][sg] + q;
+          const int p = ti * (ti + 1) / 2 + tj;
+          double *dst = partials + ((size_t)blockIdx.x * npairs_tot + p) * 64;
+          dst[gi + 8 * (2 * kk)] = acc[sg][q][0];
+          dst[gi + 8 * (2 * kk + 1)] = acc[sg][q][1];
+        }
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int idx = threadIdx.x; idx < npairs_tot * 64; idx += blockDim.x) {
+      double v = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; b++)
+        v += partials[(size_t)b * npairs_tot * 64 + idx];
+      const int p = idx >> 6, e = idx & 63;
+      int ti = 0, q = p;
+      while (q > ti) {
+        q -= ti + 1;
+        ti++;
+      }
+      const int tj = q;
+      const int row = 8 * ti + (e & 7);
+      const int cc = 8 * tj + (e >> 3);
+      if (row < ld && cc < ld) result[(size_t)row + (size_t)ld * cc] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
