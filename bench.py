@@ -121,6 +121,7 @@ def kernel_words(name, N, W, c, q):
         "Pass2F": (12 + m) * N + 15 * W + 3 * N + 5 * W,   # the accumulating refinement solve
         "Pass2RF": (16 + m) * N + 30 * W,                   # pass 2 + refinement residual
         "Pass2R1F": (14 + m) * N + 30 * W,                  # ... + first half of the next solve
+        "Pass2SF": (16 + m) * N + 20 * W,                   # accumulating pass 2 + step statistics (g)
         "StatsF": 9 * N + 8 * W,
         "TrialF": 5 * N + 6 * W,
         "Update1F": (10 + c) * N + 15 * W,
