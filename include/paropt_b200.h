@@ -53,6 +53,11 @@ int pcu_ctx_sync(pcu_ctx *ctx); /* cudaStreamSynchronize on the ctx stream */
 void *pcu_ctx_stream(pcu_ctx *ctx); /* cudaStream_t, for callers that enqueue */
 /* Number of kernels of THIS library launched on the context since creation.  */
 int64_t pcu_ctx_kernel_launches(pcu_ctx *ctx);
+/* Launch tuning knobs (no reference counterpart; results are unchanged up to
+   summation order): "prefetch", "max_blocks_per_sm", "no_tma_tile" (1: keep
+   the fused passes on the register-fed kernel), "tma_groups", "tma_npw",
+   "tma_min_tiles", "tma_grid".  Returns 0, or 1 for an unknown name.          */
+int pcu_ctx_set_param(pcu_ctx *ctx, const char *name, int value);
 /* Per-kernel device timing: enable = 1 starts bracketing every launch of this
    library with CUDA events on the launching stream, 2 also clears the totals,
    0 stops.  profile_get returns kernel name, accumulated ms and launch count. */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "pcu_ctx_sync": (C.c_int, [VP]),
     "pcu_ctx_stream": (VP, [VP]),
     "pcu_ctx_kernel_launches": (C.c_int64, [VP]),
+    "pcu_ctx_set_param": (C.c_int, [VP, C.c_char_p, C.c_int]),
     "pcu_ctx_profile": (C.c_int, [VP, C.c_int]),
     "pcu_ctx_profile_count": (C.c_int, [VP]),
     "pcu_ctx_profile_get": (C.c_int, [VP, C.c_int, C.c_char_p, C.c_int, c_double_p,

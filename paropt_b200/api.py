@@ -65,6 +65,10 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.pcu_ctx_kernel_launches(self.h))
 
+    def set_param(self, name, value):
+        """Launch tuning knob (include/paropt_b200.h: pcu_ctx_set_param)."""
+        _check(self.lib.pcu_ctx_set_param(self.h, name.encode(), int(value)), "set_param " + name)
+
     def profile(self, enable):
         _check(self.lib.pcu_ctx_profile(self.h, int(enable)), "profile")
 

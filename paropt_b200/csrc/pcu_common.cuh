@@ -81,6 +81,40 @@ __device__ __forceinline__ void stv<2>(double *__restrict__ p, long long i,
   *reinterpret_cast<double2 *>(p + i) = make_double2(in[0], in[1]);
 }
 
+// ---------------------------------------------------------------- division
+// Branch-free fp64 quotient for the fused passes: hardware reciprocal seed
+// (2^-23), two Newton steps, one residual correction -- 9 dependent-free-to-
+// interleave instructions instead of the IEEE sequence with its slow-path
+// branch (which ends a basic block per quotient and serialises the 6-12
+// quotients of a tile).  Operands here are positive, normal and far from the
+// range ends (distances to bounds, slacks, multipliers); the result is within
+// one ulp of the correctly rounded quotient.
+#ifndef PCU_FAST_DIV
+#define PCU_FAST_DIV 1
+#endif
+__device__ __forceinline__ double pcu_rcp(double b) {
+#if PCU_FAST_DIV
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / b;
+#endif
+}
+__device__ __forceinline__ double pcu_div(double a, double b) {
+#if PCU_FAST_DIV
+  const double r = pcu_rcp(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+#else
+  return a / b;
+#endif
+}
+
 // ---------------------------------------------------------------- reductions
 template <int NS, int NX, int NM>
 struct Acc {
@@ -143,13 +177,24 @@ struct RedBuf {
 
 // Block-level + grid-level deterministic combine.  Every thread of the block
 // must call this.  Result layout: sums, then maxima, then minima.
-template <int NS, int NX, int NM, class AccT_>
-__device__ void finish_reduction(AccT_ &acc, const RedBuf &rb) {
+template <int NS, int NX, int NM, class AccT_, int MAXW = PCU_THREADS / 32>
+__device__ void finish_reduction(AccT_ &acc, const RedBuf &rb, const int tid_ = -1,
+                                 const int nthr_ = 0) {
+  // default: every thread of the block; otherwise the nthr_ threads (whole warps)
+  // whose index within the group is tid_, synchronised on named barrier 1
+  const bool part = tid_ >= 0;
+  const int tid = part ? tid_ : (int)threadIdx.x;
+  const int nthr = part ? nthr_ : (int)blockDim.x;
+#define PCU_RED_SYNC()                                              \
+  do {                                                              \
+    if (part) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); \
+    else __syncthreads();                                           \
+  } while (0)
   constexpr int NR = NS + NX + NM;
-  __shared__ double sm[PCU_THREADS / 32][NR > 0 ? NR : 1];
+  __shared__ double sm[MAXW][NR > 0 ? NR : 1];
   __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nwarps = nthr >> 5;
 #pragma unroll
   for (int i = 0; i < NS; i++) {
     double v = acc.s[i];
@@ -168,9 +213,9 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, shfl_down_d(v, o));
     if (lane == 0) sm[warp][NS + NX + i] = v;
   }
-  __syncthreads();
-  if (threadIdx.x < NR) {
-    const int i = threadIdx.x;
+  PCU_RED_SYNC();
+  if (tid < NR) {
+    const int i = tid;
     double v = sm[0][i];
     for (int w = 1; w < nwarps; w++) {
       if (i < NS) v += sm[w][i];
@@ -180,12 +225,12 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb) {
     rb.partials[(size_t)blockIdx.x * NR + i] = v;
   }
   __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  PCU_RED_SYNC();
+  if (tid == 0) {
     unsigned int t = atomicAdd(rb.counter, 1u);
     is_last = (t == gridDim.x - 1);
   }
-  __syncthreads();
+  PCU_RED_SYNC();
   if (is_last) {
     __threadfence();
     // one warp per value, lanes stride over blocks, fixed order
@@ -205,8 +250,9 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb) {
       }
       if (lane == 0) rb.result[i] = v;
     }
-    if (threadIdx.x == 0) *rb.counter = 0u;
+    if (tid == 0) *rb.counter = 0u;
   }
+#undef PCU_RED_SYNC
 }
 
 // ------------------------------------------------------- sums of logarithms
@@ -233,7 +279,45 @@ __device__ __forceinline__ double lp_value(double P, double E) {
 // slice of every stream that it will touch in its NEXT grid-stride iteration
 // (cp.async.bulk.prefetch.L2, one instruction per stream, spread over the
 // lanes): the demand loads then hit in L2 and DRAM runs one iteration ahead.
+// Where a functor's loads come from.  Functors with SRC = 1 take a source as
+// first argument of every phase and name a slot with each load: GSrc reads the
+// global arrays (register-fed tile_kernel, ragged tails), SSrc<ROWS> reads the
+// shared-memory stage the bulk-copy engine filled (tma_tile_kernel).
+struct GSrc {
+  template <int W>
+  __device__ __forceinline__ void ld(int, const double *p, long long i,
+                                     double (&out)[W]) const {
+    ldv<W>(p, i, out);
+  }
+  __device__ __forceinline__ double ldw(int, const double *p, long long ci) const {
+    return p[ci];
+  }
+};
+template <int ROWS>
+struct SSrc {
+  const unsigned char *nb;  // N-slots: [slot][ROWS] doubles
+  const unsigned char *wb;  // W-slots: [slot][wpitch bytes]
+  long long row0, con0;     // first element / first weighting constraint of the tile
+  int wpitch;
+  template <int W>
+  __device__ __forceinline__ void ld(int slot, const double *, long long i,
+                                     double (&out)[W]) const {
+    const double *q = reinterpret_cast<const double *>(nb + slot * (ROWS * 8)) + (int)(i - row0);
+    if (W == 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(q);
+      out[0] = v.x;
+      out[W - 1] = v.y;
+    } else {
+      out[0] = q[0];
+    }
+  }
+  __device__ __forceinline__ double ldw(int slot, const double *, long long ci) const {
+    return *(reinterpret_cast<const double *>(wb + slot * wpitch) + (int)(ci - con0));
+  }
+};
+
 struct NoStreams {
+  static constexpr int SRC = 0;   // 1: phases take a source (GSrc / SSrc) and slot ids
   static constexpr int NB2 = 0;   // second-round per-constraint block sums (C2 / E phases)
   static constexpr int HASP = 0;  // P(ci, con): per-constraint prologue seen by A (AP form)
   static constexpr int NF = 0;    // third round F / FG after E: E leaves con.d[FD] to broadcast
@@ -277,11 +361,11 @@ struct PrefetcherNow {  // same-iteration prefetch of the thread's own 16 bytes
 //        Con::d[ND] is then broadcast to the constraint's elements
 //   template<int W> void C(i, coef[W], Elem[W], Con, acc) const -- finishes the
 //        elements (coef = 0 and Con = zero outside weighting constraints)
-template <class F>
-__device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
+template <class F, class S, class AT>
+__device__ __forceinline__ void generic_range(const F &f, const S &src, const WDesc &w,
                                               long long lo, long long hi,
                                               long long tid, long long nthreads,
-                                              typename F::AccT &acc) {
+                                              AT &acc) {
   constexpr int NB = F::NB > 0 ? F::NB : 1;
   // (1) elements outside every weighting constraint
   for (long long i = lo + tid; i < hi; i += nthreads) {
@@ -293,16 +377,27 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       typename F::Elem e[1];
       double coef[1] = {0.0};
       double part[1][NB];
-      if constexpr (F::HASP) { typename F::Con c0; c0.zero(); f.template AP<1>(i, coef, e, part, &acc, c0); } else { f.template A<1>(i, coef, e, part, &acc); }
       typename F::Con con;
       con.zero();
+      if constexpr (F::SRC) {
+        if constexpr (F::HASP) f.template AP<1>(src, i, coef, e, part, &acc, con);
+        else f.template A<1>(src, i, coef, e, part, &acc);
+      } else {
+        if constexpr (F::HASP) f.template AP<1>(i, coef, e, part, &acc, con);
+        else f.template A<1>(i, coef, e, part, &acc);
+      }
       if constexpr (F::NB2 > 0) {
         double part2[1][F::NB2];
-        f.template C2<1>(i, coef, e, con, acc, part2);
+        if constexpr (F::SRC) f.template C2<1>(src, i, coef, e, con, acc, part2);
+        else f.template C2<1>(i, coef, e, con, acc, part2);
       } else {
-        f.template C<1>(i, coef, e, con, acc);
+        if constexpr (F::SRC) f.template C<1>(src, i, coef, e, con, acc);
+        else f.template C<1>(i, coef, e, con, acc);
       }
-      if constexpr (F::NF > 0) f.FG(i, coef[0], con, acc);
+      if constexpr (F::NF > 0) {
+        if constexpr (F::SRC) f.FG(src, i, coef[0], con, acc);
+        else f.FG(i, coef[0], con, acc);
+      }
     }
   }
   // (2) whole constraints, one thread per constraint
@@ -317,16 +412,26 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
       for (int b = 0; b < NB; b++) sum[b] = 0.0;
       typename F::Con con;
       con.zero();
-      if constexpr (F::HASP) f.P(ci, con);
+      if constexpr (F::HASP) {
+        if constexpr (F::SRC) f.P(src, ci, con);
+        else f.P(ci, con);
+      }
       for (int k = 0; k < w.nw; k++) {
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
-        if constexpr (F::HASP) { f.template AP<1>(j0 + k, coef, e, part, (typename F::AccT *)nullptr, con); } else { f.template A<1>(j0 + k, coef, e, part, (typename F::AccT *)nullptr); }
+        if constexpr (F::SRC) {
+          if constexpr (F::HASP) f.template AP<1>(src, j0 + k, coef, e, part, (AT *)nullptr, con);
+          else f.template A<1>(src, j0 + k, coef, e, part, (AT *)nullptr);
+        } else {
+          if constexpr (F::HASP) f.template AP<1>(j0 + k, coef, e, part, (AT *)nullptr, con);
+          else f.template A<1>(j0 + k, coef, e, part, (AT *)nullptr);
+        }
 #pragma unroll
         for (int b = 0; b < NB; b++) sum[b] += part[0][b];
       }
-      f.B(ci, sum, con, acc);
+      if constexpr (F::SRC) f.B(src, ci, sum, con, acc);
+      else f.B(ci, sum, con, acc);
       double sum2[F::NB2 > 0 ? F::NB2 : 1];
 #pragma unroll
       for (int b = 0; b < (F::NB2 > 0 ? F::NB2 : 1); b++) sum2[b] = 0.0;
@@ -334,36 +439,134 @@ __device__ __forceinline__ void generic_range(const F &f, const WDesc &w,
         typename F::Elem e[1];
         double coef[1] = {k == 0 ? w.coef0 : w.coef_rest};
         double part[1][NB];
-        if constexpr (F::HASP) { f.template AP<1>(j0 + k, coef, e, part, &acc, con); } else { f.template A<1>(j0 + k, coef, e, part, &acc); }
+        if constexpr (F::SRC) {
+          if constexpr (F::HASP) f.template AP<1>(src, j0 + k, coef, e, part, &acc, con);
+          else f.template A<1>(src, j0 + k, coef, e, part, &acc);
+        } else {
+          if constexpr (F::HASP) f.template AP<1>(j0 + k, coef, e, part, &acc, con);
+          else f.template A<1>(j0 + k, coef, e, part, &acc);
+        }
         if constexpr (F::NB2 > 0) {
           double part2[1][F::NB2];
-          f.template C2<1>(j0 + k, coef, e, con, acc, part2);
+          if constexpr (F::SRC) f.template C2<1>(src, j0 + k, coef, e, con, acc, part2);
+          else f.template C2<1>(j0 + k, coef, e, con, acc, part2);
 #pragma unroll
           for (int b = 0; b < F::NB2; b++) sum2[b] += part2[0][b];
         } else {
-          f.template C<1>(j0 + k, coef, e, con, acc);
+          if constexpr (F::SRC) f.template C<1>(src, j0 + k, coef, e, con, acc);
+          else f.template C<1>(j0 + k, coef, e, con, acc);
         }
       }
-      if constexpr (F::NB2 > 0) f.E(ci, sum2, con, acc);
+      if constexpr (F::NB2 > 0) {
+        if constexpr (F::SRC) f.E(src, ci, sum2, con, acc);
+        else f.E(ci, sum2, con, acc);
+      }
       if constexpr (F::NF > 0) {
-        for (int k = 0; k < w.nw; k++)
-          f.FG(j0 + k, k == 0 ? w.coef0 : w.coef_rest, con, acc);
+        for (int k = 0; k < w.nw; k++) {
+          if constexpr (F::SRC) f.FG(src, j0 + k, k == 0 ? w.coef0 : w.coef_rest, con, acc);
+          else f.FG(j0 + k, k == 0 ? w.coef0 : w.coef_rest, con, acc);
+        }
       }
     }
+  }
+}
+
+// One element pair (i, i+1) per lane, a full warp at a time: the shuffle path of
+// the aligned power-of-two weighting blocks (w.mode == 1) or no blocks (mode 0).
+template <class F, class S, class AT>
+__device__ __forceinline__ void tile_pair(const F &f, const S &src, const WDesc &w,
+                                          const long long i, const long long ncon_elems,
+                                          const int half, AT &acc) {
+  constexpr int NB = F::NB > 0 ? F::NB : 1;
+  typename F::Elem e[2];
+  double coef[2] = {0.0, 0.0};
+  double part[2][NB];
+  const bool in_con = i < ncon_elems;
+  if (in_con) {
+    const int k = (int)(i & (long long)(w.nw - 1));
+    coef[0] = (k == 0) ? w.coef0 : w.coef_rest;
+    coef[1] = w.coef_rest;
+  }
+  typename F::Con con;
+  con.zero();
+  if constexpr (F::SRC) {
+    if constexpr (F::HASP) {
+      if (in_con) f.P(src, i / w.nw, con);
+      f.template AP<2>(src, i, coef, e, part, &acc, con);
+    } else {
+      f.template A<2>(src, i, coef, e, part, &acc);
+    }
+  } else {
+    if constexpr (F::HASP) {
+      if (in_con) f.P(i / w.nw, con);
+      f.template AP<2>(i, coef, e, part, &acc, con);
+    } else {
+      f.template A<2>(i, coef, e, part, &acc);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  const int lead = lane & ~(half - 1);
+  if (w.mode == 1) {
+    double sum[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) sum[b] = in_con ? part[0][b] + part[1][b] : 0.0;
+    if (F::NB > 0) {
+      for (int o = 1; o < half; o <<= 1) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) sum[b] += shfl_xor_d(sum[b], o);
+      }
+    }
+    if (in_con && lane == lead) {
+      if constexpr (F::SRC) f.B(src, i / w.nw, sum, con, acc);
+      else f.B(i / w.nw, sum, con, acc);
+    }
+    if (F::Con::ND > 0) {
+#pragma unroll
+      for (int b = 0; b < (F::Con::ND > 0 ? F::Con::ND : 1); b++)
+        con.d[b] = __shfl_sync(0xffffffffu, con.d[b], lead);
+    }
+  }
+  if constexpr (F::NB2 > 0) {
+    double part2[2][F::NB2];
+    if constexpr (F::SRC) f.template C2<2>(src, i, coef, e, con, acc, part2);
+    else f.template C2<2>(i, coef, e, con, acc, part2);
+    if (w.mode == 1) {
+      double sum2[F::NB2];
+#pragma unroll
+      for (int b = 0; b < F::NB2; b++)
+        sum2[b] = in_con ? part2[0][b] + part2[1][b] : 0.0;
+      for (int o = 1; o < half; o <<= 1) {
+#pragma unroll
+        for (int b = 0; b < F::NB2; b++) sum2[b] += shfl_xor_d(sum2[b], o);
+      }
+      if (in_con && lane == lead) {
+        if constexpr (F::SRC) f.E(src, i / w.nw, sum2, con, acc);
+        else f.E(i / w.nw, sum2, con, acc);
+      }
+      if constexpr (F::NF > 0)
+        con.d[F::FD] = __shfl_sync(0xffffffffu, con.d[F::FD], lead);
+    }
+    if constexpr (F::NF > 0) {
+      if constexpr (F::SRC) f.template F<2>(src, i, coef, e, con, acc);
+      else f.template F<2>(i, coef, e, con, acc);
+    }
+  } else {
+    if constexpr (F::SRC) f.template C<2>(src, i, coef, e, con, acc);
+    else f.template C<2>(i, coef, e, con, acc);
   }
 }
 
 template <class F>
 __global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
     tile_kernel(const F f, const long long n, const WDesc w, const RedBuf rb) {
-  constexpr int NB = F::NB > 0 ? F::NB : 1;
   typename F::AccT acc;
   acc.init();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const GSrc src;
 
   if (w.mode == 2) {
-    generic_range(f, w, 0, n, tid, nthreads, acc);
+    generic_range(f, src, w, 0, n, tid, nthreads, acc);
   } else {
     // 128-bit path over full warps of element pairs; the ragged tail (< 64
     // elements + whole constraints) goes through the generic path.
@@ -384,75 +587,243 @@ __global__ void __launch_bounds__(PCU_TILE_THREADS, F::MINB)
         pf.idx = 0;
         f.streams(pf);
       }
-      typename F::Elem e[2];
-      double coef[2] = {0.0, 0.0};
-      double part[2][NB];
-      const bool in_con = i < ncon_elems;
-      if (in_con) {
-        const int k = (int)(i & (long long)(w.nw - 1));
-        coef[0] = (k == 0) ? w.coef0 : w.coef_rest;
-        coef[1] = w.coef_rest;
-      }
-      typename F::Con con;
-      con.zero();
-      if constexpr (F::HASP) {
-        if (in_con) f.P(i / w.nw, con);
-        f.template AP<2>(i, coef, e, part, &acc, con);
-      } else {
-        f.template A<2>(i, coef, e, part, &acc);
-      }
-      if (w.mode == 1) {
-        double sum[NB];
-#pragma unroll
-        for (int b = 0; b < NB; b++) sum[b] = in_con ? part[0][b] + part[1][b] : 0.0;
-        if (F::NB > 0) {
-          for (int o = 1; o < half; o <<= 1) {
-#pragma unroll
-            for (int b = 0; b < NB; b++) sum[b] += shfl_xor_d(sum[b], o);
-          }
-        }
-        const int lane = threadIdx.x & 31;
-        const int lead = lane & ~(half - 1);
-        if (in_con && lane == lead) f.B(i / w.nw, sum, con, acc);
-        if (F::Con::ND > 0) {
-#pragma unroll
-          for (int b = 0; b < (F::Con::ND > 0 ? F::Con::ND : 1); b++)
-            con.d[b] = __shfl_sync(0xffffffffu, con.d[b], lead);
-        }
-      }
-      if constexpr (F::NB2 > 0) {
-        double part2[2][F::NB2];
-        f.template C2<2>(i, coef, e, con, acc, part2);
-        if (w.mode == 1) {
-          double sum2[F::NB2];
-#pragma unroll
-          for (int b = 0; b < F::NB2; b++)
-            sum2[b] = in_con ? part2[0][b] + part2[1][b] : 0.0;
-          for (int o = 1; o < half; o <<= 1) {
-#pragma unroll
-            for (int b = 0; b < F::NB2; b++) sum2[b] += shfl_xor_d(sum2[b], o);
-          }
-          const int lane = threadIdx.x & 31;
-          const int lead = lane & ~(half - 1);
-          if (in_con && lane == lead) f.E(i / w.nw, sum2, con, acc);
-          if constexpr (F::NF > 0)
-            con.d[F::FD] = __shfl_sync(0xffffffffu, con.d[F::FD], lead);
-        }
-        if constexpr (F::NF > 0) f.template F<2>(i, coef, e, con, acc);
-      } else {
-        f.template C<2>(i, coef, e, con, acc);
-      }
+      tile_pair(f, src, w, i, ncon_elems, half, acc);
     }
     const long long tail_lo = 2 * nvec_main;
     if (tail_lo < n && blockIdx.x == 0) {
       WDesc wt = w;
       if (w.mode == 0) wt.nwcon = 0;
-      generic_range(f, wt, tail_lo, n, threadIdx.x, blockDim.x, acc);
+      generic_range(f, src, wt, tail_lo, n, (long long)threadIdx.x, (long long)blockDim.x, acc);
     }
   }
   if (F::NS + F::NX + F::NM > 0) {
     f.finalize(acc);
     finish_reduction<F::NS, F::NX, F::NM>(acc, rb);
+  }
+}
+
+// ------------------------------------------------- bulk-copy staged harness
+// The register-fed tile_kernel keeps (threads x loads in flight) bytes moving,
+// and the fused KKT passes (35-45 streams, 70-100 registers) sit at 5.2-5.7 TB/s
+// where a plain many-stream copy reaches 7 TB/s (profiles/r1b_stream_probe.txt).
+// Here the copy engine does the streaming: NPW producer warps issue one
+// cp.async.bulk per stream per tile (ROWS rows; the copies are dealt over the
+// producer warps because one warp instruction serialises its lanes' copies)
+// into a ring of shared-memory stages; consumer group g = (ROWS / 64 warps)
+// owns the stages s with s % G == g and runs the functor's phases on them from
+// shared memory (SSrc), storing results straight to global memory.  Bytes in
+// flight = the ring, independent of registers; one CTA per SM, tiles dealt
+// round robin.  Stages are complete/empty mbarrier pairs.
+//   * W-streams (per weighting constraint) are staged for tiles that lie
+//     entirely inside the blocks; the (at most one) straddling tile and the
+//     ragged tail run through the global path on block 0 / the last block.
+struct TmaPlan {
+  long long ntiles;     // full tiles of ROWS rows
+  long long tiles_con;  // tiles [0, tiles_con) lie inside the weighting blocks
+  long long tile_skip;  // the straddling tile, or -1
+  int groups;           // consumer groups (each ROWS / 64 warps)
+  int nstages;          // multiple of groups, <= 16
+  int stage_bytes;
+  int woff;             // byte offset of the W-slots inside a stage
+  int wpitch;           // bytes per W-slot
+  int npw;              // producer warps
+};
+
+#define PCU_TMA_NPW 4        // producer warps = warpgroup 0 (the first plan.npw of them issue copies)
+#define PCU_TMA_PROD_REGS 24   // setmaxnreg: producers keep 24 registers ...
+#define PCU_TMA_CONS_REGS 160  // ... the 12 consumer warps get 160 (launch: 128 each)
+#define PCU_TMA_MAXWARPS 16  // 4 producer + 12 consumer warps per CTA (one CTA per SM)
+#define PCU_TMA_MAXSTAGES 16
+
+__device__ __forceinline__ unsigned tt_smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void tt_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tt_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tt_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tt_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TT_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TT_DONE_%=;\n"
+      "bra TT_WAIT_%=;\n"
+      "TT_DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tt_bulk_g2s(unsigned dst, const void *src,
+                                            unsigned bytes, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], "
+      "%2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// Deals the functor's streams (tstreams order) over the producer threads:
+// copy c goes to producer warp c % NPW, lane (c / NPW) % 32, at most two per thread.
+template <int ROWS>
+struct TmaAssign {
+  int me_warp, me_lane, c, npw;
+  int cnt;
+  const double *p0, *p1;
+  unsigned off0, off1;  // byte offset inside the stage
+  int w0, w1;           // 1: W-stream
+  int woff, wpitch;
+  __host__ __device__ __forceinline__ void take(const double *ptr, unsigned off, int isw) {
+    if (ptr == nullptr) return;
+    const int cc = c++;
+    if (cc % npw != me_warp || (cc / npw) % 32 != me_lane) return;
+    if (cnt == 0) {
+      p0 = ptr; off0 = off; w0 = isw;
+    } else {
+      p1 = ptr; off1 = off; w1 = isw;
+    }
+    cnt++;
+  }
+  __host__ __device__ __forceinline__ void n(int slot, const double *ptr) {
+    take(ptr, (unsigned)slot * (ROWS * 8), 0);
+  }
+  __host__ __device__ __forceinline__ void w(int slot, const double *ptr) {
+    take(ptr, (unsigned)(woff + slot * wpitch), 1);
+  }
+};
+
+template <class F, int ROWS>
+__global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
+    tma_tile_kernel(const F f, const long long n, const WDesc w, const RedBuf rb,
+                    const TmaPlan plan) {
+  constexpr int WPT = ROWS / 64;  // consumer warps per tile
+  constexpr int NCWMAX = PCU_TMA_MAXWARPS - PCU_TMA_NPW;
+  extern __shared__ double2 pcu_dyn_smem[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(pcu_dyn_smem);
+  __shared__ __align__(8) unsigned long long tt_full[PCU_TMA_MAXSTAGES];
+  __shared__ __align__(8) unsigned long long tt_empty[PCU_TMA_MAXSTAGES];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = plan.nstages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) {
+      tt_mbar_init(tt_smem_u32(&tt_full[s]), plan.npw);
+      tt_mbar_init(tt_smem_u32(&tt_empty[s]), WPT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long ncon_elems = (w.mode == 1) ? (long long)w.nwcon * w.nw : 0;
+  const int half = (w.mode == 1) ? (w.nw >> 1) : 1;
+  const int con_per_tile = (w.mode == 1) ? ROWS / w.nw : 0;
+
+  if (warp < PCU_TMA_NPW) {
+    // ------------------------------------------------- producers (warpgroup 0)
+    // hand most of this warpgroup's registers to the consumers
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PCU_TMA_PROD_REGS));
+    if (warp >= plan.npw) return;
+    TmaAssign<ROWS> as;
+    as.me_warp = warp;
+    as.me_lane = lane;
+    as.npw = plan.npw;
+    as.c = 0;
+    as.cnt = 0;
+    as.p0 = as.p1 = nullptr;
+    as.off0 = as.off1 = 0;
+    as.w0 = as.w1 = 0;
+    as.woff = plan.woff;
+    as.wpitch = plan.wpitch;
+    f.tstreams(as);
+    const unsigned nbytes = ROWS * 8, wbytes = (unsigned)con_per_tile * 8;
+    unsigned tx_n = 0, tx_w = 0;
+    if (as.cnt > 0) { if (as.w0) tx_w += wbytes; else tx_n += nbytes; }
+    if (as.cnt > 1) { if (as.w1) tx_w += wbytes; else tx_n += nbytes; }
+    for (int o = 16; o > 0; o >>= 1) {
+      tx_n += __shfl_xor_sync(0xffffffffu, tx_n, o);
+      tx_w += __shfl_xor_sync(0xffffffffu, tx_w, o);
+    }
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < plan.ntiles; tile += gridDim.x) {
+      if (tile == plan.tile_skip) continue;
+      const int s = (int)(it % S);
+      const unsigned round = (unsigned)(it / S);
+      if (round > 0) tt_mbar_wait(tt_smem_u32(&tt_empty[s]), (round - 1) & 1);
+      const bool in_con = tile < plan.tiles_con;
+      const unsigned full = tt_smem_u32(&tt_full[s]);
+      if (lane == 0) tt_mbar_expect_tx(full, tx_n + (in_con ? tx_w : 0u));
+      __syncwarp();
+      const unsigned base = tt_smem_u32(smem + (size_t)s * plan.stage_bytes);
+      if (as.cnt > 0) {
+        if (!as.w0) tt_bulk_g2s(base + as.off0, as.p0 + tile * ROWS, nbytes, full);
+        else if (in_con) tt_bulk_g2s(base + as.off0, as.p0 + tile * con_per_tile, wbytes, full);
+      }
+      if (as.cnt > 1) {
+        if (!as.w1) tt_bulk_g2s(base + as.off1, as.p1 + tile * ROWS, nbytes, full);
+        else if (in_con) tt_bulk_g2s(base + as.off1, as.p1 + tile * con_per_tile, wbytes, full);
+      }
+      it++;
+    }
+    return;
+  }
+  // ------------------------------------------------- consumers (warpgroups 1..3)
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PCU_TMA_CONS_REGS));
+  typedef Acc<F::NS, F::NX, F::NM> AT;
+  AT acc;
+  acc.init();
+  const int cw = warp - PCU_TMA_NPW;   // consumer warp index
+  const int ncw = plan.groups * WPT;   // consumer warps with a group
+  if (cw < ncw) {
+    const int g = cw / WPT, wg = cw % WPT;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < plan.ntiles; tile += gridDim.x) {
+      if (tile == plan.tile_skip) continue;
+      const long long my = it++;
+      if ((int)(my % plan.groups) != g) continue;
+      const int s = (int)(my % S);
+      tt_mbar_wait(tt_smem_u32(&tt_full[s]), (unsigned)(my / S) & 1);
+      SSrc<ROWS> src;
+      src.nb = smem + (size_t)s * plan.stage_bytes;
+      src.wb = src.nb + plan.woff;
+      src.row0 = tile * ROWS;
+      src.con0 = tile * con_per_tile;
+      src.wpitch = plan.wpitch;
+      tile_pair(f, src, w, src.row0 + wg * 64 + 2 * lane, ncon_elems, half, acc);
+      __syncwarp();
+      if (lane == 0) tt_mbar_arrive(tt_smem_u32(&tt_empty[s]));
+    }
+    // what the staged loop left out, through the global path
+    const GSrc gsrc;
+    if (plan.tile_skip >= 0 && blockIdx.x == gridDim.x - 1) {
+      for (int v = cw * 32 + lane; v < ROWS / 2; v += ncw * 32)
+        tile_pair(f, gsrc, w, plan.tile_skip * ROWS + 2 * v, ncon_elems, half, acc);
+    }
+    if (blockIdx.x == 0) {
+      const long long nvec_main = ((n / 2) / 32) * 32;
+      for (long long v = plan.ntiles * (ROWS / 2) + cw * 32 + lane; v < nvec_main;
+           v += ncw * 32)
+        tile_pair(f, gsrc, w, 2 * v, ncon_elems, half, acc);
+      const long long tail_lo = 2 * nvec_main;
+      if (tail_lo < n) {
+        WDesc wt = w;
+        if (w.mode == 0) wt.nwcon = 0;
+        generic_range(f, gsrc, wt, tail_lo, n, (long long)(cw * 32 + lane),
+                      (long long)(ncw * 32), acc);
+      }
+    }
+  }
+  if (F::NS + F::NX + F::NM > 0) {
+    f.finalize(acc);
+    finish_reduction<F::NS, F::NX, F::NM, AT, NCWMAX>(acc, rb, (int)threadIdx.x - PCU_TMA_NPW * 32,
+                                                       NCWMAX * 32);
   }
 }
 

@@ -40,6 +40,11 @@ struct pcu_ctx {
   int num_sms = 148;
   int max_blocks_per_sm = 16;  // occupancy cap of the streaming kernels
   int prefetch = -1;           // -1: same-iteration L2 prefetch; k > 0: k iterations ahead; 0 off
+  int no_tma_tile = 0;         // PCU_NO_TMA_TILE: keep the SRC functors on the register-fed kernel
+  int tma_groups = 0;          // PCU_TMA_GROUPS: cap on the consumer groups of tma_tile_kernel
+  int tma_npw = 0;             // PCU_TMA_NPW: producer warps of tma_tile_kernel (default 2)
+  int tma_min_tiles = 0;       // staged launch only from this many tiles (default 8 per SM)
+  int tma_grid = 0;            // CTAs of the staged launch (default: one per SM)
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -103,9 +108,86 @@ static inline int pcu_grid_for(const pcu_ctx *ctx, long long n) {
   return (int)need;
 }
 
+// Host-side visit of a functor's staged streams: slot count and alignment.
+struct TmaHostCheck {
+  int copies = 0;
+  bool aligned = true;
+  __host__ __device__ void n(int, const double *ptr) {
+    if (!ptr) return;
+    copies++;
+    if (((uintptr_t)ptr) & 15) aligned = false;
+  }
+  __host__ __device__ void w(int, const double *ptr) { n(0, ptr); }
+};
+
+#define PCU_TMA_ROWS 128
+#define PCU_TMA_SMEM_BUDGET (214 * 1024)
+
+// Bulk-copy staged launch of a SRC functor (tma_tile_kernel); returns -1 when
+// the launch does not qualify (small n, generic weighting pattern, too many
+// streams for the shared-memory ring) and the register-fed kernel must run.
+template <class F>
+int pcu_launch_tile_tma(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
+                        RedBuf rb) {
+  constexpr int ROWS = PCU_TMA_ROWS, WPT = ROWS / 64;
+  if (ctx->no_tma_tile || w.mode == 2) return -1;
+  if (w.mode == 1 && (w.nw < 2 || w.nw > 64 || (w.nw & (w.nw - 1)) || w.wstart != 0 ||
+                      w.wstride != w.nw))
+    return -1;
+  TmaPlan plan;
+  plan.ntiles = n / ROWS;
+  if (plan.ntiles < (ctx->tma_min_tiles > 0 ? (long long)ctx->tma_min_tiles
+                                            : (long long)ctx->num_sms * 8))
+    return -1;
+  TmaHostCheck chk;
+  f.tstreams(chk);
+  int npw = ctx->tma_npw > 0 ? ctx->tma_npw : 4;
+  if (npw > PCU_TMA_NPW) npw = PCU_TMA_NPW;
+  plan.npw = npw;
+  if (!chk.aligned || chk.copies > 64 * npw) return -1;
+  const int nslots = f.nslots();
+  const int con_per_tile = w.mode == 1 ? ROWS / w.nw : 0;
+  plan.wpitch = (con_per_tile * 8 + 15) / 16 * 16;
+  plan.woff = nslots * ROWS * 8;
+  plan.stage_bytes = (plan.woff + (w.mode == 1 ? F::NWSLOTS * plan.wpitch : 0) + 127) / 128 * 128;
+  const int fit = PCU_TMA_SMEM_BUDGET / plan.stage_bytes;
+  int groups = (PCU_TMA_MAXWARPS - PCU_TMA_NPW) / WPT;
+  if (ctx->tma_groups > 0 && ctx->tma_groups < groups) groups = ctx->tma_groups;
+  if (fit < groups) groups = fit;
+  if (groups < 2) return -1;
+  int depth = fit / groups;
+  if (depth > PCU_TMA_MAXSTAGES / groups) depth = PCU_TMA_MAXSTAGES / groups;
+  plan.groups = groups;
+  plan.nstages = groups * depth;
+  const long long ncon_elems = w.mode == 1 ? (long long)w.nwcon * w.nw : 0;
+  plan.tiles_con = ncon_elems / ROWS;
+  if (plan.tiles_con > plan.ntiles) plan.tiles_con = plan.ntiles;
+  plan.tile_skip = (ncon_elems % ROWS != 0 && plan.tiles_con < plan.ntiles) ? plan.tiles_con : -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCU_CUDA_OK(cudaFuncSetAttribute(tma_tile_kernel<F, ROWS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     PCU_TMA_SMEM_BUDGET));
+    attr_set = true;
+  }
+  const int threads = PCU_TMA_MAXWARPS * 32;
+  const size_t smem = (size_t)plan.nstages * plan.stage_bytes;
+  ctx->prof_begin(pcu_kernel_name<F>());
+  const int grid = ctx->tma_grid > 0 && ctx->tma_grid < ctx->num_sms ? ctx->tma_grid : ctx->num_sms;
+  tma_tile_kernel<F, ROWS><<<grid, threads, smem, ctx->stream>>>(f, n, w, rb, plan);
+  ctx->prof_end();
+  ctx->launches++;
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <class F>
 int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
                     RedBuf rb) {
+  if constexpr (F::SRC) {
+    const int r = pcu_launch_tile_tma(ctx, f, n, w, rb);
+    if (r >= 0) return r;
+  }
   // persistent grid: exactly as many blocks as can be co-resident
   static int blocks_per_sm = -1;
   if (blocks_per_sm < 0) {

@@ -730,7 +730,7 @@ __device__ __forceinline__ void stats_elements(
       if (ml && mu_) {
         const double prod = dl * du;
         fac *= prod;
-        const double rinv = 1.0 / prod;
+        const double rinv = pcu_rcp(prod);
         const double rl = pxq * du * rinv, ru = pxq * dl * rinv;
         if (pxq > 0.0) {
           a.s[10] += rl;
@@ -742,12 +742,12 @@ __device__ __forceinline__ void stats_elements(
       } else {
         if (ml) {
           fac *= dl;
-          const double r = pxq / dl;
+          const double r = pcu_div(pxq, dl);
           if (pxq > 0.0) a.s[10] += r; else a.s[11] += r;
         }
         if (mu_) {
           fac *= du;
-          const double r = pxq / du;
+          const double r = pcu_div(pxq, du);
           if (pxq > 0.0) a.s[11] -= r; else a.s[10] -= r;
         }
       }
@@ -758,14 +758,10 @@ __device__ __forceinline__ void stats_elements(
     lp_mul(a.s[8], a.s[9], fac);
 }
 template <class AccT_>
-__device__ __forceinline__ void stats_constraint(const IPConst &k, double tau,
-                                                 long long ci, const DVars &v,
-                                                 const DVars &p,
-                                                 const double (&sum)[2],
-                                                 AccT_ &acc) {
-    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double psw = p.sw[ci], ptw = p.tw[ci], pzsw = p.zsw[ci],
-                 pztw = p.ztw[ci];
+__device__ __forceinline__ void stats_constraint_vals(
+    const IPConst &k, double tau, long long ci, double sw, double tw, double zsw,
+    double ztw, double psw, double ptw, double pzsw, double pztw,
+    const double (&sum)[2], AccT_ &acc) {
     if (psw < 0.0) acc.m[0] = fmin(acc.m[0], -tau * sw / psw);
     if (ptw < 0.0) acc.m[0] = fmin(acc.m[0], -tau * tw / ptw);
     if (pzsw < 0.0) acc.m[1] = fmin(acc.m[1], -tau * zsw / pzsw);
@@ -776,7 +772,7 @@ __device__ __forceinline__ void stats_constraint(const IPConst &k, double tau,
     acc.s[7] += psw * pzsw + ptw * pztw;
     const double swtw = sw * tw;
     lp_mul(acc.s[12], acc.s[13], swtw);
-    const double rinv = 1.0 / swtw;
+    const double rinv = pcu_rcp(swtw);
     const double rs = psw * tw * rinv, rt = ptw * sw * rinv;
     if (psw > 0.0) acc.s[14] += rs; else acc.s[15] += rs;
     if (ptw > 0.0) acc.s[14] += rt; else acc.s[15] += rt;
@@ -787,6 +783,15 @@ __device__ __forceinline__ void stats_constraint(const IPConst &k, double tau,
     const double rw2 = (sum[1] - psw) + ptw;
     acc.s[20] = fma(rw1, rw1, acc.s[20]);
     acc.s[21] = fma(rw1, rw2, acc.s[21]);
+}
+template <class AccT_>
+__device__ __forceinline__ void stats_constraint(const IPConst &k, double tau,
+                                                 long long ci, const DVars &v,
+                                                 const DVars &p,
+                                                 const double (&sum)[2],
+                                                 AccT_ &acc) {
+    stats_constraint_vals(k, tau, ci, v.sw[ci], v.tw[ci], v.zsw[ci], v.ztw[ci], p.sw[ci],
+                          p.tw[ci], p.zsw[ci], p.ztw[ci], sum, acc);
 }
 
 // ============================================================== StatsF
@@ -871,15 +876,26 @@ struct StatsF : NoStreams {
 // step statistics are taken from the step while it is still in registers, so
 // the separate 9N + 8W statistics pass disappears (one extra stream: g).
 // Traffic: Pass2F + N.   Reductions: as StatsF (sums in shared memory).
+struct ConP2S {  // yw broadcast; the leader lane keeps the constraint's values for E
+  static constexpr int ND = 1;
+  double d[1];
+  double sw, tw, zsw, ztw, psw, ptw, pzsw, pztw;
+  __device__ __forceinline__ void zero() { d[0] = 0.0; }
+};
 struct Pass2SF : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int MINB = PCU_MINB_PASS2S;
   static constexpr int NS = 22, NX = 1, NM = 2, NB = 1, NB2 = 2;
   static constexpr int SMEM = NS * PCU_TILE_THREADS * 8;
   typedef AccS<NS, NX, NM> AccT;
-  typedef Con1 Con;  // yw
+  typedef ConP2S Con;
   struct Elem {
     double d1, dinv;
   };
+  // staged slots (tma_tile_kernel): N-streams, then the columns; W-streams
+  enum { S_D1, S_DINV, S_X, S_LB, S_UB, S_G, S_ZL, S_BZL, S_ZU, S_BZU, S_YX, S_YZL, S_YZU, S_V0 };
+  enum { W_CW, W_D2, W_SW, W_TW, W_ZSW, W_ZTW, W_BSW, W_BTW, W_BZSW, W_BZTW,
+         W_YZW, W_YZSW, W_YZTW, W_YSW, W_YTW, NWSLOTS };
   DVars v, b, y;
   const double *lb, *ub, *Dinv, *Cw, *d1, *d2, *g;
   ColTable V;
@@ -901,16 +917,37 @@ struct Pass2SF : NoStreams {
       if (k.use_upper) p_(y.zu);
     }
   }
+  int nslots() const { return S_V0 + ncols; }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_D1, d1); p_.n(S_DINV, Dinv); p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
+    p_.n(S_G, g);
+    if (k.use_lower) { p_.n(S_ZL, v.zl); p_.n(S_BZL, b.zl); }
+    if (k.use_upper) { p_.n(S_ZU, v.zu); p_.n(S_BZU, b.zu); }
+    if (accumulate) {
+      p_.n(S_YX, y.x);
+      if (k.use_lower) p_.n(S_YZL, y.zl);
+      if (k.use_upper) p_.n(S_YZU, y.zu);
+    }
+    for (int j = 0; j < ncols; j++) p_.n(S_V0 + j, V.p[j]);
+    p_.w(W_CW, Cw); p_.w(W_D2, d2);
+    p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_ZSW, v.zsw); p_.w(W_ZTW, v.ztw);
+    p_.w(W_BSW, b.sw); p_.w(W_BTW, b.tw); p_.w(W_BZSW, b.zsw); p_.w(W_BZTW, b.ztw);
+    if (accumulate) {
+      p_.w(W_YZW, y.zw); p_.w(W_YZSW, y.zsw); p_.w(W_YZTW, y.ztw);
+      p_.w(W_YSW, y.sw); p_.w(W_YTW, y.tw);
+    }
+  }
 
-  template <int W>
-  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][1], AccT *) const {
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1], AT *) const {
     double d[W], di[W];
-    ldv<W>(d1, i, d);
-    ldv<W>(Dinv, i, di);
+    src.template ld<W>(S_D1, d1, i, d);
+    src.template ld<W>(S_DINV, Dinv, i, di);
     for (int j = 0; j < ncols; j++) {
       double c[W];
-      ldv<W>(V.p[j], i, c);
+      src.template ld<W>(S_V0 + j, V.p[j], i, c);
 #pragma unroll
       for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j], c[q], d[q]);
     }
@@ -921,48 +958,52 @@ struct Pass2SF : NoStreams {
       part[q][0] = coef[q] * di[q] * d[q];
     }
   }
-  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
-                                    Con &con, AccT &) const {
-    const double yw = Cw[ci] * (d2[ci] - sum[0]);
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&sum)[1],
+                                    Con &con, AT &) const {
+    const double yw = src.ldw(W_CW, Cw, ci) * (src.ldw(W_D2, d2, ci) - sum[0]);
     con.d[0] = yw;
-    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double pzsw = yw - b.sw[ci];
-    const double pztw = -b.tw[ci] - yw;
-    const double psw = (b.zsw[ci] - sw * pzsw) / zsw;
-    const double ptw = (b.ztw[ci] - tw * pztw) / ztw;
+    const double sw = src.ldw(W_SW, v.sw, ci), tw = src.ldw(W_TW, v.tw, ci);
+    const double zsw = src.ldw(W_ZSW, v.zsw, ci), ztw = src.ldw(W_ZTW, v.ztw, ci);
+    double pzsw = yw - src.ldw(W_BSW, b.sw, ci);
+    double pztw = -src.ldw(W_BTW, b.tw, ci) - yw;
+    double psw = pcu_div(src.ldw(W_BZSW, b.zsw, ci) - sw * pzsw, zsw);
+    double ptw = pcu_div(src.ldw(W_BZTW, b.ztw, ci) - tw * pztw, ztw);
+    double pzw = yw;
     if (accumulate) {
-      y.zw[ci] += yw;
-      y.zsw[ci] += pzsw;
-      y.ztw[ci] += pztw;
-      y.sw[ci] += psw;
-      y.tw[ci] += ptw;
-    } else {
-      y.zw[ci] = yw;
-      y.zsw[ci] = pzsw;
-      y.ztw[ci] = pztw;
-      y.sw[ci] = psw;
-      y.tw[ci] = ptw;
+      pzw = src.ldw(W_YZW, y.zw, ci) + yw;
+      pzsw = src.ldw(W_YZSW, y.zsw, ci) + pzsw;
+      pztw = src.ldw(W_YZTW, y.ztw, ci) + pztw;
+      psw = src.ldw(W_YSW, y.sw, ci) + psw;
+      ptw = src.ldw(W_YTW, y.tw, ci) + ptw;
     }
+    y.zw[ci] = pzw;
+    y.zsw[ci] = pzsw;
+    y.ztw[ci] = pztw;
+    y.sw[ci] = psw;
+    y.tw[ci] = ptw;
+    con.sw = sw; con.tw = tw; con.zsw = zsw; con.ztw = ztw;
+    con.psw = psw; con.ptw = ptw; con.pzsw = pzsw; con.pztw = pztw;
   }
-  template <int W>
-  __device__ __forceinline__ void C2(long long i, const double (&coef)[W],
-                                     const Elem (&e)[W], const Con &con, AccT &acc,
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C2(const S &src, long long i, const double (&coef)[W],
+                                     const Elem (&e)[W], const Con &con, AT &acc,
                                      double (&part2)[W][2]) const {
     double x[W], l[W], u[W], zl[W], zu[W], bzl[W], bzu[W], gv[W];
     double px[W], pzl[W], pzu[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(g, i, gv);
+    src.template ld<W>(S_X, v.x, i, x);
+    src.template ld<W>(S_LB, lb, i, l);
+    src.template ld<W>(S_UB, ub, i, u);
+    src.template ld<W>(S_G, g, i, gv);
 #pragma unroll
     for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
     if (k.use_lower) {
-      ldv<W>(v.zl, i, zl);
-      ldv<W>(b.zl, i, bzl);
+      src.template ld<W>(S_ZL, v.zl, i, zl);
+      src.template ld<W>(S_BZL, b.zl, i, bzl);
     }
     if (k.use_upper) {
-      ldv<W>(v.zu, i, zu);
-      ldv<W>(b.zu, i, bzu);
+      src.template ld<W>(S_ZU, v.zu, i, zu);
+      src.template ld<W>(S_BZU, b.zu, i, bzu);
     }
 #pragma unroll
     for (int q = 0; q < W; q++) {
@@ -970,22 +1011,22 @@ struct Pass2SF : NoStreams {
       pzl[q] = 0.0;
       pzu[q] = 0.0;
       if (k.use_lower && l[q] > -k.mbv)
-        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+        pzl[q] = pcu_div(bzl[q] - zl[q] * px[q], x[q] - l[q]);
       if (k.use_upper && u[q] < k.mbv)
-        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+        pzu[q] = pcu_div(bzu[q] + zu[q] * px[q], u[q] - x[q]);
     }
     if (accumulate) {
       double o[W];
-      ldv<W>(y.x, i, o);
+      src.template ld<W>(S_YX, y.x, i, o);
 #pragma unroll
       for (int q = 0; q < W; q++) px[q] += o[q];
       if (k.use_lower) {
-        ldv<W>(y.zl, i, o);
+        src.template ld<W>(S_YZL, y.zl, i, o);
 #pragma unroll
         for (int q = 0; q < W; q++) pzl[q] += o[q];
       }
       if (k.use_upper) {
-        ldv<W>(y.zu, i, o);
+        src.template ld<W>(S_YZU, y.zu, i, o);
 #pragma unroll
         for (int q = 0; q < W; q++) pzu[q] += o[q];
       }
@@ -1000,11 +1041,14 @@ struct Pass2SF : NoStreams {
       part2[q][1] = coef[q] * px[q];
     }
   }
-  __device__ __forceinline__ void E(long long ci, const double (&sum2)[2],
-                                    const Con &, AccT &acc) const {
-    stats_constraint(k, tau, ci, v, y, sum2, acc);
+  template <class S, class AT>
+  __device__ __forceinline__ void E(const S &, long long ci, const double (&sum2)[2],
+                                    const Con &con, AT &acc) const {
+    stats_constraint_vals(k, tau, ci, con.sw, con.tw, con.zsw, con.ztw, con.psw, con.ptw,
+                          con.pzsw, con.pztw, sum2, acc);
   }
-  __device__ __forceinline__ void finalize(AccT &acc) const {
+  template <class AT>
+  __device__ __forceinline__ void finalize(AT &acc) const {
     acc.s[8] = lp_value(acc.s[8], acc.s[9]);
     acc.s[9] = 0.0;
     acc.s[12] = lp_value(acc.s[12], acc.s[13]);
@@ -1579,11 +1623,17 @@ struct Pass2RF : NoStreams {
 struct Con3 {
   static constexpr int ND = 3;
   double d[3];
+  // kept by the constraint's leader lane from B to E
+  double zw, sw, tw, zsw, ztw, pzw, psw, ptw, pzsw, pztw;
   __device__ __forceinline__ void zero() { d[0] = d[1] = d[2] = 0.0; }
 };
 template <int MR>
 struct Pass2R1F : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int MINB = PCU_MINB_PASS21;
+  enum { S_D1, S_DINV, S_X, S_LB, S_UB, S_G, S_ZL, S_BZL, S_ZU, S_BZU, S_YX, S_YZL, S_YZU, S_V0 };
+  enum { W_CW, W_D2, W_SW, W_TW, W_ZSW, W_ZTW, W_ZW, W_BSW, W_BTW, W_BZSW, W_BZTW,
+         W_YZW, W_YZSW, W_YZTW, W_YSW, W_YTW, NWSLOTS };
   static constexpr int NS = MR, NX = 0, NM = 0, NB = 1, NB2 = 3, NF = 1, FD = 2;
 #if PCU_SMEMACC21
   // the MR running dot products live in shared memory (AccS): ~48 registers less
@@ -1620,18 +1670,43 @@ struct Pass2R1F : NoStreams {
     }
   }
 
-  template <int W>
-  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
+  int nslots() const { return S_V0 + ncols; }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_D1, d1); p_.n(S_DINV, Dinv); p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
+    p_.n(S_G, g);
+    if (k.use_lower) { p_.n(S_ZL, v.zl); if (!from_vars) p_.n(S_BZL, b.zl); }
+    if (k.use_upper) { p_.n(S_ZU, v.zu); if (!from_vars) p_.n(S_BZU, b.zu); }
+    if (accumulate) {
+      p_.n(S_YX, y.x);
+      if (k.use_lower) p_.n(S_YZL, y.zl);
+      if (k.use_upper) p_.n(S_YZU, y.zu);
+    }
+    for (int j = 0; j < ncols; j++) p_.n(S_V0 + j, V.p[j]);
+    p_.w(W_CW, Cw); p_.w(W_D2, d2);
+    p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_ZSW, v.zsw); p_.w(W_ZTW, v.ztw);
+    p_.w(W_ZW, v.zw);
+    if (!from_vars) {
+      p_.w(W_BSW, b.sw); p_.w(W_BTW, b.tw); p_.w(W_BZSW, b.zsw); p_.w(W_BZTW, b.ztw);
+    }
+    if (accumulate) {
+      p_.w(W_YZW, y.zw); p_.w(W_YZSW, y.zsw); p_.w(W_YZTW, y.ztw);
+      p_.w(W_YSW, y.sw); p_.w(W_YTW, y.tw);
+    }
+  }
+
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
                                     Elem (&e)[W], double (&part)[W][1],
-                                    AccT *) const {
+                                    AT *) const {
     double d[W], di[W], lin[W];
-    ldv<W>(d1, i, d);
-    ldv<W>(Dinv, i, di);
+    src.template ld<W>(S_D1, d1, i, d);
+    src.template ld<W>(S_DINV, Dinv, i, di);
 #pragma unroll
     for (int q = 0; q < W; q++) lin[q] = 0.0;
     for (int j = 0; j < ncols; j++) {
       double c[W];
-      ldv<W>(V.p[j], i, c);
+      src.template ld<W>(S_V0 + j, V.p[j], i, c);
 #pragma unroll
       for (int q = 0; q < W; q++) {
         d[q] = fma(alpha.v[j], c[q], d[q]);
@@ -1646,64 +1721,66 @@ struct Pass2R1F : NoStreams {
       part[q][0] = coef[q] * di[q] * d[q];
     }
   }
-  __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
-                                    Con &con, AccT &) const {
-    const double yw = Cw[ci] * (d2[ci] - sum[0]);
-    const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&sum)[1],
+                                    Con &con, AT &) const {
+    const double yw = src.ldw(W_CW, Cw, ci) * (src.ldw(W_D2, d2, ci) - sum[0]);
+    const double sw = src.ldw(W_SW, v.sw, ci), tw = src.ldw(W_TW, v.tw, ci);
+    const double zsw = src.ldw(W_ZSW, v.zsw, ci), ztw = src.ldw(W_ZTW, v.ztw, ci);
+    const double zw = src.ldw(W_ZW, v.zw, ci);
     double bsw, btw, bzsw, bztw;
     if (from_vars) {  // IP.cpp:1361-1389
-      const double zw = v.zw[ci];
       bsw = (zsw - gamma_sw(k, ci)) - zw;
       btw = (ztw - k.gamma) + zw;
       bzsw = mu_rhs - sw * zsw;
       bztw = mu_rhs - tw * ztw;
     } else {
-      bsw = b.sw[ci];
-      btw = b.tw[ci];
-      bzsw = b.zsw[ci];
-      bztw = b.ztw[ci];
+      bsw = src.ldw(W_BSW, b.sw, ci);
+      btw = src.ldw(W_BTW, b.tw, ci);
+      bzsw = src.ldw(W_BZSW, b.zsw, ci);
+      bztw = src.ldw(W_BZTW, b.ztw, ci);
     }
-    const double pzsw = yw - bsw;
-    const double pztw = -btw - yw;
-    const double psw = (bzsw - sw * pzsw) / zsw;
-    const double ptw = (bztw - tw * pztw) / ztw;
+    double pzsw = yw - bsw;
+    double pztw = -btw - yw;
+    double psw = pcu_div(bzsw - sw * pzsw, zsw);
+    double ptw = pcu_div(bztw - tw * pztw, ztw);
     double tzw = yw;
     if (accumulate) {
-      tzw += y.zw[ci];
-      y.zw[ci] = tzw;
-      y.zsw[ci] += pzsw;
-      y.ztw[ci] += pztw;
-      y.sw[ci] += psw;
-      y.tw[ci] += ptw;
-    } else {
-      y.zw[ci] = yw;
-      y.zsw[ci] = pzsw;
-      y.ztw[ci] = pztw;
-      y.sw[ci] = psw;
-      y.tw[ci] = ptw;
+      tzw += src.ldw(W_YZW, y.zw, ci);
+      pzsw = src.ldw(W_YZSW, y.zsw, ci) + pzsw;
+      pztw = src.ldw(W_YZTW, y.ztw, ci) + pztw;
+      psw = src.ldw(W_YSW, y.sw, ci) + psw;
+      ptw = src.ldw(W_YTW, y.tw, ci) + ptw;
     }
+    y.zw[ci] = tzw;
+    y.zsw[ci] = pzsw;
+    y.ztw[ci] = pztw;
+    y.sw[ci] = psw;
+    y.tw[ci] = ptw;
     con.d[0] = yw;
-    con.d[1] = v.zw[ci] + tzw;
+    con.d[1] = zw + tzw;
+    con.zw = zw; con.sw = sw; con.tw = tw; con.zsw = zsw; con.ztw = ztw;
+    con.pzw = tzw; con.psw = psw; con.ptw = ptw; con.pzsw = pzsw; con.pztw = pztw;
   }
-  template <int W>
-  __device__ __forceinline__ void C2(long long i, const double (&coef)[W],
-                                     Elem (&e)[W], const Con &con, AccT &,
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C2(const S &src, long long i, const double (&coef)[W],
+                                     Elem (&e)[W], const Con &con, AT &,
                                      double (&part2)[W][3]) const {
     double x[W], l[W], u[W], zl[W], zu[W], bzl[W], bzu[W], gv[W];
     double px[W], pzl[W], pzu[W], rzl[W], rzu[W], dn[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(g, i, gv);
+    src.template ld<W>(S_X, v.x, i, x);
+    src.template ld<W>(S_LB, lb, i, l);
+    src.template ld<W>(S_UB, ub, i, u);
+    src.template ld<W>(S_G, g, i, gv);
 #pragma unroll
     for (int q = 0; q < W; q++) zl[q] = zu[q] = bzl[q] = bzu[q] = 0.0;
     if (k.use_lower) {
-      ldv<W>(v.zl, i, zl);
-      if (!from_vars) ldv<W>(b.zl, i, bzl);
+      src.template ld<W>(S_ZL, v.zl, i, zl);
+      if (!from_vars) src.template ld<W>(S_BZL, b.zl, i, bzl);
     }
     if (k.use_upper) {
-      ldv<W>(v.zu, i, zu);
-      if (!from_vars) ldv<W>(b.zu, i, bzu);
+      src.template ld<W>(S_ZU, v.zu, i, zu);
+      if (!from_vars) src.template ld<W>(S_BZU, b.zu, i, bzu);
     }
     if (from_vars) {  // rzl, rzu of computeKKTRes (IP.cpp:1417-1444)
 #pragma unroll
@@ -1718,22 +1795,22 @@ struct Pass2R1F : NoStreams {
       pzl[q] = 0.0;
       pzu[q] = 0.0;
       if (k.use_lower && l[q] > -k.mbv)
-        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+        pzl[q] = pcu_div(bzl[q] - zl[q] * px[q], x[q] - l[q]);
       if (k.use_upper && u[q] < k.mbv)
-        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+        pzu[q] = pcu_div(bzu[q] + zu[q] * px[q], u[q] - x[q]);
     }
     if (accumulate) {
       double o[W];
-      ldv<W>(y.x, i, o);
+      src.template ld<W>(S_YX, y.x, i, o);
 #pragma unroll
       for (int q = 0; q < W; q++) px[q] += o[q];
       if (k.use_lower) {
-        ldv<W>(y.zl, i, o);
+        src.template ld<W>(S_YZL, y.zl, i, o);
 #pragma unroll
         for (int q = 0; q < W; q++) pzl[q] += o[q];
       }
       if (k.use_upper) {
-        ldv<W>(y.zu, i, o);
+        src.template ld<W>(S_YZU, y.zu, i, o);
 #pragma unroll
         for (int q = 0; q < W; q++) pzu[q] += o[q];
       }
@@ -1753,11 +1830,11 @@ struct Pass2R1F : NoStreams {
       rzu[q] = 0.0;
       if (k.use_lower && l[q] > -k.mbv) {
         rzl[q] = -(dl * zl[q] - k.kappa * mu) - (dl * pzl[q] + px[q] * zl[q]);
-        t += rzl[q] / dl;
+        t += pcu_div(rzl[q], dl);
       }
       if (k.use_upper && u[q] < k.mbv) {
         rzu[q] = -(du * zu[q] - k.kappa * mu) - (du * pzu[q] - px[q] * zu[q]);
-        t -= rzu[q] / du;
+        t -= pcu_div(rzu[q], du);
       }
       dn[q] = t;
       e[q].d1 = t;
@@ -1769,12 +1846,13 @@ struct Pass2R1F : NoStreams {
     if (k.use_lower) stv<W>(b.zl, i, rzl);
     if (k.use_upper) stv<W>(b.zu, i, rzu);
   }
-  __device__ __forceinline__ void E(long long ci, const double (&sum2)[3],
-                                    Con &con, AccT &) const {
-    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
-    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double pzw = y.zw[ci], psw = y.sw[ci], ptw = y.tw[ci];
-    const double pzsw = y.zsw[ci], pztw = y.ztw[ci];
+  template <class S, class AT>
+  __device__ __forceinline__ void E(const S &src, long long ci, const double (&sum2)[3],
+                                    Con &con, AT &) const {
+    const double zw = con.zw, sw = con.sw, tw = con.tw;
+    const double zsw = con.zsw, ztw = con.ztw;
+    const double pzw = con.pzw, psw = con.psw, ptw = con.ptw;
+    const double pzsw = con.pzsw, pztw = con.pztw;
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
     const double bzw = -(((k.wconst + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
     const double bsw = ((zsw - gsw) - zw) + (pzsw - pzw);
@@ -1785,14 +1863,14 @@ struct Pass2R1F : NoStreams {
     b.tw[ci] = btw;
     b.zsw[ci] = bzsw;
     b.ztw[ci] = bztw;
-    const double dd = bzw + (bzsw + sw * bsw) / zsw - (bztw + tw * btw) / ztw;
+    const double dd = bzw + pcu_div(bzsw + sw * bsw, zsw) - pcu_div(bztw + tw * btw, ztw);
     d2[ci] = dd;
-    con.d[2] = Cw[ci] * (dd - sum2[2]);
+    con.d[2] = src.ldw(W_CW, Cw, ci) * (dd - sum2[2]);
   }
-  template <int W>
-  __device__ __forceinline__ void F(long long i, const double (&coef)[W],
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void F(const S &src, long long i, const double (&coef)[W],
                                     const Elem (&e)[W], const Con &con,
-                                    AccT &acc) const {
+                                    AT &acc) const {
     double t[W];
 #pragma unroll
     for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[2], e[q].d1);
@@ -1800,14 +1878,15 @@ struct Pass2R1F : NoStreams {
     for (int j = 0; j < MR; j++) {
       if (j < ncols) {
         double c[W];
-        ldv<W>(V.p[j], i, c);
+        src.template ld<W>(S_V0 + j, V.p[j], i, c);
 #pragma unroll
         for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
       }
     }
   }
-  __device__ __forceinline__ void FG(long long i, double coef, const Con &con,
-                                     AccT &acc) const {
+  template <class S, class AT>
+  __device__ __forceinline__ void FG(const S &, long long i, double coef, const Con &con,
+                                     AT &acc) const {
     const double t = Dinv[i] * fma(coef, con.d[2], d1out[i]);
 #pragma unroll
     for (int j = 0; j < MR; j++) {

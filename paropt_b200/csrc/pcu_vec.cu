@@ -217,6 +217,11 @@ pcu_ctx *pcu_ctx_create(int device) {
   ctx->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("PCU_MAX_BLOCKS_PER_SM")) ctx->max_blocks_per_sm = atoi(e);
   if (const char *e = getenv("PCU_PREFETCH")) ctx->prefetch = atoi(e);
+  if (getenv("PCU_NO_TMA_TILE")) ctx->no_tma_tile = 1;
+  if (const char *e = getenv("PCU_TMA_GROUPS")) ctx->tma_groups = atoi(e);
+  if (const char *e = getenv("PCU_TMA_NPW")) ctx->tma_npw = atoi(e);
+  if (const char *e = getenv("PCU_TMA_MIN_TILES")) ctx->tma_min_tiles = atoi(e);
+  if (const char *e = getenv("PCU_TMA_GRID")) ctx->tma_grid = atoi(e);
   ctx->grid = prop.multiProcessorCount * 4;
   if (ctx->grid > PCU_MAX_BLOCKS) ctx->grid = PCU_MAX_BLOCKS;
   bool ok = true;
@@ -301,6 +306,20 @@ int pcu_ctx_sync(pcu_ctx *ctx) {
 }
 void *pcu_ctx_stream(pcu_ctx *ctx) { return (void *)ctx->stream; }
 int64_t pcu_ctx_kernel_launches(pcu_ctx *ctx) { return ctx->launches; }
+
+int pcu_ctx_set_param(pcu_ctx *ctx, const char *name, int value) {
+  if (!ctx || !name) return 1;
+  const std::string k(name);
+  if (k == "prefetch") ctx->prefetch = value;
+  else if (k == "max_blocks_per_sm") ctx->max_blocks_per_sm = value;
+  else if (k == "no_tma_tile") ctx->no_tma_tile = value;
+  else if (k == "tma_groups") ctx->tma_groups = value;
+  else if (k == "tma_npw") ctx->tma_npw = value;
+  else if (k == "tma_min_tiles") ctx->tma_min_tiles = value;
+  else if (k == "tma_grid") ctx->tma_grid = value;
+  else return 1;
+  return 0;
+}
 int pcu_ctx_profile(pcu_ctx *ctx, int enable) {
   cudaStreamSynchronize(ctx->stream);
   ctx->prof_collect();

@@ -389,18 +389,24 @@ int main(int argc, char **argv) {
                  rows, ncw, bps, stages, ms, gb / ms * 1e3,
                  e == cudaSuccess ? "" : cudaGetErrorString(e));
         }
+  // G consumer groups of rows/64 warps; nstages = G * depth so that a stage always belongs to one group
   for (int rows : {64, 128, 256})
-    for (int np : {1, 2, 4})
-      for (int ncw : {8, 16}) {
+    for (int np : {1, 2, 4, 6})
+      for (int depth : {1, 2}) {
         const size_t col = (size_t)rows * 8 * a.K;
-        int stages = (int)((220 * 1024) / col);
-        if (stages > 16) stages = 16;
-        if (stages < 2) continue;
-        a.variant = 20; a.rows = rows; a.ncw = ncw; a.stages = stages; a.np = np;
+        int stages = (int)((216 * 1024) / col);
+        int G = stages / depth;
+        const int wpt = rows / 64;
+        if (G * wpt + np > 30) G = (30 - np) / wpt;
+        if (G > 16 / depth) G = 16 / depth;
+        if (G < 1) continue;
+        stages = G * depth;
+        a.variant = 20; a.rows = rows; a.ncw = G * wpt; a.stages = stages; a.np = np;
         const float ms = time_it(launch, &a, 5);
         cudaError_t e = cudaGetLastError();
-        printf("tmap rows %3d np %d ncw %2d stages %2d : %7.3f ms  %7.1f GB/s %s\n", rows, np, ncw,
-               stages, ms, gb / ms * 1e3, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        printf("tmap rows %3d np %d groups %2d depth %d (ncw %2d stages %2d) : %7.3f ms  %7.1f GB/s %s\n",
+               rows, np, G, depth, a.ncw, stages, ms, gb / ms * 1e3,
+               e == cudaSuccess ? "" : cudaGetErrorString(e));
       }
   for (int ncw : {4, 6, 8, 12})
     for (int stages : {2, 3}) {

@@ -31,6 +31,11 @@ def run(ctx, make_problem, options, iters, plain):
             os.environ[k] = "1"
         else:
             os.environ.pop(k, None)
+    # bulk-copy staged fused passes (tma_tile_kernel): forced on at these sizes with
+    # a grid small enough that every CTA wraps its stage ring several times
+    ctx.set_param("no_tma_tile", 1 if plain else 0)
+    ctx.set_param("tma_min_tiles", 1)
+    ctx.set_param("tma_grid", 7)
     try:
         prob = make_problem()
         ip = InteriorPoint(prob, dict(options, history_level=2, max_major_iters=iters))
@@ -41,6 +46,9 @@ def run(ctx, make_problem, options, iters, plain):
     finally:
         for k in SWITCHES:
             os.environ.pop(k, None)
+        ctx.set_param("no_tma_tile", 0)
+        ctx.set_param("tma_min_tiles", 0)
+        ctx.set_param("tma_grid", 0)
     return hist
 
 
