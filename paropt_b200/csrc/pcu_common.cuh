@@ -289,20 +289,42 @@ struct GSrc {
                                      double (&out)[W]) const {
     ldv<W>(p, i, out);
   }
+  template <int W>  // column j of the functor's column table (slot NFIX + j)
+  __device__ __forceinline__ void ldc(int, const double *p, long long i,
+                                      double (&out)[W]) const {
+    ldv<W>(p, i, out);
+  }
   __device__ __forceinline__ double ldw(int, const double *p, long long ci) const {
     return p[ci];
   }
 };
-template <int ROWS>
+template <int ROWS, int NFIX>
 struct SSrc {
-  const unsigned char *nb;  // N-slots: [slot][ROWS] doubles
+  const unsigned char *nb;  // N-slots: [compact slot][ROWS] doubles
   const unsigned char *wb;  // W-slots: [slot][wpitch bytes]
   long long row0, con0;     // first element / first weighting constraint of the tile
   int wpitch;
+  unsigned long long nmap[3];  // fixed slot id -> compact slot, one byte each
+  int col_base;                // compact slot of column 0 (slot id NFIX)
   template <int W>
   __device__ __forceinline__ void ld(int slot, const double *, long long i,
                                      double (&out)[W]) const {
-    const double *q = reinterpret_cast<const double *>(nb + slot * (ROWS * 8)) + (int)(i - row0);
+    const int cs = slot < NFIX ? (int)((nmap[(slot >> 3) % 3] >> ((slot & 7) * 8)) & 0xffull)
+                               : col_base + (slot - NFIX);
+    const double *q = reinterpret_cast<const double *>(nb + cs * (ROWS * 8)) + (int)(i - row0);
+    if (W == 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(q);
+      out[0] = v.x;
+      out[W - 1] = v.y;
+    } else {
+      out[0] = q[0];
+    }
+  }
+  template <int W>
+  __device__ __forceinline__ void ldc(int j, const double *, long long i,
+                                      double (&out)[W]) const {
+    const double *q =
+        reinterpret_cast<const double *>(nb + (col_base + j) * (ROWS * 8)) + (int)(i - row0);
     if (W == 2) {
       const double2 v = *reinterpret_cast<const double2 *>(q);
       out[0] = v.x;
@@ -318,6 +340,7 @@ struct SSrc {
 
 struct NoStreams {
   static constexpr int SRC = 0;   // 1: phases take a source (GSrc / SSrc) and slot ids
+  static constexpr int TROWS = 128;  // rows per staged tile (few streams -> larger tiles)
   static constexpr int NB2 = 0;   // second-round per-constraint block sums (C2 / E phases)
   static constexpr int HASP = 0;  // P(ci, con): per-constraint prologue seen by A (AP form)
   static constexpr int NF = 0;    // third round F / FG after E: E leaves con.d[FD] to broadcast
@@ -627,6 +650,8 @@ struct TmaPlan {
   int woff;             // byte offset of the W-slots inside a stage
   int wpitch;           // bytes per W-slot
   int npw;              // producer warps
+  int col_base;         // compact slot of the first column
+  unsigned long long nmap[3];  // fixed slot id -> compact slot, one byte each
 };
 
 #define PCU_TMA_NPW 4        // producer warps = warpgroup 0 (the first plan.npw of them issue copies)
@@ -634,6 +659,7 @@ struct TmaPlan {
 #define PCU_TMA_CONS_REGS 160  // ... the 12 consumer warps get 160 (launch: 128 each)
 #define PCU_TMA_MAXWARPS 16  // 4 producer + 12 consumer warps per CTA (one CTA per SM)
 #define PCU_TMA_MAXSTAGES 16
+#define PCU_TMA_WPT 2         // consumer warps per group
 
 __device__ __forceinline__ unsigned tt_smem_u32(const void *p) {
   return (unsigned)__cvta_generic_to_shared(p);
@@ -673,8 +699,10 @@ __device__ __forceinline__ void tt_bulk_g2s(unsigned dst, const void *src,
 
 // Deals the functor's streams (tstreams order) over the producer threads:
 // copy c goes to producer warp c % NPW, lane (c / NPW) % 32, at most two per thread.
-template <int ROWS>
+template <int ROWS, int NFIX>
 struct TmaAssign {
+  unsigned long long nmap[3];
+  int col_base;
   int me_warp, me_lane, c, npw;
   int cnt;
   const double *p0, *p1;
@@ -693,7 +721,9 @@ struct TmaAssign {
     cnt++;
   }
   __host__ __device__ __forceinline__ void n(int slot, const double *ptr) {
-    take(ptr, (unsigned)slot * (ROWS * 8), 0);
+    const int cs = slot < NFIX ? (int)((nmap[(slot >> 3) % 3] >> ((slot & 7) * 8)) & 0xffull)
+                               : col_base + (slot - NFIX);
+    take(ptr, (unsigned)cs * (ROWS * 8), 0);
   }
   __host__ __device__ __forceinline__ void w(int slot, const double *ptr) {
     take(ptr, (unsigned)(woff + slot * wpitch), 1);
@@ -704,7 +734,8 @@ template <class F, int ROWS>
 __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     tma_tile_kernel(const F f, const long long n, const WDesc w, const RedBuf rb,
                     const TmaPlan plan) {
-  constexpr int WPT = ROWS / 64;  // consumer warps per tile
+  constexpr int WPT = PCU_TMA_WPT;           // consumer warps per group
+  constexpr int CHUNKS = ROWS / (64 * WPT);  // 64-row chunks per warp per tile
   constexpr int NCWMAX = PCU_TMA_MAXWARPS - PCU_TMA_NPW;
   extern __shared__ double2 pcu_dyn_smem[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(pcu_dyn_smem);
@@ -731,7 +762,11 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     // hand most of this warpgroup's registers to the consumers
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PCU_TMA_PROD_REGS));
     if (warp >= plan.npw) return;
-    TmaAssign<ROWS> as;
+    TmaAssign<ROWS, F::NFIX> as;
+    as.nmap[0] = plan.nmap[0];
+    as.nmap[1] = plan.nmap[1];
+    as.nmap[2] = plan.nmap[2];
+    as.col_base = plan.col_base;
     as.me_warp = warp;
     as.me_lane = lane;
     as.npw = plan.npw;
@@ -790,13 +825,19 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
       if ((int)(my % plan.groups) != g) continue;
       const int s = (int)(my % S);
       tt_mbar_wait(tt_smem_u32(&tt_full[s]), (unsigned)(my / S) & 1);
-      SSrc<ROWS> src;
+      SSrc<ROWS, F::NFIX> src;
       src.nb = smem + (size_t)s * plan.stage_bytes;
       src.wb = src.nb + plan.woff;
       src.row0 = tile * ROWS;
       src.con0 = tile * con_per_tile;
       src.wpitch = plan.wpitch;
-      tile_pair(f, src, w, src.row0 + wg * 64 + 2 * lane, ncon_elems, half, acc);
+      src.nmap[0] = plan.nmap[0];
+      src.nmap[1] = plan.nmap[1];
+      src.nmap[2] = plan.nmap[2];
+      src.col_base = plan.col_base;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; c++)
+        tile_pair(f, src, w, src.row0 + (c * WPT + wg) * 64 + 2 * lane, ncon_elems, half, acc);
       __syncwarp();
       if (lane == 0) tt_mbar_arrive(tt_smem_u32(&tt_empty[s]));
     }

@@ -45,6 +45,7 @@ struct pcu_ctx {
   int tma_npw = 0;             // PCU_TMA_NPW: producer warps of tma_tile_kernel (default 2)
   int tma_min_tiles = 0;       // staged launch only from this many tiles (default 8 per SM)
   int tma_grid = 0;            // CTAs of the staged launch (default: one per SM)
+  int tma_max_rows = 0;        // debugging: staged launch only for tiles up to this many rows
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -108,19 +109,26 @@ static inline int pcu_grid_for(const pcu_ctx *ctx, long long n) {
   return (int)need;
 }
 
-// Host-side visit of a functor's staged streams: slot count and alignment.
+// Host-side visit of a functor's staged streams: which slots are live, alignment.
 struct TmaHostCheck {
-  int copies = 0;
+  int nfix = 0;
+  int copies = 0, ncols = 0;
   bool aligned = true;
-  __host__ __device__ void n(int, const double *ptr) {
+  bool fixed[24] = {false};
+  __host__ __device__ void n(int slot, const double *ptr) {
+    if (!ptr) return;
+    copies++;
+    if (((uintptr_t)ptr) & 15) aligned = false;
+    if (slot < nfix) fixed[slot] = true;
+    else if (slot - nfix + 1 > ncols) ncols = slot - nfix + 1;
+  }
+  __host__ __device__ void w(int, const double *ptr) {
     if (!ptr) return;
     copies++;
     if (((uintptr_t)ptr) & 15) aligned = false;
   }
-  __host__ __device__ void w(int, const double *ptr) { n(0, ptr); }
 };
 
-#define PCU_TMA_ROWS 128
 #define PCU_TMA_SMEM_BUDGET (214 * 1024)
 
 // Bulk-copy staged launch of a SRC functor (tma_tile_kernel); returns -1 when
@@ -129,8 +137,10 @@ struct TmaHostCheck {
 template <class F>
 int pcu_launch_tile_tma(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
                         RedBuf rb) {
-  constexpr int ROWS = PCU_TMA_ROWS, WPT = ROWS / 64;
+  constexpr int ROWS = F::TROWS, WPT = PCU_TMA_WPT;
+  static_assert(F::NFIX <= 24 && ROWS % (64 * WPT) == 0, "staged tile shape");
   if (ctx->no_tma_tile || w.mode == 2) return -1;
+  if (ctx->tma_max_rows > 0 && ROWS > ctx->tma_max_rows) return -1;
   if (w.mode == 1 && (w.nw < 2 || w.nw > 64 || (w.nw & (w.nw - 1)) || w.wstart != 0 ||
                       w.wstride != w.nw))
     return -1;
@@ -140,12 +150,20 @@ int pcu_launch_tile_tma(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
                                             : (long long)ctx->num_sms * 8))
     return -1;
   TmaHostCheck chk;
+  chk.nfix = F::NFIX;
   f.tstreams(chk);
+  int nslots = 0;  // live fixed slots, compacted, then the columns
+  plan.nmap[0] = plan.nmap[1] = plan.nmap[2] = 0ull;
+  for (int i = 0; i < F::NFIX; i++) {
+    plan.nmap[i >> 3] |= (unsigned long long)nslots << ((i & 7) * 8);
+    if (chk.fixed[i]) nslots++;
+  }
+  plan.col_base = nslots;
+  nslots += chk.ncols;
   int npw = ctx->tma_npw > 0 ? ctx->tma_npw : 4;
   if (npw > PCU_TMA_NPW) npw = PCU_TMA_NPW;
   plan.npw = npw;
   if (!chk.aligned || chk.copies > 64 * npw) return -1;
-  const int nslots = f.nslots();
   const int con_per_tile = w.mode == 1 ? ROWS / w.nw : 0;
   plan.wpitch = (con_per_tile * 8 + 15) / 16 * 16;
   plan.woff = nslots * ROWS * 8;

@@ -84,7 +84,12 @@ struct Con1 {  // one broadcast value
 //       3 norm-sum rx, 4 norm-sum rzw, 5..8 l1 of rsw,rtw,rzsw,rztw,
 //       9,10 norm-sum rzl, rzu;   maxima: 0 |rx|, 1 |rzw|, 2 dual parts
 struct ResF : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int MINB = PCU_MINB_RES;
+  enum { S_X, S_LB, S_UB, S_G, S_ZL, S_ZU, S_PX, S_PZL, S_PZU, S_A0 };  // then A, then Z columns
+  static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
+  static constexpr int TROWS = 512;
+  enum { W_ZW, W_SW, W_TW, W_ZSW, W_ZTW, W_PZW, W_PSW, W_PTW, W_PZSW, W_PZTW, NWSLOTS };
   // maxima: 0 |rx|, 1 |rzw|, 2 mu-independent dual parts (|rsw|, |rtw|) and, for
   // l1/l2 bookkeeping, every dual part; 3 max zl(x-lb) | zu(ub-x); 4 max sw zsw |
   // tw ztw.  minima: 0 / 1 the same two products.  With them the infinity-norm
@@ -125,23 +130,42 @@ struct ResF : NoStreams {
     }
   }
 
-  template <int W>
-  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][2], AccT *acc) const {
+  int nslots() const { return S_A0 + ncon + (has_step ? nq : 0); }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub); p_.n(S_G, g);
+    if (k.use_lower) p_.n(S_ZL, v.zl);
+    if (k.use_upper) p_.n(S_ZU, v.zu);
+    for (int j = 0; j < ncon; j++) p_.n(S_A0 + j, Acol.p[j]);
+    p_.w(W_ZW, v.zw); p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_ZSW, v.zsw);
+    p_.w(W_ZTW, v.ztw);
+    if (has_step) {
+      p_.n(S_PX, p.x);
+      if (k.use_lower) p_.n(S_PZL, p.zl);
+      if (k.use_upper) p_.n(S_PZU, p.zu);
+      for (int j = 0; j < nq; j++) p_.n(S_A0 + ncon + j, Z.p[j]);
+      p_.w(W_PZW, p.zw); p_.w(W_PSW, p.sw); p_.w(W_PTW, p.tw); p_.w(W_PZSW, p.zsw);
+      p_.w(W_PZTW, p.ztw);
+    }
+  }
+
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][2], AT *acc) const {
     double x[W], l[W], u[W], zl[W], zu[W], gv[W], rx[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(g, i, gv);
+    src.template ld<W>(S_X, v.x, i, x);
+    src.template ld<W>(S_LB, lb, i, l);
+    src.template ld<W>(S_UB, ub, i, u);
+    src.template ld<W>(S_G, g, i, gv);
 #pragma unroll
     for (int q = 0; q < W; q++) zl[q] = zu[q] = 0.0;
-    if (k.use_lower) ldv<W>(v.zl, i, zl);
-    if (k.use_upper) ldv<W>(v.zu, i, zu);
+    if (k.use_lower) src.template ld<W>(S_ZL, v.zl, i, zl);
+    if (k.use_upper) src.template ld<W>(S_ZU, v.zu, i, zu);
 #pragma unroll
     for (int q = 0; q < W; q++) rx[q] = (zl[q] - zu[q]) - gv[q];
     for (int j = 0; j < ncon; j++) {
       double a[W];
-      ldv<W>(Acol.p[j], i, a);
+      src.template ldc<W>(j, Acol.p[j], i, a);
 #pragma unroll
       for (int q = 0; q < W; q++) rx[q] = fma(z.v[j], a[q], rx[q]);
     }
@@ -149,15 +173,15 @@ struct ResF : NoStreams {
 #pragma unroll
     for (int q = 0; q < W; q++) px[q] = pzl[q] = pzu[q] = 0.0;
     if (has_step) {
-      ldv<W>(p.x, i, px);
-      if (k.use_lower) ldv<W>(p.zl, i, pzl);
-      if (k.use_upper) ldv<W>(p.zu, i, pzu);
+      src.template ld<W>(S_PX, p.x, i, px);
+      if (k.use_lower) src.template ld<W>(S_PZL, p.zl, i, pzl);
+      if (k.use_upper) src.template ld<W>(S_PZU, p.zu, i, pzu);
 #pragma unroll
       for (int q = 0; q < W; q++)
         rx[q] = fma(-b0sig, px[q], rx[q]) + (pzl[q] - pzu[q]);
       for (int j = 0; j < nq; j++) {
         double zc[W];
-        ldv<W>(Z.p[j], i, zc);
+        src.template ldc<W>(ncon + j, Z.p[j], i, zc);
 #pragma unroll
         for (int q = 0; q < W; q++) rx[q] = fma(kap.v[j], zc[q], rx[q]);
       }
@@ -199,10 +223,11 @@ struct ResF : NoStreams {
     }
   }
 
-  __device__ __forceinline__ void B(long long ci, const double (&sum)[2],
-                                    Con &con, AccT &acc) const {
-    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
-    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&sum)[2],
+                                    Con &con, AT &acc) const {
+    const double zw = src.ldw(W_ZW, v.zw, ci), sw = src.ldw(W_SW, v.sw, ci), tw = src.ldw(W_TW, v.tw, ci);
+    const double zsw = src.ldw(W_ZSW, v.zsw, ci), ztw = src.ldw(W_ZTW, v.ztw, ci);
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
     double rzw = -(((k.wconst + sum[0]) - sw) + tw);
     double rsw = (zsw - gsw) - zw;
@@ -214,8 +239,8 @@ struct ResF : NoStreams {
     acc.m[1] = fmin(acc.m[1], fmin(asw, atw));
     con.d[0] = zw;
     if (has_step) {
-      const double pzw = p.zw[ci], psw = p.sw[ci], ptw = p.tw[ci];
-      const double pzsw = p.zsw[ci], pztw = p.ztw[ci];
+      const double pzw = src.ldw(W_PZW, p.zw, ci), psw = src.ldw(W_PSW, p.sw, ci), ptw = src.ldw(W_PTW, p.tw, ci);
+      const double pzsw = src.ldw(W_PZSW, p.zsw, ci), pztw = src.ldw(W_PZTW, p.ztw, ci);
       rzw += (psw - sum[1]) - ptw;
       rsw += pzsw - pzw;
       rtw += pztw + pzw;
@@ -249,10 +274,10 @@ struct ResF : NoStreams {
     }
   }
 
-  template <int W>
-  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C(const S &, long long i, const double (&coef)[W],
                                     const Elem (&e)[W], const Con &con,
-                                    AccT &acc) const {
+                                    AT &acc) const {
     double rx[W], rzl[W], rzu[W];
 #pragma unroll
     for (int q = 0; q < W; q++) {
@@ -360,7 +385,12 @@ struct DiagF : NoStreams {
 // so the first solve of an iteration has no pass 1 of its own.
 // Traffic: reads (6 + c)N + 5W, writes 2N + 2W.
 struct DiagRhsF : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 2, HASP = 1;
+  enum { S_X, S_LB, S_UB, S_G, S_ZL, S_ZU, S_A0 };
+  static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
+  static constexpr int TROWS = 512;
+  enum { W_ZW, W_SW, W_TW, W_ZSW, W_ZTW, NWSLOTS };
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // zw
   struct Elem {};
@@ -380,27 +410,38 @@ struct DiagRhsF : NoStreams {
     if (k.use_upper) p_(v.zu);
     for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
   }
-  __device__ __forceinline__ void P(long long ci, Con &con) const {
-    con.d[0] = v.zw[ci];
+  int nslots() const { return S_A0 + ncon; }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub); p_.n(S_G, g);
+    if (k.use_lower) p_.n(S_ZL, v.zl);
+    if (k.use_upper) p_.n(S_ZU, v.zu);
+    for (int j = 0; j < ncon; j++) p_.n(S_A0 + j, Acol.p[j]);
+    p_.w(W_ZW, v.zw); p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_ZSW, v.zsw);
+    p_.w(W_ZTW, v.ztw);
   }
-  template <int W>
-  __device__ __forceinline__ void AP(long long i, const double (&coef)[W],
-                                     Elem (&)[W], double (&part)[W][2], AccT *,
+  template <class S>
+  __device__ __forceinline__ void P(const S &src, long long ci, Con &con) const {
+    con.d[0] = src.ldw(W_ZW, v.zw, ci);
+  }
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void AP(const S &src, long long i, const double (&coef)[W],
+                                     Elem (&)[W], double (&part)[W][2], AT *,
                                      const Con &con) const {
     double x[W], l[W], u[W], gv[W], zl[W], zu[W], di[W], d[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(g, i, gv);
+    src.template ld<W>(S_X, v.x, i, x);
+    src.template ld<W>(S_LB, lb, i, l);
+    src.template ld<W>(S_UB, ub, i, u);
+    src.template ld<W>(S_G, g, i, gv);
 #pragma unroll
     for (int q = 0; q < W; q++) zl[q] = zu[q] = 0.0;
-    if (k.use_lower) ldv<W>(v.zl, i, zl);
-    if (k.use_upper) ldv<W>(v.zu, i, zu);
+    if (k.use_lower) src.template ld<W>(S_ZL, v.zl, i, zl);
+    if (k.use_upper) src.template ld<W>(S_ZU, v.zu, i, zu);
 #pragma unroll
     for (int q = 0; q < W; q++) d[q] = (zl[q] - zu[q]) - gv[q];
     for (int j = 0; j < ncon; j++) {
       double a[W];
-      ldv<W>(Acol.p[j], i, a);
+      src.template ldc<W>(j, Acol.p[j], i, a);
 #pragma unroll
       for (int q = 0; q < W; q++) d[q] = fma(z.v[j], a[q], d[q]);
     }
@@ -410,14 +451,16 @@ struct DiagRhsF : NoStreams {
       double c = b0sig;                           // IP.cpp:1864-1910
       double t = fma(coef[q], con.d[0], d[q]);    // rx
       if (k.use_lower && l[q] > -k.mbv) {
-        c += zl[q] / dl;
-        t += -(dl * zl[q] - k.kappa * mu) / dl;
+        const double rl = pcu_rcp(dl);
+        c = fma(zl[q], rl, c);
+        t += -(dl * zl[q] - k.kappa * mu) * rl;
       }
       if (k.use_upper && u[q] < k.mbv) {
-        c += zu[q] / du;
-        t -= -(du * zu[q] - k.kappa * mu) / du;
+        const double ru = pcu_rcp(du);
+        c = fma(zu[q], ru, c);
+        t -= -(du * zu[q] - k.kappa * mu) * ru;
       }
-      di[q] = 1.0 / c;
+      di[q] = pcu_rcp(c);
       d[q] = t;
       part[q][0] = coef[q] * coef[q] * di[q];
       part[q][1] = coef[q] * x[q];
@@ -425,22 +468,23 @@ struct DiagRhsF : NoStreams {
     stv<W>(Dinv, i, di);
     stv<W>(d1, i, d);
   }
-  __device__ __forceinline__ void B(long long ci, const double (&sum)[2], Con &,
-                                    AccT &) const {
-    const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
-    const double zsw = v.zsw[ci], ztw = v.ztw[ci];
-    Cw[ci] = 1.0 / ((sw / zsw + tw / ztw) + sum[0]);
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&sum)[2], Con &,
+                                    AT &) const {
+    const double zw = src.ldw(W_ZW, v.zw, ci), sw = src.ldw(W_SW, v.sw, ci);
+    const double tw = src.ldw(W_TW, v.tw, ci);
+    const double zsw = src.ldw(W_ZSW, v.zsw, ci), ztw = src.ldw(W_ZTW, v.ztw, ci);
+    Cw[ci] = pcu_rcp((pcu_div(sw, zsw) + pcu_div(tw, ztw)) + sum[0]);
     const double bzw = -(((k.wconst + sum[1]) - sw) + tw);
     const double bsw = (zsw - gamma_sw(k, ci)) - zw;
     const double btw = (ztw - k.gamma) + zw;
     const double bzsw = mu - sw * zsw;
     const double bztw = mu - tw * ztw;
-    d2[ci] = bzw + (bzsw + sw * bsw) / zsw - (bztw + tw * btw) / ztw;
+    d2[ci] = bzw + pcu_div(bzsw + sw * bsw, zsw) - pcu_div(bztw + tw * btw, ztw);
   }
-  template <int W>
-  __device__ __forceinline__ void C(long long, const double (&)[W],
-                                    const Elem (&)[W], const Con &,
-                                    AccT &) const {}
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C(const S &, long long, const double (&)[W],
+                                    const Elem (&)[W], const Con &, AT &) const {}
 };
 
 // ============================================================== MehrotraCorrF
@@ -894,6 +938,7 @@ struct Pass2SF : NoStreams {
   };
   // staged slots (tma_tile_kernel): N-streams, then the columns; W-streams
   enum { S_D1, S_DINV, S_X, S_LB, S_UB, S_G, S_ZL, S_BZL, S_ZU, S_BZU, S_YX, S_YZL, S_YZU, S_V0 };
+  static constexpr int NFIX = S_V0;  // fixed slots; the columns follow
   enum { W_CW, W_D2, W_SW, W_TW, W_ZSW, W_ZTW, W_BSW, W_BTW, W_BZSW, W_BZTW,
          W_YZW, W_YZSW, W_YZTW, W_YSW, W_YTW, NWSLOTS };
   DVars v, b, y;
@@ -947,7 +992,7 @@ struct Pass2SF : NoStreams {
     src.template ld<W>(S_DINV, Dinv, i, di);
     for (int j = 0; j < ncols; j++) {
       double c[W];
-      src.template ld<W>(S_V0 + j, V.p[j], i, c);
+      src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
       for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j], c[q], d[q]);
     }
@@ -1064,7 +1109,18 @@ struct Pass2SF : NoStreams {
 //   sums: 0,1 pos/neg log (bounds); 2,3 pos/neg log (sw,tw); 4 gam.(rsw,rtw);
 //         5 |cw(rx) - rsw + rtw|^2
 struct TrialF : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int NS = 6, NX = 0, NM = 0, NB = 1;
+  enum { S_X, S_PX, S_LB, S_UB, NSLOTS };
+  static constexpr int NFIX = NSLOTS;  // fixed slots; the columns follow
+  static constexpr int TROWS = 1024;
+  enum { W_SW, W_TW, W_PSW, W_PTW, NWSLOTS };
+  int nslots() const { return NSLOTS; }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_X, v.x); p_.n(S_PX, p.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
+    p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_PSW, p.sw); p_.w(W_PTW, p.tw);
+  }
   typedef Acc<NS, NX, NM> AccT;
   typedef Con0 Con;
   struct Elem {
@@ -1081,14 +1137,14 @@ struct TrialF : NoStreams {
     p_(v.x); p_(p.x); p_(lb); p_(ub);
   }
 
-  template <int W>
-  __device__ __forceinline__ void A(long long i, const double (&coef)[W],
-                                    Elem (&e)[W], double (&part)[W][1], AccT *acc) const {
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1], AT *acc) const {
     double x[W], l[W], u[W], px[W], r[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(p.x, i, px);
+    src.template ld<W>(S_X, v.x, i, x);
+    src.template ld<W>(S_LB, lb, i, l);
+    src.template ld<W>(S_UB, ub, i, u);
+    src.template ld<W>(S_PX, p.x, i, px);
 #pragma unroll
     for (int q = 0; q < W; q++) {
       r[q] = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
@@ -1101,10 +1157,11 @@ struct TrialF : NoStreams {
     }
     stv<W>(rx, i, r);
   }
-  __device__ __forceinline__ void B(long long ci, const double (&sum)[1], Con &,
-                                    AccT &acc) const {
-    const double s = step_clip0(v.sw[ci], ax, p.sw[ci], k.dp);
-    const double t = step_clip0(v.tw[ci], ax, p.tw[ci], k.dp);
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&sum)[1], Con &,
+                                    AT &acc) const {
+    const double s = step_clip0(src.ldw(W_SW, v.sw, ci), ax, src.ldw(W_PSW, p.sw, ci), k.dp);
+    const double t = step_clip0(src.ldw(W_TW, v.tw, ci), ax, src.ldw(W_PTW, p.tw, ci), k.dp);
     rsw[ci] = s;
     rtw[ci] = t;
     lp_mul(acc.s[2], acc.s[3], s * t);
@@ -1112,16 +1169,17 @@ struct TrialF : NoStreams {
     const double rw = ((k.wconst + sum[0]) - s) + t;
     acc.s[5] = fma(rw, rw, acc.s[5]);
   }
-  template <int W>
-  __device__ __forceinline__ void C(long long, const double (&)[W],
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C(const S &, long long, const double (&)[W],
                                     const Elem (&e)[W], const Con &,
-                                    AccT &acc) const {
+                                    AT &acc) const {
     double f = e[0].f;
 #pragma unroll
     for (int q = 1; q < W; q++) f *= e[q].f;
     lp_mul(acc.s[0], acc.s[1], f);
   }
-  __device__ __forceinline__ void finalize(AccT &acc) const {
+  template <class AT>
+  __device__ __forceinline__ void finalize(AT &acc) const {
     acc.s[0] = lp_value(acc.s[0], acc.s[1]);
     acc.s[1] = 0.0;
     acc.s[2] = lp_value(acc.s[2], acc.s[3]);
@@ -1135,7 +1193,27 @@ struct TrialF : NoStreams {
 // y_qn = -g + sum_j z_j A_j + Aw^T zw with the NEW multipliers and the OLD
 // gradients.  Traffic: reads (6 + c)N + 10W, writes 4N + 5W.
 struct Update1F : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  enum { S_X, S_PX, S_LB, S_UB, S_ZL, S_PZL, S_ZU, S_PZU, S_G, S_A0 };
+  static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
+  static constexpr int TROWS = 512;
+  enum { W_ZW, W_SW, W_TW, W_ZSW, W_ZTW, W_PZW, W_PSW, W_PTW, W_PZSW, W_PZTW, NWSLOTS };
+  int nslots() const { return S_A0 + (yqn ? ncon : 0); }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_X, v.x); p_.n(S_PX, p.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
+    if (k.use_lower) { p_.n(S_ZL, v.zl); p_.n(S_PZL, p.zl); }
+    if (k.use_upper) { p_.n(S_ZU, v.zu); p_.n(S_PZU, p.zu); }
+    if (yqn) {
+      p_.n(S_G, g);
+      for (int j = 0; j < ncon; j++) p_.n(S_A0 + j, Acol.p[j]);
+    }
+    p_.w(W_ZW, v.zw); p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_ZSW, v.zsw);
+    p_.w(W_ZTW, v.ztw);
+    p_.w(W_PZW, p.zw); p_.w(W_PSW, p.sw); p_.w(W_PTW, p.tw); p_.w(W_PZSW, p.zsw);
+    p_.w(W_PZTW, p.ztw);
+  }
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // new zw
   struct Elem {};
@@ -1159,52 +1237,53 @@ struct Update1F : NoStreams {
     }
   }
 
-  template <int W>
-  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1], AccT *acc) const {}
-  __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &con,
-                                    AccT &) const {
-    const double zwn = fma(az, p.zw[ci], v.zw[ci]);  // no clipping (IP.cpp:4181)
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void A(const S &, long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1], AT *) const {}
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&)[1], Con &con,
+                                    AT &) const {
+    const double zwn = fma(az, src.ldw(W_PZW, p.zw, ci), src.ldw(W_ZW, v.zw, ci));  // no clipping (IP.cpp:4181)
     con.d[0] = zwn;
     v.zw[ci] = zwn;
-    v.sw[ci] = step_clip0(v.sw[ci], ax, p.sw[ci], k.dp);
-    v.tw[ci] = step_clip0(v.tw[ci], ax, p.tw[ci], k.dp);
-    v.zsw[ci] = step_clip0(v.zsw[ci], az, p.zsw[ci], k.dp);
-    v.ztw[ci] = step_clip0(v.ztw[ci], az, p.ztw[ci], k.dp);
+    v.sw[ci] = step_clip0(src.ldw(W_SW, v.sw, ci), ax, src.ldw(W_PSW, p.sw, ci), k.dp);
+    v.tw[ci] = step_clip0(src.ldw(W_TW, v.tw, ci), ax, src.ldw(W_PTW, p.tw, ci), k.dp);
+    v.zsw[ci] = step_clip0(src.ldw(W_ZSW, v.zsw, ci), az, src.ldw(W_PZSW, p.zsw, ci), k.dp);
+    v.ztw[ci] = step_clip0(src.ldw(W_ZTW, v.ztw, ci), az, src.ldw(W_PZTW, p.ztw, ci), k.dp);
   }
-  template <int W>
-  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C(const S &src, long long i, const double (&coef)[W],
                                     const Elem (&)[W], const Con &con,
-                                    AccT &) const {
+                                    AT &) const {
     double x[W], l[W], u[W], px[W];
-    ldv<W>(v.x, i, x);
-    ldv<W>(lb, i, l);
-    ldv<W>(ub, i, u);
-    ldv<W>(p.x, i, px);
+    src.template ld<W>(S_X, v.x, i, x);
+    src.template ld<W>(S_LB, lb, i, l);
+    src.template ld<W>(S_UB, ub, i, u);
+    src.template ld<W>(S_PX, p.x, i, px);
     if (k.use_lower) {
       double zl[W], pzl[W];
-      ldv<W>(v.zl, i, zl);
-      ldv<W>(p.zl, i, pzl);
+      src.template ld<W>(S_ZL, v.zl, i, zl);
+      src.template ld<W>(S_PZL, p.zl, i, pzl);
 #pragma unroll
       for (int q = 0; q < W; q++) zl[q] = step_clip0(zl[q], az, pzl[q], k.dp);
       stv<W>(v.zl, i, zl);
     }
     if (k.use_upper) {
       double zu[W], pzu[W];
-      ldv<W>(v.zu, i, zu);
-      ldv<W>(p.zu, i, pzu);
+      src.template ld<W>(S_ZU, v.zu, i, zu);
+      src.template ld<W>(S_PZU, p.zu, i, pzu);
 #pragma unroll
       for (int q = 0; q < W; q++) zu[q] = step_clip0(zu[q], az, pzu[q], k.dp);
       stv<W>(v.zu, i, zu);
     }
     if (yqn) {
       double gv[W], yv[W];
-      ldv<W>(g, i, gv);
+      src.template ld<W>(S_G, g, i, gv);
 #pragma unroll
       for (int q = 0; q < W; q++) yv[q] = -gv[q];
       for (int j = 0; j < ncon; j++) {
         double a[W];
-        ldv<W>(Acol.p[j], i, a);
+        src.template ldc<W>(j, Acol.p[j], i, a);
 #pragma unroll
         for (int q = 0; q < W; q++) yv[q] = fma(z.v[j], a[q], yv[q]);
       }
@@ -1226,7 +1305,19 @@ struct Update1F : NoStreams {
 // ParOptLSR1::update (QN.cpp:168-170, 641-642).
 // Traffic: reads (3 + c)N + W, writes 2N.   sums: 0 y.y, 1 y.s, 2 s.s
 struct Update2F : NoStreams {
+  static constexpr int SRC = 1;
   static constexpr int NS = 3, NX = 0, NM = 0, NB = 0;
+  enum { S_Y, S_G, S_PX, S_A0 };
+  static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
+  static constexpr int TROWS = 1024;
+  enum { W_ZW, NWSLOTS };
+  int nslots() const { return S_A0 + ncon; }
+  template <class P>
+  __host__ __device__ __forceinline__ void tstreams(P &p_) const {
+    p_.n(S_Y, yqn); p_.n(S_G, g); p_.n(S_PX, px);
+    for (int j = 0; j < ncon; j++) p_.n(S_A0 + j, Acol.p[j]);
+    p_.w(W_ZW, zw);
+  }
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // zw
   struct Elem {};
@@ -1243,28 +1334,27 @@ struct Update2F : NoStreams {
     for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
   }
 
-  template <int W>
-  __device__ __forceinline__ void A_unused() const {}
-  template <int W>
-  __device__ __forceinline__ void A(long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1], AccT *acc) const {}
-  __device__ __forceinline__ void B(long long ci, const double (&)[1], Con &con,
-                                    AccT &) const {
-    con.d[0] = zw[ci];
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void A(const S &, long long, const double (&)[W], Elem (&)[W],
+                                    double (&)[W][1], AT *) const {}
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&)[1], Con &con,
+                                    AT &) const {
+    con.d[0] = src.ldw(W_ZW, zw, ci);
   }
-  template <int W>
-  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C(const S &src, long long i, const double (&coef)[W],
                                     const Elem (&)[W], const Con &con,
-                                    AccT &acc) const {
+                                    AT &acc) const {
     double yv[W], gv[W], pv[W], sv[W];
-    ldv<W>(yqn, i, yv);
-    ldv<W>(g, i, gv);
-    ldv<W>(px, i, pv);
+    src.template ld<W>(S_Y, yqn, i, yv);
+    src.template ld<W>(S_G, g, i, gv);
+    src.template ld<W>(S_PX, px, i, pv);
 #pragma unroll
     for (int q = 0; q < W; q++) yv[q] += gv[q];
     for (int j = 0; j < ncon; j++) {
       double a[W];
-      ldv<W>(Acol.p[j], i, a);
+      src.template ldc<W>(j, Acol.p[j], i, a);
 #pragma unroll
       for (int q = 0; q < W; q++) yv[q] = fma(-z.v[j], a[q], yv[q]);
     }
@@ -1632,6 +1722,7 @@ struct Pass2R1F : NoStreams {
   static constexpr int SRC = 1;
   static constexpr int MINB = PCU_MINB_PASS21;
   enum { S_D1, S_DINV, S_X, S_LB, S_UB, S_G, S_ZL, S_BZL, S_ZU, S_BZU, S_YX, S_YZL, S_YZU, S_V0 };
+  static constexpr int NFIX = S_V0;  // fixed slots; the columns follow
   enum { W_CW, W_D2, W_SW, W_TW, W_ZSW, W_ZTW, W_ZW, W_BSW, W_BTW, W_BZSW, W_BZTW,
          W_YZW, W_YZSW, W_YZTW, W_YSW, W_YTW, NWSLOTS };
   static constexpr int NS = MR, NX = 0, NM = 0, NB = 1, NB2 = 3, NF = 1, FD = 2;
@@ -1706,7 +1797,7 @@ struct Pass2R1F : NoStreams {
     for (int q = 0; q < W; q++) lin[q] = 0.0;
     for (int j = 0; j < ncols; j++) {
       double c[W];
-      src.template ld<W>(S_V0 + j, V.p[j], i, c);
+      src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
       for (int q = 0; q < W; q++) {
         d[q] = fma(alpha.v[j], c[q], d[q]);
@@ -1878,7 +1969,7 @@ struct Pass2R1F : NoStreams {
     for (int j = 0; j < MR; j++) {
       if (j < ncols) {
         double c[W];
-        src.template ld<W>(S_V0 + j, V.p[j], i, c);
+        src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
         for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
       }

@@ -317,6 +317,7 @@ int pcu_ctx_set_param(pcu_ctx *ctx, const char *name, int value) {
   else if (k == "tma_npw") ctx->tma_npw = value;
   else if (k == "tma_min_tiles") ctx->tma_min_tiles = value;
   else if (k == "tma_grid") ctx->tma_grid = value;
+  else if (k == "tma_max_rows") ctx->tma_max_rows = value;
   else return 1;
   return 0;
 }
