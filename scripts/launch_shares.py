@@ -15,11 +15,11 @@ rows = list(csv.DictReader(lines))
 
 
 def short(name):
-    name = name.split("(")[0].replace("void ", "").replace("tile_kernel<", "")
+    name = name.split("(")[0].replace("void ", "").replace("tma_tile_kernel<", "").replace("tile_kernel<", "")
     name = name.rstrip(">")
     if name.startswith("gram"):
         name = "gram_kernel"
-    return name.split("<")[0]
+    return name.split("<")[0].split(",")[0]
 
 
 b = json.load(open(bench))
