@@ -28,10 +28,17 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries
-# exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: libraries that write to file descriptor 1
+# (NCCL prints its version banner there) are sent to stderr, the line goes to the
+# saved descriptor
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 
 from paropt_b200 import configs  # noqa: E402
 
@@ -402,7 +409,7 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -418,8 +425,8 @@ def run_reference(args):
     t0 = time.time()
     res = reference_rate(args.config, ntotal, warmup, args.steps)
     if res is None:
-        print(json.dumps({"impl": "reference",
-                          "unavailable": "oracle/_ref/ref_driver has not been built"}))
+        emit({"impl": "reference",
+              "unavailable": "oracle/_ref/ref_driver has not been built"})
         return
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
@@ -433,7 +440,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():

@@ -46,6 +46,10 @@ def run_big(make, plain):
             os.environ[k] = "1"
         else:
             os.environ.pop(k, None)
+    # staged fused passes (tma_tile_kernel) forced on at this size, small grid
+    ctx.set_param("no_tma_tile", 1 if plain else 0)
+    ctx.set_param("tma_min_tiles", 1)
+    ctx.set_param("tma_grid", 7)
     prob = make()
     ip = InteriorPoint(prob, dict(cfg_big["options"], history_level=2, max_major_iters=13))
     ip.optimize()
