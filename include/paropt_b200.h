@@ -130,6 +130,44 @@ pcu_problem *pcu_problem_create(pcu_ctx *ctx, int nvars, int ncon,
                                 const pcu_problem_callbacks *callbacks);
 void pcu_problem_destroy(pcu_problem *prob);
 
+/* ---- ParOptQuasiDefMat / ParOptQuasiDefBlockMat as a stand-alone object ------
+   (ParOptSparseMat.h:18-104, nwblock = 1; ParOptSparseMat.cpp:41-224).  What
+   ParOptProblem::createQuasiDefMat() returns for a problem whose sparse
+   constraints are the weighting rows of a pcu_weighting descriptor.
+     factor(x, Dinv, Cdiag)  Ew = Cdiag + Aw Dinv Aw^T, inverted; 0 = ok, k > 0 =
+                             zero pivot in (local) row k - 1, < 0 = bad arguments.
+                             Dinv is kept by reference until the next factor().
+     apply3(bx, yx, yw)      [[D, Aw^T], [Aw, -C]] [yx; -yw] = [bx; 0]
+     apply4(bx, bw, yx, yw)  ... = [bx; bw]   (inputs unmodified)                */
+typedef struct pcu_blockmat pcu_blockmat;
+pcu_blockmat *pcu_blockmat_create(pcu_ctx *ctx, int nvars, const pcu_weighting *weighting);
+void pcu_blockmat_destroy(pcu_blockmat *mat);
+int pcu_blockmat_factor(pcu_blockmat *mat, pcu_vec *x, pcu_vec *Dinv, pcu_vec *Cdiag);
+int pcu_blockmat_apply3(pcu_blockmat *mat, pcu_vec *bx, pcu_vec *yx, pcu_vec *yw);
+int pcu_blockmat_apply4(pcu_blockmat *mat, pcu_vec *bx, pcu_vec *bw, pcu_vec *yx,
+                        pcu_vec *yw);
+
+/* ---- ParOptCompactQuasiNewton (ParOptLBFGS / ParOptLSR1) as a stand-alone object
+   (ParOptQuasiNewton.h:32-213): what ParOptInteriorPoint::setQuasiNewton or the
+   trust-region front end is handed.  qn_type "bfgs" | "sr1".
+     update      0 normal, 1 damped, 2 skipped in *update_type (QN.cpp:162-334, 636-747)
+     mult        y = B x            (QN.cpp:390-418, 760-778)
+     mult_add    y += alpha B x     (QN.cpp:432-459, 792-809)
+     compact     returns q; b0, d0[q], M[q*q] column-major, Z[q] borrowed vectors
+                 (QN.cpp:471-487, 821-837); any output may be NULL
+     set_option  "qn_update_type" = skip_negative_curvature | damped_update,
+                 "qn_diag_type" = yty_over_yts | yts_over_sts                     */
+typedef struct pcu_qn pcu_qn;
+pcu_qn *pcu_qn_create(pcu_ctx *ctx, int nvars, const char *qn_type, int subspace);
+void pcu_qn_destroy(pcu_qn *qn);
+int pcu_qn_set_option(pcu_qn *qn, const char *name, const char *value);
+int pcu_qn_reset(pcu_qn *qn);
+int pcu_qn_max_size(pcu_qn *qn);
+int pcu_qn_update(pcu_qn *qn, pcu_vec *s, pcu_vec *y, int *update_type);
+int pcu_qn_mult(pcu_qn *qn, pcu_vec *x, pcu_vec *y);
+int pcu_qn_mult_add(pcu_qn *qn, double alpha, pcu_vec *x, pcu_vec *y);
+int pcu_qn_compact(pcu_qn *qn, double *b0, double *d0, double *M, pcu_vec **Z);
+
 /* Host-array callbacks: the shape of a ParOptProblem whose callbacks work on
    ParOptVec::getArray pointers (ParOptProblem.h:143-172, ParOpt.pyx:520-640).
    The library owns page-locked host mirrors of x, g and the ncon constraint

@@ -91,6 +91,20 @@ SIGNATURES = {
     "pcu_vec_l1norm": (C.c_int, [VP, c_double_p]),
     "pcu_vec_dot": (C.c_int, [VP, VP, c_double_p]),
     "pcu_vec_mdot": (C.c_int, [VP, C.POINTER(VP), C.c_int, c_double_p]),
+    "pcu_blockmat_create": (VP, [VP, C.c_int, C.POINTER(Weighting)]),
+    "pcu_blockmat_destroy": (None, [VP]),
+    "pcu_blockmat_factor": (C.c_int, [VP, VP, VP, VP]),
+    "pcu_blockmat_apply3": (C.c_int, [VP, VP, VP, VP]),
+    "pcu_blockmat_apply4": (C.c_int, [VP, VP, VP, VP, VP]),
+    "pcu_qn_create": (VP, [VP, C.c_int, C.c_char_p, C.c_int]),
+    "pcu_qn_destroy": (None, [VP]),
+    "pcu_qn_set_option": (C.c_int, [VP, C.c_char_p, C.c_char_p]),
+    "pcu_qn_reset": (C.c_int, [VP]),
+    "pcu_qn_max_size": (C.c_int, [VP]),
+    "pcu_qn_update": (C.c_int, [VP, VP, VP, C.POINTER(C.c_int)]),
+    "pcu_qn_mult": (C.c_int, [VP, VP, VP]),
+    "pcu_qn_mult_add": (C.c_int, [VP, C.c_double, VP, VP]),
+    "pcu_qn_compact": (C.c_int, [VP, c_double_p, c_double_p, c_double_p, C.POINTER(VP)]),
     "pcu_vec_scale": (C.c_int, [VP, C.c_double]),
     "pcu_vec_axpy": (C.c_int, [VP, C.c_double, VP]),
     "pcu_vec_device_ptr": (VP, [VP]),

@@ -176,6 +176,92 @@ class PVec:
             self.h = None
 
 
+class QuasiDefBlockMat:
+    """ParOptQuasiDefBlockMat, nwblock = 1 (ParOptSparseMat.h:64-104) for the
+    weighting rows of a `weighting` dict (nwcon, wstart, nw, wstride, coef0,
+    coef_rest, wconst)."""
+
+    def __init__(self, ctx, nvars, weighting=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        w = _lib.Weighting()
+        for k, v in (weighting or {}).items():
+            setattr(w, k, v)
+        self.nvars, self.nwcon = int(nvars), int(w.nwcon)
+        self.h = self.lib.pcu_blockmat_create(ctx.h, int(nvars), C.byref(w))
+        if not self.h:
+            raise RuntimeError("paropt_b200: pcu_blockmat_create failed")
+
+    def factor(self, x, Dinv, Cdiag):
+        """0 = ok, k > 0: zero pivot in row k - 1 (ParOptSparseMat.cpp:41-115)."""
+        rc = int(self.lib.pcu_blockmat_factor(self.h, x.h if x is not None else None,
+                                              Dinv.h, Cdiag.h))
+        if rc < 0:
+            raise RuntimeError("paropt_b200: pcu_blockmat_factor: bad arguments")
+        return rc
+
+    def apply(self, bx, *rest):
+        """apply(bx, yx, yw) / apply(bx, bw, yx, yw) (ParOptSparseMat.cpp:122-190)."""
+        if len(rest) == 2:
+            _check(self.lib.pcu_blockmat_apply3(self.h, bx.h, rest[0].h, rest[1].h), "apply")
+        else:
+            bw, yx, yw = rest
+            _check(self.lib.pcu_blockmat_apply4(self.h, bx.h, bw.h, yx.h, yw.h), "apply")
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_blockmat_destroy(self.h)
+            self.h = None
+
+
+class QuasiNewton:
+    """ParOptLBFGS / ParOptLSR1 (ParOptQuasiNewton.h:76-213; ParOpt.pyx LBFGS/LSR1)."""
+
+    def __init__(self, ctx, nvars, qn_type="bfgs", subspace=10):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.h = self.lib.pcu_qn_create(ctx.h, int(nvars), qn_type.encode(), int(subspace))
+        if not self.h:
+            raise RuntimeError("paropt_b200: pcu_qn_create failed")
+
+    def set_option(self, name, value):
+        _check(self.lib.pcu_qn_set_option(self.h, name.encode(), str(value).encode()),
+               "qn option " + name)
+
+    def reset(self):
+        _check(self.lib.pcu_qn_reset(self.h), "qn reset")
+
+    def getMaxLimitedMemorySize(self):
+        return int(self.lib.pcu_qn_max_size(self.h))
+
+    def update(self, s, y):
+        ut = C.c_int()
+        _check(self.lib.pcu_qn_update(self.h, s.h, y.h, C.byref(ut)), "qn update")
+        return ut.value
+
+    def mult(self, x, y):
+        _check(self.lib.pcu_qn_mult(self.h, x.h, y.h), "qn mult")
+
+    def multAdd(self, alpha, x, y):
+        _check(self.lib.pcu_qn_mult_add(self.h, float(alpha), x.h, y.h), "qn multAdd")
+
+    def getCompactMat(self):
+        """(b0, d0, M, Z): M is q x q (column-major in the library, returned as a
+        numpy array with M[i, j] = entry (i, j)); Z is a list of borrowed PVec."""
+        q = int(self.lib.pcu_qn_compact(self.h, None, None, None, None))
+        b0 = C.c_double()
+        d0 = np.zeros(max(q, 1))
+        M = np.zeros(max(q * q, 1))
+        Z = (C.c_void_p * max(q, 1))()
+        self.lib.pcu_qn_compact(self.h, C.byref(b0), d0.ctypes.data_as(_lib.c_double_p),
+                                M.ctypes.data_as(_lib.c_double_p), Z)
+        Mm = M[:q * q].reshape(q, q).T.copy()
+        return b0.value, d0[:q], Mm, [PVec(self.ctx, handle=Z[i]) for i in range(q)]
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_qn_destroy(self.h)
+            self.h = None
+
+
 def sepquad_params(**kw):
     p = _lib.SepQuadParams()
     defaults = dict(ntotal=1000, ncon=1, nw=0, seed=0, lam_min=1.0, lam_max=1e3,

@@ -376,6 +376,80 @@ struct DiagF : NoStreams {
                                     AccT &) const {}
 };
 
+// ============================================================== BlockFactorF / BlockApplyF
+// ParOptQuasiDefBlockMat with nwblock = 1 as a stand-alone object (SM.cpp:41-224):
+// factor: Cw = 1 / (Cdiag + Aw Dinv Aw^T) (a zero pivot is reported, :91-98);
+// apply:  yw = Cw (bw - Aw Dinv bx) [bw = 0 in the 3-argument form],
+//         yx = Dinv (bx + Aw^T yw)   -- the reference's sign convention (:117-190).
+// Traffic: factor N + 2W; apply 3N + 3W (4-argument form), one pass each.
+struct BlockFactorF : NoStreams {
+  static constexpr int NS = 0, NX = 1, NM = 0, NB = 1;  // max: failing row + 1
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con0 Con;
+  struct Elem {};
+  const double *Dinv, *Cdiag;
+  double *Cw;
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W], Elem (&)[W],
+                                    double (&part)[W][1], AccT *) const {
+    double d[W];
+    ldv<W>(Dinv, i, d);
+#pragma unroll
+    for (int q = 0; q < W; q++) part[q][0] = coef[q] * coef[q] * d[q];
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1], Con &,
+                                    AccT &acc) const {
+    const double e = Cdiag[ci] + sum[0];
+    if (e == 0.0) {
+      acc.x[0] = fmax(acc.x[0], (double)(ci + 1));
+      Cw[ci] = 0.0;
+    } else {
+      Cw[ci] = 1.0 / e;
+    }
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long, const double (&)[W], const Elem (&)[W],
+                                    const Con &, AccT &) const {}
+};
+struct BlockApplyF : NoStreams {
+  static constexpr int NS = 0, NX = 0, NM = 0, NB = 1;
+  typedef Acc<NS, NX, NM> AccT;
+  typedef Con1 Con;  // yw
+  struct Elem {
+    double bx, dinv;
+  };
+  const double *bx, *bw, *Dinv, *Cw;  // bw may be null (3-argument apply)
+  double *yx, *yw;
+  template <int W>
+  __device__ __forceinline__ void A(long long i, const double (&coef)[W], Elem (&e)[W],
+                                    double (&part)[W][1], AccT *) const {
+    double b[W], d[W];
+    ldv<W>(bx, i, b);
+    ldv<W>(Dinv, i, d);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      e[q].bx = b[q];
+      e[q].dinv = d[q];
+      part[q][0] = coef[q] * (d[q] * b[q]);
+    }
+  }
+  __device__ __forceinline__ void B(long long ci, const double (&sum)[1], Con &con,
+                                    AccT &) const {
+    const double r = (bw ? bw[ci] : 0.0) - sum[0];
+    const double v = r * Cw[ci];
+    yw[ci] = v;
+    con.d[0] = v;
+  }
+  template <int W>
+  __device__ __forceinline__ void C(long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con, AccT &) const {
+    double o[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) o[q] = fma(coef[q], con.d[0], e[q].bx) * e[q].dinv;
+    stv<W>(yx, i, o);
+  }
+};
+
 // ============================================================== DiagRhsF
 // DiagF fused with the right-hand side of the iteration's first diagonal solve:
 // d1, d2 of solveKKTDiagSystem (IP.cpp:2091-2139) applied to the KKT residual
