@@ -240,6 +240,9 @@ def run_ours(args):
         ctx.init_distributed()
 
     cfg = configs.get(args.config, args.n)
+    weak = bool(cfg.get("per_gpu")) and args.n is None
+    if weak:  # configs[4]: the named size is per GPU
+        cfg["problem"]["ntotal"] = cfg["problem"]["ntotal"] * world
     ntotal = cfg["problem"]["ntotal"]
     c = cfg["problem"]["ncon"]
     msub = cfg["options"].get("qn_subspace_size", 10)
@@ -396,7 +399,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": done, "warmup": warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if weak else "strong",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s n=%d ncon=%d nwcon=%d qn=%s m=%d" % (
                 args.config, cfg["kind"], ntotal, c, ntotal // 8 if cfg["problem"].get("nw") else 0,

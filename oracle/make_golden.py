@@ -123,6 +123,20 @@ def main():
                 json.dump(data, fp, separators=(",", ":"))
             print(fname, "niter", data["final"]["niter"], data["status"])
         return
+    if "--full" in sys.argv:
+        # the first iterations of the reference at the FULL sizes of BASELINE.json
+        # (C3: n = 64M, W = 8M; C2: n = 16M, c = 10), 8 shim ranks; ~40 GB, minutes
+        for name in ("C2", "C3"):
+            cfg = configs.get(name)
+            cfg["options"] = dict(cfg["options"], max_major_iters=13)
+            data = run_reference(cfg, 8)
+            data["generator"] = "oracle/make_golden.py --full (oracle/_ref/ref_driver, unmodified reference, 8 ranks)"
+            data["log"] = data["log"][:14]
+            fname = "%s_full.json" % name
+            with open(os.path.join(out_dir, fname), "w") as fp:
+                json.dump(data, fp, separators=(",", ":"))
+            print(fname, "niter", data["final"]["niter"], data["status"], flush=True)
+        return
     jobs = [("C1", 1), ("C2", 1), ("C3", 1), ("C4", 1), ("C2", 2), ("C3", 2)]
     for name, nranks in jobs:
         cfg = configs.small(name)

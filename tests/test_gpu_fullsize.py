@@ -1,0 +1,115 @@
+"""GPU parity at the FULL sizes of BASELINE.json (C2: n = 16M, c = 10; C3: n = 64M,
+W = 8M, c = 1), where the bulk-copy staged kernels run on all 148 SMs:
+ (a) the first 12 iterations against the unmodified reference run at the same size
+     (tests/golden/C{2,3}_full.json, made by `python -m oracle.make_golden --full`);
+ (b) size-independent properties: the staged and the register-fed harness give the
+     same history; the KKT step solves the linearised system it was asked to solve
+     (the invariant of the reference's checkKKTStep, IP.cpp:6212-6360); the vector
+     reductions are linear.
+Tolerances: tests/parity.py (RTOL = 1e-10) unless stated."""
+import os
+
+import numpy as np
+import pytest
+
+from paropt_b200 import configs
+from tests.parity import compare_histories, load_golden
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from paropt_b200.api import Context
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a 64 GB+ GPU")
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def run(ctx, cfg, iters, staged=True):
+    from paropt_b200.api import InteriorPoint, problem_from_config
+    ctx.set_param("no_tma_tile", 0 if staged else 1)
+    try:
+        prob = problem_from_config(ctx, cfg)
+        ip = InteriorPoint(prob, dict(cfg["options"], history_level=2, max_major_iters=iters))
+        ip.optimize()
+        hist = ip.history()
+        ip.free()
+        prob.free()
+    finally:
+        ctx.set_param("no_tma_tile", 0)
+    return hist
+
+
+@pytest.mark.parametrize("name", ["C3_full", "C2_full"])
+def test_first_iterations_match_reference_at_full_size(ctx, name):
+    if not os.path.exists(os.path.join(HERE, "golden", name + ".json")):
+        pytest.skip("fixture not generated")
+    gold = load_golden(name)
+    iters = 12
+    hist = run(ctx, gold["config"], iters + 1)
+    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
+    assert n == iters and first is None, (first, worst)
+    for row, rec in zip(gold["log"][:iters], hist):
+        assert row["info"] == rec["info"], (row, rec["iter"])
+
+
+def test_staged_and_register_fed_kernels_agree_at_full_size(ctx):
+    cfg = configs.get("C3")
+    a = run(ctx, cfg, 7, staged=True)
+    b = run(ctx, cfg, 7, staged=False)
+    n, worst, first = compare_histories(b, a, max_iters=6)
+    assert n == 6 and first is None, (first, worst)
+
+
+def test_kkt_step_solves_the_linearised_system_at_full_size(ctx):
+    """After computeKKTStep on the residual r, r - K p (addKKTResStep) must vanish
+    relative to r in every block (checkKKTStep, IP.cpp:6212-6360)."""
+    from paropt_b200.api import InteriorPoint, problem_from_config
+    cfg = configs.get("C3")
+    prob = problem_from_config(ctx, cfg)
+    ip = InteriorPoint(prob, dict(cfg["options"], max_major_iters=1000000))
+    ip.begin()
+    ip.iterate(4)  # a state with quasi-Newton pairs
+    import ctypes as C
+    VARS, RES, UPD = 0, 1, 2
+    mu = ip.getBarrierParameter()
+    lib, h = ip.lib, ip.h
+
+    def norms():
+        v = [C.c_double() for _ in range(4)]
+        assert lib.pcu_ip_res_norm(h, *[C.byref(a) for a in v]) == 0
+        return [a.value for a in v]
+
+    assert lib.pcu_ip_kkt_res(h, VARS, mu, RES) == 0
+    r0 = norms()
+    assert lib.pcu_ip_setup_kkt_diag(h, 1) == 0
+    assert lib.pcu_ip_setup_kkt(h, 1) == 0
+    assert lib.pcu_ip_kkt_step(h, RES, UPD, 1) == 0
+    assert lib.pcu_ip_kkt_res(h, VARS, mu, RES) == 0
+    assert lib.pcu_ip_add_kkt_res_step(h, UPD, RES) == 0
+    r1 = norms()
+    assert max(r1[:3]) <= 1e-9 * max(r0[:3]), (r0, r1)
+    ip.free()
+    prob.free()
+
+
+def test_vector_reductions_are_linear_at_full_size(ctx):
+    from paropt_b200.api import PVec
+    n = 64 * 1024 * 1024 + 5
+    x, y, z = PVec(ctx, n), PVec(ctx, n), PVec(ctx, n)
+    x.set(0.5)
+    y.set(-2.0)
+    z.copyValues(y)
+    z.axpy(3.0, x)  # z = y + 3 x = -0.5
+    assert z.maxabs() == 0.5 and z.l1norm() == 0.5 * n
+    assert abs(z.dot(x) - (y.dot(x) + 3.0 * x.dot(x))) <= 1e-12 * n
+    assert abs(z.norm() - 0.5 * np.sqrt(n)) <= 1e-12 * np.sqrt(n)
+    out = x.mdot([x, y, z])
+    assert np.allclose(out, [0.25 * n, -1.0 * n, -0.25 * n], rtol=1e-13, atol=0.0)
+    for v in (x, y, z):
+        v.free()
