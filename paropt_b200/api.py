@@ -157,6 +157,29 @@ class PVec:
     def device_ptr(self):
         return int(self.lib.pcu_vec_device_ptr(self.h) or 0)
 
+    # Zero-copy device view (torch.as_tensor(v, device="cuda"), cupy.asarray(v)):
+    # the fast path SURVEY.md section 8f-2 asks for instead of PVec's per-element
+    # host indexing (ParOpt.pyx:1082-1159).
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (len(self),), "typestr": "<f8",
+                "data": (self.device_ptr(), False), "version": 3, "strides": None}
+
+    # Host-side element access with the reference's semantics (ParOpt.pyx:1082-
+    # 1159: integers and slices); every access is a device<->host copy of the
+    # touched range's vector, meant for set-up and inspection, not for loops.
+    def __array__(self, dtype=None, copy=None):
+        a = self.to_numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, key):
+        return self.to_numpy()[key]
+
+    def __setitem__(self, key, value):
+        a = self.to_numpy()
+        a[key] = value
+        self.from_numpy(a)
+
     def to_numpy(self):
         out = np.empty(len(self))
         if len(self):
