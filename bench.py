@@ -137,6 +137,8 @@ def kernel_words(name, N, W, c, q):
         "mdot_kernel": None,  # (1 + columns of the chunk) N, see below
     }
     name = name.split("<")[0]
+    if name == "ResFT":  # ResF with has_step / norm_type fixed at compile time
+        name = "ResF"
     return table.get(name)
 
 
@@ -315,7 +317,7 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(name.split("<")[0])
+                traffic = json.load(open(tpath)).get(name.split("<")[0].replace("ResFT", "ResF"))
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak,

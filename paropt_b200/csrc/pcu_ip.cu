@@ -627,7 +627,16 @@ int pcu_ip::computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
   f.norm_type = norm_type_id();
   f.k = kconst();
   RedBuf rb = ctx->redbuf(ResF::NS, ResF::NX, ResF::NM);
-  if (launch_tile(ctx, f, nvars, wd, rb)) return 1;
+  if (!f.has_step && f.norm_type == 0) {
+    // the per-iteration launch: step terms and l1 / l2 bookkeeping compiled out
+    typedef ResFT<0, 0> Fast;
+    static_assert(sizeof(Fast) == sizeof(ResF), "same layout");
+    Fast ff;
+    memcpy((void *)&ff, (const void *)&f, sizeof(ff));
+    if (launch_tile(ctx, ff, nvars, wd, rb)) return 1;
+  } else if (launch_tile(ctx, f, nvars, wd, rb)) {
+    return 1;
+  }
   double out[ResF::NS + ResF::NX + ResF::NM];
   if (ctx->fetch(out)) return 1;
   memcpy(res_sums, out, sizeof(res_sums));

@@ -83,7 +83,13 @@ struct Con1 {  // one broadcast value
 //       constraint), 2 sparse comp product,
 //       3 norm-sum rx, 4 norm-sum rzw, 5..8 l1 of rsw,rtw,rzsw,rztw,
 //       9,10 norm-sum rzl, rzu;   maxima: 0 |rx|, 1 |rzw|, 2 dual parts
-struct ResF : NoStreams {
+// HS / NT fix has_step / norm_type at compile time (-1: run-time value): the
+// per-iteration launch (no step terms, infinity norm) sheds a third of its
+// instructions, and this pass is issue-bound, not bandwidth-bound.
+template <int HS, int NT>
+struct ResFT : NoStreams {
+  __host__ __device__ __forceinline__ int hs() const { return HS < 0 ? has_step : HS; }
+  __host__ __device__ __forceinline__ int nt() const { return NT < 0 ? norm_type : NT; }
   static constexpr int SRC = 1;
   static constexpr int MINB = PCU_MINB_RES;
   enum { S_X, S_LB, S_UB, S_G, S_ZL, S_ZU, S_PX, S_PZL, S_PZU, S_A0 };  // then A, then Z columns
@@ -122,7 +128,7 @@ struct ResF : NoStreams {
     if (k.use_lower) p_(v.zl);
     if (k.use_upper) p_(v.zu);
     for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
-    if (has_step) {
+    if (hs()) {
       p_(p.x);
       if (k.use_lower) p_(p.zl);
       if (k.use_upper) p_(p.zu);
@@ -130,7 +136,7 @@ struct ResF : NoStreams {
     }
   }
 
-  int nslots() const { return S_A0 + ncon + (has_step ? nq : 0); }
+  int nslots() const { return S_A0 + ncon + (hs() ? nq : 0); }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub); p_.n(S_G, g);
@@ -139,7 +145,7 @@ struct ResF : NoStreams {
     for (int j = 0; j < ncon; j++) p_.n(S_A0 + j, Acol.p[j]);
     p_.w(W_ZW, v.zw); p_.w(W_SW, v.sw); p_.w(W_TW, v.tw); p_.w(W_ZSW, v.zsw);
     p_.w(W_ZTW, v.ztw);
-    if (has_step) {
+    if (hs()) {
       p_.n(S_PX, p.x);
       if (k.use_lower) p_.n(S_PZL, p.zl);
       if (k.use_upper) p_.n(S_PZU, p.zu);
@@ -172,7 +178,7 @@ struct ResF : NoStreams {
     double px[W], pzl[W], pzu[W];
 #pragma unroll
     for (int q = 0; q < W; q++) px[q] = pzl[q] = pzu[q] = 0.0;
-    if (has_step) {
+    if (hs()) {
       src.template ld<W>(S_PX, p.x, i, px);
       if (k.use_lower) src.template ld<W>(S_PZL, p.zl, i, pzl);
       if (k.use_upper) src.template ld<W>(S_PZU, p.zu, i, pzu);
@@ -196,7 +202,7 @@ struct ResF : NoStreams {
       if (ml) {
         const double a = dl * zl[q];
         rzl = -(a - k.kappa * mu);
-        if (has_step) rzl -= (dl * pzl[q] + px[q] * zl[q]);
+        if (hs()) rzl -= (dl * pzl[q] + px[q] * zl[q]);
         cp += a;
         cc += 1.0;
         amax = fmax(amax, a);
@@ -205,7 +211,7 @@ struct ResF : NoStreams {
       if (mu_) {
         const double a = du * zu[q];
         rzu = -(a - k.kappa * mu);
-        if (has_step) rzu -= (du * pzu[q] - px[q] * zu[q]);
+        if (hs()) rzu -= (du * pzu[q] - px[q] * zu[q]);
         cp += a;
         cc += 1.0;
         amax = fmax(amax, a);
@@ -238,7 +244,7 @@ struct ResF : NoStreams {
     acc.x[4] = fmax(acc.x[4], fmax(asw, atw));
     acc.m[1] = fmin(acc.m[1], fmin(asw, atw));
     con.d[0] = zw;
-    if (has_step) {
+    if (hs()) {
       const double pzw = src.ldw(W_PZW, p.zw, ci), psw = src.ldw(W_PSW, p.sw, ci), ptw = src.ldw(W_PTW, p.tw, ci);
       const double pzsw = src.ldw(W_PZSW, p.zsw, ci), pztw = src.ldw(W_PZTW, p.ztw, ci);
       rzw += (psw - sum[1]) - ptw;
@@ -259,14 +265,14 @@ struct ResF : NoStreams {
     acc.s[1] += 2.0;
     acc.x[1] = fmax(acc.x[1], fabs(rzw));
     acc.x[2] = fmax(acc.x[2], fmax(fabs(rsw), fabs(rtw)));
-    if (has_step)  // no closed form in mu once the step terms are in
+    if (hs())  // no closed form in mu once the step terms are in
       acc.x[2] = fmax(acc.x[2], fmax(fabs(rzsw), fabs(rztw)));
-    if (norm_type == 1) {
+    if (nt() == 1) {
       acc.s[4] += fabs(rzw);
-    } else if (norm_type == 2) {
+    } else if (nt() == 2) {
       acc.s[4] = fma(rzw, rzw, acc.s[4]);
     }
-    if (norm_type != 0) {
+    if (nt() != 0) {
       acc.s[5] += fabs(rsw);
       acc.s[6] += fabs(rtw);
       acc.s[7] += fabs(rzsw);
@@ -289,12 +295,12 @@ struct ResF : NoStreams {
       acc.x[0] = fmax(acc.x[0], fabs(rx[q]));
       acc.x[3] = fmax(acc.x[3], e[q].amax);
       acc.m[0] = fmin(acc.m[0], e[q].amin);
-      if (has_step) acc.x[2] = fmax(acc.x[2], fmax(fabs(rzl[q]), fabs(rzu[q])));
-      if (norm_type == 1) {
+      if (hs()) acc.x[2] = fmax(acc.x[2], fmax(fabs(rzl[q]), fabs(rzu[q])));
+      if (nt() == 1) {
         acc.s[3] += fabs(rx[q]);
         acc.s[9] += fabs(rzl[q]);
         acc.s[10] += fabs(rzu[q]);
-      } else if (norm_type == 2) {
+      } else if (nt() == 2) {
         acc.s[3] = fma(rx[q], rx[q], acc.s[3]);
         acc.s[9] = fma(rzl[q], rzl[q], acc.s[9]);
         acc.s[10] = fma(rzu[q], rzu[q], acc.s[10]);
@@ -307,6 +313,7 @@ struct ResF : NoStreams {
     }
   }
 };
+typedef ResFT<-1, -1> ResF;
 
 // ============================================================== DiagF
 // setUpKKTDiagSystem, diagonal part (IP.cpp:1864-1927) + ParOptQuasiDefBlockMat

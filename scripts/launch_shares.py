@@ -19,7 +19,7 @@ def short(name):
     name = name.rstrip(">")
     if name.startswith("gram"):
         name = "gram_kernel"
-    return name.split("<")[0].split(",")[0]
+    return name.split("<")[0].split(",")[0].replace("ResFT", "ResF")
 
 
 b = json.load(open(bench))

@@ -44,7 +44,7 @@ for r in rows[2:]:
         vals.append("%.1f" % v)
     bw = (d["dram_rd_MB"] + d["dram_wr_MB"]) / max(d["time_us"], 1e-9) * 1e3
     lines.append("| %s | %s | %.0f |" % (short, " | ".join(vals), bw))
-    key = "gram_kernel" if short.startswith("gram") else short.replace("tma_", "").split("<")[0].split(",")[0]
+    key = "gram_kernel" if short.startswith("gram") else short.replace("tma_", "").split("<")[0].split(",")[0].replace("ResFT", "ResF")
     traffic.setdefault(key, []).append((d["dram_rd_MB"] + d["dram_wr_MB"]) * 1e6)
 open(out_md, "w").write("\n".join(lines) + "\n")
 if out_json:
