@@ -276,7 +276,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ctx.profile(2)
+    if not args.no_kernel_profile:
+        ctx.profile(2)
     launches0 = ctx.kernel_launches()
     it0 = ip.counters()[0]
     ctx.timer_start()
@@ -462,6 +463,8 @@ def main():
     ap.add_argument("--e2e-python", action="store_true",
                     help="drive the end-to-end leg through the Python Problem class")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true",
+                    help="no per-kernel CUDA events in the timed region (roofline = null)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
