@@ -6,6 +6,7 @@
 // it, so that the iterate crosses PCIe device->host and the gradients
 // host->device on every callback.  Counterpart of the problem class in
 // oracle/ref_driver.cpp (same generator, same arithmetic).
+#include <emmintrin.h>
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
@@ -126,24 +127,35 @@ struct HostSepQuad {
     const double hf = q->householder_factor(x);
     std::vector<double> part((size_t)T * (c + 1), 0.0);
     q->parallel([&](int t, long long lo, long long hi) {
-      double f = 0.0;
+      // one pass over x: the objective and the c constraint products together
       const double *lam = q->lam.data(), *b = q->b.data();
-      if (q->p.householder) {
-        const double *vh = q->vh.data();
-        for (long long i = lo; i < hi; i++) {
-          const double y = x[i] - hf * vh[i];
-          f += 0.5 * lam[i] * y * y + b[i] * x[i];
+      const double *vh = q->p.householder ? q->vh.data() : nullptr;
+      constexpr int CB = 16;  // constraints per sweep (c <= 16: a single sweep)
+      double f = 0.0;
+      for (int j0 = 0; j0 < c || j0 == 0; j0 += CB) {
+        const int cb = c - j0 < CB ? c - j0 : CB;
+        const double *aj[CB];
+        double sj[CB];
+        for (int j = 0; j < cb; j++) {
+          aj[j] = q->a[j0 + j].data();
+          sj[j] = 0.0;
         }
-      } else {
-        for (long long i = lo; i < hi; i++) f += (0.5 * lam[i] * x[i] + b[i]) * x[i];
+        for (long long i = lo; i < hi; i++) {
+          const double xi = x[i];
+          if (j0 == 0) {
+            if (vh) {
+              const double y = xi - hf * vh[i];
+              f += 0.5 * lam[i] * y * y + b[i] * xi;
+            } else {
+              f += (0.5 * lam[i] * xi + b[i]) * xi;
+            }
+          }
+          for (int j = 0; j < cb; j++) sj[j] += aj[j][i] * xi;
+        }
+        for (int j = 0; j < cb; j++) part[(size_t)t * (c + 1) + 1 + j0 + j] = sj[j];
+        if (c == 0) break;
       }
       part[(size_t)t * (c + 1)] = f;
-      for (int j = 0; j < c; j++) {
-        const double *aj = q->a[j].data();
-        double s = 0.0;
-        for (long long i = lo; i < hi; i++) s += aj[i] * x[i];
-        part[(size_t)t * (c + 1) + 1 + j] = s;
-      }
     });
     std::vector<double> tot(c + 1, 0.0);
     for (int t = 0; t < T; t++)
@@ -180,7 +192,13 @@ struct HostSepQuad {
       });
     } else {
       q->parallel([&](int, long long lo, long long hi) {
-        for (long long i = lo; i < hi; i++) g[i] = lam[i] * x[i] + b[i];
+        // g is write-only here: streaming stores skip the read-for-ownership
+        long long i = lo;
+        for (; i < hi && (((uintptr_t)(g + i)) & 15); i++) g[i] = lam[i] * x[i] + b[i];
+        for (; i + 2 <= hi; i += 2)
+          _mm_stream_pd(g + i, _mm_set_pd(lam[i + 1] * x[i + 1] + b[i + 1], lam[i] * x[i] + b[i]));
+        for (; i < hi; i++) g[i] = lam[i] * x[i] + b[i];
+        _mm_sfence();
       });
     }
     // the constraints are linear: the gradients are the stored coefficient rows
