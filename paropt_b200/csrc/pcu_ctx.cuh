@@ -129,7 +129,7 @@ struct TmaHostCheck {
   }
 };
 
-#define PCU_TMA_SMEM_BUDGET (214 * 1024)
+#define PCU_TMA_SMEM_BUDGET (222 * 1024)  // + <= 5 KB static: the 227 KB a CTA may hold
 
 // Bulk-copy staged launch of a SRC functor (tma_tile_kernel); returns -1 when
 // the launch does not qualify (small n, generic weighting pattern, too many
