@@ -761,6 +761,17 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
   const long long ncon_elems = (w.mode == 1) ? (long long)w.nwcon * w.nw : 0;
   const int half = (w.mode == 1) ? (w.nw >> 1) : 1;
   const int con_per_tile = (w.mode == 1) ? ROWS / w.nw : 0;
+  const unsigned full0 = tt_smem_u32(tt_full), empty0 = tt_smem_u32(tt_empty);
+  const unsigned smem0 = tt_smem_u32(smem);
+  // this CTA's tiles are blockIdx.x + j gridDim.x, j < ntl_all; the straddling tile
+  // (position js in that sequence, or -1) is left to the global path
+  const int ntl_all =
+      (long long)blockIdx.x < plan.ntiles ? (int)((plan.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  int js = -1;
+  if (plan.tile_skip >= (long long)blockIdx.x &&
+      (plan.tile_skip - (long long)blockIdx.x) % (long long)gridDim.x == 0)
+    js = (int)((plan.tile_skip - (long long)blockIdx.x) / (long long)gridDim.x);
+  const int ntl = ntl_all - (js >= 0 ? 1 : 0);
 
   if (warp < PCU_TMA_NPW) {
     // ------------------------------------------------- producers (warpgroup 0)
@@ -791,17 +802,17 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
       tx_n += __shfl_xor_sync(0xffffffffu, tx_n, o);
       tx_w += __shfl_xor_sync(0xffffffffu, tx_w, o);
     }
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < plan.ntiles; tile += gridDim.x) {
-      if (tile == plan.tile_skip) continue;
-      const int s = (int)(it % S);
-      const unsigned round = (unsigned)(it / S);
-      if (round > 0) tt_mbar_wait(tt_smem_u32(&tt_empty[s]), (round - 1) & 1);
+    int s = 0;
+    unsigned round = 0;
+    for (int kt = 0; kt < ntl; kt++) {
+      const int j = (js >= 0 && kt >= js) ? kt + 1 : kt;
+      const long long tile = blockIdx.x + (long long)j * gridDim.x;
+      if (round > 0) tt_mbar_wait(empty0 + 8u * s, (round - 1) & 1);
       const bool in_con = tile < plan.tiles_con;
-      const unsigned full = tt_smem_u32(&tt_full[s]);
+      const unsigned full = full0 + 8u * s;
       if (lane == 0) tt_mbar_expect_tx(full, tx_n + (in_con ? tx_w : 0u));
       __syncwarp();
-      const unsigned base = tt_smem_u32(smem + (size_t)s * plan.stage_bytes);
+      const unsigned base = smem0 + (unsigned)s * (unsigned)plan.stage_bytes;
       if (as.cnt > 0) {
         if (!as.w0) tt_bulk_g2s(base + as.off0, as.p0 + tile * ROWS, nbytes, full);
         else if (in_con) tt_bulk_g2s(base + as.off0, as.p0 + tile * con_per_tile, wbytes, full);
@@ -810,7 +821,10 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
         if (!as.w1) tt_bulk_g2s(base + as.off1, as.p1 + tile * ROWS, nbytes, full);
         else if (in_con) tt_bulk_g2s(base + as.off1, as.p1 + tile * con_per_tile, wbytes, full);
       }
-      it++;
+      if (++s == S) {
+        s = 0;
+        round++;
+      }
     }
     return;
   }
@@ -822,14 +836,17 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
   const int cw = warp - PCU_TMA_NPW;   // consumer warp index
   const int ncw = plan.groups * WPT;   // consumer warps with a group
   if (cw < ncw) {
+    // group g owns the tiles with sequence index g, g + G, ... and the stages
+    // g + G d (d cycles through the group's ring depth)
     const int g = cw / WPT, wg = cw % WPT;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < plan.ntiles; tile += gridDim.x) {
-      if (tile == plan.tile_skip) continue;
-      const long long my = it++;
-      if ((int)(my % plan.groups) != g) continue;
-      const int s = (int)(my % S);
-      tt_mbar_wait(tt_smem_u32(&tt_full[s]), (unsigned)(my / S) & 1);
+    const int G = plan.groups, depth = S / G;
+    int d = 0;
+    unsigned ph = 0;
+    for (int kt = g; kt < ntl; kt += G) {
+      const int j = (js >= 0 && kt >= js) ? kt + 1 : kt;
+      const long long tile = blockIdx.x + (long long)j * gridDim.x;
+      const int s = g + G * d;
+      tt_mbar_wait(full0 + 8u * s, ph);
       SSrc<ROWS, F::NFIX> src;
       src.nb = smem + (size_t)s * plan.stage_bytes;
       src.wb = src.nb + plan.woff;
@@ -844,7 +861,11 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
       for (int c = 0; c < CHUNKS; c++)
         tile_pair(f, src, w, src.row0 + (c * WPT + wg) * 64 + 2 * lane, ncon_elems, half, acc);
       __syncwarp();
-      if (lane == 0) tt_mbar_arrive(tt_smem_u32(&tt_empty[s]));
+      if (lane == 0) tt_mbar_arrive(empty0 + 8u * s);
+      if (++d == depth) {
+        d = 0;
+        ph ^= 1u;
+      }
     }
     // what the staged loop left out, through the global path
     const GSrc gsrc;
