@@ -887,10 +887,16 @@ __device__ __forceinline__ void stats_constraint_vals(
     const IPConst &k, double tau, long long ci, double sw, double tw, double zsw,
     double ztw, double psw, double ptw, double pzsw, double pztw,
     const double (&sum)[2], AccT_ &acc) {
-    if (psw < 0.0) acc.m[0] = fmin(acc.m[0], -tau * sw / psw);
-    if (ptw < 0.0) acc.m[0] = fmin(acc.m[0], -tau * tw / ptw);
-    if (pzsw < 0.0) acc.m[1] = fmin(acc.m[1], -tau * zsw / pzsw);
-    if (pztw < 0.0) acc.m[1] = fmin(acc.m[1], -tau * ztw / pztw);
+    // as in stats_elements: the quotient is only formed for a candidate that can
+    // lower the running minimum (1e-12 slack: no candidate is lost)
+    if (psw < 0.0 && tau * sw <= -acc.m[0] * psw * (1.0 + 1e-12))
+      acc.m[0] = fmin(acc.m[0], -tau * sw / psw);
+    if (ptw < 0.0 && tau * tw <= -acc.m[0] * ptw * (1.0 + 1e-12))
+      acc.m[0] = fmin(acc.m[0], -tau * tw / ptw);
+    if (pzsw < 0.0 && tau * zsw <= -acc.m[1] * pzsw * (1.0 + 1e-12))
+      acc.m[1] = fmin(acc.m[1], -tau * zsw / pzsw);
+    if (pztw < 0.0 && tau * ztw <= -acc.m[1] * pztw * (1.0 + 1e-12))
+      acc.m[1] = fmin(acc.m[1], -tau * ztw / pztw);
     acc.s[4] += sw * zsw + tw * ztw;
     acc.s[5] += psw * zsw + ptw * ztw;
     acc.s[6] += sw * pzsw + tw * pztw;
@@ -2046,13 +2052,23 @@ struct Pass2R1F : NoStreams {
     double t[W];
 #pragma unroll
     for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[2], e[q].d1);
+    // eight columns at a time: the loads of a batch are issued before the
+    // dependent multiply-adds (this loop held 18 % of the kernel's stall samples)
 #pragma unroll
-    for (int j = 0; j < MR; j++) {
-      if (j < ncols) {
-        double c[W];
-        src.template ldc<W>(j, V.p[j], i, c);
+    for (int j0 = 0; j0 < MR; j0 += 8) {
+      if (j0 < ncols) {
+        double c[8][W];
 #pragma unroll
-        for (int q = 0; q < W; q++) acc.s[j] = fma(t[q], c[q], acc.s[j]);
+        for (int jj = 0; jj < 8; jj++) {
+#pragma unroll
+          for (int q = 0; q < W; q++) c[jj][q] = 0.0;
+          if (j0 + jj < ncols) src.template ldc<W>(j0 + jj, V.p[j0 + jj], i, c[jj]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+#pragma unroll
+          for (int q = 0; q < W; q++) acc.s[j0 + jj] = fma(t[q], c[jj][q], acc.s[j0 + jj]);
+        }
       }
     }
   }
