@@ -1077,7 +1077,18 @@ struct Pass2SF : NoStreams {
     double d[W], di[W];
     src.template ld<W>(S_D1, d1, i, d);
     src.template ld<W>(S_DINV, Dinv, i, di);
-    for (int j = 0; j < ncols; j++) {
+    int j = 0;
+    for (; j + 4 <= ncols; j += 4) {  // four columns per batch: loads first
+      double c[4][W];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) src.template ldc<W>(j + jj, V.p[j + jj], i, c[jj]);
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+#pragma unroll
+        for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j + jj], c[jj][q], d[q]);
+      }
+    }
+    for (; j < ncols; j++) {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
@@ -1882,7 +1893,21 @@ struct Pass2R1F : NoStreams {
     src.template ld<W>(S_DINV, Dinv, i, di);
 #pragma unroll
     for (int q = 0; q < W; q++) lin[q] = 0.0;
-    for (int j = 0; j < ncols; j++) {
+    int j = 0;
+    for (; j + 4 <= ncols; j += 4) {  // four columns per batch: loads first
+      double c[4][W];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) src.template ldc<W>(j + jj, V.p[j + jj], i, c[jj]);
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+#pragma unroll
+        for (int q = 0; q < W; q++) {
+          d[q] = fma(alpha.v[j + jj], c[jj][q], d[q]);
+          lin[q] = fma(beta.v[j + jj], c[jj][q], lin[q]);
+        }
+      }
+    }
+    for (; j < ncols; j++) {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
