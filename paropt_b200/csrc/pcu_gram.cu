@@ -487,7 +487,7 @@ static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
   if (nslabs < grid) grid = (int)nslabs;
   if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
   ctx->prof_begin("gram_kernel");
-  gram_tma_kernel<NT, NWC, NCW><<<grid, PCU_GT_THREADS(NCW), smem, ctx->stream>>>(
+  gram_tma_kernel<NT, NWC, NCW><<<grid, PCU_GT_THREADS_T(NCW), smem, ctx->stream>>>(
       cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, nstages, stage_bytes,
       ctx->d_big_partials, ctx->d_counter, result, ld, d2, rhs_col);
   ctx->prof_end();

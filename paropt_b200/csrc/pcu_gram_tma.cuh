@@ -21,6 +21,8 @@
 // NCW consumer warps of 32 rows each: a slab has 32 NCW rows
 #define PCU_GT_ROWS(NCW) (32 * (NCW))
 #define PCU_GT_THREADS(NCW) (32 * ((NCW) + 1))
+#define PCU_GT_NPW 4  // producer warps of gram_tma_kernel: one warp instruction serialises its lanes' copies
+#define PCU_GT_THREADS_T(NCW) (32 * ((NCW) + PCU_GT_NPW))
 #define PCU_GT_COLB(NCW) (PCU_GT_ROWS(NCW) * 8 + 64)  // bytes per staged column (+64: bank shift)
 #define PCU_GT_MAXSTAGES 6
 
@@ -64,7 +66,7 @@ __device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void *src,
 // Slabs [0, slab_con) lie inside the weighting blocks, slab `slab_skip` (if >= 0)
 // straddles their end and is skipped, slabs up to nslabs are plain.
 template <int NT, int NWC, int NCW>
-__global__ void __launch_bounds__(PCU_GT_THREADS(NCW), 1)
+__global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
     gram_tma_kernel(const ColTable cols, const int m,
                     const double *__restrict__ Dinv,
                     const double *__restrict__ Cw, const WDesc w,
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS(NCW), 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; s++) {
-      gt_mbar_init(gt_smem_u32(&gt_full[s]), 1);
+      gt_mbar_init(gt_smem_u32(&gt_full[s]), PCU_GT_NPW);
       gt_mbar_init(gt_smem_u32(&gt_empty[s]), NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -106,8 +108,27 @@ __global__ void __launch_bounds__(PCU_GT_THREADS(NCW), 1)
 #pragma unroll
   for (int p = 0; p < NP; p++) acc[p][0] = acc[p][1] = 0.0;
 
-  if (warp == NCW) {
-    // ------------------------------------------------------------ producer
+  if (warp >= NCW) {
+    // ----------------------------------------------------------- producers
+    // the m + 3 copies of a slab are dealt over PCU_GT_NPW warps (copy c goes to
+    // warp c % NPW), each warp posts the bytes of its share on the full barrier
+    const int pw = warp - NCW;
+    const int c0 = pw + PCU_GT_NPW * lane;
+    unsigned my_plain = 0, my_con = 0;
+    for (int c = c0; c < m + 3; c += 32 * PCU_GT_NPW) {
+      if (c <= m) {
+        my_plain += col_bytes;
+        my_con += col_bytes;
+      } else if (c == m + 1) {
+        my_con += blk_bytes;
+      } else if (with_d2) {
+        my_con += blk_bytes;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      my_plain += __shfl_xor_sync(0xffffffffu, my_plain, o);
+      my_con += __shfl_xor_sync(0xffffffffu, my_con, o);
+    }
     long long it = 0;
     for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
       if (slab == slab_skip) continue;
@@ -116,15 +137,11 @@ __global__ void __launch_bounds__(PCU_GT_THREADS(NCW), 1)
       if (round > 0) gt_mbar_wait(gt_smem_u32(&gt_empty[s]), (round - 1) & 1);
       const bool in_con = (NWC != 0) && (slab < slab_con);
       const unsigned full = gt_smem_u32(&gt_full[s]);
-      if (lane == 0) {
-        unsigned tx = (unsigned)(m + 1) * col_bytes;
-        if (in_con) tx += blk_bytes * (with_d2 ? 2u : 1u);
-        gt_mbar_expect_tx(full, tx);
-      }
+      if (lane == 0) gt_mbar_expect_tx(full, in_con ? my_con : my_plain);
       __syncwarp();
       const unsigned base = gt_smem_u32(gt_smem + (size_t)s * stage_bytes);
       const long long row0 = slab * ROWS;
-      for (int c = lane; c < m + 3; c += 32) {
+      for (int c = c0; c < m + 3; c += 32 * PCU_GT_NPW) {
         if (c < m) {
           gt_bulk_g2s(base + c * COLB, cols.p[c] + row0, col_bytes, full);
         } else if (c == m) {

@@ -136,7 +136,6 @@ struct ResFT : NoStreams {
     }
   }
 
-  int nslots() const { return S_A0 + ncon + (hs() ? nq : 0); }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub); p_.n(S_G, g);
@@ -491,7 +490,6 @@ struct DiagRhsF : NoStreams {
     if (k.use_upper) p_(v.zu);
     for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
   }
-  int nslots() const { return S_A0 + ncon; }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub); p_.n(S_G, g);
@@ -1049,7 +1047,6 @@ struct Pass2SF : NoStreams {
       if (k.use_upper) p_(y.zu);
     }
   }
-  int nslots() const { return S_V0 + ncols; }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_D1, d1); p_.n(S_DINV, Dinv); p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
@@ -1213,7 +1210,6 @@ struct TrialF : NoStreams {
   static constexpr int NFIX = NSLOTS;  // fixed slots; the columns follow
   static constexpr int TROWS = 1024;
   enum { W_SW, W_TW, W_PSW, W_PTW, NWSLOTS };
-  int nslots() const { return NSLOTS; }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_X, v.x); p_.n(S_PX, p.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
@@ -1297,7 +1293,6 @@ struct Update1F : NoStreams {
   static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
   static constexpr int TROWS = 512;
   enum { W_ZW, W_SW, W_TW, W_ZSW, W_ZTW, W_PZW, W_PSW, W_PTW, W_PZSW, W_PZTW, NWSLOTS };
-  int nslots() const { return S_A0 + (yqn ? ncon : 0); }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_X, v.x); p_.n(S_PX, p.x); p_.n(S_LB, lb); p_.n(S_UB, ub);
@@ -1409,7 +1404,6 @@ struct Update2F : NoStreams {
   static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
   static constexpr int TROWS = 1024;
   enum { W_ZW, NWSLOTS };
-  int nslots() const { return S_A0 + ncon; }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_Y, yqn); p_.n(S_G, g); p_.n(S_PX, px);
@@ -1859,7 +1853,6 @@ struct Pass2R1F : NoStreams {
     }
   }
 
-  int nslots() const { return S_V0 + ncols; }
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_D1, d1); p_.n(S_DINV, Dinv); p_.n(S_X, v.x); p_.n(S_LB, lb); p_.n(S_UB, ub);

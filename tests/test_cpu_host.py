@@ -131,3 +131,26 @@ def test_two_rank_gloo_oracle_matches_reference(tmp_path, name, iters):
         gold = load_golden(gname)
         n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
         assert n == iters and first is None, (gname, first, worst)
+
+
+def test_unpack_output_reads_the_fixed_width_log(tmp_path):
+    """paropt_b200.ParOpt.unpack_output parses the reference's iteration rows
+    (IP.cpp:4777-4801: four %4d, then %7.1e / %12.5e columns, one blank between)."""
+    ParOpt = pytest.importorskip("paropt_b200.ParOpt")
+    rows = [(0, 1, 1, 0, 0.0, 0.0, 0.0, 1.234567e+03, 1.2e+01, 3.4e-02, 5.6e+00, 1.0e-01, 9.9e-01,
+             -1.2e+00, 0.0),
+            (1, 2, 2, 0, 1.0, 9.5e-01, 8.1e-01, -7.65432e-01, 2.2e+00, 1.4e-03, 6.6e-01, 1.0e-01,
+             8.8e-01, -3.4e-01, 1.5e+02)]
+    path = tmp_path / "paropt.out"
+    with open(path, "w") as fp:
+        fp.write("ParOpt: Parameter summary\n\n")
+        fp.write("iter nobj ngrd nhvc   alpha   alphx   alphz         fobj   |opt| |infes|  |dual|      mu"
+                 "    comp   dmerit     rho info\n")
+        for r in rows:
+            fp.write("%4d %4d %4d %4d %7.1e %7.1e %7.1e %12.5e %7.1e %7.1e %7.1e %7.1e %7.1e %8.1e %7.1e %s\n"
+                     % (r + ("skipH",)))
+    names, cols = ParOpt.unpack_output(str(path))
+    assert names[7] == "fobj" and len(cols) == 15
+    assert list(cols[0]) == [0, 1] and list(cols[2]) == [1, 2]
+    assert abs(cols[7][0] - 1.23457e+03) < 1e-2 and abs(cols[7][1] + 7.65432e-01) < 1e-6
+    assert abs(cols[13][1] + 3.4e-01) < 1e-9 and abs(cols[14][1] - 1.5e+02) < 1e-9
