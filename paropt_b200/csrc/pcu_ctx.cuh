@@ -25,7 +25,8 @@ struct pcu_ctx {
   unsigned int *d_counter = nullptr;
   double *d_result = nullptr;   // [PCU_RESULT_CAP]
   double *h_result = nullptr;   // pinned mirror
-  double *d_gather = nullptr;   // [world][PCU_RESULT_CAP] (multi-GPU)
+  double *d_gather = nullptr;   // [world][total] packed partials of all ranks (multi-GPU)
+  double *h_gather = nullptr;   // pinned mirror, combined on the host in rank order
   int result_used = 0;
   std::vector<PendingRed> pending;
 

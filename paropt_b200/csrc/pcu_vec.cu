@@ -40,31 +40,6 @@ NcclApi &nccl_api() {
     }                                                                         \
   } while (0)
 
-// Combine the per-rank copies of the small reduction buffer: slot i of rank r
-// sits at gather[r * stride + i]; ops by range [0,ns) sum, [ns,ns+nx) max, rest
-// min, for each pending descriptor.  Fixed rank order -> identical on all ranks.
-struct CombineDesc {
-  int n;
-  int off[32], ns[32], nx[32], nm[32];
-};
-__global__ void combine_ranks_kernel(const double *gather, double *result,
-                                     int world, int stride, CombineDesc d) {
-  for (int k = 0; k < d.n; k++) {
-    const int nr = d.ns[k] + d.nx[k] + d.nm[k];
-    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
-      const int idx = d.off[k] + i;
-      double v = gather[idx];
-      for (int r = 1; r < world; r++) {
-        const double p = gather[(size_t)r * stride + idx];
-        if (i < d.ns[k]) v += p;
-        else if (i < d.ns[k] + d.nx[k]) v = fmax(v, p);
-        else v = fmin(v, p);
-      }
-      result[idx] = v;
-    }
-  }
-}
-
 RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
   RedBuf rb;
   rb.prefetch = 0;
@@ -86,25 +61,35 @@ int pcu_ctx::fetch(double *out) {
   const int total = result_used;
   if (total > 0) {
     if (world > 1) {
+      // one all-gather of the `total` packed partials; the fixed-rank-order combine
+      // runs on the host of every rank (identical data, identical order: identical
+      // results) -- no combine kernel between the collective and the copy
       NcclApi &api = nccl_api();
-      PCU_NCCL_OK(api.AllGather(d_result, d_gather, PCU_RESULT_CAP, ncclFloat64,
-                                comm, stream));
-      CombineDesc d;
-      d.n = (int)pending.size();
-      for (int k = 0; k < d.n; k++) {
-        d.off[k] = pending[k].offset;
-        d.ns[k] = pending[k].ns;
-        d.nx[k] = pending[k].nx;
-        d.nm[k] = pending[k].nm;
-      }
-      combine_ranks_kernel<<<1, 128, 0, stream>>>(d_gather, d_result, world,
-                                                  PCU_RESULT_CAP, d);
-      launches++;
+      PCU_NCCL_OK(api.AllGather(d_result, d_gather, (size_t)total, ncclFloat64, comm, stream));
+      PCU_CUDA_OK(cudaMemcpyAsync(h_gather, d_gather, (size_t)world * total * sizeof(double),
+                                  cudaMemcpyDeviceToHost, stream));
+    } else {
+      PCU_CUDA_OK(cudaMemcpyAsync(h_result, d_result, total * sizeof(double),
+                                  cudaMemcpyDeviceToHost, stream));
     }
-    PCU_CUDA_OK(cudaMemcpyAsync(h_result, d_result, total * sizeof(double),
-                                cudaMemcpyDeviceToHost, stream));
   }
   PCU_CUDA_OK(cudaStreamSynchronize(stream));
+  if (world > 1 && total > 0) {
+    for (const PendingRed &pr : pending) {
+      const int nr = pr.ns + pr.nx + pr.nm;
+      for (int i = 0; i < nr; i++) {
+        const int idx = pr.offset + i;
+        double v = h_gather[idx];
+        for (int r = 1; r < world; r++) {
+          const double p = h_gather[(size_t)r * total + idx];
+          if (i < pr.ns) v += p;
+          else if (i < pr.ns + pr.nx) v = fmax(v, p);
+          else v = fmin(v, p);
+        }
+        h_result[idx] = v;
+      }
+    }
+  }
   if (out && total > 0) memcpy(out, h_result, total * sizeof(double));
   result_used = 0;
   pending.clear();
@@ -254,6 +239,7 @@ void pcu_ctx_destroy(pcu_ctx *ctx) {
   cudaFree(ctx->d_result);
   cudaFreeHost(ctx->h_result);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
   if (ctx->d_big) cudaFree(ctx->d_big);
   if (ctx->h_big) cudaFreeHost(ctx->h_big);
   if (ctx->d_big_partials) cudaFree(ctx->d_big_partials);
@@ -295,6 +281,8 @@ int pcu_ctx_init_comm(pcu_ctx *ctx, const unsigned char id128[128], int rank,
   ctx->world = world_size;
   PCU_CUDA_OK(cudaMalloc(&ctx->d_gather,
                          sizeof(double) * PCU_RESULT_CAP * world_size));
+  PCU_CUDA_OK(cudaMallocHost(&ctx->h_gather,
+                             sizeof(double) * PCU_RESULT_CAP * world_size));
   return 0;
 }
 
