@@ -154,3 +154,15 @@ def test_unpack_output_reads_the_fixed_width_log(tmp_path):
     assert list(cols[0]) == [0, 1] and list(cols[2]) == [1, 2]
     assert abs(cols[7][0] - 1.23457e+03) < 1e-2 and abs(cols[7][1] + 7.65432e-01) < 1e-6
     assert abs(cols[13][1] + 3.4e-01) < 1e-9 and abs(cols[14][1] - 1.5e+02) < 1e-9
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/paropt_b200.h must compile as C99
+    (no C++ or CUDA types in the signatures) and every prototype must link."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "paropt_b200.h"\n'
+                   "int main(void) { return pcu_version() == 0; }\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                    "-I", os.path.join(root, "include"), str(src)], check=True)
