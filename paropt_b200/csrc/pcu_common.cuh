@@ -49,6 +49,7 @@ struct WDesc {
   long long wstart;
   long long wend;    // wstart + nwcon * wstride
   double coef0, coef_rest, wconst;
+  int nw_log2;       // mode 1: nw is a power of two (constraint of element i: i >> nw_log2)
 };
 
 // ---------------------------------------------------------------- vector I/O
@@ -300,41 +301,34 @@ struct GSrc {
 };
 template <int ROWS, int NFIX>
 struct SSrc {
-  const unsigned char *nb;  // N-slots: [compact slot][ROWS] doubles
-  const unsigned char *wb;  // W-slots: [slot][wpitch bytes]
-  long long row0, con0;     // first element / first weighting constraint of the tile
+  unsigned nb;       // shared-space address of the stage: N-slots [compact slot][ROWS] doubles
+  unsigned wb;       // ... of its W-slots: [slot][wpitch bytes]
+  long long row0, con0;  // first element / first weighting constraint of the tile
   int wpitch;
-  unsigned long long nmap[3];  // fixed slot id -> compact slot, one byte each
-  int col_base;                // compact slot of column 0 (slot id NFIX)
+  unsigned off[NFIX > 0 ? NFIX : 1];  // byte offset of each fixed slot id (from the launch plan)
+  unsigned col0;                      // byte offset of column 0 (slot id NFIX)
+  template <int W>
+  __device__ __forceinline__ void lds(unsigned a, double (&out)[W]) const {
+    if (W == 2) {
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[W - 1]) : "r"(a));
+    } else {
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(out[0]) : "r"(a));
+    }
+  }
   template <int W>
   __device__ __forceinline__ void ld(int slot, const double *, long long i,
                                      double (&out)[W]) const {
-    const int cs = slot < NFIX ? (int)((nmap[(slot >> 3) % 3] >> ((slot & 7) * 8)) & 0xffull)
-                               : col_base + (slot - NFIX);
-    const double *q = reinterpret_cast<const double *>(nb + cs * (ROWS * 8)) + (int)(i - row0);
-    if (W == 2) {
-      const double2 v = *reinterpret_cast<const double2 *>(q);
-      out[0] = v.x;
-      out[W - 1] = v.y;
-    } else {
-      out[0] = q[0];
-    }
+    lds<W>(nb + off[slot] + (unsigned)(i - row0) * 8u, out);
   }
-  template <int W>
+  template <int W>  // column j of the functor's column table
   __device__ __forceinline__ void ldc(int j, const double *, long long i,
                                       double (&out)[W]) const {
-    const double *q =
-        reinterpret_cast<const double *>(nb + (col_base + j) * (ROWS * 8)) + (int)(i - row0);
-    if (W == 2) {
-      const double2 v = *reinterpret_cast<const double2 *>(q);
-      out[0] = v.x;
-      out[W - 1] = v.y;
-    } else {
-      out[0] = q[0];
-    }
+    lds<W>(nb + col0 + (unsigned)j * (ROWS * 8u) + (unsigned)(i - row0) * 8u, out);
   }
   __device__ __forceinline__ double ldw(int slot, const double *, long long ci) const {
-    return *(reinterpret_cast<const double *>(wb + slot * wpitch) + (int)(ci - con0));
+    double v[1];
+    lds<1>(wb + (unsigned)(slot * wpitch) + (unsigned)(ci - con0) * 8u, v);
+    return v[0];
   }
 };
 
@@ -514,14 +508,14 @@ __device__ __forceinline__ void tile_pair(const F &f, const S &src, const WDesc 
   con.zero();
   if constexpr (F::SRC) {
     if constexpr (F::HASP) {
-      if (in_con) f.P(src, i / w.nw, con);
+      if (in_con) f.P(src, (i >> w.nw_log2), con);
       f.template AP<2>(src, i, coef, e, part, &acc, con);
     } else {
       f.template A<2>(src, i, coef, e, part, &acc);
     }
   } else {
     if constexpr (F::HASP) {
-      if (in_con) f.P(i / w.nw, con);
+      if (in_con) f.P((i >> w.nw_log2), con);
       f.template AP<2>(i, coef, e, part, &acc, con);
     } else {
       f.template A<2>(i, coef, e, part, &acc);
@@ -540,8 +534,8 @@ __device__ __forceinline__ void tile_pair(const F &f, const S &src, const WDesc 
       }
     }
     if (in_con && lane == lead) {
-      if constexpr (F::SRC) f.B(src, i / w.nw, sum, con, acc);
-      else f.B(i / w.nw, sum, con, acc);
+      if constexpr (F::SRC) f.B(src, (i >> w.nw_log2), sum, con, acc);
+      else f.B((i >> w.nw_log2), sum, con, acc);
     }
     if (F::Con::ND > 0) {
 #pragma unroll
@@ -563,8 +557,8 @@ __device__ __forceinline__ void tile_pair(const F &f, const S &src, const WDesc 
         for (int b = 0; b < F::NB2; b++) sum2[b] += shfl_xor_d(sum2[b], o);
       }
       if (in_con && lane == lead) {
-        if constexpr (F::SRC) f.E(src, i / w.nw, sum2, con, acc);
-        else f.E(i / w.nw, sum2, con, acc);
+        if constexpr (F::SRC) f.E(src, (i >> w.nw_log2), sum2, con, acc);
+        else f.E((i >> w.nw_log2), sum2, con, acc);
       }
       if constexpr (F::NF > 0)
         con.d[F::FD] = __shfl_sync(0xffffffffu, con.d[F::FD], lead);
@@ -652,6 +646,7 @@ struct TmaPlan {
   int npw;              // producer warps
   int col_base;         // compact slot of the first column
   unsigned long long nmap[3];  // fixed slot id -> compact slot, one byte each
+  unsigned noff[24];           // the same as byte offsets inside a stage
 };
 
 #define PCU_TMA_NPW 4        // producer warps = warpgroup 0 (the first plan.npw of them issue copies)
@@ -848,15 +843,14 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
       const int s = g + G * d;
       tt_mbar_wait(full0 + 8u * s, ph);
       SSrc<ROWS, F::NFIX> src;
-      src.nb = smem + (size_t)s * plan.stage_bytes;
-      src.wb = src.nb + plan.woff;
+      src.nb = smem0 + (unsigned)s * (unsigned)plan.stage_bytes;
+      src.wb = src.nb + (unsigned)plan.woff;
       src.row0 = tile * ROWS;
       src.con0 = tile * con_per_tile;
       src.wpitch = plan.wpitch;
-      src.nmap[0] = plan.nmap[0];
-      src.nmap[1] = plan.nmap[1];
-      src.nmap[2] = plan.nmap[2];
-      src.col_base = plan.col_base;
+#pragma unroll
+      for (int q = 0; q < F::NFIX; q++) src.off[q] = plan.noff[q];
+      src.col0 = (unsigned)plan.col_base * (ROWS * 8u);
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; c++)
         tile_pair(f, src, w, src.row0 + (c * WPT + wg) * 64 + 2 * lane, ncon_elems, half, acc);

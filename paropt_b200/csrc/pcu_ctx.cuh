@@ -155,8 +155,10 @@ int pcu_launch_tile_tma(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
   f.tstreams(chk);
   int nslots = 0;  // live fixed slots, compacted, then the columns
   plan.nmap[0] = plan.nmap[1] = plan.nmap[2] = 0ull;
+  for (int i = 0; i < 24; i++) plan.noff[i] = 0u;
   for (int i = 0; i < F::NFIX; i++) {
     plan.nmap[i >> 3] |= (unsigned long long)nslots << ((i & 7) * 8);
+    plan.noff[i] = (unsigned)nslots * (unsigned)(ROWS * 8);
     if (chk.fixed[i]) nslots++;
   }
   plan.col_base = nslots;

@@ -29,6 +29,8 @@ WDesc pcu_make_wdesc(const pcu_weighting &w, int nvars) {
     const bool aligned = w.wstart == 0 && w.wstride == w.nw &&
                          (long long)w.nwcon * w.nw <= (long long)nvars;
     d.mode = (pow2 && aligned) ? 1 : 2;
+    if (d.mode == 1)
+      for (int b = w.nw; b > 1; b >>= 1) d.nw_log2++;
   }
   return d;
 }
