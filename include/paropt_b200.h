@@ -167,6 +167,9 @@ int pcu_qn_update(pcu_qn *qn, pcu_vec *s, pcu_vec *y, int *update_type);
 int pcu_qn_mult(pcu_qn *qn, pcu_vec *x, pcu_vec *y);
 int pcu_qn_mult_add(pcu_qn *qn, double alpha, pcu_vec *x, pcu_vec *y);
 int pcu_qn_compact(pcu_qn *qn, double *b0, double *d0, double *M, pcu_vec **Z);
+/* ParOptInteriorPoint::setQuasiNewton (IP.cpp:1193): the optimizer uses (and, with
+   use_quasi_newton_update, updates) the caller's object; NULL restores its own.  */
+int pcu_ip_set_quasi_newton(pcu_ip *ip, pcu_qn *qn);
 
 /* Host-array callbacks: the shape of a ParOptProblem whose callbacks work on
    ParOptVec::getArray pointers (ParOptProblem.h:143-172, ParOpt.pyx:520-640).

@@ -105,6 +105,7 @@ SIGNATURES = {
     "pcu_qn_mult": (C.c_int, [VP, VP, VP]),
     "pcu_qn_mult_add": (C.c_int, [VP, C.c_double, VP, VP]),
     "pcu_qn_compact": (C.c_int, [VP, c_double_p, c_double_p, c_double_p, C.POINTER(VP)]),
+    "pcu_ip_set_quasi_newton": (C.c_int, [VP, VP]),
     "pcu_vec_scale": (C.c_int, [VP, C.c_double]),
     "pcu_vec_axpy": (C.c_int, [VP, C.c_double, VP]),
     "pcu_vec_device_ptr": (VP, [VP]),

@@ -482,6 +482,13 @@ class InteriorPoint:
         if rc != 0:  # ParOpt.pyx:411-413 raises ValueError for unknown options
             raise ValueError("unknown or out-of-range option %s=%r" % (name, value))
 
+    def setQuasiNewton(self, qn):
+        """ParOptInteriorPoint::setQuasiNewton (IP.cpp:1193): use the caller's
+        QuasiNewton object (None: the optimizer's own)."""
+        _check(self.lib.pcu_ip_set_quasi_newton(self.h, qn.h if qn is not None else None),
+               "setQuasiNewton")
+        self._qn_ref = qn  # keep it alive
+
     def optimize(self):
         _check(self.lib.pcu_ip_optimize(self.h), "optimize")
 

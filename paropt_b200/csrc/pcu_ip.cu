@@ -338,7 +338,7 @@ pcu_ip::~pcu_ip() {
   pcu_vec *single[] = {lb, ub, g, Dinv, Cw, d1, d2, t1, s_qn, y_qn, rx, rsw, rtw};
   for (auto v : single) pcu_vec_destroy(v);
   for (auto v : Ac) pcu_vec_destroy(v);
-  delete qn;
+  if (!qn_external) delete qn;
   if (outfp && outfp != stdout) fclose(outfp);
   if (ev_it0) cudaEventDestroy(ev_it0);
   if (ev_it1) cudaEventDestroy(ev_it1);
@@ -429,12 +429,13 @@ int pcu_ip::norm_type_id() const {
 }
 
 int pcu_ip::ensure_qn() {  // IP.cpp:263-290
+  if (qn_external) return qn ? 0 : 1;  // supplied through pcu_ip_set_quasi_newton
   if (qn && qn_built_type == opt.qn_type && qn_built_size == opt.qn_subspace_size) {
     qn->damped = (opt.qn_update_type == "damped_update");
     qn->diag_yts_over_sts = (opt.qn_diag_type == "yts_over_sts");
     return 0;
   }
-  delete qn;
+  if (!qn_external) delete qn;
   qn = nullptr;
   qn_built_type = opt.qn_type;
   qn_built_size = opt.qn_subspace_size;

@@ -131,6 +131,7 @@ struct pcu_ip {
   double fobj = 0.0;
   std::vector<double> gamma_s, gamma_t;
   QuasiNewton *qn = nullptr;
+  int qn_external = 0;  // qn belongs to a pcu_qn handle (setQuasiNewton, IP.cpp:1193): not owned
   std::string qn_built_type;
   int qn_built_size = -1;
 

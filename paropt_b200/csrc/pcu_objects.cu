@@ -185,4 +185,25 @@ int pcu_qn_compact(pcu_qn *h, double *b0, double *d0, double *M, pcu_vec **Z) {
   return q;
 }
 
+// ParOptInteriorPoint::setQuasiNewton (IP.cpp:1193-1235): the optimizer uses -- and,
+// with use_quasi_newton_update, updates -- the caller's object; NULL restores the
+// optimizer's own (options qn_type / qn_subspace_size).  The handle must outlive
+// its use by the optimizer.
+int pcu_ip_set_quasi_newton(pcu_ip *ip, pcu_qn *h) {
+  if (!ip) return 1;
+  if (!ip->qn_external) delete ip->qn;
+  ip->qn = nullptr;
+  ip->qn_external = 0;
+  ip->qn_built_size = -1;
+  if (h) {
+    if (h->q.n != ip->nvars || ip->ncon + h->q.max_size() > PCU_MAX_COLS) {
+      fprintf(stderr, "paropt_b200: pcu_ip_set_quasi_newton: size mismatch\n");
+      return 1;
+    }
+    ip->qn = &h->q;
+    ip->qn_external = 1;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -136,3 +136,26 @@ def test_quasi_newton_object(ctx, kind, n, m, updates):
     assert np.array_equal(dy.to_numpy(), x)  # B = I after reset (QN.cpp:132-146)
     for o in (dx, dy, dacc, qn):
         o.free()
+
+
+def test_interior_point_with_a_supplied_quasi_newton_object(ctx):
+    """ParOptInteriorPoint::setQuasiNewton (IP.cpp:1193-1235): with the caller's
+    L-BFGS object the optimizer must walk the reference's history exactly as with
+    its own, and leave the pairs it gathered in the caller's object."""
+    from paropt_b200.api import InteriorPoint, QuasiNewton, problem_from_config
+    from tests.parity import compare_histories, load_golden
+    gold = load_golden("C2_small")
+    cfg = gold["config"]
+    prob = problem_from_config(ctx, cfg)
+    qn = QuasiNewton(ctx, prob.nvars, "bfgs", cfg["options"]["qn_subspace_size"])
+    ip = InteriorPoint(prob, dict(cfg["options"], history_level=2))
+    ip.setQuasiNewton(qn)
+    ip.optimize()
+    n, worst, first = compare_histories(gold["history"], ip.history())
+    assert first is None and n == len(gold["history"]), (first, worst)
+    b0, d0, M, Z = qn.getCompactMat()
+    assert len(Z) == 2 * cfg["options"]["qn_subspace_size"] and b0 > 0.0
+    ip.setQuasiNewton(None)
+    ip.free()
+    qn.free()
+    prob.free()
