@@ -111,9 +111,58 @@ def variant_config(base, overrides, n):
     return cfg
 
 
+def parse_tr_log(path):
+    """Iteration rows of the reference's trust-region log (ParOptTrustRegion.cpp:1433-1445:
+    %5d %12.5e, eleven %9.2e, time, info)."""
+    keys = ["fobj", "infeas", "l1", "linfty", "dx", "tr", "rho", "model_red", "zav", "zmax",
+            "gav", "gmax"]
+    rows = []
+    for line in open(path):
+        parts = line.split()
+        if len(parts) >= 14 and parts[0].isdigit():
+            try:
+                vals = [float(v) for v in parts[1:13]]
+            except ValueError:
+                continue
+            row = {"iter": int(parts[0]), "info": " ".join(parts[14:])}
+            row.update(dict(zip(keys, vals)))
+            rows.append(row)
+    return rows
+
+
+def run_reference_tr(cfg):
+    """The reference's ParOptOptimizer with algorithm = tr (sl1qp penalty method, the
+    configuration of examples/rosenbrock/rosenbrock.cpp:234-242) on a named workload:
+    centre points at full precision from the writeOutput hook + the rows of its log."""
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", PCU_SHIM_NP="1")
+    with tempfile.TemporaryDirectory() as tmp:
+        hist = os.path.join(tmp, "hist.jsonl")
+        trlog = os.path.join(tmp, "paropt.tr")
+        cmd = [DRIVER] + driver_args(cfg) + ["algorithm=tr", "hist=" + hist, "tr_log=" + trlog,
+                                             "log=" + os.path.join(tmp, "paropt.out")]
+        subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
+        recs = [json.loads(line) for line in open(hist)]
+        rows = parse_tr_log(trlog)
+    return {"config": cfg, "algorithm": "tr", "centres": [r for r in recs if "tr_iter" in r],
+            "final": [r for r in recs if "final" in r][0], "log": rows}
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--tr" in sys.argv:
+        # SURVEY.md section 8f-1 (next row): histories of the reference's trust-region
+        # front end, for the oracle / CUDA port of ParOptTrustRegion to be pinned against
+        jobs = [("C1_tr", configs.small("C1"), dict(barrier_strategy="mehrotra")),
+                ("C2_tr_small", configs.get("C2", 4000), dict(barrier_strategy="mehrotra"))]
+        for fname, cfg, extra in jobs:
+            cfg["options"] = dict(cfg["options"], **extra)
+            data = run_reference_tr(cfg)
+            data["generator"] = "oracle/make_golden.py --tr (oracle/_ref/ref_driver algorithm=tr, unmodified reference)"
+            with open(os.path.join(out_dir, fname + ".json"), "w") as fp:
+                json.dump(data, fp, separators=(",", ":"))
+            print(fname, "tr iterations", len(data["log"]), "centres", len(data["centres"]))
+        return
     if "--variants" in sys.argv:
         for label, base, overrides, n in VARIANTS:
             data = run_reference(variant_config(base, overrides, n))

@@ -42,6 +42,7 @@
 // the access-specifier override below only touches the reference's classes.
 #define private public
 #include "ParOptInteriorPoint.h"
+#include "ParOptOptimizer.h"
 #undef private
 
 // ---------------------------------------------------------------------------
@@ -81,6 +82,7 @@ class HistoryProblem : public ParOptProblem {
     hist = NULL;
     have_prev = 0;
     callback_time = 0.0;
+    tr_mode = 0;
   }
   void writeOutput(int iter, ParOptVec *xvec);
 
@@ -89,6 +91,7 @@ class HistoryProblem : public ParOptProblem {
   std::vector<double> xprev;
   int have_prev;
   double callback_time;
+  int tr_mode;  // algorithm=tr: writeOutput is the trust-region hook (ParOptTrustRegion.cpp:1559)
 };
 
 static double vsum(ParOptVec *v) {
@@ -108,9 +111,25 @@ static void print_arr(FILE *fp, const char *name, const double *a, int n) {
 }
 
 void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
-  if (!ip) return;
   int rank;
   MPI_Comm_rank(comm, &rank);
+  if (tr_mode) {
+    // one record per trust-region iteration: the centre point x_k at full precision
+    // (checksums + the first entries); the scalars of the iteration are in the
+    // reference's own trust-region log (tr_output_file), parsed by make_golden.py
+    double *x;
+    int n = xvec->getArray(&x);
+    double xs = vsum(xvec), xn = xvec->norm(), xm = xvec->maxabs();
+    if (rank == 0 && hist) {
+      fprintf(hist, "{\"tr_iter\": %d, \"xsum\": %.17g, \"xnorm\": %.17g, \"xmaxabs\": %.17g, ",
+              iter, xs, xn, xm);
+      print_arr(hist, "xhead", x, n < 8 ? n : 8);
+      fprintf(hist, "}\n");
+      fflush(hist);
+    }
+    return;
+  }
+  if (!ip) return;
   ParOptInteriorPoint::ParOptVars &v = ip->variables;
 
   // Same calls, same order as the top of the major loop
@@ -486,6 +505,7 @@ int main(int argc, char *argv[]) {
   MPI_Comm_rank(comm, &rank);
 
   std::string problem = "sepquad", hist_path, out_path = "/dev/null";
+  std::string algorithm = "ip", tr_log = "/dev/null";
   std::string dump_x;
   SepQuadParams p;
   std::vector<std::pair<std::string, std::string> > opts;
@@ -497,6 +517,8 @@ int main(int argc, char *argv[]) {
     else if (strncmp(a, "hist=", 5) == 0) hist_path = a + 5;
     else if (strncmp(a, "log=", 4) == 0) out_path = a + 4;
     else if (strncmp(a, "dump_x=", 7) == 0) dump_x = a + 7;
+    else if (strncmp(a, "algorithm=", 10) == 0) algorithm = a + 10;
+    else if (strncmp(a, "tr_log=", 7) == 0) tr_log = a + 7;
     else if (arg_d(a, "n", &v)) { p.ntotal = (long)v; rosen_n = (int)v; }
     else if (arg_d(a, "ncon", &v)) p.ncon = (int)v;
     else if (arg_d(a, "nw", &v)) p.nw = (int)v;
@@ -536,10 +558,17 @@ int main(int argc, char *argv[]) {
   prob->incref();
 
   ParOptOptions *options = new ParOptOptions(comm);
-  ParOptInteriorPoint::addDefaultOptions(options);
+  if (algorithm == "tr") ParOptOptimizer::addDefaultOptions(options);
+  else ParOptInteriorPoint::addDefaultOptions(options);
   options->incref();
   options->setOption("output_file", out_path.c_str());
   options->setOption("write_output_frequency", 1);
+  if (algorithm == "tr") {
+    options->setOption("algorithm", "tr");
+    options->setOption("tr_output_file", tr_log.c_str());
+    options->setOption("tr_write_output_frequency", 1);
+    options->setOption("output_level", 0);
+  }
   for (size_t i = 0; i < opts.size(); i++) {
     const char *name = opts[i].first.c_str();
     const char *val = opts[i].second.c_str();
@@ -560,6 +589,32 @@ int main(int argc, char *argv[]) {
     } else if (rank == 0) {
       fprintf(stderr, "ref_driver: unknown option %s\n", name);
     }
+  }
+
+  if (algorithm == "tr") {
+    // ParOptOptimizer with the trust-region front end (ParOptOptimizer.cpp:102-175,
+    // the configuration of examples/rosenbrock/rosenbrock.cpp:234-242)
+    prob->tr_mode = 1;
+    if (rank == 0 && !hist_path.empty()) prob->hist = fopen(hist_path.c_str(), "w");
+    ParOptOptimizer *opt = new ParOptOptimizer(prob, options);
+    opt->incref();
+    double t0 = MPI_Wtime();
+    opt->optimize();
+    double t1 = MPI_Wtime();
+    ParOptVec *x;
+    opt->getOptimizedPoint(&x, NULL, NULL, NULL, NULL);
+    double xs = vsum(x), xn = x->norm();
+    if (rank == 0) {
+      FILE *fp = prob->hist ? prob->hist : stdout;
+      fprintf(fp, "{\"final\": 1, \"xsum\": %.17g, \"xnorm\": %.17g, \"time_s\": %.6f}\n", xs,
+              xn, t1 - t0);
+      if (prob->hist) fclose(prob->hist);
+    }
+    opt->decref();
+    options->decref();
+    prob->decref();
+    MPI_Finalize();
+    return 0;
   }
 
   ParOptInteriorPoint *ip = new ParOptInteriorPoint(prob, options);
