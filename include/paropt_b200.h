@@ -91,6 +91,16 @@ int pcu_vec_axpy(pcu_vec *y, double alpha, pcu_vec *x);     /* :194 axpy        
 double *pcu_vec_device_ptr(pcu_vec *v);
 int pcu_vec_to_host(pcu_vec *v, double *host, int n);   /* D2H, synchronous */
 int pcu_vec_from_host(pcu_vec *v, const double *host, int n); /* H2D, sync  */
+/* getArray for reference code that loops over raw pointers (the ~25 private
+   methods of ParOptInteriorPoint, ParOptTrustRegion, user callbacks): a context
+   with pcu_ctx_set_param(ctx, "managed_vectors", 1) allocates every vector in
+   unified memory.  pcu_vec_host_ptr synchronises the context's stream and returns
+   a pointer the host may read AND write; the vector is marked host-touched and is
+   moved back to the device (prefetch on the context's stream) by the next library
+   call that uses it, so no write through the pointer is ever lost.  Returns NULL
+   for a device-only vector.                                                     */
+double *pcu_vec_host_ptr(pcu_vec *v);
+int pcu_vec_is_managed(pcu_vec *v);
 
 /* ------------------------------------------------------------------ problem
    ParOptProblem (ParOptProblem.h:42-299).  The sparse "weighting" constraints
@@ -119,6 +129,14 @@ typedef struct pcu_problem_callbacks {
   int (*get_vars_and_bounds)(void *user, pcu_vec *x, pcu_vec *lb, pcu_vec *ub);
   int (*eval_obj_con)(void *user, pcu_vec *x, double *fobj, double *cons);
   int (*eval_obj_con_gradient)(void *user, pcu_vec *x, pcu_vec *g, pcu_vec **Ac);
+  /* Optional (NULL = the reference's empty default, ParOptProblem.cpp:220-223):
+     computeQuasiNewtonUpdateCorrection (ParOptProblem.h:287; called right before
+     the quasi-Newton update, IP.cpp:4258; z = ncon host doubles) and writeOutput
+     (ParOptProblem.h:296; called every write_output_frequency iterations at the
+     top of the major loop, IP.cpp:4620-4631).                                  */
+  int (*qn_update_correction)(void *user, pcu_vec *x, const double *z, pcu_vec *zw,
+                              pcu_vec *s, pcu_vec *y);
+  int (*write_output)(void *user, int iter, pcu_vec *x);
 } pcu_problem_callbacks;
 
 /* ParOptProblem::setProblemSizes / setNumInequalities (ParOptProblem.cpp:47-76)
@@ -185,6 +203,9 @@ typedef struct pcu_host_callbacks {
                       double *cons);
   int (*eval_obj_con_gradient)(void *user, int n, const double *x, double *g,
                                double **Ac);
+  /* Optional, as in pcu_problem_callbacks; writeOutput sees the iterate in the
+     pinned host mirror (one device->host copy per call).                        */
+  int (*write_output)(void *user, int iter, int n, const double *x);
 } pcu_host_callbacks;
 pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
                                      int ninequality, int nwinequality,
@@ -254,6 +275,19 @@ int pcu_ip_optimize(pcu_ip *ip);
    (IP.cpp:4607-5329); *converged is set when the convergence test fires.       */
 int pcu_ip_begin(pcu_ip *ip);
 int pcu_ip_iterate(pcu_ip *ip, int max_iters, int *converged);
+/* resetDesignAndBounds (IP.cpp:1249): asks the problem for x, lb, ub again.     */
+int pcu_ip_reset_design_and_bounds(pcu_ip *ip);
+/* setPenaltyGamma(double) (IP.cpp:1128) and setPenaltyGamma(const double*)
+   (IP.cpp:1160; ncon values, negative entries keep the current value; the sparse
+   penalties keep the scalar).                                                  */
+int pcu_ip_set_penalty_gamma(pcu_ip *ip, double gamma);
+int pcu_ip_set_penalty_gamma_array(pcu_ip *ip, const double *gamma);
+int pcu_ip_get_penalty_gamma(pcu_ip *ip, double *gamma_t);   /* penalty_gamma_t, IP.h:431 */
+/* resetProblemInstance (IP.cpp:745): a problem of identical sizes, inequality
+   counts and weighting descriptor replaces the current one; 1 = incompatible.   */
+int pcu_ip_reset_problem(pcu_ip *ip, pcu_problem *prob);
+/* resetQuasiNewtonHessian (IP.cpp:1241).                                        */
+int pcu_ip_reset_quasi_newton(pcu_ip *ip);
 /* getOptimizedPoint / getOptimizedSlacks (IP.h:156-163): device vectors owned
    by the optimizer plus host copies of the dense parts.                       */
 int pcu_ip_get_point(pcu_ip *ip, pcu_vec **x, pcu_vec **zw, pcu_vec **zl,

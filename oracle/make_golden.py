@@ -172,6 +172,20 @@ def main():
                 json.dump(data, fp, separators=(",", ":"))
             print(fname, "niter", data["final"]["niter"], data["status"])
         return
+    if "--full-c4" in sys.argv:
+        # the dense-constraint stress config at its FULL size (n = 32M, c = 100, L-SR1
+        # m = 20): the first iterations of the unmodified reference, 8 shim ranks;
+        # ~50 GB of host memory and ~2.5 min per iteration (c (c + 1) / 2 = 5050 dots
+        # and c + q sequential solves per set-up)
+        cfg = configs.get("C4")
+        cfg["options"] = dict(cfg["options"], max_major_iters=11)
+        data = run_reference(cfg, 8)
+        data["generator"] = "oracle/make_golden.py --full-c4 (oracle/_ref/ref_driver, unmodified reference, 8 ranks)"
+        data["log"] = data["log"][:12]
+        with open(os.path.join(out_dir, "C4_full.json"), "w") as fp:
+            json.dump(data, fp, separators=(",", ":"))
+        print("C4_full.json", "niter", data["final"]["niter"], data["status"], flush=True)
+        return
     if "--full" in sys.argv:
         # the first iterations of the reference at the FULL sizes of BASELINE.json
         # (C3: n = 64M, W = 8M; C2: n = 16M, c = 10), 8 shim ranks; ~40 GB, minutes

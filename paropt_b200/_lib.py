@@ -39,10 +39,17 @@ EVAL_GRAD_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                            C.POINTER(C.c_void_p))
 
 
+QN_CORR_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, c_double_p, C.c_void_p,
+                         C.c_void_p, C.c_void_p)
+WRITE_OUT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+
+
 class Callbacks(C.Structure):
     _fields_ = [("user", C.c_void_p), ("get_vars_and_bounds", GET_VARS_CB),
                 ("eval_obj_con", EVAL_OBJ_CB),
-                ("eval_obj_con_gradient", EVAL_GRAD_CB)]
+                ("eval_obj_con_gradient", EVAL_GRAD_CB),
+                ("qn_update_correction", QN_CORR_CB),
+                ("write_output", WRITE_OUT_CB)]
 
 
 HOST_GET_VARS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p,
@@ -53,10 +60,14 @@ HOST_EVAL_GRAD_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_doub
                                 C.POINTER(c_double_p))
 
 
+HOST_WRITE_OUT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, c_double_p)
+
+
 class HostCallbacks(C.Structure):
     _fields_ = [("user", C.c_void_p), ("get_vars_and_bounds", HOST_GET_VARS_CB),
                 ("eval_obj_con", HOST_EVAL_OBJ_CB),
-                ("eval_obj_con_gradient", HOST_EVAL_GRAD_CB)]
+                ("eval_obj_con_gradient", HOST_EVAL_GRAD_CB),
+                ("write_output", HOST_WRITE_OUT_CB)]
 
 
 VP = C.c_void_p
@@ -109,6 +120,14 @@ SIGNATURES = {
     "pcu_vec_scale": (C.c_int, [VP, C.c_double]),
     "pcu_vec_axpy": (C.c_int, [VP, C.c_double, VP]),
     "pcu_vec_device_ptr": (VP, [VP]),
+    "pcu_vec_host_ptr": (VP, [VP]),
+    "pcu_vec_is_managed": (C.c_int, [VP]),
+    "pcu_ip_reset_design_and_bounds": (C.c_int, [VP]),
+    "pcu_ip_set_penalty_gamma": (C.c_int, [VP, C.c_double]),
+    "pcu_ip_set_penalty_gamma_array": (C.c_int, [VP, c_double_p]),
+    "pcu_ip_get_penalty_gamma": (C.c_int, [VP, c_double_p]),
+    "pcu_ip_reset_problem": (C.c_int, [VP, VP]),
+    "pcu_ip_reset_quasi_newton": (C.c_int, [VP]),
     "pcu_vec_to_host": (C.c_int, [VP, VP, C.c_int]),
     "pcu_vec_from_host": (C.c_int, [VP, VP, C.c_int]),
     "pcu_problem_create": (VP, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

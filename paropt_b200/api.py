@@ -157,6 +157,15 @@ class PVec:
     def device_ptr(self):
         return int(self.lib.pcu_vec_device_ptr(self.h) or 0)
 
+    def host_array(self):
+        """numpy view of a managed vector (Context.set_param("managed_vectors", 1)):
+        ParOptVec::getArray for host loops; reads and writes go to the vector itself."""
+        ptr = self.lib.pcu_vec_host_ptr(self.h)
+        if not ptr:
+            raise RuntimeError("paropt_b200: not a managed vector")
+        n = len(self)
+        return np.ctypeslib.as_array(C.cast(ptr, _lib.c_double_p), shape=(n,)) if n else np.empty(0)
+
     # Zero-copy device view (torch.as_tensor(v, device="cuda"), cupy.asarray(v)):
     # the fast path SURVEY.md section 8f-2 asks for instead of PVec's per-element
     # host indexing (ParOpt.pyx:1082-1159).
@@ -330,6 +339,10 @@ class Problem:
         self._cb.get_vars_and_bounds = _lib.HOST_GET_VARS_CB(self._get_vars)
         self._cb.eval_obj_con = _lib.HOST_EVAL_OBJ_CB(self._eval_obj)
         self._cb.eval_obj_con_gradient = _lib.HOST_EVAL_GRAD_CB(self._eval_grad)
+        # ParOptProblem::writeOutput (ParOptProblem.h:296): registered only when the
+        # subclass defines it, so that nobody pays the device->host copy otherwise
+        if hasattr(self, "writeOutput"):
+            self._cb.write_output = _lib.HOST_WRITE_OUT_CB(self._write_output)
         self._views = {}
         self.h = self.lib.pcu_problem_create_host(
             ctx.h, self.nvars, self.ncon, int(ninequality), int(nwinequality),
@@ -374,6 +387,15 @@ class Problem:
             for i in range(self.ncon):
                 cons[i] = float(con[i])
             return int(fail)
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _write_output(self, user, it, n, x):
+        try:
+            self.writeOutput(int(it), self._view(x, n))
+            return 0
         except Exception:
             import traceback
             traceback.print_exc()
@@ -488,6 +510,35 @@ class InteriorPoint:
         _check(self.lib.pcu_ip_set_quasi_newton(self.h, qn.h if qn is not None else None),
                "setQuasiNewton")
         self._qn_ref = qn  # keep it alive
+
+    def resetDesignAndBounds(self):
+        """ParOptInteriorPoint::resetDesignAndBounds (IP.cpp:1249)."""
+        _check(self.lib.pcu_ip_reset_design_and_bounds(self.h), "resetDesignAndBounds")
+
+    def setPenaltyGamma(self, gamma):
+        """setPenaltyGamma(double) / setPenaltyGamma(const double*) (IP.cpp:1128, 1160)."""
+        if np.isscalar(gamma):
+            _check(self.lib.pcu_ip_set_penalty_gamma(self.h, float(gamma)), "setPenaltyGamma")
+        else:
+            g = np.ascontiguousarray(gamma, dtype=np.float64)
+            if g.size != self.ncon:
+                raise ValueError("penalty array must have ncon entries")
+            _check(self.lib.pcu_ip_set_penalty_gamma_array(
+                self.h, g.ctypes.data_as(_lib.c_double_p)), "setPenaltyGamma")
+
+    def getPenaltyGamma(self):
+        g = np.zeros(max(self.ncon, 1))
+        _check(self.lib.pcu_ip_get_penalty_gamma(self.h, g.ctypes.data_as(_lib.c_double_p)),
+               "getPenaltyGamma")
+        return g[:self.ncon]
+
+    def resetProblemInstance(self, problem):
+        """resetProblemInstance (IP.cpp:745): a congruent problem replaces the current one."""
+        _check(self.lib.pcu_ip_reset_problem(self.h, problem.h), "resetProblemInstance")
+        self.prob = problem
+
+    def resetQuasiNewtonHessian(self):
+        _check(self.lib.pcu_ip_reset_quasi_newton(self.h), "resetQuasiNewtonHessian")
 
     def optimize(self):
         _check(self.lib.pcu_ip_optimize(self.h), "optimize")

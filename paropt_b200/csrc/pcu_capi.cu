@@ -178,6 +178,69 @@ int pcu_ip_optimize(pcu_ip *ip) {
   return 0;
 }
 
+// resetDesignAndBounds (IP.cpp:1249-1251)
+int pcu_ip_reset_design_and_bounds(pcu_ip *ip) {
+  if (!ip) return 1;
+  return ip->prob->getVarsAndBounds(ip->variables.v[PCU_X], ip->lb, ip->ub);
+}
+
+// setPenaltyGamma(double) (IP.cpp:1128-1153): every dense and sparse penalty
+int pcu_ip_set_penalty_gamma(pcu_ip *ip, double gamma) {
+  if (!ip) return 1;
+  if (gamma >= 0.0) {
+    ip->opt.penalty_gamma = gamma;
+    ip->gamma_custom = 0;
+    ip->refresh_penalties();
+  }
+  return 0;
+}
+
+// setPenaltyGamma(const double*) (IP.cpp:1160-1173): dense constraints only,
+// negative entries keep their value
+int pcu_ip_set_penalty_gamma_array(pcu_ip *ip, const double *gamma) {
+  if (!ip || (!gamma && ip->ncon > 0)) return 1;
+  ip->refresh_penalties();
+  for (int i = 0; i < ip->ncon; i++) {
+    if (gamma[i] >= 0.0) {
+      ip->gamma_s[i] = i < ip->prob->ninequality ? 0.0 : gamma[i];
+      ip->gamma_t[i] = gamma[i];
+    }
+  }
+  ip->gamma_custom = 1;
+  return 0;
+}
+
+int pcu_ip_get_penalty_gamma(pcu_ip *ip, double *gamma_t) {
+  if (!ip) return 1;
+  ip->refresh_penalties();
+  for (int i = 0; i < ip->ncon; i++) gamma_t[i] = ip->gamma_t[i];
+  return 0;
+}
+
+// resetProblemInstance (IP.cpp:745-764)
+int pcu_ip_reset_problem(pcu_ip *ip, pcu_problem *prob) {
+  if (!ip || !prob) return 1;
+  const pcu_weighting &a = prob->weighting, &b = ip->prob->weighting;
+  if (prob->ctx != ip->ctx || prob->nvars != ip->nvars || prob->ncon != ip->ncon ||
+      prob->nwcon != ip->nwcon || prob->ninequality != ip->prob->ninequality ||
+      prob->nwinequality != ip->prob->nwinequality || prob->use_lower != ip->prob->use_lower ||
+      prob->use_upper != ip->prob->use_upper || a.nwcon != b.nwcon || a.wstart != b.wstart ||
+      a.nw != b.nw || a.wstride != b.wstride || a.coef0 != b.coef0 ||
+      a.coef_rest != b.coef_rest || a.wconst != b.wconst) {
+    fprintf(stderr, "ParOpt: Incompatible problem instance\n");
+    return 1;
+  }
+  ip->prob = prob;
+  return 0;
+}
+
+// resetQuasiNewtonHessian (IP.cpp:1241-1245)
+int pcu_ip_reset_quasi_newton(pcu_ip *ip) {
+  if (!ip) return 1;
+  if (ip->qn) ip->qn->reset();
+  return 0;
+}
+
 int pcu_ip_get_point(pcu_ip *ip, pcu_vec **x, pcu_vec **zw, pcu_vec **zl,
                      pcu_vec **zu, pcu_vec **sw, pcu_vec **tw) {
   Vars &v = ip->variables;

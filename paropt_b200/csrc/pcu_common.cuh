@@ -260,14 +260,33 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb, const int tid_ = 
 // sum_i log(f_i) is accumulated as the logarithm of a running product: the
 // mantissa product P in [1, 2) and the exponent sum E live in two accumulator
 // slots (P == 0 stands for "empty"), one multiplication and a few integer
-// operations per factor instead of one fp64 log.  Factors must be positive and
-// in [1e-150, 1e150].  lp_value turns the pair into E ln2 + log(P).
+// operations per factor instead of one fp64 log.  lp_value turns the pair into
+// E ln2 + log(P).  The fast path needs a positive, normal factor in
+// [1e-150, 1e150]; anything else -- zero (a variable ON its bound: lb + dp == lb
+// for |lb| >~ 100 or design_precision = 0), negative, NaN, a product that left
+// the range -- takes log2(f) itself into E, so that log(0) = -inf (the reference's
+// merit becomes +inf and the line search rejects the trial, IP.cpp:3541-3590) and
+// NaN propagate exactly as a plain sum of logarithms would.
 __device__ __forceinline__ void lp_mul(double &P, double &E, double f) {
+  if (!(f >= 1e-150 && f <= 1e150)) {
+    E += log(f) * 1.44269504088896340735992468100189214;
+    return;
+  }
   double p = (P == 0.0 ? 1.0 : P) * f;
   const long long bits = __double_as_longlong(p);
   const int e = (int)((bits >> 52) & 0x7ff) - 1023;
   P = __longlong_as_double((bits & 0x800FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL);
   E += (double)e;
+}
+// Two factors whose product may leave the fast range (bounds near max_bound_value).
+__device__ __forceinline__ void lp_mul2(double &P, double &E, double f0, double f1) {
+  const double f = f0 * f1;
+  if (f >= 1e-150 && f <= 1e150) {
+    lp_mul(P, E, f);
+  } else {
+    lp_mul(P, E, f0);
+    lp_mul(P, E, f1);
+  }
 }
 __device__ __forceinline__ double lp_value(double P, double E) {
   return fma(E, 0.693147180559945309417232121458, P == 0.0 ? 0.0 : log(P));

@@ -28,6 +28,7 @@ struct pcu_ctx {
   double *d_gather = nullptr;   // [world][total] packed partials of all ranks (multi-GPU)
   double *h_gather = nullptr;   // pinned mirror, combined on the host in rank order
   int result_used = 0;
+  bool red_overflow = false;   // redbuf() ran out of slots: the next fetch() fails
   std::vector<PendingRed> pending;
 
   // large sum-reductions (mdot, Gram triangle)
@@ -47,6 +48,7 @@ struct pcu_ctx {
   int tma_min_tiles = 0;       // staged launch only from this many tiles (default 8 per SM)
   int tma_grid = 0;            // CTAs of the staged launch (default: one per SM)
   int tma_max_rows = 0;        // debugging: staged launch only for tiles up to this many rows
+  int managed_vectors = 0;     // pcu_vec_create allocates unified memory (pcu_vec_host_ptr)
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -95,7 +97,21 @@ struct pcu_vec {
   int n = 0;
   double *d = nullptr;
   bool owns = true;
+  bool managed = false;       // unified memory (context parameter "managed_vectors")
+  bool host_touched = false;  // handed to the host through pcu_vec_host_ptr since the last use
 };
+
+// Every C-ABI entry point that reads or writes a caller's vector on the device
+// passes it through here first: a managed vector the host has touched is moved
+// back to the device on the context's stream (pcu_vec_host_ptr, paropt_b200.h).
+static inline void pcu_vec_ready(pcu_vec *v) {
+  if (v && v->host_touched) {
+    v->host_touched = false;
+    if (v->n > 0)
+      cudaMemPrefetchAsync(v->d, ((size_t)v->n + 2) * sizeof(double), v->ctx->device,
+                           v->ctx->stream);
+  }
+}
 
 template <class F>
 const char *pcu_kernel_name() {
@@ -130,6 +146,7 @@ struct TmaHostCheck {
   }
 };
 
+#define PCU_MAX_DEVICES 64
 #define PCU_TMA_SMEM_BUDGET (222 * 1024)  // + <= 5 KB static: the 227 KB a CTA may hold
 
 // Bulk-copy staged launch of a SRC functor (tma_tile_kernel); returns -1 when
@@ -184,12 +201,15 @@ int pcu_launch_tile_tma(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
   plan.tiles_con = ncon_elems / ROWS;
   if (plan.tiles_con > plan.ntiles) plan.tiles_con = plan.ntiles;
   plan.tile_skip = (ncon_elems % ROWS != 0 && plan.tiles_con < plan.ntiles) ? plan.tiles_con : -1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per device: one flag per ordinal (several contexts /
+  // devices may live in one process)
+  static bool attr_set[PCU_MAX_DEVICES] = {false};
+  const int dev = ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0;
+  if (!attr_set[dev] || ctx->device >= PCU_MAX_DEVICES) {
     PCU_CUDA_OK(cudaFuncSetAttribute(tma_tile_kernel<F, ROWS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      PCU_TMA_SMEM_BUDGET));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int threads = PCU_TMA_MAXWARPS * 32;
   const size_t smem = (size_t)plan.nstages * plan.stage_bytes;
@@ -210,7 +230,15 @@ int pcu_launch_tile(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
     if (r >= 0) return r;
   }
   // persistent grid: exactly as many blocks as can be co-resident
-  static int blocks_per_sm = -1;
+  static int bps_dev[PCU_MAX_DEVICES];
+  static bool bps_init = false;
+  if (!bps_init) {
+    for (int i = 0; i < PCU_MAX_DEVICES; i++) bps_dev[i] = -1;
+    bps_init = true;
+  }
+  const int dev_ = ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0;
+  if (ctx->device >= PCU_MAX_DEVICES) bps_dev[dev_] = -1;  // beyond the table: always query
+  int &blocks_per_sm = bps_dev[dev_];
   if (blocks_per_sm < 0) {
     int v = 0;
     if (F::SMEM > 0)

@@ -477,8 +477,9 @@ static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
   *rows_done = nslabs * ROWS;
   *skip_lo = slab_skip >= 0 ? slab_skip * ROWS : -1;
   const int smem = nstages * stage_bytes;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static int attr_smem_dev[PCU_MAX_DEVICES] = {0};  // per device (function attribute)
+  int &attr_smem = attr_smem_dev[ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0];
+  if (smem > attr_smem || ctx->device >= PCU_MAX_DEVICES) {
     PCU_CUDA_OK(cudaFuncSetAttribute(gram_tma_kernel<NT, NWC, NCW>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
@@ -547,8 +548,9 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
   const long long nslabs = n / PCU_GW_ROWS;
   *rows_done = nslabs * PCU_GW_ROWS;
   const int smem = nstages * stage_bytes;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static int attr_smem_dev[PCU_MAX_DEVICES] = {0};  // per device (function attribute)
+  int &attr_smem = attr_smem_dev[ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0];
+  if (smem > attr_smem || ctx->device >= PCU_MAX_DEVICES) {
     PCU_CUDA_OK(cudaFuncSetAttribute(gram_wide_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;

@@ -248,6 +248,7 @@ pcu_problem *pcu_problem_create_sepquad_host(pcu_ctx *ctx,
     w.wconst = 0.0;
   }
   pcu_host_callbacks cb;
+  memset(&cb, 0, sizeof(cb));
   cb.user = q;
   cb.get_vars_and_bounds = HostSepQuad::get_vars;
   cb.eval_obj_con = HostSepQuad::eval_obj;

@@ -86,6 +86,16 @@ QuasiNewton::~QuasiNewton() {
 }
 
 int QuasiNewton::init(pcu_ctx *c, int nvars, int kind, int m) {
+  // The column tables of the kernels hold PCU_MAX_COLS entries: [S | Y] (+ the
+  // damped update's extra column) for L-BFGS, Z for L-SR1.  Checked here, before
+  // anything is allocated, so that pcu_qn_create and pcu_ip share one rule.
+  const int width = kind == 0 ? 2 * m + 1 : m;
+  if (m < 0 || width > PCU_MAX_COLS) {
+    fprintf(stderr,
+            "paropt_b200: quasi-Newton subspace %d too large (%s needs %d of %d columns)\n", m,
+            kind == 0 ? "bfgs" : "sr1", width, PCU_MAX_COLS);
+    return 1;
+  }
   ctx = c;
   n = nvars;
   type = kind;
@@ -121,13 +131,19 @@ void QuasiNewton::reset() {  // QN.cpp:132-146, 608-622
 }
 
 void QuasiNewton::z_table(ColTable &t, int off) const {
+  // (a caller may have looked at Z through pcu_qn_compact + pcu_vec_host_ptr)
   if (type == 0) {
     for (int i = 0; i < msub; i++) {
+      pcu_vec_ready(S[i]);
+      pcu_vec_ready(Y[i]);
       t.p[off + i] = S[i]->d;
       t.p[off + msub + i] = Y[i]->d;
     }
   } else {
-    for (int i = 0; i < msub; i++) t.p[off + i] = Zs[i]->d;
+    for (int i = 0; i < msub; i++) {
+      pcu_vec_ready(Zs[i]);
+      t.p[off + i] = Zs[i]->d;
+    }
   }
 }
 
@@ -213,6 +229,8 @@ int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
     }
     ColTable t;
     for (int i = 0; i < msub; i++) {
+      pcu_vec_ready(S[i]);
+      pcu_vec_ready(Y[i]);
       t.p[i] = S[i]->d;
       t.p[msub + i] = Y[i]->d;
     }
@@ -356,9 +374,14 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
   nvars = p->nvars;
   ncon = p->ncon;
   nwcon = p->nwcon;
-  if (ncon + 2 * 64 > PCU_MAX_COLS + 64) {
-    // checked again when the quasi-Newton size is known
+  if (ncon < 0 || ncon > PCU_MAX_COLS - 1) {
+    fprintf(stderr, "paropt_b200: %d dense constraints exceed the %d columns of the kernels\n",
+            ncon, PCU_MAX_COLS - 1);
+    return 1;
   }
+  if (pcu_validate_weighting(&p->weighting, nvars, ncon, p->ninequality, p->nwinequality,
+                             "pcu_ip_create"))
+    return 1;
   wd = pcu_make_wdesc(p->weighting, nvars);
   if (getenv("PCU_NO_FUSE21")) opt_no_fuse21 = 1;
   if (getenv("PCU_NO_FUSE2S")) opt_no_fuse2s = 1;
@@ -437,25 +460,39 @@ int pcu_ip::ensure_qn() {  // IP.cpp:263-290
   }
   if (!qn_external) delete qn;
   qn = nullptr;
-  qn_built_type = opt.qn_type;
-  qn_built_size = opt.qn_subspace_size;
+  qn_built_type.clear();
+  qn_built_size = -1;
   int kind = -1;
   if (opt.qn_type == "bfgs") kind = 0;
   else if (opt.qn_type == "sr1") kind = 1;
-  if (kind < 0) return 0;
-  qn = new QuasiNewton;
-  if (qn->init(ctx, nvars, kind, opt.qn_subspace_size)) return 1;
-  if (ncon + qn->max_size() > PCU_MAX_COLS) {
-    fprintf(stderr, "paropt_b200: ncon + quasi-Newton width exceeds %d\n",
-            PCU_MAX_COLS);
+  if (kind < 0) {  // "none": no quasi-Newton object (IP.cpp:263-277)
+    qn_built_type = opt.qn_type;
+    qn_built_size = opt.qn_subspace_size;
+    return 0;
+  }
+  // validate the width BEFORE allocating: a failed attempt leaves nothing cached
+  const int m = opt.qn_subspace_size;
+  const int width = kind == 0 ? 2 * m : m;
+  if (m < 0 || ncon + width + 1 > PCU_MAX_COLS) {
+    fprintf(stderr, "paropt_b200: ncon + quasi-Newton width (%d + %d) exceeds %d columns\n",
+            ncon, width, PCU_MAX_COLS - 1);
     return 1;
   }
+  QuasiNewton *fresh = new QuasiNewton;
+  if (fresh->init(ctx, nvars, kind, m)) {
+    delete fresh;
+    return 1;
+  }
+  qn = fresh;
+  qn_built_type = opt.qn_type;
+  qn_built_size = opt.qn_subspace_size;
   qn->damped = (opt.qn_update_type == "damped_update");
   qn->diag_yts_over_sts = (opt.qn_diag_type == "yts_over_sts");
   return 0;
 }
 
-void pcu_ip::refresh_penalties() {  // IP.cpp:343-355
+void pcu_ip::refresh_penalties() {  // IP.cpp:343-355, setPenaltyGamma IP.cpp:1128-1173
+  if (gamma_custom && (int)gamma_t.size() == ncon) return;  // per-constraint values were set
   gamma_s.assign(ncon, opt.penalty_gamma);
   gamma_t.assign(ncon, opt.penalty_gamma);
   for (int i = 0; i < ncon && i < prob->ninequality; i++) gamma_s[i] = 0.0;

@@ -130,6 +130,7 @@ struct pcu_ip {
   std::vector<double> c;
   double fobj = 0.0;
   std::vector<double> gamma_s, gamma_t;
+  int gamma_custom = 0;  // set through setPenaltyGamma(const double*): not refreshed from the option
   QuasiNewton *qn = nullptr;
   int qn_external = 0;  // qn belongs to a pcu_qn handle (setQuasiNewton, IP.cpp:1193): not owned
   std::string qn_built_type;

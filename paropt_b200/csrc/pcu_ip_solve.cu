@@ -1069,6 +1069,10 @@ int pcu_ip::iterate_once(int *converged) {
       qn_hessian_reset = 1;
     }
   }
+  // the problem's writeOutput hook (IP.cpp:4620-4631)
+  if (opt.write_output_frequency > 0 && k % opt.write_output_frequency == 0) {
+    if (prob->writeOutput(k, v.v[PCU_X])) return 1;
+  }
   const int rel_function_test =
       (ls.alpha_xprev == 1.0 && ls.alpha_zprev == 1.0 &&
        fabs(fobj - ls.fobj_prev) < opt.rel_func_tol * fabs(ls.fobj_prev));
@@ -1366,9 +1370,18 @@ int pcu_ip::iterate_once(int *converged) {
         if (launch_tile(ctx, f2, nvars, wd, rb)) return 1;
         double dots[3];
         if (ctx->fetch(dots)) return 1;
+        // computeQuasiNewtonUpdateCorrection (IP.cpp:4258): the user may change
+        // s and y, so the three dots are taken again afterwards
+        const bool corrected = prob->hasQnUpdateCorrection();
+        if (corrected) {
+          if (prob->qnUpdateCorrection(v.v[PCU_X], v.z.data(), v.v[PCU_ZW], s_qn, y_qn)) return 1;
+          if (pcu_vec_dot(y_qn, y_qn, &dots[0]) || pcu_vec_dot(y_qn, s_qn, &dots[1]) ||
+              pcu_vec_dot(s_qn, s_qn, &dots[2]))
+            return 1;
+        }
         // s.S_i and s.Y_i: s = ax * p, so they are ax * (Z^T p) for L-BFGS
         std::vector<double> sZ;
-        if (qn->type == 0 && !force_direct_dots && vtp_valid) {
+        if (qn->type == 0 && !force_direct_dots && vtp_valid && !corrected) {
           sZ.resize(qn->size());
           for (int i = 0; i < qn->size(); i++) sZ[i] = ax * VTp[nA + i];
         }

@@ -811,11 +811,12 @@ __device__ __forceinline__ void stats_elements(
     const double (&u)[W], const double (&zl)[W], const double (&zu)[W],
     const double (&px)[W], const double (&pzl)[W], const double (&pzu)[W],
     const double (&gv)[W], AccT_ &a) {
-    double fac = 1.0;  // product of the barrier arguments of these W elements
+    double facs[W];  // product of the barrier arguments of each element
 #pragma unroll
     for (int q = 0; q < W; q++) {
       const double dl = x[q] - l[q], du = u[q] - x[q];
       const double pxq = px[q];
+      double fac = 1.0;
       const bool ml = k.use_lower && l[q] > -k.mbv;
       const bool mu_ = k.use_upper && u[q] < k.mbv;
       // Fraction to the boundary (IP.cpp:2959-2982, 3064-3091): the quotient is
@@ -877,8 +878,10 @@ __device__ __forceinline__ void stats_elements(
       a.s[16] = fma(gv[q], pxq, a.s[16]);
       a.s[17] = fma(pxq, pxq, a.s[17]);
       a.x[0] = fmax(a.x[0], fabs(pxq));
+      facs[q] = fac;
     }
-    lp_mul(a.s[8], a.s[9], fac);
+    if (W == 2) lp_mul2(a.s[8], a.s[9], facs[0], facs[W - 1]);
+    else lp_mul(a.s[8], a.s[9], facs[0]);
 }
 template <class AccT_>
 __device__ __forceinline__ void stats_constraint_vals(
@@ -1267,10 +1270,8 @@ struct TrialF : NoStreams {
   __device__ __forceinline__ void C(const S &, long long, const double (&)[W],
                                     const Elem (&e)[W], const Con &,
                                     AT &acc) const {
-    double f = e[0].f;
-#pragma unroll
-    for (int q = 1; q < W; q++) f *= e[q].f;
-    lp_mul(acc.s[0], acc.s[1], f);
+    if (W == 2) lp_mul2(acc.s[0], acc.s[1], e[0].f, e[W - 1].f);
+    else lp_mul(acc.s[0], acc.s[1], e[0].f);
   }
   template <class AT>
   __device__ __forceinline__ void finalize(AT &acc) const {

@@ -20,7 +20,7 @@ struct pcu_blockmat {
   int nvars = 0, nwcon = 0;
   WDesc wd;
   pcu_vec *Cw = nullptr;
-  const pcu_vec *Dinv = nullptr;  // kept from factor() like the reference (SM.cpp:44-58)
+  pcu_vec *Dinv = nullptr;  // kept from factor() like the reference (SM.cpp:44-58)
   int factored = 0;
 };
 
@@ -39,10 +39,7 @@ pcu_blockmat *pcu_blockmat_create(pcu_ctx *ctx, int nvars, const pcu_weighting *
   pcu_weighting none;
   memset(&none, 0, sizeof(none));
   const pcu_weighting &ww = w ? *w : none;
-  if (ww.nwcon > 0 && (ww.nw < 1 || ww.wstride < ww.nw || ww.wstart < 0 ||
-                       (long long)ww.wstart + (long long)(ww.nwcon - 1) * ww.wstride + ww.nw >
-                           (long long)nvars)) {
-    fprintf(stderr, "paropt_b200: pcu_blockmat_create: weighting pattern outside the vector\n");
+  if (pcu_validate_weighting(&ww, nvars, 0, 0, ww.nwcon, "pcu_blockmat_create")) {
     delete m;
     return nullptr;
   }
@@ -68,6 +65,8 @@ void pcu_blockmat_destroy(pcu_blockmat *m) {
 int pcu_blockmat_factor(pcu_blockmat *m, pcu_vec *x, pcu_vec *Dinv, pcu_vec *Cdiag) {
   (void)x;
   if (!m || !Dinv || !Cdiag || Dinv->n != m->nvars || Cdiag->n != m->nwcon) return -1;
+  pcu_vec_ready(Dinv);
+  pcu_vec_ready(Cdiag);
   m->Dinv = Dinv;
   m->factored = 1;
   BlockFactorF f;
@@ -86,6 +85,11 @@ static int blockmat_apply(pcu_blockmat *m, pcu_vec *bx, pcu_vec *bw, pcu_vec *yx
   if (!m || !m->factored || !bx || !yx || !yw || bx->n != m->nvars || yx->n != m->nvars ||
       yw->n != m->nwcon || (bw && bw->n != m->nwcon))
     return 1;
+  pcu_vec_ready(bx);
+  pcu_vec_ready(bw);
+  pcu_vec_ready(yx);
+  pcu_vec_ready(yw);
+  pcu_vec_ready(m->Dinv);
   BlockApplyF f;
   f.bx = bx->d;
   f.bw = bw ? bw->d : nullptr;
@@ -133,7 +137,12 @@ int pcu_qn_set_option(pcu_qn *h, const char *name, const char *value) {
     else if (v == "damped_update") h->q.damped = 1;
     else return 1;
   } else if (k == "qn_diag_type") {
-    h->q.diag_yts_over_sts = (v == "yts_over_sts") ? 1 : 0;
+    // the inner_* values are accepted and act as yty_over_yts, exactly as in the
+    // reference (QN.cpp:200-204 tests for PAROPT_YTS_OVER_STS only)
+    if (v == "yts_over_sts") h->q.diag_yts_over_sts = 1;
+    else if (v == "yty_over_yts" || v == "inner_yty_over_yts" || v == "inner_yts_over_sts")
+      h->q.diag_yts_over_sts = 0;
+    else return 1;
   } else {
     return 1;
   }
@@ -149,6 +158,8 @@ int pcu_qn_max_size(pcu_qn *h) { return h ? h->q.msub_max : 0; }
 // int update(x, z, zw, s, y): 0 normal, 1 damped, 2 skipped (QN.cpp:162-334, 636-747)
 int pcu_qn_update(pcu_qn *h, pcu_vec *s, pcu_vec *y, int *update_type) {
   if (!h || !s || !y) return 1;
+  pcu_vec_ready(s);
+  pcu_vec_ready(y);
   double yy, ys, ss;
   if (pcu_vec_dot(y, y, &yy) || pcu_vec_dot(y, s, &ys) || pcu_vec_dot(s, s, &ss)) return 1;
   int ut = 0;
@@ -159,11 +170,15 @@ int pcu_qn_update(pcu_qn *h, pcu_vec *s, pcu_vec *y, int *update_type) {
 // y = B x (QN.cpp:390-418, 760-778)
 int pcu_qn_mult(pcu_qn *h, pcu_vec *x, pcu_vec *y) {
   if (!h || !x || !y) return 1;
+  pcu_vec_ready(x);
+  pcu_vec_ready(y);
   return h->q.mult(x, y);
 }
 // y += alpha B x (QN.cpp:432-459, 792-809)
 int pcu_qn_mult_add(pcu_qn *h, double alpha, pcu_vec *x, pcu_vec *y) {
   if (!h || !x || !y) return 1;
+  pcu_vec_ready(x);
+  pcu_vec_ready(y);
   if (h->q.mult(x, h->q.r)) return 1;
   return pcu_vec_axpy(y, alpha, h->q.r);
 }
@@ -196,7 +211,7 @@ int pcu_ip_set_quasi_newton(pcu_ip *ip, pcu_qn *h) {
   ip->qn_external = 0;
   ip->qn_built_size = -1;
   if (h) {
-    if (h->q.n != ip->nvars || ip->ncon + h->q.max_size() > PCU_MAX_COLS) {
+    if (h->q.n != ip->nvars || ip->ncon + h->q.max_size() + 1 > PCU_MAX_COLS) {
       fprintf(stderr, "paropt_b200: pcu_ip_set_quasi_newton: size mismatch\n");
       return 1;
     }

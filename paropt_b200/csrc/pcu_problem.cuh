@@ -25,6 +25,14 @@ struct pcu_problem {
   // fobj / cons are host outputs (the reference's signature, ParOptProblem.h:157)
   virtual int evalObjCon(pcu_vec *x, double *fobj, double *cons) = 0;
   virtual int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) = 0;
+  // optional hooks with the reference's empty defaults (ParOptProblem.cpp:220-223)
+  virtual int qnUpdateCorrection(pcu_vec *, const double *, pcu_vec *, pcu_vec *, pcu_vec *) {
+    return 0;
+  }
+  virtual bool hasQnUpdateCorrection() const { return false; }
+  virtual int writeOutput(int, pcu_vec *) { return 0; }
 };
 
 WDesc pcu_make_wdesc(const pcu_weighting &w, int nvars);
+int pcu_validate_weighting(const pcu_weighting *w, int nvars, int ncon, int ninequality,
+                           int nwinequality, const char *who);

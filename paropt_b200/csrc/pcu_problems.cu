@@ -35,6 +35,34 @@ WDesc pcu_make_wdesc(const pcu_weighting &w, int nvars) {
   return d;
 }
 
+// One rule for every object that takes a pcu_weighting (pcu_problem_create[_host],
+// pcu_blockmat_create, pcu_ip): the rows must lie inside the vector and must not
+// overlap (the block-diagonal Ew = Cdiag + Aw D^-1 Aw^T of ParOptQuasiDefBlockMat,
+// SM.cpp:41-115, assumes disjoint rows), and the inequality counts are counts.
+// Returns 0 when the descriptor is usable, else prints the reason.
+int pcu_validate_weighting(const pcu_weighting *w, int nvars, int ncon, int ninequality,
+                           int nwinequality, const char *who) {
+  const char *why = nullptr;
+  if (nvars < 0) why = "negative number of variables";
+  else if (ncon < 0 || ncon > PCU_MAX_COLS - 1) why = "number of dense constraints out of range";
+  else if (ninequality > ncon) why = "ninequality exceeds ncon";
+  const int nwcon = w ? w->nwcon : 0;
+  if (!why && nwcon < 0) why = "negative number of weighting constraints";
+  if (!why && nwcon > 0) {
+    if (w->nw < 1) why = "nw < 1";
+    else if (w->wstart < 0) why = "wstart < 0";
+    else if (w->wstride < w->nw) why = "wstride < nw (overlapping rows)";
+    else if ((long long)w->wstart + (long long)(nwcon - 1) * w->wstride + w->nw > (long long)nvars)
+      why = "weighting rows reach outside the vector";
+  }
+  if (!why && nwinequality > nwcon) why = "nwinequality exceeds nwcon";
+  if (why) {
+    fprintf(stderr, "paropt_b200: %s: %s\n", who, why);
+    return 1;
+  }
+  return 0;
+}
+
 static const WDesc &no_weighting() {
   static WDesc d;
   static bool init = false;
@@ -527,6 +555,14 @@ struct CallbackProblem : pcu_problem {
   int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) override {
     return cb.eval_obj_con_gradient(cb.user, x, g, Ac);
   }
+  int qnUpdateCorrection(pcu_vec *x, const double *z, pcu_vec *zw, pcu_vec *s,
+                         pcu_vec *y) override {
+    return cb.qn_update_correction ? cb.qn_update_correction(cb.user, x, z, zw, s, y) : 0;
+  }
+  bool hasQnUpdateCorrection() const override { return cb.qn_update_correction != nullptr; }
+  int writeOutput(int iter, pcu_vec *x) override {
+    return cb.write_output ? cb.write_output(cb.user, iter, x) : 0;
+  }
 };
 
 // ======================================================= host-array callbacks
@@ -606,6 +642,15 @@ struct HostProblem : pcu_problem {
     t_user += host_now_ms() - t0;
     return fail;
   }
+  int writeOutput(int iter, pcu_vec *x) override {
+    if (!cb.write_output) return 0;
+    const int keep = same_point_hint;
+    same_point_hint = 0;  // the iterate may have moved since the last callback
+    const int rc = fetch_x(x);
+    same_point_hint = keep;
+    if (rc) return 1;
+    return cb.write_output(cb.user, iter, nvars, hx);
+  }
   int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) override {
     if (fetch_x(x) || wait_uploads()) return 1;
     const double t0 = host_now_ms();
@@ -633,7 +678,10 @@ pcu_problem *pcu_problem_create(pcu_ctx *ctx, int nvars, int ncon,
                                 int use_lower, int use_upper,
                                 const pcu_weighting *weighting,
                                 const pcu_problem_callbacks *callbacks) {
-  if (!ctx || !callbacks || ncon > PCU_MAX_COLS) return nullptr;
+  if (!ctx || !callbacks) return nullptr;
+  if (pcu_validate_weighting(weighting, nvars, ncon, ninequality, nwinequality,
+                             "pcu_problem_create"))
+    return nullptr;
   CallbackProblem *p = new CallbackProblem;
   p->ctx = ctx;
   p->nvars = nvars;
@@ -657,7 +705,10 @@ pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
                                      int use_lower, int use_upper,
                                      const pcu_weighting *weighting,
                                      const pcu_host_callbacks *callbacks) {
-  if (!ctx || !callbacks || ncon > PCU_MAX_COLS) return nullptr;
+  if (!ctx || !callbacks) return nullptr;
+  if (pcu_validate_weighting(weighting, nvars, ncon, ninequality, nwinequality,
+                             "pcu_problem_create_host"))
+    return nullptr;
   HostProblem *p = new HostProblem;
   p->ctx = ctx;
   p->nvars = nvars;
@@ -698,7 +749,9 @@ int pcu_problem_transfer_bytes(pcu_problem *prob, int64_t *h2d, int64_t *d2h) {
 
 pcu_problem *pcu_problem_create_sepquad(pcu_ctx *ctx,
                                         const pcu_sepquad_params *params) {
-  if (!ctx || !params || params->ncon > PCU_MAX_COLS) return nullptr;
+  if (!ctx || !params || params->ncon < 0 || params->ncon > PCU_MAX_COLS - 1 ||
+      params->ntotal < 0 || params->nw < 0)
+    return nullptr;
   SepQuadProblem *p = new SepQuadProblem;
   p->ctx = ctx;
   p->q.p = *params;
@@ -754,6 +807,10 @@ pcu_problem *pcu_problem_create_rosenbrock(pcu_ctx *ctx, int nvars, int nwcon,
   p->weighting.coef0 = -1.0;
   p->weighting.coef_rest = -1.0;
   p->weighting.wconst = 1.0;
+  if (pcu_validate_weighting(&p->weighting, nvars, 2, 2, nwcon, "pcu_problem_create_rosenbrock")) {
+    delete p;
+    return nullptr;
+  }
   return p;
 }
 

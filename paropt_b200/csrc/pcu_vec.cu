@@ -47,9 +47,14 @@ RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
   rb.counter = d_counter;
   const int nr = ns + nx + nm;
   if (result_used + nr > PCU_RESULT_CAP || pending.size() >= 32) {
-    fprintf(stderr, "paropt_b200: reduction slots exhausted\n");
-    result_used = 0;
-    pending.clear();
+    // a caller enqueued reductions without ever fetching them: fail the next fetch
+    // (pending results are kept) and park this kernel's output in the spare slots
+    if (!red_overflow)
+      fprintf(stderr, "paropt_b200: reduction slots exhausted (%d pending): the next fetch fails\n",
+              (int)pending.size());
+    red_overflow = true;
+    rb.result = d_result + PCU_RESULT_CAP;
+    return rb;
   }
   rb.result = d_result + result_used;
   pending.push_back({result_used, ns, nx, nm});
@@ -58,6 +63,13 @@ RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
 }
 
 int pcu_ctx::fetch(double *out) {
+  if (red_overflow) {
+    red_overflow = false;
+    result_used = 0;
+    pending.clear();
+    cudaStreamSynchronize(stream);
+    return 1;
+  }
   const int total = result_used;
   if (total > 0) {
     if (world > 1) {
@@ -213,10 +225,10 @@ pcu_ctx *pcu_ctx_create(int device) {
   ok &= cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok &= cudaMalloc(&ctx->d_partials, sizeof(double) * PCU_MAX_BLOCKS * PCU_MAX_RED) == cudaSuccess;
   ok &= cudaMalloc(&ctx->d_counter, 64) == cudaSuccess;
-  ok &= cudaMalloc(&ctx->d_result, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
+  ok &= cudaMalloc(&ctx->d_result, sizeof(double) * (PCU_RESULT_CAP + PCU_MAX_RED)) == cudaSuccess;
   ok &= cudaMallocHost(&ctx->h_result, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
   ok &= cudaMemset(ctx->d_counter, 0, 64) == cudaSuccess;
-  ok &= cudaMemset(ctx->d_result, 0, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
+  ok &= cudaMemset(ctx->d_result, 0, sizeof(double) * (PCU_RESULT_CAP + PCU_MAX_RED)) == cudaSuccess;
   ok &= cudaEventCreate(&ctx->ev0) == cudaSuccess;
   ok &= cudaEventCreate(&ctx->ev1) == cudaSuccess;
   ok &= cudaDeviceSynchronize() == cudaSuccess;
@@ -306,6 +318,7 @@ int pcu_ctx_set_param(pcu_ctx *ctx, const char *name, int value) {
   else if (k == "tma_min_tiles") ctx->tma_min_tiles = value;
   else if (k == "tma_grid") ctx->tma_grid = value;
   else if (k == "tma_max_rows") ctx->tma_max_rows = value;
+  else if (k == "managed_vectors") ctx->managed_vectors = value;
   else return 1;
   return 0;
 }
@@ -524,6 +537,8 @@ static int launch_plain(pcu_ctx *ctx, const F &f, long long n, RedBuf rb) {
 
 static int vec_reduce(pcu_vec *x, pcu_vec *y, double out[4]) {
   pcu_ctx *ctx = x->ctx;
+  pcu_vec_ready(x);
+  pcu_vec_ready(y);
   VecRedF f;
   f.x = x->d;
   f.y = y ? y->d : nullptr;
@@ -540,12 +555,15 @@ pcu_vec *pcu_vec_create(pcu_ctx *ctx, int n) {
   v->ctx = ctx;
   v->n = n;
   size_t bytes = ((size_t)n + 2) * sizeof(double);
-  if (cudaMalloc(&v->d, bytes) != cudaSuccess) {
-    fprintf(stderr, "paropt_b200: cudaMalloc of %zu bytes failed\n", bytes);
+  v->managed = ctx->managed_vectors != 0;
+  const cudaError_t err = v->managed ? cudaMallocManaged(&v->d, bytes) : cudaMalloc(&v->d, bytes);
+  if (err != cudaSuccess) {
+    fprintf(stderr, "paropt_b200: %s of %zu bytes failed\n",
+            v->managed ? "cudaMallocManaged" : "cudaMalloc", bytes);
     delete v;
     return nullptr;
   }
-  cudaMemsetAsync(v->d, 0, bytes, ctx->stream);
+  cudaMemsetAsync(v->d, 0, bytes, ctx->stream);  // first touch on the device
   return v;
 }
 
@@ -561,6 +579,7 @@ void pcu_vec_destroy(pcu_vec *v) {
 int pcu_vec_size(pcu_vec *v) { return v->n; }
 
 int pcu_vec_set(pcu_vec *v, double alpha) {
+  pcu_vec_ready(v);
   VecOpF f;
   f.op = 0;
   f.alpha = alpha;
@@ -571,6 +590,7 @@ int pcu_vec_set(pcu_vec *v, double alpha) {
 }
 
 int pcu_vec_zero(pcu_vec *v) {
+  pcu_vec_ready(v);
   PCU_CUDA_OK(cudaMemsetAsync(v->d, 0, (size_t)v->n * sizeof(double),
                               v->ctx->stream));
   return 0;
@@ -580,6 +600,8 @@ int pcu_vec_copy(pcu_vec *dst, pcu_vec *src) {
   // a mismatched vector is silently ignored in the reference
   // (ParOptVec.cpp:51-55); here a size mismatch is an error
   if (!src || src->n != dst->n) return 1;
+  pcu_vec_ready(dst);
+  pcu_vec_ready(src);
   PCU_CUDA_OK(cudaMemcpyAsync(dst->d, src->d, (size_t)dst->n * sizeof(double),
                               cudaMemcpyDeviceToDevice, dst->ctx->stream));
   return 0;
@@ -619,13 +641,16 @@ int pcu_vec_mdot(pcu_vec *x, pcu_vec **vecs, int nvecs, double *out) {
   ColTable cols;
   for (int k = 0; k < nvecs; k++) {
     if (!vecs[k] || vecs[k]->n != x->n) return 1;
+    pcu_vec_ready(vecs[k]);
     cols.p[k] = vecs[k]->d;
   }
+  pcu_vec_ready(x);
   if (pcu_mdot_enqueue(x->ctx, x->d, cols, nvecs, x->n, 0)) return 1;
   return x->ctx->big_fetch(nvecs, out);
 }
 
 int pcu_vec_scale(pcu_vec *v, double alpha) {
+  pcu_vec_ready(v);
   VecOpF f;
   f.op = 1;
   f.alpha = alpha;
@@ -637,6 +662,8 @@ int pcu_vec_scale(pcu_vec *v, double alpha) {
 
 int pcu_vec_axpy(pcu_vec *y, double alpha, pcu_vec *x) {
   if (!x || x->n != y->n) return 1;
+  pcu_vec_ready(x);
+  pcu_vec_ready(y);
   VecOpF f;
   f.op = 2;
   f.alpha = alpha;
@@ -646,10 +673,24 @@ int pcu_vec_axpy(pcu_vec *y, double alpha, pcu_vec *x) {
   return launch_plain(y->ctx, f, y->n, rb);
 }
 
-double *pcu_vec_device_ptr(pcu_vec *v) { return v->d; }
+double *pcu_vec_device_ptr(pcu_vec *v) {
+  pcu_vec_ready(v);
+  return v->d;
+}
+
+// ParOptVec::getArray (ParOptVec.cpp:211) for host loops: unified memory, valid on
+// the host once the stream has drained; the next library call moves it back.
+double *pcu_vec_host_ptr(pcu_vec *v) {
+  if (!v || !v->managed) return nullptr;
+  if (cudaStreamSynchronize(v->ctx->stream) != cudaSuccess) return nullptr;
+  v->host_touched = true;
+  return v->d;
+}
+int pcu_vec_is_managed(pcu_vec *v) { return v && v->managed ? 1 : 0; }
 
 int pcu_vec_to_host(pcu_vec *v, double *host, int n) {
   if (n > v->n) return 1;
+  pcu_vec_ready(v);
   PCU_CUDA_OK(cudaMemcpyAsync(host, v->d, (size_t)n * sizeof(double),
                               cudaMemcpyDeviceToHost, v->ctx->stream));
   PCU_CUDA_OK(cudaStreamSynchronize(v->ctx->stream));
@@ -658,6 +699,7 @@ int pcu_vec_to_host(pcu_vec *v, double *host, int n) {
 
 int pcu_vec_from_host(pcu_vec *v, const double *host, int n) {
   if (n > v->n) return 1;
+  pcu_vec_ready(v);
   PCU_CUDA_OK(cudaMemcpyAsync(v->d, host, (size_t)n * sizeof(double),
                               cudaMemcpyHostToDevice, v->ctx->stream));
   PCU_CUDA_OK(cudaStreamSynchronize(v->ctx->stream));

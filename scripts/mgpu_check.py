@@ -27,7 +27,7 @@ for name, iters in (("C2_small", 41), ("C3_small", 50)):
     ip = InteriorPoint(prob, dict(cfg["options"], history_level=2, max_major_iters=iters + 1))
     ip.optimize()
     hist = ip.history()
-    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
+    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"])
     verdict["cases"][name] = {"compared": n, "first_violation": first,
                               "worst": max(worst.values()), "nvars_local": prob.nvars}
     ip.free()
@@ -67,8 +67,8 @@ for label, nbig in (("C3_big", 8 * 5003 * ctx.size), ("C2_big", 50001 * ctx.size
     plain = run_big(lambda: problem_from_config(ctx, cfg_big), True)
     host = run_big(lambda: BuiltinProblem(ctx, "sepquad", host=True, nthreads=2,
                                           **cfg_big["problem"]), False)
-    n1, w1, f1 = compare_histories(plain, fused, max_iters=12)
-    n2, w2, f2 = compare_histories(fused, host, max_iters=12)
+    n1, w1, f1 = compare_histories(plain, fused, max_iters=12, cfg=cfg_big)
+    n2, w2, f2 = compare_histories(fused, host, max_iters=12, cfg=cfg_big)
     verdict["cases"][label] = {"compared": min(n1, n2), "first_violation": f1 or f2,
                                "worst": max(max(w1.values()), max(w2.values()))}
 if ctx.rank == 0:

@@ -129,7 +129,7 @@ def test_two_rank_gloo_oracle_matches_reference(tmp_path, name, iters):
     hist = json.load(open(out))
     for gname in (name + "_np2", name):
         gold = load_golden(gname)
-        n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
+        n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"])
         assert n == iters and first is None, (gname, first, worst)
 
 

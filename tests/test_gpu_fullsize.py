@@ -45,14 +45,16 @@ def run(ctx, cfg, iters, staged=True):
     return hist
 
 
-@pytest.mark.parametrize("name", ["C3_full", "C2_full"])
-def test_first_iterations_match_reference_at_full_size(ctx, name):
+# C4_full (n = 32M, c = 100, L-SR1 m = 20: the wide Gram path at full size): 10
+# iterations -- q grows by one per iteration, and from iteration ~10 on the
+# reference's unsafeguarded L-SR1 amplifies round-off (tests/test_oracle_golden.py).
+@pytest.mark.parametrize("name,iters", [("C3_full", 12), ("C2_full", 12), ("C4_full", 10)])
+def test_first_iterations_match_reference_at_full_size(ctx, name, iters):
     if not os.path.exists(os.path.join(HERE, "golden", name + ".json")):
         pytest.skip("fixture not generated")
     gold = load_golden(name)
-    iters = 12
     hist = run(ctx, gold["config"], iters + 1)
-    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
+    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"])
     assert n == iters and first is None, (first, worst)
     for row, rec in zip(gold["log"][:iters], hist):
         assert row["info"] == rec["info"], (row, rec["iter"])
@@ -62,7 +64,7 @@ def test_staged_and_register_fed_kernels_agree_at_full_size(ctx):
     cfg = configs.get("C3")
     a = run(ctx, cfg, 7, staged=True)
     b = run(ctx, cfg, 7, staged=False)
-    n, worst, first = compare_histories(b, a, max_iters=6)
+    n, worst, first = compare_histories(b, a, max_iters=6, cfg=cfg)
     assert n == 6 and first is None, (first, worst)
 
 

@@ -239,7 +239,7 @@ def test_host_callback_problem_matches_builtin(ctx):
     prob = HostRosen(ctx, 999)
     ip = InteriorPoint(prob, dict(gold["config"]["options"], history_level=2))
     ip.optimize()
-    n, worst, first = compare_histories(gold["history"], ip.history())
+    n, worst, first = compare_histories(gold["history"], ip.history(), cfg=gold["config"])
     assert first is None, (first, worst)
     assert ip.counters()[0] == gold["final"]["niter"]
     assert prob.h2d_bytes > 0 and prob.d2h_bytes > 0

@@ -68,7 +68,7 @@ def test_fused_paths_match_oracle_and_plain_path(ctx, name, n, iters):
                               dict(cfg["options"], max_major_iters=iters))
     ref.optimize()
     for other, label in ((ref.history, "oracle"), (plain, "plain path")):
-        cnt, worst, first = compare_histories(other, fused, max_iters=iters - 1)
+        cnt, worst, first = compare_histories(other, fused, max_iters=iters - 1, cfg=cfg)
         assert cnt == iters - 1 and first is None, (label, first, worst)
 
 
@@ -107,5 +107,5 @@ def test_weighting_blocks_ending_inside_a_slab(ctx):
     opts = dict(configs.get("C3", 8192)["options"])
     fused = run(ctx, Partial, opts, 14, False)
     plain = run(ctx, Partial, opts, 14, True)
-    cnt, worst, first = compare_histories(plain, fused, max_iters=13)
+    cnt, worst, first = compare_histories(plain, fused, max_iters=13, nvars=8192)
     assert cnt == 13 and first is None, (first, worst)

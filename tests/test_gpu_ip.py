@@ -38,7 +38,7 @@ def run_gpu(ctx, cfg, max_iters=None, history_level=2):
 def test_full_history_matches_reference(ctx, name):
     gold = load_golden(name)
     out = run_gpu(ctx, gold["config"])
-    n, worst, first = compare_histories(gold["history"], out["history"])
+    n, worst, first = compare_histories(gold["history"], out["history"], cfg=gold["config"])
     assert first is None, (first, worst)
     assert n == len(gold["history"])
     niter, neval, ngeval = out["counters"]
@@ -55,7 +55,7 @@ def test_full_history_matches_reference(ctx, name):
 def test_prefix_history_matches_reference(ctx, name, iters):
     gold = load_golden(name)
     out = run_gpu(ctx, gold["config"], max_iters=iters + 1)
-    n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters)
+    n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters, cfg=gold["config"])
     assert n == iters
     assert first is None, (first, worst)
 
@@ -83,7 +83,7 @@ def test_host_array_problem_matches_reference(ctx, name, iters, flavour):
     h2d, d2h = prob.transfer_bytes()
     ip.free()
     prob.free()
-    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters)
+    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"])
     assert n == iters and first is None, (first, worst)
     nbytes = 8 * prob.nvars
     # gradients: g + ncon columns per gradient evaluation (+ x, lb, ub per
@@ -94,7 +94,8 @@ def test_host_array_problem_matches_reference(ctx, name, iters, flavour):
     assert d2h == nbytes * neval
 
 
-from tests.test_oracle_golden import VARIANT_ITERS, VARIANT_NAMES  # noqa: E402
+from tests.parity import RTOL  # noqa: E402
+from tests.test_oracle_golden import VARIANT_ITERS, VARIANT_NAMES, VARIANT_RTOL  # noqa: E402
 
 
 @pytest.mark.parametrize("name", VARIANT_NAMES)
@@ -112,7 +113,8 @@ def test_option_variants_match_reference(ctx, name):
     # non-convex run; compared over the first 16 iterations.
     if name == "C1_var_lsq_start":
         iters = 16
-    n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters)
+    n, worst, first = compare_histories(gold["history"], out["history"], max_iters=iters,
+                                        cfg=gold["config"], rtol=VARIANT_RTOL.get(name, RTOL))
     assert first is None, (first, worst)
     assert n == iters
     for row, rec in list(zip(gold["log"], out["history"]))[:iters]:

@@ -151,7 +151,7 @@ def test_interior_point_with_a_supplied_quasi_newton_object(ctx):
     ip = InteriorPoint(prob, dict(cfg["options"], history_level=2))
     ip.setQuasiNewton(qn)
     ip.optimize()
-    n, worst, first = compare_histories(gold["history"], ip.history())
+    n, worst, first = compare_histories(gold["history"], ip.history(), cfg=gold["config"])
     assert first is None and n == len(gold["history"]), (first, worst)
     b0, d0, M, Z = qn.getCompactMat()
     assert len(Z) == 2 * cfg["options"]["qn_subspace_size"] and b0 > 0.0

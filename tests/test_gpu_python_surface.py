@@ -41,7 +41,7 @@ def test_optimizer_facade_matches_oracle(tmp_path):
     x, z, zw, zl, zu = opt.getOptimizedPoint()
     ora = InteriorPointOracle(ref_prob, dict(cfg["options"], max_major_iters=25))
     ora.optimize()
-    cnt, worst, first = compare_histories(ora.history, opt.ip.history(), max_iters=24)
+    cnt, worst, first = compare_histories(ora.history, opt.ip.history(), max_iters=24, cfg=cfg)
     assert cnt == 24 and first is None, (first, worst)
     assert np.allclose(np.asarray(x), ora.variables.x, rtol=1e-9, atol=1e-12)
     assert np.allclose(z, ora.variables.z, rtol=1e-8, atol=1e-12)
