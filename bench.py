@@ -178,6 +178,86 @@ def run_ref_driver(cfg, nranks, timeout=1200):
     return [r for r in recs if "iter" in r], [r for r in recs if "final" in r][0]
 
 
+def reference_full_size(cfg_name, ntotal, warmup, steps, timed_budget_s=150.0,
+                        total_budget_s=420.0):
+    """The reference arm at the metric's OWN configuration: the unmodified reference
+    (oracle/_ref/ref_driver) at the full `ntotal`, one shim rank per host core.  The
+    driver stamps every major iteration with its wall clock; the run is stopped once
+    `steps` iterations after the warm-up are on record, or -- so that the arm ends
+    within a few minutes on any host -- once the timed region has lasted
+    `timed_budget_s` (at least 3 timed iterations are always taken)."""
+    import signal
+    from oracle.make_golden import DRIVER, driver_args  # checker side (reference arm)
+
+    if not os.path.exists(DRIVER):
+        return None
+    cores = host_cores()
+    nranks = max(1, min(cores, 64))
+    if ntotal >= (1 << 20):
+        nranks = max(1, min(nranks, ntotal // (1 << 16)))
+    cfg = configs.get(cfg_name, ntotal)
+    cfg["options"] = dict(cfg["options"], max_major_iters=warmup + steps + 1)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", PCU_SHIM_NP=str(nranks))
+    t_start = time.time()
+    with tempfile.TemporaryDirectory() as tmp:
+        hist = os.path.join(tmp, "hist.jsonl")
+        cmd = [DRIVER] + driver_args(cfg) + ["hist=" + hist, "log=/dev/null"]
+        proc = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL,
+                                stderr=subprocess.DEVNULL, start_new_session=True)
+        walls = []
+        stopped = "completed"
+
+        def read():
+            out = []
+            try:
+                for line in open(hist):
+                    try:
+                        r = json.loads(line)
+                    except ValueError:
+                        break  # partial last line
+                    if "iter" in r:
+                        out.append(r["wall"])
+            except OSError:
+                pass
+            return out
+
+        while proc.poll() is None:
+            time.sleep(0.5)
+            walls = read()
+            timed = len(walls) - 1 - warmup
+            if timed >= steps:
+                stopped = "all steps on record"
+                break
+            if timed >= 3 and walls[-1] - walls[warmup] >= timed_budget_s:
+                stopped = "timed-region budget of %.0f s" % timed_budget_s
+                break
+            if time.time() - t_start > total_budget_s and timed >= 1:
+                stopped = "total budget of %.0f s" % total_budget_s
+                break
+        if proc.poll() is None:
+            try:
+                os.killpg(proc.pid, signal.SIGKILL)
+            except OSError:
+                pass
+            proc.wait()
+        walls = read() or walls
+    if len(walls) < 3:
+        return None
+    k0 = min(warmup, len(walls) - 2)
+    k1 = min(len(walls) - 1, k0 + steps)
+    dt = walls[k1] - walls[k0]
+    rate = (k1 - k0) / dt
+    return {
+        "value": rate, "unit": UNIT, "cores": nranks, "kind": "reference",
+        "sample": ("unmodified reference ParOptInteriorPoint (oracle/_ref) at the full size "
+                   "n=%d, %d shim ranks (one per host core), major iterations %d..%d timed "
+                   "(%.1f s, the driver's own wall-clock stamps); run stopped: %s"
+                   % (ntotal, nranks, k0, k1, dt, stopped)),
+        "sample_n": ntotal, "steps": k1 - k0, "warmup": k0, "same_config": True,
+        "seconds_per_iteration": dt / (k1 - k0), "wall_s": time.time() - t_start,
+    }
+
+
 def reference_rate(cfg_name, ntotal, warmup, steps, budget_s=25.0):
     """Iterations/s of the reference's CPU implementation at `ntotal` variables,
     measured on a bounded sample (smaller n, linear scaling in n) with one shim
@@ -265,6 +345,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity across the N ranks before anything is timed ------------------
+    # The small named workloads, partitioned over the ranks of THIS run exactly as
+    # the timed workload is, against the histories of the unmodified reference
+    # (tests/golden, the rule of tests/parity.py).
+    parity = None
+    if not args.no_parity:
+        from tests.parity import compare_histories, load_golden
+
+        parity = {"world": world, "first_violation": None, "worst": 0.0, "cases": {},
+                  "rule": "tests/parity.py (RTOL 1e-10); goldens = unmodified reference"}
+        for gname, giters in (("C2_small", 41), ("C3_small", 50)):
+            gold = load_golden(gname)
+            gcfg = gold["config"]
+            gp = problem_from_config(ctx, gcfg)
+            gip = InteriorPoint(gp, dict(gcfg["options"], history_level=2,
+                                         max_major_iters=giters + 1))
+            gip.optimize()
+            ghist = gip.history()
+            gip.free()
+            gp.free()
+            n_cmp, worst, first = compare_histories(gold["history"], ghist, max_iters=giters,
+                                                    cfg=gcfg)
+            w = max(v for k, v in worst.items())
+            parity["cases"][gname] = {"compared": n_cmp, "worst": float("%.3e" % w),
+                                      "worst_key": max(worst, key=worst.get),
+                                      "first_violation": first}
+            parity["worst"] = max(parity["worst"], float("%.3e" % w))
+            if first is not None and parity["first_violation"] is None:
+                parity["first_violation"] = dict(first, case=gname)
+
     # ---- device-resident run: `value` --------------------------------------
     prob = problem_from_config(ctx, cfg)
     N, W = prob.nvars, prob.nwcon
@@ -316,7 +426,9 @@ def run_ours(args):
         achieved = words * 8 / (avg_ms * 1e-3) / 1e9 if words else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        # ncu DRAM bytes of the kernel at the 1-GPU size of the metric (C3): they say
+        # nothing about a rank's share at N > 1 or about another workload
+        if os.path.exists(tpath) and world == 1 and args.config == "C3" and args.n is None:
             try:
                 traffic = json.load(open(tpath)).get(name.split("<")[0].replace("ResFT", "ResF"))
             except Exception:
@@ -405,15 +517,13 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak" if weak else "strong",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %s n=%d ncon=%d nwcon=%d qn=%s m=%d" % (
-                args.config, cfg["kind"], ntotal, c, ntotal // 8 if cfg["problem"].get("nw") else 0,
-                cfg["options"].get("qn_type", "bfgs"), msub),
+            "config": {"workload": workload_name(args.config, cfg, ntotal),
                 "n_per_gpu": N, "partition": "block-row over %d GPU(s)" % world,
                 "l2_note": "every pass streams >= 0.5 GB per vector (>> 126 MB L2)",
                 "warmup_note": "warm-up raised to %d so the L-BFGS memory is full" % QN_WARMUP},
             "kkt_solve_ms": kkt_ms, "kkt_roofline_frac": kkt_frac,
             "callback_ms_per_step": cb_ms, "iter_roofline_frac": iter_frac,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
             "gpu_launches": launches, "clocks": clocks,
         }
         emit(line)
@@ -422,26 +532,44 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def workload_name(cfg_name, cfg, ntotal):
+    c = cfg["problem"]["ncon"]
+    return "%s: %s n=%d ncon=%d nwcon=%d qn=%s m=%d" % (
+        cfg_name, cfg["kind"], ntotal, c, ntotal // 8 if cfg["problem"].get("nw") else 0,
+        cfg["options"].get("qn_type", "bfgs"), cfg["options"].get("qn_subspace_size", 10))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cfg = configs.get(args.config, args.n)
+    if bool(cfg.get("per_gpu")) and args.n is None:
+        cfg["problem"]["ntotal"] = cfg["problem"]["ntotal"] * world
     ntotal = cfg["problem"]["ntotal"]
     warmup = max(args.warmup, QN_WARMUP)
     t0 = time.time()
-    res = reference_rate(args.config, ntotal, warmup, args.steps)
+    if args.ref_sample:
+        res = reference_rate(args.config, ntotal, warmup, args.steps)
+    else:
+        res = reference_full_size(args.config, ntotal, warmup, args.steps)
     if res is None:
         emit({"impl": "reference",
               "unavailable": "oracle/_ref/ref_driver has not been built"})
         return
+    steps = res.get("steps", args.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-        "warmup": warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s n=%d (CPU sample n=%d, linear in n)" % (
-            args.config, ntotal, res["sample_n"])},
+        "n_gpus": world, "steps": steps,
+        "warmup": res.get("warmup", warmup), "ms_per_step": 1e3 / res["value"],
+        "higher_is_better": True,
+        "scaling": "weak" if cfg.get("per_gpu") and args.n is None else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, cfg, ntotal),
+                   "reference_arm": ("CPU, the metric's own size" if res.get("same_config")
+                                     else "CPU sample n=%d, linear in n" % res["sample_n"]),
+                   "steps_requested": args.steps},
         "cpu_baseline": res,
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -466,6 +594,11 @@ def main():
     ap.add_argument("--no-kernel-profile", action="store_true",
                     help="no per-kernel CUDA events in the timed region (roofline = null)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the golden-history comparisons before the timed region")
+    ap.add_argument("--ref-sample", action="store_true",
+                    help="--impl reference on a bounded smaller-n sample (scaled by n) "
+                         "instead of the full size")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -45,6 +45,15 @@
 #include "ParOptOptimizer.h"
 #undef private
 
+// -DPCU_ADAPTERS (oracle/Makefile target _ref/adapter_driver): the same driver, the
+// same UNMODIFIED reference objects, but the problem classes hand out CUDA vectors,
+// the CUDA block matrix and the CUDA compact quasi-Newton object through the
+// reference's own factories (src/ParOptProblem.h:58,65,72; setQuasiNewton,
+// IP.cpp:1193) -- tests/adapters/paropt_cuda_adapters.h over include/paropt_b200.h.
+#ifdef PCU_ADAPTERS
+#include "paropt_cuda_adapters.h"
+#endif
+
 // ---------------------------------------------------------------------------
 // Counter-based generator ("Synthetic problems")
 // ---------------------------------------------------------------------------
@@ -85,6 +94,18 @@ class HistoryProblem : public ParOptProblem {
     tr_mode = 0;
   }
   void writeOutput(int iter, ParOptVec *xvec);
+#ifdef PCU_ADAPTERS
+  ParOptVec *createDesignVec() {
+    int nv, nc, nw;
+    getProblemSizes(&nv, &nc, &nw);
+    return new ParOptCudaVec(ParOptCudaContext(), nv);
+  }
+  ParOptVec *createConstraintVec() {
+    int nv, nc, nw;
+    getProblemSizes(&nv, &nc, &nw);
+    return new ParOptCudaVec(ParOptCudaContext(), nw);
+  }
+#endif
 
   ParOptInteriorPoint *ip;
   FILE *hist;
@@ -254,8 +275,22 @@ class SepQuad : public HistoryProblem {
   }
 
   ParOptQuasiDefMat *createQuasiDefMat() {
+#ifdef PCU_ADAPTERS
+    pcu_weighting w;
+    memset(&w, 0, sizeof(w));
+    if (nwc > 0) {
+      w.nwcon = nwc;
+      w.wstart = 0;
+      w.nw = p.nw;
+      w.wstride = p.nw;
+      w.coef0 = 1.0;
+      w.coef_rest = -1.0;
+    }
+    return new ParOptCudaQuasiDefBlockMat(ParOptCudaContext(), n, &w);
+#else
     int nwblock = (nwc > 0) ? 1 : 0;
     return new ParOptQuasiDefBlockMat(this, nwblock);
+#endif
   }
 
   int cls(int i) const { return (p.nw > 0 && (i % p.nw) != 0) ? 1 : 0; }
@@ -412,7 +447,20 @@ class Rosen : public HistoryProblem {
     setNumInequalities(2, nwc);
   }
   ParOptQuasiDefMat *createQuasiDefMat() {
+#ifdef PCU_ADAPTERS
+    pcu_weighting w;
+    memset(&w, 0, sizeof(w));
+    w.nwcon = nwc;
+    w.wstart = nwstart;
+    w.nw = nw;
+    w.wstride = nw + nwskip;
+    w.coef0 = -1.0;
+    w.coef_rest = -1.0;
+    w.wconst = 1.0;
+    return new ParOptCudaQuasiDefBlockMat(ParOptCudaContext(), n, &w);
+#else
     return new ParOptQuasiDefBlockMat(this, 1);
+#endif
   }
   void getVarsAndBounds(ParOptVec *xvec, ParOptVec *lbvec, ParOptVec *ubvec) {
     xvec->set(-1.0);
@@ -620,6 +668,29 @@ int main(int argc, char *argv[]) {
   ParOptInteriorPoint *ip = new ParOptInteriorPoint(prob, options);
   ip->incref();
   prob->ip = ip;
+#ifdef PCU_ADAPTERS
+  {
+    // the compact quasi-Newton object of the options, on the device
+    const char *qn_type = options->getEnumOption("qn_type");
+    if (strcmp(qn_type, "bfgs") == 0 || strcmp(qn_type, "sr1") == 0) {
+      int nv, nc, nw;
+      prob->getProblemSizes(&nv, &nc, &nw);
+      ParOptCudaCompactQN *cqn = new ParOptCudaCompactQN(
+          ParOptCudaContext(), nv, qn_type, options->getIntOption("qn_subspace_size"));
+      if (strcmp(options->getEnumOption("qn_update_type"), "damped_update") == 0)
+        cqn->setBFGSUpdateType(PAROPT_DAMPED_UPDATE);
+      if (strcmp(options->getEnumOption("qn_diag_type"), "yts_over_sts") == 0)
+        cqn->setInitDiagonalType(PAROPT_YTS_OVER_STS);
+      ip->setQuasiNewton(cqn);
+    }
+    if (rank == 0) {
+      double *probe;
+      ip->variables.x->getArray(&probe);
+      fprintf(stderr, "adapter_driver: reference ParOptInteriorPoint on %s vectors\n",
+              dynamic_cast<ParOptCudaVec *>(ip->variables.x) ? "ParOptCudaVec" : "HOST");
+    }
+  }
+#endif
   if (rank == 0 && !hist_path.empty()) prob->hist = fopen(hist_path.c_str(), "w");
 
   double t0 = MPI_Wtime();
@@ -650,6 +721,11 @@ int main(int argc, char *argv[]) {
     }
   }
 
+#ifdef PCU_ADAPTERS
+  if (rank == 0)
+    fprintf(stderr, "adapter_driver: %lld kernels of libparopt_b200 launched\n",
+            (long long)pcu_ctx_kernel_launches(ParOptCudaContext()));
+#endif
   ip->decref();
   options->decref();
   prob->decref();

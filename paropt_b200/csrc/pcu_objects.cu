@@ -153,7 +153,8 @@ int pcu_qn_reset(pcu_qn *h) {
   h->q.reset();
   return 0;
 }
-int pcu_qn_max_size(pcu_qn *h) { return h ? h->q.msub_max : 0; }
+// getMaxLimitedMemorySize (QN.cpp:127, 603): 2 m for L-BFGS, m for L-SR1
+int pcu_qn_max_size(pcu_qn *h) { return h ? h->q.max_size() : 0; }
 
 // int update(x, z, zw, s, y): 0 normal, 1 damped, 2 skipped (QN.cpp:162-334, 636-747)
 int pcu_qn_update(pcu_qn *h, pcu_vec *s, pcu_vec *y, int *update_type) {

@@ -166,3 +166,19 @@ def test_header_is_plain_c(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
                     "-I", os.path.join(root, "include"), str(src)], check=True)
+
+
+def test_adapter_driver_links_against_the_product_library():
+    """oracle/_ref/adapter_driver (the reference running on the CUDA adapter classes,
+    tests/adapters/paropt_cuda_adapters.h) is linked against libparopt_b200.so and
+    resolves the C-ABI symbols the adapters call -- no compute here (no GPU)."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "adapter_driver")
+    if not os.path.exists(drv):
+        pytest.skip("adapter_driver not built (needs /root/reference at build time)")
+    out = subprocess.run(["ldd", drv], capture_output=True, text=True).stdout
+    assert "libparopt_b200.so" in out and "not found" not in out, out
+    syms = subprocess.run(["nm", "-D", "--undefined-only", drv], capture_output=True,
+                          text=True).stdout
+    for name in ("pcu_vec_host_ptr", "pcu_vec_mdot", "pcu_blockmat_factor", "pcu_qn_update",
+                 "pcu_qn_compact", "pcu_ctx_set_param"):
+        assert name in syms, name

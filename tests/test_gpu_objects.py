@@ -104,7 +104,8 @@ def test_quasi_newton_object(ctx, kind, n, m, updates):
     comm = SerialComm()
     ref = LBFGS(comm, n, m) if kind == "bfgs" else LSR1(comm, n, m)
     qn = QuasiNewton(ctx, n, kind, m)
-    assert qn.getMaxLimitedMemorySize() == m
+    # ParOptLBFGS: 2 m, ParOptLSR1: m (QN.cpp:127, 603)
+    assert qn.getMaxLimitedMemorySize() == (2 * m if kind == "bfgs" else m)
     hdiag = 1.0 + 4.0 * rng.random(n)
     x = rng.standard_normal(n)
     dx, dy, dacc = vec(ctx, x), PVec(ctx, n), vec(ctx, np.ones(n))
