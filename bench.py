@@ -351,7 +351,7 @@ def run_ours(args):
     # (tests/golden, the rule of tests/parity.py).
     parity = None
     if not args.no_parity:
-        from tests.parity import compare_histories, load_golden
+        from tests.parity import checked, compare_histories, load_golden
 
         parity = {"world": world, "first_violation": None, "worst": 0.0, "cases": {},
                   "rule": "tests/parity.py (RTOL 1e-10); goldens = unmodified reference"}
@@ -367,9 +367,13 @@ def run_ours(args):
             gp.free()
             n_cmp, worst, first = compare_histories(gold["history"], ghist, max_iters=giters,
                                                     cfg=gcfg)
-            w = max(v for k, v in worst.items())
+            chk = checked(worst)
+            w = max(chk.values())
             parity["cases"][gname] = {"compared": n_cmp, "worst": float("%.3e" % w),
-                                      "worst_key": max(worst, key=worst.get),
+                                      "worst_key": max(chk, key=chk.get),
+                                      "residual_norms_rel": float("%.3e" % max(
+                                          [v for k, v in worst.items() if k.startswith("rel:")]
+                                          + [0.0])),
                                       "first_violation": first}
             parity["worst"] = max(parity["worst"], float("%.3e" % w))
             if first is not None and parity["first_violation"] is None:

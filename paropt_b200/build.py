@@ -16,6 +16,11 @@ FLAGS = [
 ] + os.environ.get("PCU_EXTRA_FLAGS", "").split()
 
 
+# pcu_dense.cu: host and device must execute the same multiply / add sequence
+# (the device chain of the KKT solve reproduces the host path bit for bit)
+PER_FILE_FLAGS = {"pcu_dense.cu": ["-fmad=false"]}
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
@@ -34,7 +39,7 @@ def build(force=False, verbose=False):
     os.makedirs(bdir, exist_ok=True)
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + PER_FILE_FLAGS.get(os.path.basename(src), []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE,
                                             stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -166,7 +166,7 @@ int pcu_ip_iterate(pcu_ip *ip, int max_iters, int *converged) {
     if (ip->iterate_once(&conv)) return 1;
   }
   if (converged) *converged = conv;
-  return 0;
+  return ip->flush_times();
 }
 
 int pcu_ip_optimize(pcu_ip *ip) {
@@ -175,7 +175,7 @@ int pcu_ip_optimize(pcu_ip *ip) {
   while (!conv && ip->ls.k < ip->opt.max_major_iters) {
     if (ip->iterate_once(&conv)) return 1;
   }
-  return 0;
+  return ip->flush_times();
 }
 
 // resetDesignAndBounds (IP.cpp:1249-1251)
@@ -299,6 +299,7 @@ const char *pcu_ip_history_info(pcu_ip *ip, int k) {
 
 int pcu_ip_iter_times(pcu_ip *ip, int k, double *total_ms, double *callback_ms,
                       double *kkt_ms) {
+  if (ip->flush_times()) return 1;
   if (k < 0 || k >= (int)ip->times.size()) return 1;
   if (total_ms) *total_ms = ip->times[k].total_ms;
   if (callback_ms) *callback_ms = ip->times[k].callback_ms;

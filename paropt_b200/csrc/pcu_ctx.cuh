@@ -69,6 +69,16 @@ struct pcu_ctx {
   void prof_end();
   void prof_collect();  // call after a stream synchronisation
 
+  // Deferred results: defer() marks every slot reserved so far; the next fetch() -- the
+  // caller's own or one made by a problem callback in between -- brings them to the
+  // host in the same copy and keeps them aside for take_deferred(), handing its caller
+  // only the slots reserved after the mark.  One synchronisation serves both.
+  int deferred_n = 0;
+  bool deferred_ready = false;
+  std::vector<double> deferred_vals;
+  void defer() { deferred_n = result_used; deferred_ready = false; }
+  int take_deferred(double *out, int n);
+
   RedBuf redbuf(int ns, int nx, int nm);       // reserves a result slot
   int fetch(double *out);                      // all pending slots -> host, sync
   int big_reserve(size_t nresult, size_t npartials);

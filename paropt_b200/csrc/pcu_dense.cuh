@@ -1,0 +1,297 @@
+// pcu_dense.cuh -- the small dense algebra of the KKT solve (the c x c matrix G,
+// the q x q matrix Ce, the Sherman-Morrison-Woodbury coefficients) as ONE piece of
+// host/device code, so that the chain
+//     Gram pass -> [this] -> pass 2 + refinement residual -> [this] -> pass 2 + statistics
+// runs on the device without a host round trip (pcu_dense.cu: single-CTA kernel on
+// a flat work buffer staged in shared memory), while every other configuration keeps
+// the host path of pcu_ip_solve.cu.  Reference: setUpKKTDiagSystem's G (IP.cpp:1932-
+// 1969, dgetrf), setUpKKTSystem's Ce (IP.cpp:2646-2664, dgetrf), the dense part of
+// solveKKTDiagSystem (IP.cpp:2150-2170, 2288-2306) and of computeKKTStep
+// (IP.cpp:2716-2735), computeKKTRes / addKKTResStep's dense residual
+// (IP.cpp:1401-1407, 1535-1541), ParOptLBFGS::mult's compact solve (QN.cpp:398-412).
+//
+// The translation unit that holds the kernel is compiled with -fmad=false: the device
+// executes exactly the multiply / add sequence of the host compiler, so the chain
+// reproduces the host path bit for bit on the same inputs.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#define PCU_DENSE_MAXM 32  // chain mode: ncon + quasi-Newton width <= 32 (ld <= 40)
+#define PCU_HD __host__ __device__ __forceinline__
+
+// Offsets (in doubles) into the flat work buffer.  [0, S) is written by the host
+// before the chain (inputs), [S, total) is produced on the device and read back.
+struct DenseOff {
+  int c, q, ld, m;
+  int mu, vz, vs, vt, vzs, vzt, cc, gs, gt;  // inputs: barrier, dense variables, c(x), penalties
+  int M, d0, Mf, mpiv;                       // quasi-Newton compact matrix, its LU and pivots
+  int S;                                     // symmetrised Gram matrix (ld x ld)
+  int Graw, Gfac, gpiv, Ceraw, Cefac, cpiv;
+  int bz, bs, bt, bzs, bzt;                  // dense residual (right-hand side)
+  int yz, ys, yt, yzs, yzt;                  // dense step (accumulated)
+  int r, vtp;                                // [A|Z]^T t1 of the current solve; [A|Z]^T step
+  int coefA, coefB;                          // alpha | beta of pass 2 + residual; alpha of the last pass
+  int total;
+};
+
+static inline DenseOff pcu_dense_offsets(int c, int q, int ld) {
+  DenseOff o;
+  o.c = c;
+  o.q = q;
+  o.ld = ld;
+  o.m = c + q;
+  int p = 0;
+  auto take = [&p](int n) {
+    const int at = p;
+    p += n;
+    return at;
+  };
+  o.mu = take(2);
+  o.vz = take(c); o.vs = take(c); o.vt = take(c); o.vzs = take(c); o.vzt = take(c);
+  o.cc = take(c); o.gs = take(c); o.gt = take(c);
+  o.M = take(q * q); o.d0 = take(q); o.Mf = take(q * q); o.mpiv = take(q);
+  p = (p + 1) & ~1;
+  o.S = take(ld * ld);
+  o.Graw = take(c * c); o.Gfac = take(c * c); o.gpiv = take(c);
+  o.Ceraw = take(q * q); o.Cefac = take(q * q); o.cpiv = take(q);
+  o.bz = take(c); o.bs = take(c); o.bt = take(c); o.bzs = take(c); o.bzt = take(c);
+  o.yz = take(c); o.ys = take(c); o.yt = take(c); o.yzs = take(c); o.yzt = take(c);
+  o.r = take(o.m); o.vtp = take(o.m);
+  p = (p + 1) & ~1;
+  o.coefA = take(2 * PCU_DENSE_MAXM);
+  o.coefB = take(PCU_DENSE_MAXM);
+  o.total = (p + 1) & ~1;
+  return o;
+}
+
+// LAPACK dgetrf / dgetrs restated (partial pivoting, column-major); pivots are kept
+// as doubles inside the flat buffer.  Same statements as pcu_lu_factor / pcu_lu_solve.
+PCU_HD int pcu_dense_lu_factor(int n, double *A, double *piv) {
+  int info = 0;
+  for (int k = 0; k < n; k++) {
+    int p = k;
+    double best = fabs(A[k + n * k]);
+    for (int i = k + 1; i < n; i++) {
+      const double v = fabs(A[i + n * k]);
+      if (v > best) {
+        best = v;
+        p = i;
+      }
+    }
+    piv[k] = (double)p;
+    if (A[p + n * k] == 0.0) {
+      if (!info) info = k + 1;
+      continue;
+    }
+    if (p != k) {
+      for (int j = 0; j < n; j++) {
+        const double t = A[k + n * j];
+        A[k + n * j] = A[p + n * j];
+        A[p + n * j] = t;
+      }
+    }
+    const double inv = 1.0 / A[k + n * k];
+    for (int i = k + 1; i < n; i++) A[i + n * k] *= inv;
+    for (int j = k + 1; j < n; j++) {
+      const double akj = A[k + n * j];
+      if (akj != 0.0) {
+        for (int i = k + 1; i < n; i++) A[i + n * j] -= A[i + n * k] * akj;
+      }
+    }
+  }
+  return info;
+}
+
+PCU_HD void pcu_dense_lu_solve(int n, const double *LU, const double *piv, double *b) {
+  for (int k = 0; k < n; k++) {
+    const int p = (int)piv[k];
+    if (p != k) {
+      const double t = b[k];
+      b[k] = b[p];
+      b[p] = t;
+    }
+  }
+  for (int k = 0; k < n; k++) {
+    const double bk = b[k];
+    if (bk != 0.0) {
+      for (int i = k + 1; i < n; i++) b[i] -= LU[i + n * k] * bk;
+    }
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    b[k] /= LU[k + n * k];
+    const double bk = b[k];
+    for (int i = 0; i < k; i++) b[i] -= LU[i + n * k] * bk;
+  }
+}
+
+// Dense residual of computeKKTRes (with_step = 0) / addKKTResStep (with_step = 1:
+// the step is w[yz..], [A|Z]^T px is w[vtp]).
+PCU_HD void pcu_dense_residual(double *w, const DenseOff &o, int with_step) {
+  const double mu = w[o.mu];
+  for (int i = 0; i < o.c; i++) {
+    const double z = w[o.vz + i], s = w[o.vs + i], t = w[o.vt + i];
+    const double zs = w[o.vzs + i], zt = w[o.vzt + i];
+    double rz = -(w[o.cc + i] - s + t);
+    double rs = -(w[o.gs + i] - zs + z);
+    double rt = -(w[o.gt + i] - zt - z);
+    double rzs = -(s * zs - mu);
+    double rzt = -(t * zt - mu);
+    if (with_step) {
+      const double pz = w[o.yz + i], ps = w[o.ys + i], pt = w[o.yt + i];
+      const double pzs = w[o.yzs + i], pzt = w[o.yzt + i];
+      rz -= (w[o.vtp + i] - ps + pt);
+      rs += (pzs - pz);
+      rt += (pzt + pz);
+      rzs -= (ps * zs + s * pzs);
+      rzt -= (pt * zt + t * pzt);
+    }
+    w[o.bz + i] = rz;
+    w[o.bs + i] = rs;
+    w[o.bt + i] = rt;
+    w[o.bzs + i] = rzs;
+    w[o.bzt + i] = rzt;
+  }
+}
+
+// G = C0 + S_AA, Ce = S_ZZ - S_ZA G^-1 S_AZ - M / (d d^T), both LU-factored
+// (the host statements of pcu_ip::setUpKKTSystem).  scratch: >= c doubles.
+PCU_HD void pcu_dense_setup(double *w, const DenseOff &o, double *scratch) {
+  const int c = o.c, q = o.q, ld = o.ld, m = o.m;
+  double *S = w + o.S;
+  for (int j = 0; j < m; j++)  // symmetrise from the lower triangle
+    for (int i = j + 1; i < m; i++) S[j + ld * i] = S[i + ld * j];
+  double *Graw = w + o.Graw, *Gfac = w + o.Gfac;
+  for (int j = 0; j < c; j++)
+    for (int i = 0; i < c; i++) Graw[i + c * j] = S[i + ld * j];
+  for (int i = 0; i < c; i++)
+    Graw[i * (c + 1)] += w[o.vs + i] / w[o.vzs + i] + w[o.vt + i] / w[o.vzt + i];
+  for (int i = 0; i < c * c; i++) Gfac[i] = Graw[i];
+  if (c > 0) pcu_dense_lu_factor(c, Gfac, w + o.gpiv);
+  if (q > 0) {
+    double *Ceraw = w + o.Ceraw, *Cefac = w + o.Cefac;
+    double *col = scratch;
+    for (int i = 0; i < q; i++) {
+      for (int j = 0; j < c; j++) col[j] = S[j + ld * (c + i)];
+      if (c > 0) pcu_dense_lu_solve(c, Gfac, w + o.gpiv, col);
+      for (int k = 0; k < q; k++) {
+        double v = S[(c + k) + ld * (c + i)];
+        for (int j = 0; j < c; j++) v -= S[(c + k) + ld * j] * col[j];
+        Ceraw[k + q * i] = v;
+      }
+    }
+    const double *M = w + o.M, *d0 = w + o.d0;
+    for (int j = 0; j < q; j++)
+      for (int i = 0; i < q; i++) Ceraw[i + q * j] -= M[i + q * j] / (d0[i] * d0[j]);
+    for (int i = 0; i < q * q; i++) Cefac[i] = Ceraw[i];
+    pcu_dense_lu_factor(q, Cefac, w + o.cpiv);
+  }
+}
+
+// Dense half of computeKKTStep on the right-hand side w[bz..] with the reductions
+// w[r]: SMW coefficients into `alpha` (m values), the dense step into w[yz..]
+// (added when accumulate), w[vtp] = (accumulate ? vtp : 0) + r + S alpha.
+// scratch: >= 2 m + 5 c doubles.
+PCU_HD void pcu_dense_step(double *w, const DenseOff &o, int accumulate, double *alpha,
+                           double *scratch) {
+  const int c = o.c, q = o.q, ld = o.ld, m = o.m;
+  const double *S = w + o.S, *r = w + o.r;
+  double *yz1 = scratch, *pz = yz1 + c, *ps = pz + c, *pt = ps + c, *pzs = pt + c;
+  double *pzt = pzs + c, *ww = pzt + c, *yz2 = ww + q;
+  for (int i = 0; i < c; i++) {
+    const double s = w[o.vs + i], t = w[o.vt + i], zs = w[o.vzs + i], zt = w[o.vzt + i];
+    yz1[i] = (w[o.bz + i] + (w[o.bzs + i] + s * w[o.bs + i]) / zs -
+              (w[o.bzt + i] + t * w[o.bt + i]) / zt - r[i]);
+  }
+  if (c > 0) pcu_dense_lu_solve(c, w + o.Gfac, w + o.gpiv, yz1);
+  for (int i = 0; i < c; i++) {
+    const double s = w[o.vs + i], t = w[o.vt + i], zs = w[o.vzs + i], zt = w[o.vzt + i];
+    pz[i] = yz1[i];
+    pzs[i] = yz1[i] - w[o.bs + i];
+    pzt[i] = -w[o.bt + i] - yz1[i];
+    ps[i] = (w[o.bzs + i] - s * pzs[i]) / zs;
+    pt[i] = (w[o.bzt + i] - t * pzt[i]) / zt;
+    alpha[i] = yz1[i];
+  }
+  if (q > 0) {
+    for (int kq = 0; kq < q; kq++) {  // Z^T yx = r_Z + S_ZA yz1
+      double v = r[c + kq];
+      for (int j = 0; j < c; j++) v += S[(c + kq) + ld * j] * yz1[j];
+      ww[kq] = v;
+    }
+    pcu_dense_lu_solve(q, w + o.Cefac, w + o.cpiv, ww);
+    for (int j = 0; j < c; j++) {  // second solve: A^T P Z w = S_AZ w
+      double v = 0.0;
+      for (int kq = 0; kq < q; kq++) v += S[j + ld * (c + kq)] * ww[kq];
+      yz2[j] = -v;
+    }
+    if (c > 0) pcu_dense_lu_solve(c, w + o.Gfac, w + o.gpiv, yz2);
+    for (int i = 0; i < c; i++) {
+      const double s = w[o.vs + i], t = w[o.vt + i], zs = w[o.vzs + i], zt = w[o.vzt + i];
+      const double yzs2 = yz2[i], yzt2 = -yz2[i];
+      const double ys2 = -(s * yzs2) / zs;
+      const double yt2 = -(t * yzt2) / zt;
+      pz[i] -= yz2[i];
+      pzs[i] -= yzs2;
+      pzt[i] -= yzt2;
+      ps[i] -= ys2;
+      pt[i] -= yt2;
+      alpha[i] = pz[i];
+    }
+    for (int kq = 0; kq < q; kq++) alpha[c + kq] = -ww[kq];
+  }
+  for (int i = 0; i < c; i++) {
+    if (accumulate) {
+      w[o.yz + i] += pz[i];
+      w[o.ys + i] += ps[i];
+      w[o.yt + i] += pt[i];
+      w[o.yzs + i] += pzs[i];
+      w[o.yzt + i] += pzt[i];
+    } else {
+      w[o.yz + i] = pz[i];
+      w[o.ys + i] = ps[i];
+      w[o.yt + i] = pt[i];
+      w[o.yzs + i] = pzs[i];
+      w[o.yzt + i] = pzt[i];
+    }
+  }
+  for (int i = 0; i < m; i++) {  // [A|Z]^T D0^-1 (d1 + V alpha) = r + S alpha
+    double vv = r[i];
+    for (int j = 0; j < m; j++) vv += S[i + ld * j] * alpha[j];
+    w[o.vtp + i] = accumulate ? w[o.vtp + i] + vv : vv;
+  }
+}
+
+// Phase A: everything between the Gram pass and the pass that applies the first
+// solve and emits the refinement residual.  Sin: the Gram result (ld x ld, lower
+// triangle, row m = [A|Z]^T t1 of the first solve).
+PCU_HD void pcu_dense_phase_a(double *w, const DenseOff &o, double *scratch) {
+  const int c = o.c, q = o.q, ld = o.ld, m = o.m;
+  for (int j = 0; j < m; j++) w[o.r + j] = w[o.S + m + ld * j];
+  pcu_dense_setup(w, o, scratch);
+  pcu_dense_residual(w, o, 0);
+  double *alpha = w + o.coefA, *beta = alpha + PCU_DENSE_MAXM;
+  pcu_dense_step(w, o, 0, alpha, scratch);
+  // coefficients of the linearised residual: z + pz for A, the compact
+  // quasi-Newton solve kap = d0 M^-1 d0 (Z^T p) for Z (IP.cpp:1474-1476)
+  for (int j = 0; j < c; j++) beta[j] = w[o.vz + j] + w[o.yz + j];
+  if (q > 0) {
+    double *kap = scratch;
+    for (int i = 0; i < q; i++) kap[i] = w[o.vtp + c + i] * w[o.d0 + i];
+    pcu_dense_lu_solve(q, w + o.Mf, w + o.mpiv, kap);
+    for (int i = 0; i < q; i++) beta[c + i] = kap[i] * w[o.d0 + i];
+  }
+  pcu_dense_residual(w, o, 1);  // right-hand side of the refinement solve
+}
+
+// Phase B: between that pass (whose reductions r' = [A|Z]^T t1' arrive as `world`
+// rank-ordered partial vectors of `stride` doubles) and the last pass.
+PCU_HD void pcu_dense_phase_b(double *w, const DenseOff &o, const double *red, int world,
+                              int stride, double *scratch) {
+  for (int i = 0; i < o.m; i++) {
+    double v = red[i];
+    for (int rk = 1; rk < world; rk++) v += red[(size_t)rk * stride + i];
+    w[o.r + i] = v;
+  }
+  pcu_dense_step(w, o, 1, w + o.coefB, scratch);
+}

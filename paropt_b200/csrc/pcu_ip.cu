@@ -213,8 +213,21 @@ void QuasiNewton::mat_update() {
 // ParOptLBFGS::update (QN.cpp:162-334) / ParOptLSR1::update (QN.cpp:636-747).
 // One multi-dot pass gives s.S_i and s.Y_i for every stored pair: it provides
 // both Z^T s (for s^T B s) and the new rows of S^T S and L.
+// steal: the caller does not need the contents of s and y afterwards (the optimizer's
+// own s_qn / y_qn): the new pair is stored by exchanging buffers with the slot it
+// replaces instead of two N-sized copies (4 N words per iteration).
+static int qn_store(pcu_vec *slot, pcu_vec *src, int steal) {
+  if (steal && slot->owns && src->owns && slot->managed == src->managed && slot->n == src->n &&
+      slot->ctx == src->ctx) {
+    std::swap(slot->d, src->d);
+    std::swap(slot->host_touched, src->host_touched);
+    return 0;
+  }
+  return pcu_vec_copy(slot, src);
+}
+
 int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
-                        double sTs, const double *sZ, int *update_type) {
+                        double sTs, const double *sZ, int *update_type, int steal) {
   *update_type = 0;
   const int m = msub_max;
   std::vector<double> sS(msub), sY(msub);
@@ -305,10 +318,10 @@ int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
   // store the pair (pointer rotation instead of copies where possible)
   int shift = 0;
   if (msub < m) {
-    if (pcu_vec_copy(S[msub], s) || pcu_vec_copy(Y[msub], y_update)) return 1;
+    if (qn_store(S[msub], s, steal) || qn_store(Y[msub], y_update, steal)) return 1;
     msub++;
   } else if (m > 0) {
-    if (pcu_vec_copy(S[0], s) || pcu_vec_copy(Y[0], y_update)) return 1;
+    if (qn_store(S[0], s, steal) || qn_store(Y[0], y_update, steal)) return 1;
     std::rotate(S.begin(), S.begin() + 1, S.end());
     std::rotate(Y.begin(), Y.begin() + 1, Y.end());
     for (int i = 0; i < msub - 1; i++) D[i] = D[i + 1];
@@ -357,14 +370,17 @@ pcu_ip::~pcu_ip() {
   for (auto v : single) pcu_vec_destroy(v);
   for (auto v : Ac) pcu_vec_destroy(v);
   if (!qn_external) delete qn;
+  if (dense_dev) cudaFree(dense_dev);
+  if (dense_host) cudaFreeHost(dense_host);
   if (outfp && outfp != stdout) fclose(outfp);
-  if (ev_it0) cudaEventDestroy(ev_it0);
-  if (ev_it1) cudaEventDestroy(ev_it1);
-  if (ev_k0) cudaEventDestroy(ev_k0);
-  if (ev_k1) cudaEventDestroy(ev_k1);
-  for (auto &e : cb_events) {
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
+  for (IterEvents &e : evs) {
+    cudaEvent_t all[4] = {e.it0, e.it1, e.k0, e.k1};
+    for (cudaEvent_t ev : all)
+      if (ev) cudaEventDestroy(ev);
+    for (auto &c : e.cb) {
+      cudaEventDestroy(c.first);
+      cudaEventDestroy(c.second);
+    }
   }
 }
 
@@ -386,6 +402,7 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
   if (getenv("PCU_NO_FUSE21")) opt_no_fuse21 = 1;
   if (getenv("PCU_NO_FUSE2S")) opt_no_fuse2s = 1;
   if (getenv("PCU_NO_RHSGRAM")) opt_no_rhsgram = 1;
+  if (getenv("PCU_NO_CHAIN")) opt_no_chain = 1;
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all) {
     for (int i = 0; i < 8; i++) {
@@ -416,10 +433,12 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
   if (ctx->big_reserve((size_t)PCU_MAX_COLS * PCU_MAX_COLS + 64,
                        (size_t)PCU_MAX_BLOCKS * 64 * 15))
     return 1;
-  PCU_CUDA_OK(cudaEventCreate(&ev_it0));
-  PCU_CUDA_OK(cudaEventCreate(&ev_it1));
-  PCU_CUDA_OK(cudaEventCreate(&ev_k0));
-  PCU_CUDA_OK(cudaEventCreate(&ev_k1));
+  for (IterEvents &e : evs) {
+    PCU_CUDA_OK(cudaEventCreate(&e.it0));
+    PCU_CUDA_OK(cudaEventCreate(&e.it1));
+    PCU_CUDA_OK(cudaEventCreate(&e.k0));
+    PCU_CUDA_OK(cudaEventCreate(&e.k1));
+  }
   barrier_param = opt.init_barrier_param;
   rho_penalty_search = opt.init_rho_penalty_search;
   if (initAndCheckDesignAndBounds()) return 1;
@@ -500,32 +519,62 @@ void pcu_ip::refresh_penalties() {  // IP.cpp:343-355, setPenaltyGamma IP.cpp:11
 
 // ------------------------------------------------------------- callbacks
 int pcu_ip::cb_begin() {
-  if (cb_used == cb_events.size()) {
+  IterEvents &e = evs[ev_cur];
+  if (e.cb_used == e.cb.size()) {
     cudaEvent_t a, b;
     PCU_CUDA_OK(cudaEventCreate(&a));
     PCU_CUDA_OK(cudaEventCreate(&b));
-    cb_events.push_back({a, b});
+    e.cb.push_back({a, b});
   }
-  PCU_CUDA_OK(cudaEventRecord(cb_events[cb_used].first, ctx->stream));
+  PCU_CUDA_OK(cudaEventRecord(e.cb[e.cb_used].first, ctx->stream));
   return 0;
 }
 int pcu_ip::cb_end() {
-  PCU_CUDA_OK(cudaEventRecord(cb_events[cb_used].second, ctx->stream));
-  cb_used++;
+  IterEvents &e = evs[ev_cur];
+  PCU_CUDA_OK(cudaEventRecord(e.cb[e.cb_used].second, ctx->stream));
+  e.cb_used++;
   return 0;
 }
-double pcu_ip::cb_collect() {  // after a stream synchronisation
+double pcu_ip::cb_collect() {  // callbacks of the current event set (after a synchronisation)
+  IterEvents &e = evs[ev_cur];
   double ms = 0.0;
-  for (size_t i = 0; i < cb_used; i++) {
+  for (size_t i = 0; i < e.cb_used; i++) {
     float f = 0.f;
-    if (cudaEventSynchronize(cb_events[i].second) == cudaSuccess &&
-        cudaEventElapsedTime(&f, cb_events[i].first, cb_events[i].second) ==
-            cudaSuccess)
+    if (cudaEventSynchronize(e.cb[i].second) == cudaSuccess &&
+        cudaEventElapsedTime(&f, e.cb[i].first, e.cb[i].second) == cudaSuccess)
       ms += f;
   }
-  cb_used = 0;
+  e.cb_used = 0;
   prob->callback_ms += ms;
   return ms;
+}
+// One finished iteration: total / KKT-solve / callback milliseconds into `times`.
+int pcu_ip::collect_times(IterEvents &e) {
+  if (!e.pending) return 0;
+  e.pending = false;
+  PCU_CUDA_OK(cudaEventSynchronize(e.it1));
+  IterTime tm;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.it0, e.it1);
+  tm.total_ms = ms;
+  ms = 0.f;
+  cudaEventElapsedTime(&ms, e.k0, e.k1);
+  tm.kkt_ms = ms;
+  double cb = 0.0;
+  for (size_t i = 0; i < e.cb_used; i++) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, e.cb[i].first, e.cb[i].second) == cudaSuccess) cb += f;
+  }
+  e.cb_used = 0;
+  prob->callback_ms += cb;
+  tm.callback_ms = cb;
+  times.push_back(tm);
+  return 0;
+}
+int pcu_ip::flush_times() {
+  // oldest first: the set that is not current was recorded before the current one
+  if (collect_times(evs[ev_cur ^ 1])) return 1;
+  return collect_times(evs[ev_cur]);
 }
 int pcu_ip::evalObjCon(pcu_vec *x) {
   if (cb_begin()) return 1;

@@ -94,7 +94,7 @@ struct QuasiNewton {
   void solve_compact(const double *rz, double *kap) const;
   int mult(pcu_vec *x, pcu_vec *y);
   int update(pcu_vec *s, pcu_vec *y, double yTy, double yTs, double sTs,
-             const double *sZ, int *update_type);
+             const double *sZ, int *update_type, int steal = 0);
   void mat_update();
 };
 
@@ -159,6 +159,9 @@ struct pcu_ip {
   double stats_tau_used = 0.0;
   double stats_out[32];
   int opt_no_fuse21 = 0;      // debugging: keep pass 2 and the next pass 1 separate
+  int opt_no_chain = 0;       // debugging (PCU_NO_CHAIN): dense algebra of the KKT solve on the host
+  double *dense_dev = nullptr, *dense_host = nullptr;  // work buffer of pcu_dense_kernel (+ pinned mirror)
+  int dense_cap = 0;
   int pass1_ready = 0;        // Pass2R1F left d1', d2' and [A|Z]^T t1' for the next solve
   std::vector<double> pass1_r;
   double stats_pmax = 0.0;  // |px|_inf of the last StatsF launch
@@ -179,9 +182,19 @@ struct pcu_ip {
   std::vector<HistRec> history;
   std::vector<IterTime> times;
   FILE *outfp = nullptr;
-  cudaEvent_t ev_it0 = nullptr, ev_it1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t> > cb_events;
-  size_t cb_used = 0;
+  // Device timing of a major iteration (whole iteration, KKT solve, callbacks): two
+  // event sets used alternately, so that iteration k is read out during iteration
+  // k + 1 (after its first reduction has synchronised anyway) instead of costing a
+  // synchronisation of its own.
+  struct IterEvents {
+    cudaEvent_t it0 = nullptr, it1 = nullptr, k0 = nullptr, k1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t> > cb;
+    size_t cb_used = 0;
+    bool pending = false;
+  } evs[2];
+  int ev_cur = 0;
+  int collect_times(IterEvents &e);  // waits for e.it1 when it is still pending
+  int flush_times();
 
   ~pcu_ip();
   int init(pcu_problem *p);
@@ -211,6 +224,7 @@ struct pcu_ip {
   int setUpKKTDiagSystem(Vars &vars, int use_qn, int identity);
   int setUpKKTDiagRhs(Vars &vars, int use_qn, double mu);
   int setUpKKTSystem(Vars &vars, int use_qn, const double *gdiag, int with_rhs = 0);
+  int kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double tau, double *VTp);
   int computeKKTStep(Vars &vars, Vars &res, Vars &step, int use_qn,
                      int accumulate, double *VTp, int emit_res, double mu_res,
                      int *emitted, int rhs_from_vars = 0, double stats_tau = -1.0);

@@ -391,6 +391,7 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
         ff.V = fr.V; ff.alpha = fr.alpha; ff.beta = fr.beta;
         ff.ncols = m; ff.accumulate = accumulate; ff.from_vars = fr.from_vars;
         ff.b0sig = fr.b0sig; ff.mu = fr.mu; ff.mu_rhs = fr.mu_rhs; ff.k = k;
+        ff.cdev = nullptr;
         RedBuf rb = ctx->redbuf(decltype(ff)::NS, 0, 0);
         if (launch_tile(ctx, ff, nvars, wd, rb)) return 1;
         double out[decltype(ff)::NS];
@@ -421,6 +422,7 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     fs.d1 = f2.d1; fs.d2 = f2.d2; fs.g = g->d;
     fs.V = f2.V; fs.alpha = f2.alpha; fs.ncols = f2.ncols;
     fs.accumulate = f2.accumulate; fs.tau = stats_tau; fs.k = f2.k;
+    fs.cdev = nullptr;
     RedBuf rb = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
     if (launch_tile(ctx, fs, nvars, wd, rb)) return 1;
     if (ctx->fetch(stats_out)) return 1;
@@ -438,6 +440,163 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
       if (ctx->big_fetch(ncon + qa, VTp)) return 1;
     }
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------ kktChain
+// The KKT solve of a default iteration (monotone barrier, one refinement step,
+// ncon + q <= 32) as ONE stream-ordered chain without a host round trip:
+//   DiagRhsF -> Gram (+ in-stream all-reduce) -> dense phase A -> Pass2R1F
+//   (+ in-stream all-gather of its partials) -> dense phase B -> Pass2SF -> fetch.
+// The small dense algebra (LU of G and Ce, SMW coefficients, dense residuals) runs in
+// pcu_dense_kernel on a flat device buffer; the two passes read their coefficient
+// tables from it.  Same arithmetic as setUpKKTDiagRhs + setUpKKTSystem +
+// computeKKTStep x 2 (IP.cpp:1832-1971, 2634-2737, 4971-4991), which remain the path of
+// every other configuration (and of PCU_NO_CHAIN).
+int pcu_dense_enqueue(cudaStream_t stream, double *buf, const DenseOff &o, int phase,
+                      const double *Sin, const double *red, int world, int stride);
+
+int pcu_ip::kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double tau,
+                     double *VTp) {
+  const int q = (qn && use_qn) ? qn->size() : 0;
+  const int m = ncon + q;
+  sq = q;
+  stats_ready = 0;
+  pass1_ready = 0;
+  if (setUpKKTDiagRhs(vars, use_qn, mu)) return 1;
+  // ---- inputs of the dense kernel (host -> device, stream-ordered, 1-7 KB)
+  const int ld = 8 * ((m + 1 + 7) / 8);
+  const DenseOff o = pcu_dense_offsets(ncon, q, ld);
+  if (!dense_dev || dense_cap < o.total) {
+    if (dense_dev) cudaFree(dense_dev);
+    if (dense_host) cudaFreeHost(dense_host);
+    dense_cap = pcu_dense_offsets(ncon, qn ? qn->max_size() : 0, 40).total + 64;
+    if (dense_cap < o.total) dense_cap = o.total + 64;
+    PCU_CUDA_OK(cudaMalloc(&dense_dev, sizeof(double) * dense_cap));
+    PCU_CUDA_OK(cudaMallocHost(&dense_host, sizeof(double) * dense_cap));
+  }
+  double *h = dense_host;
+  h[o.mu] = mu;
+  h[o.mu + 1] = 0.0;
+  for (int i = 0; i < ncon; i++) {
+    h[o.vz + i] = vars.z[i];
+    h[o.vs + i] = vars.s[i];
+    h[o.vt + i] = vars.t[i];
+    h[o.vzs + i] = vars.zs[i];
+    h[o.vzt + i] = vars.zt[i];
+    h[o.cc + i] = c[i];
+    h[o.gs + i] = gamma_s[i];
+    h[o.gt + i] = gamma_t[i];
+  }
+  if (q > 0) {
+    memcpy(h + o.M, qn->M.data(), sizeof(double) * q * q);
+    memcpy(h + o.d0, qn->d0.data(), sizeof(double) * q);
+    memcpy(h + o.Mf, qn->Mf.data(), sizeof(double) * q * q);
+    for (int i = 0; i < q; i++) h[o.mpiv + i] = (double)qn->piv[i];
+  }
+  PCU_CUDA_OK(cudaMemcpyAsync(dense_dev, h, sizeof(double) * o.S, cudaMemcpyHostToDevice,
+                              ctx->stream));
+  // ---- Gram pass with the first solve's right-hand side as column m
+  ColTable V;
+  for (int j = 0; j < ncon; j++) V.p[j] = Ac[j]->d;
+  if (q > 0) qn->z_table(V, ncon);
+  ColTable Vg = V;
+  Vg.p[m] = d1->d;
+  int ldg = 0;
+  if (pcu_gram_enqueue(ctx, Vg, m + 1, Dinv->d, Cw->d, wd, nvars, &ldg, d2->d, m)) return 1;
+  if (ldg != ld) return 1;
+  if (ctx->world > 1) {
+    NcclApi &api = nccl_api();
+    if (api.AllReduce(ctx->d_big, ctx->d_big, (size_t)ld * ld, ncclFloat64, ncclSum, ctx->comm,
+                      ctx->stream) != ncclSuccess)
+      return 1;
+  }
+  ctx->prof_begin("dense_kernel");
+  if (pcu_dense_enqueue(ctx->stream, dense_dev, o, 0, ctx->d_big, nullptr, 1, 0)) return 1;
+  ctx->prof_end();
+  ctx->launches++;
+  // ---- pass 2 of the first solve + refinement residual + pass 1 of the refinement
+  const IPConst k = kconst();
+  double *red1 = nullptr;
+  int mr = 0;
+  auto fused21 = [&](auto ff) -> int {
+    ff.v = vars.dv(); ff.b = b.dv(); ff.y = y.dv();
+    ff.lb = lb->d; ff.ub = ub->d; ff.Dinv = Dinv->d; ff.Cw = Cw->d;
+    ff.d1 = d1->d; ff.g = g->d;
+    ff.d2 = d2->d;
+    ff.d1out = t1->d;
+    ff.V = V;
+    ff.cdev = dense_dev + o.coefA;
+    ff.ncols = m; ff.accumulate = 0; ff.from_vars = 1;
+    ff.b0sig = opt.qn_sigma + ((qn && !opt.sequential_linear_method) ? qn->b0 : 0.0);
+    ff.mu = mu; ff.mu_rhs = mu; ff.k = k;
+    RedBuf rb = ctx->redbuf(decltype(ff)::NS, 0, 0);
+    red1 = rb.result;
+    mr = decltype(ff)::NS;
+    return launch_tile(ctx, ff, nvars, wd, rb);
+  };
+  int rc;
+  if (m <= 8) rc = fused21(Pass2R1F<8>());
+  else if (m <= 16) rc = fused21(Pass2R1F<16>());
+  else if (m <= 24) rc = fused21(Pass2R1F<24>());
+  else rc = fused21(Pass2R1F<32>());
+  if (rc) return 1;
+  std::swap(d1, t1);  // the last pass reads d1' where the fused pass wrote it
+  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k1, ctx->stream));
+  const double *red = red1;
+  if (ctx->world > 1) {
+    NcclApi &api = nccl_api();
+    if (api.AllGather(red1, ctx->d_gather, (size_t)mr, ncclFloat64, ctx->comm, ctx->stream) !=
+        ncclSuccess)
+      return 1;
+    red = ctx->d_gather;
+  }
+  ctx->prof_begin("dense_kernel");
+  if (pcu_dense_enqueue(ctx->stream, dense_dev, o, 1, nullptr, red, ctx->world, mr)) return 1;
+  ctx->prof_end();
+  ctx->launches++;
+  // ---- pass 2 of the refinement solve, accumulated, + the step statistics
+  Pass2SF fs;
+  fs.v = vars.dv(); fs.b = b.dv(); fs.y = y.dv();
+  fs.lb = lb->d; fs.ub = ub->d; fs.Dinv = Dinv->d; fs.Cw = Cw->d;
+  fs.d1 = d1->d; fs.d2 = d2->d; fs.g = g->d;
+  fs.V = V;
+  fs.cdev = dense_dev + o.coefB;
+  fs.ncols = m;
+  fs.accumulate = 1; fs.tau = tau; fs.k = k;
+  RedBuf rb2 = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
+  if (launch_tile(ctx, fs, nvars, wd, rb2)) return 1;
+  PCU_CUDA_OK(cudaMemcpyAsync(h + o.S, dense_dev + o.S, sizeof(double) * (o.total - o.S),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  double out[PCU_DENSE_MAXM + Pass2SF::NS + Pass2SF::NX + Pass2SF::NM];
+  if (ctx->fetch(out)) return 1;
+  memcpy(stats_out, out + mr, sizeof(double) * (Pass2SF::NS + Pass2SF::NX + Pass2SF::NM));
+  stats_ready = 1;
+  stats_tau_used = tau;
+  // ---- host mirrors of what the dense kernel produced
+  for (int i = 0; i < ncon; i++) {
+    y.z[i] = h[o.yz + i];
+    y.s[i] = h[o.ys + i];
+    y.t[i] = h[o.yt + i];
+    y.zs[i] = h[o.yzs + i];
+    y.zt[i] = h[o.yzt + i];
+    b.z[i] = h[o.bz + i];
+    b.s[i] = h[o.bs + i];
+    b.t[i] = h[o.bt + i];
+    b.zs[i] = h[o.bzs + i];
+    b.zt[i] = h[o.bzt + i];
+  }
+  for (int i = 0; i < m; i++) VTp[i] = h[o.vtp + i];
+  sld = ld;
+  Sgram.assign(h + o.S, h + o.S + (size_t)ld * ld);
+  Graw.assign(h + o.Graw, h + o.Graw + (size_t)ncon * ncon);
+  Gfac.assign(h + o.Gfac, h + o.Gfac + (size_t)ncon * ncon);
+  gpiv.assign(ncon > 0 ? ncon : 1, 0);
+  for (int i = 0; i < ncon; i++) gpiv[i] = (int)h[o.gpiv + i];
+  Ceraw.assign(h + o.Ceraw, h + o.Ceraw + (size_t)q * q);
+  Cefac.assign(h + o.Cefac, h + o.Cefac + (size_t)q * q);
+  cpiv.assign(q, 0);
+  for (int i = 0; i < q; i++) cpiv[i] = (int)h[o.cpiv + i];
   return 0;
 }
 
@@ -1059,8 +1218,14 @@ int pcu_ip::iterate_once(int *converged) {
   const double fp = opt.function_precision;
   const int uq = opt.use_quasi_newton_update;
   const int slm = opt.sequential_linear_method;
-  PCU_CUDA_OK(cudaEventRecord(ev_it0, ctx->stream));
-  const double cb_before = prob->callback_ms;
+  // this iteration records into the other event set; the previous iteration's set is
+  // read out below, once the first reduction of this iteration has synchronised
+  ev_cur ^= 1;
+  if (collect_times(evs[ev_cur])) return 1;  // (two iterations old: long finished)
+  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].it0, ctx->stream));
+  // k0 / k1 bracket the KKT solve; give them a defined value for iterations that end early
+  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k0, ctx->stream));
+  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k1, ctx->stream));
 
   int qn_hessian_reset = 0;
   if (qn && !slm) {
@@ -1131,6 +1296,9 @@ int pcu_ip::iterate_once(int *converged) {
       }
     }
   }
+  // the residual statistics above synchronised the stream: the previous iteration's
+  // events are complete, reading them costs nothing
+  if (collect_times(evs[ev_cur ^ 1])) return 1;
   last_comp = comp;
   log_line(k, comp, max_prime, max_infeas, max_dual);
 
@@ -1183,7 +1351,7 @@ int pcu_ip::iterate_once(int *converged) {
   std::vector<double> VTp(nA + nZ + 1, 0.0);
   bool vtp_valid = true;
 
-  PCU_CUDA_OK(cudaEventRecord(ev_k0, ctx->stream));
+  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k0, ctx->stream));
   // The first solve's right-hand side can ride in the Gram pass when that solve
   // takes the fused residual-free route (see computeKKTStep).
   bool rhs_in_gram = false;
@@ -1194,7 +1362,16 @@ int pcu_ip::iterate_once(int *converged) {
                   !diagonal_qn_step && q0 == qa && ncon + q0 >= 1 &&
                   ncon + q0 <= 32;
   }
-  if (rhs_in_gram) {
+  const int nref = opt.iterative_refinement_steps;
+  // fraction-to-boundary parameter of this iteration (IP.cpp:5069-5077), known before
+  // the solves
+  double tau_pre = opt.min_fraction_to_boundary;
+  if (1.0 - barrier_param >= tau_pre) tau_pre = 1.0 - barrier_param;
+  const bool chain = rhs_in_gram && nref == 1 && !mehrotra && !opt_no_chain &&
+                     !opt_no_fuse21 && !opt_no_fuse2s;
+  if (chain) {
+    if (kktChain(v, res, upd, use_qn, mu_for_res, tau_pre, VTp.data())) return 1;
+  } else if (rhs_in_gram) {
     if (setUpKKTDiagRhs(v, use_qn, mu_for_res)) return 1;
     if (setUpKKTSystem(v, use_qn, nullptr, 1)) return 1;
   } else {
@@ -1202,7 +1379,6 @@ int pcu_ip::iterate_once(int *converged) {
     if (setUpKKTSystem(v, use_qn, nullptr)) return 1;
   }
   if (diagonal_qn_step) use_qn = 0;
-  const int nref = opt.iterative_refinement_steps;
   auto kkt_with_refinement = [&](double mu_res, bool allow_refine) -> int {
     const bool need_dots = true;
     (void)need_dots;
@@ -1220,7 +1396,7 @@ int pcu_ip::iterate_once(int *converged) {
     }
     return 0;
   };
-  {
+  if (!chain) {
     // the fraction-to-boundary parameter is known before the solves (it depends on
     // the barrier only, IP.cpp:5069-5077), so the last pass of the last solve can
     // take the step statistics (not under the Mehrotra strategies, whose
@@ -1235,7 +1411,7 @@ int pcu_ip::iterate_once(int *converged) {
     if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nref > 0, mu_for_res,
                        &emitted, lazy_res ? 1 : 0, nref == 0 ? tau_s : -1.0))
       return 1;
-    PCU_CUDA_OK(cudaEventRecord(ev_k1, ctx->stream));
+    PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k1, ctx->stream));
     for (int it = 0; it < nref; it++) {
       if (!emitted &&
           computeKKTRes(v, mu_for_res, res, &upd, VTp.data(), VTp.data() + nA))
@@ -1385,8 +1561,10 @@ int pcu_ip::iterate_once(int *converged) {
           sZ.resize(qn->size());
           for (int i = 0; i < qn->size(); i++) sZ[i] = ax * VTp[nA + i];
         }
+        // s_qn / y_qn are rewritten from scratch by the next iteration: hand their
+        // buffers to the quasi-Newton memory instead of copying them
         if (qn->update(s_qn, y_qn, dots[0], dots[1], dots[2],
-                       sZ.empty() ? nullptr : sZ.data(), &update_type))
+                       sZ.empty() ? nullptr : sZ.data(), &update_type, 1))
           return 1;
       }
     }
@@ -1414,9 +1592,11 @@ int pcu_ip::iterate_once(int *converged) {
       RedBuf rb = ctx->redbuf(TrialF::NS, 0, 0);
       if (launch_tile(ctx, ft, nvars, wd, rb)) return -1;
       double ts[TrialF::NS];
-      // the objective callback fetches its own reductions; keep ours first
-      if (ctx->fetch(ts)) return -1;
+      // the merit sums travel with the reductions the objective callback fetches
+      // (one synchronisation for both)
+      ctx->defer();
       int fail_obj = evalObjCon(rx);
+      if (ctx->take_deferred(ts, TrialF::NS)) return -1;
       if (fail_obj) return 1;
       if (!merit_too) return 0;
       for (int i = 0; i < ncon; i++) {
@@ -1613,17 +1793,8 @@ int pcu_ip::iterate_once(int *converged) {
   ls.info = info;
   if (monotone_barrier_converged) ls.barrier_strategy = ls.input_barrier_strategy;
 
-  PCU_CUDA_OK(cudaEventRecord(ev_it1, ctx->stream));
-  PCU_CUDA_OK(cudaEventSynchronize(ev_it1));
-  cb_collect();
-  IterTime tm;
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, ev_it0, ev_it1);
-  tm.total_ms = ms;
-  cudaEventElapsedTime(&ms, ev_k0, ev_k1);
-  tm.kkt_ms = ms;
-  tm.callback_ms = prob->callback_ms - cb_before;
-  times.push_back(tm);
+  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].it1, ctx->stream));
+  evs[ev_cur].pending = true;
   ls.k++;
   niter++;
   return 0;

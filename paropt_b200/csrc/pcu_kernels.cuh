@@ -16,6 +16,7 @@
 #pragma once
 
 #include "pcu_common.cuh"
+#include "pcu_dense.cuh"
 
 // occupancy hints (blocks of 128 threads per SM) of the register-heavy kernels
 #ifndef PCU_MINB_RES
@@ -55,6 +56,13 @@ struct IPConst {
 
 __device__ __forceinline__ double gamma_sw(const IPConst &k, long long ci) {
   return ci < k.nwineq ? 0.0 : k.gamma;
+}
+
+// Coefficient j of a column table: from kernel-parameter space (host-computed), or --
+// device chain of the KKT solve, pcu_dense.cu -- from the work buffer the dense kernel
+// filled just before this launch (uniform address: one L1-resident line per table).
+__device__ __forceinline__ double pcu_coef(const double *dev, const CoefTable &tab, int j) {
+  return dev ? __ldg(dev + j) : tab.v[j];
 }
 
 struct Con0 {  // no per-constraint data
@@ -1033,6 +1041,7 @@ struct Pass2SF : NoStreams {
   const double *lb, *ub, *Dinv, *Cw, *d1, *d2, *g;
   ColTable V;
   CoefTable alpha;
+  const double *cdev;  // device-resident alpha (chain mode), or null
   int ncols;
   int accumulate;
   double tau;
@@ -1082,17 +1091,22 @@ struct Pass2SF : NoStreams {
       double c[4][W];
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) src.template ldc<W>(j + jj, V.p[j + jj], i, c[jj]);
+      double al[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) al[jj] = pcu_coef(cdev, alpha, j + jj);
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) {
 #pragma unroll
-        for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j + jj], c[jj][q], d[q]);
+        for (int q = 0; q < W; q++) d[q] = fma(al[jj], c[jj][q], d[q]);
       }
     }
     for (; j < ncols; j++) {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
-      for (int q = 0; q < W; q++) d[q] = fma(alpha.v[j], c[q], d[q]);
+      const double aj = pcu_coef(cdev, alpha, j);
+#pragma unroll
+      for (int q = 0; q < W; q++) d[q] = fma(aj, c[q], d[q]);
     }
 #pragma unroll
     for (int q = 0; q < W; q++) {
@@ -1835,6 +1849,7 @@ struct Pass2R1F : NoStreams {
   double *d2, *d1out;
   ColTable V;
   CoefTable alpha, beta;
+  const double *cdev;  // device-resident alpha | beta (chain mode, beta at +PCU_DENSE_MAXM), or null
   int ncols;
   int accumulate;
   int from_vars;
@@ -1892,22 +1907,30 @@ struct Pass2R1F : NoStreams {
       double c[4][W];
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) src.template ldc<W>(j + jj, V.p[j + jj], i, c[jj]);
+      double al[4], be[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        al[jj] = pcu_coef(cdev, alpha, j + jj);
+        be[jj] = pcu_coef(cdev ? cdev + PCU_DENSE_MAXM : nullptr, beta, j + jj);
+      }
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) {
 #pragma unroll
         for (int q = 0; q < W; q++) {
-          d[q] = fma(alpha.v[j + jj], c[jj][q], d[q]);
-          lin[q] = fma(beta.v[j + jj], c[jj][q], lin[q]);
+          d[q] = fma(al[jj], c[jj][q], d[q]);
+          lin[q] = fma(be[jj], c[jj][q], lin[q]);
         }
       }
     }
     for (; j < ncols; j++) {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
+      const double aj = pcu_coef(cdev, alpha, j);
+      const double bj = pcu_coef(cdev ? cdev + PCU_DENSE_MAXM : nullptr, beta, j);
 #pragma unroll
       for (int q = 0; q < W; q++) {
-        d[q] = fma(alpha.v[j], c[q], d[q]);
-        lin[q] = fma(beta.v[j], c[q], lin[q]);
+        d[q] = fma(aj, c[q], d[q]);
+        lin[q] = fma(bj, c[q], lin[q]);
       }
     }
 #pragma unroll

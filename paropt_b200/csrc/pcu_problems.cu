@@ -424,8 +424,11 @@ struct SepQuadProblem : pcu_problem {
       // NS = 1 but unused: still needs a reduction slot for the harness
       RedBuf rb = ctx->redbuf(1, 0, 0);
       if (pcu_launch_tile(ctx, f1, nvars, no_weighting(), rb)) return 1;
-      ctx->result_used = 0;  // discard the slot without a host round trip
-      ctx->pending.clear();
+      // discard that slot (the last one reserved) without a host round trip
+      if (!ctx->pending.empty()) {
+        ctx->result_used = ctx->pending.back().offset;
+        ctx->pending.pop_back();
+      }
     }
     for (int j0 = 0; j0 < ncon; j0 += 8) {
       SQConGradF f;

@@ -66,6 +66,7 @@ int pcu_ctx::fetch(double *out) {
   if (red_overflow) {
     red_overflow = false;
     result_used = 0;
+    deferred_n = 0;
     pending.clear();
     cudaStreamSynchronize(stream);
     return 1;
@@ -102,9 +103,27 @@ int pcu_ctx::fetch(double *out) {
       }
     }
   }
-  if (out && total > 0) memcpy(out, h_result, total * sizeof(double));
+  int skip = 0;
+  if (deferred_n > 0) {  // results of an earlier launch ride along (see defer())
+    skip = deferred_n <= total ? deferred_n : total;
+    deferred_vals.assign(h_result, h_result + skip);
+    deferred_ready = true;
+    deferred_n = 0;
+  }
+  if (out && total > skip) memcpy(out, h_result + skip, (total - skip) * sizeof(double));
   result_used = 0;
   pending.clear();
+  return 0;
+}
+
+int pcu_ctx::take_deferred(double *out, int n) {
+  if (!deferred_ready) {
+    // nobody fetched since defer(): the deferred slots are still on the device
+    if (deferred_n <= 0 || fetch(nullptr)) return 1;
+  }
+  deferred_ready = false;
+  if ((int)deferred_vals.size() < n) return 1;
+  memcpy(out, deferred_vals.data() + (deferred_vals.size() - n), n * sizeof(double));
   return 0;
 }
 

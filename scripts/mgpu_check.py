@@ -12,7 +12,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from paropt_b200.api import Context, InteriorPoint, problem_from_config  # noqa: E402
-from tests.parity import compare_histories, load_golden  # noqa: E402
+from tests.parity import checked, compare_histories, load_golden  # noqa: E402
 
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
@@ -29,7 +29,7 @@ for name, iters in (("C2_small", 41), ("C3_small", 50)):
     hist = ip.history()
     n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"])
     verdict["cases"][name] = {"compared": n, "first_violation": first,
-                              "worst": max(worst.values()), "nvars_local": prob.nvars}
+                              "worst": max(checked(worst).values()), "nvars_local": prob.nvars}
     ip.free()
     prob.free()
 # fused / bulk-copy-staged paths at a size where they are active on every rank,
@@ -70,7 +70,7 @@ for label, nbig in (("C3_big", 8 * 5003 * ctx.size), ("C2_big", 50001 * ctx.size
     n1, w1, f1 = compare_histories(plain, fused, max_iters=12, cfg=cfg_big)
     n2, w2, f2 = compare_histories(fused, host, max_iters=12, cfg=cfg_big)
     verdict["cases"][label] = {"compared": min(n1, n2), "first_violation": f1 or f2,
-                               "worst": max(max(w1.values()), max(w2.values()))}
+                               "worst": max(max(checked(w1).values()), max(checked(w2).values()))}
 if ctx.rank == 0:
     print("MGPU_VERDICT " + json.dumps(verdict))
 ctx.close()

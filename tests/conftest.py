@@ -29,9 +29,10 @@ def pytest_terminal_summary(terminalreporter, exitstatus, config):
     tr = terminalreporter
     tr.section("parity: worst error per history comparison (tolerance 1e-10)")
     for label, rec in sorted(parity.REPORTS.items()):
-        w = rec["worst"]
+        w = parity.checked(rec["worst"])
         top = max(w.values()) if w else 0.0
         key = max(w, key=w.get) if w else "-"
+        w = rec["worst"]
         rel = max([v for k, v in w.items() if k.startswith("rel:")] + [0.0])
         tr.write_line("%-46s iters %3d  worst %.2e (%s)  residual norms rel %.2e"
                       % (label, rec["compared"], top, key, rel))

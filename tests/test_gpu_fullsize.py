@@ -48,13 +48,23 @@ def run(ctx, cfg, iters, staged=True):
 # C4_full (n = 32M, c = 100, L-SR1 m = 20: the wide Gram path at full size): 10
 # iterations -- q grows by one per iteration, and from iteration ~10 on the
 # reference's unsafeguarded L-SR1 amplifies round-off (tests/test_oracle_golden.py).
+# Stated tolerance 1e-9 instead of 1e-10: the 100 x 100 matrix G is a sum over 32M
+# rows of nearly parallel columns, and the unmodified reference run on 4 instead of 8
+# ranks (another partition of its 5050 sequential dot products) already differs from
+# ITSELF by 1.7e-10 at iteration 3 and 4.3e-10 at iteration 4
+# (tests/golden/C4_full_np4.json, test_reference_reproducibility_at_C4_full); the
+# CUDA path stays within 1.1e-10 of the 8-rank run over all 10 iterations.
+FULL_RTOL = {"C4_full": 1e-9}
+
+
 @pytest.mark.parametrize("name,iters", [("C3_full", 12), ("C2_full", 12), ("C4_full", 10)])
 def test_first_iterations_match_reference_at_full_size(ctx, name, iters):
     if not os.path.exists(os.path.join(HERE, "golden", name + ".json")):
         pytest.skip("fixture not generated")
     gold = load_golden(name)
     hist = run(ctx, gold["config"], iters + 1)
-    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"])
+    n, worst, first = compare_histories(gold["history"], hist, max_iters=iters, cfg=gold["config"],
+                                        rtol=FULL_RTOL.get(name, 1e-10))
     assert n == iters and first is None, (first, worst)
     for row, rec in zip(gold["log"][:iters], hist):
         assert row["info"] == rec["info"], (row, rec["iter"])

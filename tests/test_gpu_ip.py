@@ -34,7 +34,7 @@ def run_gpu(ctx, cfg, max_iters=None, history_level=2):
     return out
 
 
-@pytest.mark.parametrize("name", ["C1_small", "C2_small"])
+@pytest.mark.parametrize("name", ["C1_small", "C2_small", "C3_small"])
 def test_full_history_matches_reference(ctx, name):
     gold = load_golden(name)
     out = run_gpu(ctx, gold["config"])
@@ -51,7 +51,9 @@ def test_full_history_matches_reference(ctx, name):
     assert out["launches"] > 0
 
 
-@pytest.mark.parametrize("name,iters", [("C3_small", 50), ("C4_small", 9)])
+# C4 (L-SR1): 11 iterations -- as far as the reference agrees with itself on another
+# rank count (tests/test_oracle_golden.py: test_reference_l_sr1_reproducibility)
+@pytest.mark.parametrize("name,iters", [("C4_small", 11)])
 def test_prefix_history_matches_reference(ctx, name, iters):
     gold = load_golden(name)
     out = run_gpu(ctx, gold["config"], max_iters=iters + 1)
