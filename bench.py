@@ -133,6 +133,9 @@ def kernel_words(name, N, W, c, q):
         "TrialF": 5 * N + 6 * W,
         "Update1F": (10 + c) * N + 15 * W,
         "Update2F": (5 + c) * N + W,
+        "Update1FT": (10 + c) * N + 15 * W,                 # <1>: + next iteration's statistics, no extra traffic
+        "Update2FT": (7 + c) * N + W,                       # <1>: + zl, zu for |rx| of the next iteration
+        "dense_kernel": None,
         "gram_kernel": (m + 2) * N + 2 * W,                 # [A|Z|d1] columns + Dinv; Cw, d2
         "mdot_kernel": None,  # (1 + columns of the chunk) N, see below
     }

@@ -161,6 +161,7 @@ int pcu_ip_begin(pcu_ip *ip) { return ip->begin(); }
 
 int pcu_ip_iterate(pcu_ip *ip, int max_iters, int *converged) {
   int conv = 0;
+  ip->upd_stats_valid = 0;  // the caller may have touched the state between calls
   for (int i = 0; i < max_iters && !conv; i++) {
     if (ip->ls.k >= ip->opt.max_major_iters) break;
     if (ip->iterate_once(&conv)) return 1;

@@ -79,6 +79,10 @@ struct pcu_ctx {
   void defer() { deferred_n = result_used; deferred_ready = false; }
   int take_deferred(double *out, int n);
 
+  // the device chain of the KKT solve keeps its coefficient tables in a constant bank
+  // (one per device and process): only while this is the device's only context
+  bool chain_ok() const;
+
   RedBuf redbuf(int ns, int nx, int nm);       // reserves a result slot
   int fetch(double *out);                      // all pending slots -> host, sync
   int big_reserve(size_t nresult, size_t npartials);

@@ -1,12 +1,12 @@
 // pcu_dense.cu -- device side of pcu_dense.cuh: a single-CTA kernel that runs the
 // small dense algebra of the KKT solve between two streaming passes, so that the
 // iteration's chain  Gram -> pass 2 + residual -> pass 2 + statistics  needs no host
-// round trip (VERDICT K21: "LU of G and Ce + SMW coefficient assembly, fed by the
-// in-stream all-reduce / all-gather result").
+// round trip (LU of G and Ce, SMW coefficient assembly, dense residuals, fed by the
+// in-stream all-reduce / all-gather result).
 //
-// The flat work buffer (<= 5k doubles) is staged in shared memory by all threads,
-// thread 0 runs the sequential algorithm of pcu_dense.cuh on it (the matrices are at
-// most 32 x 32: ~10 us), all threads write the result region back.
+// The flat work buffer (<= 5k doubles) is staged in shared memory by all threads, warp
+// 0 runs the lane-parallel algorithm of pcu_dense.cuh on it (matrices of at most
+// 32 x 32), all threads write the result region back.
 //
 // Built with -fmad=false (paropt_b200/build.py): identical multiply / add sequence to
 // the host compiler's, so chain and host path agree bit for bit on the same inputs.
@@ -21,16 +21,17 @@ __global__ void __launch_bounds__(PCU_DENSE_THREADS, 1)
                      const double *red, const int world, const int stride) {
   extern __shared__ double2 dense_smem2[];
   double *w = reinterpret_cast<double *>(dense_smem2);
-  double *scratch = w + o.total;  // 2 m + 5 c + q doubles
+  double *scratch = w + o.total;
   const int tid = threadIdx.x;
-  for (int i = tid; i < o.total; i += PCU_DENSE_THREADS) w[i] = buf[i];
-  __syncthreads();
+  // phase 0 needs the inputs only (the rest is produced here); phase 1 everything
+  const int n_in = phase == 0 ? o.S : o.total;
+  for (int i = tid; i < n_in; i += PCU_DENSE_THREADS) w[i] = buf[i];
   if (phase == 0) {
     const int nS = o.ld * o.ld;
     for (int i = tid; i < nS; i += PCU_DENSE_THREADS) w[o.S + i] = Sin[i];
-    __syncthreads();
   }
-  if (tid == 0) {
+  __syncthreads();
+  if (tid < 32) {
     if (phase == 0) pcu_dense_phase_a(w, o, scratch);
     else pcu_dense_phase_b(w, o, red, world, stride, scratch);
   }
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(PCU_DENSE_THREADS, 1)
 // result (phase 0); red / world / stride: rank-ordered partial reductions (phase 1).
 int pcu_dense_enqueue(cudaStream_t stream, double *buf, const DenseOff &o, int phase,
                       const double *Sin, const double *red, int world, int stride) {
-  const size_t smem = sizeof(double) * (size_t)(o.total + 2 * o.m + 5 * o.c + o.q + 8);
+  const size_t smem = sizeof(double) * (size_t)(o.total + PCU_DENSE_SCRATCH(o.c, o.q));
   if (smem > 48 * 1024) {
     static bool raised[64] = {false};
     int dev = 0;
@@ -59,11 +60,11 @@ int pcu_dense_enqueue(cudaStream_t stream, double *buf, const DenseOff &o, int p
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// The same two phases on the host (the checker of the device path and the fallback of
-// configurations outside the chain): identical statements, identical rounding.
+// The same two phases on the host (checker of the device path): identical statements,
+// identical rounding.
 void pcu_dense_host(double *w, const DenseOff &o, int phase, const double *Sin,
                     const double *red, int world, int stride) {
-  double scratch[2 * PCU_DENSE_MAXM + 5 * PCU_DENSE_MAXM + PCU_DENSE_MAXM + 8];
+  double scratch[PCU_DENSE_SCRATCH(PCU_DENSE_MAXM / 2, PCU_DENSE_MAXM / 2) + 8 * PCU_DENSE_MAXM];
   if (phase == 0) {
     for (int i = 0; i < o.ld * o.ld; i++) w[o.S + i] = Sin[i];
     pcu_dense_phase_a(w, o, scratch);

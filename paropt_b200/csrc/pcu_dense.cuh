@@ -65,12 +65,48 @@ static inline DenseOff pcu_dense_offsets(int c, int q, int ld) {
   return o;
 }
 
-// LAPACK dgetrf / dgetrs restated (partial pivoting, column-major); pivots are kept
-// as doubles inside the flat buffer.  Same statements as pcu_lu_factor / pcu_lu_solve.
+// ---------------------------------------------------------------- lane model
+// The phases below are written once for the host (one "lane", no barrier) and for the
+// device, where ONE WARP runs them on the shared-memory copy of the buffer: loops whose
+// iterations are independent are dealt over the lanes (PCU_PFOR) and separated by
+// __syncwarp(); every element still sees exactly the host's sequence of operations, so
+// the results are bit-identical.
+#ifdef __CUDA_ARCH__
+#define PCU_LANE ((int)(threadIdx.x & 31))
+#define PCU_NLANE 32
+#define PCU_SYNC() __syncwarp()
+#else
+#define PCU_LANE 0
+#define PCU_NLANE 1
+#define PCU_SYNC() ((void)0)
+#endif
+#define PCU_PFOR(i, lo, hi) for (int i = (lo) + PCU_LANE; i < (hi); i += PCU_NLANE)
+// doubles of scratch the phases need next to the buffer
+#define PCU_DENSE_SCRATCH(c, q) ((c) * (q) + 2 * ((c) + (q)) + 5 * (c) + (q) + 8)
+
+// LAPACK dgetrf / dgetrs restated (partial pivoting, first largest entry, column-major;
+// n <= 32); pivots are kept as doubles inside the flat buffer.  Same statements as
+// pcu_lu_factor / pcu_lu_solve of pcu_ip.cu.
 PCU_HD int pcu_dense_lu_factor(int n, double *A, double *piv) {
   int info = 0;
   for (int k = 0; k < n; k++) {
     int p = k;
+#ifdef __CUDA_ARCH__
+    {
+      const int i = k + PCU_LANE;
+      double v = i < n ? fabs(A[i + n * k]) : -1.0;
+      int idx = i < n ? i : n;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (v2 > v || (v2 == v && i2 < idx)) {
+          v = v2;
+          idx = i2;
+        }
+      }
+      p = idx;
+    }
+#else
     double best = fabs(A[k + n * k]);
     for (int i = k + 1; i < n; i++) {
       const double v = fabs(A[i + n * k]);
@@ -79,31 +115,82 @@ PCU_HD int pcu_dense_lu_factor(int n, double *A, double *piv) {
         p = i;
       }
     }
-    piv[k] = (double)p;
-    if (A[p + n * k] == 0.0) {
+#endif
+    if (PCU_LANE == 0) piv[k] = (double)p;
+    const double pivot = A[p + n * k];
+    PCU_SYNC();  // every lane has read the pivot before the rows are exchanged
+    if (pivot == 0.0) {
       if (!info) info = k + 1;
       continue;
     }
     if (p != k) {
-      for (int j = 0; j < n; j++) {
+      PCU_PFOR(j, 0, n) {
         const double t = A[k + n * j];
         A[k + n * j] = A[p + n * j];
         A[p + n * j] = t;
       }
+      PCU_SYNC();
     }
-    const double inv = 1.0 / A[k + n * k];
-    for (int i = k + 1; i < n; i++) A[i + n * k] *= inv;
-    for (int j = k + 1; j < n; j++) {
-      const double akj = A[k + n * j];
-      if (akj != 0.0) {
-        for (int i = k + 1; i < n; i++) A[i + n * j] -= A[i + n * k] * akj;
+    const double inv = 1.0 / pivot;
+    PCU_PFOR(i, k + 1, n) A[i + n * k] *= inv;
+    PCU_SYNC();
+    // trailing update: a lane owns row i (n <= 32), its multiplier stays in a
+    // register, four columns per batch so that the loads of a batch overlap
+    PCU_PFOR(i, k + 1, n) {
+      const double lik = A[i + n * k];
+      int j = k + 1;
+      for (; j + 4 <= n; j += 4) {
+        double akj[4], aij[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          akj[u] = A[k + n * (j + u)];
+          aij[u] = A[i + n * (j + u)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (akj[u] != 0.0) A[i + n * (j + u)] = aij[u] - lik * akj[u];
+      }
+      for (; j < n; j++) {
+        const double akj = A[k + n * j];
+        if (akj != 0.0) A[i + n * j] -= lik * akj;
       }
     }
+    PCU_SYNC();
   }
   return info;
 }
 
 PCU_HD void pcu_dense_lu_solve(int n, const double *LU, const double *piv, double *b) {
+  if (PCU_LANE == 0) {
+    for (int k = 0; k < n; k++) {
+      const int p = (int)piv[k];
+      if (p != k) {
+        const double t = b[k];
+        b[k] = b[p];
+        b[p] = t;
+      }
+    }
+  }
+  PCU_SYNC();
+  for (int k = 0; k < n; k++) {
+    const double bk = b[k];
+    if (bk != 0.0) {
+      PCU_PFOR(i, k + 1, n) b[i] -= LU[i + n * k] * bk;
+    }
+    PCU_SYNC();
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    if (PCU_LANE == 0) b[k] /= LU[k + n * k];
+    PCU_SYNC();
+    const double bk = b[k];
+    PCU_PFOR(i, 0, k) b[i] -= LU[i + n * k] * bk;
+    PCU_SYNC();
+  }
+}
+
+// The same solve run by ONE lane on its own right-hand side (several independent
+// solves side by side).
+PCU_HD void pcu_dense_lu_solve_lane(int n, const double *LU, const double *piv, double *b) {
   for (int k = 0; k < n; k++) {
     const int p = (int)piv[k];
     if (p != k) {
@@ -129,7 +216,7 @@ PCU_HD void pcu_dense_lu_solve(int n, const double *LU, const double *piv, doubl
 // the step is w[yz..], [A|Z]^T px is w[vtp]).
 PCU_HD void pcu_dense_residual(double *w, const DenseOff &o, int with_step) {
   const double mu = w[o.mu];
-  for (int i = 0; i < o.c; i++) {
+  PCU_PFOR(i, 0, o.c) {
     const double z = w[o.vz + i], s = w[o.vs + i], t = w[o.vt + i];
     const double zs = w[o.vzs + i], zt = w[o.vzt + i];
     double rz = -(w[o.cc + i] - s + t);
@@ -152,38 +239,49 @@ PCU_HD void pcu_dense_residual(double *w, const DenseOff &o, int with_step) {
     w[o.bzs + i] = rzs;
     w[o.bzt + i] = rzt;
   }
+  PCU_SYNC();
 }
 
 // G = C0 + S_AA, Ce = S_ZZ - S_ZA G^-1 S_AZ - M / (d d^T), both LU-factored
-// (the host statements of pcu_ip::setUpKKTSystem).  scratch: >= c doubles.
+// (the host statements of pcu_ip::setUpKKTSystem).  scratch: >= c * q doubles.
 PCU_HD void pcu_dense_setup(double *w, const DenseOff &o, double *scratch) {
   const int c = o.c, q = o.q, ld = o.ld, m = o.m;
   double *S = w + o.S;
-  for (int j = 0; j < m; j++)  // symmetrise from the lower triangle
-    for (int i = j + 1; i < m; i++) S[j + ld * i] = S[i + ld * j];
+  PCU_PFOR(e, 0, m * m) {  // symmetrise from the lower triangle
+    const int j = e / m, i = e % m;
+    if (i > j) S[j + ld * i] = S[i + ld * j];
+  }
+  PCU_SYNC();
   double *Graw = w + o.Graw, *Gfac = w + o.Gfac;
-  for (int j = 0; j < c; j++)
-    for (int i = 0; i < c; i++) Graw[i + c * j] = S[i + ld * j];
-  for (int i = 0; i < c; i++)
-    Graw[i * (c + 1)] += w[o.vs + i] / w[o.vzs + i] + w[o.vt + i] / w[o.vzt + i];
-  for (int i = 0; i < c * c; i++) Gfac[i] = Graw[i];
+  PCU_PFOR(e, 0, c * c) {
+    const int j = e / c, i = e % c;
+    double g = S[i + ld * j];
+    if (i == j) g += w[o.vs + i] / w[o.vzs + i] + w[o.vt + i] / w[o.vzt + i];
+    Graw[e] = g;
+    Gfac[e] = g;
+  }
+  PCU_SYNC();
   if (c > 0) pcu_dense_lu_factor(c, Gfac, w + o.gpiv);
   if (q > 0) {
     double *Ceraw = w + o.Ceraw, *Cefac = w + o.Cefac;
-    double *col = scratch;
-    for (int i = 0; i < q; i++) {
+    // column i of G^-1 S_AZ, one lane per column
+    PCU_PFOR(i, 0, q) {
+      double *col = scratch + c * i;
       for (int j = 0; j < c; j++) col[j] = S[j + ld * (c + i)];
-      if (c > 0) pcu_dense_lu_solve(c, Gfac, w + o.gpiv, col);
-      for (int k = 0; k < q; k++) {
-        double v = S[(c + k) + ld * (c + i)];
-        for (int j = 0; j < c; j++) v -= S[(c + k) + ld * j] * col[j];
-        Ceraw[k + q * i] = v;
-      }
+      if (c > 0) pcu_dense_lu_solve_lane(c, Gfac, w + o.gpiv, col);
     }
+    PCU_SYNC();
     const double *M = w + o.M, *d0 = w + o.d0;
-    for (int j = 0; j < q; j++)
-      for (int i = 0; i < q; i++) Ceraw[i + q * j] -= M[i + q * j] / (d0[i] * d0[j]);
-    for (int i = 0; i < q * q; i++) Cefac[i] = Ceraw[i];
+    PCU_PFOR(e, 0, q * q) {
+      const int i = e / q, k = e % q;  // entry (k, i)
+      const double *col = scratch + c * i;
+      double v = S[(c + k) + ld * (c + i)];
+      for (int j = 0; j < c; j++) v -= S[(c + k) + ld * j] * col[j];
+      v -= M[k + q * i] / (d0[k] * d0[i]);
+      Ceraw[k + q * i] = v;
+      Cefac[k + q * i] = v;
+    }
+    PCU_SYNC();
     pcu_dense_lu_factor(q, Cefac, w + o.cpiv);
   }
 }
@@ -198,13 +296,14 @@ PCU_HD void pcu_dense_step(double *w, const DenseOff &o, int accumulate, double 
   const double *S = w + o.S, *r = w + o.r;
   double *yz1 = scratch, *pz = yz1 + c, *ps = pz + c, *pt = ps + c, *pzs = pt + c;
   double *pzt = pzs + c, *ww = pzt + c, *yz2 = ww + q;
-  for (int i = 0; i < c; i++) {
+  PCU_PFOR(i, 0, c) {
     const double s = w[o.vs + i], t = w[o.vt + i], zs = w[o.vzs + i], zt = w[o.vzt + i];
     yz1[i] = (w[o.bz + i] + (w[o.bzs + i] + s * w[o.bs + i]) / zs -
               (w[o.bzt + i] + t * w[o.bt + i]) / zt - r[i]);
   }
+  PCU_SYNC();
   if (c > 0) pcu_dense_lu_solve(c, w + o.Gfac, w + o.gpiv, yz1);
-  for (int i = 0; i < c; i++) {
+  PCU_PFOR(i, 0, c) {
     const double s = w[o.vs + i], t = w[o.vt + i], zs = w[o.vzs + i], zt = w[o.vzt + i];
     pz[i] = yz1[i];
     pzs[i] = yz1[i] - w[o.bs + i];
@@ -213,20 +312,23 @@ PCU_HD void pcu_dense_step(double *w, const DenseOff &o, int accumulate, double 
     pt[i] = (w[o.bzt + i] - t * pzt[i]) / zt;
     alpha[i] = yz1[i];
   }
+  PCU_SYNC();
   if (q > 0) {
-    for (int kq = 0; kq < q; kq++) {  // Z^T yx = r_Z + S_ZA yz1
+    PCU_PFOR(kq, 0, q) {  // Z^T yx = r_Z + S_ZA yz1
       double v = r[c + kq];
       for (int j = 0; j < c; j++) v += S[(c + kq) + ld * j] * yz1[j];
       ww[kq] = v;
     }
+    PCU_SYNC();
     pcu_dense_lu_solve(q, w + o.Cefac, w + o.cpiv, ww);
-    for (int j = 0; j < c; j++) {  // second solve: A^T P Z w = S_AZ w
+    PCU_PFOR(j, 0, c) {  // second solve: A^T P Z w = S_AZ w
       double v = 0.0;
       for (int kq = 0; kq < q; kq++) v += S[j + ld * (c + kq)] * ww[kq];
       yz2[j] = -v;
     }
+    PCU_SYNC();
     if (c > 0) pcu_dense_lu_solve(c, w + o.Gfac, w + o.gpiv, yz2);
-    for (int i = 0; i < c; i++) {
+    PCU_PFOR(i, 0, c) {
       const double s = w[o.vs + i], t = w[o.vt + i], zs = w[o.vzs + i], zt = w[o.vzt + i];
       const double yzs2 = yz2[i], yzt2 = -yz2[i];
       const double ys2 = -(s * yzs2) / zs;
@@ -238,9 +340,10 @@ PCU_HD void pcu_dense_step(double *w, const DenseOff &o, int accumulate, double 
       pt[i] -= yt2;
       alpha[i] = pz[i];
     }
-    for (int kq = 0; kq < q; kq++) alpha[c + kq] = -ww[kq];
+    PCU_PFOR(kq, 0, q) alpha[c + kq] = -ww[kq];
+    PCU_SYNC();
   }
-  for (int i = 0; i < c; i++) {
+  PCU_PFOR(i, 0, c) {
     if (accumulate) {
       w[o.yz + i] += pz[i];
       w[o.ys + i] += ps[i];
@@ -255,32 +358,36 @@ PCU_HD void pcu_dense_step(double *w, const DenseOff &o, int accumulate, double 
       w[o.yzt + i] = pzt[i];
     }
   }
-  for (int i = 0; i < m; i++) {  // [A|Z]^T D0^-1 (d1 + V alpha) = r + S alpha
+  PCU_PFOR(i, 0, m) {  // [A|Z]^T D0^-1 (d1 + V alpha) = r + S alpha
     double vv = r[i];
     for (int j = 0; j < m; j++) vv += S[i + ld * j] * alpha[j];
     w[o.vtp + i] = accumulate ? w[o.vtp + i] + vv : vv;
   }
+  PCU_SYNC();
 }
 
 // Phase A: everything between the Gram pass and the pass that applies the first
-// solve and emits the refinement residual.  Sin: the Gram result (ld x ld, lower
-// triangle, row m = [A|Z]^T t1 of the first solve).
+// solve and emits the refinement residual.  w[S] holds the Gram result (ld x ld, lower
+// triangle, row m = [A|Z]^T t1 of the first solve).  scratch: >= max(c q, 2 m + 5 c).
 PCU_HD void pcu_dense_phase_a(double *w, const DenseOff &o, double *scratch) {
   const int c = o.c, q = o.q, ld = o.ld, m = o.m;
-  for (int j = 0; j < m; j++) w[o.r + j] = w[o.S + m + ld * j];
+  PCU_PFOR(j, 0, m) w[o.r + j] = w[o.S + m + ld * j];
+  PCU_SYNC();
   pcu_dense_setup(w, o, scratch);
   pcu_dense_residual(w, o, 0);
   double *alpha = w + o.coefA, *beta = alpha + PCU_DENSE_MAXM;
   pcu_dense_step(w, o, 0, alpha, scratch);
   // coefficients of the linearised residual: z + pz for A, the compact
   // quasi-Newton solve kap = d0 M^-1 d0 (Z^T p) for Z (IP.cpp:1474-1476)
-  for (int j = 0; j < c; j++) beta[j] = w[o.vz + j] + w[o.yz + j];
+  PCU_PFOR(j, 0, c) beta[j] = w[o.vz + j] + w[o.yz + j];
   if (q > 0) {
     double *kap = scratch;
-    for (int i = 0; i < q; i++) kap[i] = w[o.vtp + c + i] * w[o.d0 + i];
+    PCU_PFOR(i, 0, q) kap[i] = w[o.vtp + c + i] * w[o.d0 + i];
+    PCU_SYNC();
     pcu_dense_lu_solve(q, w + o.Mf, w + o.mpiv, kap);
-    for (int i = 0; i < q; i++) beta[c + i] = kap[i] * w[o.d0 + i];
+    PCU_PFOR(i, 0, q) beta[c + i] = kap[i] * w[o.d0 + i];
   }
+  PCU_SYNC();
   pcu_dense_residual(w, o, 1);  // right-hand side of the refinement solve
 }
 
@@ -288,10 +395,11 @@ PCU_HD void pcu_dense_phase_a(double *w, const DenseOff &o, double *scratch) {
 // rank-ordered partial vectors of `stride` doubles) and the last pass.
 PCU_HD void pcu_dense_phase_b(double *w, const DenseOff &o, const double *red, int world,
                               int stride, double *scratch) {
-  for (int i = 0; i < o.m; i++) {
+  PCU_PFOR(i, 0, o.m) {
     double v = red[i];
     for (int rk = 1; rk < world; rk++) v += red[(size_t)rk * stride + i];
     w[o.r + i] = v;
   }
+  PCU_SYNC();
   pcu_dense_step(w, o, 1, w + o.coefB, scratch);
 }

@@ -159,6 +159,10 @@ struct pcu_ip {
   double stats_tau_used = 0.0;
   double stats_out[32];
   int opt_no_fuse21 = 0;      // debugging: keep pass 2 and the next pass 1 separate
+  // residual statistics of the NEXT iteration taken by the update passes (ResF layout)
+  double upd_sums[11], upd_max[5], upd_min[2];
+  int upd_stats_valid = 0;
+  int opt_no_updstats = 0;    // debugging (PCU_NO_UPDSTATS): always run the residual pass
   int opt_no_chain = 0;       // debugging (PCU_NO_CHAIN): dense algebra of the KKT solve on the host
   double *dense_dev = nullptr, *dense_host = nullptr;  // work buffer of pcu_dense_kernel (+ pinned mirror)
   int dense_cap = 0;

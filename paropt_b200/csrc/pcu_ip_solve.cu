@@ -391,7 +391,7 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
         ff.V = fr.V; ff.alpha = fr.alpha; ff.beta = fr.beta;
         ff.ncols = m; ff.accumulate = accumulate; ff.from_vars = fr.from_vars;
         ff.b0sig = fr.b0sig; ff.mu = fr.mu; ff.mu_rhs = fr.mu_rhs; ff.k = k;
-        ff.cdev = nullptr;
+        ff.cbank = -1;
         RedBuf rb = ctx->redbuf(decltype(ff)::NS, 0, 0);
         if (launch_tile(ctx, ff, nvars, wd, rb)) return 1;
         double out[decltype(ff)::NS];
@@ -422,7 +422,7 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     fs.d1 = f2.d1; fs.d2 = f2.d2; fs.g = g->d;
     fs.V = f2.V; fs.alpha = f2.alpha; fs.ncols = f2.ncols;
     fs.accumulate = f2.accumulate; fs.tau = stats_tau; fs.k = f2.k;
-    fs.cdev = nullptr;
+    fs.cbank = -1;
     RedBuf rb = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
     if (launch_tile(ctx, fs, nvars, wd, rb)) return 1;
     if (ctx->fetch(stats_out)) return 1;
@@ -515,6 +515,10 @@ int pcu_ip::kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double
   if (pcu_dense_enqueue(ctx->stream, dense_dev, o, 0, ctx->d_big, nullptr, 1, 0)) return 1;
   ctx->prof_end();
   ctx->launches++;
+  // alpha | beta of the next pass: device buffer -> constant bank, stream-ordered
+  PCU_CUDA_OK(cudaMemcpyToSymbolAsync(pcu_chain_coef, dense_dev + o.coefA,
+                                      sizeof(double) * 2 * PCU_DENSE_MAXM, 0,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
   // ---- pass 2 of the first solve + refinement residual + pass 1 of the refinement
   const IPConst k = kconst();
   double *red1 = nullptr;
@@ -526,7 +530,7 @@ int pcu_ip::kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double
     ff.d2 = d2->d;
     ff.d1out = t1->d;
     ff.V = V;
-    ff.cdev = dense_dev + o.coefA;
+    ff.cbank = 0;
     ff.ncols = m; ff.accumulate = 0; ff.from_vars = 1;
     ff.b0sig = opt.qn_sigma + ((qn && !opt.sequential_linear_method) ? qn->b0 : 0.0);
     ff.mu = mu; ff.mu_rhs = mu; ff.k = k;
@@ -555,13 +559,17 @@ int pcu_ip::kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double
   if (pcu_dense_enqueue(ctx->stream, dense_dev, o, 1, nullptr, red, ctx->world, mr)) return 1;
   ctx->prof_end();
   ctx->launches++;
+  PCU_CUDA_OK(cudaMemcpyToSymbolAsync(pcu_chain_coef, dense_dev + o.coefB,
+                                      sizeof(double) * PCU_DENSE_MAXM,
+                                      sizeof(double) * 2 * PCU_DENSE_MAXM,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
   // ---- pass 2 of the refinement solve, accumulated, + the step statistics
   Pass2SF fs;
   fs.v = vars.dv(); fs.b = b.dv(); fs.y = y.dv();
   fs.lb = lb->d; fs.ub = ub->d; fs.Dinv = Dinv->d; fs.Cw = Cw->d;
   fs.d1 = d1->d; fs.d2 = d2->d; fs.g = g->d;
   fs.V = V;
-  fs.cdev = dense_dev + o.coefB;
+  fs.cbank = 2 * PCU_DENSE_MAXM;
   fs.ncols = m;
   fs.accumulate = 1; fs.tau = tau; fs.k = k;
   RedBuf rb2 = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
@@ -1266,9 +1274,19 @@ int pcu_ip::iterate_once(int *converged) {
     computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
     if (k == 0) ls.res_norm_prev = res_norm;
   } else {
-    // statistics only: the first solve recomputes the residual on the fly
-    if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr, lazy_res ? 0 : 1))
+    if (lazy_res && upd_stats_valid && norm_type_id() == 0) {
+      // taken at this very point by the update passes of the previous iteration
+      memcpy(res_sums, upd_sums, sizeof(res_sums));
+      memcpy(res_max, upd_max, sizeof(res_max));
+      memcpy(res_min, upd_min, sizeof(res_min));
+      res_mu = barrier_param;
+      res_has_step = 0;
+      denseResidual(v, barrier_param, res, nullptr, nullptr);
+    } else if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr, lazy_res ? 0 : 1)) {
+      // statistics only (lazy_res): the first solve recomputes the residual on the fly
       return 1;
+    }
+    upd_stats_valid = 0;
     comp = compFromStats(v);
     computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
     if (snapshot(k, comp, max_prime, max_dual, max_infeas, res_norm)) return 1;
@@ -1368,7 +1386,7 @@ int pcu_ip::iterate_once(int *converged) {
   double tau_pre = opt.min_fraction_to_boundary;
   if (1.0 - barrier_param >= tau_pre) tau_pre = 1.0 - barrier_param;
   const bool chain = rhs_in_gram && nref == 1 && !mehrotra && !opt_no_chain &&
-                     !opt_no_fuse21 && !opt_no_fuse2s;
+                     !opt_no_fuse21 && !opt_no_fuse2s && ctx->chain_ok();
   if (chain) {
     if (kktChain(v, res, upd, use_qn, mu_for_res, tau_pre, VTp.data())) return 1;
   } else if (rhs_in_gram) {
@@ -1499,22 +1517,35 @@ int pcu_ip::iterate_once(int *converged) {
       v.zs[i] = clip0(v.zs[i], az, upd.zs[i]);
       v.zt[i] = clip0(v.zt[i], az, upd.zt[i]);
     }
-    Update1F f1;
-    f1.v = v.dv();
-    f1.p = upd.dv();
-    f1.lb = lb->d;
-    f1.ub = ub->d;
-    f1.g = g->d;
-    f1.ncon = ncon;
-    for (int j = 0; j < ncon; j++) {
-      f1.Acol.p[j] = Ac[j]->d;
-      f1.z.v[j] = v.z[j];
-    }
-    f1.yqn = form_pair ? y_qn->d : nullptr;
-    f1.ax = ax;
-    f1.az = az;
-    f1.k = kc;
-    if (launch_tile(ctx, f1, nvars, wd, NO_RED)) return 1;
+    // With a quasi-Newton pair to form, the infinity norm and the monotone strategy,
+    // the two update passes also take the residual statistics of the NEXT iteration
+    // at the new point (Update1FT<1> / Update2FT<1>): its stand-alone residual pass
+    // and one synchronisation disappear.
+    const bool take_stats = form_pair && lazy_res && norm_type_id() == 0 && !opt_no_updstats;
+    auto launch_update1 = [&](auto f1) -> int {
+      f1.v = v.dv();
+      f1.p = upd.dv();
+      f1.lb = lb->d;
+      f1.ub = ub->d;
+      f1.g = g->d;
+      f1.ncon = ncon;
+      for (int j = 0; j < ncon; j++) {
+        f1.Acol.p[j] = Ac[j]->d;
+        f1.z.v[j] = v.z[j];
+      }
+      f1.yqn = form_pair ? y_qn->d : nullptr;
+      f1.ax = ax;
+      f1.az = az;
+      f1.k = kc;
+      if (decltype(f1)::NS > 0) {
+        RedBuf rb = ctx->redbuf(decltype(f1)::NS, decltype(f1)::NX, decltype(f1)::NM);
+        if (launch_tile(ctx, f1, nvars, wd, rb)) return 1;
+        ctx->defer();  // fetched together with Update2F's dots (or a callback's sums)
+        return 0;
+      }
+      return launch_tile(ctx, f1, nvars, wd, NO_RED);
+    };
+    if (take_stats ? launch_update1(Update1FT<1>()) : launch_update1(Update1FT<0>())) return 1;
     if (eval_obj_con) {
       if (evalObjCon(v.v[PCU_X])) {
         fprintf(stderr, "ParOpt: Function and constraint evaluation failed\n");
@@ -1530,22 +1561,48 @@ int pcu_ip::iterate_once(int *converged) {
     update_type = 0;
     if (qn) {
       if (uq) {
-        Update2F f2;
-        f2.zw = v.v[PCU_ZW]->d;
-        f2.px = upd.v[PCU_X]->d;
-        f2.g = g->d;
-        f2.ncon = ncon;
-        for (int j = 0; j < ncon; j++) {
-          f2.Acol.p[j] = Ac[j]->d;
-          f2.z.v[j] = v.z[j];
-        }
-        f2.yqn = y_qn->d;
-        f2.sqn = s_qn->d;
-        f2.ax = ax;
-        RedBuf rb = ctx->redbuf(3, 0, 0);
-        if (launch_tile(ctx, f2, nvars, wd, rb)) return 1;
         double dots[3];
-        if (ctx->fetch(dots)) return 1;
+        auto launch_update2 = [&](auto f2) -> int {
+          f2.zw = v.v[PCU_ZW]->d;
+          f2.px = upd.v[PCU_X]->d;
+          f2.g = g->d;
+          f2.zl = prob->use_lower ? v.v[PCU_ZL]->d : nullptr;
+          f2.zu = prob->use_upper ? v.v[PCU_ZU]->d : nullptr;
+          f2.ncon = ncon;
+          for (int j = 0; j < ncon; j++) {
+            f2.Acol.p[j] = Ac[j]->d;
+            f2.z.v[j] = v.z[j];
+          }
+          f2.yqn = y_qn->d;
+          f2.sqn = s_qn->d;
+          f2.ax = ax;
+          RedBuf rb = ctx->redbuf(3, decltype(f2)::NX, 0);
+          if (launch_tile(ctx, f2, nvars, wd, rb)) return 1;
+          double out[4];
+          if (ctx->fetch(out)) return 1;
+          dots[0] = out[0];
+          dots[1] = out[1];
+          dots[2] = out[2];
+          if (decltype(f2)::NX > 0) {
+            // residual statistics of the next iteration, in ResF's layout
+            double u1[9];
+            if (ctx->take_deferred(u1, 9)) return 1;
+            memset(upd_sums, 0, sizeof(upd_sums));
+            upd_sums[0] = u1[0];
+            upd_sums[1] = u1[1];
+            upd_sums[2] = u1[2];
+            upd_max[0] = out[3];  // |rx|
+            upd_max[1] = u1[3];   // |rzw|
+            upd_max[2] = u1[4];   // |rsw|, |rtw|
+            upd_max[3] = u1[5];   // bound products
+            upd_max[4] = u1[6];   // sparse products
+            upd_min[0] = u1[7];
+            upd_min[1] = u1[8];
+            upd_stats_valid = 1;
+          }
+          return 0;
+        };
+        if (take_stats ? launch_update2(Update2FT<1>()) : launch_update2(Update2FT<0>())) return 1;
         // computeQuasiNewtonUpdateCorrection (IP.cpp:4258): the user may change
         // s and y, so the three dots are taken again afterwards
         const bool corrected = prob->hasQnUpdateCorrection();

@@ -59,10 +59,15 @@ __device__ __forceinline__ double gamma_sw(const IPConst &k, long long ci) {
 }
 
 // Coefficient j of a column table: from kernel-parameter space (host-computed), or --
-// device chain of the KKT solve, pcu_dense.cu -- from the work buffer the dense kernel
-// filled just before this launch (uniform address: one L1-resident line per table).
-__device__ __forceinline__ double pcu_coef(const double *dev, const CoefTable &tab, int j) {
-  return dev ? __ldg(dev + j) : tab.v[j];
+// device chain of the KKT solve, pcu_dense.cu -- from a constant bank that a
+// stream-ordered device-to-device copy fills from the dense kernel's output right
+// before this launch (cudaMemcpyToSymbolAsync): the same constant-cache operand either
+// way, no load in the column loops.  Layout: alpha | beta of Pass2R1F, alpha of Pass2SF.
+// (One bank per device and process: the chain is only taken while a single context
+// uses the device, pcu_ctx::chain_ok.)
+static __constant__ double pcu_chain_coef[3 * PCU_DENSE_MAXM];
+__device__ __forceinline__ double pcu_coef(int cbank, const CoefTable &tab, int j) {
+  return cbank >= 0 ? pcu_chain_coef[cbank + j] : tab.v[j];
 }
 
 struct Con0 {  // no per-constraint data
@@ -1041,7 +1046,7 @@ struct Pass2SF : NoStreams {
   const double *lb, *ub, *Dinv, *Cw, *d1, *d2, *g;
   ColTable V;
   CoefTable alpha;
-  const double *cdev;  // device-resident alpha (chain mode), or null
+  int cbank;  // >= 0: alpha at this offset of the constant bank (chain mode); -1: `alpha`
   int ncols;
   int accumulate;
   double tau;
@@ -1093,7 +1098,7 @@ struct Pass2SF : NoStreams {
       for (int jj = 0; jj < 4; jj++) src.template ldc<W>(j + jj, V.p[j + jj], i, c[jj]);
       double al[4];
 #pragma unroll
-      for (int jj = 0; jj < 4; jj++) al[jj] = pcu_coef(cdev, alpha, j + jj);
+      for (int jj = 0; jj < 4; jj++) al[jj] = pcu_coef(cbank, alpha, j + jj);
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) {
 #pragma unroll
@@ -1104,7 +1109,7 @@ struct Pass2SF : NoStreams {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
 #pragma unroll
-      const double aj = pcu_coef(cdev, alpha, j);
+      const double aj = pcu_coef(cbank, alpha, j);
 #pragma unroll
       for (int q = 0; q < W; q++) d[q] = fma(aj, c[q], d[q]);
     }
@@ -1301,9 +1306,19 @@ struct TrialF : NoStreams {
 // step (ax = alpha*alpha_x for primal, az = alpha*alpha_z for dual parts) and
 // y_qn = -g + sum_j z_j A_j + Aw^T zw with the NEW multipliers and the OLD
 // gradients.  Traffic: reads (6 + c)N + 10W, writes 4N + 5W.
-struct Update1F : NoStreams {
+// STATS = 1 also takes, at the NEW point, the part of the next iteration's residual
+// statistics that does not depend on the new gradients (computeComp, IP.cpp:2742-2820;
+// the sparse and bound parts of computeResNorm, IP.cpp:1588-1723) -- the values are in
+// registers here anyway, and together with Update2F's |rx| the stand-alone residual
+// pass (ResF) of a default iteration disappears.  Same expressions, same accumulation
+// order as ResF.   sums: 0 bound comp product, 1 comp count, 2 sparse comp product;
+// maxima: 0 |rzw|, 1 |rsw| / |rtw|, 2 bound products, 3 sparse products; minima: 0
+// bound products, 1 sparse products.
+template <int STATS>
+struct Update1FT : NoStreams {
   static constexpr int SRC = 1;
-  static constexpr int NS = 0, NX = 0, NM = 0, NB = 0;
+  static constexpr int NS = STATS ? 3 : 0, NX = STATS ? 4 : 0, NM = STATS ? 2 : 0,
+                       NB = STATS ? 1 : 0;
   enum { S_X, S_PX, S_LB, S_UB, S_ZL, S_PZL, S_ZU, S_PZU, S_G, S_A0 };
   static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
   static constexpr int TROWS = 512;
@@ -1324,7 +1339,9 @@ struct Update1F : NoStreams {
   }
   typedef Acc<NS, NX, NM> AccT;
   typedef Con1 Con;  // new zw
-  struct Elem {};
+  struct Elem {
+    double x;  // the new x
+  };
   DVars v, p;
   const double *lb, *ub, *g;
   ColTable Acol;
@@ -1346,30 +1363,63 @@ struct Update1F : NoStreams {
   }
 
   template <int W, class S, class AT>
-  __device__ __forceinline__ void A(const S &, long long, const double (&)[W], Elem (&)[W],
-                                    double (&)[W][1], AT *) const {}
-  template <class S, class AT>
-  __device__ __forceinline__ void B(const S &src, long long ci, const double (&)[1], Con &con,
-                                    AT &) const {
-    const double zwn = fma(az, src.ldw(W_PZW, p.zw, ci), src.ldw(W_ZW, v.zw, ci));  // no clipping (IP.cpp:4181)
-    con.d[0] = zwn;
-    v.zw[ci] = zwn;
-    v.sw[ci] = step_clip0(src.ldw(W_SW, v.sw, ci), ax, src.ldw(W_PSW, p.sw, ci), k.dp);
-    v.tw[ci] = step_clip0(src.ldw(W_TW, v.tw, ci), ax, src.ldw(W_PTW, p.tw, ci), k.dp);
-    v.zsw[ci] = step_clip0(src.ldw(W_ZSW, v.zsw, ci), az, src.ldw(W_PZSW, p.zsw, ci), k.dp);
-    v.ztw[ci] = step_clip0(src.ldw(W_ZTW, v.ztw, ci), az, src.ldw(W_PZTW, p.ztw, ci), k.dp);
-  }
-  template <int W, class S, class AT>
-  __device__ __forceinline__ void C(const S &src, long long i, const double (&coef)[W],
-                                    const Elem (&)[W], const Con &con,
-                                    AT &) const {
+  __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
+                                    Elem (&e)[W], double (&part)[W][1], AT *) const {
     double x[W], l[W], u[W], px[W];
     src.template ld<W>(S_X, v.x, i, x);
     src.template ld<W>(S_LB, lb, i, l);
     src.template ld<W>(S_UB, ub, i, u);
     src.template ld<W>(S_PX, p.x, i, px);
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      e[q].x = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
+      part[q][0] = coef[q] * e[q].x;
+    }
+  }
+  template <class S, class AT>
+  __device__ __forceinline__ void B(const S &src, long long ci, const double (&sum)[1], Con &con,
+                                    AT &acc) const {
+    const double zwn = fma(az, src.ldw(W_PZW, p.zw, ci), src.ldw(W_ZW, v.zw, ci));  // no clipping (IP.cpp:4181)
+    con.d[0] = zwn;
+    const double sw = step_clip0(src.ldw(W_SW, v.sw, ci), ax, src.ldw(W_PSW, p.sw, ci), k.dp);
+    const double tw = step_clip0(src.ldw(W_TW, v.tw, ci), ax, src.ldw(W_PTW, p.tw, ci), k.dp);
+    const double zsw = step_clip0(src.ldw(W_ZSW, v.zsw, ci), az, src.ldw(W_PZSW, p.zsw, ci), k.dp);
+    const double ztw = step_clip0(src.ldw(W_ZTW, v.ztw, ci), az, src.ldw(W_PZTW, p.ztw, ci), k.dp);
+    v.zw[ci] = zwn;
+    v.sw[ci] = sw;
+    v.tw[ci] = tw;
+    v.zsw[ci] = zsw;
+    v.ztw[ci] = ztw;
+    if (STATS) {  // ResF::B at the new point
+      const double gsw = gamma_sw(k, ci), gtw = k.gamma;
+      const double rzw = -(((k.wconst + sum[0]) - sw) + tw);
+      const double rsw = (zsw - gsw) - zwn;
+      const double rtw = (ztw - gtw) + zwn;
+      const double asw = sw * zsw, atw = tw * ztw;
+      acc.x[3] = fmax(acc.x[3], fmax(asw, atw));
+      acc.m[1] = fmin(acc.m[1], fmin(asw, atw));
+      acc.s[2] += asw + atw;
+      acc.s[1] += 2.0;
+      acc.x[0] = fmax(acc.x[0], fabs(rzw));
+      acc.x[1] = fmax(acc.x[1], fmax(fabs(rsw), fabs(rtw)));
+    }
+  }
+  template <int W, class S, class AT>
+  __device__ __forceinline__ void C(const S &src, long long i, const double (&coef)[W],
+                                    const Elem (&e)[W], const Con &con,
+                                    AT &acc) const {
+    double l[W], u[W], zl[W], zu[W], x[W];
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      x[q] = e[q].x;
+      zl[q] = zu[q] = 0.0;
+    }
+    if (STATS) {
+      src.template ld<W>(S_LB, lb, i, l);
+      src.template ld<W>(S_UB, ub, i, u);
+    }
     if (k.use_lower) {
-      double zl[W], pzl[W];
+      double pzl[W];
       src.template ld<W>(S_ZL, v.zl, i, zl);
       src.template ld<W>(S_PZL, p.zl, i, pzl);
 #pragma unroll
@@ -1377,7 +1427,7 @@ struct Update1F : NoStreams {
       stv<W>(v.zl, i, zl);
     }
     if (k.use_upper) {
-      double zu[W], pzu[W];
+      double pzu[W];
       src.template ld<W>(S_ZU, v.zu, i, zu);
       src.template ld<W>(S_PZU, p.zu, i, pzu);
 #pragma unroll
@@ -1399,12 +1449,37 @@ struct Update1F : NoStreams {
       for (int q = 0; q < W; q++) yv[q] = fma(coef[q], con.d[0], yv[q]);
       stv<W>(yqn, i, yv);
     }
-#pragma unroll
-    for (int q = 0; q < W; q++)
-      x[q] = step_clip(x[q], ax, px[q], l[q], u[q], k.dp);
     stv<W>(v.x, i, x);
+    if (STATS) {  // ResF::A / C at the new point: complementarity of the bounds
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        const bool ml = k.use_lower && (l[q] > -k.mbv);
+        const bool mu_ = k.use_upper && (u[q] < k.mbv);
+        const double dl = x[q] - l[q], du = u[q] - x[q];
+        double cp = 0.0, cc = 0.0, amax = 0.0, amin = 1.0e300;
+        if (ml) {
+          const double a = dl * zl[q];
+          cp += a;
+          cc += 1.0;
+          amax = fmax(amax, a);
+          amin = fmin(amin, a);
+        }
+        if (mu_) {
+          const double a = du * zu[q];
+          cp += a;
+          cc += 1.0;
+          amax = fmax(amax, a);
+          amin = fmin(amin, a);
+        }
+        acc.s[0] += cp;
+        acc.s[1] += cc;
+        acc.x[2] = fmax(acc.x[2], amax);
+        acc.m[0] = fmin(acc.m[0], amin);
+      }
+    }
   }
 };
+typedef Update1FT<0> Update1F;
 
 // ============================================================== Update2F
 // computeStepAndUpdate, second half (IP.cpp:4244-4256) after the new gradients:
@@ -1412,16 +1487,21 @@ struct Update1F : NoStreams {
 // fused with the three dot products that open ParOptLBFGS::update /
 // ParOptLSR1::update (QN.cpp:168-170, 641-642).
 // Traffic: reads (3 + c)N + W, writes 2N.   sums: 0 y.y, 1 y.s, 2 s.s
-struct Update2F : NoStreams {
+// RX = 1 (+ 2N reads: zl, zu) also takes |rx|_inf of the NEXT iteration's residual
+// rx = zl - zu - g + sum_j z_j A_j + Aw^T zw (computeKKTRes, IP.cpp:1337-1399, with
+// ResF's expression order) -- see Update1FT<1>.   maxima: 0 |rx|
+template <int RX>
+struct Update2FT : NoStreams {
   static constexpr int SRC = 1;
-  static constexpr int NS = 3, NX = 0, NM = 0, NB = 0;
-  enum { S_Y, S_G, S_PX, S_A0 };
+  static constexpr int NS = 3, NX = RX ? 1 : 0, NM = 0, NB = 0;
+  enum { S_Y, S_G, S_PX, S_ZL, S_ZU, S_A0 };
   static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
   static constexpr int TROWS = 1024;
   enum { W_ZW, NWSLOTS };
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
     p_.n(S_Y, yqn); p_.n(S_G, g); p_.n(S_PX, px);
+    if (RX) { p_.n(S_ZL, zl); p_.n(S_ZU, zu); }
     for (int j = 0; j < ncon; j++) p_.n(S_A0 + j, Acol.p[j]);
     p_.w(W_ZW, zw);
   }
@@ -1429,6 +1509,7 @@ struct Update2F : NoStreams {
   typedef Con1 Con;  // zw
   struct Elem {};
   const double *zw, *px, *g;
+  const double *zl, *zu;  // RX only; null when the bound is not used
   ColTable Acol;
   CoefTable z;
   int ncon;
@@ -1438,6 +1519,7 @@ struct Update2F : NoStreams {
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
     p_(yqn); p_(g); p_(px);
+    if (RX) { p_(zl); p_(zu); }
     for (int j = 0; j < ncon; j++) p_(Acol.p[j]);
   }
 
@@ -1453,17 +1535,29 @@ struct Update2F : NoStreams {
   __device__ __forceinline__ void C(const S &src, long long i, const double (&coef)[W],
                                     const Elem (&)[W], const Con &con,
                                     AT &acc) const {
-    double yv[W], gv[W], pv[W], sv[W];
+    double yv[W], gv[W], pv[W], sv[W], rx[W];
     src.template ld<W>(S_Y, yqn, i, yv);
     src.template ld<W>(S_G, g, i, gv);
     src.template ld<W>(S_PX, px, i, pv);
+    if (RX) {
+      double a[W], b[W];
+#pragma unroll
+      for (int q = 0; q < W; q++) a[q] = b[q] = 0.0;
+      if (zl) src.template ld<W>(S_ZL, zl, i, a);
+      if (zu) src.template ld<W>(S_ZU, zu, i, b);
+#pragma unroll
+      for (int q = 0; q < W; q++) rx[q] = (a[q] - b[q]) - gv[q];
+    }
 #pragma unroll
     for (int q = 0; q < W; q++) yv[q] += gv[q];
     for (int j = 0; j < ncon; j++) {
       double a[W];
       src.template ldc<W>(j, Acol.p[j], i, a);
 #pragma unroll
-      for (int q = 0; q < W; q++) yv[q] = fma(-z.v[j], a[q], yv[q]);
+      for (int q = 0; q < W; q++) {
+        yv[q] = fma(-z.v[j], a[q], yv[q]);
+        if (RX) rx[q] = fma(z.v[j], a[q], rx[q]);
+      }
     }
 #pragma unroll
     for (int q = 0; q < W; q++) {
@@ -1472,11 +1566,13 @@ struct Update2F : NoStreams {
       acc.s[0] = fma(yv[q], yv[q], acc.s[0]);
       acc.s[1] = fma(yv[q], sv[q], acc.s[1]);
       acc.s[2] = fma(sv[q], sv[q], acc.s[2]);
+      if (RX) acc.x[0] = fmax(acc.x[0], fabs(fma(coef[q], con.d[0], rx[q])));
     }
     stv<W>(yqn, i, yv);
     stv<W>(sqn, i, sv);
   }
 };
+typedef Update2FT<0> Update2F;
 
 // ============================================================== LinCombF
 // out = beta * x + sum_j alpha_j V_j   (ParOptLBFGS::mult, QN.cpp:390-418, second
@@ -1849,7 +1945,7 @@ struct Pass2R1F : NoStreams {
   double *d2, *d1out;
   ColTable V;
   CoefTable alpha, beta;
-  const double *cdev;  // device-resident alpha | beta (chain mode, beta at +PCU_DENSE_MAXM), or null
+  int cbank;  // >= 0: alpha | beta at this offset (+ PCU_DENSE_MAXM) of the constant bank; -1: tables
   int ncols;
   int accumulate;
   int from_vars;
@@ -1910,8 +2006,8 @@ struct Pass2R1F : NoStreams {
       double al[4], be[4];
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) {
-        al[jj] = pcu_coef(cdev, alpha, j + jj);
-        be[jj] = pcu_coef(cdev ? cdev + PCU_DENSE_MAXM : nullptr, beta, j + jj);
+        al[jj] = pcu_coef(cbank, alpha, j + jj);
+        be[jj] = pcu_coef(cbank >= 0 ? cbank + PCU_DENSE_MAXM : -1, beta, j + jj);
       }
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) {
@@ -1925,8 +2021,8 @@ struct Pass2R1F : NoStreams {
     for (; j < ncols; j++) {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
-      const double aj = pcu_coef(cdev, alpha, j);
-      const double bj = pcu_coef(cdev ? cdev + PCU_DENSE_MAXM : nullptr, beta, j);
+      const double aj = pcu_coef(cbank, alpha, j);
+      const double bj = pcu_coef(cbank >= 0 ? cbank + PCU_DENSE_MAXM : -1, beta, j);
 #pragma unroll
       for (int q = 0; q < W; q++) {
         d[q] = fma(aj, c[q], d[q]);

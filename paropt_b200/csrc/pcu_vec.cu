@@ -40,6 +40,11 @@ NcclApi &nccl_api() {
     }                                                                         \
   } while (0)
 
+static int g_ctx_on_device[PCU_MAX_DEVICES] = {0};
+bool pcu_ctx::chain_ok() const {
+  return device >= 0 && device < PCU_MAX_DEVICES && g_ctx_on_device[device] == 1;
+}
+
 RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
   RedBuf rb;
   rb.prefetch = 0;
@@ -257,11 +262,13 @@ pcu_ctx *pcu_ctx_create(int device) {
     delete ctx;
     return nullptr;
   }
+  if (device >= 0 && device < PCU_MAX_DEVICES) g_ctx_on_device[device]++;
   return ctx;
 }
 
 void pcu_ctx_destroy(pcu_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES) g_ctx_on_device[ctx->device]--;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);

@@ -109,3 +109,44 @@ def test_weighting_blocks_ending_inside_a_slab(ctx):
     plain = run(ctx, Partial, opts, 14, True)
     cnt, worst, first = compare_histories(plain, fused, max_iters=13, nvars=8192)
     assert cnt == 13 and first is None, (first, worst)
+
+
+@pytest.mark.parametrize("name,n", [("C3", 8 * 5003), ("C2", 50001)])
+def test_device_chain_reproduces_host_dense_algebra_bitwise(ctx, name, n):
+    """The device chain of the KKT solve (pcu_dense.cu: LU of G and Ce, SMW
+    coefficients and dense residuals in a single-CTA kernel between the streaming
+    passes) executes the statements of the host path with the same rounding
+    (-fmad=false): with PCU_NO_CHAIN the dense algebra runs on the host instead, and
+    the two histories are identical to the last bit."""
+    from paropt_b200.api import problem_from_config
+    cfg = configs.get(name, n)
+    chain = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 16, False)
+    os.environ["PCU_NO_CHAIN"] = "1"
+    try:
+        host = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 16, False)
+    finally:
+        os.environ.pop("PCU_NO_CHAIN", None)
+    assert len(chain) == len(host) == 16
+    for a, b in zip(chain, host):
+        for key in a:
+            assert a[key] == b[key], (a["iter"], key, a[key], b[key])
+
+
+@pytest.mark.parametrize("name,n", [("C3", 8 * 5003), ("C2", 50001)])
+def test_residual_statistics_taken_by_the_update_passes(ctx, name, n):
+    """Update1FT<1> / Update2FT<1> take the next iteration's residual statistics at the
+    new point with ResF's own expressions: with PCU_NO_UPDSTATS the stand-alone residual
+    pass runs instead.  Same terms, another summation order across the tiles: the two
+    histories agree to 1e-12 (measured: last-bit differences in comp / fobj)."""
+    from paropt_b200.api import problem_from_config
+    cfg = configs.get(name, n)
+    fused = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 16, False)
+    os.environ["PCU_NO_UPDSTATS"] = "1"
+    try:
+        plain = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 16, False)
+    finally:
+        os.environ.pop("PCU_NO_UPDSTATS", None)
+    cnt, worst, first = compare_histories(plain, fused, max_iters=16, cfg=cfg, rtol=1e-12)
+    assert cnt == 16 and first is None, (first, worst)
+    for a, b in zip(fused, plain):
+        assert a["info"] == b["info"] and a["neval"] == b["neval"]
