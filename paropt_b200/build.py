@@ -16,9 +16,8 @@ FLAGS = [
 ] + os.environ.get("PCU_EXTRA_FLAGS", "").split()
 
 
-# pcu_dense.cu: host and device must execute the same multiply / add sequence
-# (the device chain of the KKT solve reproduces the host path bit for bit)
-PER_FILE_FLAGS = {"pcu_dense.cu": ["-fmad=false"]}
+# per-file nvcc flags (none today)
+PER_FILE_FLAGS = {}
 
 
 def needs_build():

@@ -112,12 +112,12 @@ def test_weighting_blocks_ending_inside_a_slab(ctx):
 
 
 @pytest.mark.parametrize("name,n", [("C3", 8 * 5003), ("C2", 50001)])
-def test_device_chain_reproduces_host_dense_algebra_bitwise(ctx, name, n):
+def test_device_chain_matches_host_dense_algebra(ctx, name, n):
     """The device chain of the KKT solve (pcu_dense.cu: LU of G and Ce, SMW
     coefficients and dense residuals in a single-CTA kernel between the streaming
-    passes) executes the statements of the host path with the same rounding
-    (-fmad=false): with PCU_NO_CHAIN the dense algebra runs on the host instead, and
-    the two histories are identical to the last bit."""
+    passes) executes the statements of the host path, with reciprocals (<= 1 ulp)
+    in place of the divisions on its critical path: with PCU_NO_CHAIN the dense algebra
+    runs on the host instead, and the two histories agree to 1e-12."""
     from paropt_b200.api import problem_from_config
     cfg = configs.get(name, n)
     chain = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 16, False)
@@ -126,10 +126,10 @@ def test_device_chain_reproduces_host_dense_algebra_bitwise(ctx, name, n):
         host = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 16, False)
     finally:
         os.environ.pop("PCU_NO_CHAIN", None)
-    assert len(chain) == len(host) == 16
+    cnt, worst, first = compare_histories(host, chain, max_iters=16, cfg=cfg, rtol=1e-12)
+    assert cnt == 16 and first is None, (first, worst)
     for a, b in zip(chain, host):
-        for key in a:
-            assert a[key] == b[key], (a["iter"], key, a[key], b[key])
+        assert a["info"] == b["info"] and a["neval"] == b["neval"]
 
 
 @pytest.mark.parametrize("name,n", [("C3", 8 * 5003), ("C2", 50001)])
