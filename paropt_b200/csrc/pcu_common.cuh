@@ -174,6 +174,13 @@ struct RedBuf {
   unsigned int *counter;   // zero before launch, reset by the last block
   double *result;          // [NR] device
   int prefetch;            // grid-stride iterations to prefetch ahead into L2 (0: off)
+  // Zero-copy hand-over to the host (optional): the last block also stores the NR
+  // results into page-locked host memory mapped into the device address space and
+  // then publishes `seq` in *hflag (system-scope release); the host polls the flag
+  // instead of enqueueing a copy and synchronising the stream.
+  double *hres;
+  unsigned long long *hflag;
+  unsigned long long seq;
 };
 
 // Block-level + grid-level deterministic combine.  Every thread of the block
@@ -249,9 +256,22 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb, const int tid_ = 
         else if (i < NS + NX) v = fmax(v, q);
         else v = fmin(v, q);
       }
-      if (lane == 0) rb.result[i] = v;
+      if (lane == 0) {
+        rb.result[i] = v;
+        if (rb.hres) {
+          rb.hres[i] = v;
+          __threadfence_system();
+        }
+      }
     }
     if (tid == 0) *rb.counter = 0u;
+    if (rb.hres) {  // (uniform) every value is on its way to the host: publish
+      PCU_RED_SYNC();
+      if (tid == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(rb.hflag) = rb.seq;
+      }
+    }
   }
 #undef PCU_RED_SYNC
 }

@@ -27,6 +27,27 @@ struct pcu_ctx {
   double *h_result = nullptr;   // pinned mirror
   double *d_gather = nullptr;   // [world][total] packed partials of all ranks (multi-GPU)
   double *h_gather = nullptr;   // pinned mirror, combined on the host in rank order
+  // zero-copy results (RedBuf::hres / hflag): page-locked host memory mapped into the
+  // device; [0, CAP + MAX_RED) doubles of results, then the flag word
+  double *h_zc = nullptr, *d_zc = nullptr;
+  unsigned long long *h_zflag = nullptr, *d_zflag = nullptr;
+  unsigned long long zc_seq = 0;       // sequence number of the last reduction launched
+  bool zc_on = false;
+  // single-node all-gather of the ranks' packed partials through POSIX shared memory
+  // (the values are consumed by the hosts: PCIe write + shared memory is the shortest
+  // path from N GPUs to N host threads); NCCL all-gather when unavailable
+  struct ShmRank {
+    volatile unsigned long long seq;
+    char pad[56];
+    double data[2][512];
+  };
+  void *shm_base = nullptr;
+  size_t shm_bytes = 0;
+  unsigned long long shm_pub = 0;      // publications made so far
+  char shm_name[64] = {0};
+  int wait_flag(unsigned long long seq);
+  int shm_setup(const unsigned char id128[128]);
+  int shm_allgather(int total);
   int result_used = 0;
   bool red_overflow = false;   // redbuf() ran out of slots: the next fetch() fails
   std::vector<PendingRed> pending;

@@ -403,6 +403,7 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
   if (getenv("PCU_NO_FUSE2S")) opt_no_fuse2s = 1;
   if (getenv("PCU_NO_RHSGRAM")) opt_no_rhsgram = 1;
   if (getenv("PCU_NO_CHAIN")) opt_no_chain = 1;
+  if (getenv("PCU_CHAIN")) opt_force_chain = 1;
   if (getenv("PCU_NO_UPDSTATS")) opt_no_updstats = 1;
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all) {

@@ -2,8 +2,15 @@
 // (reference: src/ParOptVec.cpp:15-217; one fused, deterministic kernel per
 // BLAS-1 call + MPI_Allreduce pair of the reference).
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
 
 #include "pcu_ctx.cuh"
 
@@ -46,7 +53,7 @@ bool pcu_ctx::chain_ok() const {
 }
 
 RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
-  RedBuf rb;
+  RedBuf rb = {};
   rb.prefetch = 0;
   rb.partials = d_partials;
   rb.counter = d_counter;
@@ -62,9 +69,121 @@ RedBuf pcu_ctx::redbuf(int ns, int nx, int nm) {
     return rb;
   }
   rb.result = d_result + result_used;
+  if (zc_on) {
+    rb.hres = d_zc + result_used;
+    rb.hflag = d_zflag;
+    rb.seq = ++zc_seq;
+  }
   pending.push_back({result_used, ns, nx, nm});
   result_used += nr;
   return rb;
+}
+
+// Host side of the zero-copy hand-over: poll the flag the last block of the most
+// recent reduction kernel publishes (kernels of one stream complete in order).
+int pcu_ctx::wait_flag(unsigned long long seq) {
+  volatile unsigned long long *flag = h_zflag;
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  while (*flag < seq) {
+    if ((++spins & 0xfff) == 0) {
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        fprintf(stderr, "paropt_b200: CUDA error while waiting for a reduction: %s\n",
+                cudaGetErrorString(q));
+        return 1;
+      }
+      if (q == cudaSuccess && *flag < seq) {
+        // the stream drained without the flag: the launch itself failed
+        if (*flag < seq) {
+          fprintf(stderr, "paropt_b200: reduction result never arrived\n");
+          return 1;
+        }
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+        fprintf(stderr, "paropt_b200: timed out waiting for a reduction\n");
+        return 1;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return 0;
+}
+
+// ----- shared-memory all-gather between the ranks of one node
+static unsigned long long hash128(const unsigned char id[128]) {
+  unsigned long long h = 1469598103934665603ull;
+  for (int i = 0; i < 128; i++) h = (h ^ id[i]) * 1099511628211ull;
+  return h;
+}
+
+int pcu_ctx::shm_setup(const unsigned char id128[128]) {
+  snprintf(shm_name, sizeof(shm_name), "/pcu_%016llx", hash128(id128));
+  shm_bytes = 4096 + sizeof(ShmRank) * (size_t)world;
+  int fd = -1;
+  if (rank == 0) {
+    shm_unlink(shm_name);
+    fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd >= 0 && ftruncate(fd, (off_t)shm_bytes) != 0) {
+      close(fd);
+      fd = -1;
+    }
+  } else {
+    for (int tries = 0; tries < 20000 && fd < 0; tries++) {  // rank 0 creates it first
+      fd = shm_open(shm_name, O_RDWR, 0600);
+      if (fd >= 0) {
+        struct stat st;
+        if (fstat(fd, &st) != 0 || (size_t)st.st_size < shm_bytes) {
+          close(fd);
+          fd = -1;
+        }
+      }
+      if (fd < 0) usleep(500);
+    }
+  }
+  if (fd < 0) return 1;
+  void *p = mmap(nullptr, shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return 1;
+  shm_base = p;
+  // attach count: rank 0 removes the name once everybody is in
+  volatile int *attached = reinterpret_cast<volatile int *>(p);
+  __sync_fetch_and_add(attached, 1);
+  if (rank == 0) {
+    for (long tries = 0; *attached < world && tries < 40000; tries++) usleep(500);
+    shm_unlink(shm_name);
+    if (*attached < world) return 1;
+  }
+  return 0;
+}
+
+int pcu_ctx::shm_allgather(int total) {
+  ShmRank *ranks = reinterpret_cast<ShmRank *>(reinterpret_cast<char *>(shm_base) + 4096);
+  const unsigned long long n = ++shm_pub;
+  ShmRank &mine = ranks[rank];
+  memcpy(mine.data[n & 1], h_zc, sizeof(double) * (size_t)total);
+  std::atomic_thread_fence(std::memory_order_release);
+  mine.seq = n;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < world; r++) {
+    unsigned long spins = 0;
+    while (ranks[r].seq < n) {
+      if ((++spins & 0xffff) == 0 &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
+        fprintf(stderr, "paropt_b200: rank %d timed out waiting for rank %d\n", rank, r);
+        return 1;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(h_gather + (size_t)r * total, ranks[r].data[n & 1], sizeof(double) * (size_t)total);
+  }
+  return 0;
 }
 
 int pcu_ctx::fetch(double *out) {
@@ -77,7 +196,14 @@ int pcu_ctx::fetch(double *out) {
     return 1;
   }
   const int total = result_used;
-  if (total > 0) {
+  const bool zc = zc_on && total > 0 && total <= 512;
+  const bool via_shm = zc && world > 1 && shm_base != nullptr;
+  if (zc && (world == 1 || via_shm)) {
+    // zero-copy: the results are already on their way into h_zc
+    if (wait_flag(zc_seq)) return 1;
+    if (world == 1) memcpy(h_result, h_zc, sizeof(double) * (size_t)total);
+    else if (shm_allgather(total)) return 1;
+  } else if (total > 0) {
     if (world > 1) {
       // one all-gather of the `total` packed partials; the fixed-rank-order combine
       // runs on the host of every rank (identical data, identical order: identical
@@ -91,7 +217,7 @@ int pcu_ctx::fetch(double *out) {
                                   cudaMemcpyDeviceToHost, stream));
     }
   }
-  PCU_CUDA_OK(cudaStreamSynchronize(stream));
+  if (!(zc && (world == 1 || via_shm))) PCU_CUDA_OK(cudaStreamSynchronize(stream));
   if (world > 1 && total > 0) {
     for (const PendingRed &pr : pending) {
       const int nr = pr.ns + pr.nx + pr.nm;
@@ -251,6 +377,19 @@ pcu_ctx *pcu_ctx_create(int device) {
   ok &= cudaMalloc(&ctx->d_counter, 64) == cudaSuccess;
   ok &= cudaMalloc(&ctx->d_result, sizeof(double) * (PCU_RESULT_CAP + PCU_MAX_RED)) == cudaSuccess;
   ok &= cudaMallocHost(&ctx->h_result, sizeof(double) * PCU_RESULT_CAP) == cudaSuccess;
+  if (!getenv("PCU_NO_ZEROCOPY")) {
+    void *hp = nullptr, *dp = nullptr;
+    const size_t zbytes = sizeof(double) * (PCU_RESULT_CAP + PCU_MAX_RED) + 128;
+    if (cudaHostAlloc(&hp, zbytes, cudaHostAllocMapped) == cudaSuccess &&
+        cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+      memset(hp, 0, zbytes);
+      ctx->h_zc = (double *)hp;
+      ctx->d_zc = (double *)dp;
+      ctx->h_zflag = (unsigned long long *)((char *)hp + zbytes - 64);
+      ctx->d_zflag = (unsigned long long *)((char *)dp + zbytes - 64);
+      ctx->zc_on = true;
+    }
+  }
   ok &= cudaMemset(ctx->d_counter, 0, 64) == cudaSuccess;
   ok &= cudaMemset(ctx->d_result, 0, sizeof(double) * (PCU_RESULT_CAP + PCU_MAX_RED)) == cudaSuccess;
   ok &= cudaEventCreate(&ctx->ev0) == cudaSuccess;
@@ -276,6 +415,8 @@ void pcu_ctx_destroy(pcu_ctx *ctx) {
   cudaFree(ctx->d_counter);
   cudaFree(ctx->d_result);
   cudaFreeHost(ctx->h_result);
+  if (ctx->h_zc) cudaFreeHost(ctx->h_zc);
+  if (ctx->shm_base) munmap(ctx->shm_base, ctx->shm_bytes);
   if (ctx->d_gather) cudaFree(ctx->d_gather);
   if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
   if (ctx->d_big) cudaFree(ctx->d_big);
@@ -321,6 +462,21 @@ int pcu_ctx_init_comm(pcu_ctx *ctx, const unsigned char id128[128], int rank,
                          sizeof(double) * PCU_RESULT_CAP * world_size));
   PCU_CUDA_OK(cudaMallocHost(&ctx->h_gather,
                              sizeof(double) * PCU_RESULT_CAP * world_size));
+  // host-consumed reductions: shared-memory all-gather between the ranks of this node
+  // (every rank decides alike: the verdict is all-reduced over NCCL)
+  int have = 0;
+  if (ctx->zc_on && !getenv("PCU_NO_SHM")) have = ctx->shm_setup(id128) == 0 ? 1 : 0;
+  int *d_have = nullptr;
+  PCU_CUDA_OK(cudaMalloc(&d_have, sizeof(int)));
+  PCU_CUDA_OK(cudaMemcpy(d_have, &have, sizeof(int), cudaMemcpyHostToDevice));
+  PCU_NCCL_OK(api.AllReduce(d_have, d_have, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+  PCU_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  PCU_CUDA_OK(cudaMemcpy(&have, d_have, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_have);
+  if (!have && ctx->shm_base) {
+    munmap(ctx->shm_base, ctx->shm_bytes);
+    ctx->shm_base = nullptr;
+  }
   return 0;
 }
 

@@ -64,6 +64,14 @@ def run_big(make, plain):
 for label, nbig in (("C3_big", 8 * 5003 * ctx.size), ("C2_big", 50001 * ctx.size)):
     cfg_big = configs.get(label[:2], nbig)
     fused = run_big(lambda: problem_from_config(ctx, cfg_big), False)
+    # the device chain of the KKT solve across the ranks (in-stream all-reduce /
+    # all-gather feeding the dense kernel): opt-in at world > 1
+    os.environ["PCU_CHAIN"] = "1"
+    chained = run_big(lambda: problem_from_config(ctx, cfg_big), False)
+    os.environ.pop("PCU_CHAIN", None)
+    n0, w0, f0 = compare_histories(fused, chained, max_iters=12, cfg=cfg_big, rtol=1e-12)
+    verdict["cases"][label + "_chain"] = {"compared": n0, "first_violation": f0,
+                                          "worst": max(checked(w0).values())}
     plain = run_big(lambda: problem_from_config(ctx, cfg_big), True)
     host = run_big(lambda: BuiltinProblem(ctx, "sepquad", host=True, nthreads=2,
                                           **cfg_big["problem"]), False)
