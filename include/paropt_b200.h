@@ -165,6 +165,28 @@ int pcu_blockmat_apply3(pcu_blockmat *mat, pcu_vec *bx, pcu_vec *yx, pcu_vec *yw
 int pcu_blockmat_apply4(pcu_blockmat *mat, pcu_vec *bx, pcu_vec *bw, pcu_vec *yx,
                         pcu_vec *yw);
 
+/* Block form, nwblock > 1 (ParOptQuasiDefBlockMat with nwblock = nb, SM.cpp:72-111,
+   196-224): the sparse constraints come in groups of nb consecutive rows that share
+   the nw variables of one block; block b covers the variables
+   [wstart + b * wstride, + nw), its rows are  cw_{b nb + r}(x) = wconst[r] +
+   sum_k coef[r * nw + k] * x[wstart + b * wstride + k].  Ew = Cdiag + Aw Dinv Aw^T is
+   then block diagonal with dense nb x nb blocks, kept packed upper and factored by
+   Cholesky (LAPACK dpptrf / dpptrs "U" in the reference).  1 <= nb <= 8, nw <= 64;
+   coef / wconst are copied.  factor / apply3 / apply4 as for pcu_blockmat_create;
+   factor returns k > 0 when the block holding (local) row k - 1 is not positive
+   definite.                                                                       */
+typedef struct pcu_block_weighting {
+  int nblocks;        /* local number of blocks (nwcon = nblocks * nb)              */
+  int wstart;         /* first variable of block 0                                  */
+  int nw;             /* variables per block                                        */
+  int wstride;        /* distance between the first variables of consecutive blocks */
+  int nb;             /* constraints per block = nwblock                            */
+  const double *coef; /* [nb][nw] row-major                                         */
+  const double *wconst; /* [nb], may be NULL (zeros)                                */
+} pcu_block_weighting;
+pcu_blockmat *pcu_blockmat_create_blocks(pcu_ctx *ctx, int nvars,
+                                         const pcu_block_weighting *blocks);
+
 /* ---- ParOptCompactQuasiNewton (ParOptLBFGS / ParOptLSR1) as a stand-alone object
    (ParOptQuasiNewton.h:32-213): what ParOptInteriorPoint::setQuasiNewton or the
    trust-region front end is handed.  qn_type "bfgs" | "sr1".

@@ -186,6 +186,19 @@ def main():
             json.dump(data, fp, separators=(",", ":"))
         print("C4_full.json", "niter", data["final"]["niter"], data["status"], flush=True)
         return
+    if "--nb2" in sys.argv:
+        # ParOptQuasiDefBlockMat with nwblock = 2 (dense 2 x 2 blocks of Ew, dpptrf /
+        # dpptrs): C3-style workload whose blocks carry two sparse constraints
+        cfg = configs.get("C3", 4000)
+        cfg["problem"]["nb"] = 2
+        cfg["options"] = dict(cfg["options"], max_major_iters=40)
+        data = run_reference(cfg)
+        data["generator"] = ("oracle/make_golden.py --nb2 (oracle/_ref/ref_driver, unmodified "
+                             "reference, ParOptQuasiDefBlockMat nwblock = 2)")
+        with open(os.path.join(out_dir, "C3_nb2_small.json"), "w") as fp:
+            json.dump(data, fp, separators=(",", ":"))
+        print("C3_nb2_small.json", "niter", data["final"]["niter"], data["status"])
+        return
     if "--full-c4-np4" in sys.argv:
         # evidence for the stated C4_full tolerance: the SAME unmodified reference on 4
         # instead of 8 ranks (another summation partition of the 5050 Gram dot

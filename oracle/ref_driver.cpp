@@ -74,6 +74,7 @@ struct SepQuadParams {
   long ntotal = 1000;
   int ncon = 1;
   int nw = 0;  // variables per weighting block; 0 = no weighting constraints
+  int nb = 1;  // sparse constraints per block (nwblock of ParOptQuasiDefBlockMat): 1 or 2
   uint64_t seed = 0;
   double lam_min = 1.0, lam_max = 1e3;
   double b_lo = 0.0, b_w = 1.0;
@@ -246,7 +247,11 @@ class SepQuad : public HistoryProblem {
     offset = u0 * unit;
     n = (int)((u1 - u0) * unit);
     if (rank == size - 1) n = (int)(p.ntotal - offset);
-    nwc = p.nw > 0 ? (int)(u1 - u0) : 0;
+    nblk = p.nw > 0 ? (int)(u1 - u0) : 0;
+    nwc = nblk * p.nb;
+    // second row of a block (nb = 2): cw = 1.5 - sum_k ((k % 3) + 1) / 3 x_k
+    c1.resize(p.nw > 0 ? p.nw : 1);
+    for (int k = 0; k < p.nw; k++) c1[k] = -((k % 3) + 1) / 3.0;
     setProblemSizes(n, p.ncon, nwc);
     setNumInequalities(p.ncon, nwc);
 
@@ -276,6 +281,23 @@ class SepQuad : public HistoryProblem {
 
   ParOptQuasiDefMat *createQuasiDefMat() {
 #ifdef PCU_ADAPTERS
+    if (p.nb > 1) {
+      // block form: nb rows per block, dense nb x nw coefficient matrix
+      std::vector<double> coef((size_t)p.nb * p.nw);
+      for (int k = 0; k < p.nw; k++) {
+        coef[k] = k == 0 ? 1.0 : -1.0;
+        coef[p.nw + k] = c1[k];
+      }
+      pcu_block_weighting bw;
+      memset(&bw, 0, sizeof(bw));
+      bw.nblocks = nblk;
+      bw.wstart = 0;
+      bw.nw = p.nw;
+      bw.wstride = p.nw;
+      bw.nb = p.nb;
+      bw.coef = coef.data();
+      return new ParOptCudaQuasiDefBlockMat(ParOptCudaContext(), n, &bw);
+    }
     pcu_weighting w;
     memset(&w, 0, sizeof(w));
     if (nwc > 0) {
@@ -288,7 +310,7 @@ class SepQuad : public HistoryProblem {
     }
     return new ParOptCudaQuasiDefBlockMat(ParOptCudaContext(), n, &w);
 #else
-    int nwblock = (nwc > 0) ? 1 : 0;
+    int nwblock = (nwc > 0) ? p.nb : 0;
     return new ParOptQuasiDefBlockMat(this, nwblock);
 #endif
   }
@@ -379,15 +401,22 @@ class SepQuad : public HistoryProblem {
   }
 
   // cw_i = x[nw i] - sum_{k=1}^{nw-1} x[nw i + k]
-  // (weighting form of examples/dmo_truss/dmo_truss_analysis.py:650-679)
+  // (weighting form of examples/dmo_truss/dmo_truss_analysis.py:650-679); with nb = 2
+  // every block carries a second row 1.5 + sum_k c1_k x[nw i + k] and the blocks of
+  // Aw D^-1 Aw^T are dense 2 x 2 (packed upper: (0,0), (0,1), (1,1))
   void evalSparseCon(ParOptVec *xvec, ParOptVec *out) {
     double *x, *o;
     xvec->getArray(&x);
     out->getArray(&o);
-    for (int i = 0; i < nwc; i++) {
+    for (int i = 0; i < nblk; i++) {
       double s = x[p.nw * i];
       for (int k = 1; k < p.nw; k++) s -= x[p.nw * i + k];
-      o[i] = s;
+      o[p.nb * i] = s;
+      if (p.nb > 1) {
+        double s1 = 1.5;
+        for (int k = 0; k < p.nw; k++) s1 += c1[k] * x[p.nw * i + k];
+        o[p.nb * i + 1] = s1;
+      }
     }
   }
   void addSparseJacobian(ParOptScalar alpha, ParOptVec *, ParOptVec *px,
@@ -395,10 +424,15 @@ class SepQuad : public HistoryProblem {
     double *v, *o;
     px->getArray(&v);
     out->getArray(&o);
-    for (int i = 0; i < nwc; i++) {
+    for (int i = 0; i < nblk; i++) {
       double s = v[p.nw * i];
       for (int k = 1; k < p.nw; k++) s -= v[p.nw * i + k];
-      o[i] += alpha * s;
+      o[p.nb * i] += alpha * s;
+      if (p.nb > 1) {
+        double s1 = 0.0;
+        for (int k = 0; k < p.nw; k++) s1 += c1[k] * v[p.nw * i + k];
+        o[p.nb * i + 1] += alpha * s1;
+      }
     }
   }
   void addSparseJacobianTranspose(ParOptScalar alpha, ParOptVec *,
@@ -406,25 +440,44 @@ class SepQuad : public HistoryProblem {
     double *z, *o;
     pzw->getArray(&z);
     out->getArray(&o);
-    for (int i = 0; i < nwc; i++) {
-      o[p.nw * i] += alpha * z[i];
-      for (int k = 1; k < p.nw; k++) o[p.nw * i + k] -= alpha * z[i];
+    for (int i = 0; i < nblk; i++) {
+      o[p.nw * i] += alpha * z[p.nb * i];
+      for (int k = 1; k < p.nw; k++) o[p.nw * i + k] -= alpha * z[p.nb * i];
+      if (p.nb > 1) {
+        for (int k = 0; k < p.nw; k++) o[p.nw * i + k] += alpha * c1[k] * z[p.nb * i + 1];
+      }
     }
   }
   void addSparseInnerProduct(ParOptScalar alpha, ParOptVec *, ParOptVec *cvec,
                              ParOptScalar *A) {
     double *cv;
     cvec->getArray(&cv);
-    for (int i = 0; i < nwc; i++) {
-      double s = 0.0;
-      for (int k = 0; k < p.nw; k++) s += cv[p.nw * i + k];
-      A[i] += alpha * s;
+    if (p.nb == 1) {
+      for (int i = 0; i < nblk; i++) {
+        double s = 0.0;
+        for (int k = 0; k < p.nw; k++) s += cv[p.nw * i + k];
+        A[i] += alpha * s;
+      }
+    } else {
+      for (int i = 0; i < nblk; i++) {
+        double s00 = 0.0, s01 = 0.0, s11 = 0.0;
+        for (int k = 0; k < p.nw; k++) {
+          const double c0 = k == 0 ? 1.0 : -1.0, d = cv[p.nw * i + k];
+          s00 += c0 * c0 * d;
+          s01 += c0 * c1[k] * d;
+          s11 += c1[k] * c1[k] * d;
+        }
+        A[3 * i] += alpha * s00;
+        A[3 * i + 1] += alpha * s01;
+        A[3 * i + 2] += alpha * s11;
+      }
     }
   }
 
   SepQuadParams p;
   long offset;
-  int n, nwc;
+  int n, nwc, nblk;
+  std::vector<double> c1;
   double vtv;
   std::vector<double> lam, b, vh, beta, ytmp;
 };
@@ -570,6 +623,7 @@ int main(int argc, char *argv[]) {
     else if (arg_d(a, "n", &v)) { p.ntotal = (long)v; rosen_n = (int)v; }
     else if (arg_d(a, "ncon", &v)) p.ncon = (int)v;
     else if (arg_d(a, "nw", &v)) p.nw = (int)v;
+    else if (arg_d(a, "nb", &v)) p.nb = (int)v;
     else if (arg_d(a, "seed", &v)) p.seed = (uint64_t)v;
     else if (arg_d(a, "lam_min", &v)) p.lam_min = v;
     else if (arg_d(a, "lam_max", &v)) p.lam_max = v;

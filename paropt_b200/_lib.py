@@ -22,6 +22,12 @@ class Weighting(C.Structure):
                 ("coef_rest", C.c_double), ("wconst", C.c_double)]
 
 
+class BlockWeighting(C.Structure):
+    _fields_ = [("nblocks", C.c_int), ("wstart", C.c_int), ("nw", C.c_int),
+                ("wstride", C.c_int), ("nb", C.c_int), ("coef", c_double_p),
+                ("wconst", c_double_p)]
+
+
 class SepQuadParams(C.Structure):
     _fields_ = [("ntotal", C.c_int64), ("ncon", C.c_int), ("nw", C.c_int),
                 ("seed", C.c_uint64), ("lam_min", C.c_double),
@@ -103,6 +109,7 @@ SIGNATURES = {
     "pcu_vec_dot": (C.c_int, [VP, VP, c_double_p]),
     "pcu_vec_mdot": (C.c_int, [VP, C.POINTER(VP), C.c_int, c_double_p]),
     "pcu_blockmat_create": (VP, [VP, C.c_int, C.POINTER(Weighting)]),
+    "pcu_blockmat_create_blocks": (VP, [VP, C.c_int, C.POINTER(BlockWeighting)]),
     "pcu_blockmat_destroy": (None, [VP]),
     "pcu_blockmat_factor": (C.c_int, [VP, VP, VP, VP]),
     "pcu_blockmat_apply3": (C.c_int, [VP, VP, VP, VP]),

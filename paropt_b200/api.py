@@ -213,8 +213,24 @@ class QuasiDefBlockMat:
     weighting rows of a `weighting` dict (nwcon, wstart, nw, wstride, coef0,
     coef_rest, wconst)."""
 
-    def __init__(self, ctx, nvars, weighting=None):
+    def __init__(self, ctx, nvars, weighting=None, blocks=None):
+        """weighting: nwblock = 1 rows (pcu_weighting).  blocks: the block form with
+        nwblock = nb > 1 -- dict(nblocks, wstart, nw, wstride, coef=[nb][nw] array)
+        (pcu_block_weighting, ParOptSparseMat.cpp:72-111, 196-224)."""
         self.ctx, self.lib = ctx, ctx.lib
+        if blocks is not None:
+            coef = np.ascontiguousarray(blocks["coef"], dtype=np.float64)
+            nb, nw = coef.shape
+            b = _lib.BlockWeighting()
+            b.nblocks, b.wstart, b.nw = int(blocks["nblocks"]), int(blocks.get("wstart", 0)), nw
+            b.wstride, b.nb = int(blocks.get("wstride", nw)), nb
+            b.coef = coef.ctypes.data_as(_lib.c_double_p)
+            b.wconst = None
+            self.nvars, self.nwcon = int(nvars), b.nblocks * nb
+            self.h = self.lib.pcu_blockmat_create_blocks(ctx.h, int(nvars), C.byref(b))
+            if not self.h:
+                raise RuntimeError("paropt_b200: pcu_blockmat_create_blocks failed")
+            return
         w = _lib.Weighting()
         for k, v in (weighting or {}).items():
             setattr(w, k, v)

@@ -137,6 +137,11 @@ class ParOptCudaQuasiDefBlockMat : public ParOptQuasiDefMat {
     mat = pcu_blockmat_create(ctx, nvars, w);
     if (!mat) abort();
   }
+  /* nwblock > 1: groups of nb rows with a dense coefficient matrix */
+  ParOptCudaQuasiDefBlockMat(pcu_ctx *ctx, int nvars, const pcu_block_weighting *b) {
+    mat = pcu_blockmat_create_blocks(ctx, nvars, b);
+    if (!mat) abort();
+  }
   ~ParOptCudaQuasiDefBlockMat() { pcu_blockmat_destroy(mat); }
   int factor(ParOptVec *x, ParOptVec *Dinv, ParOptVec *Cdiag) {
     return pcu_blockmat_factor(mat, ParOptCudaVec::handle(x), ParOptCudaVec::handle(Dinv),

@@ -96,6 +96,53 @@ def test_blockmat_reports_zero_pivot(ctx):
         o.free()
 
 
+@pytest.mark.parametrize("nb,nw,nblocks,start,skip", [(2, 8, 4099, 0, 0), (3, 5, 1001, 2, 1),
+                                                      (4, 4, 513, 0, 3), (8, 16, 257, 5, 0),
+                                                      (1, 6, 100, 0, 0)])
+def test_blockmat_with_nwblock_greater_than_one(ctx, nb, nw, nblocks, start, skip):
+    """pcu_blockmat_create_blocks: ParOptQuasiDefBlockMat with nwblock = nb
+    (ParOptSparseMat.cpp:72-111 packed-upper dpptrf, :196-224 dpptrs), dense nb x nb blocks
+    of Ew = Cdiag + Aw Dinv Aw^T, against the oracle's per-block Cholesky; a block that is
+    not positive definite is reported with its row."""
+    from oracle.ip_oracle import BlockMatNB, BlockWeighting
+    from paropt_b200.api import PVec, QuasiDefBlockMat
+    rng = np.random.default_rng(100 * nb + nw)
+    stride = nw + skip
+    nvars = start + nblocks * stride + 3
+    coef = rng.standard_normal((nb, nw))
+    w = BlockWeighting(nblocks, coef, start=start, stride=stride)
+    Dinv = 0.1 + rng.random(nvars)
+    Cd = 0.05 + rng.random(w.nwcon)
+    bx, bw = rng.standard_normal(nvars), rng.standard_normal(w.nwcon)
+    ref = BlockMatNB(w, nvars)
+    assert ref.factor(Dinv, Cd) == 0
+    mat = QuasiDefBlockMat(ctx, nvars, blocks=dict(nblocks=nblocks, wstart=start, wstride=stride,
+                                                    coef=coef))
+    dD, dC = vec(ctx, Dinv), vec(ctx, Cd)
+    assert mat.factor(None, dD, dC) == 0
+    dbx, dbw = vec(ctx, bx), vec(ctx, bw)
+    yx, yw = PVec(ctx, nvars), PVec(ctx, w.nwcon)
+    mat.apply(dbx, dbw, yx, yw)
+    rx, rw = ref.apply(bx, bw)
+    assert relerr(rx, yx.to_numpy()) <= 1e-12 and relerr(rw, yw.to_numpy()) <= 1e-12
+    mat.apply(dbx, yx, yw)
+    rx, rw = ref.apply(bx)
+    assert relerr(rx, yx.to_numpy()) <= 1e-12 and relerr(rw, yw.to_numpy()) <= 1e-12
+    # inputs unmodified
+    assert np.array_equal(dbx.to_numpy(), bx) and np.array_equal(dbw.to_numpy(), bw)
+    # an indefinite block: its first failing row (1-based) comes back
+    if nb > 1:
+        Cbad = Cd.copy()
+        blk = nblocks // 2
+        Cbad[blk * nb: (blk + 1) * nb] = -1e6
+        dCb = vec(ctx, Cbad)
+        rc = mat.factor(None, dD, dCb)
+        assert blk * nb < rc <= (blk + 1) * nb, rc
+        dCb.free()
+    for o in (dD, dC, dbx, dbw, yx, yw, mat):
+        o.free()
+
+
 @pytest.mark.parametrize("kind,n,m,updates", [("bfgs", 5003, 4, 9), ("bfgs", 70001, 10, 14),
                                                ("sr1", 4099, 5, 7)])
 def test_quasi_newton_object(ctx, kind, n, m, updates):

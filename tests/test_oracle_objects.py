@@ -54,3 +54,32 @@ def test_compact_quasi_newton_matches_the_dense_formula(cls, m):
         if cls is LBFGS and len(Z):
             # the pairs satisfy the secant condition of the most recent update
             assert np.allclose(B @ s, y, rtol=1e-8, atol=1e-8)
+
+
+def test_block_form_of_the_block_matrix_against_dense_formulas():
+    """BlockMatNB (nwblock = nb > 1, ParOptSparseMat.cpp:72-111, 196-224): the solution
+    of [[D, Aw^T], [Aw, -C]] [yx; -yw] = [bx; bw] against a dense solve."""
+    from oracle.ip_oracle import BlockMatNB, BlockWeighting
+    rng = np.random.default_rng(5)
+    nb, nw, nblocks, extra = 3, 5, 7, 4
+    n = nblocks * (nw + 1) + extra
+    coef = rng.standard_normal((nb, nw))
+    w = BlockWeighting(nblocks, coef, start=2, stride=nw + 1)
+    Dinv = 0.2 + rng.random(n)
+    C = 0.1 + rng.random(w.nwcon)
+    bx, bw = rng.standard_normal(n), rng.standard_normal(w.nwcon)
+    mat = BlockMatNB(w, n)
+    assert mat.factor(Dinv, C) == 0
+    yx, yw = mat.apply(bx, bw)
+    Aw = np.zeros((w.nwcon, n))
+    for b in range(nblocks):
+        for r in range(nb):
+            Aw[b * nb + r, w.idx[b]] = coef[r]
+    K = np.block([[np.diag(1.0 / Dinv), Aw.T], [Aw, -np.diag(C)]])
+    sol = np.linalg.solve(K, np.concatenate([bx, bw]))
+    assert np.allclose(yx, sol[:n], rtol=1e-11, atol=1e-12)
+    assert np.allclose(yw, -sol[n:], rtol=1e-11, atol=1e-12)
+    yx3, yw3 = mat.apply(bx)
+    sol3 = np.linalg.solve(K, np.concatenate([bx, np.zeros(w.nwcon)]))
+    assert np.allclose(yx3, sol3[:n], rtol=1e-11, atol=1e-12)
+    assert np.allclose(yw3, -sol3[n:], rtol=1e-11, atol=1e-12)
