@@ -323,6 +323,33 @@ int pcu_ip_counters(pcu_ip *ip, int *niter, int *neval, int *ngeval);
    3 "could not be improved" (the three messages at IP.cpp:4815-4830).         */
 int pcu_ip_status(pcu_ip *ip);
 
+/* -------------------------------------------------- trust-region front end
+   ParOptTrustRegion with the SL1QP penalty method and the adaptive penalty update
+   (src/ParOptTrustRegion.cpp:1454-1690) over ParOptQuadraticSubproblem /
+   ParOptInfeasSubproblem model problems that live on the device (TR.cpp:27-660) --
+   what ParOptOptimizer runs for algorithm = "tr" (src/ParOptOptimizer.cpp:102-175).
+   Options: the tr_* names of ParOptTrustRegion::addDefaultOptions (TR.cpp:739-845),
+   the qn_* names, and every interior-point option (forwarded to the subproblem
+   optimizer).  Not built: tr_accept_step_strategy = filter_method, tr_use_soc.     */
+typedef struct pcu_tr pcu_tr;
+pcu_tr *pcu_tr_create(pcu_problem *prob);
+void pcu_tr_destroy(pcu_tr *tr);
+int pcu_tr_set_option_float(pcu_tr *tr, const char *name, double value);
+int pcu_tr_set_option_int(pcu_tr *tr, const char *name, int value);
+int pcu_tr_set_option_str(pcu_tr *tr, const char *name, const char *value);
+int pcu_tr_optimize(pcu_tr *tr);                 /* TR.cpp:2367 optimize            */
+int pcu_tr_status(pcu_tr *tr);                   /* 1: converged (TR.cpp:1603-1608) */
+/* One record per trust-region iteration, the columns of the reference's log row
+   (TR.cpp:1433-1445) at full precision plus checksums of the centre x_k:
+   iter fobj infeas l1 linfty |x-xk| tr rho model_red zav zmax gav gmax
+   subproblem_iters adaptive_iters accepted xsum xnorm xmaxabs (19 doubles).        */
+int pcu_tr_history_len(pcu_tr *tr);
+int pcu_tr_history_get(pcu_tr *tr, int k, double *out19);
+const char *pcu_tr_history_info(pcu_tr *tr, int k);
+pcu_vec *pcu_tr_point(pcu_tr *tr);               /* getOptimizedPoint TR.cpp:888    */
+pcu_ip *pcu_tr_interior_point(pcu_tr *tr);       /* the subproblem optimizer        */
+int pcu_tr_penalty_gamma(pcu_tr *tr, double *gamma);   /* getPenaltyGamma TR.cpp:1076 */
+
 /* Per-iteration history at the point of the reference's writeOutput hook
    (IP.cpp:4620-4631): one record per major iteration, PCU_HIST_FIELDS doubles
    followed by 6*ncon doubles (c, z, s, t, zs, zt).  Field order:

@@ -9,7 +9,8 @@ takes a `Context` (one per GPU / rank); `ParOpt.Problem(None, ...)` opens GPU 0.
     opt = ParOpt.Optimizer(problem, {"algorithm": "ip", "qn_type": "bfgs"})
     opt.optimize(); x, z, zw, zl, zu = opt.getOptimizedPoint()
 
-Only `algorithm = "ip"` is built (trust-region and MMA front ends: SURVEY.md 8f-1).
+`algorithm = "ip"` and `algorithm = "tr"` (SL1QP trust region, penalty method) are built;
+the MMA front end is not.
 """
 import numpy as np
 
@@ -86,27 +87,42 @@ class LSR1(api.QuasiNewton):
         super().__init__(problem.ctx, problem.nvars, "sr1", subspace)
 
 
+class TrustRegion(api.TrustRegion):
+    """ParOpt.TrustRegion (ParOptTrustRegion.h) over the built-in quadratic subproblem."""
+
+
 class Optimizer:
-    """ParOpt.Optimizer (ParOptOptimizer.cpp:27-175) for algorithm = "ip"."""
+    """ParOpt.Optimizer (ParOptOptimizer.cpp:27-175): algorithm = "ip" runs the
+    interior-point optimizer on the problem, algorithm = "tr" the trust-region front
+    end (quadratic model with the compact quasi-Newton Hessian of the qn_* options,
+    ParOptOptimizer.cpp:102-175).  The reference's default is "tr"
+    (ParOptOptimizer.cpp:41)."""
 
     def __init__(self, problem, options=None):
         self.problem = problem
         self.options = dict(options or {})
-        algorithm = self.options.pop("algorithm", "ip")
-        if algorithm != "ip":
-            raise ValueError("algorithm=%r is not built (only 'ip': SURVEY.md section 8f)" % algorithm)
+        self.algorithm = self.options.pop("algorithm", "tr")
+        if self.algorithm not in ("ip", "tr"):
+            raise ValueError("algorithm=%r is not built ('ip' and 'tr' are)" % self.algorithm)
         self.ip = None
+        self.tr = None
 
     def optimize(self):
-        if self.ip is None:
-            self.ip = InteriorPoint(self.problem, self.options)
-        self.ip.optimize()
+        if self.algorithm == "ip":
+            if self.ip is None:
+                self.ip = InteriorPoint(self.problem, self.options)
+            self.ip.optimize()
+        else:
+            if self.tr is None:
+                self.tr = TrustRegion(self.problem, self.options)
+            self.tr.optimize()
 
     def getOptimizedPoint(self):
-        return self.ip.getOptimizedPoint()
+        return (self.ip if self.algorithm == "ip" else self.tr).getOptimizedPoint()
 
     def setTrustRegionSubproblem(self, subproblem):
-        raise NotImplementedError("trust-region front end is not built")
+        raise NotImplementedError("user-defined trust-region subproblems are not built; the "
+                                  "quadratic subproblem of ParOptOptimizer is")
 
 
 def unpack_output(filename):

@@ -168,6 +168,19 @@ SIGNATURES = {
     "pcu_ip_complementarity": (C.c_int, [VP, c_double_p]),
     "pcu_ip_counters": (C.c_int, [VP, c_int_p, c_int_p, c_int_p]),
     "pcu_ip_status": (C.c_int, [VP]),
+    "pcu_tr_create": (VP, [VP]),
+    "pcu_tr_destroy": (None, [VP]),
+    "pcu_tr_set_option_float": (C.c_int, [VP, C.c_char_p, C.c_double]),
+    "pcu_tr_set_option_int": (C.c_int, [VP, C.c_char_p, C.c_int]),
+    "pcu_tr_set_option_str": (C.c_int, [VP, C.c_char_p, C.c_char_p]),
+    "pcu_tr_optimize": (C.c_int, [VP]),
+    "pcu_tr_status": (C.c_int, [VP]),
+    "pcu_tr_history_len": (C.c_int, [VP]),
+    "pcu_tr_history_get": (C.c_int, [VP, C.c_int, c_double_p]),
+    "pcu_tr_history_info": (C.c_char_p, [VP, C.c_int]),
+    "pcu_tr_point": (VP, [VP]),
+    "pcu_tr_interior_point": (VP, [VP]),
+    "pcu_tr_penalty_gamma": (C.c_int, [VP, c_double_p]),
     "pcu_ip_history_len": (C.c_int, [VP]),
     "pcu_ip_history_get": (C.c_int, [VP, C.c_int, c_double_p, C.c_int]),
     "pcu_ip_history_info": (C.c_char_p, [VP, C.c_int]),

@@ -649,3 +649,77 @@ class InteriorPoint:
         if self.h:
             self.lib.pcu_ip_destroy(self.h)
             self.h = None
+
+
+TR_FIELDS = ("iter", "fobj", "infeas", "l1", "linfty", "dx", "tr", "rho", "model_red", "zav",
+             "zmax", "gav", "gmax", "subproblem_iters", "adaptive_iters", "accepted", "xsum",
+             "xnorm", "xmaxabs")
+
+
+class TrustRegion:
+    """ParOptTrustRegion + ParOptQuadraticSubproblem on the device (pcu_tr): the SL1QP
+    penalty method with the adaptive penalty update (ParOptTrustRegion.cpp:1454-1690);
+    what ParOpt.Optimizer runs for algorithm = "tr"."""
+
+    def __init__(self, problem, options=None):
+        self.prob = problem
+        self.ctx = problem.ctx
+        self.lib = self.ctx.lib
+        self.h = self.lib.pcu_tr_create(problem.h)
+        if not self.h:
+            raise RuntimeError("paropt_b200: trust-region creation failed")
+        self.ncon = problem.ncon
+        for k, v in (options or {}).items():
+            self.setOption(k, v)
+
+    def setOption(self, name, value):
+        key = name.encode()
+        if isinstance(value, bool):
+            rc = self.lib.pcu_tr_set_option_int(self.h, key, int(value))
+        elif isinstance(value, int):
+            rc = self.lib.pcu_tr_set_option_int(self.h, key, value)
+        elif isinstance(value, float):
+            rc = self.lib.pcu_tr_set_option_float(self.h, key, value)
+        else:
+            rc = self.lib.pcu_tr_set_option_str(self.h, key, str(value).encode())
+        if rc != 0:
+            raise ValueError("option %s=%r is not available" % (name, value))
+
+    def optimize(self):
+        _check(self.lib.pcu_tr_optimize(self.h), "trust-region optimize")
+
+    def converged(self):
+        return int(self.lib.pcu_tr_status(self.h)) == 1
+
+    def history(self):
+        out = []
+        buf = np.zeros(len(TR_FIELDS))
+        for k in range(int(self.lib.pcu_tr_history_len(self.h))):
+            _check(self.lib.pcu_tr_history_get(self.h, k, buf.ctypes.data_as(_lib.c_double_p)),
+                   "tr history")
+            rec = {name: float(buf[i]) for i, name in enumerate(TR_FIELDS)}
+            for name in ("iter", "subproblem_iters", "adaptive_iters", "accepted"):
+                rec[name] = int(rec[name])
+            rec["info"] = self.lib.pcu_tr_history_info(self.h, k).decode()
+            out.append(rec)
+        return out
+
+    def getOptimizedPoint(self):
+        """x (the centre), z, zw, zl, zu of the last subproblem solve
+        (ParOptOptimizer::getOptimizedPoint, ParOptOptimizer.cpp:231-262)."""
+        x = PVec(self.ctx, handle=self.lib.pcu_tr_point(self.h))
+        ip = InteriorPoint.__new__(InteriorPoint)
+        ip.prob, ip.ctx, ip.lib, ip.ncon = self.prob, self.ctx, self.lib, self.ncon
+        ip.h = self.lib.pcu_tr_interior_point(self.h)
+        _, z, zw, zl, zu = ip.getOptimizedPoint()
+        return x, z, zw, zl, zu
+
+    def getPenaltyGamma(self):
+        g = np.zeros(max(self.ncon, 1))
+        self.lib.pcu_tr_penalty_gamma(self.h, g.ctypes.data_as(_lib.c_double_p))
+        return g[:self.ncon]
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_tr_destroy(self.h)
+            self.h = None

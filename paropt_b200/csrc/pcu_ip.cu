@@ -460,6 +460,7 @@ IPConst pcu_ip::kconst() const {
   k.gamma = opt.penalty_gamma;
   k.dp = opt.design_precision;
   k.wconst = wd.wconst;
+  k.wc = prob->wconst_vec ? prob->wconst_vec->d : nullptr;
   k.use_lower = prob->use_lower;
   k.use_upper = prob->use_upper;
   k.nwineq = prob->nwinequality;

@@ -50,10 +50,17 @@ struct IPConst {
                   // equalities and 0 for sparse inequalities (IP.cpp:357-374)
   double dp;      // design_precision
   double wconst;  // constant term of cw(x)
+  // per-constraint constant terms (null: wconst for every row).  The trust-region
+  // subproblem's sparse constraints are cw(x_k) + Aw p (ParOptTrustRegion.cpp:318-321):
+  // the same rows, a different constant each.
+  const double *wc;
   int use_lower, use_upper;
   int nwineq;     // local number of sparse inequalities
 };
 
+__device__ __forceinline__ double wconst_at(const IPConst &k, long long ci) {
+  return k.wc ? k.wc[ci] : k.wconst;
+}
 __device__ __forceinline__ double gamma_sw(const IPConst &k, long long ci) {
   return ci < k.nwineq ? 0.0 : k.gamma;
 }
@@ -247,7 +254,7 @@ struct ResFT : NoStreams {
     const double zw = src.ldw(W_ZW, v.zw, ci), sw = src.ldw(W_SW, v.sw, ci), tw = src.ldw(W_TW, v.tw, ci);
     const double zsw = src.ldw(W_ZSW, v.zsw, ci), ztw = src.ldw(W_ZTW, v.ztw, ci);
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
-    double rzw = -(((k.wconst + sum[0]) - sw) + tw);
+    double rzw = -(((wconst_at(k, ci) + sum[0]) - sw) + tw);
     double rsw = (zsw - gsw) - zw;
     double rtw = (ztw - gtw) + zw;
     const double asw = sw * zsw, atw = tw * ztw;
@@ -567,7 +574,7 @@ struct DiagRhsF : NoStreams {
     const double tw = src.ldw(W_TW, v.tw, ci);
     const double zsw = src.ldw(W_ZSW, v.zsw, ci), ztw = src.ldw(W_ZTW, v.ztw, ci);
     Cw[ci] = pcu_rcp((pcu_div(sw, zsw) + pcu_div(tw, ztw)) + sum[0]);
-    const double bzw = -(((k.wconst + sum[1]) - sw) + tw);
+    const double bzw = -(((wconst_at(k, ci) + sum[1]) - sw) + tw);
     const double bsw = (zsw - gamma_sw(k, ci)) - zw;
     const double btw = (ztw - k.gamma) + zw;
     const double bzsw = mu - sw * zsw;
@@ -924,7 +931,7 @@ __device__ __forceinline__ void stats_constraint_vals(
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
     acc.s[18] += gsw * sw + gtw * tw;
     acc.s[19] += gsw * psw + gtw * ptw;
-    const double rw1 = ((k.wconst + sum[0]) - sw) + tw;
+    const double rw1 = ((wconst_at(k, ci) + sum[0]) - sw) + tw;
     const double rw2 = (sum[1] - psw) + ptw;
     acc.s[20] = fma(rw1, rw1, acc.s[20]);
     acc.s[21] = fma(rw1, rw2, acc.s[21]);
@@ -1282,7 +1289,7 @@ struct TrialF : NoStreams {
     rtw[ci] = t;
     lp_mul(acc.s[2], acc.s[3], s * t);
     acc.s[4] += gamma_sw(k, ci) * s + k.gamma * t;
-    const double rw = ((k.wconst + sum[0]) - s) + t;
+    const double rw = ((wconst_at(k, ci) + sum[0]) - s) + t;
     acc.s[5] = fma(rw, rw, acc.s[5]);
   }
   template <int W, class S, class AT>
@@ -1392,7 +1399,7 @@ struct Update1FT : NoStreams {
     v.ztw[ci] = ztw;
     if (STATS) {  // ResF::B at the new point
       const double gsw = gamma_sw(k, ci), gtw = k.gamma;
-      const double rzw = -(((k.wconst + sum[0]) - sw) + tw);
+      const double rzw = -(((wconst_at(k, ci) + sum[0]) - sw) + tw);
       const double rsw = (zsw - gsw) - zwn;
       const double rtw = (ztw - gtw) + zwn;
       const double asw = sw * zsw, atw = tw * ztw;
@@ -1895,7 +1902,7 @@ struct Pass2RF : NoStreams {
     const double pzw = y.zw[ci], psw = y.sw[ci], ptw = y.tw[ci];
     const double pzsw = y.zsw[ci], pztw = y.ztw[ci];
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
-    b.zw[ci] = -(((k.wconst + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
+    b.zw[ci] = -(((wconst_at(k, ci) + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
     b.sw[ci] = ((zsw - gsw) - zw) + (pzsw - pzw);
     b.tw[ci] = ((ztw - gtw) + zw) + (pztw + pzw);
     b.zsw[ci] = (mu - sw * zsw) - (psw * zsw + sw * pzsw);
@@ -2170,7 +2177,7 @@ struct Pass2R1F : NoStreams {
     const double pzw = con.pzw, psw = con.psw, ptw = con.ptw;
     const double pzsw = con.pzsw, pztw = con.pztw;
     const double gsw = gamma_sw(k, ci), gtw = k.gamma;
-    const double bzw = -(((k.wconst + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
+    const double bzw = -(((wconst_at(k, ci) + sum2[0]) - sw) + tw) + ((psw - sum2[1]) - ptw);
     const double bsw = ((zsw - gsw) - zw) + (pzsw - pzw);
     const double btw = ((ztw - gtw) + zw) + (pztw + pzw);
     const double bzsw = (mu - sw * zsw) - (psw * zsw + sw * pzsw);
@@ -2294,7 +2301,7 @@ struct Pass1VF : NoStreams {
                                     Con &con, AccT &) const {
     const double zw = v.zw[ci], sw = v.sw[ci], tw = v.tw[ci];
     const double zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double bzw = -(((k.wconst + sum[1]) - sw) + tw);
+    const double bzw = -(((wconst_at(k, ci) + sum[1]) - sw) + tw);
     const double bsw = (zsw - gamma_sw(k, ci)) - zw;
     const double btw = (ztw - k.gamma) + zw;
     const double bzsw = mu - sw * zsw;

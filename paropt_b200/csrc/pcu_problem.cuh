@@ -11,6 +11,8 @@ struct pcu_problem {
   int ninequality = 0, nwinequality = 0;
   int use_lower = 1, use_upper = 1;
   pcu_weighting weighting;
+  // per-constraint constants of the weighting rows (W-sized), or null: weighting.wconst
+  pcu_vec *wconst_vec = nullptr;
   double callback_ms = 0.0;  // device time inside the callbacks
   cudaEvent_t cb0 = nullptr, cb1 = nullptr;
   bool time_callbacks = true;

@@ -51,7 +51,7 @@ def test_optimizer_facade_matches_oracle(tmp_path):
     k = min(len(cols[7]), len(hist)) - 1
     assert abs(cols[7][k] - hist[k]["fobj"]) <= 1e-5 * max(1.0, abs(hist[k]["fobj"]))
     with pytest.raises(ValueError):
-        ParOpt.Optimizer(prob, {"algorithm": "tr"})
+        ParOpt.Optimizer(prob, {"algorithm": "mma"})
 
 
 def test_pvec_array_protocols():
