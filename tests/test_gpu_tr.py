@@ -58,8 +58,14 @@ def test_trust_region_history_matches_reference(ctx, name):
             assert err <= CENTRE_RTOL, (k, key, h[key], c[key], err)
         # the log row prints 3 significant digits (%12.5e for fobj)
         assert abs(h["fobj"] - row["fobj"]) <= 2e-5 * max(abs(row["fobj"]), 1e-300), (k, "fobj")
+        # rho = actual / predicted reduction and the predicted reduction itself are
+        # differences of objective values: below ~1e-11 |f| they are round-off (the
+        # last rows of C1_tr: model_red = 1.4e-10 at f = 987) and are not compared
+        noise = abs(row["model_red"]) <= 1e-11 * max(1.0, abs(row["fobj"]))
         for key in ("infeas", "l1", "linfty", "dx", "tr", "rho", "model_red", "zav", "zmax",
                     "gav", "gmax"):
+            if noise and key in ("rho", "model_red"):
+                continue
             ref = row[key]
             assert abs(h[key] - ref) <= 6e-3 * abs(ref) + 1e-12, (k, key, h[key], ref)
     final = gold["final"]
