@@ -310,6 +310,15 @@ int pcu_ip_get_penalty_gamma(pcu_ip *ip, double *gamma_t);   /* penalty_gamma_t,
 int pcu_ip_reset_problem(pcu_ip *ip, pcu_problem *prob);
 /* resetQuasiNewtonHessian (IP.cpp:1241).                                        */
 int pcu_ip_reset_quasi_newton(pcu_ip *ip);
+/* writeSolutionFile / readSolutionFile (IP.cpp:883-975, 986-1104): the reference's
+   binary checkpoint, byte for byte -- int[3] {global nvars, global nwcon, ncon},
+   barrier, s, t, z, zs, zt (ncon doubles each), then x, zl, zu (global nvars each) and
+   zw, sw (global nwcon each) in rank order; every rank writes / reads its own slice.
+   The option "ip_checkpoint_file" makes optimize() write it at every
+   write_output_frequency-th iteration (IP.cpp:4621-4629).  1 on failure (a size
+   mismatch prints the reference's message).                                      */
+int pcu_ip_write_solution(pcu_ip *ip, const char *filename);
+int pcu_ip_read_solution(pcu_ip *ip, const char *filename);
 /* getOptimizedPoint / getOptimizedSlacks (IP.h:156-163): device vectors owned
    by the optimizer plus host copies of the dense parts.                       */
 int pcu_ip_get_point(pcu_ip *ip, pcu_vec **x, pcu_vec **zw, pcu_vec **zl,

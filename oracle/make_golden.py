@@ -186,6 +186,25 @@ def main():
             json.dump(data, fp, separators=(",", ":"))
         print("C4_full.json", "niter", data["final"]["niter"], data["status"], flush=True)
         return
+    if "--checkpoint" in sys.argv:
+        # the reference's binary checkpoint (writeSolutionFile, IP.cpp:883-975) of the final
+        # state of a small C3 run: the byte layout the CUDA reader / writer must honour
+        cfg = configs.get("C3", 256)
+        cfg["options"] = dict(cfg["options"], max_major_iters=20)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", PCU_SHIM_NP="1")
+        with tempfile.TemporaryDirectory() as tmp:
+            hist = os.path.join(tmp, "hist.jsonl")
+            out = os.path.join(out_dir, "C3_ckpt.bin")
+            cmd = [DRIVER] + driver_args(cfg) + ["hist=" + hist, "log=/dev/null", "checkpoint=" + out]
+            subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
+            recs = [json.loads(line) for line in open(hist)]
+        data = {"config": cfg, "history": [r for r in recs if "iter" in r],
+                "final": [r for r in recs if "final" in r][0],
+                "generator": "oracle/make_golden.py --checkpoint (unmodified reference, writeSolutionFile)"}
+        with open(os.path.join(out_dir, "C3_ckpt.json"), "w") as fp:
+            json.dump(data, fp, separators=(",", ":"))
+        print("C3_ckpt.bin", os.path.getsize(out), "bytes; niter", data["final"]["niter"])
+        return
     if "--nb2" in sys.argv:
         # ParOptQuasiDefBlockMat with nwblock = 2 (dense 2 x 2 blocks of Ew, dpptrf /
         # dpptrs): C3-style workload whose blocks carry two sparse constraints

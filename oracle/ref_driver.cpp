@@ -607,7 +607,7 @@ int main(int argc, char *argv[]) {
 
   std::string problem = "sepquad", hist_path, out_path = "/dev/null";
   std::string algorithm = "ip", tr_log = "/dev/null";
-  std::string dump_x;
+  std::string dump_x, checkpoint;
   SepQuadParams p;
   std::vector<std::pair<std::string, std::string> > opts;
   int rosen_n = 1000;
@@ -618,6 +618,7 @@ int main(int argc, char *argv[]) {
     else if (strncmp(a, "hist=", 5) == 0) hist_path = a + 5;
     else if (strncmp(a, "log=", 4) == 0) out_path = a + 4;
     else if (strncmp(a, "dump_x=", 7) == 0) dump_x = a + 7;
+    else if (strncmp(a, "checkpoint=", 11) == 0) checkpoint = a + 11;
     else if (strncmp(a, "algorithm=", 10) == 0) algorithm = a + 10;
     else if (strncmp(a, "tr_log=", 7) == 0) tr_log = a + 7;
     else if (arg_d(a, "n", &v)) { p.ntotal = (long)v; rosen_n = (int)v; }
@@ -750,6 +751,9 @@ int main(int argc, char *argv[]) {
   double t0 = MPI_Wtime();
   int fail = ip->optimize();
   double t1 = MPI_Wtime();
+
+  // the reference's own binary checkpoint of the final state (IP.cpp:883-975)
+  if (!checkpoint.empty()) ip->writeSolutionFile(checkpoint.c_str());
 
   int niter, neval, ngeval;
   ip->getIterationCounters(&niter, &neval, &ngeval);

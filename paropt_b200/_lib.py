@@ -135,6 +135,8 @@ SIGNATURES = {
     "pcu_ip_get_penalty_gamma": (C.c_int, [VP, c_double_p]),
     "pcu_ip_reset_problem": (C.c_int, [VP, VP]),
     "pcu_ip_reset_quasi_newton": (C.c_int, [VP]),
+    "pcu_ip_write_solution": (C.c_int, [VP, C.c_char_p]),
+    "pcu_ip_read_solution": (C.c_int, [VP, C.c_char_p]),
     "pcu_vec_to_host": (C.c_int, [VP, VP, C.c_int]),
     "pcu_vec_from_host": (C.c_int, [VP, VP, C.c_int]),
     "pcu_problem_create": (VP, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -553,6 +553,14 @@ class InteriorPoint:
         _check(self.lib.pcu_ip_reset_problem(self.h, problem.h), "resetProblemInstance")
         self.prob = problem
 
+    def writeSolutionFile(self, filename):
+        """ParOptInteriorPoint::writeSolutionFile (IP.cpp:883): the reference's binary layout."""
+        return int(self.lib.pcu_ip_write_solution(self.h, str(filename).encode()))
+
+    def readSolutionFile(self, filename):
+        """ParOptInteriorPoint::readSolutionFile (IP.cpp:986)."""
+        return int(self.lib.pcu_ip_read_solution(self.h, str(filename).encode()))
+
     def resetQuasiNewtonHessian(self):
         _check(self.lib.pcu_ip_reset_quasi_newton(self.h), "resetQuasiNewtonHessian")
 

@@ -2,9 +2,12 @@
 // (include/paropt_b200.h).  Context / vector / problem entry points live next to
 // their implementations (pcu_vec.cu, pcu_problems.cu).
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "pcu_ip.cuh"
 
@@ -66,6 +69,7 @@ const OptEntry OPTIONS[] = {
     OPT_S(starting_point_strategy,
           "least_squares_multipliers|affine_step|no_start_strategy"),
     OPT_S(output_file, nullptr),
+    OPT_S(ip_checkpoint_file, nullptr),
     OPT_S(problem_name, nullptr),
 };
 
@@ -240,6 +244,112 @@ int pcu_ip_reset_quasi_newton(pcu_ip *ip) {
   if (!ip) return 1;
   if (ip->qn) ip->qn->reset();
   return 0;
+}
+
+// ------------------------------------------------------------- checkpoint file
+// Global offsets of this rank's slices (var_range / wcon_range, IP.cpp:214-229)
+static int checkpoint_ranges(pcu_ip *ip, long long *n0, long long *ntot, long long *w0,
+                             long long *wtot) {
+  pcu_ctx *ctx = ip->ctx;
+  std::vector<double> sizes(2 * (size_t)ctx->world, 0.0);
+  sizes[2 * ctx->rank] = ip->nvars;
+  sizes[2 * ctx->rank + 1] = ip->nwcon;
+  if (pcu_ctx_allreduce_sum(ctx, sizes.data(), (int)sizes.size())) return 1;
+  *n0 = *w0 = *ntot = *wtot = 0;
+  for (int r = 0; r < ctx->world; r++) {
+    if (r < ctx->rank) {
+      *n0 += (long long)sizes[2 * r];
+      *w0 += (long long)sizes[2 * r + 1];
+    }
+    *ntot += (long long)sizes[2 * r];
+    *wtot += (long long)sizes[2 * r + 1];
+  }
+  return 0;
+}
+
+int pcu_ip_write_solution(pcu_ip *ip, const char *filename) {
+  if (!ip || !filename) return 1;
+  pcu_ctx *ctx = ip->ctx;
+  long long n0, ntot, w0, wtot;
+  if (checkpoint_ranges(ip, &n0, &ntot, &w0, &wtot)) return 1;
+  const int c = ip->ncon;
+  Vars &v = ip->variables;
+  if (ctx->rank == 0) {  // header + dense parts (IP.cpp:902-917), file truncated
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) return 1;
+    const int sizes[3] = {(int)ntot, (int)wtot, c};
+    fwrite(sizes, sizeof(int), 3, fp);
+    fwrite(&ip->barrier_param, sizeof(double), 1, fp);
+    const std::vector<double> *parts[5] = {&v.s, &v.t, &v.z, &v.zs, &v.zt};
+    for (auto p : parts) fwrite(p->data(), sizeof(double), c, fp);
+    fclose(fp);
+  }
+  double flag = 1.0;  // the other ranks write after the file exists
+  if (pcu_ctx_allreduce_sum(ctx, &flag, 1)) return 1;
+  FILE *fp = fopen(filename, "r+b");
+  if (!fp) return 1;
+  const long long base = 3 * (long long)sizeof(int) + (5LL * c + 1) * (long long)sizeof(double);
+  std::vector<double> host((size_t)std::max(ip->nvars, ip->nwcon) + 1);
+  int fail = 0;
+  auto put = [&](pcu_vec *vec, long long off_elems, int count) {
+    if (count == 0) return;
+    if (pcu_vec_to_host(vec, host.data(), count)) fail = 1;
+    if (fseeko(fp, (off_t)(base + off_elems * (long long)sizeof(double)), SEEK_SET) != 0) fail = 1;
+    if (fwrite(host.data(), sizeof(double), count, fp) != (size_t)count) fail = 1;
+  };
+  put(v.v[PCU_X], n0, ip->nvars);
+  put(v.v[PCU_ZL], ntot + n0, ip->nvars);
+  put(v.v[PCU_ZU], 2 * ntot + n0, ip->nvars);
+  if (wtot > 0) {
+    put(v.v[PCU_ZW], 3 * ntot + w0, ip->nwcon);
+    put(v.v[PCU_SW], 3 * ntot + wtot + w0, ip->nwcon);
+  }
+  fclose(fp);
+  flag = fail;
+  if (pcu_ctx_allreduce_sum(ctx, &flag, 1)) return 1;
+  return flag != 0.0;
+}
+
+int pcu_ip_read_solution(pcu_ip *ip, const char *filename) {
+  if (!ip || !filename) return 1;
+  long long n0, ntot, w0, wtot;
+  if (checkpoint_ranges(ip, &n0, &ntot, &w0, &wtot)) return 1;
+  FILE *fp = fopen(filename, "rb");
+  if (!fp) return 1;
+  const int c = ip->ncon;
+  Vars &v = ip->variables;
+  int sizes[3] = {0, 0, 0};
+  if (fread(sizes, sizeof(int), 3, fp) != 3 || sizes[0] != (int)ntot || sizes[1] != (int)wtot ||
+      sizes[2] != c) {
+    if (ip->ctx->rank == 0)
+      fprintf(stderr, "ParOpt: Problem size incompatible with solution file\n");
+    fclose(fp);
+    return 1;
+  }
+  int fail = 0;
+  // every rank reads the replicated dense parts itself (root + Bcast in the reference)
+  if (fread(&ip->barrier_param, sizeof(double), 1, fp) != 1) fail = 1;
+  std::vector<double> *parts[5] = {&v.s, &v.t, &v.z, &v.zs, &v.zt};
+  for (auto p : parts)
+    if (c > 0 && fread(p->data(), sizeof(double), c, fp) != (size_t)c) fail = 1;
+  const long long base = 3 * (long long)sizeof(int) + (5LL * c + 1) * (long long)sizeof(double);
+  std::vector<double> host((size_t)std::max(ip->nvars, ip->nwcon) + 1);
+  auto get = [&](pcu_vec *vec, long long off_elems, int count) {
+    if (count == 0) return;
+    if (fseeko(fp, (off_t)(base + off_elems * (long long)sizeof(double)), SEEK_SET) != 0) fail = 1;
+    if (fread(host.data(), sizeof(double), count, fp) != (size_t)count) fail = 1;
+    if (pcu_vec_from_host(vec, host.data(), count)) fail = 1;
+  };
+  get(v.v[PCU_X], n0, ip->nvars);
+  get(v.v[PCU_ZL], ntot + n0, ip->nvars);
+  get(v.v[PCU_ZU], 2 * ntot + n0, ip->nvars);
+  if (wtot > 0) {
+    get(v.v[PCU_ZW], 3 * ntot + w0, ip->nwcon);
+    get(v.v[PCU_SW], 3 * ntot + wtot + w0, ip->nwcon);
+  }
+  fclose(fp);
+  ip->upd_stats_valid = 0;
+  return fail;
 }
 
 int pcu_ip_get_point(pcu_ip *ip, pcu_vec **x, pcu_vec **zw, pcu_vec **zl,

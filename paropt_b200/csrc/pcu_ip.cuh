@@ -47,6 +47,7 @@ struct IPOptions {
   std::string barrier_strategy = "monotone";
   std::string starting_point_strategy = "affine_step";
   std::string output_file;  // empty: no text log
+  std::string ip_checkpoint_file;  // empty: no checkpoint (ParOptOptimizer.cpp:98)
   std::string problem_name;
 };
 
@@ -163,6 +164,7 @@ struct pcu_ip {
   double upd_sums[11], upd_max[5], upd_min[2];
   int upd_stats_valid = 0;
   int opt_no_updstats = 0;    // debugging (PCU_NO_UPDSTATS): always run the residual pass
+  int checkpoint_failed = 0;
   int opt_force_chain = 0;    // PCU_CHAIN=1: device chain also across GPUs
   int opt_no_chain = 0;       // debugging (PCU_NO_CHAIN): dense algebra of the KKT solve on the host
   double *dense_dev = nullptr, *dense_host = nullptr;  // work buffer of pcu_dense_kernel (+ pinned mirror)

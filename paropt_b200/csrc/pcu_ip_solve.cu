@@ -1247,6 +1247,14 @@ int pcu_ip::iterate_once(int *converged) {
   }
   // the problem's writeOutput hook (IP.cpp:4620-4631)
   if (opt.write_output_frequency > 0 && k % opt.write_output_frequency == 0) {
+    if (!opt.ip_checkpoint_file.empty() && !checkpoint_failed) {
+      // a failed write is reported once and not tried again (IP.cpp:4622-4628)
+      if (pcu_ip_write_solution(this, opt.ip_checkpoint_file.c_str())) {
+        fprintf(stderr, "ParOpt: Checkpoint file %s creation failed\n",
+                opt.ip_checkpoint_file.c_str());
+        checkpoint_failed = 1;
+      }
+    }
     if (prob->writeOutput(k, v.v[PCU_X])) return 1;
   }
   const int rel_function_test =
