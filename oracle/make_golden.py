@@ -102,6 +102,22 @@ VARIANTS = [
 ]
 
 
+GMRES_VARIANTS = [
+    ("C2_var_gmres", "C2", {}),
+    ("C3_var_gmres", "C3", {}),
+    ("C3_var_gmres_noprecon", "C3", dict(use_qn_gmres_precon=False)),
+]
+
+
+def gmres_config(base, extra):
+    cfg = configs.small(base)
+    cfg["problem"]["ntotal"] = 4000
+    cfg["options"] = dict(cfg["options"], max_major_iters=40, use_hvec_product=True,
+                          gmres_subspace_size=15, nk_switch_tol=1e3, max_gmres_rtol=0.5,
+                          **extra)
+    return cfg
+
+
 def variant_config(base, overrides, n):
     cfg = configs.small(base)
     if n is not None:
@@ -171,6 +187,20 @@ def main():
             with open(os.path.join(out_dir, fname), "w") as fp:
                 json.dump(data, fp, separators=(",", ":"))
             print(fname, "niter", data["final"]["niter"], data["status"])
+        return
+    if "--gmres" in sys.argv:
+        # the inexact-Newton path (computeKKTGMRESStep, IP.cpp:5789-6191)
+        # with the problem's exact Hessian-vector products, switched on early (nk_switch_tol)
+        # so that most iterations of the history take it
+        for fname, base, extra in GMRES_VARIANTS:
+            cfg = gmres_config(base, extra)
+            data = run_reference(cfg)
+            data["generator"] = ("oracle/make_golden.py --gmres (oracle/_ref/ref_driver, unmodified "
+                                 "reference, use_hvec_product)")
+            with open(os.path.join(out_dir, fname + ".json"), "w") as fp:
+                json.dump(data, fp, separators=(",", ":"))
+            print(fname, "niter", data["final"]["niter"], data["status"],
+                  "nhvec", data["history"][-1]["nhvec"])
         return
     if "--full-c4" in sys.argv:
         # the dense-constraint stress config at its FULL size (n = 32M, c = 100, L-SR1

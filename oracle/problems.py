@@ -132,6 +132,16 @@ class SepQuad:
             Ac[j][:] = self.A[j]
         return 0
 
+    def evalHvecProduct(self, x, z, zw, px, hvec):
+        """H = P diag(lam) P (constant): the callback of the inexact-Newton GMRES path."""
+        w = self.lam * self._applyP(px)
+        if self.p["householder"]:
+            vw = self._sum([np.dot(self.vh, w)])[0]
+            hvec[:] = w - (2.0 * vw / self.vtv) * self.vh
+        else:
+            hvec[:] = w
+        return 0
+
 
 class Rosenbrock:
     """examples/rosenbrock/rosenbrock.cpp:9-199 with scale = 1 (single rank)."""

@@ -204,14 +204,14 @@ void HistoryProblem::writeOutput(int iter, ParOptVec *xvec) {
             "{\"iter\": %d, \"wall\": %.6f, \"fobj\": %.17g, \"mu\": %.17g, \"rho\": %.17g, "
             "\"comp\": %.17g, \"max_prime\": %.17g, \"max_dual\": %.17g, "
             "\"max_infeas\": %.17g, \"res_norm\": %.17g, \"neval\": %d, "
-            "\"ngeval\": %d, \"alpha\": %.17g, \"pnorm2\": %.17g, "
+            "\"ngeval\": %d, \"nhvec\": %d, \"alpha\": %.17g, \"pnorm2\": %.17g, "
             "\"qn_b0\": %.17g, \"qn_size\": %d, \"xsum\": %.17g, "
             "\"xnorm\": %.17g, \"zlsum\": %.17g, \"zusum\": %.17g, "
             "\"zlnorm\": %.17g, \"zunorm\": %.17g, \"zwsum\": %.17g, "
             "\"zwnorm\": %.17g, \"swsum\": %.17g, \"twsum\": %.17g, "
             "\"zswsum\": %.17g, \"ztwsum\": %.17g, \"gmax\": %.17g, ",
             iter, MPI_Wtime(), ip->fobj, ip->barrier_param, ip->rho_penalty_search, comp,
-            max_prime, max_dual, max_infeas, res_norm, ip->neval, ip->ngeval,
+            max_prime, max_dual, max_infeas, res_norm, ip->neval, ip->ngeval, ip->nhvec,
             alpha, pnorm2, b0, qsize, sums[0], xnorm, sums[1], sums[2], zlnorm,
             zunorm, sums[3], zwnorm, sums[4], sums[5], sums[6], sums[7], gmax);
     print_arr(hist, "c", ip->c, ncon);
@@ -397,6 +397,27 @@ class SepQuad : public HistoryProblem {
       }
     }
     callback_time += MPI_Wtime() - t0;
+    return 0;
+  }
+
+  // H = P diag(lam) P is constant (quadratic objective, linear constraints):
+  // the callback of the inexact-Newton GMRES path (IP.cpp:5973)
+  int evalHvecProduct(ParOptVec *, ParOptScalar *, ParOptVec *, ParOptVec *pxvec,
+                      ParOptVec *hvec) {
+    double *px, *h;
+    pxvec->getArray(&px);
+    hvec->getArray(&h);
+    applyP(px, ytmp.data());
+    for (int i = 0; i < n; i++) ytmp[i] *= lam[i];
+    if (p.householder) {
+      double loc = 0.0, vw = 0.0;
+      for (int i = 0; i < n; i++) loc += vh[i] * ytmp[i];
+      MPI_Allreduce(&loc, &vw, 1, MPI_DOUBLE, MPI_SUM, comm);
+      double f = 2.0 * vw / vtv;
+      for (int i = 0; i < n; i++) h[i] = ytmp[i] - f * vh[i];
+    } else {
+      for (int i = 0; i < n; i++) h[i] = ytmp[i];
+    }
     return 0;
   }
 
