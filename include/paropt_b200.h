@@ -137,6 +137,12 @@ typedef struct pcu_problem_callbacks {
   int (*qn_update_correction)(void *user, pcu_vec *x, const double *z, pcu_vec *zw,
                               pcu_vec *s, pcu_vec *y);
   int (*write_output)(void *user, int iter, pcu_vec *x);
+  /* Optional: hvec = H(x, z, zw) px, the Hessian of the Lagrangian
+     (ParOptProblem::evalHvecProduct, ParOptProblem.h:188).  Needed only with the option
+     use_hvec_product (inexact-Newton GMRES steps, IP.cpp:4853-4900, 5789-6191); NULL
+     makes such a step fail.                                                      */
+  int (*eval_hvec_product)(void *user, pcu_vec *x, const double *z, pcu_vec *zw,
+                           pcu_vec *px, pcu_vec *hvec);
 } pcu_problem_callbacks;
 
 /* ParOptProblem::setProblemSizes / setNumInequalities (ParOptProblem.cpp:47-76)
@@ -228,6 +234,10 @@ typedef struct pcu_host_callbacks {
   /* Optional, as in pcu_problem_callbacks; writeOutput sees the iterate in the
      pinned host mirror (one device->host copy per call).                        */
   int (*write_output)(void *user, int iter, int n, const double *x);
+  /* Optional, as in pcu_problem_callbacks: hvec = H(x, z, zw) px on host arrays
+     (z: ncon values, zw: nw local sparse multipliers).                          */
+  int (*eval_hvec_product)(void *user, int n, const double *x, const double *z, int nw,
+                           const double *zw, const double *px, double *hvec);
 } pcu_host_callbacks;
 pcu_problem *pcu_problem_create_host(pcu_ctx *ctx, int nvars, int ncon,
                                      int ninequality, int nwinequality,
@@ -364,8 +374,8 @@ int pcu_tr_penalty_gamma(pcu_tr *tr, double *gamma);   /* getPenaltyGamma TR.cpp
    followed by 6*ncon doubles (c, z, s, t, zs, zt).  Field order:
    iter fobj mu rho comp max_prime max_dual max_infeas res_norm neval ngeval
    alpha pnorm2 qn_b0 qn_size xsum xnorm zlsum zusum zwsum swsum twsum gmax
-   alpha_x alpha_z                                                            */
-#define PCU_HIST_FIELDS 25
+   alpha_x alpha_z nhvec                                                      */
+#define PCU_HIST_FIELDS 26
 int pcu_ip_history_len(pcu_ip *ip);
 int pcu_ip_history_get(pcu_ip *ip, int k, double *out, int out_len);
 /* The `info` tag string of the log row printed at iteration k (IP.cpp:5272).  */

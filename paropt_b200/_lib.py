@@ -48,6 +48,8 @@ EVAL_GRAD_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
 QN_CORR_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, c_double_p, C.c_void_p,
                          C.c_void_p, C.c_void_p)
 WRITE_OUT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+HVEC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, c_double_p, C.c_void_p, C.c_void_p,
+                      C.c_void_p)
 
 
 class Callbacks(C.Structure):
@@ -55,7 +57,8 @@ class Callbacks(C.Structure):
                 ("eval_obj_con", EVAL_OBJ_CB),
                 ("eval_obj_con_gradient", EVAL_GRAD_CB),
                 ("qn_update_correction", QN_CORR_CB),
-                ("write_output", WRITE_OUT_CB)]
+                ("write_output", WRITE_OUT_CB),
+                ("eval_hvec_product", HVEC_CB)]
 
 
 HOST_GET_VARS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p,
@@ -67,13 +70,16 @@ HOST_EVAL_GRAD_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_doub
 
 
 HOST_WRITE_OUT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, c_double_p)
+HOST_HVEC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_int,
+                           c_double_p, c_double_p, c_double_p)
 
 
 class HostCallbacks(C.Structure):
     _fields_ = [("user", C.c_void_p), ("get_vars_and_bounds", HOST_GET_VARS_CB),
                 ("eval_obj_con", HOST_EVAL_OBJ_CB),
                 ("eval_obj_con_gradient", HOST_EVAL_GRAD_CB),
-                ("write_output", HOST_WRITE_OUT_CB)]
+                ("write_output", HOST_WRITE_OUT_CB),
+                ("eval_hvec_product", HOST_HVEC_CB)]
 
 
 VP = C.c_void_p

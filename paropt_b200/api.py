@@ -15,7 +15,7 @@ from . import _lib
 HIST_FIELDS = ("iter", "fobj", "mu", "rho", "comp", "max_prime", "max_dual",
                "max_infeas", "res_norm", "neval", "ngeval", "alpha", "pnorm2",
                "qn_b0", "qn_size", "xsum", "xnorm", "zlsum", "zusum", "zwsum",
-               "swsum", "twsum", "gmax", "alpha_x", "alpha_z")
+               "swsum", "twsum", "gmax", "alpha_x", "alpha_z", "nhvec")
 STATUS = {0: None, 1: "tolerance", 2: "rel_function", 3: "no_improvement"}
 
 
@@ -359,6 +359,10 @@ class Problem:
         # subclass defines it, so that nobody pays the device->host copy otherwise
         if hasattr(self, "writeOutput"):
             self._cb.write_output = _lib.HOST_WRITE_OUT_CB(self._write_output)
+        # ParOptProblem::evalHvecProduct (ParOptProblem.h:188; ParOpt.pyx _evalhvecproduct):
+        # evalHvecProduct(x, z, zw, px, hvec) -> fail, for the option use_hvec_product
+        if hasattr(self, "evalHvecProduct"):
+            self._cb.eval_hvec_product = _lib.HOST_HVEC_CB(self._eval_hvec)
         self._views = {}
         self.h = self.lib.pcu_problem_create_host(
             ctx.h, self.nvars, self.ncon, int(ninequality), int(nwinequality),
@@ -403,6 +407,17 @@ class Problem:
             for i in range(self.ncon):
                 cons[i] = float(con[i])
             return int(fail)
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _eval_hvec(self, user, n, x, z, nw, zw, px, hvec):
+        try:
+            zz = np.array([z[i] for i in range(self.ncon)])
+            fail = self.evalHvecProduct(self._view(x, n), zz, self._view(zw, nw),
+                                        self._view(px, n), self._view(hvec, n))
+            return int(fail or 0)
         except Exception:
             import traceback
             traceback.print_exc()
@@ -615,7 +630,7 @@ class InteriorPoint:
             _check(self.lib.pcu_ip_history_get(self.h, k, buf.ctypes.data_as(_lib.c_double_p),
                                                buf.size), "history")
             rec = {name: float(buf[i]) for i, name in enumerate(HIST_FIELDS)}
-            for name in ("iter", "neval", "ngeval", "qn_size"):
+            for name in ("iter", "neval", "ngeval", "qn_size", "nhvec"):
                 rec[name] = int(rec[name])
             off = len(HIST_FIELDS)
             for j, name in enumerate(("c", "z", "s", "t", "zs", "zt")):

@@ -59,6 +59,14 @@ const OptEntry OPTIONS[] = {
     OPT_I(output_level, 0, 1000000),
     OPT_I(write_output_frequency, 0, 1000000),
     OPT_I(history_level, 0, 2),
+    OPT_I(use_hvec_product, 0, 1),
+    OPT_I(use_qn_gmres_precon, 0, 1),
+    OPT_I(gmres_subspace_size, 0, 1000),
+    OPT_F(nk_switch_tol, 0.0, 1e20),
+    OPT_F(eisenstat_walker_alpha, 0.0, 2.0),
+    OPT_F(eisenstat_walker_gamma, 0.0, 1.0),
+    OPT_F(max_gmres_rtol, 0.0, 1.0),
+    OPT_F(gmres_atol, 0.0, 1.0),
     OPT_S(qn_type, "bfgs|scaled_bfgs|sr1|none"),
     OPT_S(qn_update_type, "skip_negative_curvature|damped_update"),
     OPT_S(qn_diag_type,

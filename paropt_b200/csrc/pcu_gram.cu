@@ -614,7 +614,15 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
   const int ld = 8 * nt;
   *ld_out = ld;
   if (m == 0) return 0;
-  if (rhs_col >= 0 && (rhs_col != m - 1 || nt > 5)) return 1;
+  if (rhs_col >= 0 && rhs_col != m - 1) return 1;
+  if (rhs_col >= 0 && nt > 5) {
+    // Wide column sets: without weighting constraints the right-hand side is one more
+    // plain column (row m - 1 of S is d1^T Dinv V_j = V_j . t1); with them the block
+    // part of t1 needs the narrow kernels' correction step.
+    if (wd.nwcon > 0) return 1;
+    rhs_col = -1;
+    d2 = nullptr;
+  }
   if (ctx->big_reserve((size_t)ld * ld + 64, 1)) return 1;
   WDesc w = wd;
   if (w.mode == 2 || w.nwcon == 0) {

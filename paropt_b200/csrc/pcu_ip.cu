@@ -369,6 +369,7 @@ pcu_ip::~pcu_ip() {
   pcu_vec *single[] = {lb, ub, g, Dinv, Cw, d1, d2, t1, s_qn, y_qn, rx, rsw, rtw};
   for (auto v : single) pcu_vec_destroy(v);
   for (auto v : Ac) pcu_vec_destroy(v);
+  for (auto v : gmres_W) pcu_vec_destroy(v);
   if (!qn_external) delete qn;
   if (dense_dev) cudaFree(dense_dev);
   if (dense_host) cudaFreeHost(dense_host);
@@ -701,8 +702,8 @@ int pcu_ip::computeKKTRes(Vars &vars, double mu, Vars &res, Vars *step,
   f.b0sig = 0.0;
   f.has_step = step ? 1 : 0;
   if (step) {
-    f.b0sig = opt.qn_sigma;
-    if (qn && !opt.sequential_linear_method) {  // IP.cpp:1474-1476
+    f.b0sig = res_skip_hessian ? 0.0 : opt.qn_sigma;
+    if (qn && !opt.sequential_linear_method && !res_skip_hessian) {  // IP.cpp:1474-1476
       f.b0sig += qn->b0;
       f.nq = qn->size();
       if (f.nq > 0) {

@@ -40,6 +40,15 @@ struct IPOptions {
   int output_level = 0;
   int write_output_frequency = 10;
   int history_level = 1;  // 0 none, 1 scalars, 2 + state checksums (one extra pass)
+  // inexact-Newton GMRES path (IP.cpp:593-611, 639, 646, 668)
+  int use_hvec_product = 0;
+  int use_qn_gmres_precon = 1;
+  int gmres_subspace_size = 0;
+  double nk_switch_tol = 1e-3;
+  double eisenstat_walker_alpha = 1.5;
+  double eisenstat_walker_gamma = 1.0;
+  double max_gmres_rtol = 0.1;
+  double gmres_atol = 1e-30;
   std::string qn_type = "bfgs";
   std::string qn_update_type = "skip_negative_curvature";
   std::string qn_diag_type = "yty_over_yts";
@@ -145,13 +154,15 @@ struct pcu_ip {
   double b0_used = 0.0;
 
   double barrier_param = 0.1, rho_penalty_search = 0.0;
-  int niter = 0, neval = 0, ngeval = 0;
+  int niter = 0, neval = 0, ngeval = 0, nhvec = 0;
   int status = 0;
+  std::vector<pcu_vec *> gmres_W;  // Krylov vectors (x block), gmres_subspace_size + 1
 
   // statistics of the last ResF launch
   double res_sums[11], res_max[5], res_min[2];
   double res_mu = 0.0;   // barrier of the last ResF launch
   int res_has_step = 0;  // the last ResF launch included the step terms
+  int res_skip_hessian = 0;  // computeKKTRes with a step: leave the B p term to the caller
   double last_comp = 0.0;
   int force_direct_dots = 0;  // debugging: recompute [A|Z]^T p with multi-dots
   int opt_no_rhsgram = 0;     // debugging: keep the first solve's pass 1 out of the Gram pass
@@ -240,7 +251,13 @@ struct pcu_ip {
   int addMehrotraCorrectorResidual(Vars &step, Vars &res);
   int stepStats(Vars &vars, Vars &step, double tau, double *sums, double *mins);
   int scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
-                    const double *VTp, double fixed_scale, StepScale *out);
+                    const double *VTp, double fixed_scale, StepScale *out,
+                    int inexact_newton_step = 0);
+  // computeKKTGMRESStep (IP.cpp:5789-6191): > 0 iterations taken, < 0 the step failed
+  // the descent tests, 0 nothing done; *rc_err != 0 on a CUDA / callback error
+  int computeKKTGMRESStep(Vars &vars, Vars &res, Vars &step, double rtol, double atol,
+                          int use_qn, double *VTp, int *rc_err);
+  int evalHvecProduct(pcu_vec *px, pcu_vec *hvec);
   int initLeastSquaresMultipliers();
   int initAffineStepMultipliers();
   int begin();

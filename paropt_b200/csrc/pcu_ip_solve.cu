@@ -164,9 +164,11 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     // The residual-free first solve needs the fused pass-1 / pass-2 kernels;
     // otherwise materialise the right-hand side first.
     const int q0 = (qn && use_qn && !Cefac.empty()) ? std::min(sq, qn->size()) : 0;
+    // more than 32 columns: only with this solve's first half already done by the
+    // Gram pass (pass 2 is then Pass2RF, which takes any width)
     const bool fused_ok = emit_res && VTp && !force_direct_dots &&
                           q0 == (qn ? qn->size() : 0) && ncon + q0 > 0 &&
-                          ncon + q0 <= 32;
+                          (ncon + q0 <= 32 || pass1_ready);
     if (rhs_from_vars && !fused_ok) {
       if (computeKKTRes(vars, mu_res, b, nullptr, nullptr, nullptr, 1)) return 1;
       rhs_from_vars = 0;
@@ -855,7 +857,8 @@ int pcu_ip::initAffineStepMultipliers() {
   if (initLeastSquaresMultipliers()) return 1;
   // (out-of-range multipliers are already zero)
   if (computeKKTRes(vars, 0.0, res, nullptr, nullptr, nullptr)) return 1;
-  int use_qn = opt.sequential_linear_method ? 0 : 1;
+  // (the GMRES preconditioner switch also acts here, IP.cpp:5575-5578)
+  int use_qn = (opt.sequential_linear_method || !opt.use_qn_gmres_precon) ? 0 : 1;
   if (setUpKKTDiagSystem(vars, use_qn, 0)) return 1;
   if (setUpKKTSystem(vars, use_qn, nullptr)) return 1;
   if (computeKKTStep(vars, res, step, use_qn, 0, nullptr, 0, 0.0, nullptr)) return 1;
@@ -999,6 +1002,7 @@ int pcu_ip::snapshot(int k, double comp, double max_prime, double max_dual,
   f[22] = sums[7];
   f[23] = ls.alpha_xprev;
   f[24] = ls.alpha_zprev;
+  f[25] = nhvec;
   rec.dense.reserve(6 * ncon);
   const std::vector<double> *parts[6] = {&c, &variables.z, &variables.s,
                                          &variables.t, &variables.zs,
@@ -1022,12 +1026,12 @@ void pcu_ip::log_line(int k, double comp, double max_prime, double max_infeas,
   if (k == 0) {
     fprintf(outfp,
             "%4d %4d %4d %4d %7s %7s %7s %12.5e %7.1e %7.1e %7.1e %7.1e %7.1e %8s %7s %s\n",
-            k, neval, ngeval, 0, "--", "--", "--", fobj, max_prime, max_infeas,
+            k, neval, ngeval, nhvec, "--", "--", "--", fobj, max_prime, max_infeas,
             max_dual, barrier_param, comp, "--", "--", ls.info.c_str());
   } else {
     fprintf(outfp,
             "%4d %4d %4d %4d %7.1e %7.1e %7.1e %12.5e %7.1e %7.1e %7.1e %7.1e %7.1e %8.1e %7.1e %s\n",
-            k, neval, ngeval, 0, ls.alpha_prev, ls.alpha_xprev, ls.alpha_zprev,
+            k, neval, ngeval, nhvec, ls.alpha_prev, ls.alpha_xprev, ls.alpha_zprev,
             fobj, max_prime, max_infeas, max_dual, barrier_param, comp,
             ls.dm0_prev, rho_penalty_search, ls.info.c_str());
   }
@@ -1042,7 +1046,7 @@ void pcu_ip::log_line(int k, double comp, double max_prime, double max_infeas,
 // fixed_scale is the max_x argument of the reference's evalMeritInitDeriv.
 int pcu_ip::scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
                           const double *VTp, double fixed_scale,
-                          StepScale *out) {
+                          StepScale *out, int inexact_newton_step) {
   const double abs_res_tol = opt.abs_res_tol;
   const int slm = opt.sequential_linear_method;
   const int nA = ncon;
@@ -1076,6 +1080,10 @@ int pcu_ip::scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
       ceq_step = 1;
       if (alpha_x > alpha_z) alpha_x = alpha_z;
       else alpha_z = alpha_x;
+    }
+    if (inexact_newton_step) {  // IP.cpp:3241-3248: one step length, no other rule
+      alpha_x = alpha_z = std::min(mins[0], mins[1]);
+      ceq_step = 0;
     }
     if (fixed_scale >= 0.0) {
       alpha_x = 1.0;
@@ -1187,7 +1195,7 @@ int pcu_ip::begin() {
   ls.input_barrier_strategy = strat(opt.barrier_strategy);
   barrier_param = opt.init_barrier_param;
   rho_penalty_search = opt.init_rho_penalty_search;
-  niter = neval = ngeval = 0;
+  niter = neval = ngeval = nhvec = 0;
   status = 0;
   history.clear();
   times.clear();
@@ -1266,8 +1274,10 @@ int pcu_ip::iterate_once(int *converged) {
   double max_prime = 0.0, max_dual = 0.0, max_infeas = 0.0, res_norm = 0.0;
   int monotone_barrier_converged = 0;
   // monotone strategy with refinement: the residual vectors are never stored
+  // (the GMRES right-hand side is the stored residual: no lazy residual with
+  // use_hvec_product)
   const bool lazy_res = (ls.barrier_strategy == BS_MONOTONE) &&
-                        opt.iterative_refinement_steps > 0;
+                        opt.iterative_refinement_steps > 0 && !opt.use_hvec_product;
   // residual + norms + complementarity in one pass (IP.cpp:4656-4671)
   if (ls.barrier_strategy == BS_COMP_FRACTION) {
     // mu depends on comp: a first pass for comp, then the residual
@@ -1353,11 +1363,47 @@ int pcu_ip::iterate_once(int *converged) {
     return 0;
   }
 
+  const int nA = ncon, nZ = qn ? qn->max_size() : 0;
+  std::vector<double> VTp(nA + nZ + 1, 0.0);
+  bool vtp_valid = true;
+
+  // Newton or quasi-Newton step (IP.cpp:4842-4900): with exact Hessian-vector products
+  // and small enough residuals, right-preconditioned GMRES on the exact KKT system
+  int gmres_iters = 0, inexact_newton_step = 0;
+  if (opt.use_hvec_product) {
+    const double gmres_rtol = opt.eisenstat_walker_gamma *
+                              pow(res_norm / ls.res_norm_prev, opt.eisenstat_walker_alpha);
+    const double tol = opt.nk_switch_tol;
+    if (max_prime < tol && max_dual < tol && max_infeas < tol &&
+        gmres_rtol < opt.max_gmres_rtol) {
+      const int use_qn_g = (slm || !opt.use_qn_gmres_precon) ? 0 : 1;
+      PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k0, ctx->stream));
+      if (setUpKKTDiagSystem(v, use_qn_g, 0)) return 1;
+      if (setUpKKTSystem(v, use_qn_g, nullptr)) return 1;
+      int err = 0;
+      gmres_iters = computeKKTGMRESStep(v, res, upd, gmres_rtol, opt.gmres_atol, use_qn_g,
+                                        VTp.data(), &err);
+      if (err) return 1;
+      PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k1, ctx->stream));
+      if (gmres_iters < 0) {
+        if (outfp && ctx->rank == 0 && opt.output_level > 0)
+          fprintf(outfp, "      %9s\n", "step failed");
+        // the residual was destroyed by the failed attempt (IP.cpp:4889-4893)
+        if (computeKKTRes(v, barrier_param, res, nullptr, nullptr, nullptr)) return 1;
+        computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
+      } else {
+        inexact_newton_step = 1;
+      }
+    }
+  }
+
   ls.fobj_prev = fobj;
   ls.res_norm_prev = res_norm;
   int seq_linear_step = 0, diagonal_qn_step = 0;
   int use_qn = 1;
-  if (slm) {
+  if (inexact_newton_step) {
+    // the step is there: none of the quasi-Newton step computations below run
+  } else if (slm) {
     use_qn = 0;
   } else if (ls.line_search_failed && !uq) {
     use_qn = 0;
@@ -1370,26 +1416,27 @@ int pcu_ip::iterate_once(int *converged) {
   double mu_for_res = barrier_param;
   const bool mehrotra =
       ls.barrier_strategy == BS_MEHROTRA || ls.barrier_strategy == BS_MPC;
-  if (mehrotra) {
+  if (mehrotra && !inexact_newton_step) {
     mu_for_res = 0.0;
     if (computeKKTRes(v, mu_for_res, res, nullptr, nullptr, nullptr)) return 1;
     computeResNorm(res, &max_prime, &max_dual, &max_infeas, &res_norm);
   }
   if (diagonal_qn_step) use_qn = 1;
-  const int nA = ncon, nZ = qn ? qn->max_size() : 0;
-  std::vector<double> VTp(nA + nZ + 1, 0.0);
-  bool vtp_valid = true;
 
-  PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k0, ctx->stream));
+  if (!inexact_newton_step) PCU_CUDA_OK(cudaEventRecord(evs[ev_cur].k0, ctx->stream));
   // The first solve's right-hand side can ride in the Gram pass when that solve
   // takes the fused residual-free route (see computeKKTStep).
-  bool rhs_in_gram = false;
+  bool rhs_in_gram = false, wide_rhs = false;
   {
     const int qa = qn ? qn->size() : 0;
     const int q0 = (qn && use_qn) ? qa : 0;
+    // (more than 32 columns: the wide Gram kernel takes the right-hand side as a plain
+    // column, which needs a problem without weighting constraints)
     rhs_in_gram = lazy_res && !opt_no_rhsgram && !force_direct_dots &&
                   !diagonal_qn_step && q0 == qa && ncon + q0 >= 1 &&
-                  ncon + q0 <= 32;
+                  (ncon + q0 <= 32 || (nwcon == 0 && ctx->world == 1 &&
+                                       ncon + q0 + 1 <= PCU_MAX_COLS));
+    wide_rhs = rhs_in_gram && ncon + q0 > 32;
   }
   const int nref = opt.iterative_refinement_steps;
   // fraction-to-boundary parameter of this iteration (IP.cpp:5069-5077), known before
@@ -1400,10 +1447,12 @@ int pcu_ip::iterate_once(int *converged) {
   // of dense kernel against two flag-polled host round trips); across GPUs the host
   // path is faster (measured at 8 GPUs: 1.94 against 2.04 ms per iteration), so it
   // is taken there only on request (PCU_CHAIN=1).
-  const bool chain = rhs_in_gram && nref == 1 && !mehrotra && !opt_no_chain &&
+  const bool chain = rhs_in_gram && !wide_rhs && nref == 1 && !mehrotra && !opt_no_chain &&
                      !opt_no_fuse21 && !opt_no_fuse2s && ctx->chain_ok() &&
                      (ctx->world == 1 || opt_force_chain);
-  if (chain) {
+  if (inexact_newton_step) {
+    // nothing to set up
+  } else if (chain) {
     if (kktChain(v, res, upd, use_qn, mu_for_res, tau_pre, VTp.data())) return 1;
   } else if (rhs_in_gram) {
     if (setUpKKTDiagRhs(v, use_qn, mu_for_res)) return 1;
@@ -1414,13 +1463,24 @@ int pcu_ip::iterate_once(int *converged) {
   }
   if (diagonal_qn_step) use_qn = 0;
   auto kkt_with_refinement = [&](double mu_res, bool allow_refine) -> int {
-    const bool need_dots = true;
-    (void)need_dots;
     const int nr = allow_refine ? nref : 0;
     int emitted = 0;
-    if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nr > 0, mu_res, &emitted))
+    // after an inexact-Newton step the refinement residual takes the exact Hessian
+    // (addKKTResStep with the outer flag, IP.cpp:5155-5156, 1461-1463)
+    const bool hres = inexact_newton_step != 0;
+    if (computeKKTStep(v, res, upd, use_qn, 0, VTp.data(), nr > 0 && !hres, mu_res, &emitted))
       return 1;
     for (int it = 0; it < nr; it++) {  // IP.cpp:4985-4991
+      if (hres) {
+        res_skip_hessian = 1;
+        const int rc = computeKKTRes(v, mu_res, res, &upd, VTp.data(), VTp.data() + nA);
+        res_skip_hessian = 0;
+        if (rc || evalHvecProduct(upd.v[PCU_X], t1) ||
+            pcu_vec_axpy(res.v[PCU_X], -1.0, t1))
+          return 1;
+        if (computeKKTStep(v, res, upd, use_qn, 1, VTp.data(), 0, mu_res, &emitted)) return 1;
+        continue;
+      }
       if (!emitted &&
           computeKKTRes(v, mu_res, res, &upd, VTp.data(), VTp.data() + nA))
         return 1;
@@ -1430,7 +1490,7 @@ int pcu_ip::iterate_once(int *converged) {
     }
     return 0;
   };
-  if (!chain) {
+  if (!chain && !inexact_newton_step) {
     // the fraction-to-boundary parameter is known before the solves (it depends on
     // the barrier only, IP.cpp:5069-5077), so the last pass of the last solve can
     // take the step statistics (not under the Mehrotra strategies, whose
@@ -1457,7 +1517,7 @@ int pcu_ip::iterate_once(int *converged) {
   }
   (void)ref;
   double sums[StatsF::NS], mins[2];
-  if (mehrotra) {  // IP.cpp:4999-5051
+  if (mehrotra && !inexact_newton_step) {  // IP.cpp:4999-5051
     if (stepStats(v, upd, 1.0, sums, mins)) return 1;
     const double max_x = mins[0], max_z = mins[1];
     double product = (sums[0] + max_x * sums[1] + max_z * sums[2] +
@@ -1496,9 +1556,9 @@ int pcu_ip::iterate_once(int *converged) {
 
   // scaleKKTStep (IP.cpp:3196-3274) + evalMeritInitDeriv (IP.cpp:3652-3924) from
   // ONE statistics pass; the step itself stays unscaled on the device.
-  auto scale_and_merit = [&]() -> int {
+  auto scale_and_merit = [&](int inexact) -> int {
     StepScale sc;
-    if (scaleAndMerit(v, upd, tau, comp, VTp.data(), -1.0, &sc)) return 1;
+    if (scaleAndMerit(v, upd, tau, comp, VTp.data(), -1.0, &sc, inexact)) return 1;
     alpha_x = sc.alpha_x;
     alpha_z = sc.alpha_z;
     ceq_step = sc.ceq;
@@ -1507,7 +1567,7 @@ int pcu_ip::iterate_once(int *converged) {
     pnorm2 = sc.pnorm2;
     return 0;
   };
-  if (scale_and_merit()) return 1;
+  if (scale_and_merit(inexact_newton_step)) return 1;
 
   double alpha = 1.0;
   int line_fail = LS_FAILURE;
@@ -1782,7 +1842,7 @@ int pcu_ip::iterate_once(int *converged) {
         if (setUpKKTDiagSystem(v, use_qn, 0)) return 1;
         if (setUpKKTSystem(v, use_qn, nullptr)) return 1;
         if (kkt_with_refinement(barrier_param, true)) return 1;
-        if (scale_and_merit()) return 1;
+        if (scale_and_merit(0)) return 1;
         ls.dm0_prev = dm0;
       }
       if (dm0 >= 0.0) {
@@ -1851,6 +1911,7 @@ int pcu_ip::iterate_once(int *converged) {
     qn->reset();
   }
   std::string info;
+  if (gmres_iters != 0) info += "iNK" + std::to_string(gmres_iters) + " ";
   if (update_type == 1) info += "dampH ";
   else if (update_type == 2) info += "skipH ";
   if (qn_hessian_reset) info += "resetH ";

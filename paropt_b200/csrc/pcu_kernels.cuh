@@ -649,6 +649,9 @@ struct Pass1F : NoStreams {
   const double *lb, *ub, *Dinv, *Cw;
   double *d1, *d2, *t1;
   IPConst k;
+  // every part of the right-hand side except b.x is scaled by bs: the alpha-scaled
+  // variant of the solve that the GMRES path uses (IP.cpp:2441-2614); 1 otherwise
+  double bs = 1.0;
 
   template <int W>
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
@@ -666,8 +669,8 @@ struct Pass1F : NoStreams {
 #pragma unroll
     for (int q = 0; q < W; q++) {
       double t = bx[q];
-      if (k.use_lower && l[q] > -k.mbv) t += bzl[q] / (x[q] - l[q]);
-      if (k.use_upper && u[q] < k.mbv) t -= bzu[q] / (u[q] - x[q]);
+      if (k.use_lower && l[q] > -k.mbv) t += bs * bzl[q] / (x[q] - l[q]);
+      if (k.use_upper && u[q] < k.mbv) t -= bs * bzu[q] / (u[q] - x[q]);
       d[q] = t;
       e[q].d1 = t;
       e[q].dinv = di[q];
@@ -678,8 +681,8 @@ struct Pass1F : NoStreams {
   __device__ __forceinline__ void B(long long ci, const double (&sum)[1],
                                     Con &con, AccT &) const {
     const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double dd = b.zw[ci] + (b.zsw[ci] + sw * b.sw[ci]) / zsw -
-                      (b.ztw[ci] + tw * b.tw[ci]) / ztw;
+    const double dd = bs * (b.zw[ci] + (b.zsw[ci] + sw * b.sw[ci]) / zsw -
+                            (b.ztw[ci] + tw * b.tw[ci]) / ztw);
     con.d[0] = Cw[ci] * (dd - sum[0]);
     d2[ci] = dd;
   }
@@ -716,6 +719,7 @@ struct Pass2F : NoStreams {
   int ncols;
   int accumulate;
   IPConst k;
+  double bs = 1.0;  // scale of the right-hand side parts (see Pass1F)
 
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
@@ -754,10 +758,10 @@ struct Pass2F : NoStreams {
     const double yw = Cw[ci] * (d2[ci] - sum[0]);
     con.d[0] = yw;
     const double sw = v.sw[ci], tw = v.tw[ci], zsw = v.zsw[ci], ztw = v.ztw[ci];
-    const double pzsw = yw - b.sw[ci];
-    const double pztw = -b.tw[ci] - yw;
-    const double psw = (b.zsw[ci] - sw * pzsw) / zsw;
-    const double ptw = (b.ztw[ci] - tw * pztw) / ztw;
+    const double pzsw = yw - bs * b.sw[ci];
+    const double pztw = -bs * b.tw[ci] - yw;
+    const double psw = (bs * b.zsw[ci] - sw * pzsw) / zsw;
+    const double ptw = (bs * b.ztw[ci] - tw * pztw) / ztw;
     if (accumulate) {
       y.zw[ci] += yw;
       y.zsw[ci] += pzsw;
@@ -797,9 +801,9 @@ struct Pass2F : NoStreams {
       pzl[q] = 0.0;
       pzu[q] = 0.0;
       if (k.use_lower && l[q] > -k.mbv)
-        pzl[q] = (bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
+        pzl[q] = (bs * bzl[q] - zl[q] * px[q]) / (x[q] - l[q]);
       if (k.use_upper && u[q] < k.mbv)
-        pzu[q] = (bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
+        pzu[q] = (bs * bzu[q] + zu[q] * px[q]) / (u[q] - x[q]);
     }
     if (accumulate) {
       double o[W];

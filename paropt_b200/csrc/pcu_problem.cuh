@@ -33,6 +33,14 @@ struct pcu_problem {
   }
   virtual bool hasQnUpdateCorrection() const { return false; }
   virtual int writeOutput(int, pcu_vec *) { return 0; }
+  // hvec = H(x, z, zw) px, the Hessian of the Lagrangian (ParOptProblem.h:188); only the
+  // inexact-Newton GMRES path calls it (use_hvec_product, IP.cpp:5973, 1461).  The
+  // reference's default prints an error and returns 0 (ParOptProblem.cpp:205-212);
+  // here a problem without the callback fails the step.
+  virtual int evalHvecProduct(pcu_vec *, const double *, pcu_vec *, pcu_vec *, pcu_vec *) {
+    return 1;
+  }
+  virtual bool hasHvecProduct() const { return false; }
 };
 
 WDesc pcu_make_wdesc(const pcu_weighting &w, int nvars);

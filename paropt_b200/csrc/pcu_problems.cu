@@ -242,10 +242,13 @@ struct SQGrad1F : NoStreams {
         o[e] = l[e] * (xv[e] - hf * v[e]);
         acc.s[0] = fma(v[e], o[e], acc.s[0]);
       }
-    } else {
+    } else if (b) {
       ldv<W>(b, i, bb);
 #pragma unroll
       for (int e = 0; e < W; e++) o[e] = l[e] * xv[e] + bb[e];
+    } else {  // Hessian-vector product: no linear term
+#pragma unroll
+      for (int e = 0; e < W; e++) o[e] = l[e] * xv[e];
     }
     stv<W>(g, i, o);
   }
@@ -270,10 +273,15 @@ struct SQGrad2F : NoStreams {  // g = (w - hf2 * vh) + b
                                     AccT &) const {
     double o[W], bb[W], v[W];
     ldv<W>(g, i, o);
-    ldv<W>(b, i, bb);
     ldv<W>(vh, i, v);
+    if (b) {
+      ldv<W>(b, i, bb);
 #pragma unroll
-    for (int e = 0; e < W; e++) o[e] = (o[e] - hf2 * v[e]) + bb[e];
+      for (int e = 0; e < W; e++) o[e] = (o[e] - hf2 * v[e]) + bb[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < W; e++) o[e] = o[e] - hf2 * v[e];
+    }
     stv<W>(g, i, o);
   }
 };
@@ -398,13 +406,36 @@ struct SepQuadProblem : pcu_problem {
     return 0;
   }
 
+  // H = P diag(lam) P is constant: hvec = gradient of the quadratic part at px
+  int evalHvecProduct(pcu_vec *, const double *, pcu_vec *, pcu_vec *px, pcu_vec *hvec) override {
+    return grad_into(px, hvec, false);
+  }
+  bool hasHvecProduct() const override { return true; }
+
   int evalObjConGradient(pcu_vec *x, pcu_vec *g, pcu_vec **Ac) override {
+    if (grad_into(x, g, true)) return 1;
+    for (int j0 = 0; j0 < ncon; j0 += 8) {
+      SQConGradF f;
+      f.q = q;
+      f.nj = ncon - j0 < 8 ? ncon - j0 : 8;
+      for (int j = 0; j < f.nj; j++) {
+        f.cols[j] = Ac[j0 + j]->d;
+        f.keys[j] = stream_key(q.p.seed, 100 + (uint64_t)(j0 + j));
+      }
+      RedBuf rb = {nullptr, nullptr, nullptr, 0};
+      if (pcu_launch_tile(ctx, f, nvars, no_weighting(), rb)) return 1;
+    }
+    return 0;
+  }
+
+  // g = P diag(lam) P x (+ b)
+  int grad_into(pcu_vec *x, pcu_vec *g, bool with_b) {
     double hf;
     if (householder_factor(x, &hf)) return 1;
     SQGrad1F f1;
     f1.x = x->d;
     f1.lam = lam->d;
-    f1.b = b->d;
+    f1.b = with_b ? b->d : nullptr;
     f1.vh = vh ? vh->d : nullptr;
     f1.hf = hf;
     f1.g = g->d;
@@ -414,7 +445,7 @@ struct SepQuadProblem : pcu_problem {
       double vw;
       if (ctx->fetch(&vw)) return 1;
       SQGrad2F f2;
-      f2.b = b->d;
+      f2.b = with_b ? b->d : nullptr;
       f2.vh = vh->d;
       f2.hf2 = 2.0 * vw / vtv;
       f2.g = g->d;
@@ -429,17 +460,6 @@ struct SepQuadProblem : pcu_problem {
         ctx->result_used = ctx->pending.back().offset;
         ctx->pending.pop_back();
       }
-    }
-    for (int j0 = 0; j0 < ncon; j0 += 8) {
-      SQConGradF f;
-      f.q = q;
-      f.nj = ncon - j0 < 8 ? ncon - j0 : 8;
-      for (int j = 0; j < f.nj; j++) {
-        f.cols[j] = Ac[j0 + j]->d;
-        f.keys[j] = stream_key(q.p.seed, 100 + (uint64_t)(j0 + j));
-      }
-      RedBuf rb = {nullptr, nullptr, nullptr, 0};
-      if (pcu_launch_tile(ctx, f, nvars, no_weighting(), rb)) return 1;
     }
     return 0;
   }
@@ -566,6 +586,11 @@ struct CallbackProblem : pcu_problem {
   int writeOutput(int iter, pcu_vec *x) override {
     return cb.write_output ? cb.write_output(cb.user, iter, x) : 0;
   }
+  int evalHvecProduct(pcu_vec *x, const double *z, pcu_vec *zw, pcu_vec *px,
+                      pcu_vec *hvec) override {
+    return cb.eval_hvec_product ? cb.eval_hvec_product(cb.user, x, z, zw, px, hvec) : 1;
+  }
+  bool hasHvecProduct() const override { return cb.eval_hvec_product != nullptr; }
 };
 
 // ======================================================= host-array callbacks
@@ -580,7 +605,7 @@ struct HostProblem : pcu_problem {
   pcu_host_callbacks cb;
   double t_d2h = 0.0, t_user = 0.0, t_h2d = 0.0;  // wall-clock ms per phase
   bool timing = false;  // PCU_HOST_TIMING: synchronise after the uploads to time them
-  double *hx = nullptr, *hg = nullptr;
+  double *hx = nullptr, *hg = nullptr, *hzw = nullptr;
   std::vector<double *> hA;
   cudaEvent_t up_done = nullptr;  // last host->device copy of g / A
   bool up_pending = false;
@@ -588,6 +613,7 @@ struct HostProblem : pcu_problem {
   ~HostProblem() {
     if (hx) cudaFreeHost(hx);
     if (hg) cudaFreeHost(hg);
+    if (hzw) cudaFreeHost(hzw);
     for (double *p : hA)
       if (p) cudaFreeHost(p);
     if (up_done) cudaEventDestroy(up_done);
@@ -672,6 +698,31 @@ struct HostProblem : pcu_problem {
     up_pending = true;
     return fail;
   }
+  // hvec = H(x, z, zw) px on host arrays: x in hx, px in hg, the result in hA[0]
+  int evalHvecProduct(pcu_vec *x, const double *z, pcu_vec *zw, pcu_vec *px,
+                      pcu_vec *hvec) override {
+    if (!cb.eval_hvec_product) return 1;
+    same_point_hint = 0;  // the iterate may have moved since the last callback
+    if (fetch_x(x) || wait_uploads()) return 1;
+    if (nwcon > 0 && !hzw)
+      PCU_CUDA_OK(cudaHostAlloc(&hzw, sizeof(double) * (size_t)nwcon, cudaHostAllocDefault));
+    if (nvars > 0)
+      PCU_CUDA_OK(cudaMemcpyAsync(hg, px->d, sizeof(double) * (size_t)nvars,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    if (nwcon > 0)
+      PCU_CUDA_OK(cudaMemcpyAsync(hzw, zw->d, sizeof(double) * (size_t)nwcon,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    PCU_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    d2h_bytes += (long long)(sizeof(double) * ((size_t)nvars + (size_t)nwcon));
+    const double t0 = host_now_ms();
+    const int fail = cb.eval_hvec_product(cb.user, nvars, hx, z, nwcon, hzw, hg, hA[0]);
+    t_user += host_now_ms() - t0;
+    if (push(hvec, hA[0])) return 1;
+    PCU_CUDA_OK(cudaEventRecord(up_done, ctx->stream));
+    up_pending = true;
+    return fail;
+  }
+  bool hasHvecProduct() const override { return cb.eval_hvec_product != nullptr; }
 };
 
 extern "C" {

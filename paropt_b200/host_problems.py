@@ -137,3 +137,18 @@ class HostSepQuad(Problem):
         for j in range(self.ncon):
             self._t(A[j]).copy_(t["A"][j])
         return 0
+
+    def evalHvecProduct(self, x, z, zw, px, hvec):
+        """H = P diag(lam) P (constant): for the option use_hvec_product."""
+        import torch
+        t = self._tensors()
+        pt, ht = self._t(px), self._t(hvec)
+        if self.hh:
+            vx = float(self.allreduce(np.array([float(torch.dot(t["vh"], pt))]))[0])
+            y = torch.add(pt, t["vh"], alpha=-(2.0 * vx / self.vtv))
+            torch.mul(t["lam"], y, out=ht)
+            vw = float(self.allreduce(np.array([float(torch.dot(t["vh"], ht))]))[0])
+            ht.add_(t["vh"], alpha=-(2.0 * vw / self.vtv))
+        else:
+            torch.mul(t["lam"], pt, out=ht)
+        return 0
