@@ -193,6 +193,46 @@ typedef struct pcu_block_weighting {
 pcu_blockmat *pcu_blockmat_create_blocks(pcu_ctx *ctx, int nvars,
                                          const pcu_block_weighting *blocks);
 
+/* ---- ParOptQuasiDefSparseMat (ParOptSparseMat.cpp:231-451): the quasi-definite matrix
+   of a problem whose sparse constraints are a general CSR Jacobian A (nwcon x nvars,
+   rank-local: ParOptSparseProblem, ParOptProblem.h:301-407).  What createQuasiDefMat()
+   returns for such a problem.
+     create      pattern rowp[nwcon + 1], cols[nnz] (host; any column order inside a row, no
+                 duplicates); symbolic Cholesky of K = C + A D^-1 A^T on the host.
+                 ordering: 0 natural, 1 minimum degree.  ctx may be NULL: symbolic data
+                 only (pcu_sparsemat_symbolic / _info), no device calls.
+     set_data    the nnz Jacobian values in CSR order (host array; what
+                 getSparseJacobianData returns after evalSparseObjConGradient)
+     factor      K assembled and factored on the device; 0 = ok, k > 0 = non-positive pivot
+                 in constraint k - 1, < 0 = bad arguments.  Dinv is kept by reference.
+     apply3/4    yw = K^-1 (bw - A D^-1 bx), yx = D^-1 (bx + A^T yw)   (bw = 0 for apply3)
+     mult_add, mult_transpose_add
+                 out += alpha A px, out += alpha A^T pzw: ParOptSparseProblem's
+                 addSparseJacobian / addSparseJacobianTranspose (ParOptProblem.cpp:756-816) */
+typedef struct pcu_sparsemat pcu_sparsemat;
+pcu_sparsemat *pcu_sparsemat_create(pcu_ctx *ctx, int nvars, int nwcon, const int *rowp,
+                                    const int *cols, int ordering);
+void pcu_sparsemat_destroy(pcu_sparsemat *mat);
+int pcu_sparsemat_set_data(pcu_sparsemat *mat, const double *data);
+double *pcu_sparsemat_data_device_ptr(pcu_sparsemat *mat);
+int pcu_sparsemat_factor(pcu_sparsemat *mat, pcu_vec *x, pcu_vec *Dinv, pcu_vec *Cdiag);
+int pcu_sparsemat_apply3(pcu_sparsemat *mat, pcu_vec *bx, pcu_vec *yx, pcu_vec *yw);
+int pcu_sparsemat_apply4(pcu_sparsemat *mat, pcu_vec *bx, pcu_vec *bw, pcu_vec *yx,
+                         pcu_vec *yw);
+int pcu_sparsemat_mult_add(pcu_sparsemat *mat, double alpha, pcu_vec *px, pcu_vec *out);
+int pcu_sparsemat_mult_transpose_add(pcu_sparsemat *mat, double alpha, pcu_vec *pzw,
+                                     pcu_vec *out);
+/* nnz of the lower triangles of K and of L, levels of the elimination tree, kernel
+   launches of one factorisation (getFactorInfo, ParOptSparseMat.cpp:430-451)            */
+int pcu_sparsemat_info(pcu_sparsemat *mat, int *nnzK, int *nnzL, int *nlevels,
+                       int *nlaunches);
+/* The symbolic factorisation as host arrays (sizes from pcu_sparsemat_info: perm nwcon,
+   Lp nwcon + 1, Li nnzL, Rp nwcon + 1, Rk / Rpos nnzL - nwcon, kpos / ka / kb nnzK,
+   level_ptr nlevels + 1, level_cols nwcon); NULL outputs are skipped.                   */
+int pcu_sparsemat_symbolic(pcu_sparsemat *mat, int *perm, int *Lp, int *Li, int *Rp, int *Rk,
+                           int *Rpos, int *kpos, int *ka, int *kb, int *level_ptr,
+                           int *level_cols);
+
 /* ---- ParOptCompactQuasiNewton (ParOptLBFGS / ParOptLSR1) as a stand-alone object
    (ParOptQuasiNewton.h:32-213): what ParOptInteriorPoint::setQuasiNewton or the
    trust-region front end is handed.  qn_type "bfgs" | "sr1".

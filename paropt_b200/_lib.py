@@ -116,6 +116,17 @@ SIGNATURES = {
     "pcu_vec_mdot": (C.c_int, [VP, C.POINTER(VP), C.c_int, c_double_p]),
     "pcu_blockmat_create": (VP, [VP, C.c_int, C.POINTER(Weighting)]),
     "pcu_blockmat_create_blocks": (VP, [VP, C.c_int, C.POINTER(BlockWeighting)]),
+    "pcu_sparsemat_create": (VP, [VP, C.c_int, C.c_int, c_int_p, c_int_p, C.c_int]),
+    "pcu_sparsemat_destroy": (None, [VP]),
+    "pcu_sparsemat_set_data": (C.c_int, [VP, c_double_p]),
+    "pcu_sparsemat_data_device_ptr": (c_double_p, [VP]),
+    "pcu_sparsemat_factor": (C.c_int, [VP, VP, VP, VP]),
+    "pcu_sparsemat_apply3": (C.c_int, [VP, VP, VP, VP]),
+    "pcu_sparsemat_apply4": (C.c_int, [VP, VP, VP, VP, VP]),
+    "pcu_sparsemat_mult_add": (C.c_int, [VP, C.c_double, VP, VP]),
+    "pcu_sparsemat_mult_transpose_add": (C.c_int, [VP, C.c_double, VP, VP]),
+    "pcu_sparsemat_info": (C.c_int, [VP, c_int_p, c_int_p, c_int_p, c_int_p]),
+    "pcu_sparsemat_symbolic": (C.c_int, [VP] + [c_int_p] * 11),
     "pcu_blockmat_destroy": (None, [VP]),
     "pcu_blockmat_factor": (C.c_int, [VP, VP, VP, VP]),
     "pcu_blockmat_apply3": (C.c_int, [VP, VP, VP, VP]),

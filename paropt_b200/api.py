@@ -261,6 +261,64 @@ class QuasiDefBlockMat:
             self.h = None
 
 
+class QuasiDefSparseMat:
+    """ParOptQuasiDefSparseMat (ParOptSparseMat.cpp:231-451) for a CSR constraint Jacobian
+    (rowp, cols; ParOptSparseProblem.setSparseJacobianData): K = C + A D^-1 A^T assembled
+    and factored on the device (pcu_sparsemat).  ordering: "minimum_degree" | "natural"."""
+
+    def __init__(self, ctx, nvars, nwcon, rowp, cols, ordering="minimum_degree"):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.nvars, self.nwcon = int(nvars), int(nwcon)
+        rowp = np.ascontiguousarray(rowp, dtype=np.int32)
+        cols = np.ascontiguousarray(cols if len(cols) else [0], dtype=np.int32)
+        self.nnz = int(rowp[-1])
+        self.h = self.lib.pcu_sparsemat_create(
+            ctx.h, self.nvars, self.nwcon, rowp.ctypes.data_as(_lib.c_int_p),
+            cols.ctypes.data_as(_lib.c_int_p), 1 if ordering == "minimum_degree" else 0)
+        if not self.h:
+            raise RuntimeError("paropt_b200: pcu_sparsemat_create failed")
+
+    def set_data(self, data):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        if data.size != self.nnz:
+            raise ValueError("expected %d Jacobian values" % self.nnz)
+        if self.nnz:
+            _check(self.lib.pcu_sparsemat_set_data(self.h, data.ctypes.data_as(_lib.c_double_p)),
+                   "set_data")
+
+    def factor(self, x, Dinv, Cdiag):
+        """0 = ok, k > 0: non-positive pivot in constraint k - 1."""
+        rc = int(self.lib.pcu_sparsemat_factor(self.h, x.h if x is not None else None,
+                                               Dinv.h, Cdiag.h))
+        if rc < 0:
+            raise RuntimeError("paropt_b200: pcu_sparsemat_factor: bad arguments")
+        return rc
+
+    def apply(self, bx, *rest):
+        if len(rest) == 2:
+            _check(self.lib.pcu_sparsemat_apply3(self.h, bx.h, rest[0].h, rest[1].h), "apply")
+        else:
+            bw, yx, yw = rest
+            _check(self.lib.pcu_sparsemat_apply4(self.h, bx.h, bw.h, yx.h, yw.h), "apply")
+
+    def mult_add(self, alpha, px, out):
+        _check(self.lib.pcu_sparsemat_mult_add(self.h, float(alpha), px.h, out.h), "mult_add")
+
+    def mult_transpose_add(self, alpha, pzw, out):
+        _check(self.lib.pcu_sparsemat_mult_transpose_add(self.h, float(alpha), pzw.h, out.h),
+               "mult_transpose_add")
+
+    def info(self):
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.pcu_sparsemat_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return dict(nnzK=a.value, nnzL=b.value, levels=c.value, launches=d.value)
+
+    def free(self):
+        if self.h:
+            self.lib.pcu_sparsemat_destroy(self.h)
+            self.h = None
+
+
 class QuasiNewton:
     """ParOptLBFGS / ParOptLSR1 (ParOptQuasiNewton.h:76-213; ParOpt.pyx LBFGS/LSR1)."""
 

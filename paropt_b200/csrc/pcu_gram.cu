@@ -449,16 +449,19 @@ static int launch_gram_fast(pcu_ctx *ctx, const ColTable &cols, int m,
   }
 }
 
-template <int NT, int NWC, int NCW>
+template <int NT, int NWC, int NCW, int RPW>
 static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
                              const double *Dinv, const double *Cw, const WDesc &w,
                              long long n, double *result, int ld, const double *d2,
-                             int rhs_col, long long *rows_done, long long *skip_lo) {
+                             int rhs_col, long long *rows_done, long long *skip_lo,
+                             int *slab_rows) {
   constexpr int NP = (NT * (NT + 1)) / 2;
-  constexpr int ROWS = PCU_GT_ROWS(NCW);
-  int stage_bytes = (m + 1) * PCU_GT_COLB(NCW) + 2 * ROWS;
+  constexpr int ROWS = RPW * NCW;
+  *slab_rows = ROWS;
+  int stage_bytes = (m + 1) * (ROWS * 8 + 64) + 2 * ROWS;
   stage_bytes = (stage_bytes + 127) / 128 * 128;
-  int nstages = (208 * 1024) / stage_bytes;
+  // 227 KB per block less the kernel's 8.3 KB of static shared memory
+  int nstages = (214 * 1024) / stage_bytes;
   if (nstages > PCU_GT_MAXSTAGES) nstages = PCU_GT_MAXSTAGES;
   if (nstages < 2) return -1;
   if (const char *e = getenv("PCU_GT_STAGES")) {
@@ -480,7 +483,7 @@ static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
   static int attr_smem_dev[PCU_MAX_DEVICES] = {0};  // per device (function attribute)
   int &attr_smem = attr_smem_dev[ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0];
   if (smem > attr_smem || ctx->device >= PCU_MAX_DEVICES) {
-    PCU_CUDA_OK(cudaFuncSetAttribute(gram_tma_kernel<NT, NWC, NCW>,
+    PCU_CUDA_OK(cudaFuncSetAttribute(gram_tma_kernel<NT, NWC, NCW, RPW>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
@@ -488,7 +491,7 @@ static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
   if (nslabs < grid) grid = (int)nslabs;
   if (ctx->big_reserve(0, (size_t)grid * NP * 64)) return 1;
   ctx->prof_begin("gram_kernel");
-  gram_tma_kernel<NT, NWC, NCW><<<grid, PCU_GT_THREADS_T(NCW), smem, ctx->stream>>>(
+  gram_tma_kernel<NT, NWC, NCW, RPW><<<grid, PCU_GT_THREADS_T(NCW), smem, ctx->stream>>>(
       cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, nstages, stage_bytes,
       ctx->d_big_partials, ctx->d_counter, result, ld, d2, rhs_col);
   ctx->prof_end();
@@ -501,12 +504,20 @@ static int launch_gram_tma(pcu_ctx *ctx, const ColTable &cols, int m,
                            const double *Dinv, const double *Cw, const WDesc &w,
                            long long n, double *result, int ld, const double *d2,
                            int rhs_col, int nt, int nwc, long long *rows_done,
-                           long long *skip_lo) {
-#define PCU_GT_ARGS ctx, cols, m, Dinv, Cw, w, n, result, ld, d2, rhs_col, rows_done, skip_lo
-#define PCU_GT_CASE(NT_, NCW_)                                          \
-  case NT_:                                                             \
-    return nwc == 0 ? launch_gram_tma_t<NT_, 0, NCW_>(PCU_GT_ARGS)      \
-                    : launch_gram_tma_t<NT_, 8, NCW_>(PCU_GT_ARGS);
+                           long long *skip_lo, int *slab_rows) {
+#define PCU_GT_ARGS \
+  ctx, cols, m, Dinv, Cw, w, n, result, ld, d2, rhs_col, rows_done, skip_lo, slab_rows
+#define PCU_GT_CASE(NT_, NCW_)                                              \
+  case NT_:                                                                 \
+    return nwc == 0 ? launch_gram_tma_t<NT_, 0, NCW_, 32>(PCU_GT_ARGS)      \
+                    : launch_gram_tma_t<NT_, 8, NCW_, 32>(PCU_GT_ARGS);
+  // 17-24 columns with 16 consumer warps: 24 rows per warp make a stage 73 KB instead
+  // of 97 KB, and three of them fit (PCU_GT_RPW=32 restores the two-stage ring)
+  static const int rpw3 = getenv("PCU_GT_RPW") ? atoi(getenv("PCU_GT_RPW")) : PCU_GT_RPW3;
+  if (nt == 3 && rpw3 == 24) {
+    return nwc == 0 ? launch_gram_tma_t<3, 0, 16, 24>(PCU_GT_ARGS)
+                    : launch_gram_tma_t<3, 8, 16, 24>(PCU_GT_ARGS);
+  }
   switch (nt) {
     PCU_GT_CASE(1, 16)
     PCU_GT_CASE(2, 16)
@@ -639,11 +650,12 @@ int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
     // bulk-copy staged kernel on the whole slabs, general kernel on the slab that
     // straddles the end of the weighting blocks and on the tail
     long long rows_done = 0, skip_lo = -1;
+    int slab_rows = 0;
     rc = launch_gram_tma(ctx, cols, m, Dinv, Cw, w, n, R, ld, d2, rhs_col, nt,
-                         w.mode == 0 ? 0 : 8, &rows_done, &skip_lo);
+                         w.mode == 0 ? 0 : 8, &rows_done, &skip_lo, &slab_rows);
     if (rc) return 1;
     if (skip_lo >= 0) {
-      const long long hi = skip_lo + (nt <= 3 ? PCU_GT_ROWS(16) : PCU_GT_ROWS(8));
+      const long long hi = skip_lo + slab_rows;
       rc = gram_range_accumulate(ctx, cols, m, Dinv, Cw, w, skip_lo, hi, R, ld, nt, d2,
                                  rhs_col);
       if (rc) return rc;

@@ -25,6 +25,9 @@
 #define PCU_GT_THREADS_T(NCW) (32 * ((NCW) + PCU_GT_NPW))
 #define PCU_GT_COLB(NCW) (PCU_GT_ROWS(NCW) * 8 + 64)  // bytes per staged column (+64: bank shift)
 #define PCU_GT_MAXSTAGES 6
+#ifndef PCU_GT_RPW3
+#define PCU_GT_RPW3 32  // rows per consumer warp of the 17-24 column kernel (32 or 24)
+#endif
 
 __device__ __forceinline__ unsigned gt_smem_u32(const void *p) {
   return (unsigned)__cvta_generic_to_shared(p);
@@ -65,7 +68,9 @@ __device__ __forceinline__ void gt_bulk_g2s(unsigned dst, const void *src,
 // NWC: 0 = no weighting correction, 8 = blocks of exactly 8 rows.
 // Slabs [0, slab_con) lie inside the weighting blocks, slab `slab_skip` (if >= 0)
 // straddles their end and is skipped, slabs up to nslabs are plain.
-template <int NT, int NWC, int NCW>
+// RPW: rows of a slab per consumer warp (32, or 24 = three blocks of 8: smaller
+// stages, so that a third one fits for the 22-24 column passes).
+template <int NT, int NWC, int NCW, int RPW>
 __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
     gram_tma_kernel(const ColTable cols, const int m,
                     const double *__restrict__ Dinv,
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
                     const int ld, const double *__restrict__ d2,
                     const int rhs_col) {
   constexpr int NP = (NT * (NT + 1)) / 2;
-  constexpr int ROWS = PCU_GT_ROWS(NCW), COLB = PCU_GT_COLB(NCW);
+  constexpr int ROWS = RPW * NCW, COLB = ROWS * 8 + 64;
   extern __shared__ __align__(128) unsigned char gt_smem[];
   __shared__ __align__(8) unsigned long long gt_full[PCU_GT_MAXSTAGES];
   __shared__ __align__(8) unsigned long long gt_empty[PCU_GT_MAXSTAGES];
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
     const bool rhs_lane = (rhs_col >= 0) && (8 * (NT - 1) + gi == rhs_col);
     const double c1 = w.coef_rest;
     const double dc = (kk == 0) ? (w.coef0 - w.coef_rest) : 0.0;
-    const int rowb = (warp * 32 + 2 * kk) * 8;  // byte offset of the lane's first row
+    const int rowb = (warp * RPW + 2 * kk) * 8;  // byte offset of the lane's first row
 
     long long it = 0;
     for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
 #pragma unroll
       for (int t = 0; t < NT; t++) h[t] = 0.0;
 #pragma unroll
-      for (int step = 0; step < 4; step++) {
+      for (int step = 0; step < RPW / 8; step++) {
         const int ro = rowb + step * 64;
         const double2 wv = *reinterpret_cast<const double2 *>(st + off_dinv + ro);
         double2 fb[NT], fa[NT];
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
               u[t] += shfl_xor_d(u[t], 2);
             }
             if (kk == step) {  // park it in k-slot `step`
-              const int bi = warp * 4 + step;
+              const int bi = warp * (RPW / 8) + step;
               hcw = *reinterpret_cast<const double *>(st + off_cw + bi * 8);
               if (rhs_lane) hd = *reinterpret_cast<const double *>(st + off_d2 + bi * 8);
 #pragma unroll
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
         }
       }
       if (NWC != 0) {
-        if (in_con) {  // one correction DMMA set for the warp's four blocks
+        if (in_con) {  // one correction DMMA set for the warp's RPW / 8 blocks
           int pp = 0;
 #pragma unroll
           for (int ti = 0; ti < NT; ti++) {
