@@ -29,7 +29,7 @@ def driver_args(cfg):
     if cfg["kind"] == "rosenbrock":
         args += ["problem=rosenbrock", "n=%d" % cfg["problem"]["n"]]
     else:
-        args += ["problem=sepquad"]
+        args += ["problem=" + cfg["kind"]]  # sepquad | sparsequad
         for k, v in cfg["problem"].items():
             key = "n" if k == "ntotal" else k
             args.append("%s=%r" % (key, v))
@@ -201,6 +201,16 @@ def main():
                 json.dump(data, fp, separators=(",", ":"))
             print(fname, "niter", data["final"]["niter"], data["status"],
                   "nhvec", data["history"][-1]["nhvec"])
+        return
+    if "--sparse" in sys.argv:
+        # a ParOptSparseProblem (general CSR sparse constraints,
+        # ParOptQuasiDefSparseMat + the reference's sparse Cholesky)
+        data = run_reference(configs.small("S1"))
+        data["generator"] = ("oracle/make_golden.py --sparse (oracle/_ref/ref_driver, unmodified "
+                             "reference, ParOptSparseProblem / ParOptQuasiDefSparseMat)")
+        with open(os.path.join(out_dir, "S1_small.json"), "w") as fp:
+            json.dump(data, fp, separators=(",", ":"))
+        print("S1_small.json", "niter", data["final"]["niter"], data["status"])
         return
     if "--full-c4" in sys.argv:
         # the dense-constraint stress config at its FULL size (n = 32M, c = 100, L-SR1

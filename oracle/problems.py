@@ -174,3 +174,121 @@ class Rosenbrock:
         Ac[1][:] = 0.0
         Ac[1][::2] = 1.0
         return 0
+
+
+class CSRWeighting:
+    """The sparse-constraint callbacks of ParOptSparseProblem (ParOptProblem.cpp:734-816):
+    evalSparseCon returns the values cached by the last evalObjCon (whatever x is passed),
+    the products use the Jacobian values of the last gradient evaluation."""
+
+    def __init__(self, prob):
+        self.prob = prob
+
+    def eval(self, x):
+        return self.prob.cw.copy()
+
+    def add_jac(self, alpha, px, out):
+        out += alpha * (self.prob.jac() @ px)
+
+    def add_jac_t(self, alpha, pzw, out):
+        out += alpha * (self.prob.jac().T @ pzw)
+
+
+class SparseMatOracle:
+    """ParOptQuasiDefSparseMat (SM.cpp:231-451) with a dense Cholesky of
+    K = C + A D^-1 A^T (the reference's sparse Cholesky is an exact factorisation too)."""
+
+    def __init__(self, prob):
+        self.prob = prob
+
+    def factor(self, Dinv, C):
+        import scipy.linalg as sla
+        self.Dinv = Dinv
+        self.A = self.prob.jac().copy()
+        K = np.diag(C) + (self.A * Dinv) @ self.A.T
+        try:
+            self.chol = sla.cho_factor(K)
+        except Exception:
+            return 1
+        return 0
+
+    def apply(self, bx, bw=None):
+        import scipy.linalg as sla
+        rhs = -(self.A @ (self.Dinv * bx))
+        if bw is not None:
+            rhs = bw + rhs
+        yw = sla.cho_solve(self.chol, rhs) if rhs.size else rhs
+        yx = self.Dinv * (bx + self.A.T @ yw)
+        return yx, yw
+
+
+class SparseQuad:
+    """oracle/ref_driver.cpp class SparseQuad: separable quadratic objective, dense linear
+    constraints, W = (n - 1) / 3 sparse constraints cw_i = rad - sum_k w_ik (x_j - xc)^2
+    over the columns 3i .. 3i+3 (+ (7i + 11) mod n for i % 5 == 0).  Single rank."""
+
+    RAD, XC = 1.0, 0.3
+
+    def __init__(self, comm=None, **p):
+        defaults = dict(ntotal=400, ncon=1, nw=0, seed=0, lam_min=1.0, lam_max=10.0,
+                        b_lo=-2.0, b_w=0.0, a_lo=0.0, a_w=-1.0, beta_c=0.0, beta_n=0.6,
+                        beta_u=0.0, x0_lo0=0.3, x0_w0=0.2, lb0=-1.0, ub0=1.5)
+        defaults.update(p)
+        self.p = p = defaults
+        n = self.nvars = int(p["ntotal"])
+        W = self.nwcon = (n - 1) // 3
+        self.ncon = int(p["ncon"])
+        self.ninequality, self.nwinequality = self.ncon, W
+        rowp, cols = [0], []
+        for i in range(W):
+            cols += [3 * i + k for k in range(4)]
+            if i % 5 == 0:
+                far = (7 * i + 11) % n
+                if far < 3 * i or far > 3 * i + 3:
+                    cols.append(far)
+            rowp.append(len(cols))
+        self.rowp = np.array(rowp, dtype=np.int32)
+        self.cols = np.array(cols, dtype=np.int32)
+        self.rowid = np.repeat(np.arange(W), np.diff(self.rowp))
+        seed = p["seed"]
+        self.wk = 0.5 + uniform01(stream_key(seed, 9), np.arange(len(cols)))
+        gi = np.arange(n)
+        self.lam = p["lam_min"] + (p["lam_max"] - p["lam_min"]) * uniform01(stream_key(seed, 1), gi)
+        self.b = p["b_lo"] + p["b_w"] * uniform01(stream_key(seed, 2), gi)
+        self.A = [p["a_lo"] + p["a_w"] * uniform01(stream_key(seed, 100 + j), gi)
+                  for j in range(self.ncon)]
+        self.beta = np.array([p["beta_c"] + p["beta_n"] * float(n)
+                              + p["beta_u"] * float(uniform01(stream_key(seed, 5), np.uint64(j)))
+                              for j in range(self.ncon)])
+        self.x0 = p["x0_lo0"] + p["x0_w0"] * uniform01(stream_key(seed, 3), gi)
+        self.data = np.zeros(len(cols))
+        self.cw = np.zeros(W)
+        self.weighting = CSRWeighting(self)
+
+    def make_mat(self):
+        return SparseMatOracle(self)
+
+    def jac(self):
+        J = np.zeros((self.nwcon, self.nvars))
+        J[self.rowid, self.cols] = self.data
+        return J
+
+    def getVarsAndBounds(self, x, lb, ub):
+        x[:] = self.x0
+        lb[:] = self.p["lb0"]
+        ub[:] = self.p["ub0"]
+
+    def evalObjCon(self, x):
+        f = float(np.sum(0.5 * self.lam * x * x + self.b * x))
+        con = self.beta + np.array([np.dot(a, x) for a in self.A])
+        d = x[self.cols] - self.XC
+        self.cw = self.RAD - np.bincount(self.rowid, weights=self.wk * d * d,
+                                         minlength=self.nwcon)
+        return 0, f, con
+
+    def evalObjConGradient(self, x, g, Ac):
+        g[:] = self.lam * x + self.b
+        for j in range(self.ncon):
+            Ac[j][:] = self.A[j]
+        self.data = -2.0 * self.wk * (x[self.cols] - self.XC)
+        return 0

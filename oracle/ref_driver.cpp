@@ -504,6 +504,166 @@ class SepQuad : public HistoryProblem {
 };
 
 // ---------------------------------------------------------------------------
+// sparsequad: a ParOptSparseProblem (ParOptProblem.h:301-407) -- general CSR sparse
+// constraints, ParOptQuasiDefSparseMat + the reference's sparse Cholesky.
+//   f = sum 1/2 lam_i x_i^2 + b_i x_i,   c_j = beta_j + a_j . x >= 0 (dense, as sepquad),
+//   cw_i = rad - sum_k w_ik (x_{j(i,k)} - xc)^2 >= 0,   i < W = (n - 1) / 3,
+//   j(i, .) = 3i, 3i+1, 3i+2, 3i+3 (neighbouring rows share a variable: K = C + A D^-1 A^T
+//   is tridiagonal) and, for i % 5 == 0, the long-range column (7i + 11) mod n (fill).
+// The Jacobian values -2 w_ik (x - xc) change with x: every factorisation sees new data.
+// Single rank (the reference's sparse path is serial per rank).
+// ---------------------------------------------------------------------------
+class Recorder : public HistoryProblem {  // the history hook without a problem of its own
+ public:
+  Recorder(MPI_Comm comm) : HistoryProblem(comm) {}
+  ParOptQuasiDefMat *createQuasiDefMat() { return NULL; }
+  void getVarsAndBounds(ParOptVec *, ParOptVec *, ParOptVec *) {}
+  int evalObjCon(ParOptVec *, ParOptScalar *, ParOptScalar *) { return 1; }
+  int evalObjConGradient(ParOptVec *, ParOptVec *, ParOptVec **) { return 1; }
+};
+
+class SparseQuad : public ParOptSparseProblem {
+ public:
+  SparseQuad(MPI_Comm comm, const SepQuadParams &params) : ParOptSparseProblem(comm) {
+    p = params;
+    rec = new Recorder(comm);
+    rec->incref();
+    n = (int)p.ntotal;
+    W = (n - 1) / 3;
+    setProblemSizes(n, p.ncon, W);
+    setNumInequalities(p.ncon, W);
+    std::vector<int> rowp(W + 1, 0), cols;
+    for (int i = 0; i < W; i++) {
+      for (int k = 0; k < 4; k++) cols.push_back(3 * i + k);
+      if (i % 5 == 0) {
+        const int far = (int)((7L * i + 11) % n);
+        if (far < 3 * i || far > 3 * i + 3) cols.push_back(far);
+      }
+      rowp[i + 1] = (int)cols.size();
+    }
+    setSparseJacobianData(rowp.data(), cols.data());
+    wk.resize(cols.size());
+    uint64_t kw = stream_key(p.seed, 9);
+    for (size_t e = 0; e < cols.size(); e++) wk[e] = 0.5 + uniform01(kw, (uint64_t)e);
+    lam.resize(n);
+    b.resize(n);
+    uint64_t klam = stream_key(p.seed, 1), kb = stream_key(p.seed, 2);
+    for (int i = 0; i < n; i++) {
+      lam[i] = p.lam_min + (p.lam_max - p.lam_min) * uniform01(klam, (uint64_t)i);
+      b[i] = p.b_lo + p.b_w * uniform01(kb, (uint64_t)i);
+    }
+    beta.resize(p.ncon);
+    uint64_t kbeta = stream_key(p.seed, 5);
+    for (int j = 0; j < p.ncon; j++)
+      beta[j] = p.beta_c + p.beta_n * (double)p.ntotal + p.beta_u * uniform01(kbeta, (uint64_t)j);
+#ifdef PCU_ADAPTERS
+    cmat = NULL;
+#endif
+  }
+  ~SparseQuad() { rec->decref(); }
+  static double rad() { return 1.0; }
+  static double xc() { return 0.3; }
+
+#ifdef PCU_ADAPTERS
+  ParOptVec *createDesignVec() { return new ParOptCudaVec(ParOptCudaContext(), n); }
+  ParOptVec *createConstraintVec() { return new ParOptCudaVec(ParOptCudaContext(), W); }
+  ParOptQuasiDefMat *createQuasiDefMat() {
+    cmat = new ParOptCudaQuasiDefSparseMat(ParOptCudaContext(), this);
+    return cmat;
+  }
+  // the two CSR products on the device (the values are the ones of the last factor():
+  // the optimizer factors after every gradient evaluation and before any product)
+  void addSparseJacobian(ParOptScalar alpha, ParOptVec *x, ParOptVec *px, ParOptVec *out) {
+    if (!cmat) return ParOptSparseProblem::addSparseJacobian(alpha, x, px, out);
+    sync_data();
+    PCU_ADAPTER_CHECK(pcu_sparsemat_mult_add(cmat->mat, alpha, ParOptCudaVec::handle(px),
+                                             ParOptCudaVec::handle(out)));
+  }
+  void addSparseJacobianTranspose(ParOptScalar alpha, ParOptVec *x, ParOptVec *pzw,
+                                  ParOptVec *out) {
+    if (!cmat) return ParOptSparseProblem::addSparseJacobianTranspose(alpha, x, pzw, out);
+    sync_data();
+    PCU_ADAPTER_CHECK(pcu_sparsemat_mult_transpose_add(
+        cmat->mat, alpha, ParOptCudaVec::handle(pzw), ParOptCudaVec::handle(out)));
+  }
+  void sync_data() {
+    if (!data_dirty) return;
+    const ParOptScalar *data = NULL;
+    getSparseJacobianData(NULL, NULL, &data);
+    PCU_ADAPTER_CHECK(pcu_sparsemat_set_data(cmat->mat, data));
+    data_dirty = 0;
+  }
+  ParOptCudaQuasiDefSparseMat *cmat;
+#endif
+  int data_dirty = 1;
+
+  void writeOutput(int iter, ParOptVec *xvec) { rec->writeOutput(iter, xvec); }
+
+  void getVarsAndBounds(ParOptVec *xvec, ParOptVec *lbvec, ParOptVec *ubvec) {
+    double *x, *lb, *ub;
+    xvec->getArray(&x);
+    lbvec->getArray(&lb);
+    ubvec->getArray(&ub);
+    uint64_t kx = stream_key(p.seed, 3);
+    for (int i = 0; i < n; i++) {
+      x[i] = p.x0_lo[0] + p.x0_w[0] * uniform01(kx, (uint64_t)i);
+      lb[i] = p.lb[0];
+      ub[i] = p.ub[0];
+    }
+  }
+  int evalSparseObjCon(ParOptVec *xvec, ParOptScalar *fobj, ParOptScalar *cons,
+                       ParOptVec *sparse_con) {
+    double *x, *cw;
+    xvec->getArray(&x);
+    sparse_con->getArray(&cw);
+    double f = 0.0;
+    for (int i = 0; i < n; i++) f += 0.5 * lam[i] * x[i] * x[i] + b[i] * x[i];
+    *fobj = f;
+    for (int j = 0; j < p.ncon; j++) {
+      uint64_t key = stream_key(p.seed, 100 + (uint64_t)j);
+      double sum = 0.0;
+      for (int i = 0; i < n; i++) sum += (p.a_lo + p.a_w * uniform01(key, (uint64_t)i)) * x[i];
+      cons[j] = beta[j] + sum;
+    }
+    const int *rowp, *cols;
+    getSparseJacobianData(&rowp, &cols, NULL);
+    for (int i = 0; i < W; i++) {
+      double sum = 0.0;
+      for (int e = rowp[i]; e < rowp[i + 1]; e++) {
+        const double d = x[cols[e]] - xc();
+        sum += wk[e] * d * d;
+      }
+      cw[i] = rad() - sum;
+    }
+    return 0;
+  }
+  int evalSparseObjConGradient(ParOptVec *xvec, ParOptVec *gvec, ParOptVec **Ac,
+                               ParOptScalar *data) {
+    double *x, *g;
+    xvec->getArray(&x);
+    gvec->getArray(&g);
+    for (int i = 0; i < n; i++) g[i] = lam[i] * x[i] + b[i];
+    for (int j = 0; j < p.ncon; j++) {
+      double *a;
+      Ac[j]->getArray(&a);
+      uint64_t key = stream_key(p.seed, 100 + (uint64_t)j);
+      for (int i = 0; i < n; i++) a[i] = p.a_lo + p.a_w * uniform01(key, (uint64_t)i);
+    }
+    const int *rowp, *cols;
+    getSparseJacobianData(&rowp, &cols, NULL);
+    for (int i = 0; i < W; i++)
+      for (int e = rowp[i]; e < rowp[i + 1]; e++) data[e] = -2.0 * wk[e] * (x[cols[e]] - xc());
+    data_dirty = 1;
+    return 0;
+  }
+
+  SepQuadParams p;
+  Recorder *rec;
+  int n, W;
+  std::vector<double> wk, lam, b, beta;
+};
+
+// ---------------------------------------------------------------------------
 // rosenbrock: same mathematical problem as the class in
 // /root/reference/examples/rosenbrock/rosenbrock.cpp:9-199 (scale = 1)
 // ---------------------------------------------------------------------------
@@ -672,14 +832,21 @@ int main(int argc, char *argv[]) {
     }
   }
 
-  HistoryProblem *prob = NULL;
+  HistoryProblem *prob = NULL;      // history hook + bookkeeping
+  ParOptProblem *opt_prob = NULL;   // what the optimizer sees
   if (problem == "rosenbrock") {
     // rosenbrock.cpp:225-229: nvars-1 variables, nwcon=5, nw=5, start 1, skip 1
     prob = new Rosen(comm, rosen_n - 1, 5, 1, 5, 1);
+  } else if (problem == "sparsequad") {
+    SparseQuad *sq = new SparseQuad(comm, p);
+    sq->incref();
+    prob = sq->rec;
+    opt_prob = sq;
   } else {
     prob = new SepQuad(comm, p);
   }
   prob->incref();
+  if (!opt_prob) opt_prob = prob;
 
   ParOptOptions *options = new ParOptOptions(comm);
   if (algorithm == "tr") ParOptOptimizer::addDefaultOptions(options);
@@ -720,7 +887,7 @@ int main(int argc, char *argv[]) {
     // the configuration of examples/rosenbrock/rosenbrock.cpp:234-242)
     prob->tr_mode = 1;
     if (rank == 0 && !hist_path.empty()) prob->hist = fopen(hist_path.c_str(), "w");
-    ParOptOptimizer *opt = new ParOptOptimizer(prob, options);
+    ParOptOptimizer *opt = new ParOptOptimizer(opt_prob, options);
     opt->incref();
     double t0 = MPI_Wtime();
     opt->optimize();
@@ -741,7 +908,7 @@ int main(int argc, char *argv[]) {
     return 0;
   }
 
-  ParOptInteriorPoint *ip = new ParOptInteriorPoint(prob, options);
+  ParOptInteriorPoint *ip = new ParOptInteriorPoint(opt_prob, options);
   ip->incref();
   prob->ip = ip;
 #ifdef PCU_ADAPTERS
@@ -750,7 +917,7 @@ int main(int argc, char *argv[]) {
     const char *qn_type = options->getEnumOption("qn_type");
     if (strcmp(qn_type, "bfgs") == 0 || strcmp(qn_type, "sr1") == 0) {
       int nv, nc, nw;
-      prob->getProblemSizes(&nv, &nc, &nw);
+      opt_prob->getProblemSizes(&nv, &nc, &nw);
       ParOptCudaCompactQN *cqn = new ParOptCudaCompactQN(
           ParOptCudaContext(), nv, qn_type, options->getIntOption("qn_subspace_size"));
       if (strcmp(options->getEnumOption("qn_update_type"), "damped_update") == 0)

@@ -46,6 +46,15 @@ CONFIGS = {
         options=dict(qn_type="sr1", qn_subspace_size=20, abs_res_tol=1e-8,
                      start_affine_multiplier_min=0.01),
     ),
+    # general sparse constraints (a ParOptSparseProblem: CSR
+    # Jacobian, ParOptQuasiDefSparseMat); oracle/ref_driver.cpp class SparseQuad
+    "S1": dict(
+        kind="sparsequad",
+        problem=dict(ntotal=400, ncon=1, seed=0, lam_min=1.0, lam_max=10.0, b_lo=-2.0,
+                     b_w=0.0, a_lo=0.0, a_w=-1.0, beta_c=0.0, beta_n=0.3, beta_u=0.0,
+                     x0_lo0=0.3, x0_w0=0.2, lb0=-1.0, ub0=1.5),
+        options=dict(qn_type="bfgs", qn_subspace_size=10),
+    ),
     # configs[4]: weak scaling, C2 with n = 16M per GPU
     "C5": dict(
         kind="sepquad",
@@ -68,7 +77,7 @@ def get(name, ntotal=None, **problem_overrides):
 
 
 def small(name):
-    sizes = {"C1": 1000, "C2": 20000, "C3": 16000, "C4": 12000, "C5": 20000}
+    sizes = {"C1": 1000, "C2": 20000, "C3": 16000, "C4": 12000, "C5": 20000, "S1": 400}
     cfg = get(name, sizes[name])
     if name == "C4":
         cfg["problem"]["ncon"] = 24

@@ -162,24 +162,33 @@ int symbolic(pcu_sparsemat *m, int ordering) {
     std::sort(Kcol[jn].begin(), Kcol[jn].end());
     m->nnzK += (int)Kcol[jn].size();
   }
+  bool fill_overflow = false;
   {
+    // the factor is addressed with 32-bit indices: give up beyond PCU_SPARSE_MAX_FILL
+    // entries (a bad ordering of a matrix with long-range couplings fills in completely)
+    const long long max_fill = 400000000LL;
+    long long total = 0;
     std::vector<int> mark(nw, -1);
-    for (int j = 0; j < nw; j++) {
+    for (int j = 0; j < nw && !fill_overflow; j++) {
       std::vector<int> &p = Lcol[j];
       for (int i : Kcol[j]) {
         mark[i] = j;
         p.push_back(i);
       }
-      for (int c : children[j])
+      for (int c : children[j]) {
         for (int i : Lcol[c])
           if (i != c && mark[i] != j) {
             mark[i] = j;
             p.push_back(i);
           }
+      }
       std::sort(p.begin(), p.end());
       if (p.size() > 1) children[p[1]].push_back(j);
+      total += (long long)p.size();
+      if (total > max_fill) fill_overflow = true;
     }
   }
+  if (fill_overflow) return 2;
   m->Lp.assign(nw + 1, 0);
   for (int j = 0; j < nw; j++) m->Lp[j + 1] = m->Lp[j] + (int)Lcol[j].size();
   m->Li.resize(m->Lp[nw]);
@@ -512,8 +521,12 @@ pcu_sparsemat *pcu_sparsemat_create(pcu_ctx *ctx, int nvars, int nwcon, const in
   m->nwcon = nwcon;
   m->rowp.assign(rowp, rowp + nwcon + 1);
   m->cols.assign(cols, cols + rowp[nwcon]);
-  if (symbolic(m, ordering)) {
-    fprintf(stderr, "paropt_b200: pcu_sparsemat_create: column index out of range or duplicate entry\n");
+  const int src = symbolic(m, ordering);
+  if (src) {
+    fprintf(stderr, src == 2 ? "paropt_b200: pcu_sparsemat_create: the Cholesky factor exceeds 4e8 entries "
+                               "with this ordering\n"
+                             : "paropt_b200: pcu_sparsemat_create: column index out of range or "
+                               "duplicate entry\n");
     delete m;
     return nullptr;
   }

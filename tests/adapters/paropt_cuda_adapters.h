@@ -8,6 +8,7 @@
 
     ParOptCudaVec               : ParOptVec                 (src/ParOptVec.h:53-70)
     ParOptCudaQuasiDefBlockMat  : ParOptQuasiDefMat         (src/ParOptSparseMat.h:18-62)
+    ParOptCudaQuasiDefSparseMat : ParOptQuasiDefMat         (src/ParOptSparseMat.h:106-188, CSR)
     ParOptCudaCompactQN         : ParOptCompactQuasiNewton  (src/ParOptQuasiNewton.h:32-67)
 
   and the three factory overrides a problem class adds (src/ParOptProblem.h:58,65,72).
@@ -162,6 +163,50 @@ class ParOptCudaQuasiDefBlockMat : public ParOptQuasiDefMat {
   pcu_blockmat *mat;
 };
 
+/* ParOptQuasiDefSparseMat (src/ParOptSparseMat.cpp:231-451) on the device, for a
+   ParOptSparseProblem (general CSR sparse constraints): what its createQuasiDefMat()
+   override returns.  Takes the Jacobian values the problem holds at every factor(), like
+   the reference (ParOptSparseMat.cpp:318-321). */
+class ParOptCudaQuasiDefSparseMat : public ParOptQuasiDefMat {
+ public:
+  ParOptCudaQuasiDefSparseMat(pcu_ctx *ctx, ParOptSparseProblem *problem) : prob(problem) {
+    int nv, nc, nw;
+    prob->getProblemSizes(&nv, &nc, &nw);
+    const int *rowp = NULL, *cols = NULL;
+    prob->getSparseJacobianData(&rowp, &cols, NULL);
+    mat = pcu_sparsemat_create(ctx, nv, nw, rowp, cols, 1);
+    if (!mat) abort();
+  }
+  ~ParOptCudaQuasiDefSparseMat() { pcu_sparsemat_destroy(mat); }
+  int factor(ParOptVec *x, ParOptVec *Dinv, ParOptVec *Cdiag) {
+    const ParOptScalar *data = NULL;
+    prob->getSparseJacobianData(NULL, NULL, &data);
+    PCU_ADAPTER_CHECK(pcu_sparsemat_set_data(mat, data));
+    return pcu_sparsemat_factor(mat, ParOptCudaVec::handle(x), ParOptCudaVec::handle(Dinv),
+                                ParOptCudaVec::handle(Cdiag));
+  }
+  void apply(ParOptVec *bx, ParOptVec *yx, ParOptVec *yw) {
+    PCU_ADAPTER_CHECK(pcu_sparsemat_apply3(mat, ParOptCudaVec::handle(bx),
+                                           ParOptCudaVec::handle(yx), ParOptCudaVec::handle(yw)));
+  }
+  void apply(ParOptVec *bx, ParOptVec *bw, ParOptVec *yx, ParOptVec *yw) {
+    PCU_ADAPTER_CHECK(pcu_sparsemat_apply4(mat, ParOptCudaVec::handle(bx),
+                                           ParOptCudaVec::handle(bw), ParOptCudaVec::handle(yx),
+                                           ParOptCudaVec::handle(yw)));
+  }
+  const char *getFactorInfo() {
+    int nk = 0, nl = 0, nlev = 0, nlaunch = 0;
+    pcu_sparsemat_info(mat, &nk, &nl, &nlev, &nlaunch);
+    snprintf(info, sizeof(info), "paropt_b200 sparse Cholesky (CUDA) nnz(K) %d nnz(L) %d levels %d",
+             nk, nl, nlev);
+    return info;
+  }
+  pcu_sparsemat *mat;
+
+ private:
+  ParOptSparseProblem *prob;
+  char info[160];
+};
 /* ParOptLBFGS / ParOptLSR1 on the device ("bfgs" | "sr1"). */
 class ParOptCudaCompactQN : public ParOptCompactQuasiNewton {
  public:

@@ -37,10 +37,13 @@ def run_adapter_driver(cfg, tmp_path):
 
 
 # C3_nb2_small: two sparse constraints per block -- the reference's ParOptQuasiDefBlockMat
-# with nwblock = 2 (packed-upper dpptrf / dpptrs) against pcu_blockmat_create_blocks
+# with nwblock = 2 (packed-upper dpptrf / dpptrs) against pcu_blockmat_create_blocks.
+# S1_small: a ParOptSparseProblem (general CSR sparse constraints) --
+# the reference's ParOptQuasiDefSparseMat + sparse Cholesky against pcu_sparsemat
+# (ParOptCudaQuasiDefSparseMat in oracle/ref_driver.cpp), the CSR products on the device.
 @pytest.mark.parametrize("name,iters", [("C1_small", None), ("C2_small", None),
                                         ("C3_small", None), ("C4_small", 11),
-                                        ("C3_nb2_small", 39)])
+                                        ("C3_nb2_small", 39), ("S1_small", None)])
 def test_reference_interior_point_runs_on_cuda_vectors(tmp_path, name, iters):
     if not os.path.exists(DRIVER):
         pytest.skip("oracle/_ref/adapter_driver not built (needs /root/reference at build time)")
