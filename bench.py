@@ -56,6 +56,18 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_fp64_tflops():
+    """cuBLAS DGEMM burst peak measured on this pool's B200 (scripts/measure_fp64_peak.py):
+    the denominator of the FP64-tensor roofline of the Gram pass (MEASURED_PEAKS.json has
+    no fp64 figure)."""
+    path = os.path.join(ROOT, "profiles", "r2b_fp64_peak.json")
+    try:
+        with open(path) as fp:
+            return float(json.load(fp)["fp64_dgemm_tflops_burst"]), "measured (profiles/r2b_fp64_peak.json, cuBLAS DGEMM 8192^3)"
+    except Exception:
+        return 40.0, "fallback (nominal B200 fp64 tensor peak)"
+
+
 # ---------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples nvidia-smi while the timed region runs (B200_PROFILING.md)."""
@@ -448,6 +460,20 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": words * 8 if words else None,
                 "kernels": {k: {"ms": round(v[0], 3), "launches": v[1]}
                             for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    if roof and roof["kernel"] == "gram_kernel" and words:
+        # the Gram pass S = V^T D0^-1 V over mcol = c + q (+ 1: right-hand side) columns:
+        # (mcol)(mcol + 1) N flops on the lower triangle the kernel computes; tensor-bound
+        # when its arithmetic intensity exceeds the ridge of the two measured peaks
+        tf_peak, tf_src = measured_fp64_tflops()
+        mcol = c + qn_size + 1
+        flops = float(mcol) * (mcol + 1) * N
+        ai = flops / (words * 8.0)
+        if ai > tf_peak * 1e12 / (peak * 1e9):
+            ach = flops / (roof["avg_launch_ms"] * 1e-3) / 1e12
+            roof.update({"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": ach / tf_peak, "peak_source": tf_src,
+                         "algorithmic_flops_per_launch": flops,
+                         "arithmetic_intensity_flop_per_byte": ai})
     iter_bytes = 8.0 * iteration_words(N, W, c, qn_size)
     user_ms = cb_ms
     solver_ms = max(ms_per_step - user_ms, 1e-9)
