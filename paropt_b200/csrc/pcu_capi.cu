@@ -244,6 +244,7 @@ int pcu_ip_reset_problem(pcu_ip *ip, pcu_problem *prob) {
     return 1;
   }
   ip->prob = prob;
+  ip->gaz_valid = 0;
   return 0;
 }
 
@@ -447,6 +448,7 @@ int pcu_ip_vars_dense_set(pcu_ip *ip, int which, const double *in5c) {
   const int c = ip->ncon;
   std::vector<double> *parts[5] = {&b->z, &b->s, &b->t, &b->zs, &b->zt};
   for (int k = 0; k < 5; k++) memcpy(parts[k]->data(), in5c + k * c, sizeof(double) * c);
+  ip->gaz_valid = 0;  // the multipliers z changed
   return 0;
 }
 

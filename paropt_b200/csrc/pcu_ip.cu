@@ -366,7 +366,7 @@ pcu_ip::~pcu_ip() {
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all)
     for (int i = 0; i < 8; i++) pcu_vec_destroy(vs->v[i]);
-  pcu_vec *single[] = {lb, ub, g, Dinv, Cw, d1, d2, t1, s_qn, y_qn, rx, rsw, rtw};
+  pcu_vec *single[] = {lb, ub, g, Dinv, Cw, d1, d2, t1, s_qn, y_qn, rx, rsw, rtw, gaz};
   for (auto v : single) pcu_vec_destroy(v);
   for (auto v : Ac) pcu_vec_destroy(v);
   for (auto v : gmres_W) pcu_vec_destroy(v);
@@ -406,6 +406,7 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
   if (getenv("PCU_NO_CHAIN")) opt_no_chain = 1;
   if (getenv("PCU_CHAIN")) opt_force_chain = 1;
   if (getenv("PCU_NO_UPDSTATS")) opt_no_updstats = 1;
+  if (getenv("PCU_NO_GAZ")) opt_no_gaz = 1;
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all) {
     for (int i = 0; i < 8; i++) {
@@ -590,6 +591,7 @@ int pcu_ip::evalObjCon(pcu_vec *x) {
 int pcu_ip::evalObjConGradient(pcu_vec *x, int same_point) {
   if (cb_begin()) return 1;
   prob->same_point_hint = same_point;
+  gaz_valid = 0;
   int fail = prob->evalObjConGradient(x, g, Ac.data());
   prob->same_point_hint = 0;
   ngeval++;

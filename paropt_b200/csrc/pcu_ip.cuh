@@ -137,6 +137,10 @@ struct pcu_ip {
   pcu_vec *d1 = nullptr, *d2 = nullptr, *t1 = nullptr;  // KKT-solve scratch
   pcu_vec *s_qn = nullptr, *y_qn = nullptr;
   pcu_vec *rx = nullptr, *rsw = nullptr, *rtw = nullptr;  // line-search trial
+  // g - A z at the current point, written by the last update pass (ncon >= 3): the first
+  // pass of the next KKT solve reads it instead of g and the ncon constraint gradients
+  pcu_vec *gaz = nullptr;
+  int gaz_valid = 0;
   std::vector<double> c;
   double fobj = 0.0;
   std::vector<double> gamma_s, gamma_t;
@@ -177,6 +181,7 @@ struct pcu_ip {
   int opt_no_updstats = 0;    // debugging (PCU_NO_UPDSTATS): always run the residual pass
   int checkpoint_failed = 0;
   int opt_force_chain = 0;    // PCU_CHAIN=1: device chain also across GPUs
+  int opt_no_gaz = 0;         // debugging (PCU_NO_GAZ): the update pass does not leave g - A z
   int opt_no_chain = 0;       // debugging (PCU_NO_CHAIN): dense algebra of the KKT solve on the host
   double *dense_dev = nullptr, *dense_host = nullptr;  // work buffer of pcu_dense_kernel (+ pinned mirror)
   int dense_cap = 0;

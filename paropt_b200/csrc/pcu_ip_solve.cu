@@ -69,6 +69,11 @@ int pcu_ip::setUpKKTDiagRhs(Vars &vars, int use_qn, double mu) {
     f.Acol.p[j] = Ac[j]->d;
     f.z.v[j] = vars.z[j];
   }
+  if (gaz_valid && &vars == &variables) {
+    // g - A z of this very point was left by the last update pass
+    f.g = gaz->d;
+    f.ncon = 0;
+  }
   double b0 = 0.0;
   if (qn && use_qn) b0 = qn->b0;
   b0_used = b0;
@@ -1179,6 +1184,7 @@ int pcu_ip::scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
 // Everything ParOptInteriorPoint::optimize does before its major loop
 // (IP.cpp:4399-4606).
 int pcu_ip::begin() {
+  gaz_valid = 0;
   if (ensure_qn()) return 1;
   refresh_penalties();
   if (!opt.output_file.empty() && !outfp && ctx->rank == 0) {
@@ -1652,8 +1658,15 @@ int pcu_ip::iterate_once(int *converged) {
           f2.yqn = y_qn->d;
           f2.sqn = s_qn->d;
           f2.ax = ax;
+          // with three or more dense constraints: leave g - A z for the next solve
+          if (ncon >= 3 && !opt_no_gaz) {
+            if (!gaz) gaz = pcu_vec_create(ctx, nvars);
+            if (!gaz) return 1;
+            f2.gaz = gaz->d;
+          }
           RedBuf rb = ctx->redbuf(3, decltype(f2)::NX, 0);
           if (launch_tile(ctx, f2, nvars, wd, rb)) return 1;
+          gaz_valid = f2.gaz != nullptr;
           double out[4];
           if (ctx->fetch(out)) return 1;
           dots[0] = out[0];

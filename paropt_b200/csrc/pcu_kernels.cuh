@@ -1526,6 +1526,10 @@ struct Update2FT : NoStreams {
   int ncon;
   double *yqn, *sqn;
   double ax;
+  // optional output: g - sum_j z_j A_j at the new point, the part of the next
+  // iteration's residual rx that needs the constraint gradients (DiagRhsF then reads
+  // this vector instead of g and the ncon columns)
+  double *gaz = nullptr;
 
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
@@ -1559,8 +1563,12 @@ struct Update2FT : NoStreams {
 #pragma unroll
       for (int q = 0; q < W; q++) rx[q] = (a[q] - b[q]) - gv[q];
     }
+    double ga[W];
 #pragma unroll
-    for (int q = 0; q < W; q++) yv[q] += gv[q];
+    for (int q = 0; q < W; q++) {
+      yv[q] += gv[q];
+      ga[q] = gv[q];
+    }
     for (int j = 0; j < ncon; j++) {
       double a[W];
       src.template ldc<W>(j, Acol.p[j], i, a);
@@ -1568,8 +1576,10 @@ struct Update2FT : NoStreams {
       for (int q = 0; q < W; q++) {
         yv[q] = fma(-z.v[j], a[q], yv[q]);
         if (RX) rx[q] = fma(z.v[j], a[q], rx[q]);
+        if (gaz) ga[q] = fma(-z.v[j], a[q], ga[q]);
       }
     }
+    if (gaz) stv<W>(gaz, i, ga);
 #pragma unroll
     for (int q = 0; q < W; q++) {
       yv[q] = fma(-coef[q], con.d[0], yv[q]);
