@@ -51,6 +51,8 @@ struct pcu_sparsemat {
   int *d_Lp = nullptr, *d_Li = nullptr, *d_Rp = nullptr, *d_Rk = nullptr, *d_Rpos = nullptr;
   int *d_kpos = nullptr, *d_ka = nullptr, *d_kb = nullptr;
   int *d_level_ptr = nullptr, *d_level_cols = nullptr, *d_fail = nullptr;
+  int *d_where = nullptr;  // row -> position maps of the columns being factored (nslots x nwcon)
+  int nslots = 1;
   double *d_data = nullptr, *d_Lx = nullptr, *d_work = nullptr;
   pcu_vec *Dinv = nullptr;  // kept from factor() like the reference (SM.cpp:306-312)
   int factored = 0;
@@ -285,30 +287,22 @@ __global__ void __launch_bounds__(SP_THREADS)
   Lx[kpos[e]] = v;
 }
 
-// position of row i in the sorted row list of a column
-__device__ __forceinline__ int sp_find(const int *__restrict__ Li, int lo, int hi, int i) {
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (Li[mid] < i) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
-}
-
-// Left-looking Cholesky of one column by one thread block
+// Left-looking Cholesky of one column by one thread block.  `where` (one int per row of
+// the matrix, private to the block) maps a row index to its position in column j: the rows
+// of every contributing column's tail are rows of column j (fill property), so only
+// entries written for this column are ever read.
 __device__ void sp_chol_column(int j, const int *__restrict__ Lp, const int *__restrict__ Li,
                                const int *__restrict__ Rp, const int *__restrict__ Rk,
                                const int *__restrict__ Rpos, double *Lx, const int *perm,
-                               int *fail) {
+                               int *fail, int *where) {
   const int c0 = Lp[j], c1 = Lp[j + 1];
+  for (int t = c0 + threadIdx.x; t < c1; t += blockDim.x) where[Li[t]] = t;
+  __syncthreads();
   for (int r = Rp[j]; r < Rp[j + 1]; r++) {  // fixed order: columns ascending
     const int k = Rk[r], pos = Rpos[r];
     const double ljk = Lx[pos];
     const int kend = Lp[k + 1];
-    for (int t = pos + threadIdx.x; t < kend; t += blockDim.x) {
-      const int at = sp_find(Li, c0, c1, Li[t]);
-      Lx[at] -= Lx[t] * ljk;
-    }
+    for (int t = pos + threadIdx.x; t < kend; t += blockDim.x) Lx[where[Li[t]]] -= Lx[t] * ljk;
     __syncthreads();
   }
   double d = Lx[c0];
@@ -327,11 +321,11 @@ __global__ void __launch_bounds__(SP_THREADS)
                    const int *__restrict__ level_cols, const int *__restrict__ Lp,
                    const int *__restrict__ Li, const int *__restrict__ Rp,
                    const int *__restrict__ Rk, const int *__restrict__ Rpos, double *Lx,
-                   const int *__restrict__ perm, int *fail) {
+                   const int *__restrict__ perm, int *fail, int *where_all, int nw) {
+  int *where = where_all + (size_t)blockIdx.x * nw;
   for (int l = l0; l < l1; l++) {  // more than one level only when each has a single column
-    const int idx = level_ptr[l] + blockIdx.x;
-    if (idx < level_ptr[l + 1])
-      sp_chol_column(level_cols[idx], Lp, Li, Rp, Rk, Rpos, Lx, perm, fail);
+    for (int idx = level_ptr[l] + blockIdx.x; idx < level_ptr[l + 1]; idx += gridDim.x)
+      sp_chol_column(level_cols[idx], Lp, Li, Rp, Rk, Rpos, Lx, perm, fail, where);
     __threadfence_block();
   }
 }
@@ -544,6 +538,17 @@ pcu_sparsemat *pcu_sparsemat_create(pcu_ctx *ctx, int nvars, int nwcon, const in
   bad |= cudaMalloc((void **)&m->d_data, sizeof(double) * (m->nnz > 0 ? m->nnz : 1)) != cudaSuccess;
   bad |= cudaMalloc((void **)&m->d_work, sizeof(double) * (nwcon > 0 ? nwcon : 1)) != cudaSuccess;
   bad |= cudaMalloc((void **)&m->d_fail, sizeof(int)) != cudaSuccess;
+  {
+    // concurrent columns of the factorisation: two blocks per SM, at most 256 MB of maps
+    int widest = 1;
+    for (const SparseLaunch &L : m->launches) widest = std::max(widest, L.grid);
+    long long slots = std::min<long long>(widest, 2LL * ctx->num_sms);
+    const long long cap = (256LL << 20) / (4LL * std::max(nwcon, 1));
+    slots = std::max<long long>(1, std::min(slots, cap));
+    m->nslots = (int)slots;
+    bad |= cudaMalloc((void **)&m->d_where, sizeof(int) * (size_t)slots * (size_t)std::max(nwcon, 1)) !=
+           cudaSuccess;
+  }
   if (!bad) bad |= cudaMemset(m->d_data, 0, sizeof(double) * (m->nnz > 0 ? m->nnz : 1)) != cudaSuccess;
   if (bad) {
     fprintf(stderr, "paropt_b200: pcu_sparsemat_create: device allocation failed\n");
@@ -558,7 +563,7 @@ void pcu_sparsemat_destroy(pcu_sparsemat *m) {
   if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
   void *ptrs[] = {m->d_rowp, m->d_cols, m->d_srt_cols, m->d_srt_idx, m->d_colp, m->d_rows,
                   m->d_tmap, m->d_perm, m->d_Lp, m->d_Li, m->d_Rp, m->d_Rk, m->d_Rpos,
-                  m->d_kpos, m->d_ka, m->d_kb, m->d_level_ptr, m->d_level_cols, m->d_fail,
+                  m->d_kpos, m->d_ka, m->d_kb, m->d_level_ptr, m->d_level_cols, m->d_fail, m->d_where,
                   m->d_data, m->d_Lx, m->d_work};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -600,9 +605,11 @@ int pcu_sparsemat_factor(pcu_sparsemat *m, pcu_vec *x, pcu_vec *Dinv, pcu_vec *C
     m->ctx->launches++;
   }
   for (const SparseLaunch &L : m->launches) {
-    sp_chol_kernel<<<L.grid, SP_THREADS, 0, st>>>(L.l0, L.l1, m->d_level_ptr, m->d_level_cols,
-                                                  m->d_Lp, m->d_Li, m->d_Rp, m->d_Rk, m->d_Rpos,
-                                                  m->d_Lx, m->d_perm, m->d_fail);
+    const int grid = L.grid < m->nslots ? L.grid : m->nslots;
+    sp_chol_kernel<<<grid, SP_THREADS, 0, st>>>(L.l0, L.l1, m->d_level_ptr, m->d_level_cols,
+                                                m->d_Lp, m->d_Li, m->d_Rp, m->d_Rk, m->d_Rpos,
+                                                m->d_Lx, m->d_perm, m->d_fail, m->d_where,
+                                                m->nwcon);
     m->ctx->launches++;
   }
   int fail = 0;
