@@ -366,7 +366,7 @@ pcu_ip::~pcu_ip() {
   Vars *all[4] = {&variables, &residual, &update, &refine};
   for (auto vs : all)
     for (int i = 0; i < 8; i++) pcu_vec_destroy(vs->v[i]);
-  pcu_vec *single[] = {lb, ub, g, Dinv, Cw, d1, d2, t1, s_qn, y_qn, rx, rsw, rtw, gaz};
+  pcu_vec *single[] = {lb, ub, g, Dinv, Cw, d1, d2, t1, s_qn, y_qn, rx, rsw, rtw, gaz, apz1, apz2};
   for (auto v : single) pcu_vec_destroy(v);
   for (auto v : Ac) pcu_vec_destroy(v);
   for (auto v : gmres_W) pcu_vec_destroy(v);
@@ -682,6 +682,27 @@ int pcu_ip::initAndCheckDesignAndBounds() {
       fprintf(outfp, "ParOpt Warning: Variables may be too close to upper bound\n");
   }
   return 0;
+}
+
+// A p_z hand-over from the pass-2 kernels to the update pass (pcu_ip.cuh)
+double *pcu_ip::apz_target(int accumulate, bool supported) {
+  if (ncon < 3 || opt_no_gaz) return nullptr;
+  if (!accumulate) apz_state = 0;
+  const int slot = !accumulate ? 1 : (apz_state == 1 ? 2 : 0);
+  if (!supported || slot == 0) {
+    if (accumulate) apz_state = -1;  // a contribution to the step nobody recorded
+    return nullptr;
+  }
+  pcu_vec *&v = slot == 1 ? apz1 : apz2;
+  if (!v) v = pcu_vec_create(ctx, nvars);
+  if (!v) {
+    apz_state = -1;
+    return nullptr;
+  }
+  return v->d;
+}
+void pcu_ip::apz_done(int accumulate, double *target) {
+  if (target) apz_state = accumulate ? 3 : 1;
 }
 
 // --------------------------------------------------------------- residuals

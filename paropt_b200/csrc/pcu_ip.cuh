@@ -141,6 +141,16 @@ struct pcu_ip {
   // pass of the next KKT solve reads it instead of g and the ncon constraint gradients
   pcu_vec *gaz = nullptr;
   int gaz_valid = 0;
+  // A p_z of the iteration's two solves (first solve / its one refinement), written by the
+  // pass-2 kernels while they read the constraint gradients anyway: with g - A z they give
+  // the update pass -(g - A z+) without another sweep over the ncon columns.
+  // apz_state: 0 nothing, 1 first solve there, 3 both there, -1 a solve did not report
+  pcu_vec *apz1 = nullptr, *apz2 = nullptr;
+  int apz_state = 0;
+  // which of the two a pass-2 launch of this solve writes (null: none); `supported`: the
+  // kernel about to run can emit it
+  double *apz_target(int accumulate, bool supported);
+  void apz_done(int accumulate, double *target);
   std::vector<double> c;
   double fobj = 0.0;
   std::vector<double> gamma_s, gamma_t;

@@ -399,8 +399,11 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
         ff.ncols = m; ff.accumulate = accumulate; ff.from_vars = fr.from_vars;
         ff.b0sig = fr.b0sig; ff.mu = fr.mu; ff.mu_rhs = fr.mu_rhs; ff.k = k;
         ff.cbank = -1;
+        ff.apz = apz_target(accumulate, true);
+        ff.nca = ncon;
         RedBuf rb = ctx->redbuf(decltype(ff)::NS, 0, 0);
         if (launch_tile(ctx, ff, nvars, wd, rb)) return 1;
+        apz_done(accumulate, ff.apz);
         double out[decltype(ff)::NS];
         if (ctx->fetch(out)) return 1;
         pass1_r.assign(out, out + m);
@@ -415,7 +418,10 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
       std::swap(d1, t1);  // the next pass 2 reads d1' where the fused pass wrote it
       pass1_ready = 1;
     } else {
+      fr.apz = apz_target(accumulate, true);
+      fr.nca = ncon;
       if (launch_tile(ctx, fr, nvars, wd, NO_RED)) return 1;
+      apz_done(accumulate, fr.apz);
     }
     denseResidual(vars, mu_res, b, &y, VTp);
     if (emitted) *emitted = 1;
@@ -430,12 +436,16 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     fs.V = f2.V; fs.alpha = f2.alpha; fs.ncols = f2.ncols;
     fs.accumulate = f2.accumulate; fs.tau = stats_tau; fs.k = f2.k;
     fs.cbank = -1;
+    fs.apz = apz_target(accumulate, true);
+    fs.nca = ncon;
     RedBuf rb = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
     if (launch_tile(ctx, fs, nvars, wd, rb)) return 1;
+    apz_done(accumulate, fs.apz);
     if (ctx->fetch(stats_out)) return 1;
     stats_ready = 1;
     stats_tau_used = stats_tau;
   } else {
+    apz_target(accumulate, false);
     if (launch_tile(ctx, f2, nvars, wd, NO_RED)) return 1;
   }
   if (VTp && !derived) {
@@ -541,10 +551,14 @@ int pcu_ip::kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double
     ff.ncols = m; ff.accumulate = 0; ff.from_vars = 1;
     ff.b0sig = opt.qn_sigma + ((qn && !opt.sequential_linear_method) ? qn->b0 : 0.0);
     ff.mu = mu; ff.mu_rhs = mu; ff.k = k;
+    ff.apz = apz_target(0, true);
+    ff.nca = ncon;
     RedBuf rb = ctx->redbuf(decltype(ff)::NS, 0, 0);
     red1 = rb.result;
     mr = decltype(ff)::NS;
-    return launch_tile(ctx, ff, nvars, wd, rb);
+    if (launch_tile(ctx, ff, nvars, wd, rb)) return 1;
+    apz_done(0, ff.apz);
+    return 0;
   };
   int rc;
   if (m <= 8) rc = fused21(Pass2R1F<8>());
@@ -584,8 +598,11 @@ int pcu_ip::kktChain(Vars &vars, Vars &b, Vars &y, int use_qn, double mu, double
   fs.cbank = 2 * PCU_DENSE_MAXM;
   fs.ncols = m;
   fs.accumulate = 1; fs.tau = tau; fs.k = k;
+  fs.apz = apz_target(1, true);
+  fs.nca = ncon;
   RedBuf rb2 = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
   if (launch_tile(ctx, fs, nvars, wd, rb2)) return 1;
+  apz_done(1, fs.apz);
   double out[PCU_DENSE_MAXM + Pass2SF::NS + Pass2SF::NX + Pass2SF::NM];
   if (ctx->fetch(out)) return 1;
   memcpy(stats_out, out + mr, sizeof(double) * (Pass2SF::NS + Pass2SF::NX + Pass2SF::NM));
@@ -1185,6 +1202,7 @@ int pcu_ip::scaleAndMerit(Vars &v, Vars &upd, double tau, double comp,
 // (IP.cpp:4399-4606).
 int pcu_ip::begin() {
   gaz_valid = 0;
+  apz_state = 0;
   if (ensure_qn()) return 1;
   refresh_penalties();
   if (!opt.output_file.empty() && !outfp && ctx->rank == 0) {
@@ -1616,6 +1634,17 @@ int pcu_ip::iterate_once(int *converged) {
         f1.z.v[j] = v.z[j];
       }
       f1.yqn = form_pair ? y_qn->d : nullptr;
+      if (form_pair && gaz_valid && apz_state == 3 && apz1 && apz2) {
+        // -(g - A z+) = -(g - A z) + az A p_z: g - A z was left by the last update pass,
+        // A p_z by the two pass-2 kernels of this iteration's solves -- three vectors
+        // instead of g and the ncon constraint gradients
+        f1.g = gaz->d;
+        f1.ncon = 2;
+        f1.Acol.p[0] = apz1->d;
+        f1.Acol.p[1] = apz2->d;
+        f1.z.v[0] = az;
+        f1.z.v[1] = az;
+      }
       f1.ax = ax;
       f1.az = az;
       f1.k = kc;
@@ -1691,7 +1720,13 @@ int pcu_ip::iterate_once(int *converged) {
           }
           return 0;
         };
-        if (take_stats ? launch_update2(Update2FT<1>()) : launch_update2(Update2FT<0>())) return 1;
+        // (more than 16 constraint gradients: 128-row tiles, so that the staged ring holds them)
+        int rc2;
+        if (ncon > 16)
+          rc2 = take_stats ? launch_update2(Update2FT<1, 128>()) : launch_update2(Update2FT<0, 128>());
+        else
+          rc2 = take_stats ? launch_update2(Update2FT<1>()) : launch_update2(Update2FT<0>());
+        if (rc2) return 1;
         // computeQuasiNewtonUpdateCorrection (IP.cpp:4258): the user may change
         // s and y, so the three dots are taken again afterwards
         const bool corrected = prob->hasQnUpdateCorrection();

@@ -1062,6 +1062,11 @@ struct Pass2SF : NoStreams {
   int accumulate;
   double tau;
   IPConst k;
+  // optional output: sum over the first nca columns (the constraint gradients) of
+  // alpha_j V_j = A p_z of this solve; the update pass then forms -(g - A z+) from
+  // g - A z (left by the previous update pass) without re-reading the nca columns
+  double *apz = nullptr;
+  int nca = 0;
 
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
@@ -1099,9 +1104,11 @@ struct Pass2SF : NoStreams {
   template <int W, class S, class AT>
   __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
                                     Elem (&e)[W], double (&part)[W][1], AT *) const {
-    double d[W], di[W];
+    double d[W], di[W], qa[W];
     src.template ld<W>(S_D1, d1, i, d);
     src.template ld<W>(S_DINV, Dinv, i, di);
+#pragma unroll
+    for (int q = 0; q < W; q++) qa[q] = 0.0;
     int j = 0;
     for (; j + 4 <= ncols; j += 4) {  // four columns per batch: loads first
       double c[4][W];
@@ -1114,16 +1121,24 @@ struct Pass2SF : NoStreams {
       for (int jj = 0; jj < 4; jj++) {
 #pragma unroll
         for (int q = 0; q < W; q++) d[q] = fma(al[jj], c[jj][q], d[q]);
+        if (apz && j + jj < nca) {
+#pragma unroll
+          for (int q = 0; q < W; q++) qa[q] = fma(al[jj], c[jj][q], qa[q]);
+        }
       }
     }
     for (; j < ncols; j++) {
       double c[W];
       src.template ldc<W>(j, V.p[j], i, c);
-#pragma unroll
       const double aj = pcu_coef(cbank, alpha, j);
 #pragma unroll
       for (int q = 0; q < W; q++) d[q] = fma(aj, c[q], d[q]);
+      if (apz && j < nca) {
+#pragma unroll
+        for (int q = 0; q < W; q++) qa[q] = fma(aj, c[q], qa[q]);
+      }
     }
+    if (apz) stv<W>(apz, i, qa);
 #pragma unroll
     for (int q = 0; q < W; q++) {
       e[q].d1 = d[q];
@@ -1501,13 +1516,15 @@ typedef Update1FT<0> Update1F;
 // RX = 1 (+ 2N reads: zl, zu) also takes |rx|_inf of the NEXT iteration's residual
 // rx = zl - zu - g + sum_j z_j A_j + Aw^T zw (computeKKTRes, IP.cpp:1337-1399, with
 // ResF's expression order) -- see Update1FT<1>.   maxima: 0 |rx|
-template <int RX>
+// TR: rows per staged tile -- 1024 for a handful of streams, 128 when the ncon columns make
+// a 1024-row stage too large for the ring (C4: 105 streams)
+template <int RX, int TR = 1024>
 struct Update2FT : NoStreams {
   static constexpr int SRC = 1;
   static constexpr int NS = 3, NX = RX ? 1 : 0, NM = 0, NB = 0;
   enum { S_Y, S_G, S_PX, S_ZL, S_ZU, S_A0 };
   static constexpr int NFIX = S_A0;  // fixed slots; the columns follow
-  static constexpr int TROWS = 1024;
+  static constexpr int TROWS = TR;
   enum { W_ZW, NWSLOTS };
   template <class P>
   __host__ __device__ __forceinline__ void tstreams(P &p_) const {
@@ -1754,6 +1771,11 @@ struct Pass2RF : NoStreams {
                   // here instead of being read from `b`
   double b0sig, mu, mu_rhs;
   IPConst k;
+  // optional output: sum over the first nca columns (the constraint gradients) of
+  // alpha_j V_j = A p_z of this solve; the update pass then forms -(g - A z+) from
+  // g - A z (left by the previous update pass) without re-reading the nca columns
+  double *apz = nullptr;
+  int nca = 0;
 
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
@@ -1772,11 +1794,11 @@ struct Pass2RF : NoStreams {
   __device__ __forceinline__ void A(long long i, const double (&coef)[W],
                                     Elem (&e)[W], double (&part)[W][1],
                                     AccT *) const {
-    double d[W], di[W], lin[W];
+    double d[W], di[W], lin[W], qa[W];
     ldv<W>(d1, i, d);
     ldv<W>(Dinv, i, di);
 #pragma unroll
-    for (int q = 0; q < W; q++) lin[q] = 0.0;
+    for (int q = 0; q < W; q++) lin[q] = qa[q] = 0.0;
     for (int j = 0; j < ncols; j++) {
       double c[W];
       ldv<W>(V.p[j], i, c);
@@ -1785,7 +1807,12 @@ struct Pass2RF : NoStreams {
         d[q] = fma(alpha.v[j], c[q], d[q]);
         lin[q] = fma(beta.v[j], c[q], lin[q]);
       }
+      if (apz && j < nca) {
+#pragma unroll
+        for (int q = 0; q < W; q++) qa[q] = fma(alpha.v[j], c[q], qa[q]);
+      }
     }
+    if (apz) stv<W>(apz, i, qa);
 #pragma unroll
     for (int q = 0; q < W; q++) {
       e[q].d1 = d[q];
@@ -1972,6 +1999,11 @@ struct Pass2R1F : NoStreams {
   int from_vars;
   double b0sig, mu, mu_rhs;
   IPConst k;
+  // optional output: sum over the first nca columns (the constraint gradients) of
+  // alpha_j V_j = A p_z of this solve; the update pass then forms -(g - A z+) from
+  // g - A z (left by the previous update pass) without re-reading the nca columns
+  double *apz = nullptr;
+  int nca = 0;
 
   template <class P>
   __device__ __forceinline__ void streams(P &p_) const {
@@ -2014,11 +2046,11 @@ struct Pass2R1F : NoStreams {
   __device__ __forceinline__ void A(const S &src, long long i, const double (&coef)[W],
                                     Elem (&e)[W], double (&part)[W][1],
                                     AT *) const {
-    double d[W], di[W], lin[W];
+    double d[W], di[W], lin[W], qa[W];
     src.template ld<W>(S_D1, d1, i, d);
     src.template ld<W>(S_DINV, Dinv, i, di);
 #pragma unroll
-    for (int q = 0; q < W; q++) lin[q] = 0.0;
+    for (int q = 0; q < W; q++) lin[q] = qa[q] = 0.0;
     int j = 0;
     for (; j + 4 <= ncols; j += 4) {  // four columns per batch: loads first
       double c[4][W];
@@ -2037,6 +2069,10 @@ struct Pass2R1F : NoStreams {
           d[q] = fma(al[jj], c[jj][q], d[q]);
           lin[q] = fma(be[jj], c[jj][q], lin[q]);
         }
+        if (apz && j + jj < nca) {
+#pragma unroll
+          for (int q = 0; q < W; q++) qa[q] = fma(al[jj], c[jj][q], qa[q]);
+        }
       }
     }
     for (; j < ncols; j++) {
@@ -2049,7 +2085,12 @@ struct Pass2R1F : NoStreams {
         d[q] = fma(aj, c[q], d[q]);
         lin[q] = fma(bj, c[q], lin[q]);
       }
+      if (apz && j < nca) {
+#pragma unroll
+        for (int q = 0; q < W; q++) qa[q] = fma(aj, c[q], qa[q]);
+      }
     }
+    if (apz) stv<W>(apz, i, qa);
 #pragma unroll
     for (int q = 0; q < W; q++) {
       e[q].d1 = d[q];
