@@ -133,3 +133,15 @@ def test_bad_patterns_are_rejected():
     rowp = np.array([0, 2], dtype=np.int32)
     assert not lib.pcu_sparsemat_create(None, 4, 1, ip(rowp), ip(np.array([1, 7], dtype=np.int32)), 1)
     assert not lib.pcu_sparsemat_create(None, 4, 1, ip(rowp), ip(np.array([2, 2], dtype=np.int32)), 1)
+
+
+def test_degenerate_sizes():
+    """No sparse constraints at all, and constraints with empty rows (K = C, diagonal)."""
+    lib = _lib.load()
+    s0 = symbolic(lib, 10, 0, np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32), 1)
+    assert (s0["nk"], s0["nl"], s0["nlev"]) == (0, 0, 0)
+    s1 = symbolic(lib, 10, 5, np.zeros(6, dtype=np.int32), np.zeros(0, dtype=np.int32), 1)
+    assert (s1["nk"], s1["nl"], s1["nlev"], s1["nlaunch"]) == (5, 5, 1, 1)
+    K = np.diag(np.arange(1.0, 6.0))
+    b = np.ones(5)
+    assert np.allclose(emulate_solve(s1, K, b, 5), b / np.arange(1.0, 6.0), rtol=1e-15)
