@@ -20,6 +20,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+#include <vector>
+
 #include "pcu_ctx.cuh"
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -531,38 +534,15 @@ static int launch_gram_tma(pcu_ctx *ctx, const ColTable &cols, int m,
 }
 
 // Wide path: one launch for up to 160 columns, no weighting correction.
-static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
-                            const double *Dinv, long long n, double *result, int ld,
-                            long long *rows_done) {
-  const int nt = (m + 7) / 8;
-  GramSegTable segs;
-  memset(&segs, 0, sizeof(segs));
-  int cnt[PCU_GW_NCW] = {0};
-  int next = 0;
-  // longest rows first so that the single-pair segments spread out
-  for (int ti = nt - 1; ti >= 0; ti--) {
-    for (int tj = 0; tj <= ti; tj += 2) {
-      const int w = next % PCU_GW_NCW;
-      next++;
-      if (cnt[w] >= PCU_GW_MAXSEG) return -1;
-      segs.ti[w][cnt[w]] = (unsigned char)ti;
-      segs.tj[w][cnt[w]] = (unsigned char)tj;
-      segs.np[w][cnt[w]] = (unsigned char)((tj + 1 <= ti) ? 2 : 1);
-      cnt[w]++;
-    }
-  }
-  int stage_bytes = (m + 2) * PCU_GW_COLB;
-  stage_bytes = (stage_bytes + 127) / 128 * 128;
-  int nstages = (208 * 1024) / stage_bytes;
-  if (nstages > PCU_GT_MAXSTAGES) nstages = PCU_GT_MAXSTAGES;
-  if (nstages < 2) return -1;
-  const long long nslabs = n / PCU_GW_ROWS;
-  *rows_done = nslabs * PCU_GW_ROWS;
+template <int N2U>
+static int launch_gram_wide_t(pcu_ctx *ctx, const ColTable &cols, int m, int nt,
+                              const GramSegTable &segs, const double *Dinv, long long nslabs,
+                              int nstages, int stage_bytes, double *result, int ld) {
   const int smem = nstages * stage_bytes;
   static int attr_smem_dev[PCU_MAX_DEVICES] = {0};  // per device (function attribute)
   int &attr_smem = attr_smem_dev[ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0];
   if (smem > attr_smem || ctx->device >= PCU_MAX_DEVICES) {
-    PCU_CUDA_OK(cudaFuncSetAttribute(gram_wide_kernel,
+    PCU_CUDA_OK(cudaFuncSetAttribute(gram_wide_kernel<N2U>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
@@ -571,13 +551,76 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
   const int npairs = nt * (nt + 1) / 2;
   if (ctx->big_reserve(0, (size_t)grid * npairs * 64)) return 1;
   ctx->prof_begin("gram_kernel");
-  gram_wide_kernel<<<grid, 32 * (PCU_GW_NCW + 1), smem, ctx->stream>>>(
+  gram_wide_kernel<N2U><<<grid, 32 * (PCU_GW_NCW + 1), smem, ctx->stream>>>(
       cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, ctx->d_big_partials,
       ctx->d_counter, result, ld);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
+                            const double *Dinv, long long n, double *result, int ld,
+                            long long *rows_done) {
+  const int nt = (m + 7) / 8;
+  // segments of the tile triangle: two-pair (ti, tj0), (ti, tj0 + 1) and, at the end of
+  // the odd rows, single-pair ones
+  std::vector<std::pair<int, int> > two, one;
+  for (int ti = nt - 1; ti >= 0; ti--)
+    for (int tj = 0; tj <= ti; tj += 2) (tj + 1 <= ti ? two : one).push_back({ti, tj});
+  const int n2u = (int)two.size() / PCU_GW_NCW;  // common two-pair segments per warp
+  if (n2u > 6) return -1;
+  GramSegTable segs;
+  memset(&segs, 0, sizeof(segs));
+  int load[PCU_GW_NCW];
+  size_t at = 0;
+  for (int w = 0; w < PCU_GW_NCW; w++) {
+    for (int s = 0; s < n2u; s++, at++) {
+      segs.ti[w][s] = (unsigned char)two[at].first;
+      segs.tj[w][s] = (unsigned char)two[at].second;
+      segs.np[w][s] = 2;
+    }
+    load[w] = 2 * n2u;
+  }
+  // the remaining two-pair segments: one each to the first warps (slot n2u); the
+  // single-pair ones to the warps with the fewest pairs (slot n2u + 1)
+  for (int w = 0; at < two.size(); w++, at++) {
+    segs.ti[w][n2u] = (unsigned char)two[at].first;
+    segs.tj[w][n2u] = (unsigned char)two[at].second;
+    segs.np[w][n2u] = 2;
+    load[w] += 2;
+  }
+  if (one.size() > PCU_GW_NCW) return -1;
+  for (size_t k = 0; k < one.size(); k++) {
+    int w = -1;
+    for (int c = 0; c < PCU_GW_NCW; c++)
+      if (segs.np[c][n2u + 1] == 0 && (w < 0 || load[c] < load[w])) w = c;
+    segs.ti[w][n2u + 1] = (unsigned char)one[k].first;
+    segs.tj[w][n2u + 1] = (unsigned char)one[k].second;
+    segs.np[w][n2u + 1] = 1;
+    load[w] += 1;
+  }
+  int stage_bytes = (m + 2) * PCU_GW_COLB;
+  stage_bytes = (stage_bytes + 127) / 128 * 128;
+  int nstages = (208 * 1024) / stage_bytes;
+  if (nstages > PCU_GT_MAXSTAGES) nstages = PCU_GT_MAXSTAGES;
+  if (nstages < 2) return -1;
+  const long long nslabs = n / PCU_GW_ROWS;
+  *rows_done = nslabs * PCU_GW_ROWS;
+#define PCU_GW_CASE(K) \
+  case K: return launch_gram_wide_t<K>(ctx, cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, result, ld);
+  switch (n2u) {
+    PCU_GW_CASE(0)
+    PCU_GW_CASE(1)
+    PCU_GW_CASE(2)
+    PCU_GW_CASE(3)
+    PCU_GW_CASE(4)
+    PCU_GW_CASE(5)
+    PCU_GW_CASE(6)
+  }
+#undef PCU_GW_CASE
+  return -1;
 }
 
 // General kernel on the row range [lo, hi) (lo a multiple of 64 and of the block

@@ -304,25 +304,32 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
 
 // ----------------------------------------------------------------------------
 // Wide variant (m up to 160 columns, no weighting correction): FP64-tensor-bound
-// (C4: 120 columns, 15 flop/B).  The slab is 64 rows and every consumer warp
+// (C4: 121 columns, 15 flop/B).  The slab is 64 rows and every consumer warp
 // reads ALL of it; the work is split over the lower-triangle TILE PAIRS instead
 // of over rows: row ti of the tile triangle is cut into segments of two pairs
-// (ti, tj0), (ti, tj0 + 1) that share the weighted A fragment, and the segments
-// are dealt round robin to the 16 consumer warps (nt = 15: 64 segments, four per
-// warp, 120 of 128 pair slots busy).  One pass over the columns replaces the
-// six 40-column block-pair launches of the register-fed path.
+// (ti, tj0), (ti, tj0 + 1) that share the weighted A fragment (+ one single-pair
+// segment per odd row), and the segments are dealt to the 16 consumer warps so that
+// every warp holds N2U two-pair segments plus at most one more two-pair and one
+// single-pair segment (nt = 16: 136 pairs = 8 warps x 9 + 8 warps x 8).
+// The N2U common segments are straight-line code in chunks of two -- six fragment
+// loads, then eight DMMAs -- so that the loads of a chunk overlap the DMMAs of the
+// one before (the first version branched per segment and issued every load right
+// before its use: tensor pipe 62 %, 0.38 eligible warps per cycle).
 #define PCU_GW_ROWS 64
 #define PCU_GW_NCW 16
 #define PCU_GW_COLB (PCU_GW_ROWS * 8 + 64)
-#define PCU_GW_MAXSEG 7   // segments per warp (nt <= 20: 110 segments)
+#define PCU_GW_MAXSEG 8   // segments per warp: N2U <= 6 common + 2 optional
 
 struct GramSegTable {
-  // segment s of warp w: tile row, first tile column, pairs (1 or 2; 0 = none)
+  // segment s of warp w: tile row, first tile column, pairs (1 or 2; 0 = none).
+  // Order: the N2U common two-pair segments, then the optional two-pair one, then
+  // the optional single-pair one.
   unsigned char ti[PCU_GW_NCW][PCU_GW_MAXSEG];
   unsigned char tj[PCU_GW_NCW][PCU_GW_MAXSEG];
   unsigned char np[PCU_GW_NCW][PCU_GW_MAXSEG];
 };
 
+template <int N2U>
 __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
     gram_wide_kernel(const ColTable cols, const int m, const int nt,
                      const GramSegTable segs, const double *__restrict__ Dinv,
@@ -330,6 +337,7 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
                      const int stage_bytes, double *__restrict__ partials,
                      unsigned int *counter, double *__restrict__ result,
                      const int ld) {
+  constexpr int NSEG = N2U + 2;
   extern __shared__ __align__(128) unsigned char gt_smem[];
   __shared__ __align__(8) unsigned long long gt_full[PCU_GT_MAXSTAGES];
   __shared__ __align__(8) unsigned long long gt_empty[PCU_GT_MAXSTAGES];
@@ -356,9 +364,9 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
   }
   __syncthreads();
 
-  double acc[PCU_GW_MAXSEG][2][2];
+  double acc[NSEG][2][2];
 #pragma unroll
-  for (int s = 0; s < PCU_GW_MAXSEG; s++)
+  for (int s = 0; s < NSEG; s++)
     acc[s][0][0] = acc[s][0][1] = acc[s][1][0] = acc[s][1][1] = 0.0;
 
   if (warp == PCU_GW_NCW) {
@@ -379,19 +387,19 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
     }
   } else {
     // this lane's column offsets per segment (padded columns read the zero column)
-    int offA[PCU_GW_MAXSEG], offB0[PCU_GW_MAXSEG], offB1[PCU_GW_MAXSEG];
-    int npv[PCU_GW_MAXSEG];
+    int offA[NSEG], offB0[NSEG], offB1[NSEG];
+    auto colof = [&](int t) -> int {
+      const int c = 8 * t + gi;
+      return c < m ? c * PCU_GW_COLB : off_zero;
+    };
 #pragma unroll
-    for (int s = 0; s < PCU_GW_MAXSEG; s++) {
-      npv[s] = segs.np[warp][s];
-      auto colof = [&](int t) -> int {
-        const int c = 8 * t + gi;
-        return c < m ? c * PCU_GW_COLB : off_zero;
-      };
+    for (int s = 0; s < NSEG; s++) {
       offA[s] = colof(segs.ti[warp][s]);
       offB0[s] = colof(segs.tj[warp][s]);
       offB1[s] = colof(segs.tj[warp][s] + 1);
     }
+    const bool x2 = segs.np[warp][N2U] == 2;          // the optional two-pair segment
+    const bool x1 = segs.np[warp][N2U + 1] == 1;      // the optional single-pair segment
     long long it = 0;
     for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
       const int s = (int)(it % nstages);
@@ -401,21 +409,51 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
 #pragma unroll 2
       for (int step = 0; step < PCU_GW_ROWS / 8; step++) {
         const int ro = step * 64 + kk * 16;
-        double2 wv = *reinterpret_cast<const double2 *>(st + off_dinv + ro);
+        const double2 wv = *reinterpret_cast<const double2 *>(st + off_dinv + ro);
+        // the optional segments' fragments first: their latency hides behind the
+        // common segments
+        double2 xa = make_double2(0.0, 0.0), xb0 = xa, xb1 = xa, ya = xa, yb0 = xa;
+        if (x2) {
+          xa = *reinterpret_cast<const double2 *>(st + offA[N2U] + ro);
+          xb0 = *reinterpret_cast<const double2 *>(st + offB0[N2U] + ro);
+          xb1 = *reinterpret_cast<const double2 *>(st + offB1[N2U] + ro);
+        }
+        if (x1) {
+          ya = *reinterpret_cast<const double2 *>(st + offA[N2U + 1] + ro);
+          yb0 = *reinterpret_cast<const double2 *>(st + offB0[N2U + 1] + ro);
+        }
 #pragma unroll
-        for (int sg = 0; sg < PCU_GW_MAXSEG; sg++) {
-          if (npv[sg] > 0) {  // warp-uniform
-            const double2 a = *reinterpret_cast<const double2 *>(st + offA[sg] + ro);
-            const double2 b0 = *reinterpret_cast<const double2 *>(st + offB0[sg] + ro);
-            const double ax = a.x * wv.x, ay = a.y * wv.y;
-            dmma884(acc[sg][0], ax, b0.x);
-            dmma884(acc[sg][0], ay, b0.y);
-            if (npv[sg] > 1) {
-              const double2 b1 = *reinterpret_cast<const double2 *>(st + offB1[sg] + ro);
-              dmma884(acc[sg][1], ax, b1.x);
-              dmma884(acc[sg][1], ay, b1.y);
+        for (int c0 = 0; c0 < N2U; c0 += 2) {
+          double2 a[2], b0[2], b1[2];
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            if (c0 + u < N2U) {
+              a[u] = *reinterpret_cast<const double2 *>(st + offA[c0 + u] + ro);
+              b0[u] = *reinterpret_cast<const double2 *>(st + offB0[c0 + u] + ro);
+              b1[u] = *reinterpret_cast<const double2 *>(st + offB1[c0 + u] + ro);
             }
           }
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            if (c0 + u < N2U) {
+              const double ax = a[u].x * wv.x, ay = a[u].y * wv.y;
+              dmma884(acc[c0 + u][0], ax, b0[u].x);
+              dmma884(acc[c0 + u][1], ax, b1[u].x);
+              dmma884(acc[c0 + u][0], ay, b0[u].y);
+              dmma884(acc[c0 + u][1], ay, b1[u].y);
+            }
+          }
+        }
+        if (x2) {  // warp-uniform
+          const double ax = xa.x * wv.x, ay = xa.y * wv.y;
+          dmma884(acc[N2U][0], ax, xb0.x);
+          dmma884(acc[N2U][1], ax, xb1.x);
+          dmma884(acc[N2U][0], ay, xb0.y);
+          dmma884(acc[N2U][1], ay, xb1.y);
+        }
+        if (x1) {
+          dmma884(acc[N2U + 1][0], ya.x * wv.x, yb0.x);
+          dmma884(acc[N2U + 1][0], ya.y * wv.y, yb0.y);
         }
       }
       __syncwarp();
@@ -423,10 +461,11 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
     }
     // every tile pair is owned by exactly one warp of the CTA
 #pragma unroll
-    for (int sg = 0; sg < PCU_GW_MAXSEG; sg++) {
+    for (int sg = 0; sg < NSEG; sg++) {
+      const int npv = segs.np[warp][sg];
 #pragma unroll
       for (int q = 0; q < 2; q++) {
-        if (q < npv[sg]) {
+        if (q < npv) {
           const int ti = segs.ti[warp][sg], tj = segs.tj[warp][sg] + q;
           const int p = ti * (ti + 1) / 2 + tj;
           double *dst = partials + ((size_t)blockIdx.x * npairs_tot + p) * 64;
