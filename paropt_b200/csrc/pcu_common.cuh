@@ -337,6 +337,10 @@ struct GSrc {
   __device__ __forceinline__ double ldw(int, const double *p, long long ci) const {
     return p[ci];
   }
+  template <int W>  // scratch slots exist in the staged sources only
+  __device__ __forceinline__ void st(int, long long, const double (&)[W]) const {
+    __trap();
+  }
 };
 template <int ROWS, int NFIX>
 struct SSrc {
@@ -363,6 +367,15 @@ struct SSrc {
   __device__ __forceinline__ void ldc(int j, const double *, long long i,
                                       double (&out)[W]) const {
     lds<W>(nb + col0 + (unsigned)j * (ROWS * 8u) + (unsigned)(i - row0) * 8u, out);
+  }
+  template <int W>  // scratch slot of the stage (not filled by the copy engine)
+  __device__ __forceinline__ void st(int slot, long long i, const double (&v)[W]) const {
+    const unsigned a = nb + off[slot] + (unsigned)(i - row0) * 8u;
+    if (W == 2) {
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v[0]), "d"(v[W - 1]) : "memory");
+    } else {
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v[0]) : "memory");
+    }
   }
   __device__ __forceinline__ double ldw(int slot, const double *, long long ci) const {
     double v[1];

@@ -401,6 +401,7 @@ int pcu_ip::init(pcu_problem *p) {  // constructor, IP.cpp:182-438
     return 1;
   wd = pcu_make_wdesc(p->weighting, nvars);
   if (getenv("PCU_NO_FUSE21")) opt_no_fuse21 = 1;
+  if (getenv("PCU_NO_WIDE")) opt_no_wide = 1;
   if (getenv("PCU_NO_FUSE2S")) opt_no_fuse2s = 1;
   if (getenv("PCU_NO_RHSGRAM")) opt_no_rhsgram = 1;
   if (getenv("PCU_NO_CHAIN")) opt_no_chain = 1;

@@ -184,6 +184,7 @@ struct pcu_ip {
   int stats_ready = 0;        // Pass2SF left the step statistics in stats_out
   double stats_tau_used = 0.0;
   double stats_out[32];
+  int opt_no_wide = 0;        // debugging: more than 32 columns stay on the register-fed pass 2
   int opt_no_fuse21 = 0;      // debugging: keep pass 2 and the next pass 1 separate
   // residual statistics of the NEXT iteration taken by the update passes (ResF layout)
   double upd_sums[11], upd_max[5], upd_min[2];

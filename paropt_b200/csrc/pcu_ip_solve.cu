@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "pcu_ip.cuh"
+#include "pcu_wide.cuh"
 
 int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
                      int ncols, long long n, int dst_off);
@@ -418,10 +419,40 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
       std::swap(d1, t1);  // the next pass 2 reads d1' where the fused pass wrote it
       pass1_ready = 1;
     } else {
-      fr.apz = apz_target(accumulate, true);
-      fr.nca = ncon;
-      if (launch_tile(ctx, fr, nvars, wd, NO_RED)) return 1;
-      apz_done(accumulate, fr.apz);
+      // more than 32 columns: the same fusion on the column-split staged kernel
+      // (whole 64-row tiles, no weighting constraints); otherwise the register-fed
+      // Pass2RF and, in the next solve, Pass1F + a multi-dot
+      int rc = -1;
+      double *apz_w = apz_target(accumulate, true);
+      if (!opt_no_fuse21 && !opt_no_wide) {
+        Pass2R1F<0, 1> ff;
+        ff.v = fr.v; ff.b = fr.b; ff.y = fr.y;
+        ff.lb = fr.lb; ff.ub = fr.ub; ff.Dinv = fr.Dinv; ff.Cw = fr.Cw;
+        ff.d1 = fr.d1; ff.g = fr.g;
+        ff.d2 = d2->d;
+        ff.d1out = t1->d;
+        ff.V = fr.V; ff.alpha = fr.alpha; ff.beta = fr.beta;
+        ff.ncols = m; ff.accumulate = accumulate; ff.from_vars = fr.from_vars;
+        ff.b0sig = fr.b0sig; ff.mu = fr.mu; ff.mu_rhs = fr.mu_rhs; ff.k = k;
+        ff.cbank = -1;
+        ff.apz = apz_w;
+        ff.nca = ncon;
+        rc = pcu_launch_wide<Pass2R1F<0, 1>, 1>(ctx, ff, nvars, wd, NO_RED, m);
+        if (rc > 0) return 1;
+        if (rc == 0) {
+          apz_done(accumulate, apz_w);
+          pass1_r.assign(m, 0.0);
+          if (ctx->big_fetch(m, pass1_r.data())) return 1;
+          std::swap(d1, t1);
+          pass1_ready = 1;
+        }
+      }
+      if (rc < 0) {
+        fr.apz = apz_w;
+        fr.nca = ncon;
+        if (launch_tile(ctx, fr, nvars, wd, NO_RED)) return 1;
+        apz_done(accumulate, fr.apz);
+      }
     }
     denseResidual(vars, mu_res, b, &y, VTp);
     if (emitted) *emitted = 1;
@@ -439,7 +470,12 @@ int pcu_ip::computeKKTStep(Vars &vars, Vars &b, Vars &y, int use_qn,
     fs.apz = apz_target(accumulate, true);
     fs.nca = ncon;
     RedBuf rb = ctx->redbuf(Pass2SF::NS, Pass2SF::NX, Pass2SF::NM);
-    if (launch_tile(ctx, fs, nvars, wd, rb)) return 1;
+    int rcw = -1;
+    if (m > 32 && !opt_no_wide) {
+      rcw = pcu_launch_wide<Pass2SF, 0>(ctx, fs, nvars, wd, rb, m);
+      if (rcw > 0) return 1;
+    }
+    if (rcw < 0 && launch_tile(ctx, fs, nvars, wd, rb)) return 1;
     apz_done(accumulate, fs.apz);
     if (ctx->fetch(stats_out)) return 1;
     stats_ready = 1;

@@ -1968,11 +1968,15 @@ struct Con3 {
   double zw, sw, tw, zsw, ztw, pzw, psw, ptw, pzsw, pztw;
   __device__ __forceinline__ void zero() { d[0] = d[1] = d[2] = 0.0; }
 };
-template <int MR>
+// WIDE = 1 (wide_tile_kernel, pcu_wide.cuh; MR = 0): the column sums of phase A arrive
+// pre-added in the d1 slot and in the slot S_LIN of the stage, and phase F leaves t1'
+// in the slot S_T for the kernel's column phase instead of walking the columns.
+template <int MR, int WIDE = 0>
 struct Pass2R1F : NoStreams {
   static constexpr int SRC = 1;
   static constexpr int MINB = PCU_MINB_PASS21;
-  enum { S_D1, S_DINV, S_X, S_LB, S_UB, S_G, S_ZL, S_BZL, S_ZU, S_BZU, S_YX, S_YZL, S_YZU, S_V0 };
+  enum { S_D1, S_DINV, S_X, S_LB, S_UB, S_G, S_ZL, S_BZL, S_ZU, S_BZU, S_YX, S_YZL, S_YZU,
+         S_LIN, S_T, S_V0 };
   static constexpr int NFIX = S_V0;  // fixed slots; the columns follow
   enum { W_CW, W_D2, W_SW, W_TW, W_ZSW, W_ZTW, W_ZW, W_BSW, W_BTW, W_BZSW, W_BZTW,
          W_YZW, W_YZSW, W_YZTW, W_YSW, W_YTW, NWSLOTS };
@@ -2051,6 +2055,7 @@ struct Pass2R1F : NoStreams {
     src.template ld<W>(S_DINV, Dinv, i, di);
 #pragma unroll
     for (int q = 0; q < W; q++) lin[q] = qa[q] = 0.0;
+    if constexpr (WIDE) src.template ld<W>(S_LIN, nullptr, i, lin);
     int j = 0;
     for (; j + 4 <= ncols; j += 4) {  // four columns per batch: loads first
       double c[4][W];
@@ -2252,10 +2257,11 @@ struct Pass2R1F : NoStreams {
     double t[W];
 #pragma unroll
     for (int q = 0; q < W; q++) t[q] = e[q].dinv * fma(coef[q], con.d[2], e[q].d1);
+    if constexpr (WIDE) src.template st<W>(S_T, i, t);
     // eight columns at a time: the loads of a batch are issued before the
     // dependent multiply-adds (this loop held 18 % of the kernel's stall samples)
 #pragma unroll
-    for (int j0 = 0; j0 < MR; j0 += 8) {
+    for (int j0 = 0; j0 < (WIDE ? 0 : MR); j0 += 8) {
       if (j0 < ncols) {
         double c[8][W];
 #pragma unroll

@@ -54,9 +54,11 @@ def run(ctx, make_problem, options, iters, plain):
 
 # C4 (100 dense constraints + L-SR1: 120 columns) exercises the wide tile-pair
 # Gram kernel; its L-SR1 history is only reproducible for 9 iterations (see
-# tests/test_oracle_golden.py).
+# tests/test_oracle_golden.py).  With n a multiple of 64 its two pass-2 kernels run on
+# the column-split staged harness (wide_tile_kernel, pcu_wide.cuh).
 @pytest.mark.parametrize("name,n,iters", [("C3", 8 * 5003, 14), ("C2", 50001, 14),
-                                          ("C3", 8 * 4096, 14), ("C4", 40008, 9)])
+                                          ("C3", 8 * 4096, 14), ("C4", 40008, 9),
+                                          ("C4", 625 * 64, 9)])
 def test_fused_paths_match_oracle_and_plain_path(ctx, name, n, iters):
     from oracle.ip_oracle import InteriorPointOracle
     from oracle.problems import SepQuad
