@@ -169,6 +169,35 @@ __device__ __forceinline__ double shfl_down_d(double v, int o) {
   return __shfl_down_sync(0xffffffffu, v, o);
 }
 
+// Last-block combines: sum of p[b * stride], b = first, first + step, ... < nb, added in
+// that order, with the (independent) loads issued sixteen at a time -- a plain
+// `for (b) v += p[...]` waits one L2 round trip per block (148 CTAs: ~11 us in the Gram
+// kernels, ~2 us per value in finish_reduction; launch_overhead_probe.py).  ld.cg: the
+// partials were written by other SMs.
+__device__ __forceinline__ double pcu_ordered_sum(const double *p, size_t stride,
+                                                  unsigned first, unsigned step, unsigned nb) {
+  double v = 0.0;
+  unsigned b = first;
+  for (; b + 15u * step < nb; b += 16u * step) {
+    double t[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) t[u] = __ldcg(p + (size_t)(b + (unsigned)u * step) * stride);
+#pragma unroll
+    for (int u = 0; u < 16; u++) v += t[u];
+  }
+  double t[16];
+#pragma unroll
+  for (int u = 0; u < 16; u++) {
+    const unsigned bb = b + (unsigned)u * step;
+    t[u] = bb < nb ? __ldcg(p + (size_t)bb * stride) : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < 16; u++) {
+    if (b + (unsigned)u * step < nb) v += t[u];
+  }
+  return v;
+}
+
 struct RedBuf {
   double *partials;        // [gridDim.x][NR]
   unsigned int *counter;   // zero before launch, reset by the last block
@@ -243,12 +272,25 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb, const int tid_ = 
     __threadfence();
     // one warp per value, lanes stride over blocks, fixed order
     for (int i = warp; i < NR; i += nwarps) {
-      double v = (i < NS) ? 0.0 : ((i < NS + NX) ? 0.0 : 1.0e300);
-      for (unsigned int b = lane; b < gridDim.x; b += 32) {
-        double p = rb.partials[(size_t)b * NR + i];
-        if (i < NS) v += p;
-        else if (i < NS + NX) v = fmax(v, p);
-        else v = fmin(v, p);
+      const double ident = (i < NS) ? 0.0 : ((i < NS + NX) ? 0.0 : 1.0e300);
+      double v = ident;
+      // eight independent loads in flight per lane (one L2 round trip per batch
+      // instead of one per block), combined in the order b = lane, lane + 32, ...
+      for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 256u) {
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const unsigned int b = b0 + 32u * (unsigned)u;
+          p[u] = b < gridDim.x ? __ldcg(rb.partials + (size_t)b * NR + i) : ident;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (b0 + 32u * (unsigned)u < gridDim.x) {
+            if (i < NS) v += p[u];
+            else if (i < NS + NX) v = fmax(v, p[u]);
+            else v = fmin(v, p[u]);
+          }
+        }
       }
       for (int o = 16; o > 0; o >>= 1) {
         double q = shfl_down_d(v, o);
@@ -258,16 +300,17 @@ __device__ void finish_reduction(AccT_ &acc, const RedBuf &rb, const int tid_ = 
       }
       if (lane == 0) {
         rb.result[i] = v;
-        if (rb.hres) {
-          rb.hres[i] = v;
-          __threadfence_system();
-        }
+        sm[0][i] = v;
       }
     }
     if (tid == 0) *rb.counter = 0u;
-    if (rb.hres) {  // (uniform) every value is on its way to the host: publish
+    if (rb.hres) {  // (uniform) publish: ONE thread stores every value, fences once
+      // (system scope: one PCIe round trip instead of one per value -- 4-5 us of every
+      // fused kernel, scripts/reduce_probe.py) and raises the flag
       PCU_RED_SYNC();
       if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < NR; i++) rb.hres[i] = sm[0][i];
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(rb.hflag) = rb.seq;
       }

@@ -14,6 +14,8 @@ struct PendingRed {
   int offset, ns, nx, nm;
 };
 
+#define PCU_SHM_CAP 1024  // doubles per publication of the shared-memory all-gather
+
 struct pcu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -39,7 +41,7 @@ struct pcu_ctx {
   struct ShmRank {
     volatile unsigned long long seq;
     char pad[56];
-    double data[2][512];
+    double data[2][PCU_SHM_CAP];
   };
   void *shm_base = nullptr;
   size_t shm_bytes = 0;
@@ -47,7 +49,8 @@ struct pcu_ctx {
   char shm_name[64] = {0};
   int wait_flag(unsigned long long seq);
   int shm_setup(const unsigned char id128[128]);
-  int shm_allgather(int total);
+  int shm_allgather(int total, const double *src = nullptr, double *dst = nullptr);
+  std::vector<double> big_gather;      // [world][n] of big_fetch's host-side all-reduce
   int result_used = 0;
   bool red_overflow = false;   // redbuf() ran out of slots: the next fetch() fails
   std::vector<PendingRed> pending;
@@ -63,6 +66,7 @@ struct pcu_ctx {
   int num_sms = 148;
   int max_blocks_per_sm = 16;  // occupancy cap of the streaming kernels
   int prefetch = -1;           // -1: same-iteration L2 prefetch; k > 0: k iterations ahead; 0 off
+  int no_shm_big = 1;          // 0 (PCU_SHM_BIG=1): big_fetch adds the ranks' partials on the hosts
   int no_tma_tile = 0;         // PCU_NO_TMA_TILE: keep the SRC functors on the register-fed kernel
   int tma_groups = 0;          // PCU_TMA_GROUPS: cap on the consumer groups of tma_tile_kernel
   int tma_npw = 0;             // PCU_TMA_NPW: producer warps of tma_tile_kernel (default 2)

@@ -216,9 +216,7 @@ __global__ void __launch_bounds__(PCU_THREADS, PCU_GRAM_MINB)
   if (is_last) {
     __threadfence();
     for (int idx = threadIdx.x; idx < NP * 64; idx += blockDim.x) {
-      double v = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; b++)
-        v += partials[(size_t)b * NP * 64 + idx];
+      const double v = pcu_ordered_sum(partials + idx, (size_t)NP * 64, 0u, 1u, gridDim.x);
       const int p = idx >> 6, e = idx & 63;
       int ti = 0, q = p;
       while (q > ti) {

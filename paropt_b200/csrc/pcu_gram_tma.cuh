@@ -284,9 +284,7 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
   if (is_last) {
     __threadfence();
     for (int idx = threadIdx.x; idx < NP * 64; idx += blockDim.x) {
-      double v = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; b++)
-        v += partials[(size_t)b * NP * 64 + idx];
+      const double v = pcu_ordered_sum(partials + idx, (size_t)NP * 64, 0u, 1u, gridDim.x);
       const int p = idx >> 6, e = idx & 63;
       int ti = 0, q = p;
       while (q > ti) {
@@ -485,9 +483,8 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
   if (is_last) {
     __threadfence();
     for (int idx = threadIdx.x; idx < npairs_tot * 64; idx += blockDim.x) {
-      double v = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; b++)
-        v += partials[(size_t)b * npairs_tot * 64 + idx];
+      const double v =
+          pcu_ordered_sum(partials + idx, (size_t)npairs_tot * 64, 0u, 1u, gridDim.x);
       const int p = idx >> 6, e = idx & 63;
       int ti = 0, q = p;
       while (q > ti) {

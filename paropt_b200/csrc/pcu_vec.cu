@@ -160,11 +160,14 @@ int pcu_ctx::shm_setup(const unsigned char id128[128]) {
   return 0;
 }
 
-int pcu_ctx::shm_allgather(int total) {
+// src / dst default to the zero-copy result buffer and h_gather
+int pcu_ctx::shm_allgather(int total, const double *src, double *dst) {
+  if (!src) src = h_zc;
+  if (!dst) dst = h_gather;
   ShmRank *ranks = reinterpret_cast<ShmRank *>(reinterpret_cast<char *>(shm_base) + 4096);
   const unsigned long long n = ++shm_pub;
   ShmRank &mine = ranks[rank];
-  memcpy(mine.data[n & 1], h_zc, sizeof(double) * (size_t)total);
+  memcpy(mine.data[n & 1], src, sizeof(double) * (size_t)total);
   std::atomic_thread_fence(std::memory_order_release);
   mine.seq = n;
   const auto t0 = std::chrono::steady_clock::now();
@@ -181,7 +184,7 @@ int pcu_ctx::shm_allgather(int total) {
 #endif
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    memcpy(h_gather + (size_t)r * total, ranks[r].data[n & 1], sizeof(double) * (size_t)total);
+    memcpy(dst + (size_t)r * total, ranks[r].data[n & 1], sizeof(double) * (size_t)total);
   }
   return 0;
 }
@@ -318,6 +321,25 @@ int pcu_ctx::big_reserve(size_t nresult, size_t npartials) {
 }
 
 int pcu_ctx::big_fetch(size_t n, double *out) {
+  if (world > 1 && n > 0 && n <= PCU_SHM_CAP && shm_base != nullptr && !no_shm_big) {
+    // ranks of one node: every rank copies its partial to the host, the partials are
+    // exchanged through the shared-memory segment and added in rank order on every host
+    // (identical data, identical order: identical results) -- the result is consumed by
+    // the host anyway, and the in-stream all-reduce of a few hundred doubles costs
+    // 20-30 us of latency at 8 GPUs.  d_big keeps the LOCAL partial.
+    PCU_CUDA_OK(cudaMemcpyAsync(h_big, d_big, n * sizeof(double), cudaMemcpyDeviceToHost,
+                                stream));
+    PCU_CUDA_OK(cudaStreamSynchronize(stream));
+    big_gather.resize((size_t)world * n);
+    if (shm_allgather((int)n, h_big, big_gather.data())) return 1;
+    for (size_t i = 0; i < n; i++) {
+      double v = big_gather[i];
+      for (int r = 1; r < world; r++) v += big_gather[(size_t)r * n + i];
+      h_big[i] = v;
+    }
+    if (out) memcpy(out, h_big, n * sizeof(double));
+    return 0;
+  }
   if (world > 1 && n > 0) {
     PCU_NCCL_OK(nccl_api().AllReduce(d_big, d_big, n, ncclFloat64, ncclSum, comm,
                                      stream));
@@ -365,6 +387,9 @@ pcu_ctx *pcu_ctx_create(int device) {
   if (const char *e = getenv("PCU_MAX_BLOCKS_PER_SM")) ctx->max_blocks_per_sm = atoi(e);
   if (const char *e = getenv("PCU_PREFETCH")) ctx->prefetch = atoi(e);
   if (getenv("PCU_NO_TMA_TILE")) ctx->no_tma_tile = 1;
+  // measured at 2 GPUs: 6.81 ms / iteration against 6.77 with the in-stream NCCL
+  // all-reduce -- no gain, so the host-side variant is opt-in
+  ctx->no_shm_big = getenv("PCU_SHM_BIG") ? 0 : 1;
   if (const char *e = getenv("PCU_TMA_GROUPS")) ctx->tma_groups = atoi(e);
   if (const char *e = getenv("PCU_TMA_NPW")) ctx->tma_npw = atoi(e);
   if (const char *e = getenv("PCU_TMA_MIN_TILES")) ctx->tma_min_tiles = atoi(e);
@@ -681,9 +706,7 @@ __global__ void __launch_bounds__(PCU_THREADS)
   if (is_last) {
     __threadfence();
     for (int k = warp; k < ncols; k += PCU_THREADS / 32) {
-      double v = 0.0;
-      for (unsigned int b = lane; b < gridDim.x; b += 32)
-        v += partials[(size_t)b * KC + k];
+      double v = pcu_ordered_sum(partials + k, (size_t)KC, (unsigned)lane, 32u, gridDim.x);
       for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
       if (lane == 0) result[col0 + k] = v;
     }

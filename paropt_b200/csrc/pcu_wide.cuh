@@ -299,8 +299,7 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     if (wt_last) {
       __threadfence();
       for (int j = cw; j < m; j += NCW) {
-        double v = 0.0;
-        for (unsigned int b = lane; b < gridDim.x; b += 32) v += dot_partials[(size_t)b * m + j];
+        double v = pcu_ordered_sum(dot_partials + j, (size_t)m, (unsigned)lane, 32u, gridDim.x);
         for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
         if (lane == 0) dot_result[j] = v;
       }
