@@ -549,7 +549,7 @@ static int launch_gram_wide_t(pcu_ctx *ctx, const ColTable &cols, int m, int nt,
   const int npairs = nt * (nt + 1) / 2;
   if (ctx->big_reserve(0, (size_t)grid * npairs * 64)) return 1;
   ctx->prof_begin("gram_kernel");
-  gram_wide_kernel<N2U><<<grid, 32 * (PCU_GW_NCW + 1), smem, ctx->stream>>>(
+  gram_wide_kernel<N2U><<<grid, 32 * (PCU_GW_NCW + PCU_GW_NPW), smem, ctx->stream>>>(
       cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, ctx->d_big_partials,
       ctx->d_counter, result, ld);
   ctx->prof_end();
@@ -568,7 +568,7 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
   for (int ti = nt - 1; ti >= 0; ti--)
     for (int tj = 0; tj <= ti; tj += 2) (tj + 1 <= ti ? two : one).push_back({ti, tj});
   const int n2u = (int)two.size() / PCU_GW_NCW;  // common two-pair segments per warp
-  if (n2u > 6) return -1;
+  if (n2u > PCU_GW_MAXN2U) return -1;
   GramSegTable segs;
   memset(&segs, 0, sizeof(segs));
   int load[PCU_GW_NCW];
@@ -616,6 +616,8 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
     PCU_GW_CASE(4)
     PCU_GW_CASE(5)
     PCU_GW_CASE(6)
+    PCU_GW_CASE(7)
+    PCU_GW_CASE(8)
   }
 #undef PCU_GW_CASE
   return -1;

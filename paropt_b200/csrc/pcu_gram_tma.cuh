@@ -306,17 +306,27 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
 // reads ALL of it; the work is split over the lower-triangle TILE PAIRS instead
 // of over rows: row ti of the tile triangle is cut into segments of two pairs
 // (ti, tj0), (ti, tj0 + 1) that share the weighted A fragment (+ one single-pair
-// segment per odd row), and the segments are dealt to the 16 consumer warps so that
+// segment per odd row), and the segments are dealt to the consumer warps so that
 // every warp holds N2U two-pair segments plus at most one more two-pair and one
-// single-pair segment (nt = 16: 136 pairs = 8 warps x 9 + 8 warps x 8).
-// The N2U common segments are straight-line code in chunks of two -- six fragment
-// loads, then eight DMMAs -- so that the loads of a chunk overlap the DMMAs of the
-// one before (the first version branched per segment and issued every load right
-// before its use: tensor pipe 62 %, 0.38 eligible warps per cycle).
+// single-pair segment (nt = 16: 136 pairs = 4 warps x 12 + 8 warps x 11).
+//
+// 12 consumer warps (three warpgroups, 160 registers each after setmaxnreg) + 4
+// producer warps (24 registers) that deal the m + 1 bulk copies of a slab among
+// themselves.  ncu of the version with 16 + 1 warps (96 registers, profiles/
+// r2t_ncu_raw_C4.csv): a DMMA.8x8x4 held the tensor pipe 20.7 cycles against 16 when
+// consecutive DMMAs are independent (the narrow kernel, cuBLAS DGEMM) -- the compiler
+// had sunk every fragment load to its use and left the two halves of an accumulator
+// two instructions apart.  Here a step works in two chunks of three or four segments:
+// the chunk's fragment loads, the scalings, its x-half DMMAs on six to eight different
+// accumulators, then the y-half DMMAs.
 #define PCU_GW_ROWS 64
-#define PCU_GW_NCW 16
+#define PCU_GW_NCW 12
+#define PCU_GW_NPW 4
 #define PCU_GW_COLB (PCU_GW_ROWS * 8 + 64)
-#define PCU_GW_MAXSEG 8   // segments per warp: N2U <= 6 common + 2 optional
+#define PCU_GW_MAXN2U 8
+#define PCU_GW_MAXSEG (PCU_GW_MAXN2U + 2)  // N2U common segments + 2 optional ones
+#define PCU_GW_CONS_REGS 160
+#define PCU_GW_PROD_REGS 24
 
 struct GramSegTable {
   // segment s of warp w: tile row, first tile column, pairs (1 or 2; 0 = none).
@@ -327,8 +337,14 @@ struct GramSegTable {
   unsigned char np[PCU_GW_NCW][PCU_GW_MAXSEG];
 };
 
+__device__ __forceinline__ double2 gw_lds2(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+
 template <int N2U>
-__global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
+__global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
     gram_wide_kernel(const ColTable cols, const int m, const int nt,
                      const GramSegTable segs, const double *__restrict__ Dinv,
                      const long long nslabs, const int nstages,
@@ -336,6 +352,8 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
                      unsigned int *counter, double *__restrict__ result,
                      const int ld) {
   constexpr int NSEG = N2U + 2;
+  constexpr int CH = NSEG <= 8 ? (NSEG + 1) / 2 : 4;  // segments per chunk of a step
+  constexpr int NCT = PCU_GW_NCW * 32;  // consumer threads
   extern __shared__ __align__(128) unsigned char gt_smem[];
   __shared__ __align__(8) unsigned long long gt_full[PCU_GT_MAXSTAGES];
   __shared__ __align__(8) unsigned long long gt_empty[PCU_GT_MAXSTAGES];
@@ -346,7 +364,7 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; s++) {
-      gt_mbar_init(gt_smem_u32(&gt_full[s]), 1);
+      gt_mbar_init(gt_smem_u32(&gt_full[s]), PCU_GW_NPW);
       gt_mbar_init(gt_smem_u32(&gt_empty[s]), PCU_GW_NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -362,33 +380,43 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
   }
   __syncthreads();
 
-  double acc[NSEG][2][2];
-#pragma unroll
-  for (int s = 0; s < NSEG; s++)
-    acc[s][0][0] = acc[s][0][1] = acc[s][1][0] = acc[s][1][1] = 0.0;
-
-  if (warp == PCU_GW_NCW) {
+  if (warp >= PCU_GW_NCW) {
+    // ----------------------------------------------------------- producers
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PCU_GW_PROD_REGS));
+    const int pw = warp - PCU_GW_NCW;
+    const int c0 = pw + PCU_GW_NPW * lane;  // copy c goes to warp c % NPW
+    unsigned mine = 0;
+    for (int c = c0; c <= m; c += 32 * PCU_GW_NPW) mine += col_bytes;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     long long it = 0;
     for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
       if (round > 0) gt_mbar_wait(gt_smem_u32(&gt_empty[s]), (round - 1) & 1);
       const unsigned full = gt_smem_u32(&gt_full[s]);
-      if (lane == 0) gt_mbar_expect_tx(full, (unsigned)(m + 1) * col_bytes);
+      if (lane == 0) gt_mbar_expect_tx(full, mine);
       __syncwarp();
       const unsigned base = gt_smem_u32(gt_smem + (size_t)s * stage_bytes);
       const long long row0 = slab * PCU_GW_ROWS;
-      for (int c = lane; c <= m; c += 32) {
+      for (int c = c0; c <= m; c += 32 * PCU_GW_NPW) {
         if (c < m) gt_bulk_g2s(base + c * PCU_GW_COLB, cols.p[c] + row0, col_bytes, full);
         else gt_bulk_g2s(base + off_dinv, Dinv + row0, col_bytes, full);
       }
     }
-  } else {
+    return;
+  }
+  // ------------------------------------------------------------- consumers
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PCU_GW_CONS_REGS));
+  double acc[NSEG][2][2];
+#pragma unroll
+  for (int s = 0; s < NSEG; s++)
+    acc[s][0][0] = acc[s][0][1] = acc[s][1][0] = acc[s][1][1] = 0.0;
+  {
     // this lane's column offsets per segment (padded columns read the zero column)
-    int offA[NSEG], offB0[NSEG], offB1[NSEG];
-    auto colof = [&](int t) -> int {
+    unsigned offA[NSEG], offB0[NSEG], offB1[NSEG];
+    auto colof = [&](int t) -> unsigned {
       const int c = 8 * t + gi;
-      return c < m ? c * PCU_GW_COLB : off_zero;
+      return (unsigned)(c < m ? c * PCU_GW_COLB : off_zero);
     };
 #pragma unroll
     for (int s = 0; s < NSEG; s++) {
@@ -396,62 +424,64 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
       offB0[s] = colof(segs.tj[warp][s]);
       offB1[s] = colof(segs.tj[warp][s] + 1);
     }
-    const bool x2 = segs.np[warp][N2U] == 2;          // the optional two-pair segment
-    const bool x1 = segs.np[warp][N2U + 1] == 1;      // the optional single-pair segment
+    // pairs of slot s: 2 for the common segments (compile time), 0..2 / 0..1 for the
+    // two optional ones (warp-uniform)
+    const int npx = segs.np[warp][N2U], npy = segs.np[warp][N2U + 1];
     long long it = 0;
     for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
       gt_mbar_wait(gt_smem_u32(&gt_full[s]), round & 1);
-      const unsigned char *st = gt_smem + (size_t)s * stage_bytes;
-#pragma unroll 2
+      const unsigned sb = gt_smem_u32(gt_smem) + (unsigned)s * (unsigned)stage_bytes;
+#pragma unroll 1
       for (int step = 0; step < PCU_GW_ROWS / 8; step++) {
-        const int ro = step * 64 + kk * 16;
-        const double2 wv = *reinterpret_cast<const double2 *>(st + off_dinv + ro);
-        // the optional segments' fragments first: their latency hides behind the
-        // common segments
-        double2 xa = make_double2(0.0, 0.0), xb0 = xa, xb1 = xa, ya = xa, yb0 = xa;
-        if (x2) {
-          xa = *reinterpret_cast<const double2 *>(st + offA[N2U] + ro);
-          xb0 = *reinterpret_cast<const double2 *>(st + offB0[N2U] + ro);
-          xb1 = *reinterpret_cast<const double2 *>(st + offB1[N2U] + ro);
-        }
-        if (x1) {
-          ya = *reinterpret_cast<const double2 *>(st + offA[N2U + 1] + ro);
-          yb0 = *reinterpret_cast<const double2 *>(st + offB0[N2U + 1] + ro);
-        }
+        const unsigned ro = sb + (unsigned)(step * 64 + kk * 16);
+        const double2 wv = gw_lds2(ro + (unsigned)off_dinv);
 #pragma unroll
-        for (int c0 = 0; c0 < N2U; c0 += 2) {
-          double2 a[2], b0[2], b1[2];
+        for (int c0 = 0; c0 < NSEG; c0 += CH) {
+          double2 a[CH], b0[CH], b1[CH];
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (c0 + u < N2U) {
-              a[u] = *reinterpret_cast<const double2 *>(st + offA[c0 + u] + ro);
-              b0[u] = *reinterpret_cast<const double2 *>(st + offB0[c0 + u] + ro);
-              b1[u] = *reinterpret_cast<const double2 *>(st + offB1[c0 + u] + ro);
+          for (int u = 0; u < CH; u++) {
+            const int sg = c0 + u;
+            a[u] = b0[u] = b1[u] = make_double2(0.0, 0.0);
+            if (sg < N2U) {
+              a[u] = gw_lds2(ro + offA[sg]);
+              b0[u] = gw_lds2(ro + offB0[sg]);
+              b1[u] = gw_lds2(ro + offB1[sg]);
+            } else if (sg < NSEG) {
+              const int np = sg == N2U ? npx : npy;
+              if (np > 0) {
+                a[u] = gw_lds2(ro + offA[sg]);
+                b0[u] = gw_lds2(ro + offB0[sg]);
+              }
+              if (np > 1) b1[u] = gw_lds2(ro + offB1[sg]);
             }
           }
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (c0 + u < N2U) {
-              const double ax = a[u].x * wv.x, ay = a[u].y * wv.y;
-              dmma884(acc[c0 + u][0], ax, b0[u].x);
-              dmma884(acc[c0 + u][1], ax, b1[u].x);
-              dmma884(acc[c0 + u][0], ay, b0[u].y);
-              dmma884(acc[c0 + u][1], ay, b1[u].y);
+          for (int u = 0; u < CH; u++) {
+            if (c0 + u < NSEG) {
+              a[u].x *= wv.x;
+              a[u].y *= wv.y;
             }
           }
-        }
-        if (x2) {  // warp-uniform
-          const double ax = xa.x * wv.x, ay = xa.y * wv.y;
-          dmma884(acc[N2U][0], ax, xb0.x);
-          dmma884(acc[N2U][1], ax, xb1.x);
-          dmma884(acc[N2U][0], ay, xb0.y);
-          dmma884(acc[N2U][1], ay, xb1.y);
-        }
-        if (x1) {
-          dmma884(acc[N2U + 1][0], ya.x * wv.x, yb0.x);
-          dmma884(acc[N2U + 1][0], ya.y * wv.y, yb0.y);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {  // x halves of the chunk, then its y halves
+#pragma unroll
+            for (int u = 0; u < CH; u++) {
+              const int sg = c0 + u;
+              const double av = h == 0 ? a[u].x : a[u].y;
+              const double bv0 = h == 0 ? b0[u].x : b0[u].y;
+              const double bv1 = h == 0 ? b1[u].x : b1[u].y;
+              if (sg < N2U) {
+                dmma884(acc[sg][0], av, bv0);
+                dmma884(acc[sg][1], av, bv1);
+              } else if (sg < NSEG) {
+                const int np = sg == N2U ? npx : npy;
+                if (np > 0) dmma884(acc[sg][0], av, bv0);
+                if (np > 1) dmma884(acc[sg][1], av, bv1);
+              }
+            }
+          }
         }
       }
       __syncwarp();
@@ -473,16 +503,17 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + 1), 1)
       }
     }
   }
+  // the consumer threads alone from here on (the producers have returned)
   __threadfence();
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(counter, 1u);
     is_last = (t == gridDim.x - 1);
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
   if (is_last) {
     __threadfence();
-    for (int idx = threadIdx.x; idx < npairs_tot * 64; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < npairs_tot * 64; idx += NCT) {
       const double v =
           pcu_ordered_sum(partials + idx, (size_t)npairs_tot * 64, 0u, 1u, gridDim.x);
       const int p = idx >> 6, e = idx & 63;
