@@ -67,6 +67,7 @@ struct pcu_ctx {
   int max_blocks_per_sm = 16;  // occupancy cap of the streaming kernels
   int prefetch = -1;           // -1: same-iteration L2 prefetch; k > 0: k iterations ahead; 0 off
   int no_shm_big = 1;          // 0 (PCU_SHM_BIG=1): big_fetch adds the ranks' partials on the hosts
+  int no_reverse = 0;          // PCU_NO_REVERSE: every staged pass walks its tiles upwards
   int no_tma_tile = 0;         // PCU_NO_TMA_TILE: keep the SRC functors on the register-fed kernel
   int tma_groups = 0;          // PCU_TMA_GROUPS: cap on the consumer groups of tma_tile_kernel
   int tma_npw = 0;             // PCU_TMA_NPW: producer warps of tma_tile_kernel (default 2)
@@ -218,6 +219,7 @@ int pcu_launch_tile_tma(pcu_ctx *ctx, const F &f, long long n, const WDesc &w,
     if (chk.fixed[i]) nslots++;
   }
   plan.col_base = nslots;
+  plan.reverse = (F::REVERSE && !ctx->no_reverse) ? 1 : 0;
   nslots += chk.ncols;
   int npw = ctx->tma_npw > 0 ? ctx->tma_npw : 4;
   if (npw > PCU_TMA_NPW) npw = PCU_TMA_NPW;

@@ -494,7 +494,7 @@ static int launch_gram_tma_t(pcu_ctx *ctx, const ColTable &cols, int m,
   ctx->prof_begin("gram_kernel");
   gram_tma_kernel<NT, NWC, NCW, RPW><<<grid, PCU_GT_THREADS_T(NCW), smem, ctx->stream>>>(
       cols, m, Dinv, Cw, w, nslabs, slab_con, slab_skip, nstages, stage_bytes,
-      ctx->d_big_partials, ctx->d_counter, result, ld, d2, rhs_col);
+      ctx->d_big_partials, ctx->d_counter, result, ld, d2, rhs_col, ctx->no_reverse ? 0 : 1);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
@@ -551,7 +551,7 @@ static int launch_gram_wide_t(pcu_ctx *ctx, const ColTable &cols, int m, int nt,
   ctx->prof_begin("gram_kernel");
   gram_wide_kernel<N2U><<<grid, 32 * (PCU_GW_NCW + PCU_GW_NPW), smem, ctx->stream>>>(
       cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, ctx->d_big_partials,
-      ctx->d_counter, result, ld);
+      ctx->d_counter, result, ld, ctx->no_reverse ? 0 : 1);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());

@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
                     const int stage_bytes, double *__restrict__ partials,
                     unsigned int *counter, double *__restrict__ result,
                     const int ld, const double *__restrict__ d2,
-                    const int rhs_col) {
+                    const int rhs_col, const int reverse) {
+  // reverse: the slabs are taken from the last one down (the pass before this one,
+  // DiagRhsF, walks upwards and leaves its last rows in L2; see NoStreams::REVERSE)
   constexpr int NP = (NT * (NT + 1)) / 2;
   constexpr int ROWS = RPW * NCW, COLB = ROWS * 8 + 64;
   extern __shared__ __align__(128) unsigned char gt_smem[];
@@ -135,7 +137,8 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
       my_con += __shfl_xor_sync(0xffffffffu, my_con, o);
     }
     long long it = 0;
-    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+    for (long long sq = blockIdx.x; sq < nslabs; sq += gridDim.x) {
+      const long long slab = reverse ? nslabs - 1 - sq : sq;
       if (slab == slab_skip) continue;
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
@@ -178,7 +181,8 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
     const int rowb = (warp * RPW + 2 * kk) * 8;  // byte offset of the lane's first row
 
     long long it = 0;
-    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+    for (long long sq = blockIdx.x; sq < nslabs; sq += gridDim.x) {
+      const long long slab = reverse ? nslabs - 1 - sq : sq;
       if (slab == slab_skip) continue;
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
                      const long long nslabs, const int nstages,
                      const int stage_bytes, double *__restrict__ partials,
                      unsigned int *counter, double *__restrict__ result,
-                     const int ld) {
+                     const int ld, const int reverse) {
   constexpr int NSEG = N2U + 2;
   constexpr int CH = NSEG <= 8 ? (NSEG + 1) / 2 : 4;  // segments per chunk of a step
   constexpr int NCT = PCU_GW_NCW * 32;  // consumer threads
@@ -389,7 +393,8 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
     for (int c = c0; c <= m; c += 32 * PCU_GW_NPW) mine += col_bytes;
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     long long it = 0;
-    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
+    for (long long sq = blockIdx.x; sq < nslabs; sq += gridDim.x, it++) {
+      const long long slab = reverse ? nslabs - 1 - sq : sq;
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
       if (round > 0) gt_mbar_wait(gt_smem_u32(&gt_empty[s]), (round - 1) & 1);
@@ -428,7 +433,8 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
     // two optional ones (warp-uniform)
     const int npx = segs.np[warp][N2U], npy = segs.np[warp][N2U + 1];
     long long it = 0;
-    for (long long slab = blockIdx.x; slab < nslabs; slab += gridDim.x, it++) {
+    for (long long sq = blockIdx.x; sq < nslabs; sq += gridDim.x, it++) {
+      const long long slab = reverse ? nslabs - 1 - sq : sq;
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
       gt_mbar_wait(gt_smem_u32(&gt_full[s]), round & 1);

@@ -1040,6 +1040,7 @@ struct ConP2S {  // yw broadcast; the leader lane keeps the constraint's values 
 };
 struct Pass2SF : NoStreams {
   static constexpr int SRC = 1;
+  static constexpr int REVERSE = 1;  // after Pass2R1F (upwards)
   static constexpr int MINB = PCU_MINB_PASS2S;
   static constexpr int NS = 22, NX = 1, NM = 2, NB = 1, NB2 = 2;
   static constexpr int SMEM = NS * PCU_TILE_THREADS * 8;
@@ -1343,6 +1344,7 @@ struct TrialF : NoStreams {
 template <int STATS>
 struct Update1FT : NoStreams {
   static constexpr int SRC = 1;
+  static constexpr int REVERSE = 1;  // after TrialF and the objective callback (upwards)
   static constexpr int NS = STATS ? 3 : 0, NX = STATS ? 4 : 0, NM = STATS ? 2 : 0,
                        NB = STATS ? 1 : 0;
   enum { S_X, S_PX, S_LB, S_UB, S_ZL, S_PZL, S_ZU, S_PZU, S_G, S_A0 };
@@ -1521,6 +1523,7 @@ typedef Update1FT<0> Update1F;
 template <int RX, int TR = 1024>
 struct Update2FT : NoStreams {
   static constexpr int SRC = 1;
+  static constexpr int REVERSE = 1;  // after the gradient callbacks (upwards); DiagRhsF follows upwards
   static constexpr int NS = 3, NX = RX ? 1 : 0, NM = 0, NB = 0;
   enum { S_Y, S_G, S_PX, S_ZL, S_ZU, S_A0 };
   static constexpr int NFIX = S_A0;  // fixed slots; the columns follow

@@ -387,6 +387,7 @@ pcu_ctx *pcu_ctx_create(int device) {
   if (const char *e = getenv("PCU_MAX_BLOCKS_PER_SM")) ctx->max_blocks_per_sm = atoi(e);
   if (const char *e = getenv("PCU_PREFETCH")) ctx->prefetch = atoi(e);
   if (getenv("PCU_NO_TMA_TILE")) ctx->no_tma_tile = 1;
+  if (getenv("PCU_NO_REVERSE")) ctx->no_reverse = 1;
   // measured at 2 GPUs: 6.81 ms / iteration against 6.77 with the in-stream NCCL
   // all-reduce -- no gain, so the host-side variant is opt-in
   ctx->no_shm_big = getenv("PCU_SHM_BIG") ? 0 : 1;

@@ -39,6 +39,7 @@ struct WidePlan {
   unsigned noff[24];
   unsigned scr_off;  // the teams' scratch, after the ring
   int m, nca;        // columns; the first nca of them also go into apz
+  int reverse;       // F::REVERSE: tiles from the last one down (see NoStreams::REVERSE)
 };
 
 // producer-side visitor: the functor's fixed N-streams (W-streams do not exist here)
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     int s = 0;
     unsigned round = 0;
     for (int kt = 0; kt < ntl; kt++) {
-      const long long tile = blockIdx.x + (long long)kt * gridDim.x;
+      const long long tq = blockIdx.x + (long long)kt * gridDim.x;
+      const long long tile = plan.reverse ? plan.ntiles - 1 - tq : tq;
       if (round > 0) tt_mbar_wait(empty0 + 8u * s, (round - 1) & 1);
       const unsigned full = full0 + 8u * s;
       if (lane == 0) tt_mbar_expect_tx(full, tx);
@@ -175,7 +177,8 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
   w0.coef0 = w0.coef_rest = w0.wconst = 0.0;
 
   for (int kt = team; kt < ntl; kt += PCU_WT_TEAMS) {
-    const long long tile = blockIdx.x + (long long)kt * gridDim.x;
+    const long long tq = blockIdx.x + (long long)kt * gridDim.x;
+    const long long tile = plan.reverse ? plan.ntiles - 1 - tq : tq;
     const int s = kt % S;
     tt_mbar_wait(full0 + 8u * s, (unsigned)(kt / S) & 1u);
     const unsigned base = smem0 + (unsigned)s * (unsigned)plan.stage_bytes;
@@ -358,6 +361,7 @@ int pcu_launch_wide(pcu_ctx *ctx, F f, long long n, const WDesc &w, RedBuf rb, i
   plan.scr_off = (unsigned)(plan.nstages * plan.stage_bytes);
   plan.m = m;
   plan.nca = apz ? f.nca : 0;
+  plan.reverse = (F::REVERSE && !ctx->no_reverse) ? 1 : 0;
   const size_t smem = (size_t)plan.nstages * plan.stage_bytes + scratch;
   static size_t attr_smem[PCU_MAX_DEVICES] = {0};
   const int dev = ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0;
