@@ -141,6 +141,8 @@ def kernel_words(name, N, W, c, q):
         "Pass2RF": (16 + m) * N + 30 * W,                   # pass 2 + refinement residual
         "Pass2R1F": (14 + m) * N + 30 * W,                  # ... + first half of the next solve
         "Pass2SF": (16 + m) * N + 20 * W,                   # accumulating pass 2 + step statistics (g)
+        "Pass2R1W": (15 + m) * N,                           # Pass2R1F on the column-split staged kernel (+ A p_z)
+        "Pass2SW": (17 + m) * N,                            # Pass2SF likewise
         "StatsF": 9 * N + 8 * W,
         "TrialF": 5 * N + 6 * W,
         "Update1F": (10 + c) * N + 15 * W,
