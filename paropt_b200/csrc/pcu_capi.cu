@@ -67,6 +67,13 @@ const OptEntry OPTIONS[] = {
     OPT_F(eisenstat_walker_gamma, 0.0, 1.0),
     OPT_F(max_gmres_rtol, 0.0, 1.0),
     OPT_F(gmres_atol, 0.0, 1.0),
+    // The choices are the reference's own (IP.cpp:694-707), with the reference's own
+    // behaviour: ParOptInteriorPoint's constructor builds a quasi-Newton object for "bfgs"
+    // and "sr1" only ("scaled_bfgs" leaves qn = NULL exactly like "none", IP.cpp:262-277:
+    // ParOptScaledQuasiNewton is created by ParOptOptimizer and handed in through
+    // setQuasiNewton), and ParOptLBFGS / ParOptLSR1 test the diagonal type against
+    // PAROPT_YTS_OVER_STS alone (QN.cpp:200, 256, 645): both "inner_*" values act as
+    // "yty_over_yts".  Same option dictionary, same optimizer behaviour.
     OPT_S(qn_type, "bfgs|scaled_bfgs|sr1|none"),
     OPT_S(qn_update_type, "skip_negative_curvature|damped_update"),
     OPT_S(qn_diag_type,
