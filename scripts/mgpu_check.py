@@ -79,6 +79,37 @@ for label, nbig in (("C3_big", 8 * 5003 * ctx.size), ("C2_big", 50001 * ctx.size
     n2, w2, f2 = compare_histories(fused, host, max_iters=12, cfg=cfg_big)
     verdict["cases"][label] = {"compared": min(n1, n2), "first_violation": f1 or f2,
                                "worst": max(max(checked(w1).values()), max(checked(w2).values()))}
+# C4 (100 dense constraints + L-SR1: 120 columns): wide Gram kernel and the column-split
+# staged pass 2 (wide_tile_kernel: whole 64-row tiles per rank) against the plain path;
+# 9 iterations -- as far as an L-SR1 history is reproducible (tests/test_oracle_golden.py)
+cfg_big = configs.get("C4", 625 * 64 * ctx.size)
+
+
+def run_c4(plain):
+    for k in SWITCHES:
+        if plain:
+            os.environ[k] = "1"
+        else:
+            os.environ.pop(k, None)
+    ctx.set_param("no_tma_tile", 1 if plain else 0)
+    ctx.set_param("tma_min_tiles", 1)
+    ctx.set_param("tma_grid", 7)
+    prob = problem_from_config(ctx, cfg_big)
+    ip = InteriorPoint(prob, dict(cfg_big["options"], history_level=2, max_major_iters=9))
+    ip.optimize()
+    hist = ip.history()
+    ip.free()
+    prob.free()
+    for k in SWITCHES:
+        os.environ.pop(k, None)
+    return hist
+
+
+fused = run_c4(False)
+plain = run_c4(True)
+n1, w1, f1 = compare_histories(plain, fused, max_iters=8, cfg=cfg_big)
+verdict["cases"]["C4_big_wide"] = {"compared": n1, "first_violation": f1,
+                                   "worst": max(checked(w1).values())}
 if ctx.rank == 0:
     print("MGPU_VERDICT " + json.dumps(verdict))
 ctx.close()
