@@ -26,6 +26,7 @@
 #pragma once
 
 #include "pcu_common.cuh"
+#include "pcu_ctx.cuh"
 
 #define PCU_WT_ROWS 64
 #define PCU_WT_TEAMS 2
@@ -353,7 +354,9 @@ int pcu_launch_wide(pcu_ctx *ctx, F f, long long n, const WDesc &w, RedBuf rb, i
   if (!chk.aligned || chk.copies > 64 * plan.npw) return -1;
   plan.stage_bytes = nslots * ROWS * 8;
   const int scratch = PCU_WT_TEAMS * PCU_WT_TEAMW * (DOTS ? 3 : 2) * ROWS * 8;
-  const int budget = 226 * 1024 - (DOTS ? PCU_WT_TEAMS * PCU_MAX_COLS * 8 : 0);
+  // 227 KB per CTA less the static shared memory (mbarriers, the reduction's staging
+  // rows, the teams' dot products)
+  const int budget = PCU_TMA_SMEM_BUDGET - (DOTS ? PCU_WT_TEAMS * PCU_MAX_COLS * 8 : 0);
   int fit = (budget - scratch) / plan.stage_bytes;
   if (fit > PCU_TMA_MAXSTAGES) fit = PCU_TMA_MAXSTAGES;
   if (fit < 2) return -1;

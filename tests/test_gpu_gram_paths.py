@@ -74,6 +74,19 @@ def test_fused_paths_match_oracle_and_plain_path(ctx, name, n, iters):
         assert cnt == iters - 1 and first is None, (label, first, worst)
 
 
+def test_widest_column_set_matches_plain_path(ctx):
+    """139 dense constraints + L-SR1 m = 20 + the right-hand side = PCU_MAX_COLS columns: the wide Gram kernel
+    with 20 tile rows (eight common segments per warp), `Pass2SF` on the column-split
+    staged kernel with 159 columns; the refinement half-solve's fused multi-dot stops at
+    132 columns, so `Pass2RF` + `Pass1F` + multi-dot run register-fed."""
+    from paropt_b200.api import problem_from_config
+    cfg = configs.get("C4", 625 * 64, ncon=139)
+    fused = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 9, False)
+    plain = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 9, True)
+    cnt, worst, first = compare_histories(plain, fused, max_iters=8, cfg=cfg)
+    assert cnt == 8 and first is None, (first, worst)
+
+
 def test_weighting_blocks_ending_inside_a_slab(ctx):
     """Blocks of 8 cover only the first 24008 of 40024 variables: the Gram slab
     that straddles their end and the ragged tail go to the general kernel."""
