@@ -1,6 +1,6 @@
 // pcu_wide.cuh -- bulk-copy staged harness for the pass-2 kernels of the KKT solve
 // with MANY columns (33..160 constraint gradients + quasi-Newton vectors; C4: 120)
-// and no weighting constraints.
+// and no weighting constraints (any even number of rows).
 //
 // tma_tile_kernel gives every tile to a group of two warps and every element pair to
 // one lane, which then walks ALL columns: with 130+ streams only 64-row tiles fit the
@@ -16,7 +16,7 @@
 //            d1 slot of the stage in place, fills the `lin` slot, stores A p_z, and
 //            runs the functor's ordinary phases (ncols = 0) on the 64 rows
 //   phase F  (DOTS) every warp: its columns x the t1' the functor left in the stage
-//            -> running dot products in registers (<= 22 per lane)
+//            -> running dot products in registers (<= 27 per lane)
 // Two teams work on alternate tiles, so the single-warp phase E of one overlaps the
 // column phases of the other; the ring holds three 64-row stages (66-68 KB each at
 // C4) filled by four producer warps with one cp.async.bulk per stream.  Reference
@@ -31,10 +31,10 @@
 #define PCU_WT_ROWS 64
 #define PCU_WT_TEAMS 2
 #define PCU_WT_TEAMW 6   // warps per team
-#define PCU_WT_MAXJ 22   // dot-product columns per warp: m <= 132 for the DOTS variant
 
 struct WidePlan {
-  long long ntiles;
+  long long ntiles;  // tiles, the last one possibly partial
+  int tail;          // rows of the last tile when it is partial (even), else 0
   int nstages, stage_bytes, npw, col_base;
   unsigned long long nmap[3];
   unsigned noff[24];
@@ -86,7 +86,7 @@ __device__ __forceinline__ void wt_team_sync(int team) {
 // F: Pass2R1F<0, 1> (DOTS = 1: lin slot, t slot, dot products) or Pass2SF (DOTS = 0).
 // f.ncols == 0 and f.apz == nullptr; the columns are f.V.p[0 .. plan.m), their
 // coefficients f.alpha (and f.beta with DOTS).
-template <class F, int DOTS>
+template <class F, int DOTS, int MAXJ>
 __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     wide_tile_kernel(const F f, const RedBuf rb, const WidePlan plan, double *apz,
                      double *dot_partials, unsigned int *dot_counter, double *dot_result) {
@@ -134,17 +134,19 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     as.off0 = as.off1 = 0;
     f.tstreams(as);
     for (int j = 0; j < m; j++) as.n(F::NFIX + j, f.V.p[j]);
-    const unsigned nbytes = ROWS * 8;
-    unsigned tx = (unsigned)as.cnt * nbytes;
-    for (int o = 16; o > 0; o >>= 1) tx += __shfl_xor_sync(0xffffffffu, tx, o);
+    unsigned ncopies = (unsigned)as.cnt;
+    for (int o = 16; o > 0; o >>= 1) ncopies += __shfl_xor_sync(0xffffffffu, ncopies, o);
     int s = 0;
     unsigned round = 0;
     for (int kt = 0; kt < ntl; kt++) {
       const long long tq = blockIdx.x + (long long)kt * gridDim.x;
       const long long tile = plan.reverse ? plan.ntiles - 1 - tq : tq;
+      // the ragged last tile: only its rows are copied (an even number: 16-byte units)
+      const unsigned nbytes =
+          (plan.tail > 0 && tile == plan.ntiles - 1) ? (unsigned)plan.tail * 8u : ROWS * 8u;
       if (round > 0) tt_mbar_wait(empty0 + 8u * s, (round - 1) & 1);
       const unsigned full = full0 + 8u * s;
-      if (lane == 0) tt_mbar_expect_tx(full, tx);
+      if (lane == 0) tt_mbar_expect_tx(full, ncopies * nbytes);
       __syncwarp();
       const unsigned base = smem0 + (unsigned)s * (unsigned)plan.stage_bytes;
       if (as.cnt > 0) tt_bulk_g2s(base + as.off0, as.p0 + tile * ROWS, nbytes, full);
@@ -165,9 +167,9 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
   const int team = cw / TEAMW, tw = cw % TEAMW;
   const unsigned scr = smem0 + plan.scr_off + (unsigned)team * (TEAMW * NV * ROWS * 8u);
   const unsigned col0 = (unsigned)plan.col_base * (ROWS * 8u);
-  double dacc[DOTS ? PCU_WT_MAXJ : 1];
+  double dacc[DOTS ? MAXJ : 1];
 #pragma unroll
-  for (int jj = 0; jj < (DOTS ? PCU_WT_MAXJ : 1); jj++) dacc[jj] = 0.0;
+  for (int jj = 0; jj < (DOTS ? MAXJ : 1); jj++) dacc[jj] = 0.0;
   WDesc w0;
   w0.nwcon = 0;
   w0.mode = 0;
@@ -181,6 +183,10 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
     const long long tq = blockIdx.x + (long long)kt * gridDim.x;
     const long long tile = plan.reverse ? plan.ntiles - 1 - tq : tq;
     const int s = kt % S;
+    // rows of this tile; lanes beyond them neither store nor reduce (their part of the
+    // stage holds leftovers of an earlier tile: finite numbers nobody looks at)
+    const int rows = (plan.tail > 0 && tile == plan.ntiles - 1) ? plan.tail : ROWS;
+    const bool live = 2 * lane < rows;
     tt_mbar_wait(full0 + 8u * s, (unsigned)(kt / S) & 1u);
     const unsigned base = smem0 + (unsigned)s * (unsigned)plan.stage_bytes;
     // ---- phase A: this warp's columns x 64 rows
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
       dv.y += sd.y;
       wt_sts2(ad, dv);
       if constexpr (DOTS) wt_sts2(base + plan.noff[F::S_LIN] + (unsigned)lane * 16u, sl);
-      if (apz) *reinterpret_cast<double2 *>(apz + tile * ROWS + 2 * lane) = sq;
+      if (apz && live) *reinterpret_cast<double2 *>(apz + tile * ROWS + 2 * lane) = sq;
       __syncwarp();
       SSrc<ROWS, F::NFIX> src;
       src.nb = base;
@@ -259,20 +265,22 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
 #pragma unroll
       for (int q = 0; q < F::NFIX; q++) src.off[q] = plan.noff[q];
       src.col0 = col0;
-      tile_pair(f, src, w0, src.row0 + 2 * lane, 0ll, 1, acc);
+      if (live) tile_pair(f, src, w0, src.row0 + 2 * lane, 0ll, 1, acc);
     }
     if constexpr (DOTS) {
       wt_team_sync(team);
       // ---- phase F: this warp's columns against the t1' of the rows
-      const double2 t = wt_lds2(base + plan.noff[F::S_T] + (unsigned)lane * 16u);
-      const unsigned cb = base + col0 + (unsigned)lane * 16u;
+      if (live) {  // (the rows beyond a ragged tile may hold anything, NaNs included)
+        const double2 t = wt_lds2(base + plan.noff[F::S_T] + (unsigned)lane * 16u);
+        const unsigned cb = base + col0 + (unsigned)lane * 16u;
 #pragma unroll
-      for (int jj = 0; jj < PCU_WT_MAXJ; jj++) {
-        const int j = tw + TEAMW * jj;
-        if (j < m) {
-          const double2 c = wt_lds2(cb + (unsigned)j * (ROWS * 8u));
-          dacc[jj] = fma(t.x, c.x, dacc[jj]);
-          dacc[jj] = fma(t.y, c.y, dacc[jj]);
+        for (int jj = 0; jj < MAXJ; jj++) {
+          const int j = tw + TEAMW * jj;
+          if (j < m) {
+            const double2 c = wt_lds2(cb + (unsigned)j * (ROWS * 8u));
+            dacc[jj] = fma(t.x, c.x, dacc[jj]);
+            dacc[jj] = fma(t.y, c.y, dacc[jj]);
+          }
         }
       }
     }
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
   if constexpr (DOTS) {
     // warp totals -> team totals -> CTA partials -> the last CTA adds them in order
 #pragma unroll
-    for (int jj = 0; jj < PCU_WT_MAXJ; jj++) {
+    for (int jj = 0; jj < MAXJ; jj++) {
       const int j = tw + TEAMW * jj;
       double v = dacc[jj];
       for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
@@ -319,15 +327,26 @@ __global__ void __launch_bounds__(PCU_TMA_MAXWARPS * 32, 1)
 // Host side.  Returns -1 when the launch does not qualify (the caller then takes the
 // register-fed kernels), 1 on error.  On success with DOTS the m dot products are in
 // ctx->d_big (ctx->big_fetch(m, ...)).
+template <class F, int DOTS, int MAXJ>
+int pcu_launch_wide_t(pcu_ctx *ctx, F f, long long n, const WDesc &w, RedBuf rb, int m);
+
+// MAXJ: dot products per lane -- 22 up to 132 columns (C4: 120), 27 up to PCU_MAX_COLS
 template <class F, int DOTS>
 int pcu_launch_wide(pcu_ctx *ctx, F f, long long n, const WDesc &w, RedBuf rb, int m) {
+  if (DOTS && m > PCU_WT_TEAMW * 22) return pcu_launch_wide_t<F, DOTS, DOTS ? 27 : 1>(ctx, f, n, w, rb, m);
+  return pcu_launch_wide_t<F, DOTS, DOTS ? 22 : 1>(ctx, f, n, w, rb, m);
+}
+
+template <class F, int DOTS, int MAXJ>
+int pcu_launch_wide_t(pcu_ctx *ctx, F f, long long n, const WDesc &w, RedBuf rb, int m) {
   constexpr int ROWS = PCU_WT_ROWS;
   static_assert(F::NFIX <= 24, "fixed slots");
   if (ctx->no_tma_tile || w.nwcon > 0 || m < 1 || m > PCU_MAX_COLS) return -1;
-  if (DOTS && m > PCU_WT_TEAMW * PCU_WT_MAXJ) return -1;
-  if (n % ROWS != 0) return -1;  // whole tiles only
+  if (DOTS && m > PCU_WT_TEAMW * MAXJ) return -1;
+  if (n & 1) return -1;  // the ragged last tile is copied in 16-byte units
   WidePlan plan;
-  plan.ntiles = n / ROWS;
+  plan.tail = (int)(n % ROWS);
+  plan.ntiles = n / ROWS + (plan.tail > 0 ? 1 : 0);
   if (plan.ntiles < (ctx->tma_min_tiles > 0 ? (long long)ctx->tma_min_tiles
                                             : (long long)ctx->num_sms * 8))
     return -1;
@@ -369,14 +388,14 @@ int pcu_launch_wide(pcu_ctx *ctx, F f, long long n, const WDesc &w, RedBuf rb, i
   static size_t attr_smem[PCU_MAX_DEVICES] = {0};
   const int dev = ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0;
   if (attr_smem[dev] < smem || ctx->device >= PCU_MAX_DEVICES) {
-    PCU_CUDA_OK(cudaFuncSetAttribute(wide_tile_kernel<F, DOTS>,
+    PCU_CUDA_OK(cudaFuncSetAttribute(wide_tile_kernel<F, DOTS, MAXJ>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[dev] = smem;
   }
   const int grid = ctx->tma_grid > 0 && ctx->tma_grid < ctx->num_sms ? ctx->tma_grid : ctx->num_sms;
   if (DOTS && ctx->big_reserve((size_t)m, (size_t)grid * m)) return 1;
   ctx->prof_begin(DOTS ? "Pass2R1W" : "Pass2SW");
-  wide_tile_kernel<F, DOTS><<<grid, PCU_TMA_MAXWARPS * 32, smem, ctx->stream>>>(
+  wide_tile_kernel<F, DOTS, MAXJ><<<grid, PCU_TMA_MAXWARPS * 32, smem, ctx->stream>>>(
       f, rb, plan, apz, ctx->d_big_partials, ctx->d_counter, ctx->d_big);
   ctx->prof_end();
   ctx->launches++;

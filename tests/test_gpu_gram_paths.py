@@ -54,11 +54,12 @@ def run(ctx, make_problem, options, iters, plain):
 
 # C4 (100 dense constraints + L-SR1: 120 columns) exercises the wide tile-pair
 # Gram kernel; its L-SR1 history is only reproducible for 9 iterations (see
-# tests/test_oracle_golden.py).  With n a multiple of 64 its two pass-2 kernels run on
-# the column-split staged harness (wide_tile_kernel, pcu_wide.cuh).
+# tests/test_oracle_golden.py).  With an even n its two pass-2 kernels run on the
+# column-split staged harness (wide_tile_kernel, pcu_wide.cuh; 40008: a ragged last tile
+# of 8 rows), with an odd n (40009) on the register-fed kernels.
 @pytest.mark.parametrize("name,n,iters", [("C3", 8 * 5003, 14), ("C2", 50001, 14),
                                           ("C3", 8 * 4096, 14), ("C4", 40008, 9),
-                                          ("C4", 625 * 64, 9)])
+                                          ("C4", 625 * 64, 9), ("C4", 40009, 9)])
 def test_fused_paths_match_oracle_and_plain_path(ctx, name, n, iters):
     from oracle.ip_oracle import InteriorPointOracle
     from oracle.problems import SepQuad
@@ -75,10 +76,10 @@ def test_fused_paths_match_oracle_and_plain_path(ctx, name, n, iters):
 
 
 def test_widest_column_set_matches_plain_path(ctx):
-    """139 dense constraints + L-SR1 m = 20 + the right-hand side = PCU_MAX_COLS columns: the wide Gram kernel
-    with 20 tile rows (eight common segments per warp), `Pass2SF` on the column-split
-    staged kernel with 159 columns; the refinement half-solve's fused multi-dot stops at
-    132 columns, so `Pass2RF` + `Pass1F` + multi-dot run register-fed."""
+    """139 dense constraints + L-SR1 m = 20 + the right-hand side = PCU_MAX_COLS columns: the wide
+    Gram kernel with 20 tile rows (eight common segments per warp) and both pass-2 kernels
+    on the column-split staged kernel with 159 columns (27 running dot products per lane in
+    the refinement half-solve)."""
     from paropt_b200.api import problem_from_config
     cfg = configs.get("C4", 625 * 64, ncon=139)
     fused = run(ctx, lambda: problem_from_config(ctx, cfg), cfg["options"], 9, False)
