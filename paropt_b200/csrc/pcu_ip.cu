@@ -12,6 +12,9 @@
 
 #include "pcu_ip.cuh"
 
+int pcu_sr1_pairs_enqueue(pcu_ctx *ctx, const double *s, const double *const *S,
+                          const double *const *Y, double *const *Z, int np, double b0,
+                          long long n);
 int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
                      int ncols, long long n, int dst_off);
 int pcu_gram_enqueue(pcu_ctx *ctx, const ColTable &cols, int m,
@@ -100,6 +103,7 @@ int QuasiNewton::init(pcu_ctx *c, int nvars, int kind, int m) {
   n = nvars;
   type = kind;
   msub_max = m;
+  fused_sr1 = getenv("PCU_NO_FUSED_SR1") ? 0 : 1;
   for (int i = 0; i < m; i++) {
     S.push_back(pcu_vec_create(ctx, n));
     Y.push_back(pcu_vec_create(ctx, n));
@@ -311,7 +315,9 @@ int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
       // dots of s with stored Y are unchanged; the new pair uses y_update
     }
   } else {
-    if (stored_dots()) return 1;
+    // L-SR1: the dots with the stored pairs are taken by the sweep that rebuilds Z
+    // (after the new pair is in place); b0 needs the two scalars only
+    if (fused_sr1 == 0 && stored_dots()) return 1;
     b0 = (yTs > eps * yTy) ? yTy / yTs : 1.0;  // QN.cpp:645-649
   }
 
@@ -336,6 +342,30 @@ int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
     return 0;
   }
   const int last = msub - 1;
+  if (type == 1 && fused_sr1) {
+    // one sweep over the pairs as they are stored now: Z_i = Y_i - b0 S_i (QN.cpp:730-735)
+    // together with s . S_i and s . Y_i (s = S[last], the pair just stored)
+    std::vector<const double *> Sp(msub), Yp(msub);
+    std::vector<double *> Zp(msub);
+    for (int i = 0; i < msub; i++) {
+      pcu_vec_ready(S[i]);
+      pcu_vec_ready(Y[i]);
+      pcu_vec_ready(Zs[i]);
+      Sp[i] = S[i]->d;
+      Yp[i] = Y[i]->d;
+      Zp[i] = Zs[i]->d;
+    }
+    if (pcu_sr1_pairs_enqueue(ctx, S[last]->d, Sp.data(), Yp.data(), Zp.data(), msub, b0, n))
+      return 1;
+    std::vector<double> out(2 * (size_t)msub);
+    if (ctx->big_fetch(2 * (size_t)msub, out.data())) return 1;
+    sS.assign(msub + 1, 0.0);
+    sY.assign(msub + 1, 0.0);
+    for (int i = 0; i < last; i++) {
+      sS[i + shift] = out[i];
+      sY[i + shift] = out[msub + i];
+    }
+  }
   for (int i = 0; i < last; i++) {  // QN.cpp:307-321
     B[last + (size_t)m * i] = sS[i + shift];
     B[i + (size_t)m * last] = sS[i + shift];
@@ -344,7 +374,7 @@ int QuasiNewton::update(pcu_vec *s, pcu_vec *y, double yTy, double yTs,
   B[last + (size_t)m * last] = sTs;
   D[last] = yTs;
   mat_update();
-  if (type == 1) {  // Z_i = Y_i - b0 S_i  (QN.cpp:730-735)
+  if (type == 1 && !fused_sr1) {  // Z_i = Y_i - b0 S_i  (QN.cpp:730-735)
     for (int i = 0; i < msub; i++) {
       LinCombF f;
       f.x = Y[i]->d;

@@ -87,6 +87,7 @@ struct QuasiNewton {
   int msub_max = 0, msub = 0;
   int damped = 0;
   int diag_yts_over_sts = 0;
+  int fused_sr1 = 1;  // L-SR1: Z rebuild + stored-pair dots in one sweep (PCU_NO_FUSED_SR1: off)
   double b0 = 1.0;
   double eps = 1e-12;
   std::vector<pcu_vec *> S, Y, Zs;

@@ -734,6 +734,124 @@ int pcu_mdot_enqueue(pcu_ctx *ctx, const double *x, const ColTable &cols,
   return 0;
 }
 
+// L-SR1 update in one sweep over the stored pairs (QN.cpp:636-747): for pair i
+//   Z_i = Y_i - b0 S_i                    (QN.cpp:730-735: the whole Z is rebuilt, b0 is new)
+//   s . S_i,  s . Y_i                     (QN.cpp:668-688: the new rows of B and L)
+// G pairs per launch: (1 + 3 G) N words instead of the (2 + 3) N per pair of a multi-dot
+// over [S | Y] followed by one linear combination per column.  s = the newest stored S.
+struct PairTable {
+  const double *S[4];
+  const double *Y[4];
+  double *Z[4];
+};
+template <int G>
+__global__ void __launch_bounds__(PCU_THREADS)
+    sr1_pairs_kernel(const double *__restrict__ s, PairTable t, int npairs, double b0,
+                     long long n, double *partials, unsigned int *counter, double *result,
+                     int dst_s, int dst_y) {
+  double acc[2 * G];
+#pragma unroll
+  for (int k = 0; k < 2 * G; k++) acc[k] = 0.0;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long nvec = n / 2;
+  for (long long v = tid; v < nvec; v += nthreads) {
+    const double2 sv = *reinterpret_cast<const double2 *>(s + 2 * v);
+    double2 a[G], b[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (g < npairs) {
+        a[g] = *reinterpret_cast<const double2 *>(t.S[g] + 2 * v);
+        b[g] = *reinterpret_cast<const double2 *>(t.Y[g] + 2 * v);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (g < npairs) {
+        double2 z;
+        z.x = fma(-b0, a[g].x, b[g].x);
+        z.y = fma(-b0, a[g].y, b[g].y);
+        *reinterpret_cast<double2 *>(t.Z[g] + 2 * v) = z;
+        acc[2 * g] = fma(sv.x, a[g].x, acc[2 * g]);
+        acc[2 * g] = fma(sv.y, a[g].y, acc[2 * g]);
+        acc[2 * g + 1] = fma(sv.x, b[g].x, acc[2 * g + 1]);
+        acc[2 * g + 1] = fma(sv.y, b[g].y, acc[2 * g + 1]);
+      }
+    }
+  }
+  if ((n & 1) && tid == 0) {
+    const double sv = s[n - 1];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (g < npairs) {
+        const double a = t.S[g][n - 1], b = t.Y[g][n - 1];
+        t.Z[g][n - 1] = fma(-b0, a, b);
+        acc[2 * g] = fma(sv, a, acc[2 * g]);
+        acc[2 * g + 1] = fma(sv, b, acc[2 * g + 1]);
+      }
+    }
+  }
+  constexpr int KC = 2 * G;
+  __shared__ double sm[PCU_THREADS / 32][KC];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KC; k++) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
+    if (lane == 0) sm[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < KC) {
+    double v = 0.0;
+    for (int w = 0; w < PCU_THREADS / 32; w++) v += sm[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * KC + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int c = atomicAdd(counter, 1u);
+    is_last = (c == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int k = warp; k < 2 * npairs; k += PCU_THREADS / 32) {
+      double v = pcu_ordered_sum(partials + k, (size_t)KC, (unsigned)lane, 32u, gridDim.x);
+      for (int o = 16; o > 0; o >>= 1) v += shfl_down_d(v, o);
+      if (lane == 0) result[((k & 1) ? dst_y : dst_s) + (k >> 1)] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// Enqueue the sweep over `np` pairs: ctx->d_big[i] = s . S_i, ctx->d_big[np + i] = s . Y_i.
+int pcu_sr1_pairs_enqueue(pcu_ctx *ctx, const double *s, const double *const *S,
+                          const double *const *Y, double *const *Z, int np, double b0,
+                          long long n) {
+  constexpr int G = 4;
+  if (np <= 0) return 0;
+  if (ctx->big_reserve(2 * (size_t)np + 8, (size_t)PCU_MAX_BLOCKS * 2 * G)) return 1;
+  const int grid = pcu_grid_for(ctx, n);
+  for (int p0 = 0; p0 < np; p0 += G) {
+    PairTable t;
+    const int k = np - p0 < G ? np - p0 : G;
+    for (int g = 0; g < G; g++) {
+      const int i = p0 + (g < k ? g : 0);
+      t.S[g] = S[i];
+      t.Y[g] = Y[i];
+      t.Z[g] = Z[i];
+    }
+    ctx->prof_begin("sr1_pairs_kernel");
+    sr1_pairs_kernel<G><<<grid, PCU_THREADS, 0, ctx->stream>>>(
+        s, t, k, b0, n, ctx->d_big_partials, ctx->d_counter, ctx->d_big, p0, np + p0);
+    ctx->prof_end();
+    ctx->launches++;
+  }
+  PCU_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <class F>
 static int launch_plain(pcu_ctx *ctx, const F &f, long long n, RedBuf rb) {
   WDesc w;
