@@ -532,26 +532,27 @@ static int launch_gram_tma(pcu_ctx *ctx, const ColTable &cols, int m,
 }
 
 // Wide path: one launch for up to 160 columns, no weighting correction.
-template <int N2U>
+template <int N2U, int SIDE>
 static int launch_gram_wide_t(pcu_ctx *ctx, const ColTable &cols, int m, int nt,
                               const GramSegTable &segs, const double *Dinv, long long nslabs,
-                              int nstages, int stage_bytes, double *result, int ld) {
+                              int nstages, int stage_bytes, double *result, int ld,
+                              int side_off) {
   const int smem = nstages * stage_bytes;
   static int attr_smem_dev[PCU_MAX_DEVICES] = {0};  // per device (function attribute)
   int &attr_smem = attr_smem_dev[ctx->device >= 0 && ctx->device < PCU_MAX_DEVICES ? ctx->device : 0];
   if (smem > attr_smem || ctx->device >= PCU_MAX_DEVICES) {
-    PCU_CUDA_OK(cudaFuncSetAttribute(gram_wide_kernel<N2U>,
+    PCU_CUDA_OK(cudaFuncSetAttribute(gram_wide_kernel<N2U, SIDE>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
   int grid = ctx->num_sms;
   if (nslabs < grid) grid = (int)nslabs;
   const int npairs = nt * (nt + 1) / 2;
-  if (ctx->big_reserve(0, (size_t)grid * npairs * 64)) return 1;
+  if (ctx->big_reserve(0, (size_t)grid * ((size_t)npairs * 64 + (SIDE ? ld : 0)))) return 1;
   ctx->prof_begin("gram_kernel");
-  gram_wide_kernel<N2U><<<grid, 32 * (PCU_GW_NCW + PCU_GW_NPW), smem, ctx->stream>>>(
+  gram_wide_kernel<N2U, SIDE><<<grid, 32 * (PCU_GW_NCW + PCU_GW_NPW), smem, ctx->stream>>>(
       cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, ctx->d_big_partials,
-      ctx->d_counter, result, ld, ctx->no_reverse ? 0 : 1);
+      ctx->d_counter, result, ld, ctx->no_reverse ? 0 : 1, side_off);
   ctx->prof_end();
   ctx->launches++;
   PCU_CUDA_OK(cudaGetLastError());
@@ -561,7 +562,11 @@ static int launch_gram_wide_t(pcu_ctx *ctx, const ColTable &cols, int m, int nt,
 static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
                             const double *Dinv, long long n, double *result, int ld,
                             long long *rows_done) {
-  const int nt = (m + 7) / 8;
+  // a last column alone in its tile (m = 8 k + 1: C4's 120 columns + right-hand side) is
+  // taken as the side column of the tile rows' first segments instead of a tile row
+  static const bool no_side = getenv("PCU_NO_GRAM_SIDE") != nullptr;
+  const bool side = !no_side && m > 8 && (m % 8) == 1;
+  const int nt = side ? (m - 1) / 8 : (m + 7) / 8;
   // segments of the tile triangle: two-pair (ti, tj0), (ti, tj0 + 1) and, at the end of
   // the odd rows, single-pair ones
   std::vector<std::pair<int, int> > two, one;
@@ -571,34 +576,30 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
   if (n2u > PCU_GW_MAXN2U) return -1;
   GramSegTable segs;
   memset(&segs, 0, sizeof(segs));
-  int load[PCU_GW_NCW];
+  int load[PCU_GW_NCW] = {0};
   size_t at = 0;
-  for (int w = 0; w < PCU_GW_NCW; w++) {
-    for (int s = 0; s < n2u; s++, at++) {
-      segs.ti[w][s] = (unsigned char)two[at].first;
-      segs.tj[w][s] = (unsigned char)two[at].second;
-      segs.np[w][s] = 2;
-    }
-    load[w] = 2 * n2u;
-  }
-  // the remaining two-pair segments: one each to the first warps (slot n2u); the
-  // single-pair ones to the warps with the fewest pairs (slot n2u + 1)
-  for (int w = 0; at < two.size(); w++, at++) {
-    segs.ti[w][n2u] = (unsigned char)two[at].first;
-    segs.tj[w][n2u] = (unsigned char)two[at].second;
-    segs.np[w][n2u] = 2;
-    load[w] += 2;
-  }
-  if (one.size() > PCU_GW_NCW) return -1;
-  for (size_t k = 0; k < one.size(); k++) {
+  auto put = [&](int w, int slot, const std::pair<int, int> &sg, int np) {
+    segs.ti[w][slot] = (unsigned char)sg.first;
+    segs.tj[w][slot] = (unsigned char)sg.second;
+    segs.np[w][slot] = (unsigned char)np;
+    load[w] += np;
+  };
+  for (int w = 0; w < PCU_GW_NCW; w++)
+    for (int s = 0; s < n2u; s++, at++) put(w, s, two[at], 2);
+  // the remaining two-pair segments, then the single-pair ones: each to the warp with the
+  // fewest pairs that still has one of its two optional slots (n2u, n2u + 1) free
+  auto place = [&](const std::pair<int, int> &sg, int np) -> bool {
     int w = -1;
     for (int c = 0; c < PCU_GW_NCW; c++)
-      if (segs.np[c][n2u + 1] == 0 && (w < 0 || load[c] < load[w])) w = c;
-    segs.ti[w][n2u + 1] = (unsigned char)one[k].first;
-    segs.tj[w][n2u + 1] = (unsigned char)one[k].second;
-    segs.np[w][n2u + 1] = 1;
-    load[w] += 1;
-  }
+      if ((segs.np[c][n2u] == 0 || segs.np[c][n2u + 1] == 0) && (w < 0 || load[c] < load[w])) w = c;
+    if (w < 0) return false;
+    put(w, segs.np[w][n2u] == 0 ? n2u : n2u + 1, sg, np);
+    return true;
+  };
+  for (; at < two.size(); at++)
+    if (!place(two[at], 2)) return -1;
+  for (size_t k = 0; k < one.size(); k++)
+    if (!place(one[k], 1)) return -1;
   int stage_bytes = (m + 2) * PCU_GW_COLB;
   stage_bytes = (stage_bytes + 127) / 128 * 128;
   int nstages = (208 * 1024) / stage_bytes;
@@ -606,8 +607,13 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
   if (nstages < 2) return -1;
   const long long nslabs = n / PCU_GW_ROWS;
   *rows_done = nslabs * PCU_GW_ROWS;
-#define PCU_GW_CASE(K) \
-  case K: return launch_gram_wide_t<K>(ctx, cols, m, nt, segs, Dinv, nslabs, nstages, stage_bytes, result, ld);
+  const int side_off = side ? (m - 1) * PCU_GW_COLB : -1;
+#define PCU_GW_CASE(K)                                                                          \
+  case K:                                                                                       \
+    return side ? launch_gram_wide_t<K, 1>(ctx, cols, m, nt, segs, Dinv, nslabs, nstages,       \
+                                           stage_bytes, result, ld, side_off)                   \
+                : launch_gram_wide_t<K, 0>(ctx, cols, m, nt, segs, Dinv, nslabs, nstages,       \
+                                           stage_bytes, result, ld, side_off);
   switch (n2u) {
     PCU_GW_CASE(0)
     PCU_GW_CASE(1)

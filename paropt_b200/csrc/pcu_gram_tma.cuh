@@ -347,14 +347,20 @@ __device__ __forceinline__ double2 gw_lds2(unsigned a) {
   return v;
 }
 
-template <int N2U>
+template <int N2U, int SIDE>
 __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
     gram_wide_kernel(const ColTable cols, const int m, const int nt,
                      const GramSegTable segs, const double *__restrict__ Dinv,
                      const long long nslabs, const int nstages,
                      const int stage_bytes, double *__restrict__ partials,
                      unsigned int *counter, double *__restrict__ result,
-                     const int ld, const int reverse) {
+                     const int ld, const int reverse, const int side_off) {
+  // SIDE: column m - 1 (byte offset side_off in a stage) is alone in its tile -- C4: 120
+  // columns + the first solve's right-hand side.  As a 16th tile row it would cost 16 of
+  // 136 tile pairs for 121 useful numbers; instead the tiles cover the first m - 1 columns
+  // (nt = (m - 1) / 8) and row m - 1 of S is accumulated with DFMAs: warp w takes the
+  // columns of tile rows w and w + 12 (straight-line code: a tile row beyond nt reads the
+  // zero column), 3 loads + 8 fp64 operations per step next to ~80 DMMAs.
   constexpr int NSEG = N2U + 2;
   constexpr int CH = NSEG <= 8 ? (NSEG + 1) / 2 : 4;  // segments per chunk of a step
   constexpr int NCT = PCU_GW_NCW * 32;  // consumer threads
@@ -365,6 +371,7 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = lane >> 2, kk = lane & 3;
   const int npairs_tot = nt * (nt + 1) / 2;
+  const size_t pstride = (size_t)npairs_tot * 64 + (SIDE ? (size_t)ld : 0);  // per CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; s++) {
@@ -432,17 +439,31 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
     // pairs of slot s: 2 for the common segments (compile time), 0..2 / 0..1 for the
     // two optional ones (warp-uniform)
     const int npx = segs.np[warp][N2U], npy = segs.np[warp][N2U + 1];
+    double sacc[2] = {0.0, 0.0}, srr = 0.0;
+    const unsigned offS0 = colof(warp), offS1 = colof(warp + PCU_GW_NCW);
+    const bool own0 = warp < nt, own1 = warp + PCU_GW_NCW < nt;
     long long it = 0;
     for (long long sq = blockIdx.x; sq < nslabs; sq += gridDim.x, it++) {
-      const long long slab = reverse ? nslabs - 1 - sq : sq;
       const int s = (int)(it % nstages);
       const unsigned round = (unsigned)(it / nstages);
       gt_mbar_wait(gt_smem_u32(&gt_full[s]), round & 1);
       const unsigned sb = gt_smem_u32(gt_smem) + (unsigned)s * (unsigned)stage_bytes;
-#pragma unroll 1
+#pragma unroll 2
       for (int step = 0; step < PCU_GW_ROWS / 8; step++) {
         const unsigned ro = sb + (unsigned)(step * 64 + kk * 16);
         const double2 wv = gw_lds2(ro + (unsigned)off_dinv);
+        if constexpr (SIDE) {
+          const double2 rr = gw_lds2(ro + (unsigned)side_off);
+          const double2 c0v = gw_lds2(ro + (own0 ? offS0 : (unsigned)off_zero));
+          const double2 c1v = gw_lds2(ro + (own1 ? offS1 : (unsigned)off_zero));
+          const double rwx = rr.x * wv.x, rwy = rr.y * wv.y;
+          sacc[0] = fma(c0v.x, rwx, sacc[0]);
+          sacc[0] = fma(c0v.y, rwy, sacc[0]);
+          sacc[1] = fma(c1v.x, rwx, sacc[1]);
+          sacc[1] = fma(c1v.y, rwy, sacc[1]);
+          srr = fma(rr.x, rwx, srr);
+          srr = fma(rr.y, rwy, srr);
+        }
 #pragma unroll
         for (int c0 = 0; c0 < NSEG; c0 += CH) {
           double2 a[CH], b0[CH], b1[CH];
@@ -502,11 +523,28 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
         if (q < npv) {
           const int ti = segs.ti[warp][sg], tj = segs.tj[warp][sg] + q;
           const int p = ti * (ti + 1) / 2 + tj;
-          double *dst = partials + ((size_t)blockIdx.x * npairs_tot + p) * 64;
+          double *dst = partials + (size_t)blockIdx.x * pstride + (size_t)p * 64;
           dst[gi + 8 * (2 * kk)] = acc[sg][q][0];
           dst[gi + 8 * (2 * kk + 1)] = acc[sg][q][1];
         }
       }
+    }
+    if constexpr (SIDE) {
+      // the four lanes of a column hold two of a step's eight rows each
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        double v = sacc[q];
+        v += shfl_xor_d(v, 1);
+        v += shfl_xor_d(v, 2);
+        const int ti = warp + PCU_GW_NCW * q;
+        if (kk == 0 && ti < nt)
+          partials[(size_t)blockIdx.x * pstride + (size_t)npairs_tot * 64 + 8 * ti + gi] = v;
+      }
+      double v = srr;  // the side column with itself (warp 0, lanes 0..3)
+      v += shfl_xor_d(v, 1);
+      v += shfl_xor_d(v, 2);
+      if (warp == 0 && lane == 0)
+        partials[(size_t)blockIdx.x * pstride + (size_t)npairs_tot * 64 + (m - 1)] = v;
     }
   }
   // the consumer threads alone from here on (the producers have returned)
@@ -520,8 +558,7 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
   if (is_last) {
     __threadfence();
     for (int idx = threadIdx.x; idx < npairs_tot * 64; idx += NCT) {
-      const double v =
-          pcu_ordered_sum(partials + idx, (size_t)npairs_tot * 64, 0u, 1u, gridDim.x);
+      const double v = pcu_ordered_sum(partials + idx, pstride, 0u, 1u, gridDim.x);
       const int p = idx >> 6, e = idx & 63;
       int ti = 0, q = p;
       while (q > ti) {
@@ -532,6 +569,11 @@ __global__ void __launch_bounds__(32 * (PCU_GW_NCW + PCU_GW_NPW), 1)
       const int row = 8 * ti + (e & 7);
       const int cc = 8 * tj + (e >> 3);
       if (row < ld && cc < ld) result[(size_t)row + (size_t)ld * cc] = v;
+    }
+    if constexpr (SIDE) {  // row m - 1 of S
+      for (int c = threadIdx.x; c < m; c += NCT)
+        result[(size_t)(m - 1) + (size_t)ld * c] = pcu_ordered_sum(
+            partials + (size_t)npairs_tot * 64 + c, pstride, 0u, 1u, gridDim.x);
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
