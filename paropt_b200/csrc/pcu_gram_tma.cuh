@@ -329,8 +329,15 @@ __global__ void __launch_bounds__(PCU_GT_THREADS_T(NCW), 1)
 #define PCU_GW_COLB (PCU_GW_ROWS * 8 + 64)
 #define PCU_GW_MAXN2U 8
 #define PCU_GW_MAXSEG (PCU_GW_MAXN2U + 2)  // N2U common segments + 2 optional ones
+// setmaxnreg moves registers inside the CTA's own allocation (launch: 128 x 512): the
+// producers' 104 x 128 cover the consumers' 32 x 384.  (16 consumer warps + 4 producers
+// launch at 96 registers: the consumers could reach 112, not more -- a request beyond the
+// pool waits forever.)
 #define PCU_GW_CONS_REGS 160
 #define PCU_GW_PROD_REGS 24
+static_assert((128 - PCU_GW_PROD_REGS) * PCU_GW_NPW >= (PCU_GW_CONS_REGS - 128) * PCU_GW_NCW,
+              "setmaxnreg: the producers do not free what the consumers ask for");
+static_assert((PCU_GW_NCW + PCU_GW_NPW) * 32 == 512, "gram_wide_kernel is laid out for 16 warps");
 
 struct GramSegTable {
   // segment s of warp w: tile row, first tile column, pairs (1 or 2; 0 = none).
