@@ -467,6 +467,15 @@ int pcu_ip_merit_init_deriv(pcu_ip *ip, double max_x, double *merit,
 /* Gram blocks of the last setup: G (ncon x ncon, col-major, before LU) and
    Ce (q x q, col-major, before LU) -- IP.cpp:1932-1961 and 2646-2661.         */
 int pcu_ip_get_gram(pcu_ip *ip, double *G, double *Ce, int *q);
+/* Work partition of the wide Gram kernel (more than 40 columns: the A^T D^-1 A / Z^T D^-1 Z
+   contraction of setUpKKTDiagSystem / setUpKKTSystem, IP.cpp:1932-1961, 2646-2661, on the
+   FP64 tensor cores) for m columns, as host arrays -- inspection and CPU tests, no device
+   call: nt tile rows of 8 columns, n2u common two-pair segments per consumer warp, side = 1
+   when the last column is taken as a side column; ti / tj / np [warps][slots]: tile row,
+   first tile column and number of tile pairs (0 = empty slot) of every segment.  NULL
+   tables are skipped; returns non-zero when the wide kernel does not take this width.   */
+int pcu_gram_wide_plan(int m, int *nt, int *n2u, int *side, int *warps, int *slots,
+                       unsigned char *ti, unsigned char *tj, unsigned char *np);
 
 #ifdef __cplusplus
 }

@@ -225,6 +225,7 @@ SIGNATURES = {
     "pcu_ip_comp_step": (C.c_int, [VP, C.c_double, C.c_double, C.c_int, c_double_p]),
     "pcu_ip_merit_init_deriv": (C.c_int, [VP, C.c_double, c_double_p, c_double_p]),
     "pcu_ip_get_gram": (C.c_int, [VP, c_double_p, c_double_p, c_int_p]),
+    "pcu_gram_wide_plan": (C.c_int, [C.c_int] + [c_int_p] * 5 + [C.POINTER(C.c_ubyte)] * 3),
 }
 
 

@@ -559,14 +559,16 @@ static int launch_gram_wide_t(pcu_ctx *ctx, const ColTable &cols, int m, int nt,
   return 0;
 }
 
-static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
-                            const double *Dinv, long long n, double *result, int ld,
-                            long long *rows_done) {
+// Work partition of the wide kernel for m columns (host only): tile rows nt, common
+// two-pair segments per warp n2u, whether the last column is a side column, and the
+// segment table.  Returns -1 when the kernel does not take this width.
+static int gram_wide_deal(int m, int *nt_out, int *n2u_out, bool *side_out, GramSegTable *segs_out) {
   // a last column alone in its tile (m = 8 k + 1: C4's 120 columns + right-hand side) is
-  // taken as the side column of the tile rows' first segments instead of a tile row
+  // taken as the side column of two tile rows per warp instead of a tile row of its own
   static const bool no_side = getenv("PCU_NO_GRAM_SIDE") != nullptr;
   const bool side = !no_side && m > 8 && (m % 8) == 1;
   const int nt = side ? (m - 1) / 8 : (m + 7) / 8;
+  if (side && nt > 2 * PCU_GW_NCW) return -1;  // warp w takes tile rows w and w + NCW
   // segments of the tile triangle: two-pair (ti, tj0), (ti, tj0 + 1) and, at the end of
   // the odd rows, single-pair ones
   std::vector<std::pair<int, int> > two, one;
@@ -574,7 +576,7 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
     for (int tj = 0; tj <= ti; tj += 2) (tj + 1 <= ti ? two : one).push_back({ti, tj});
   const int n2u = (int)two.size() / PCU_GW_NCW;  // common two-pair segments per warp
   if (n2u > PCU_GW_MAXN2U) return -1;
-  GramSegTable segs;
+  GramSegTable &segs = *segs_out;
   memset(&segs, 0, sizeof(segs));
   int load[PCU_GW_NCW] = {0};
   size_t at = 0;
@@ -600,6 +602,36 @@ static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
     if (!place(two[at], 2)) return -1;
   for (size_t k = 0; k < one.size(); k++)
     if (!place(one[k], 1)) return -1;
+  *nt_out = nt;
+  *n2u_out = n2u;
+  *side_out = side;
+  return 0;
+}
+
+// The partition as plain arrays [warps][slots] (inspection / CPU tests; no device call).
+extern "C" int pcu_gram_wide_plan(int m, int *nt, int *n2u, int *side, int *warps, int *slots,
+                                  unsigned char *ti, unsigned char *tj, unsigned char *np) {
+  if (!nt || !n2u || !side || !warps || !slots) return 1;
+  *warps = PCU_GW_NCW;
+  *slots = PCU_GW_MAXSEG;
+  if (m < 1 || m > PCU_MAX_COLS) return 1;
+  GramSegTable segs;
+  bool sd = false;
+  if (gram_wide_deal(m, nt, n2u, &sd, &segs)) return 1;
+  *side = sd ? 1 : 0;
+  if (ti) memcpy(ti, segs.ti, sizeof(segs.ti));
+  if (tj) memcpy(tj, segs.tj, sizeof(segs.tj));
+  if (np) memcpy(np, segs.np, sizeof(segs.np));
+  return 0;
+}
+
+static int launch_gram_wide(pcu_ctx *ctx, const ColTable &cols, int m,
+                            const double *Dinv, long long n, double *result, int ld,
+                            long long *rows_done) {
+  int nt = 0, n2u = 0;
+  bool side = false;
+  GramSegTable segs;
+  if (gram_wide_deal(m, &nt, &n2u, &side, &segs)) return -1;
   int stage_bytes = (m + 2) * PCU_GW_COLB;
   stage_bytes = (stage_bytes + 127) / 128 * 128;
   int nstages = (208 * 1024) / stage_bytes;

@@ -33,6 +33,56 @@ def test_library_exports_every_declared_symbol():
     _lib.load()
 
 
+def test_wide_gram_partition_covers_the_tile_triangle_once():
+    """Host side of gram_wide_kernel (pcu_gram.cu, gram_wide_deal): for every width the
+    kernel takes, the segments dealt to the consumer warps cover each pair of 8-column tiles
+    (ti >= tj) exactly once, every warp holds n2u two-pair segments plus at most two optional
+    ones, the loads differ by at most two pairs, and a last column alone in its tile
+    (m = 8 k + 1) becomes a side column instead of a tile row (C4: m = 121 -> 15 tile rows,
+    120 tile pairs, ten per warp)."""
+    from paropt_b200 import _lib
+    lib = _lib.load()
+    I = ctypes.c_int
+    taken = 0
+    for m in range(41, 161):
+        nt, n2u, side, warps, slots = I(), I(), I(), I(), I()
+        probe = lib.pcu_gram_wide_plan(m, nt, n2u, side, warps, slots, None, None, None)
+        assert warps.value > 0 and slots.value > 0
+        if probe != 0:
+            continue
+        taken += 1
+        size = warps.value * slots.value
+        ti = (ctypes.c_ubyte * size)()
+        tj = (ctypes.c_ubyte * size)()
+        npairs = (ctypes.c_ubyte * size)()
+        assert lib.pcu_gram_wide_plan(m, nt, n2u, side, warps, slots, ti, tj, npairs) == 0
+        assert side.value == (1 if m % 8 == 1 else 0)
+        assert nt.value == ((m - 1) // 8 if side.value else (m + 7) // 8)
+        seen = set()
+        loads = []
+        for w in range(warps.value):
+            load = 0
+            for s_ in range(slots.value):
+                k = w * slots.value + s_
+                if npairs[k] == 0:
+                    continue
+                assert s_ < n2u.value + 2
+                if s_ < n2u.value:
+                    assert npairs[k] == 2
+                for q in range(npairs[k]):
+                    pair = (ti[k], tj[k] + q)
+                    assert pair[1] <= pair[0] < nt.value, (m, pair)
+                    assert pair not in seen, (m, pair)
+                    seen.add(pair)
+                load += npairs[k]
+            loads.append(load)
+        assert len(seen) == nt.value * (nt.value + 1) // 2, (m, len(seen))
+        assert max(loads) - min(loads) <= 2, (m, loads)
+        if m == 121:
+            assert nt.value == 15 and loads == [10] * warps.value
+    assert taken == 120  # every width from 41 to 160 columns
+
+
 def test_library_is_sm100a_only():
     from paropt_b200 import build
     out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True).stdout
